@@ -1,0 +1,61 @@
+"""Python wrappers over the raw kernel entry points of libcddpm_b200 (one function per C symbol).
+
+These exist for the parity tests and for host code that needs a single kernel; the UNet forward itself runs inside
+the C++ engine (cddpm/engine.py -> cddpm_unet_*).  All tensors are CUDA tensors; activations are NHWC 16-bit.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import check, current_stream, fmt_of, int_array, lib, ptr, ptr_array
+
+
+def pack_conv_weight(weight: torch.Tensor, splits: Sequence[int], dtype=torch.bfloat16) -> torch.Tensor:
+    """OIHW fp32 weight -> packed [Cout, Ktot] 16-bit matrix; `splits` = input-channel count of each A source."""
+    assert weight.is_cuda and weight.dtype == torch.float32 and weight.dim() == 4
+    cout, cin, kh, kw = weight.shape
+    assert kh == kw and sum(splits) == cin
+    ktot = cin * kh * kw
+    out = torch.empty(cout, ktot, device=weight.device, dtype=dtype)
+    w = weight.contiguous()
+    cin_off = koff = 0
+    for c_s in splits:
+        check(
+            lib().cddpm_pack_conv_weight(ptr(w), cout, cin, kh, cin_off, c_s, ptr(out), ktot, koff, fmt_of(dtype),
+                                         current_stream()),
+            "cddpm_pack_conv_weight",
+        )
+        cin_off += c_s
+        koff += c_s * kh * kw
+    return out
+
+
+def conv_igemm(
+    srcs: Sequence[torch.Tensor],
+    taps: Sequence[int],
+    wpacked: torch.Tensor,
+    bias: Optional[torch.Tensor] = None,
+    residual: Optional[torch.Tensor] = None,
+    out_f32: bool = False,
+) -> torch.Tensor:
+    """sum_s conv(srcs[s]) + bias + residual; srcs are NHWC 16-bit, wpacked is [Cout, sum_s taps_s*C_s]."""
+    B, H, W, _ = srcs[0].shape
+    cout = wpacked.shape[0]
+    dtype = srcs[0].dtype
+    out = torch.empty(B, H, W, cout, device=srcs[0].device, dtype=torch.float32 if out_f32 else dtype)
+    check(
+        lib().cddpm_conv_igemm(
+            len(srcs),
+            ptr_array([ptr(s) for s in srcs]),
+            int_array([s.shape[3] for s in srcs]),
+            int_array(list(taps)),
+            B, H, W, cout,
+            ptr(wpacked), ptr(bias), ptr(residual), ptr(out),
+            1 if out_f32 else 0, fmt_of(dtype), current_stream(),
+        ),
+        "cddpm_conv_igemm",
+    )
+    return out

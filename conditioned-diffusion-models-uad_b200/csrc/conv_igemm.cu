@@ -1,0 +1,409 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a.  See conv_igemm.cuh for the contract.
+//
+// One persistent CTA per SM walks output tiles of 128 pixels x n_tile channels.
+//   warp 0  (one lane)  TMA producer: per K step, one 4-D box load per spatial box of the tile (the 3x3 tap is a
+//                       coordinate shift; out-of-image coordinates are zero-filled by TMA = the conv padding) plus
+//                       one 2-D load of the weight slab, into a ring of 128B-swizzled stages.
+//   warp 1  (one lane)  MMA issuer: 4 x tcgen05.mma (K=16 each) per stage into a TMEM accumulator; tcgen05.commit
+//                       releases the stage and, after the last K step, publishes the accumulator.
+//   warp 2              TMEM allocation / deallocation.
+//   warps 4-7           epilogue: tcgen05.ld the accumulator (one TMEM lane = one pixel per thread), add bias and
+//                       residual, round to the 16-bit activation type and store NHWC.  Two accumulator stages let
+//                       the epilogue of tile i overlap the main loop of tile i+1.
+#include "conv_igemm.cuh"
+
+#include <cuda_fp16.h>
+#include <string.h>
+
+#include "ptx.cuh"
+
+namespace cddpm {
+
+namespace {
+
+constexpr int kAStageBytes = kConvTileM * kConvBlockK * 2;  // 16 KiB
+constexpr int kSmemBudget = 227 * 1024;
+
+struct TapShift {
+  int dy, dx;
+};
+
+__device__ __forceinline__ uint32_t pack_16bit(float a, float b, int ab_format) {
+  if (ab_format == 1) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  } else {
+    __half2 v = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+}
+__device__ __forceinline__ float2 unpack_16bit(uint32_t u, int ab_format) {
+  if (ab_format == 1) {
+    return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+  } else {
+    return __half22float2(*reinterpret_cast<__half2*>(&u));
+  }
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvIgemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 128B-swizzled operand tiles need 1024-byte alignment.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_stages = p.num_stages;
+  const int b_stage_bytes = p.n_tile * kConvBlockK * 2;
+  const int stage_bytes = kAStageBytes + b_stage_bytes;
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + num_stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + num_stages;
+  uint64_t* tfull_bar = empty_bar + num_stages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  int num_ksteps = 0;
+  for (int s = 0; s < p.num_src; ++s) num_ksteps += p.src_taps[s] * (p.src_c[s] / kConvBlockK);
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int box_px = p.box_w * p.box_h;
+  const int boxes_per_img = p.tiles_w * p.tiles_h;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.num_src; ++s) tma_prefetch_desc(&p.tmap_a[s]);
+    tma_prefetch_desc(&p.tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < num_stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.num_n_tiles;
+        const int n_idx = tile % p.num_n_tiles;
+        int kstep = 0;
+        for (int s = 0; s < p.num_src; ++s) {
+          const int chunks = p.src_c[s] / kConvBlockK;
+          const int taps = p.src_taps[s];
+          for (int tap = 0; tap < taps; ++tap) {
+            const int dy = (taps == 9) ? (tap / 3 - 1) : 0;
+            const int dx = (taps == 9) ? (tap % 3 - 1) : 0;
+            for (int ch = 0; ch < chunks; ++ch, ++kstep) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* a_dst = smem + stage * stage_bytes;
+              uint8_t* b_dst = a_dst + kAStageBytes;
+              mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
+              for (int b = 0; b < p.boxes_per_tile; ++b) {
+                const int box = m_tile * p.boxes_per_tile + b;
+                const int n = box / boxes_per_img;
+                const int r = box - n * boxes_per_img;
+                const int ty = r / p.tiles_w;
+                const int tx = r - ty * p.tiles_w;
+                tma_load_4d(a_dst + b * box_px * 128, &p.tmap_a[s], &full_bar[stage], ch * kConvBlockK,
+                            tx * p.box_w + dx, ty * p.box_h + dy, n);
+              }
+              tma_load_2d(b_dst, &p.tmap_b, &full_bar[stage], kstep * kConvBlockK, n_idx * p.n_tile);
+              if (++stage == num_stages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = umma_idesc_f16(kConvTileM, static_cast<uint32_t>(p.n_tile), static_cast<uint32_t>(p.ab_format));
+    int stage = 0;
+    uint32_t phase = 0;
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+      const int acc = iter & 1;
+      const uint32_t acc_phase = (iter >> 1) & 1;
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * p.n_tile);
+      for (int kstep = 0; kstep < num_ksteps; ++kstep) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
+          const uint32_t b_addr = a_addr + kAStageBytes;
+#pragma unroll
+          for (int k = 0; k < kConvBlockK / 16; ++k) {
+            umma_f16_ss(tmem_d, umma_desc_k128(a_addr + k * 32), umma_desc_k128(b_addr + k * 32), idesc,
+                        (kstep | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kstep == num_ksteps - 1) umma_commit(&tfull_bar[acc]);
+        }
+        __syncwarp();
+        if (++stage == num_stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+    const int row = quarter * 32 + lane;
+    const int fmt = p.ab_format;
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+      const int acc = iter & 1;
+      const uint32_t acc_phase = (iter >> 1) & 1;
+      const int m_tile = tile / p.num_n_tiles;
+      const int n_idx = tile % p.num_n_tiles;
+
+      // pixel owned by this thread
+      const int b = row / box_px;
+      const int rr = row - b * box_px;
+      const int box = m_tile * p.boxes_per_tile + b;
+      const int n = box / boxes_per_img;
+      const int r = box - n * boxes_per_img;
+      const int ty = r / p.tiles_w;
+      const int tx = r - ty * p.tiles_w;
+      const int y = ty * p.box_h + rr / p.box_w;
+      const int x = tx * p.box_w + rr % p.box_w;
+      const bool valid = (box < p.total_boxes);
+      const size_t pix = (static_cast<size_t>(n) * p.H + y) * p.W + x;
+      const size_t off = pix * p.Cout + static_cast<size_t>(n_idx) * p.n_tile;
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * p.n_tile);
+      const int nchunks = p.n_tile / 32;
+      for (int c = 0; c < nchunks; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c * 32, v);
+        tmem_ld_wait();
+        if (c == nchunks - 1) {
+          // every TMEM read of this accumulator stage has completed: hand it back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&tempty_bar[acc]);
+        }
+        if (valid) {
+          const int co = n_idx * p.n_tile + c * 32;
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + co + j));
+              f[j] += bv.x;
+              f[j + 1] += bv.y;
+              f[j + 2] += bv.z;
+              f[j + 3] += bv.w;
+            }
+          }
+          if (p.residual != nullptr) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off + c * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 rv = __ldg(rp + q);
+              const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 t = unpack_16bit(w[e], fmt);
+                f[q * 8 + e * 2] += t.x;
+                f[q * 8 + e * 2 + 1] += t.y;
+              }
+            }
+          }
+          if (p.out_is_f32) {
+            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off + c * 32);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) op[q] = make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
+          } else {
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + off + c * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 o;
+              o.x = pack_16bit(f[q * 8 + 0], f[q * 8 + 1], fmt);
+              o.y = pack_16bit(f[q * 8 + 2], f[q * 8 + 3], fmt);
+              o.z = pack_16bit(f[q * 8 + 4], f[q * 8 + 5], fmt);
+              o.w = pack_16bit(f[q * 8 + 6], f[q * 8 + 7], fmt);
+              op[q] = o;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+  }
+}
+
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, int Cin_total, int ksize, int cin_off,
+                                        int C_s, uint16_t* __restrict__ out, int Ktot, int koff, int ab_format) {
+  const int taps = ksize * ksize;
+  const size_t total = static_cast<size_t>(Cout) * taps * C_s;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int ci = static_cast<int>(i % C_s);
+    const int tap = static_cast<int>((i / C_s) % taps);
+    const int co = static_cast<int>(i / (static_cast<size_t>(C_s) * taps));
+    const float v = w[(static_cast<size_t>(co) * Cin_total + cin_off + ci) * taps + tap];
+    uint16_t bits;
+    if (ab_format == 1) {
+      __nv_bfloat16 h = __float2bfloat16_rn(v);
+      bits = *reinterpret_cast<uint16_t*>(&h);
+    } else {
+      __half h = __float2half_rn(v);
+      bits = *reinterpret_cast<uint16_t*>(&h);
+    }
+    out[static_cast<size_t>(co) * Ktot + koff + tap * C_s + ci] = bits;
+  }
+}
+
+}  // namespace
+
+int conv_ktot(const ConvDesc& d) {
+  int k = 0;
+  for (int s = 0; s < d.num_src; ++s) k += d.src_taps[s] * d.src_c[s];
+  return k;
+}
+
+static bool pick_box(int H, int W, int* bw, int* bh) {
+  if (W % 16 == 0 && H % 8 == 0) {
+    *bw = 16;
+    *bh = 8;
+    return true;
+  }
+  if (W % 8 == 0 && H % 8 == 0) {
+    *bw = 8;
+    *bh = 8;
+    return true;
+  }
+  return false;
+}
+
+int conv_num_boxes(int B, int H, int W) {
+  int bw, bh;
+  if (!pick_box(H, W, &bw, &bh)) return 0;
+  return B * (W / bw) * (H / bh);
+}
+
+int build_conv_params(const ConvDesc& d, ConvIgemmParams* p) {
+  if (d.num_src < 1 || d.num_src > kConvMaxSrc) return fail(kInvalidArgument, "conv: num_src must be 1..3");
+  if (d.B < 1 || d.H < 1 || d.W < 1) return fail(kInvalidArgument, "conv: empty problem");
+  memset(p, 0, sizeof(*p));
+  int bw, bh;
+  if (!pick_box(d.H, d.W, &bw, &bh))
+    return fail(kUnsupported, "conv: H and W must be multiples of 8 for the tcgen05 implicit-GEMM path");
+  p->num_src = d.num_src;
+  p->B = d.B;
+  p->H = d.H;
+  p->W = d.W;
+  p->Cout = d.Cout;
+  p->box_w = bw;
+  p->box_h = bh;
+  p->boxes_per_tile = kConvTileM / (bw * bh);
+  p->tiles_w = d.W / bw;
+  p->tiles_h = d.H / bh;
+  p->total_boxes = d.B * p->tiles_w * p->tiles_h;
+  p->num_m_tiles = (p->total_boxes + p->boxes_per_tile - 1) / p->boxes_per_tile;
+  // N tile: the largest of 256/192/128/64/32 dividing Cout
+  int n_tile = 0;
+  const int cands[] = {256, 192, 128, 96, 64, 32};
+  for (int c : cands) {
+    if (d.Cout % c == 0) {
+      n_tile = c;
+      break;
+    }
+  }
+  if (n_tile == 0) return fail(kUnsupported, "conv: Cout must be a multiple of 32");
+  p->n_tile = n_tile;
+  p->num_n_tiles = d.Cout / n_tile;
+  int cols = 32;
+  while (cols < 2 * n_tile) cols *= 2;
+  p->tmem_cols = cols;
+  const int stage_bytes = kAStageBytes + n_tile * kConvBlockK * 2;
+  int stages = (kSmemBudget - 2048) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages < 2) return fail(kUnsupported, "conv: not enough shared memory for a 2-stage pipeline");
+  p->num_stages = stages;
+  p->ab_format = d.ab_format;
+  p->out_is_f32 = d.out_is_f32;
+  p->bias = d.bias;
+  p->residual = reinterpret_cast<const bf16*>(d.residual);
+  p->out = d.out;
+  p->gn_partial = d.gn_partial;
+  p->gn_cpg = d.gn_cpg;
+
+  int ktot = 0;
+  for (int s = 0; s < d.num_src; ++s) {
+    if (d.src_c[s] % kConvBlockK != 0) return fail(kUnsupported, "conv: source channels must be a multiple of 64");
+    if (d.src_taps[s] != 1 && d.src_taps[s] != 9) return fail(kInvalidArgument, "conv: taps must be 1 or 9");
+    p->src_c[s] = d.src_c[s];
+    p->src_taps[s] = d.src_taps[s];
+    const uint64_t C = static_cast<uint64_t>(d.src_c[s]);
+    const uint64_t dims[4] = {C, static_cast<uint64_t>(d.W), static_cast<uint64_t>(d.H), static_cast<uint64_t>(d.B)};
+    const uint64_t strides[3] = {C * 2, C * 2 * d.W, C * 2 * d.W * d.H};
+    const uint32_t box[4] = {static_cast<uint32_t>(kConvBlockK), static_cast<uint32_t>(bw), static_cast<uint32_t>(bh), 1u};
+    CDDPM_TRY(encode_tmap_16bit(&p->tmap_a[s], d.src[s], 4, dims, strides, box));
+    ktot += d.src_taps[s] * d.src_c[s];
+  }
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(ktot), static_cast<uint64_t>(d.Cout)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(ktot) * 2};
+    const uint32_t box[2] = {static_cast<uint32_t>(kConvBlockK), static_cast<uint32_t>(n_tile)};
+    CDDPM_TRY(encode_tmap_16bit(&p->tmap_b, d.wpacked, 2, dims, strides, box));
+  }
+  return kOk;
+}
+
+int launch_conv_igemm(const ConvIgemmParams& p, cudaStream_t stream, int max_ctas) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CDDPM_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    attr_set = true;
+  }
+  const int stage_bytes = kAStageBytes + p.n_tile * kConvBlockK * 2;
+  const int smem = p.num_stages * stage_bytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  int grid = device_sm_count();
+  if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
+  if (num_tiles < grid) grid = num_tiles;
+  conv_igemm_kernel<<<grid, kConvThreads, smem, stream>>>(p);
+  return check_launch("conv_igemm_kernel");
+}
+
+int launch_pack_conv_weight(const float* w_oihw, int Cout, int Cin_total, int ksize, int cin_off, int C_s,
+                            void* wpacked, int Ktot, int koff, int ab_format, cudaStream_t stream) {
+  const size_t total = static_cast<size_t>(Cout) * ksize * ksize * C_s;
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > 4096) blocks = 4096;
+  if (blocks < 1) blocks = 1;
+  pack_conv_weight_kernel<<<blocks, 256, 0, stream>>>(w_oihw, Cout, Cin_total, ksize, cin_off, C_s,
+                                                      reinterpret_cast<uint16_t*>(wpacked), Ktot, koff, ab_format);
+  return check_launch("pack_conv_weight_kernel");
+}
+
+}  // namespace cddpm
