@@ -1,0 +1,29 @@
+"""Stand-in for skimage.measure.{label, regionprops} built on scipy.ndimage (utils_eval.py:4,495-499).
+filled_area = voxel count of the component after hole filling inside its bounding box.  PARITY UNPINNED against
+real scikit-image (not installed here)."""
+import numpy as np
+from scipy import ndimage
+
+
+def label(vol, connectivity=None):
+    vol = np.asarray(vol)
+    conn = connectivity if connectivity is not None else vol.ndim
+    st = ndimage.generate_binary_structure(vol.ndim, conn)
+    lab, _ = ndimage.label(vol, structure=st)
+    return lab
+
+
+class _Region(dict):
+    pass
+
+
+def regionprops(lab):
+    out = []
+    objs = ndimage.find_objects(lab)
+    for i, sl in enumerate(objs):
+        if sl is None:
+            continue
+        region = lab[sl] == (i + 1)
+        filled = ndimage.binary_fill_holes(region)
+        out.append(_Region(label=i + 1, filled_area=int(filled.sum()), area=int(region.sum())))
+    return out
