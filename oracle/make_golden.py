@@ -1,0 +1,350 @@
+"""ORACLE (test infrastructure).  Generates tests/golden/*.npz by importing the UNMODIFIED reference live from
+/root/reference (only possible in the build container; the GPU box never sees /root/reference).
+
+    NUMBA_CACHE_DIR=/tmp/numba_cache PYTHONDONTWRITEBYTECODE=1 python oracle/make_golden.py
+
+Stub packages under oracle/stubs/ shadow the third-party imports that are not installed here.
+Weights come from oracle/weights.make_state_dict (deterministic, per-key seeded) and are loaded into the reference
+modules with strict=True — which also pins our statement of the state_dict key/shape layout.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/numba_cache")
+os.environ.setdefault("PYTHONDONTWRITEBYTECODE", "1")
+sys.dont_write_bytecode = True
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("CDDPM_REFERENCE", "/root/reference")
+sys.path[:0] = [os.path.join(ROOT, "oracle", "stubs"), REF, ROOT]
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from oracle import diffusion_port, resnet_port, unet_port  # noqa: E402
+from oracle.weights import make_state_dict, synthetic_slices, synthetic_volume  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+class Cfg(dict):
+    __getattr__ = dict.get
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+def base_cfg(**over):
+    c = Cfg(imageDim=[192, 192, 100], rescaleFactor=2, unet_dim=128, dim_mults=[1, 2, 2], condition=True,
+            backbone="Spark_Encoder_2D", version="resnet50", cond_dim=128, noisetype="simplex", noise_ensemble=True,
+            test_timesteps=500, lr=1e-4, resizedEvaluation=True, erodeBrainmask=True, medianFiltering=True,
+            saveOutputImages=False, evalSeg=True, threshold="auto", spatial_transformer=False,
+            pretrained_encoder=False)
+    c.update(over)
+    return c
+
+
+def save(name, **arrays):
+    path = os.path.join(GOLD, name)
+    np.savez_compressed(path, **{k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v))
+                                 for k, v in arrays.items()})
+    print(f"wrote {path} ({os.path.getsize(path) / 1024:.1f} KiB)")
+
+
+def ref_unet(spec: unet_port.UNetSpec, image=96):
+    from src.models.modules.OpenAI_Unet import UNetModel
+
+    m = UNetModel(image_size=(image, image), in_channels=spec.in_channels, model_channels=spec.model_channels,
+                  out_channels=spec.out_channels, num_res_blocks=spec.num_res_blocks,
+                  attention_resolutions=tuple(spec.attention_resolutions), dropout=0,
+                  channel_mult=list(spec.channel_mult), conv_resample=True, dims=2, num_classes=spec.num_classes,
+                  use_checkpoint=False, use_fp16=True, num_heads=1, num_head_channels=spec.num_head_channels,
+                  num_heads_upsample=-1, use_scale_shift_norm=True, resblock_updown=True,
+                  use_new_attention_order=True, use_spatial_transformer=False, transformer_depth=1)
+    shapes = unet_port.param_shapes(spec)
+    ref_shapes = [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
+    assert ref_shapes == shapes, "oracle.unet_port.param_shapes disagrees with the reference state_dict"
+    return m.eval(), shapes
+
+
+def golden_schedule():
+    from src.models.modules.cond_DDPM import GaussianDiffusion
+
+    d = GaussianDiffusion(torch.nn.Identity(), image_size=(96, 96), timesteps=1000, sampling_timesteps=1000,
+                          objective="pred_x0", channels=1, loss_type="l1", p2_loss_weight_gamma=0, cfg=base_cfg())
+    bufs = {k: v for k, v in d.state_dict().items()}
+    assert list(bufs.keys()) == diffusion_port.BUFFER_NAMES, list(bufs.keys())
+    mine = diffusion_port.schedule_buffers()
+    for k in bufs:
+        assert torch.equal(bufs[k], mine[k]), k
+    save("schedule.npz", **bufs)
+
+
+def golden_simplex():
+    from src.utils.generate_noise import gen_noise
+
+    from oracle.simplex_port import gen_noise_port
+
+    out = {}
+    for seed in (0, 7):
+        np.random.seed(seed)
+        ref = gen_noise(base_cfg(), (2, 1, 96, 96))
+        np.random.seed(seed)
+        mine = gen_noise_port((2, 1, 96, 96))
+        assert ref.dtype == torch.float16 and tuple(ref.shape) == (2, 1, 96, 96)
+        assert torch.equal(ref, mine), f"simplex port differs from the reference for seed {seed}"
+        out[f"field_seed{seed}"] = ref[0, 0]
+    save("simplex.npz", **out)
+
+
+def golden_unet():
+    # 1. the production geometry, conditioned and unconditioned, B=2 at 96x96
+    for tag, ncls in (("cond", 128), ("uncond", None)):
+        spec = unet_port.UNetSpec(num_classes=ncls)
+        m, shapes = ref_unet(spec)
+        sd = make_state_dict(shapes, seed=1)
+        m.load_state_dict(sd, strict=True)
+        x = synthetic_slices(2, 96, seed=3) * 2 - 1 + 0.3 * torch.randn(2, 1, 96, 96, generator=torch.Generator().manual_seed(4))
+        t = torch.tensor([499, 37])
+        cond = torch.randn(2, 128, generator=torch.Generator().manual_seed(5)) if ncls else None
+        with torch.no_grad():
+            y = m(x, t, cond=cond)
+            mine = unet_port.unet_forward(sd, spec, x, t, cond)
+        err = (y - mine).abs().max().item()
+        print(f"unet {tag}: |ref| max {y.abs().max().item():.3f}, port-vs-ref max abs {err:.3g}")
+        assert err < 1e-4
+        arrays = dict(x=x, t=t, y=y)
+        if cond is not None:
+            arrays["cond"] = cond
+        save(f"unet_{tag}_96.npz", **arrays)
+    with open(os.path.join(GOLD, "unet_cond_keys.json"), "w") as f:
+        json.dump([[k, list(s)] for k, s in unet_port.param_shapes(unet_port.UNetSpec())], f)
+    # 2. a small geometry for quick tests (64 base channels, 2 levels, 32x32, attention in the middle only)
+    spec = unet_port.UNetSpec(model_channels=64, channel_mult=(1, 2), num_res_blocks=1, num_classes=128)
+    m, shapes = ref_unet(spec, image=32)
+    sd = make_state_dict(shapes, seed=2)
+    m.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(3, 1, 32, 32, generator=g)
+    t = torch.tensor([0, 250, 999])
+    cond = torch.randn(3, 128, generator=g)
+    with torch.no_grad():
+        y = m(x, t, cond=cond)
+        mine = unet_port.unet_forward(sd, spec, x, t, cond)
+    assert (y - mine).abs().max().item() < 1e-4
+    save("unet_small_32.npz", x=x, t=t, cond=cond, y=y)
+
+
+def golden_encoder():
+    from src.models.modules.DDPM_encoder import get_encoder
+
+    cfg = base_cfg()
+    enc, out_features = get_encoder(cfg)
+    assert out_features == 128
+    shapes = resnet_port.param_shapes(128)
+    ref_shapes = [(k, tuple(v.shape)) for k, v in enc.state_dict().items()]
+    assert ref_shapes == [("encoder." + k, s) for k, s in shapes], "encoder state_dict layout mismatch"
+    sd = make_state_dict(shapes, seed=3)
+    enc.load_state_dict({"encoder." + k: v for k, v in sd.items()}, strict=True)
+    enc.eval()
+    x = synthetic_slices(2, 96, seed=8)
+    with torch.no_grad():
+        c = enc(x)
+        mine = resnet_port.resnet_forward(sd, x)
+    err = (c - mine).abs().max().item()
+    print(f"encoder: |c| max {c.abs().max().item():.3f}, port-vs-ref {err:.3g}")
+    assert err < 1e-4
+    save("encoder_96.npz", x=x, c=c)
+
+
+def golden_diffusion():
+    from src.models.modules import cond_DDPM
+    from src.models.modules.cond_DDPM import GaussianDiffusion
+
+    spec = unet_port.UNetSpec(model_channels=64, channel_mult=(1, 2), num_res_blocks=1, num_classes=128)
+    m, shapes = ref_unet(spec, image=32)
+    sd = make_state_dict(shapes, seed=2)
+    m.load_state_dict(sd, strict=True)
+    sched = diffusion_port.schedule_buffers()
+    g = torch.Generator().manual_seed(9)
+    img = torch.rand(3, 1, 32, 32, generator=g)
+    cond = torch.randn(3, 128, generator=g)
+    noise = (0.6 * torch.randn(1, 1, 32, 32, generator=g)).repeat(3, 1, 1, 1).half()
+    out = {"img": img, "cond": cond, "noise": noise}
+    model = lambda x, t, c: unet_port.unet_forward(sd, spec, x, t, c)  # noqa: E731
+    for objective in ("pred_x0", "pred_noise"):
+        d = GaussianDiffusion(m, image_size=(32, 32), timesteps=1000, sampling_timesteps=1000, objective=objective,
+                              channels=1, loss_type="l1", p2_loss_weight_gamma=0, cfg=base_cfg())
+        with torch.no_grad():
+            loss, reco = d(img, cond=cond, t=499, noise=noise)
+            ploss, preco = diffusion_port.reconstruct(model, sched, img, 499, cond, noise, objective=objective)
+        assert (reco - preco).abs().max().item() < 1e-4 and abs(loss.item() - ploss.item()) < 1e-5
+        out[f"reco_{objective}"] = reco
+        out[f"loss_{objective}"] = loss
+    # reverse loop (cond_DDPM.py:517-530, :446-464); the shipped code needs use_spatial_transformer set by the caller
+    d = GaussianDiffusion(m, image_size=(32, 32), timesteps=1000, sampling_timesteps=1000, objective="pred_x0",
+                          channels=1, loss_type="l1", p2_loss_weight_gamma=0, cfg=base_cfg())
+    d.use_spatial_transformer = False
+    T0 = 4
+    noises = [(0.6 * torch.randn(1, 1, 32, 32, generator=g)).repeat(3, 1, 1, 1).half() for _ in range(T0 + 1)]
+    feed = list(noises)
+    orig = cond_DDPM.gen_noise
+    cond_DDPM.gen_noise = lambda cfg, shape: feed.pop(0)
+    try:
+        with torch.no_grad():
+            rec = d.sample(cond=cond, x_start=img * 2 - 1, start_t=T0, noise=True)
+    finally:
+        cond_DDPM.gen_noise = orig
+    feed2 = list(noises)
+    with torch.no_grad():
+        prec = diffusion_port.reverse_loop(model, sched, img * 2 - 1, cond, T0, lambda: feed2.pop(0))
+    assert (rec - prec).abs().max().item() < 1e-4
+    out["reverse_T0"] = T0
+    out["reverse_noises"] = torch.stack(noises)
+    out["reverse_out"] = rec
+    save("diffusion_small_32.npz", **out)
+
+
+def golden_tail():
+    """utils_eval._test_step / _test_end on synthetic volumes with a GIVEN reconstruction (val then test stage)."""
+    from src.utils import utils_eval
+
+    from oracle import tail_port
+
+    class Host:
+        pass
+
+    res = {}
+    for depth, tag in ((50, "d50"), (4, "d4")):
+        host = Host()
+        host.cfg = base_cfg()
+        host.eval_dict = utils_eval.get_eval_dictionary()
+        host.threshold = {}
+        host.dataset = ["Brats21"]
+        host.new_size = [160, 190, 160]
+        host.diffs_list, host.seg_list = [], []
+        vols = [synthetic_volume(s, depth=depth) for s in (0, 1)]
+        # ---- val stage
+        host.stage = "val"
+        ports = []
+        for i, v in enumerate(vols):
+            utils_eval._test_step(host, v["reco"].clone(), v["vol"].clone(), v["seg_orig"].clone(),
+                                  v["mask_orig"].clone(), i, [f"v{i}"], torch.tensor([1]))
+            ports.append(tail_port.volume_tail(v["reco"][0, 0].numpy(), v["vol"][0, 0].numpy(),
+                                               v["seg_orig"][0, 0].numpy(), v["mask_orig"][0, 0].numpy(), stage="val"))
+        val_dict = {k: list(host.eval_dict[k]) for k in
+                    ("DiceScorePerVol", "BestDicePerVol", "BestThresholdPerVol", "AUCPerVol", "AUPRCPerVol", "TPPerVol",
+                     "FPPerVol", "TNPerVol", "FNPerVol", "TPRPerVol", "FPRPerVol", "l1recoErrorAll", "l2recoErrorAll",
+                     "l1recoErrorUnhealthy", "l1recoErrorHealthy", "l2recoErrorUnhealthy", "l2recoErrorHealthy",
+                     "AccuracyPerVol", "PrecisionPerVol", "RecallPerVol", "SpecificityPerVol", "lesionSizePerVol",
+                     "DiceScorePerSlice", "AnomalyScoreRecoPerSlice", "labelPerSlice", "AnomalyScoreRecoPerVol",
+                     "AUCAnomalyRecoPerSlice", "AUPRCAnomalyRecoPerSlice")}
+        utils_eval._test_end(host)
+        total = host.threshold["total"]
+        # port parity on the val stage
+        for i, p in enumerate(ports):
+            assert p["BestThreshold"] == val_dict["BestThresholdPerVol"][i], (p["BestThreshold"], val_dict["BestThresholdPerVol"][i])
+            assert p["BestDice"] == val_dict["BestDicePerVol"][i]
+            assert p["Dice"] == val_dict["DiceScorePerVol"][i]
+            assert (p["TP"], p["FP"], p["TN"], p["FN"]) == tuple(int(val_dict[k][i]) for k in ("TPPerVol", "FPPerVol", "TNPerVol", "FNPerVol"))
+            assert abs(p["AUC"] - val_dict["AUCPerVol"][i]) < 1e-12 and abs(p["AUPRC"] - val_dict["AUPRCPerVol"][i]) < 1e-12
+            assert abs(p["l1recoErrorAll"] - val_dict["l1recoErrorAll"][i]) < 1e-7
+            assert abs(float(p["AnomalyScoreRecoPerVol"]) - float(val_dict["AnomalyScoreRecoPerVol"][i])) < 1e-7
+        flat = np.concatenate([p["diff_filtered"].flatten() for p in ports])
+        gflat = np.concatenate([(v["seg_orig"][0, 0].numpy() > 0).flatten() for v in vols])
+        _, ptotal = tail_port.find_best_val(flat, gflat, val_range=(0, np.max(flat)), max_steps=10)
+        assert ptotal == total, (ptotal, total)
+        # ---- test stage with the global threshold
+        host.eval_dict = utils_eval.get_eval_dictionary()
+        host.stage = "test"
+        v = vols[0]
+        utils_eval._test_step(host, v["reco"].clone(), v["vol"].clone(), v["seg_orig"].clone(), v["mask_orig"].clone(),
+                              0, ["v0"], torch.tensor([1]))
+        pt = tail_port.volume_tail(v["reco"][0, 0].numpy(), v["vol"][0, 0].numpy(), v["seg_orig"][0, 0].numpy(),
+                                   v["mask_orig"][0, 0].numpy(), stage="test", threshold_total=total)
+        assert pt["Dice"] == host.eval_dict["DiceScorePerVol"][0]
+        res[tag] = dict(
+            val={k: [float(x) for x in vals] for k, vals in val_dict.items()},
+            threshold_total=float(total),
+            test_dice=float(host.eval_dict["DiceScorePerVol"][0]),
+            test_counts=[int(host.eval_dict[k][0]) for k in ("TPPerVol", "FPPerVol", "TNPerVol", "FNPerVol")],
+            filtered_sum=[float(p["diff_filtered"].astype(np.float64).sum()) for p in ports],
+            masked_sum=[float(p["diff_masked"].astype(np.float64).sum()) for p in ports],
+            thresholded_count=[int(p["thresholded"].sum()) for p in ports],
+        )
+        print(f"tail {tag}: total threshold {total:.6f}, val dice {val_dict['DiceScorePerVol']}, test dice {res[tag]['test_dice']:.4f}")
+    with open(os.path.join(GOLD, "tail.json"), "w") as f:
+        json.dump(res, f, indent=1)
+    # small dense fixtures for the stencils (erosion + median) incl. borders: W=32 -> 1 erosion, W=56 -> 2,
+    # W=24 -> W//25 == 0 which scipy reads as "erode until stable" (everything vanishes)
+    arrays = {}
+    for hw, d in ((32, 10), (56, 6), (24, 7)):
+        g = np.random.default_rng(hw)
+        vol = g.random((hw, hw, d), dtype=np.float32)
+        mask = (g.random((hw, hw, d)) > 0.04).astype(np.float32)
+        t = torch.from_numpy(vol.copy())[None, None]
+        masked = utils_eval.apply_brainmask_volume(t.clone(), torch.from_numpy(mask)[None, None]).squeeze().numpy()
+        filt = utils_eval.apply_3d_median_filter(masked.copy(), kernelsize=5)
+        assert np.array_equal(masked, tail_port.apply_brainmask_volume(vol, mask)), hw
+        assert np.array_equal(filt, tail_port.median_filter_3d(masked, 5)), hw
+        print(f"stencil {hw}: nonzero after erosion {np.count_nonzero(masked)}")
+        arrays.update({f"vol{hw}": vol, f"mask{hw}": mask.astype(np.uint8), f"masked{hw}": masked, f"filtered{hw}": filt})
+    save("stencil.npz", **arrays)
+
+
+def golden_test_step():
+    """The whole reference DDPM_2D (encoder -> UNet -> diffusion -> test_step -> _test_step) on one synthetic volume.
+    Only inputs that cannot be regenerated (none) and the outputs are stored: reco volume + eval_dict scalars."""
+    from src.models.DDPM_2D import DDPM_2D
+
+    cfg = base_cfg(noise_ensemble=True)
+    model = DDPM_2D(cfg, prefix="t/")
+    enc_sd = make_state_dict(resnet_port.param_shapes(128), seed=3)
+    unet_sd = make_state_dict(unet_port.param_shapes(unet_port.UNetSpec()), seed=1)
+    sched = diffusion_port.schedule_buffers()
+    full = {"encoder.encoder." + k: v for k, v in enc_sd.items()}
+    full.update({"diffusion." + k: v for k, v in sched.items()})
+    full.update({"diffusion.model." + k: v for k, v in unet_sd.items()})
+    assert list(model.state_dict().keys()) == list(full.keys()), "DDPM_2D state_dict layout mismatch"
+    model.load_state_dict(full, strict=True)
+    model.eval()
+    v = synthetic_volume(0, depth=8)
+    batch = {"Dataset": ["Brats21"], "vol": {"data": v["vol"]}, "vol_orig": {"data": v["vol"].clone()},
+             "seg_orig": {"data": v["seg_orig"]}, "mask_orig": {"data": v["mask_orig"]}, "ID": ["v0"],
+             "age": torch.tensor([50]), "stage": "val", "label": torch.tensor([1]), "seg_available": True}
+    np.random.seed(11)
+    captured = {}
+    from src.utils import utils_eval as ue
+    import src.models.DDPM_2D as mod
+
+    orig_ts = mod._test_step
+
+    def spy(self, final_volume, *a, **k):
+        captured["reco"] = final_volume.detach().clone()
+        return orig_ts(self, final_volume, *a, **k)
+
+    mod._test_step = spy
+    try:
+        with torch.no_grad():
+            model.on_test_start()
+            model.test_step(batch, 0)
+    finally:
+        mod._test_step = orig_ts
+    ed = model.eval_dict
+    keys = ("DiceScorePerVol", "BestDicePerVol", "BestThresholdPerVol", "AUCPerVol", "AUPRCPerVol", "l1recoErrorAll",
+            "AnomalyScoreRecoPerVol", "AnomalyScoreRegPerVol")
+    save("test_step_96.npz", reco=captured["reco"][0, 0], latent=ed["latentSpace"][0],
+         **{k: np.asarray([float(x) for x in ed[k]]) for k in keys})
+    print({k: [float(x) for x in ed[k]] for k in keys})
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLD, exist_ok=True)
+    which = sys.argv[1:] or ["schedule", "simplex", "unet", "encoder", "diffusion", "tail", "test_step"]
+    torch.manual_seed(0)
+    for w in which:
+        print(f"== {w}")
+        globals()["golden_" + w]()
