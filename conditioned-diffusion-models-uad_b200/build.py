@@ -55,7 +55,8 @@ def build(force: bool = False, verbose: bool = True) -> str:
 
     def compile_one(src):
         obj = os.path.join(OBJDIR, src.replace(".cu", ".o"))
-        cmd = [NVCC] + ARCH_FLAGS + COMMON + ["-c", os.path.join(CSRC, src), "-o", obj]
+        extra = ["-fmad=false"] if src.endswith("_nofma.cu") else []  # bit-exact float64 restatements
+        cmd = [NVCC] + ARCH_FLAGS + COMMON + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")

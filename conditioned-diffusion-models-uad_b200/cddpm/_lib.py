@@ -20,6 +20,19 @@ class CddpmError(RuntimeError):
     """Raised when a libcddpm_b200 entry point returns a non-zero status."""
 
 
+class UNetConfig(ctypes.Structure):
+    """struct cddpm_unet_config (include/cddpm_b200.h)."""
+
+    _fields_ = [
+        ("image_h", ctypes.c_int), ("image_w", ctypes.c_int),
+        ("in_channels", ctypes.c_int), ("model_channels", ctypes.c_int), ("out_channels", ctypes.c_int),
+        ("num_res_blocks", ctypes.c_int),
+        ("n_mult", ctypes.c_int), ("channel_mult", ctypes.c_int * 8),
+        ("n_attn_res", ctypes.c_int), ("attention_resolutions", ctypes.c_int * 8),
+        ("num_classes", ctypes.c_int), ("num_head_channels", ctypes.c_int), ("fmt", ctypes.c_int),
+    ]
+
+
 _lib: Optional[ctypes.CDLL] = None
 
 
@@ -30,8 +43,30 @@ def _signatures(c):
     return {
         "cddpm_last_error": (c.c_char_p, []),
         "cddpm_version": (c.c_char_p, []),
+        "cddpm_memcpy_d2d": (i32, [vp, vp, i64, vp]),
         "cddpm_pack_conv_weight": (i32, [vp, i32, i32, i32, i32, i32, vp, i32, i32, i32, vp]),
         "cddpm_conv_igemm": (i32, [i32, pvp, pi32, pi32, i32, i32, i32, i32, vp, vp, vp, vp, i32, i32, vp]),
+        "cddpm_gn_workspace_floats": (i64, [i32, i32]),
+        "cddpm_groupnorm_film_silu": (
+            i32, [vp, i32, vp, i32, i32, i32, i32, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, i32, vp]),
+        "cddpm_linear": (i32, [vp, i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+        "cddpm_timestep_embedding": (i32, [vp, vp, i32, i32, vp]),
+        "cddpm_attention": (i32, [vp, vp, i32, i32, i32, i32, vp]),
+        "cddpm_unet_create": (i32, [c.POINTER(UNetConfig), pvp]),
+        "cddpm_unet_destroy": (None, [vp]),
+        "cddpm_unet_param_count": (i32, [vp]),
+        "cddpm_unet_param_info": (i32, [vp, i32, c.POINTER(c.c_char_p), c.POINTER(i64)]),
+        "cddpm_unet_set_param": (i32, [vp, c.c_char_p, vp, i64, vp]),
+        "cddpm_unet_forward": (i32, [vp, vp, vp, vp, vp, i32, vp]),
+        "cddpm_unet_tap": (i32, [vp, c.c_char_p, pvp, pi32, pi32, pi32]),
+        "cddpm_unet_film": (i32, [vp, pvp, pi32]),
+        "cddpm_unet_conv_flops": (i64, [vp]),
+        "cddpm_unet_launches": (i32, [vp]),
+        "cddpm_simplex_noise": (i32, [c.c_char_p, vp, vp, i32, i32, i32, i32, c.c_double, c.c_double, vp]),
+        "cddpm_q_sample": (i32, [vp, vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+        "cddpm_posterior_step": (i32, [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]),
+        "cddpm_recon_finish": (
+            i32, [vp, vp, vp, vp, i32, vp, f32, f32, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     }
 
 

@@ -1,0 +1,132 @@
+"""Handle to the C++ UNet engine (cddpm_unet_* in include/cddpm_b200.h)."""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import CddpmError, UNetConfig, check, current_stream, lib, ptr
+
+
+class UNetEngine:
+    """Owns one cddpm_unet_t.  Parameters are pushed by reference state_dict key; forward runs the planned kernel
+    sequence on the current CUDA stream.  No CPU path: everything here requires CUDA tensors."""
+
+    def __init__(self, *, image_size: Tuple[int, int], in_channels: int, model_channels: int, out_channels: int,
+                 num_res_blocks: int, attention_resolutions: Sequence[int], channel_mult: Sequence[int],
+                 num_classes: Optional[int], num_head_channels: int = 64, dtype=torch.float16):
+        cfg = UNetConfig()
+        cfg.image_h, cfg.image_w = int(image_size[0]), int(image_size[1])
+        cfg.in_channels, cfg.model_channels, cfg.out_channels = in_channels, model_channels, out_channels
+        cfg.num_res_blocks = num_res_blocks
+        cfg.n_mult = len(channel_mult)
+        for i, m in enumerate(channel_mult):
+            cfg.channel_mult[i] = int(m)
+        cfg.n_attn_res = len(attention_resolutions)
+        for i, a in enumerate(attention_resolutions):
+            cfg.attention_resolutions[i] = int(a)
+        cfg.num_classes = int(num_classes) if num_classes else 0
+        cfg.num_head_channels = num_head_channels
+        cfg.fmt = _lib.fmt_of(dtype)
+        self.dtype = dtype
+        self.image_size = (cfg.image_h, cfg.image_w)
+        self.num_classes = cfg.num_classes
+        self._h = ctypes.c_void_p()
+        check(lib().cddpm_unet_create(ctypes.byref(cfg), ctypes.byref(self._h)), "cddpm_unet_create")
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                lib().cddpm_unet_destroy(h)
+            except Exception:
+                pass
+            self._h = ctypes.c_void_p()
+
+    # ------------------------------------------------------------------ parameters
+    def param_names(self) -> List[Tuple[str, int]]:
+        n = lib().cddpm_unet_param_count(self._h)
+        out = []
+        name = ctypes.c_char_p()
+        numel = ctypes.c_int64()
+        for i in range(n):
+            check(lib().cddpm_unet_param_info(self._h, i, ctypes.byref(name), ctypes.byref(numel)))
+            out.append((name.value.decode(), int(numel.value)))
+        return out
+
+    def set_param(self, name: str, value: torch.Tensor) -> None:
+        if not value.is_cuda:
+            raise CddpmError(f"parameter {name} is on {value.device}; the cDDPM engine needs CUDA tensors")
+        v = value.detach()
+        if v.dtype != torch.float32 or not v.is_contiguous():
+            v = v.float().contiguous()
+        check(lib().cddpm_unet_set_param(self._h, name.encode(), ptr(v), v.numel(), current_stream()),
+              f"cddpm_unet_set_param({name})")
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], prefix: str = "") -> None:
+        for name, _ in self.param_names():
+            self.set_param(name, sd[prefix + name])
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x: torch.Tensor, t: torch.Tensor, cond: Optional[torch.Tensor] = None,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if not x.is_cuda:
+            raise CddpmError("UNet forward needs CUDA tensors (there is no CPU path)")
+        B = x.shape[0]
+        if tuple(x.shape[1:]) != (1, self.image_size[0], self.image_size[1]):
+            raise CddpmError(f"expected input [B,1,{self.image_size[0]},{self.image_size[1]}], got {tuple(x.shape)}")
+        x = x.float().contiguous()
+        t = t.to(device=x.device, dtype=torch.int64).contiguous()
+        if t.numel() != B:
+            raise CddpmError("timesteps must have one entry per batch element")
+        if self.num_classes:
+            if cond is None:
+                raise CddpmError("conditioned UNet called without cond")
+            cond = cond.float().contiguous()
+            if tuple(cond.shape) != (B, self.num_classes):
+                raise CddpmError(f"cond must be [B,{self.num_classes}], got {tuple(cond.shape)}")
+        else:
+            cond = None
+        if out is None:
+            out = torch.empty_like(x)
+        check(lib().cddpm_unet_forward(self._h, ptr(x), ptr(t), ptr(cond), ptr(out), B, current_stream()),
+              "cddpm_unet_forward")
+        return out
+
+    # ------------------------------------------------------------------ introspection (parity tests, bench)
+    def tap(self, layer: str, batch: int) -> torch.Tensor:
+        """NCHW fp32 copy of a layer output of the last forward."""
+        p = ctypes.c_void_p()
+        C, H, W = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        check(lib().cddpm_unet_tap(self._h, layer.encode(), ctypes.byref(p), ctypes.byref(C), ctypes.byref(H),
+                                   ctypes.byref(W)), f"cddpm_unet_tap({layer})")
+        n = batch * C.value * H.value * W.value
+        buf = torch.empty(n, dtype=self.dtype, device="cuda")
+        torch.cuda.current_stream().synchronize()
+        _cudart_memcpy(buf.data_ptr(), p.value, n * 2)
+        return buf.view(batch, H.value, W.value, C.value).permute(0, 3, 1, 2).float()
+
+    def film(self, batch: int) -> torch.Tensor:
+        p = ctypes.c_void_p()
+        stride = ctypes.c_int()
+        check(lib().cddpm_unet_film(self._h, ctypes.byref(p), ctypes.byref(stride)))
+        buf = torch.empty(batch, stride.value, dtype=torch.float32, device="cuda")
+        torch.cuda.current_stream().synchronize()
+        _cudart_memcpy(buf.data_ptr(), p.value, batch * stride.value * 4)
+        return buf
+
+    @property
+    def conv_flops_per_sample(self) -> int:
+        return int(lib().cddpm_unet_conv_flops(self._h))
+
+    @property
+    def launches_per_forward(self) -> int:
+        return int(lib().cddpm_unet_launches(self._h))
+
+
+def _cudart_memcpy(dst: int, src: int, nbytes: int) -> None:
+    """Device-to-device copy on the current stream (used only by the introspection helpers)."""
+    check(lib().cddpm_memcpy_d2d(dst, src, nbytes, current_stream()), "cddpm_memcpy_d2d")
+    torch.cuda.current_stream().synchronize()

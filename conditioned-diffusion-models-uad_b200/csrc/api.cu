@@ -2,7 +2,12 @@
 #include "../../include/cddpm_b200.h"
 
 #include "common.h"
+#include "attention.cuh"
 #include "conv_igemm.cuh"
+#include "diffusion.cuh"
+#include "elementwise.cuh"
+#include "simplex.cuh"
+#include "unet_engine.cuh"
 
 namespace cddpm {
 const char* last_error_cstr();
@@ -14,6 +19,11 @@ extern "C" {
 
 const char* cddpm_last_error(void) { return last_error_cstr(); }
 const char* cddpm_version(void) { return "cddpm_b200 0.1 (sm_100a)"; }
+int cddpm_memcpy_d2d(void* dst, const void* src, int64_t nbytes, void* stream) {
+  if (!dst || !src || nbytes < 0) return fail(kInvalidArgument, "memcpy_d2d: bad arguments");
+  return check_cuda(cudaMemcpyAsync(dst, src, static_cast<size_t>(nbytes), cudaMemcpyDeviceToDevice,
+                                    static_cast<cudaStream_t>(stream)), "cudaMemcpyAsync");
+}
 
 int cddpm_pack_conv_weight(const float* w_oihw, int cout, int cin_total, int ksize, int cin_off, int c_s,
                            void* wpacked, int ktot, int koff, int fmt, void* stream) {
@@ -51,5 +61,129 @@ int cddpm_conv_igemm(int num_src, const void* const* src, const int* src_c, cons
   CDDPM_TRY(build_conv_params(d, &p));
   return launch_conv_igemm(p, static_cast<cudaStream_t>(stream));
 }
+
+int64_t cddpm_gn_workspace_floats(int B, int HW) {
+  return static_cast<int64_t>(B) * gn_num_chunks(B, HW) * kGnGroups * 2;
+}
+
+int cddpm_groupnorm_film_silu(const void* x0, int c0, const void* x1, int c1, int B, int H, int W,
+                              const float* gamma, const float* beta, const float* film, int film_stride,
+                              int film_off, int silu, int mode, void* out, void* raw_out, float* workspace, int fmt,
+                              void* stream) {
+  if (!workspace) return fail(kInvalidArgument, "groupnorm: workspace is required");
+  CatView v;
+  v.p0 = x0;
+  v.c0 = c0;
+  v.p1 = x1;
+  v.c1 = c1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CDDPM_TRY(launch_gn_stats(v, B, H * W, workspace, fmt, s));
+  GnApplyArgs g;
+  g.x = v;
+  g.B = B;
+  g.H = H;
+  g.W = W;
+  g.partial = workspace;
+  g.gamma = gamma;
+  g.beta = beta;
+  g.film = film;
+  g.film_stride = film_stride;
+  g.film_off = film_off;
+  g.silu = silu;
+  g.mode = mode;
+  g.out = out;
+  g.raw_out = raw_out;
+  g.fmt = fmt;
+  return launch_gn_apply(g, s);
+}
+
+int cddpm_linear(const float* in, int in_stride, const float* w, const float* bias, float* out, int out_stride,
+                 int B, int I, int O, int silu_in, int silu_out, void* stream) {
+  return launch_linear_ex(in, in_stride, w, bias, out, out_stride, B, I, O, silu_in, silu_out,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int cddpm_timestep_embedding(const int64_t* t, float* emb, int B, int dim, void* stream) {
+  if (!t || !emb) return fail(kInvalidArgument, "timestep_embedding: null pointer");
+  return launch_timestep_embedding(t, emb, B, dim, static_cast<cudaStream_t>(stream));
+}
+
+int cddpm_attention(const void* qkv, void* out, int B, int L, int C, int fmt, void* stream) {
+  return launch_attention(qkv, out, B, L, C, fmt, static_cast<cudaStream_t>(stream));
+}
+
+int cddpm_q_sample(const float* img, const void* noise, int noise_f16, float* out, const float* sqrt_alphas_cumprod,
+                   const float* sqrt_one_minus_alphas_cumprod, const int64_t* t, int t_shared, int B, int HW,
+                   int normalize, void* stream) {
+  return launch_q_sample(img, noise, noise_f16, out, sqrt_alphas_cumprod, sqrt_one_minus_alphas_cumprod, t, t_shared,
+                         B, HW, normalize, static_cast<cudaStream_t>(stream));
+}
+
+int cddpm_posterior_step(const float* model_out, const float* x_t, const void* noise, int noise_f16, float* x_prev,
+                         const float* posterior_mean_coef1, const float* posterior_mean_coef2,
+                         const float* posterior_log_variance_clipped, const float* sqrt_recip_alphas_cumprod,
+                         const float* sqrt_recipm1_alphas_cumprod, int64_t t, int B, int HW, int pred_noise,
+                         int final_unnormalize, void* stream) {
+  return launch_posterior_step(model_out, x_t, noise, noise_f16, x_prev, posterior_mean_coef1, posterior_mean_coef2,
+                               posterior_log_variance_clipped, sqrt_recip_alphas_cumprod,
+                               sqrt_recipm1_alphas_cumprod, t, B, HW, pred_noise, final_unnormalize,
+                               static_cast<cudaStream_t>(stream));
+}
+
+int cddpm_recon_finish(const float* model_out, const float* img, const float* x_t, const void* noise, int noise_f16,
+                       float* reco, float reco_alpha, float reco_beta, float* loss,
+                       const float* sqrt_one_minus_alphas_cumprod, const float* p2_loss_weight, const int64_t* t,
+                       int t_shared, int B, int HW, int pred_noise, int l2, void* stream) {
+  return launch_recon_finish(model_out, img, x_t, noise, noise_f16, reco, reco_alpha, reco_beta, loss,
+                             sqrt_one_minus_alphas_cumprod, p2_loss_weight, t, t_shared, B, HW, pred_noise, l2,
+                             static_cast<cudaStream_t>(stream));
+}
+
+int cddpm_simplex_noise(const uint8_t* perm_host, void* out_f16, float* out_f32, int B, int H, int W, int octaves,
+                        double persistence, double frequency, void* stream) {
+  return launch_simplex_noise(perm_host, out_f16, out_f32, B, H, W, octaves, persistence, frequency,
+                              static_cast<cudaStream_t>(stream));
+}
+
+struct cddpm_unet {
+  UNetEngine engine;
+};
+
+int cddpm_unet_create(const cddpm_unet_config* cfg, cddpm_unet_t** out) {
+  if (!cfg || !out) return fail(kInvalidArgument, "unet_create: null pointer");
+  cddpm_unet* h = new cddpm_unet();
+  int st = h->engine.init(*cfg);
+  if (st != kOk) {
+    delete h;
+    return st;
+  }
+  *out = h;
+  return kOk;
+}
+void cddpm_unet_destroy(cddpm_unet_t* h) { delete h; }
+int cddpm_unet_param_count(const cddpm_unet_t* h) { return h ? h->engine.param_count() : 0; }
+int cddpm_unet_param_info(const cddpm_unet_t* h, int index, const char** name, int64_t* numel) {
+  if (!h || !name || !numel) return fail(kInvalidArgument, "unet_param_info: null pointer");
+  return h->engine.param_info(index, name, numel);
+}
+int cddpm_unet_set_param(cddpm_unet_t* h, const char* name, const float* value, int64_t numel, void* stream) {
+  if (!h || !name) return fail(kInvalidArgument, "unet_set_param: null pointer");
+  return h->engine.set_param(name, value, numel, static_cast<cudaStream_t>(stream));
+}
+int cddpm_unet_forward(cddpm_unet_t* h, const float* x, const int64_t* t, const float* cond, float* out, int B,
+                       void* stream) {
+  if (!h) return fail(kInvalidArgument, "unet_forward: null handle");
+  return h->engine.forward(x, t, cond, out, B, static_cast<cudaStream_t>(stream));
+}
+int cddpm_unet_tap(const cddpm_unet_t* h, const char* layer, void** ptr, int* C, int* H, int* W) {
+  if (!h || !layer || !ptr || !C || !H || !W) return fail(kInvalidArgument, "unet_tap: null pointer");
+  return h->engine.tap(layer, ptr, C, H, W);
+}
+int cddpm_unet_film(const cddpm_unet_t* h, const float** ptr, int* stride) {
+  if (!h || !ptr || !stride) return fail(kInvalidArgument, "unet_film: null pointer");
+  return h->engine.film(ptr, stride);
+}
+int64_t cddpm_unet_conv_flops(const cddpm_unet_t* h) { return h ? h->engine.conv_flops_per_sample() : 0; }
+int cddpm_unet_launches(const cddpm_unet_t* h) { return h ? h->engine.launches_per_forward() : 0; }
 
 }  // extern "C"

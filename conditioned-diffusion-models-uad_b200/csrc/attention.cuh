@@ -1,0 +1,12 @@
+// Spatial self-attention core of the UNet's AttentionBlock (QKVAttention, "new attention order"):
+// src/models/modules/OpenAI_Unet.py:457-476.  qkv is the NHWC output of the 1x1 qkv convolution.
+#pragma once
+#include "common.h"
+
+namespace cddpm {
+
+// qkv [B, L, 3*C] 16-bit with q = channels [0,C), k = [C,2C), v = [2C,3C); head h owns channels [h*64,(h+1)*64) of
+// each.  out[b, t, h*64+c] = sum_s softmax_s((q_t . k_s) / sqrt(64)) * v[s, c]   (fp32 softmax), 16-bit.
+int launch_attention(const void* qkv, void* out, int B, int L, int C, int fmt, cudaStream_t stream);
+
+}  // namespace cddpm

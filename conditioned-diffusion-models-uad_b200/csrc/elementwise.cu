@@ -1,0 +1,482 @@
+// Bandwidth-bound kernels of the UNet forward (see elementwise.cuh).  16-byte vector accesses along the channel
+// (innermost NHWC) dimension, fp32 math, one rounding to the 16-bit activation type on store.
+#include "elementwise.cuh"
+
+#include <cuda_fp16.h>
+
+namespace cddpm {
+
+namespace {
+
+__device__ __forceinline__ void unpack8(const uint4& u, int fmt, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float2 t;
+    if (fmt == 1) {
+      t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+    } else {
+      t = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
+    }
+    f[2 * e] = t.x;
+    f[2 * e + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b, int fmt) {
+  if (fmt == 1) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+  __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8], int fmt) {
+  uint4 o;
+  o.x = pack2(f[0], f[1], fmt);
+  o.y = pack2(f[2], f[3], fmt);
+  o.z = pack2(f[4], f[5], fmt);
+  o.w = pack2(f[6], f[7], fmt);
+  return o;
+}
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+
+// ---------------------------------------------------------------------------------------------- GroupNorm stats
+__global__ void __launch_bounds__(256) gn_stats_kernel(const uint16_t* __restrict__ p0, const uint16_t* __restrict__ p1,
+                                                       int c0, int c1, int HW, int P, float* __restrict__ partial,
+                                                       int fmt) {
+  extern __shared__ float sh[];  // [C] sums, [C] squares
+  const int C = c0 + c1;
+  const int nvec = C >> 3;
+  const int lanes = blockDim.x / nvec;
+  const int chunk = blockIdx.x, b = blockIdx.y, nchunks = gridDim.x;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  const int v = threadIdx.x % nvec;
+  const int pl = threadIdx.x / nvec;
+  if (pl < lanes) {
+    const int cb = v << 3;
+    const uint16_t* src;
+    int cs, cbs;
+    if (cb < c0) {
+      src = p0; cs = c0; cbs = cb;
+    } else {
+      src = p1; cs = c1; cbs = cb - c0;
+    }
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+    const size_t base = static_cast<size_t>(b) * HW;
+    for (int p = chunk * P + pl; p < (chunk + 1) * P; p += lanes) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + (base + p) * cs + cbs));
+      float f[8];
+      unpack8(u, fmt, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += f[j];
+        q[j] = fmaf(f[j], f[j], q[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sh[cb + j], s[j]);
+      atomicAdd(&sh[C + cb + j], q[j]);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < kGnGroups) {
+    const int cpg = C / kGnGroups;
+    float s = 0.f, q = 0.f;
+    for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c) {
+      s += sh[c];
+      q += sh[C + c];
+    }
+    float* o = partial + ((static_cast<size_t>(b) * nchunks + chunk) * kGnGroups + threadIdx.x) * 2;
+    o[0] = s;
+    o[1] = q;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- GroupNorm apply
+struct GnApplyDev {
+  const uint16_t* p0;
+  const uint16_t* p1;
+  int c0, c1, H, W, Ho, Wo, Pout, nchunks_stats, P_stats;
+  const float* partial;
+  const float* gamma;
+  const float* beta;
+  const float* film;
+  int film_stride, film_off, silu, mode, fmt;
+  uint16_t* out;
+  uint16_t* raw_out;
+};
+
+__global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyDev a) {
+  extern __shared__ float sh[];  // A[C], Bc[C], mean[32], rstd[32]
+  const int C = a.c0 + a.c1;
+  float* sA = sh;
+  float* sB = sh + C;
+  float* sMean = sh + 2 * C;
+  float* sRstd = sMean + kGnGroups;
+  const int b = blockIdx.y;
+  const int cpg = C / kGnGroups;
+  if (threadIdx.x < kGnGroups) {
+    double s = 0.0, q = 0.0;
+    const float* pp = a.partial + (static_cast<size_t>(b) * a.nchunks_stats * kGnGroups + threadIdx.x) * 2;
+    for (int k = 0; k < a.nchunks_stats; ++k) {
+      s += static_cast<double>(pp[static_cast<size_t>(k) * kGnGroups * 2]);
+      q += static_cast<double>(pp[static_cast<size_t>(k) * kGnGroups * 2 + 1]);
+    }
+    const double n = static_cast<double>(a.H) * a.W * cpg;
+    const double mean = s / n;
+    double var = q / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    sMean[threadIdx.x] = static_cast<float>(mean);
+    sRstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + 1e-5));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    float A = sRstd[g] * a.gamma[c];
+    float Bc = a.beta[c] - sMean[g] * A;
+    if (a.film != nullptr) {
+      const float* f = a.film + static_cast<size_t>(b) * a.film_stride + a.film_off;
+      const float sc = 1.0f + f[c];
+      const float shf = f[C + c];
+      A *= sc;
+      Bc = Bc * sc + shf;
+    }
+    sA[c] = A;
+    sB[c] = Bc;
+  }
+  __syncthreads();
+
+  const int nvec = C >> 3;
+  const int lanes = blockDim.x / nvec;
+  const int v = threadIdx.x % nvec;
+  const int pl = threadIdx.x / nvec;
+  if (pl >= lanes) return;
+  const int cb = v << 3;
+  const uint16_t* src;
+  int cs, cbs;
+  if (cb < a.c0) {
+    src = a.p0; cs = a.c0; cbs = cb;
+  } else {
+    src = a.p1; cs = a.c1; cbs = cb - a.c0;
+  }
+  float A[8], Bc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    A[j] = sA[cb + j];
+    Bc[j] = sB[cb + j];
+  }
+  const size_t in_base = static_cast<size_t>(b) * a.H * a.W;
+  const size_t out_base = static_cast<size_t>(b) * a.Ho * a.Wo;
+  const int HWo = a.Ho * a.Wo;
+  const int p_end = min((static_cast<int>(blockIdx.x) + 1) * a.Pout, HWo);
+  for (int op = blockIdx.x * a.Pout + pl; op < p_end; op += lanes) {
+    const int oy = op / a.Wo, ox = op - oy * a.Wo;
+    float y[8], r[8];
+    if (a.mode == kResampleDown2) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = r[j] = 0.f;
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        const int iy = 2 * oy + (d >> 1), ix = 2 * ox + (d & 1);
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + (in_base + static_cast<size_t>(iy) * a.W + ix) * cs + cbs));
+        float f[8];
+        unpack8(u, a.fmt, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float t = fmaf(f[j], A[j], Bc[j]);
+          if (a.silu) t = silu_f(t);
+          y[j] += t;
+          r[j] += f[j];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        y[j] *= 0.25f;
+        r[j] *= 0.25f;
+      }
+    } else {
+      const int iy = (a.mode == kResampleUp2) ? (oy >> 1) : oy;
+      const int ix = (a.mode == kResampleUp2) ? (ox >> 1) : ox;
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + (in_base + static_cast<size_t>(iy) * a.W + ix) * cs + cbs));
+      unpack8(u, a.fmt, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float t = fmaf(r[j], A[j], Bc[j]);
+        if (a.silu) t = silu_f(t);
+        y[j] = t;
+      }
+    }
+    *reinterpret_cast<uint4*>(a.out + (out_base + op) * C + cb) = pack8(y, a.fmt);
+    if (a.raw_out != nullptr) *reinterpret_cast<uint4*>(a.raw_out + (out_base + op) * C + cb) = pack8(r, a.fmt);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- small linears
+constexpr int kLinBT = 8;
+__global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ in, int in_stride,
+                                                     const float* __restrict__ W, const float* __restrict__ bias,
+                                                     float* __restrict__ out, int out_stride, int B, int I, int O,
+                                                     int act_in, int act_out) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int warp_global = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  const int total_warps = gridDim.x * warps_per_block;
+  for (int o = warp_global; o < O; o += total_warps) {
+    const float* w = W + static_cast<size_t>(o) * I;
+    for (int b0 = 0; b0 < B; b0 += kLinBT) {
+      float acc[kLinBT];
+#pragma unroll
+      for (int j = 0; j < kLinBT; ++j) acc[j] = 0.f;
+      for (int i = lane; i < I; i += 32) {
+        const float wv = __ldg(w + i);
+#pragma unroll
+        for (int j = 0; j < kLinBT; ++j) {
+          if (b0 + j < B) {
+            float xv = __ldg(in + static_cast<size_t>(b0 + j) * in_stride + i);
+            if (act_in) xv = xv / (1.0f + expf(-xv));
+            acc[j] = fmaf(wv, xv, acc[j]);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kLinBT; ++j) {
+        float v = acc[j];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0 && b0 + j < B) {
+          v += (bias != nullptr) ? bias[o] : 0.f;
+          if (act_out) v = v / (1.0f + expf(-v));
+          out[static_cast<size_t>(b0 + j) * out_stride + o] = v;
+        }
+      }
+    }
+  }
+}
+
+__global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, float* __restrict__ emb, int B, int dim) {
+  const int half = dim / 2;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * half) return;
+  const int b = idx / half, i = idx - b * half;
+  const float freq = expf(-logf(10000.0f) * static_cast<float>(i) / static_cast<float>(half));
+  const float arg = static_cast<float>(t[b]) * freq;
+  emb[static_cast<size_t>(b) * dim + i] = cosf(arg);
+  emb[static_cast<size_t>(b) * dim + half + i] = sinf(arg);
+  if ((dim & 1) && i == 0) emb[static_cast<size_t>(b) * dim + dim - 1] = 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------- stem / head convs
+__global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                      const float* __restrict__ bias, uint16_t* __restrict__ out,
+                                                      int B, int H, int W, int Cout, int fmt) {
+  extern __shared__ float sw[];  // [9][Cout] weights, [Cout] bias
+  for (int i = threadIdx.x; i < 9 * Cout; i += blockDim.x) {
+    const int tap = i / Cout, co = i - tap * Cout;
+    sw[i] = w[co * 9 + tap];
+  }
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[9 * Cout + i] = bias[i];
+  __syncthreads();
+  const int ngrp = Cout >> 3;
+  const int ppb = blockDim.x / ngrp;
+  const int g = threadIdx.x % ngrp;
+  const int pl = threadIdx.x / ngrp;
+  if (pl >= ppb) return;
+  const size_t total = static_cast<size_t>(B) * H * W;
+  for (size_t pix = static_cast<size_t>(blockIdx.x) * ppb + pl; pix < total; pix += static_cast<size_t>(gridDim.x) * ppb) {
+    const int xw = static_cast<int>(pix % W);
+    const int yh = static_cast<int>((pix / W) % H);
+    const size_t n = pix / (static_cast<size_t>(W) * H);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = sw[9 * Cout + g * 8 + j];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int iy = yh + tap / 3 - 1, ix = xw + tap % 3 - 1;
+      float v = 0.f;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(x + (n * H + iy) * W + ix);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, sw[tap * Cout + g * 8 + j], acc[j]);
+    }
+    *reinterpret_cast<uint4*>(out + pix * Cout + g * 8) = pack8(acc, fmt);
+  }
+}
+
+__global__ void __launch_bounds__(256) conv_out_kernel(const uint16_t* __restrict__ x, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, float* __restrict__ out, int B,
+                                                       int H, int W, int C, int fmt) {
+  extern __shared__ float sw[];  // [9][C]
+  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) {
+    const int tap = i / C, c = i - tap * C;
+    sw[i] = w[c * 9 + tap];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const size_t total = static_cast<size_t>(B) * H * W;
+  for (size_t pix = static_cast<size_t>(blockIdx.x) * wpb + (threadIdx.x >> 5); pix < total;
+       pix += static_cast<size_t>(gridDim.x) * wpb) {
+    const int xw = static_cast<int>(pix % W);
+    const int yh = static_cast<int>((pix / W) % H);
+    const size_t n = pix / (static_cast<size_t>(W) * H);
+    float acc = 0.f;
+    for (int tap = 0; tap < 9; ++tap) {
+      const int iy = yh + tap / 3 - 1, ix = xw + tap % 3 - 1;
+      if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+      const uint16_t* row = x + ((n * H + iy) * W + ix) * C;
+      for (int c = lane * 2; c < C; c += 64) {
+        const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(row + c));
+        float2 f;
+        if (fmt == 1) {
+          f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+        } else {
+          f = __half22float2(*reinterpret_cast<const __half2*>(&u));
+        }
+        acc = fmaf(f.x, sw[tap * C + c], acc);
+        acc = fmaf(f.y, sw[tap * C + c + 1], acc);
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) out[pix] = acc + bias[0];
+  }
+}
+
+__global__ void vec_add_kernel(const float* a, const float* b, float* out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] + (b ? b[i] : 0.f);
+}
+
+}  // namespace
+
+// number of statistics chunks per image: smallest divisor k of HW/64 with B*k >= 256 (else the largest <= 64)
+static int gn_pick_chunks(int B, int HW) {
+  const int units = HW / 64;
+  int best = 1;
+  for (int k = 1; k <= units && k <= kGnMaxChunks; ++k) {
+    if (units % k != 0) continue;
+    best = k;
+    if (B * k >= 256) break;
+  }
+  return best;
+}
+
+int gn_num_chunks(int B, int HW) { return gn_pick_chunks(B, HW); }
+
+static int check_view(const CatView& x, const char* who) {
+  if (x.p0 == nullptr || x.c0 <= 0) return fail(kInvalidArgument, std::string(who) + ": missing source");
+  if (x.c0 % 8 != 0 || x.c1 % 8 != 0) return fail(kUnsupported, std::string(who) + ": channel counts must be multiples of 8");
+  const int C = x.c0 + x.c1;
+  if (C % kGnGroups != 0) return fail(kUnsupported, std::string(who) + ": channels must be a multiple of 32");
+  if (C / 8 > 256) return fail(kUnsupported, std::string(who) + ": at most 2048 channels");
+  if (x.c1 > 0 && x.p1 == nullptr) return fail(kInvalidArgument, std::string(who) + ": missing second source");
+  return kOk;
+}
+
+int launch_gn_stats(const CatView& x, int B, int HW, float* partial, int fmt, cudaStream_t stream) {
+  CDDPM_TRY(check_view(x, "gn_stats"));
+  if (HW % 64 != 0) return fail(kUnsupported, "gn_stats: H*W must be a multiple of 64");
+  const int C = x.C();
+  const int k = gn_pick_chunks(B, HW);
+  const int nvec = C / 8;
+  const int threads = (256 / nvec) * nvec;
+  dim3 grid(k, B);
+  gn_stats_kernel<<<grid, threads, 2 * C * sizeof(float), stream>>>(
+      reinterpret_cast<const uint16_t*>(x.p0), reinterpret_cast<const uint16_t*>(x.p1), x.c0, x.c1, HW, HW / k,
+      partial, fmt);
+  return check_launch("gn_stats_kernel");
+}
+
+int launch_gn_apply(const GnApplyArgs& a, cudaStream_t stream) {
+  CDDPM_TRY(check_view(a.x, "gn_apply"));
+  if (!a.partial || !a.gamma || !a.beta || !a.out) return fail(kInvalidArgument, "gn_apply: null pointer");
+  const int HW = a.H * a.W;
+  if (HW % 64 != 0) return fail(kUnsupported, "gn_apply: H*W must be a multiple of 64");
+  if (a.mode == kResampleDown2 && ((a.H | a.W) & 1)) return fail(kInvalidArgument, "gn_apply: odd size for avg-pool");
+  GnApplyDev d;
+  d.p0 = reinterpret_cast<const uint16_t*>(a.x.p0);
+  d.p1 = reinterpret_cast<const uint16_t*>(a.x.p1);
+  d.c0 = a.x.c0;
+  d.c1 = a.x.c1;
+  d.H = a.H;
+  d.W = a.W;
+  d.Ho = a.mode == kResampleUp2 ? a.H * 2 : (a.mode == kResampleDown2 ? a.H / 2 : a.H);
+  d.Wo = a.mode == kResampleUp2 ? a.W * 2 : (a.mode == kResampleDown2 ? a.W / 2 : a.W);
+  d.nchunks_stats = gn_pick_chunks(a.B, HW);
+  d.P_stats = HW / d.nchunks_stats;
+  d.partial = a.partial;
+  d.gamma = a.gamma;
+  d.beta = a.beta;
+  d.film = a.film;
+  d.film_stride = a.film_stride;
+  d.film_off = a.film_off;
+  d.silu = a.silu;
+  d.mode = a.mode;
+  d.fmt = a.fmt;
+  d.out = reinterpret_cast<uint16_t*>(a.out);
+  d.raw_out = reinterpret_cast<uint16_t*>(a.raw_out);
+  const int C = a.x.C();
+  const int HWo = d.Ho * d.Wo;
+  d.Pout = 128;
+  const int nvec = C / 8;
+  const int threads = (256 / nvec) * nvec;
+  dim3 grid((HWo + d.Pout - 1) / d.Pout, a.B);
+  gn_apply_kernel<<<grid, threads, (2 * C + 2 * kGnGroups) * sizeof(float), stream>>>(d);
+  return check_launch("gn_apply_kernel");
+}
+
+int launch_linear_ex(const float* in, int in_stride, const float* W, const float* bias, float* out, int out_stride,
+                     int B, int I, int O, int act_in, int act_out, cudaStream_t stream) {
+  if (!in || !W || !out) return fail(kInvalidArgument, "linear: null pointer");
+  int blocks = (O + 7) / 8;
+  if (blocks > 8192) blocks = 8192;
+  if (blocks < 1) blocks = 1;
+  linear_kernel<<<blocks, 256, 0, stream>>>(in, in_stride, W, bias, out, out_stride, B, I, O, act_in, act_out);
+  return check_launch("linear_kernel");
+}
+
+int launch_linear(const float* in, int in_stride, const float* W, const float* bias, float* out, int out_stride,
+                  int B, int I, int O, int act_in, cudaStream_t stream) {
+  return launch_linear_ex(in, in_stride, W, bias, out, out_stride, B, I, O, act_in, 0, stream);
+}
+
+int launch_timestep_embedding(const int64_t* t, float* emb, int B, int dim, cudaStream_t stream) {
+  const int n = B * (dim / 2);
+  timestep_embedding_kernel<<<(n + 255) / 256, 256, 0, stream>>>(t, emb, B, dim);
+  return check_launch("timestep_embedding_kernel");
+}
+
+int launch_conv_in(const float* x, const float* w, const float* bias, void* out, int B, int H, int W, int Cout,
+                   int fmt, cudaStream_t stream) {
+  if (Cout % 8 != 0 || Cout > 2048) return fail(kUnsupported, "conv_in: Cout must be a multiple of 8");
+  const int ngrp = Cout / 8;
+  const int threads = (256 / ngrp) * ngrp;
+  const int ppb = threads / ngrp;
+  const size_t total = static_cast<size_t>(B) * H * W;
+  int blocks = static_cast<int>((total + ppb - 1) / ppb);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  conv_in_kernel<<<blocks, threads, (10 * Cout) * sizeof(float), stream>>>(x, w, bias, reinterpret_cast<uint16_t*>(out), B,
+                                                                         H, W, Cout, fmt);
+  return check_launch("conv_in_kernel");
+}
+
+int launch_conv_out(const void* x, const float* w, const float* bias, float* out, int B, int H, int W, int C,
+                    int fmt, cudaStream_t stream) {
+  if (C % 64 != 0) return fail(kUnsupported, "conv_out: C must be a multiple of 64");
+  const size_t total = static_cast<size_t>(B) * H * W;
+  int blocks = static_cast<int>((total + 7) / 8);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  conv_out_kernel<<<blocks, 256, 9 * C * sizeof(float), stream>>>(reinterpret_cast<const uint16_t*>(x), w, bias, out, B, H,
+                                                                 W, C, fmt);
+  return check_launch("conv_out_kernel");
+}
+
+int launch_vec_add(const float* a, const float* b, float* out, int n, cudaStream_t stream) {
+  vec_add_kernel<<<(n + 255) / 256, 256, 0, stream>>>(a, b, out, n);
+  return check_launch("vec_add_kernel");
+}
+
+}  // namespace cddpm

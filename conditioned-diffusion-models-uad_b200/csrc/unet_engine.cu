@@ -1,0 +1,661 @@
+#include "unet_engine.cuh"
+
+#include <string.h>
+
+#include "attention.cuh"
+
+namespace cddpm {
+
+UNetEngine::~UNetEngine() {
+  free_acts();
+  for (void* p : owned_) cudaFree(p);
+}
+
+void UNetEngine::free_acts() {
+  for (void* p : act_owned_) cudaFree(p);
+  act_owned_.clear();
+  ops_.clear();
+  taps_.clear();
+  planned_B_ = 0;
+}
+
+template <typename T>
+int UNetEngine::dalloc(T** p, size_t n) {
+  void* q = nullptr;
+  CDDPM_CUDA(cudaMalloc(&q, n * sizeof(T) + 256));
+  owned_.push_back(q);
+  *p = reinterpret_cast<T*>(q);
+  return kOk;
+}
+
+int UNetEngine::add_param(const std::string& name, int64_t numel,
+                          std::function<int(const float*, cudaStream_t)> load) {
+  Param p;
+  p.name = name;
+  p.numel = numel;
+  p.load = std::move(load);
+  param_index_[name] = static_cast<int>(params_.size());
+  params_.push_back(std::move(p));
+  return kOk;
+}
+
+int UNetEngine::add_copy_param(const std::string& name, int64_t numel, float** dst) {
+  CDDPM_TRY(dalloc(dst, static_cast<size_t>(numel)));
+  float* d = *dst;
+  return add_param(name, numel, [d, numel](const float* src, cudaStream_t s) {
+    return check_cuda(cudaMemcpyAsync(d, src, numel * sizeof(float), cudaMemcpyDeviceToDevice, s), "param copy");
+  });
+}
+
+int UNetEngine::param_info(int i, const char** name, int64_t* numel) const {
+  if (i < 0 || i >= param_count()) return fail(kInvalidArgument, "param index out of range");
+  *name = params_[i].name.c_str();
+  *numel = params_[i].numel;
+  return kOk;
+}
+
+int UNetEngine::set_param(const char* name, const float* dev_ptr, int64_t numel, cudaStream_t stream) {
+  auto it = param_index_.find(name);
+  if (it == param_index_.end()) return fail(kInvalidArgument, std::string("unknown UNet parameter: ") + name);
+  Param& p = params_[it->second];
+  if (p.numel != numel)
+    return fail(kInvalidArgument, std::string("size mismatch for ") + name + ": expected " + std::to_string(p.numel) +
+                                      ", got " + std::to_string(numel));
+  if (!dev_ptr) return fail(kInvalidArgument, "null parameter pointer");
+  CDDPM_TRY(p.load(dev_ptr, stream));
+  p.set = true;
+  return kOk;
+}
+
+// ------------------------------------------------------------------------------------------------ construction
+int UNetEngine::add_res(const std::string& prefix, int c0, int c1, int cout, int mode) {
+  ResLayer L;
+  L.prefix = prefix;
+  L.cin = c0 + c1;
+  L.cout = cout;
+  L.mode = mode;
+  L.in_c0 = c0;
+  L.in_c1 = c1;
+  L.has_skip = (L.cin != cout);
+  L.film_off = film_total_;
+  film_total_ += 2 * cout;
+  const int fmt = cfg_.fmt;
+  const int cin = L.cin;
+  if (cin % 64 != 0 || cout % 64 != 0)
+    return fail(kUnsupported, "UNet channel counts must be multiples of 64 for the tcgen05 convolution path");
+  CDDPM_TRY(add_copy_param(prefix + ".in_layers.0.weight", cin, &L.gn1_w));
+  CDDPM_TRY(add_copy_param(prefix + ".in_layers.0.bias", cin, &L.gn1_b));
+  {
+    uint16_t* w = nullptr;
+    CDDPM_TRY(dalloc(&w, static_cast<size_t>(cout) * 9 * cin));
+    L.w1 = w;
+    CDDPM_TRY(add_param(prefix + ".in_layers.2.weight", static_cast<int64_t>(cout) * cin * 9,
+                        [=](const float* src, cudaStream_t s) {
+                          return launch_pack_conv_weight(src, cout, cin, 3, 0, cin, w, 9 * cin, 0, fmt, s);
+                        }));
+  }
+  CDDPM_TRY(add_copy_param(prefix + ".in_layers.2.bias", cout, &L.b1));
+  // emb_layers.1 lands in the concatenated FiLM projection (rows [film_off, film_off + 2*cout))
+  {
+    const int off = L.film_off;
+    const int E = emb_dim_;
+    UNetEngine* self = this;
+    CDDPM_TRY(add_param(prefix + ".emb_layers.1.weight", static_cast<int64_t>(2) * cout * E,
+                        [=](const float* src, cudaStream_t s) {
+                          return check_cuda(cudaMemcpyAsync(self->film_w + static_cast<size_t>(off) * E, src,
+                                                            static_cast<size_t>(2) * cout * E * sizeof(float),
+                                                            cudaMemcpyDeviceToDevice, s),
+                                            "film weight copy");
+                        }));
+    CDDPM_TRY(add_param(prefix + ".emb_layers.1.bias", 2 * cout, [=](const float* src, cudaStream_t s) {
+      return check_cuda(cudaMemcpyAsync(self->film_b + off, src, static_cast<size_t>(2) * cout * sizeof(float),
+                                        cudaMemcpyDeviceToDevice, s),
+                        "film bias copy");
+    }));
+  }
+  CDDPM_TRY(add_copy_param(prefix + ".out_layers.0.weight", cout, &L.gn2_w));
+  CDDPM_TRY(add_copy_param(prefix + ".out_layers.0.bias", cout, &L.gn2_b));
+  const int k2 = 9 * cout + (L.has_skip ? cin : 0);
+  {
+    uint16_t* w = nullptr;
+    CDDPM_TRY(dalloc(&w, static_cast<size_t>(cout) * k2));
+    L.w2 = w;
+    CDDPM_TRY(add_param(prefix + ".out_layers.3.weight", static_cast<int64_t>(cout) * cout * 9,
+                        [=](const float* src, cudaStream_t s) {
+                          return launch_pack_conv_weight(src, cout, cout, 3, 0, cout, w, k2, 0, fmt, s);
+                        }));
+    CDDPM_TRY(dalloc(&L.b2, static_cast<size_t>(cout)));
+    CDDPM_TRY(dalloc(&L.b2sum, static_cast<size_t>(cout)));
+    float* b2 = L.b2;
+    float* b2sum = L.b2sum;
+    if (L.has_skip) {
+      CDDPM_TRY(dalloc(&L.bskip, static_cast<size_t>(cout)));
+      CDDPM_CUDA(cudaMemset(L.bskip, 0, cout * sizeof(float)));
+      CDDPM_CUDA(cudaMemset(L.b2, 0, cout * sizeof(float)));
+    }
+    float* bskip = L.bskip;
+    CDDPM_TRY(add_param(prefix + ".out_layers.3.bias", cout, [=](const float* src, cudaStream_t s) {
+      CDDPM_CUDA(cudaMemcpyAsync(b2, src, cout * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      return launch_vec_add(b2, bskip, b2sum, cout, s);
+    }));
+    if (L.has_skip) {
+      // 1x1 skip over the (possibly concatenated) raw input: extra K columns after the 3x3 block
+      CDDPM_TRY(add_param(prefix + ".skip_connection.weight", static_cast<int64_t>(cout) * cin,
+                          [=](const float* src, cudaStream_t s) {
+                            CDDPM_TRY(launch_pack_conv_weight(src, cout, cin, 1, 0, c0, w, k2, 9 * cout, fmt, s));
+                            if (c1 > 0)
+                              CDDPM_TRY(launch_pack_conv_weight(src, cout, cin, 1, c0, c1, w, k2, 9 * cout + c0, fmt, s));
+                            return static_cast<int>(kOk);
+                          }));
+      CDDPM_TRY(add_param(prefix + ".skip_connection.bias", cout, [=](const float* src, cudaStream_t s) {
+        CDDPM_CUDA(cudaMemcpyAsync(bskip, src, cout * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        return launch_vec_add(b2, bskip, b2sum, cout, s);
+      }));
+    }
+  }
+  res_.push_back(L);
+  return kOk;
+}
+
+int UNetEngine::add_attn(const std::string& prefix, int ch) {
+  AttnLayer L;
+  L.prefix = prefix;
+  L.ch = ch;
+  const int fmt = cfg_.fmt;
+  if (ch % 64 != 0) return fail(kUnsupported, "attention channels must be a multiple of 64");
+  CDDPM_TRY(add_copy_param(prefix + ".norm.weight", ch, &L.gn_w));
+  CDDPM_TRY(add_copy_param(prefix + ".norm.bias", ch, &L.gn_b));
+  uint16_t *wq = nullptr, *wp = nullptr;
+  CDDPM_TRY(dalloc(&wq, static_cast<size_t>(3) * ch * ch));
+  CDDPM_TRY(dalloc(&wp, static_cast<size_t>(ch) * ch));
+  L.wqkv = wq;
+  L.wproj = wp;
+  CDDPM_TRY(add_param(prefix + ".qkv.weight", static_cast<int64_t>(3) * ch * ch, [=](const float* src, cudaStream_t s) {
+    return launch_pack_conv_weight(src, 3 * ch, ch, 1, 0, ch, wq, ch, 0, fmt, s);
+  }));
+  CDDPM_TRY(add_copy_param(prefix + ".qkv.bias", 3 * ch, &L.bqkv));
+  CDDPM_TRY(add_param(prefix + ".proj_out.weight", static_cast<int64_t>(ch) * ch, [=](const float* src, cudaStream_t s) {
+    return launch_pack_conv_weight(src, ch, ch, 1, 0, ch, wp, ch, 0, fmt, s);
+  }));
+  CDDPM_TRY(add_copy_param(prefix + ".proj_out.bias", ch, &L.bproj));
+  attn_.push_back(L);
+  return kOk;
+}
+
+int UNetEngine::build_layers() {
+  const int mc = cfg_.model_channels;
+  auto in_attn = [&](int ds) {
+    for (int i = 0; i < cfg_.n_attn_res; ++i)
+      if (cfg_.attention_resolutions[i] == ds) return true;
+    return false;
+  };
+  // registration order follows the reference module tree: label_emb, time_embed, input_blocks, middle, output, out
+  if (cfg_.num_classes > 0) {
+    CDDPM_TRY(add_copy_param("label_emb.0.weight", static_cast<int64_t>(half_dim_) * cfg_.num_classes, &le0_w));
+    CDDPM_TRY(add_copy_param("label_emb.0.bias", half_dim_, &le0_b));
+    CDDPM_TRY(add_copy_param("label_emb.2.weight", static_cast<int64_t>(half_dim_) * half_dim_, &le2_w));
+    CDDPM_TRY(add_copy_param("label_emb.2.bias", half_dim_, &le2_b));
+  }
+  CDDPM_TRY(add_copy_param("time_embed.0.weight", static_cast<int64_t>(half_dim_) * mc, &te0_w));
+  CDDPM_TRY(add_copy_param("time_embed.0.bias", half_dim_, &te0_b));
+  CDDPM_TRY(add_copy_param("time_embed.2.weight", static_cast<int64_t>(half_dim_) * half_dim_, &te2_w));
+  CDDPM_TRY(add_copy_param("time_embed.2.bias", half_dim_, &te2_b));
+
+  CDDPM_TRY(add_copy_param("input_blocks.0.0.weight", static_cast<int64_t>(mc) * cfg_.in_channels * 9, &stem_w));
+  CDDPM_TRY(add_copy_param("input_blocks.0.0.bias", mc, &stem_b));
+  in_blocks_.push_back({Layer{0, 0}});
+  in_block_ch_.push_back(mc);
+  int ch = mc, ds = 1;
+  for (int level = 0; level < cfg_.n_mult; ++level) {
+    const int mult = cfg_.channel_mult[level];
+    for (int r = 0; r < cfg_.num_res_blocks; ++r) {
+      const int bi = static_cast<int>(in_blocks_.size());
+      std::vector<Layer> layers;
+      CDDPM_TRY(add_res("input_blocks." + std::to_string(bi) + ".0", ch, 0, mult * mc, kResampleNone));
+      layers.push_back(Layer{1, static_cast<int>(res_.size()) - 1});
+      ch = mult * mc;
+      if (in_attn(ds)) {
+        CDDPM_TRY(add_attn("input_blocks." + std::to_string(bi) + ".1", ch));
+        layers.push_back(Layer{2, static_cast<int>(attn_.size()) - 1});
+      }
+      in_blocks_.push_back(layers);
+      in_block_ch_.push_back(ch);
+    }
+    if (level != cfg_.n_mult - 1) {
+      const int bi = static_cast<int>(in_blocks_.size());
+      CDDPM_TRY(add_res("input_blocks." + std::to_string(bi) + ".0", ch, 0, ch, kResampleDown2));
+      in_blocks_.push_back({Layer{1, static_cast<int>(res_.size()) - 1}});
+      in_block_ch_.push_back(ch);
+      ds *= 2;
+    }
+  }
+  CDDPM_TRY(add_res("middle_block.0", ch, 0, ch, kResampleNone));
+  mid_.push_back(Layer{1, static_cast<int>(res_.size()) - 1});
+  CDDPM_TRY(add_attn("middle_block.1", ch));
+  mid_.push_back(Layer{2, static_cast<int>(attn_.size()) - 1});
+  CDDPM_TRY(add_res("middle_block.2", ch, 0, ch, kResampleNone));
+  mid_.push_back(Layer{1, static_cast<int>(res_.size()) - 1});
+
+  std::vector<int> chans = in_block_ch_;
+  for (int level = cfg_.n_mult - 1; level >= 0; --level) {
+    const int mult = cfg_.channel_mult[level];
+    for (int i = 0; i < cfg_.num_res_blocks + 1; ++i) {
+      const int ich = chans.back();
+      chans.pop_back();
+      const int bi = static_cast<int>(out_blocks_.size());
+      std::vector<Layer> layers;
+      int li = 0;
+      CDDPM_TRY(add_res("output_blocks." + std::to_string(bi) + "." + std::to_string(li++), ch, ich, mc * mult,
+                        kResampleNone));
+      layers.push_back(Layer{1, static_cast<int>(res_.size()) - 1});
+      ch = mc * mult;
+      if (in_attn(ds)) {
+        CDDPM_TRY(add_attn("output_blocks." + std::to_string(bi) + "." + std::to_string(li++), ch));
+        layers.push_back(Layer{2, static_cast<int>(attn_.size()) - 1});
+      }
+      if (level > 0 && i == cfg_.num_res_blocks) {
+        CDDPM_TRY(add_res("output_blocks." + std::to_string(bi) + "." + std::to_string(li++), ch, 0, ch, kResampleUp2));
+        layers.push_back(Layer{1, static_cast<int>(res_.size()) - 1});
+        ds /= 2;
+      }
+      out_blocks_.push_back(layers);
+    }
+  }
+  CDDPM_TRY(add_copy_param("out.0.weight", ch, &head_gn_w));
+  CDDPM_TRY(add_copy_param("out.0.bias", ch, &head_gn_b));
+  CDDPM_TRY(add_copy_param("out.2.weight", static_cast<int64_t>(cfg_.out_channels) * mc * 9, &head_w));
+  CDDPM_TRY(add_copy_param("out.2.bias", cfg_.out_channels, &head_b));
+  if (ch != mc) return fail(kUnsupported, "UNet head expects model_channels at the output");
+  // concatenated FiLM projection
+  CDDPM_TRY(dalloc(&film_w, static_cast<size_t>(film_total_) * emb_dim_));
+  CDDPM_TRY(dalloc(&film_b, static_cast<size_t>(film_total_)));
+  return kOk;
+}
+
+int UNetEngine::init(const cddpm_unet_config& cfg) {
+  cfg_ = cfg;
+  if (cfg.in_channels != 1 || cfg.out_channels != 1)
+    return fail(kUnsupported, "UNet engine supports in_channels == out_channels == 1 (the cDDPM configuration)");
+  if (cfg.n_mult < 1 || cfg.n_mult > 8 || cfg.n_attn_res < 0 || cfg.n_attn_res > 8)
+    return fail(kInvalidArgument, "bad channel_mult / attention_resolutions length");
+  if (cfg.num_head_channels != 64) return fail(kUnsupported, "attention head dim must be 64");
+  if (cfg.image_h % (8 << (cfg.n_mult - 1)) != 0 || cfg.image_w % (8 << (cfg.n_mult - 1)) != 0)
+    return fail(kUnsupported, "image size must keep every level a multiple of 8 pixels");
+  half_dim_ = cfg.model_channels * 4;
+  emb_dim_ = half_dim_ * (cfg.num_classes > 0 ? 2 : 1);
+  return build_layers();
+}
+
+// ------------------------------------------------------------------------------------------------ planning
+int UNetEngine::act_alloc(ActTensor* t, int C, int H, int W, int B, bool scratch_f32) {
+  void* q = nullptr;
+  const size_t bytes = static_cast<size_t>(B) * H * W * C * (scratch_f32 ? 4 : 2) + 256;
+  CDDPM_CUDA(cudaMalloc(&q, bytes));
+  act_owned_.push_back(q);
+  t->p = q;
+  t->C = C;
+  t->H = H;
+  t->W = W;
+  return kOk;
+}
+
+void UNetEngine::push_conv(const ConvDesc& d, int* status) {
+  if (*status != kOk) return;
+  auto p = std::make_shared<ConvIgemmParams>();
+  *status = build_conv_params(d, p.get());
+  if (*status != kOk) return;
+  conv_flops_ += 2ll * d.H * d.W * d.Cout * conv_ktot(d);
+  ops_.push_back([p](cudaStream_t s) { return launch_conv_igemm(*p, s); });
+}
+
+int UNetEngine::plan_res(const ResLayer& L, const ActTensor& a0, const ActTensor* a1, ActTensor* out, int B) {
+  const int fmt = cfg_.fmt;
+  const int H = a0.H, W = a0.W;
+  const int Ho = L.mode == kResampleUp2 ? 2 * H : (L.mode == kResampleDown2 ? H / 2 : H);
+  const int Wo = L.mode == kResampleUp2 ? 2 * W : (L.mode == kResampleDown2 ? W / 2 : W);
+  CatView v;
+  v.p0 = a0.p;
+  v.c0 = a0.C;
+  if (a1) {
+    v.p1 = a1->p;
+    v.c1 = a1->C;
+  }
+  if (v.C() != L.cin) return fail(kInvalidArgument, "plan_res: channel mismatch at " + L.prefix);
+  ActTensor tA, tH, tB, tS;
+  CDDPM_TRY(act_alloc(&tA, L.cin, Ho, Wo, B));
+  CDDPM_TRY(act_alloc(&tH, L.cout, Ho, Wo, B));
+  CDDPM_TRY(act_alloc(&tB, L.cout, Ho, Wo, B));
+  if (L.mode != kResampleNone) CDDPM_TRY(act_alloc(&tS, L.cin, Ho, Wo, B));
+  CDDPM_TRY(act_alloc(out, L.cout, Ho, Wo, B));
+  float* partial = gn_partial_;
+  // 1-2. in_layers: GroupNorm + SiLU (+ resample of both the normalised and the raw input)
+  ops_.push_back([=](cudaStream_t s) { return launch_gn_stats(v, B, H * W, partial, fmt, s); });
+  {
+    GnApplyArgs g;
+    g.x = v;
+    g.B = B;
+    g.H = H;
+    g.W = W;
+    g.partial = partial;
+    g.gamma = L.gn1_w;
+    g.beta = L.gn1_b;
+    g.silu = 1;
+    g.mode = L.mode;
+    g.out = tA.p;
+    g.raw_out = (L.mode != kResampleNone) ? tS.p : nullptr;
+    g.fmt = fmt;
+    ops_.push_back([=](cudaStream_t s) { return launch_gn_apply(g, s); });
+  }
+  int st = kOk;
+  // 3. in_layers conv 3x3
+  {
+    ConvDesc d;
+    d.num_src = 1;
+    d.src[0] = tA.p;
+    d.src_c[0] = L.cin;
+    d.src_taps[0] = 9;
+    d.B = B;
+    d.H = Ho;
+    d.W = Wo;
+    d.Cout = L.cout;
+    d.wpacked = L.w1;
+    d.bias = L.b1;
+    d.out = tH.p;
+    d.ab_format = fmt;
+    push_conv(d, &st);
+    CDDPM_TRY(st);
+  }
+  // 4-5. out_layers: GroupNorm * (1 + scale) + shift, SiLU (dropout p = 0)
+  {
+    CatView hv;
+    hv.p0 = tH.p;
+    hv.c0 = L.cout;
+    ops_.push_back([=](cudaStream_t s) { return launch_gn_stats(hv, B, Ho * Wo, partial, fmt, s); });
+    GnApplyArgs g;
+    g.x = hv;
+    g.B = B;
+    g.H = Ho;
+    g.W = Wo;
+    g.partial = partial;
+    g.gamma = L.gn2_w;
+    g.beta = L.gn2_b;
+    g.film = film_out_;
+    g.film_stride = film_total_;
+    g.film_off = L.film_off;
+    g.silu = 1;
+    g.mode = kResampleNone;
+    g.out = tB.p;
+    g.fmt = fmt;
+    ops_.push_back([=](cudaStream_t s) { return launch_gn_apply(g, s); });
+  }
+  // 6. out_layers conv 3x3 + skip (identity residual, or 1x1 over the raw input fused as extra K columns)
+  {
+    ConvDesc d;
+    d.num_src = 1;
+    d.src[0] = tB.p;
+    d.src_c[0] = L.cout;
+    d.src_taps[0] = 9;
+    d.B = B;
+    d.H = Ho;
+    d.W = Wo;
+    d.Cout = L.cout;
+    d.wpacked = L.w2;
+    d.out = out->p;
+    d.ab_format = fmt;
+    if (L.has_skip) {
+      if (L.mode != kResampleNone) return fail(kUnsupported, "resampling ResBlock with channel change");
+      d.src[d.num_src] = a0.p;
+      d.src_c[d.num_src] = a0.C;
+      d.src_taps[d.num_src] = 1;
+      d.num_src++;
+      if (a1) {
+        d.src[d.num_src] = a1->p;
+        d.src_c[d.num_src] = a1->C;
+        d.src_taps[d.num_src] = 1;
+        d.num_src++;
+      }
+      d.bias = L.b2sum;
+    } else {
+      if (a1) return fail(kUnsupported, "identity skip over a concatenated input");
+      d.bias = L.b2sum;
+      d.residual = (L.mode != kResampleNone) ? tS.p : a0.p;
+    }
+    push_conv(d, &st);
+    CDDPM_TRY(st);
+  }
+  taps_[L.prefix] = *out;
+  taps_[L.prefix + "/in_conv"] = tH;
+  return kOk;
+}
+
+int UNetEngine::plan_attn(const AttnLayer& L, const ActTensor& x, ActTensor* out, int B) {
+  const int fmt = cfg_.fmt;
+  const int H = x.H, W = x.W, C = L.ch;
+  ActTensor tN, tQ, tA;
+  CDDPM_TRY(act_alloc(&tN, C, H, W, B));
+  CDDPM_TRY(act_alloc(&tQ, 3 * C, H, W, B));
+  CDDPM_TRY(act_alloc(&tA, C, H, W, B));
+  CDDPM_TRY(act_alloc(out, C, H, W, B));
+  float* partial = gn_partial_;
+  CatView v;
+  v.p0 = x.p;
+  v.c0 = C;
+  ops_.push_back([=](cudaStream_t s) { return launch_gn_stats(v, B, H * W, partial, fmt, s); });
+  {
+    GnApplyArgs g;
+    g.x = v;
+    g.B = B;
+    g.H = H;
+    g.W = W;
+    g.partial = partial;
+    g.gamma = L.gn_w;
+    g.beta = L.gn_b;
+    g.silu = 0;
+    g.out = tN.p;
+    g.fmt = fmt;
+    ops_.push_back([=](cudaStream_t s) { return launch_gn_apply(g, s); });
+  }
+  int st = kOk;
+  {
+    ConvDesc d;
+    d.num_src = 1;
+    d.src[0] = tN.p;
+    d.src_c[0] = C;
+    d.src_taps[0] = 1;
+    d.B = B;
+    d.H = H;
+    d.W = W;
+    d.Cout = 3 * C;
+    d.wpacked = L.wqkv;
+    d.bias = L.bqkv;
+    d.out = tQ.p;
+    d.ab_format = fmt;
+    push_conv(d, &st);
+    CDDPM_TRY(st);
+  }
+  {
+    void* q = tQ.p;
+    void* o = tA.p;
+    ops_.push_back([=](cudaStream_t s) { return launch_attention(q, o, B, H * W, C, fmt, s); });
+  }
+  {
+    ConvDesc d;
+    d.num_src = 1;
+    d.src[0] = tA.p;
+    d.src_c[0] = C;
+    d.src_taps[0] = 1;
+    d.B = B;
+    d.H = H;
+    d.W = W;
+    d.Cout = C;
+    d.wpacked = L.wproj;
+    d.bias = L.bproj;
+    d.residual = x.p;
+    d.out = out->p;
+    d.ab_format = fmt;
+    push_conv(d, &st);
+    CDDPM_TRY(st);
+  }
+  taps_[L.prefix] = *out;
+  taps_[L.prefix + "/qkv"] = tQ;
+  taps_[L.prefix + "/attn"] = tA;
+  return kOk;
+}
+
+int UNetEngine::plan(int B) {
+  free_acts();
+  conv_flops_ = 0;
+  const int fmt = cfg_.fmt;
+  const int mc = cfg_.model_channels;
+  const int H = cfg_.image_h, W = cfg_.image_w;
+  auto falloc = [&](float** p, size_t n) {
+    void* q = nullptr;
+    int st = check_cuda(cudaMalloc(&q, n * sizeof(float) + 256), "cudaMalloc");
+    if (st == kOk) {
+      act_owned_.push_back(q);
+      *p = reinterpret_cast<float*>(q);
+    }
+    return st;
+  };
+  CDDPM_TRY(falloc(&sinus_, static_cast<size_t>(B) * mc));
+  CDDPM_TRY(falloc(&hid_t_, static_cast<size_t>(B) * half_dim_));
+  CDDPM_TRY(falloc(&hid_c_, static_cast<size_t>(B) * half_dim_));
+  CDDPM_TRY(falloc(&emb_act_, static_cast<size_t>(B) * emb_dim_));
+  CDDPM_TRY(falloc(&film_out_, static_cast<size_t>(B) * film_total_));
+  CDDPM_TRY(falloc(&gn_partial_, static_cast<size_t>(B) * kGnMaxChunks * kGnGroups * 2));
+
+  // ---- embedding: emb_act = SiLU([time_embed(sin(t)) | label_emb(cond)]); film = emb_layers(emb_act) for all blocks
+  ops_.push_back([=](cudaStream_t s) { return launch_timestep_embedding(cur_t_, sinus_, B, mc, s); });
+  ops_.push_back([=](cudaStream_t s) {
+    return launch_linear_ex(sinus_, mc, te0_w, te0_b, hid_t_, half_dim_, B, mc, half_dim_, 0, 1, s);
+  });
+  ops_.push_back([=](cudaStream_t s) {
+    return launch_linear_ex(hid_t_, half_dim_, te2_w, te2_b, emb_act_, emb_dim_, B, half_dim_, half_dim_, 0, 1, s);
+  });
+  if (cfg_.num_classes > 0) {
+    const int nc = cfg_.num_classes;
+    ops_.push_back([=](cudaStream_t s) {
+      if (cur_cond_ == nullptr) return fail(kInvalidArgument, "conditioned UNet called without cond");
+      return launch_linear_ex(cur_cond_, nc, le0_w, le0_b, hid_c_, half_dim_, B, nc, half_dim_, 0, 1, s);
+    });
+    ops_.push_back([=](cudaStream_t s) {
+      return launch_linear_ex(hid_c_, half_dim_, le2_w, le2_b, emb_act_ + half_dim_, emb_dim_, B, half_dim_,
+                              half_dim_, 0, 1, s);
+    });
+  }
+  ops_.push_back([=](cudaStream_t s) {
+    return launch_linear_ex(emb_act_, emb_dim_, film_w, film_b, film_out_, film_total_, B, emb_dim_, film_total_, 0, 0, s);
+  });
+
+  // ---- input blocks
+  std::vector<ActTensor> hs;
+  ActTensor h;
+  for (size_t bi = 0; bi < in_blocks_.size(); ++bi) {
+    for (const Layer& l : in_blocks_[bi]) {
+      ActTensor o;
+      if (l.kind == 0) {
+        CDDPM_TRY(act_alloc(&o, mc, H, W, B));
+        void* op = o.p;
+        ops_.push_back([=](cudaStream_t s) { return launch_conv_in(cur_x_, stem_w, stem_b, op, B, H, W, mc, fmt, s); });
+        taps_["input_blocks.0.0"] = o;
+      } else if (l.kind == 1) {
+        CDDPM_TRY(plan_res(res_[l.idx], h, nullptr, &o, B));
+      } else {
+        CDDPM_TRY(plan_attn(attn_[l.idx], h, &o, B));
+      }
+      h = o;
+    }
+    hs.push_back(h);
+  }
+  for (const Layer& l : mid_) {
+    ActTensor o;
+    if (l.kind == 1) {
+      CDDPM_TRY(plan_res(res_[l.idx], h, nullptr, &o, B));
+    } else {
+      CDDPM_TRY(plan_attn(attn_[l.idx], h, &o, B));
+    }
+    h = o;
+  }
+  for (size_t bi = 0; bi < out_blocks_.size(); ++bi) {
+    ActTensor skip = hs.back();
+    hs.pop_back();
+    bool first = true;
+    for (const Layer& l : out_blocks_[bi]) {
+      ActTensor o;
+      if (l.kind == 1) {
+        CDDPM_TRY(plan_res(res_[l.idx], h, first ? &skip : nullptr, &o, B));
+      } else {
+        CDDPM_TRY(plan_attn(attn_[l.idx], h, &o, B));
+      }
+      first = false;
+      h = o;
+    }
+  }
+  // ---- head: GroupNorm + SiLU + conv 3x3 -> 1 channel, fp32 NCHW
+  {
+    ActTensor tN;
+    CDDPM_TRY(act_alloc(&tN, h.C, h.H, h.W, B));
+    CatView v;
+    v.p0 = h.p;
+    v.c0 = h.C;
+    float* partial = gn_partial_;
+    const int hh = h.H, ww = h.W, cc = h.C;
+    ops_.push_back([=](cudaStream_t s) { return launch_gn_stats(v, B, hh * ww, partial, fmt, s); });
+    GnApplyArgs g;
+    g.x = v;
+    g.B = B;
+    g.H = hh;
+    g.W = ww;
+    g.partial = partial;
+    g.gamma = head_gn_w;
+    g.beta = head_gn_b;
+    g.silu = 1;
+    g.out = tN.p;
+    g.fmt = fmt;
+    ops_.push_back([=](cudaStream_t s) { return launch_gn_apply(g, s); });
+    void* np = tN.p;
+    ops_.push_back([=](cudaStream_t s) { return launch_conv_out(np, head_w, head_b, cur_out_, B, hh, ww, cc, fmt, s); });
+  }
+  planned_B_ = B;
+  return kOk;
+}
+
+int UNetEngine::forward(const float* x, const int64_t* t, const float* cond, float* out, int B, cudaStream_t stream) {
+  if (!x || !t || !out) return fail(kInvalidArgument, "unet_forward: null pointer");
+  if (B < 1) return fail(kInvalidArgument, "unet_forward: empty batch");
+  for (const Param& p : params_)
+    if (!p.set) return fail(kNotReady, "UNet parameter not set: " + p.name);
+  if (B != planned_B_) {
+    // (re)planning allocates; make sure nothing is still running on the old buffers
+    CDDPM_CUDA(cudaDeviceSynchronize());
+    int st = plan(B);
+    if (st != kOk) {
+      free_acts();
+      return st;
+    }
+  }
+  cur_x_ = x;
+  cur_t_ = t;
+  cur_cond_ = cond;
+  cur_out_ = out;
+  for (auto& op : ops_) CDDPM_TRY(op(stream));
+  return kOk;
+}
+
+int UNetEngine::tap(const char* layer, void** ptr, int* C, int* H, int* W) const {
+  auto it = taps_.find(layer);
+  if (it == taps_.end()) return fail(kInvalidArgument, std::string("no such tap: ") + layer);
+  *ptr = it->second.p;
+  *C = it->second.C;
+  *H = it->second.H;
+  *W = it->second.W;
+  return kOk;
+}
+
+int UNetEngine::film(const float** ptr, int* stride) const {
+  *ptr = film_out_;
+  *stride = film_total_;
+  return kOk;
+}
+
+}  // namespace cddpm

@@ -1,0 +1,112 @@
+// The conditioned denoising UNet forward as a pre-planned sequence of sm_100a kernels.
+//
+// Mirrors the module tree of the reference's UNetModel (src/models/modules/OpenAI_Unet.py:483-1006) and speaks its
+// state_dict vocabulary: parameters are pushed by their reference key ("input_blocks.4.0.in_layers.2.weight", ...)
+// as fp32 device arrays and re-laid-out here (16-bit K-major conv panels, concatenated FiLM projection, ...).
+#pragma once
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/cddpm_b200.h"
+#include "common.h"
+#include "conv_igemm.cuh"
+#include "elementwise.cuh"
+
+namespace cddpm {
+
+struct ActTensor {
+  void* p = nullptr;
+  int C = 0, H = 0, W = 0;
+  size_t elems(int B) const { return static_cast<size_t>(B) * H * W * C; }
+};
+
+class UNetEngine {
+ public:
+  ~UNetEngine();
+  int init(const cddpm_unet_config& cfg);
+  int param_count() const { return static_cast<int>(params_.size()); }
+  int param_info(int i, const char** name, int64_t* numel) const;
+  int set_param(const char* name, const float* dev_ptr, int64_t numel, cudaStream_t stream);
+  int forward(const float* x, const int64_t* t, const float* cond, float* out, int B, cudaStream_t stream);
+  int tap(const char* layer, void** ptr, int* C, int* H, int* W) const;
+  int film(const float** ptr, int* stride) const;
+  int64_t conv_flops_per_sample() const { return conv_flops_; }
+  int launches_per_forward() const { return static_cast<int>(ops_.size()); }
+  int fmt() const { return cfg_.fmt; }
+
+ private:
+  struct Param {
+    std::string name;
+    int64_t numel = 0;
+    bool set = false;
+    std::function<int(const float*, cudaStream_t)> load;
+  };
+  struct ResLayer {
+    std::string prefix;
+    int cin = 0, cout = 0, mode = 0, film_off = 0;
+    bool has_skip = false;
+    float *gn1_w = nullptr, *gn1_b = nullptr, *gn2_w = nullptr, *gn2_b = nullptr;
+    void *w1 = nullptr, *w2 = nullptr;
+    float *b1 = nullptr, *b2 = nullptr, *bskip = nullptr, *b2sum = nullptr;
+    int in_c0 = 0, in_c1 = 0;  // channel split of the (possibly concatenated) block input
+  };
+  struct AttnLayer {
+    std::string prefix;
+    int ch = 0;
+    float *gn_w = nullptr, *gn_b = nullptr, *bqkv = nullptr, *bproj = nullptr;
+    void *wqkv = nullptr, *wproj = nullptr;
+  };
+  struct Layer {
+    int kind = 0;  // 0 stem conv, 1 res, 2 attn
+    int idx = 0;
+  };
+
+  template <typename T>
+  int dalloc(T** p, size_t n);
+  int add_param(const std::string& name, int64_t numel, std::function<int(const float*, cudaStream_t)> load);
+  int add_copy_param(const std::string& name, int64_t numel, float** dst);
+  int build_layers();
+  int add_res(const std::string& prefix, int c0, int c1, int cout, int mode);
+  int add_attn(const std::string& prefix, int ch);
+  int plan(int B);
+  int plan_res(const ResLayer& L, const ActTensor& a0, const ActTensor* a1, ActTensor* out, int B);
+  int plan_attn(const AttnLayer& L, const ActTensor& x, ActTensor* out, int B);
+  int act_alloc(ActTensor* t, int C, int H, int W, int B, bool scratch_f32 = false);
+  void free_acts();
+  void push_conv(const ConvDesc& d, int* status);
+
+  cddpm_unet_config cfg_{};
+  int emb_dim_ = 0, half_dim_ = 0, film_total_ = 0;
+  std::vector<Param> params_;
+  std::map<std::string, int> param_index_;
+  std::vector<void*> owned_;       // parameter-side allocations
+  std::vector<void*> act_owned_;   // activation-side allocations (re-planned when B changes)
+  std::vector<ResLayer> res_;
+  std::vector<AttnLayer> attn_;
+  std::vector<std::vector<Layer>> in_blocks_, out_blocks_;
+  std::vector<Layer> mid_;
+  std::vector<int> in_block_ch_;
+  // embedding parameters
+  float *te0_w = nullptr, *te0_b = nullptr, *te2_w = nullptr, *te2_b = nullptr;
+  float *le0_w = nullptr, *le0_b = nullptr, *le2_w = nullptr, *le2_b = nullptr;
+  float *film_w = nullptr, *film_b = nullptr;
+  float *stem_w = nullptr, *stem_b = nullptr, *head_gn_w = nullptr, *head_gn_b = nullptr, *head_w = nullptr,
+        *head_b = nullptr;
+  // per-forward bindings
+  const float* cur_x_ = nullptr;
+  const int64_t* cur_t_ = nullptr;
+  const float* cur_cond_ = nullptr;
+  float* cur_out_ = nullptr;
+  // plan
+  int planned_B_ = 0;
+  std::vector<std::function<int(cudaStream_t)>> ops_;
+  std::map<std::string, ActTensor> taps_;
+  float *sinus_ = nullptr, *hid_t_ = nullptr, *hid_c_ = nullptr, *emb_act_ = nullptr, *film_out_ = nullptr,
+        *gn_partial_ = nullptr;
+  int64_t conv_flops_ = 0;
+};
+
+}  // namespace cddpm

@@ -34,6 +34,8 @@ extern "C" {
 const char* cddpm_last_error(void);
 /* Library version string, e.g. "cddpm_b200 0.1 (sm_100a)". */
 const char* cddpm_version(void);
+/* Stream-ordered device-to-device copy (lets hosts without a CUDA runtime binding read engine-owned buffers). */
+int cddpm_memcpy_d2d(void* dst, const void* src, int64_t nbytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Convolution (nn.Conv2d 3x3 pad 1 / 1x1, stride 1): OpenAI_Unet.py:231,257,268 (ResBlock in/out/skip convs),
@@ -51,6 +53,108 @@ int cddpm_pack_conv_weight(const float* w_oihw, int cout, int cin_total, int ksi
 int cddpm_conv_igemm(int num_src, const void* const* src, const int* src_c, const int* src_taps, int B, int H,
                      int W, int cout, const void* wpacked, const float* bias, const void* residual, void* out,
                      int out_f32, int fmt, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Bandwidth-bound UNet pieces, exposed one by one for the parity tests.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* GroupNorm32 (util.py:214-216) over an NHWC 16-bit tensor that may be the channel concat of two tensors
+ * (th.cat([h, hs.pop()], 1), OpenAI_Unet.py:948), fused with the FiLM modulation h*(1+scale)+shift
+ * (OpenAI_Unet.py:325-331; film = [B][film_stride] fp32 with scale at film_off+c, shift at film_off+C+c, or NULL),
+ * SiLU (silu != 0) and the ResBlock resampling (mode 0 none, 1 nearest x2 (Upsample :115-129), 2 avg-pool 2
+ * (Downsample :172-179)).  raw_out (optional) receives the un-normalised input resampled the same way (x_upd).
+ * workspace: at least cddpm_gn_workspace_floats(B, H*W) floats. */
+int64_t cddpm_gn_workspace_floats(int B, int HW);
+int cddpm_groupnorm_film_silu(const void* x0, int c0, const void* x1, int c1, int B, int H, int W,
+                              const float* gamma, const float* beta, const float* film, int film_stride,
+                              int film_off, int silu, int mode, void* out, void* raw_out, float* workspace, int fmt,
+                              void* stream);
+
+/* nn.Linear on fp32 rows with optional SiLU on the input and/or output (time_embed / label_emb / emb_layers,
+ * OpenAI_Unet.py:583-602, :245-251). */
+int cddpm_linear(const float* in, int in_stride, const float* w, const float* bias, float* out, int out_stride,
+                 int B, int I, int O, int silu_in, int silu_out, void* stream);
+/* timestep_embedding (util.py:151-171): emb[B][dim] = [cos(t f_i) | sin(t f_i)]. */
+int cddpm_timestep_embedding(const int64_t* t, float* emb, int B, int dim, void* stream);
+
+/* QKVAttention.forward (OpenAI_Unet.py:457-476) on the NHWC output of the qkv 1x1 conv: qkv [B,L,3C] -> [B,L,C]. */
+int cddpm_attention(const void* qkv, void* out, int B, int L, int C, int fmt, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * UNet engine: UNetModel.__init__/forward (OpenAI_Unet.py:513-797, :823-1006) behind the reference's state_dict keys.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct cddpm_unet_config {
+  int image_h, image_w;
+  int in_channels, model_channels, out_channels;
+  int num_res_blocks;
+  int n_mult;
+  int channel_mult[8];
+  int n_attn_res;
+  int attention_resolutions[8];
+  int num_classes;       /* 0 = unconditioned (num_classes=None) */
+  int num_head_channels; /* 64 */
+  int fmt;               /* CDDPM_FMT_BF16 | CDDPM_FMT_F16: activation / tensor-core operand type */
+} cddpm_unet_config;
+
+typedef struct cddpm_unet cddpm_unet_t;
+
+int cddpm_unet_create(const cddpm_unet_config* cfg, cddpm_unet_t** out);
+void cddpm_unet_destroy(cddpm_unet_t* h);
+/* Parameters in the reference's registration order; names are the reference's state_dict keys under diffusion.model. */
+int cddpm_unet_param_count(const cddpm_unet_t* h);
+int cddpm_unet_param_info(const cddpm_unet_t* h, int index, const char** name, int64_t* numel);
+/* Copy / re-layout one fp32 parameter (device pointer, reference shape, contiguous) into the engine. */
+int cddpm_unet_set_param(cddpm_unet_t* h, const char* name, const float* value, int64_t numel, void* stream);
+/* model(x, timesteps, cond): x [B,1,H,W] fp32, t [B] int64, cond [B,num_classes] fp32 or NULL -> out [B,1,H,W] fp32. */
+int cddpm_unet_forward(cddpm_unet_t* h, const float* x, const int64_t* t, const float* cond, float* out, int B,
+                       void* stream);
+/* Output buffer (NHWC 16-bit, valid until the next forward) of a layer of the last forward, by module path,
+ * e.g. "input_blocks.3.0", "middle_block.1", "output_blocks.7.1"; "<res>/in_conv", "<attn>/qkv", "<attn>/attn". */
+int cddpm_unet_tap(const cddpm_unet_t* h, const char* layer, void** ptr, int* C, int* H, int* W);
+/* FiLM projections of the last forward: [B][stride] fp32 (all emb_layers outputs, concatenated in module order). */
+int cddpm_unet_film(const cddpm_unet_t* h, const float** ptr, int* stride);
+/* Algorithmic tensor-core FLOPs of the implicit-GEMM convolutions per sample, and kernel launches per forward. */
+int64_t cddpm_unet_conv_flops(const cddpm_unet_t* h);
+int cddpm_unet_launches(const cddpm_unet_t* h);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * gen_noise (src/utils/generate_noise.py:8-52): OpenSimplex-2D fractal field (octaves 6, persistence 0.8,
+ * frequency 64 in the reference), bit-identical to the reference's float64 numba code.  perm_host is the 256-entry
+ * permutation of generate_noise.py:214-232 in HOST memory.  out_f16 [B,1,H,W] (same field for every b) and/or
+ * out_f32 [H,W]; either may be NULL.
+ * ---------------------------------------------------------------------------------------------------------- */
+int cddpm_simplex_noise(const uint8_t* perm_host, void* out_f16, float* out_f32, int B, int H, int W, int octaves,
+                        double persistence, double frequency, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * DDPM arithmetic around the UNet: GaussianDiffusion (src/models/modules/cond_DDPM.py).
+ * Images are [B,1,H,W] fp32 (HW = H*W contiguous per sample); noise is fp16 (gen_noise(...).half(),
+ * generate_noise.py:12) when noise_f16 != 0, else fp32; schedule arrays are the module's fp32 [T] buffers.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* q_sample (cond_DDPM.py:548-554), optionally fused with normalize_to_neg_one_to_one (:75, :653).
+ * t is [B] int64, or a single shared index when t_shared != 0 (p_sample_loop's torch.tensor([T]), :452). */
+int cddpm_q_sample(const float* img, const void* noise, int noise_f16, float* out, const float* sqrt_alphas_cumprod,
+                   const float* sqrt_one_minus_alphas_cumprod, const int64_t* t, int t_shared, int B, int HW,
+                   int normalize, void* stream);
+
+/* p_sample (cond_DDPM.py:432-444): model_predictions (:400-420, clip to [-1,1]) + q_posterior (:391-398) +
+ * sigma_t * noise for t > 0.  noise may be NULL (t == 0).  pred_noise selects the objective.  final_unnormalize
+ * applies unnormalize_to_zero_to_one (:78, :463) to the result of the last step. */
+int cddpm_posterior_step(const float* model_out, const float* x_t, const void* noise, int noise_f16, float* x_prev,
+                         const float* posterior_mean_coef1, const float* posterior_mean_coef2,
+                         const float* posterior_log_variance_clipped, const float* sqrt_recip_alphas_cumprod,
+                         const float* sqrt_recipm1_alphas_cumprod, int64_t t, int B, int HW, int pred_noise,
+                         int final_unnormalize, void* stream);
+
+/* Tail of p_losses (cond_DDPM.py:636-645): reco = reco*reco_beta + reco_alpha * unnormalize(model_out) (pred_x0) or
+ * unnormalize(x_t - sqrt(1-acp)*model_out) (pred_noise, as the reference computes it); loss[b] = mean |out-target|
+ * (l2: squared) * p2_loss_weight[t_b].  reco / loss may be NULL.  The alpha/beta pair folds the test-time ensemble
+ * mean (DDPM_2D.py:225-238) into the same pass. */
+int cddpm_recon_finish(const float* model_out, const float* img, const float* x_t, const void* noise, int noise_f16,
+                       float* reco, float reco_alpha, float reco_beta, float* loss,
+                       const float* sqrt_one_minus_alphas_cumprod, const float* p2_loss_weight, const int64_t* t,
+                       int t_shared, int B, int HW, int pred_noise, int l2, void* stream);
 
 #ifdef __cplusplus
 }
