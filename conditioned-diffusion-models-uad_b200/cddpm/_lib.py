@@ -33,6 +33,12 @@ class UNetConfig(ctypes.Structure):
     ]
 
 
+class VolView(ctypes.Structure):
+    """struct cddpm_vol_view: a float32 volume addressed as (y, x, d) with element strides."""
+
+    _fields_ = [("ptr", ctypes.c_void_p), ("sy", ctypes.c_int64), ("sx", ctypes.c_int64), ("sd", ctypes.c_int64)]
+
+
 _lib: Optional[ctypes.CDLL] = None
 
 
@@ -40,6 +46,7 @@ def _signatures(c):
     """(restype, argtypes) of every symbol include/cddpm_b200.h declares, in header order."""
     vp, i32, i64, f32 = c.c_void_p, c.c_int, c.c_int64, c.c_float
     pvp, pi32 = c.POINTER(vp), c.POINTER(i32)
+    pview = c.POINTER(VolView)
     return {
         "cddpm_last_error": (c.c_char_p, []),
         "cddpm_version": (c.c_char_p, []),
@@ -67,6 +74,14 @@ def _signatures(c):
         "cddpm_posterior_step": (i32, [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]),
         "cddpm_recon_finish": (
             i32, [vp, vp, vp, vp, i32, vp, f32, f32, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+        "cddpm_residual_erode": (i32, [pview, pview, pview, pview, i32, i32, i32, i32, i32, vp, vp, vp]),
+        "cddpm_median3d": (i32, [vp, vp, i32, i32, i32, i32, vp]),
+        "cddpm_max": (i32, [vp, i64, vp, vp]),
+        "cddpm_threshold_counts": (i32, [vp, pview, i32, i32, i32, c.POINTER(f32), i32, vp, vp]),
+        "cddpm_threshold_mask": (i32, [vp, i64, f32, vp, vp]),
+        "cddpm_row_stats": (i32, [vp, pview, pview, i32, i32, i32, f32, vp, vp, vp]),
+        "cddpm_ranking_workspace_bytes": (i64, [i64]),
+        "cddpm_ranking_metrics": (i32, [vp, pview, i32, i32, i32, vp, i64, vp, vp]),
     }
 
 

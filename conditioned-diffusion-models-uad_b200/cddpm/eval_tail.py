@@ -1,0 +1,531 @@
+"""Drop-in for the model-independent evaluation code of the reference, src/utils/utils_eval.py:
+_test_step (:18-194), _test_end (:196-297), get_eval_dictionary (:324-445), apply_brainmask_volume (:454-460),
+apply_3d_median_filter (:462-464), find_best_val (:508-539), dice (:540-545), compute_roc / compute_prc (:548-557),
+filter_3d_connected_components (:489-503), tpr / fpr (:566-575).
+
+Everything voxel-sized runs on the GPU (residual, eroded-mask multiply, 5x5x5 median, max, Dice counts for the
+threshold bisection, thresholding, row statistics, sort-based AUC / AP): kernels cddpm_residual_erode,
+cddpm_median3d, cddpm_max, cddpm_threshold_counts, cddpm_threshold_mask, cddpm_row_stats, cddpm_ranking_metrics.
+The host keeps only scalar control flow (the bisection decisions, in numpy float32/float64 exactly like the reference)
+and the connected-component filter, which stays on scipy this round.  PNG/wandb logging is out of
+scope.  The quirks of the reference are reproduced on purpose: per-"slice" loops run over image rows (axis 0), the
+confusion-matrix names are permuted (:108), fpr() is FP/(FP+TP) (:572-575).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from ._lib import CddpmError, VolView, check, current_stream, lib, ptr
+
+_EVAL_KEYS = """IDs x reconstructions diffs diffs_volume Segmentation reconstructionTimes latentSpace Age AgeGroup
+l1reconstructionErrors l1recoErrorAll l1recoErrorUnhealthy l1recoErrorHealthy l2recoErrorAll l2recoErrorUnhealthy
+l2recoErrorHealthy l1reconstructionErrorMean l1reconstructionErrorStd l2reconstructionErrors l2reconstructionErrorMean
+l2reconstructionErrorStd HausPerVol TPPerVol FPPerVol FNPerVol TNPerVol TPRPerVol FPRPerVol TPTotal FPTotal FNTotal
+TNTotal TPRTotal FPRTotal PrecisionPerVol RecallPerVol PrecisionPerSlice RecallPerSlice lesionSizePerSlice
+lesionSizePerVol Dice DiceScorePerSlice DiceScorePerVol BestDicePerVol BestThresholdPerVol AUCPerVol AUPRCPerVol
+SpecificityPerVol AccuracyPerVol TPgradELBO FPgradELBO FNgradELBO TNgradELBO TPRgradELBO FPRgradELBO DicegradELBO
+DiceScorePerVolgradELBO BestDicePerVolgradELBO BestThresholdPerVolgradELBO AUCPerVolgradELBO AUPRCPerVolgradELBO
+KLD_to_learned_prior AUCAnomalyCombPerSlice AUPRCAnomalyCombPerSlice AnomalyScoreCombPerSlice AUCAnomalyKLDPerSlice
+AUPRCAnomalyKLDPerSlice AnomalyScoreKLDPerSlice AUCAnomalyRecoPerSlice AUPRCAnomalyRecoPerSlice
+AnomalyScoreRecoPerSlice AnomalyScoreRecoBinPerSlice AnomalyScoreAgePerSlice AUCAnomalyAgePerSlice
+AUPRCAnomalyAgePerSlice labelPerSlice labelPerVol AnomalyScoreCombPerVol AnomalyScoreCombiPerVol
+AnomalyScoreCombMeanPerVol AnomalyScoreRegPerVol AnomalyScoreRegMeanPerVol AnomalyScoreRecoPerVol
+AnomalyScoreCombPriorPerVol AnomalyScoreCombiPriorPerVol AnomalyScoreAgePerVol AnomalyScoreRecoMeanPerVol
+DiceScoreKLPerVol DiceScoreKLCombPerVol BestDiceKLCombPerVol BestDiceKLPerVol AUCKLCombPerVol AUPRCKLCombPerVol
+AUCKLPerVol AUPRCKLPerVol TPKLCombPerVol FPKLCombPerVol TNKLCombPerVol FNKLCombPerVol TPRKLCombPerVol FPRKLCombPerVol
+TPKLPerVol FPKLPerVol TNKLPerVol FNKLPerVol TPRKLPerVol FPRKLPerVol""".split()
+
+
+def get_eval_dictionary():
+    return {k: [] for k in _EVAL_KEYS}
+
+
+# ------------------------------------------------------------------------------------------------ device helpers
+def _as_cuda_f32(t, device=None) -> torch.Tensor:
+    if isinstance(t, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(t))
+    if not torch.is_tensor(t):
+        raise CddpmError("expected a tensor or ndarray")
+    if not t.is_cuda:
+        if device is None:
+            raise CddpmError("the anomaly-scoring tail runs on CUDA tensors (there is no CPU path)")
+        t = t.to(device)
+    return t if t.dtype == torch.float32 else t.float()
+
+
+def _view3(t: torch.Tensor) -> Tuple[VolView, Tuple[int, int, int], torch.Tensor]:
+    """(view, (H, W, D), keep-alive) for a [.., H, W, D] tensor whose leading dims are singletons."""
+    while t.dim() > 3 and t.shape[0] == 1:
+        t = t[0]
+    if t.dim() != 3:
+        raise CddpmError(f"expected a [1,1,H,W,D] / [H,W,D] volume, got {tuple(t.shape)}")
+    sy, sx, sd = t.stride()
+    return VolView(t.data_ptr(), sy, sx, sd), tuple(t.shape), t
+
+
+class _Volume:
+    """Device state of one evaluated volume: filtered residual in [D,H,W] order plus the seg / mask views."""
+
+    def __init__(self, diff_dhw: torch.Tensor, seg: torch.Tensor, mask: torch.Tensor, shape):
+        self.diff = diff_dhw
+        self.seg = seg
+        self.mask = mask
+        self.shape = shape  # (H, W, D)
+
+    @property
+    def seg_view(self):
+        return _view3(self.seg)[0]
+
+    @property
+    def mask_view(self):
+        return _view3(self.mask)[0]
+
+    def diff_hwd(self) -> torch.Tensor:
+        return self.diff.permute(1, 2, 0)
+
+
+def residual_and_filter(final_volume, data_orig, data_seg, data_mask, *, erode=True, median=True, kernelsize=5):
+    """Steps (i)-(v) of _test_step: |orig - reco|, l1/l2 error sums, eroded-mask multiply, 3-D median.
+    Returns (_Volume, sums[7] float64 numpy)."""
+    orig = _as_cuda_f32(data_orig)
+    dev = orig.device
+    reco = _as_cuda_f32(final_volume, dev)
+    seg = _as_cuda_f32(data_seg, dev)
+    mask = _as_cuda_f32(data_mask, dev)
+    vo, shape, orig = _view3(orig)
+    vr, shape_r, reco = _view3(reco)
+    vs, _, seg = _view3(seg)
+    vm, _, mask = _view3(mask)
+    if shape_r != shape or tuple(seg.shape) != shape or tuple(mask.shape) != shape:
+        raise CddpmError(f"volume shapes differ: {shape} {shape_r} {tuple(seg.shape)} {tuple(mask.shape)}")
+    H, W, D = shape
+    with torch.cuda.device(dev):
+        a = torch.empty(D, H, W, dtype=torch.float32, device=dev)
+        sums = torch.empty(7, dtype=torch.float64, device=dev)
+        check(lib().cddpm_residual_erode(ctypes.byref(vo), ctypes.byref(vr), ctypes.byref(vs), ctypes.byref(vm), H, W, D,
+                                         W // 25, 1 if erode else 0, ptr(a), ptr(sums), current_stream()),
+              "cddpm_residual_erode")
+        if median:
+            b = torch.empty_like(a)
+            check(lib().cddpm_median3d(ptr(a), ptr(b), H, W, D, int(kernelsize), current_stream()), "cddpm_median3d")
+            a = b
+    return _Volume(a, seg, mask, shape), sums.cpu().numpy()
+
+
+def apply_brainmask_volume(vol, mask_vol, erode=True, iterations=10):
+    """[.. H, W, D] residual x eroded brain mask; like the reference, `erode`/`iterations` are ignored (W // 25 cross
+    erosions are always applied) and the result is written back into `vol` when it is a tensor."""
+    v = _as_cuda_f32(vol)
+    m = _as_cuda_f32(mask_vol, v.device)
+    vv, shape, v3 = _view3(v)
+    vm, _, m3 = _view3(m)
+    H, W, D = shape
+    zero = torch.zeros_like(v3)
+    vz, _, zero = _view3(zero)
+    out = torch.empty(D, H, W, dtype=torch.float32, device=v.device)
+    with torch.cuda.device(v.device):
+        # |v - 0| == v for the non-negative residuals this is applied to; negative inputs are handled by the sign fix
+        check(lib().cddpm_residual_erode(ctypes.byref(vv), ctypes.byref(vz), None, ctypes.byref(vm), H, W, D, W // 25,
+                                         1, ptr(out), None, current_stream()), "cddpm_residual_erode")
+    res = out.permute(1, 2, 0)
+    res = torch.where(v3 < 0, -res, res)
+    if torch.is_tensor(vol) and vol.is_cuda:
+        vol.squeeze().copy_(res)
+        return vol
+    return res
+
+
+def apply_3d_median_filter(volume, kernelsize=5):
+    """scipy.ndimage.median_filter(volume, (k,k,k)) (mode 'reflect') for a [H,W,D] CUDA tensor / ndarray."""
+    is_np = isinstance(volume, np.ndarray)
+    v = _as_cuda_f32(volume, "cuda" if is_np else None).squeeze()
+    H, W, D = v.shape
+    src = v.permute(2, 0, 1).contiguous()
+    dst = torch.empty_like(src)
+    with torch.cuda.device(v.device):
+        check(lib().cddpm_median3d(ptr(src), ptr(dst), H, W, D, int(kernelsize), current_stream()), "cddpm_median3d")
+    out = dst.permute(1, 2, 0)
+    return out.cpu().numpy() if is_np else out
+
+
+# ------------------------------------------------------------------------------------------------ threshold search
+def dice(P, G):
+    psum = np.sum(P.flatten())
+    gsum = np.sum(G.flatten())
+    pgsum = np.sum(np.multiply(P.flatten(), G.flatten()))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return (2 * pgsum) / (psum + gsum)
+
+
+def _dice_counts(p, g, pg):
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return (2 * np.int64(pg)) / (np.int64(p) + np.int64(g))
+
+
+def _counts(vols: Sequence[_Volume], qs: Sequence[float], reduce_fn=None):
+    """[#g, #p0, #pg0, #p1, #pg1] summed over `vols` (and over ranks when reduce_fn is given)."""
+    dev = vols[0].diff.device
+    with torch.cuda.device(dev):
+        cnt = torch.zeros(1 + 2 * len(qs), dtype=torch.int64, device=dev)
+        q = (ctypes.c_float * len(qs))(*[float(v) for v in qs])
+        for v in vols:
+            H, W, D = v.shape
+            sv = v.seg_view
+            check(lib().cddpm_threshold_counts(ptr(v.diff), ctypes.byref(sv), H, W, D, q, len(qs), ptr(cnt),
+                                               current_stream()), "cddpm_threshold_counts")
+    if reduce_fn is not None:
+        reduce_fn(cnt)
+    return cnt.cpu().numpy()
+
+
+def _bisect(count_fn, val_range, max_steps):
+    """find_best_val's control flow (utils_eval.py:508-539) with Dice evaluated from integer counts; the range
+    arithmetic stays in numpy scalars so float32/float64 promotion matches the reference."""
+    bottom, top = val_range
+    max_val, max_point = 0, 0
+    for _ in range(max_steps):
+        if bottom == top:
+            top = 1
+        center = bottom + (top - bottom) * 0.5
+        q_bottom = bottom + (top - bottom) * 0.25
+        q_top = bottom + (top - bottom) * 0.75
+        # the reference compares a float32 image against these scalars: the comparison happens in float32
+        c = count_fn((np.float32(q_bottom), np.float32(q_top)))
+        val_bottom = _dice_counts(c[1], c[0], c[2])
+        val_top = _dice_counts(c[3], c[0], c[4])
+        if val_bottom >= val_top:
+            if val_bottom >= max_val:
+                max_val, max_point = val_bottom, q_bottom
+            top = center
+        else:
+            if val_top >= max_val:
+                max_val, max_point = val_top, q_top
+            bottom = center
+    return max_val, max_point
+
+
+def _device_max(vols: Sequence[_Volume], reduce_fn=None):
+    dev = vols[0].diff.device
+    best = None
+    with torch.cuda.device(dev):
+        out = torch.empty(1, dtype=torch.float32, device=dev)
+        for v in vols:
+            check(lib().cddpm_max(ptr(v.diff), v.diff.numel(), ptr(out), current_stream()), "cddpm_max")
+            best = out.clone() if best is None else torch.maximum(best, out)
+    if reduce_fn is not None:
+        reduce_fn(best)
+    return np.float32(best.item())
+
+
+def find_best_val(x, y, val_range=(0, 1), max_steps=4, step=0, max_val=0, max_point=0):
+    """Dice-optimal threshold by quartile bisection.  x: residual volume (CUDA tensor / ndarray, any shape), y: labels."""
+    if step != 0 or max_val != 0 or max_point != 0:
+        raise NotImplementedError("find_best_val is only ever entered at step 0 by the reference")
+    xv = _as_cuda_f32(x, "cuda").reshape(1, 1, -1)
+    yv = _as_cuda_f32(np.asarray(y, dtype=np.float32) if isinstance(y, np.ndarray) else y, xv.device).reshape(1, 1, -1)
+    vol = _Volume(xv.reshape(-1, 1, 1).contiguous(), yv, yv, (1, 1, xv.numel()))
+    return _bisect(lambda qs: _counts([vol], qs), val_range, max_steps)
+
+
+# ------------------------------------------------------------------------------------------------ ranking metrics
+def _binary_curve(scores: np.ndarray, labels: np.ndarray):
+    order = np.argsort(scores, kind="mergesort")[::-1]
+    s = scores[order]
+    l = labels[order].astype(np.float64)
+    idx = np.r_[np.where(np.diff(s))[0], l.size - 1]
+    tps = np.cumsum(l)[idx]
+    fps = 1 + idx - tps
+    return fps, tps, s[idx]
+
+
+def _roc_curve_host(scores, labels):
+    """sklearn.metrics.roc_curve (drop_intermediate=True) restated for the small host-side uses."""
+    fps, tps, thr = _binary_curve(np.asarray(scores, dtype=np.float64), np.asarray(labels).astype(int))
+    if len(fps) > 2:
+        keep = np.where(np.r_[True, np.logical_or(np.diff(fps, 2), np.diff(tps, 2)), True])[0]
+        fps, tps, thr = fps[keep], tps[keep], thr[keep]
+    tps = np.r_[0, tps]
+    fps = np.r_[0, fps]
+    thr = np.r_[np.inf, thr]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        fpr = fps / fps[-1] if fps[-1] > 0 else np.repeat(np.nan, fps.shape)
+        tpr_ = tps / tps[-1] if tps[-1] > 0 else np.repeat(np.nan, tps.shape)
+    return fpr, tpr_, thr
+
+
+def compute_roc(predictions, labels):
+    """(auc, fpr, tpr, thresholds).  Large CUDA inputs use the device kernel for the AUC; the curve itself is only
+    materialised on the host for small inputs (the reference never reads it for volumes)."""
+    if torch.is_tensor(predictions) and predictions.is_cuda:
+        auc_, _ = _ranking_device(predictions, labels)
+        return auc_, None, None, None
+    fpr, tpr_, thr = _roc_curve_host(np.asarray(predictions), np.asarray(labels))
+    return float(np.trapezoid(tpr_, fpr)), fpr, tpr_, thr
+
+
+def compute_prc(predictions, labels):
+    if torch.is_tensor(predictions) and predictions.is_cuda:
+        _, ap = _ranking_device(predictions, labels)
+        return ap, None, None, None
+    fps, tps, thr = _binary_curve(np.asarray(predictions, dtype=np.float64), np.asarray(labels).astype(int))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        precision = tps / (tps + fps)
+        recall = tps / tps[-1] if tps[-1] > 0 else np.ones_like(tps)
+    precision = np.r_[precision[::-1], 1.0]
+    recall = np.r_[recall[::-1], 0.0]
+    return float(-np.sum(np.diff(recall) * precision[:-1])), precision, recall, thr[::-1]
+
+
+def _ranking_device(x: torch.Tensor, labels) -> Tuple[float, float]:
+    xv = x.float().reshape(-1, 1, 1).contiguous()
+    lv = _as_cuda_f32(np.asarray(labels, dtype=np.float32) if isinstance(labels, np.ndarray) else labels, x.device)
+    vol = _Volume(xv, lv.reshape(1, 1, -1), lv.reshape(1, 1, -1), (1, 1, xv.numel()))
+    return _ranking_volume(vol)
+
+
+def _ranking_volume(v: _Volume) -> Tuple[float, float]:
+    H, W, D = v.shape
+    n = H * W * D
+    dev = v.diff.device
+    with torch.cuda.device(dev):
+        nbytes = int(lib().cddpm_ranking_workspace_bytes(n))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        res = torch.empty(2, dtype=torch.float64, device=dev)
+        sv = v.seg_view
+        check(lib().cddpm_ranking_metrics(ptr(v.diff), ctypes.byref(sv), H, W, D, ptr(ws), nbytes, ptr(res),
+                                          current_stream()), "cddpm_ranking_metrics")
+    r = res.cpu().numpy()
+    return float(r[0]), float(r[1])
+
+
+def tpr(P, G):
+    tp = np.sum(np.multiply(P.flatten(), G.flatten()))
+    fn = np.sum(np.multiply(np.invert(P.flatten()), G.flatten()))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return tp / (tp + fn)
+
+
+def fpr(P, G):
+    tp = np.sum(np.multiply(P.flatten(), G.flatten()))
+    fp = np.sum(np.multiply(P.flatten(), np.invert(G.flatten())))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return fp / (fp + tp)
+
+
+def filter_3d_connected_components(volume):
+    """26-connected components whose hole-filled size is <= 7 are removed (utils_eval.py:489-503).  Host scipy this
+    round; scikit-image's exact `filled_area` is not available in this image (parity unpinned for this step)."""
+    from scipy import ndimage
+
+    vol = np.array(volume.cpu() if torch.is_tensor(volume) else volume, dtype=bool)
+    shape = vol.shape
+    if vol.ndim > 3:
+        vol = vol.reshape(shape[0] * shape[1], shape[2], shape[3])
+    lab, _ = ndimage.label(vol, structure=np.ones((3, 3, 3)))
+    for i, sl in enumerate(ndimage.find_objects(lab)):
+        if sl is None:
+            continue
+        region = lab[sl] == (i + 1)
+        if int(ndimage.binary_fill_holes(region).sum()) <= 7:
+            vol[sl][region] = False
+    return vol.reshape(shape)
+
+
+# ------------------------------------------------------------------------------------------------ _test_step / _test_end
+def _dist_sum(t: torch.Tensor):
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+
+def _dist_max(t: torch.Tensor):
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+
+
+def _test_step(self, final_volume, data_orig, data_seg, data_mask, batch_idx, ID, label_vol):
+    self.healthy_sets = ["IXI"]
+    cfg = self.cfg
+    if not cfg.resizedEvaluation:
+        raise NotImplementedError("full-resolution evaluation (trilinear resize to new_size) belongs to the "
+                                  "datamodule side (SURVEY.md §8 f-3); use resizedEvaluation=True")
+    vol, sums = residual_and_filter(final_volume, data_orig, data_seg, data_mask, erode=bool(cfg["erodeBrainmask"]),
+                                    median=bool(cfg["medianFiltering"]), kernelsize=cfg.get("kernelsize_median", 5))
+    H, W, D = vol.shape
+    n = H * W * D
+    n_les = sums[6]
+    ed = self.eval_dict
+    with np.errstate(invalid="ignore", divide="ignore"):
+        ed["l1recoErrorAll"].append(float(sums[0] / n))
+        ed["l1recoErrorUnhealthy"].append(float(np.float64(sums[2]) / n_les))
+        ed["l1recoErrorHealthy"].append(float(sums[4] / (n - n_les)))
+        ed["l2recoErrorAll"].append(float(sums[1] / n))
+        ed["l2recoErrorUnhealthy"].append(float(np.float64(sums[3]) / n_les))
+        ed["l2recoErrorHealthy"].append(float(sums[5] / (n - n_les)))
+    if cfg["saveOutputImages"]:
+        raise NotImplementedError("PNG / wandb image logging is out of scope (I/O); run with saveOutputImages=False")
+
+    dev = vol.diff.device
+    best_thresh = None
+    if cfg.evalSeg and self.dataset[0] not in self.healthy_sets:
+        AUC, AUPRC = _ranking_volume(vol)
+        top = _device_max([vol])
+        bestDice, bestThresh = _bisect(lambda qs: _counts([vol], qs), (0, top), 10)
+        if "test" in self.stage:
+            bestThresh = self.threshold["total"]
+        thr = bestThresh if cfg["threshold"] == "auto" else cfg["threshold"]
+        with torch.cuda.device(dev):
+            tmask = torch.empty(D, H, W, dtype=torch.uint8, device=dev)
+            check(lib().cddpm_threshold_mask(ptr(vol.diff), n, float(np.float32(thr)), ptr(tmask), current_stream()),
+                  "cddpm_threshold_mask")
+        pred = tmask.cpu().numpy().astype(bool)  # [D,H,W]
+        if "node" not in self.dataset[0].lower():
+            pred = filter_3d_connected_components(pred)
+        g = (vol.seg.permute(2, 0, 1) > 0).cpu().numpy()  # [D,H,W]
+        p_, g_ = pred.ravel(), g.ravel()
+        c11 = int(np.count_nonzero(p_ & g_))
+        c10 = int(np.count_nonzero(p_ & ~g_))
+        c01 = int(np.count_nonzero(~p_ & g_))
+        c00 = int(p_.size - c11 - c10 - c01)
+        diceScore = _dice_counts(c11 + c10, c11 + c01, c11)
+        # confusion_matrix(pred, truth).ravel() unpacked as TP, FP, TN, FN by the reference (:108)
+        TP, FP, TN, FN = c00, c01, c10, c11
+        with np.errstate(invalid="ignore", divide="ignore"):
+            TPR = np.int64(c11) / (np.int64(c11) + np.int64(c01))
+            FPR = np.int64(c10) / (np.int64(c10) + np.int64(c11))
+        ed["lesionSizePerVol"].append(int(np.count_nonzero(g_)))
+        ed["DiceScorePerVol"].append(diceScore)
+        ed["BestDicePerVol"].append(bestDice)
+        ed["BestThresholdPerVol"].append(bestThresh)
+        ed["AUCPerVol"].append(AUC)
+        ed["AUPRCPerVol"].append(AUPRC)
+        ed["TPPerVol"].append(TP)
+        ed["FPPerVol"].append(FP)
+        ed["TNPerVol"].append(TN)
+        ed["FNPerVol"].append(FN)
+        ed["TPRPerVol"].append(TPR)
+        ed["FPRPerVol"].append(FPR)
+        ed["IDs"].append(ID[0])
+        ed["AccuracyPerVol"].append((c11 + c00) / p_.size)
+        ed["PrecisionPerVol"].append(c11 / (c11 + c10) if (c11 + c10) else 0.0)
+        ed["RecallPerVol"].append(c11 / (c11 + c01) if (c11 + c01) else 0.0)
+        ed["SpecificityPerVol"].append(TN / (TN + FP + 0.0000001))
+        ed["HausPerVol"].append(float("nan"))  # monai Hausdorff: SURVEY.md §8 f-4, reported as NaN
+        best_thresh = bestThresh
+
+    # row ("slice") statistics in one pass: Dice / precision / recall per row with lesion, masked mean residual per row
+    thr_rows = float(np.float32(best_thresh)) if best_thresh is not None else float("inf")
+    with torch.cuda.device(dev):
+        rows = torch.empty(H, 4, dtype=torch.int64, device=dev)
+        rowsum = torch.empty(H, dtype=torch.float64, device=dev)
+        sv, mv = vol.seg_view, vol.mask_view
+        check(lib().cddpm_row_stats(ptr(vol.diff), ctypes.byref(sv), ctypes.byref(mv), H, W, D, thr_rows, ptr(rows),
+                                    ptr(rowsum), current_stream()), "cddpm_row_stats")
+    rows_h = rows.cpu().numpy()
+    rowsum_h = rowsum.cpu().numpy()
+    if best_thresh is not None:
+        for y in range(H):
+            p, g, pg = (int(v) for v in rows_h[y, :3])
+            if g > 0:
+                ed["DiceScorePerSlice"].append(_dice_counts(p, g, pg))
+                ed["PrecisionPerSlice"].append(pg / p if p else 0.0)
+                ed["RecallPerSlice"].append(pg / g)
+                ed["lesionSizePerSlice"].append(g)
+
+    if "val" in self.stage:
+        if batch_idx == 0 or not isinstance(self.diffs_list, list):
+            self.diffs_list, self.seg_list = [], []
+        self.diffs_list.append(vol)
+        self.seg_list.append(vol.seg)
+
+    n_mask = int(rows_h[:, 3].sum())
+    if cfg.get("use_postprocessed_score", True):
+        score_vol = float(rowsum_h.sum() / n_mask) if n_mask else float("nan")
+    # reconstruction-based anomaly score per image row (0.0 where the row holds no brain), utils_eval.py:158-183
+    score_rows = [float(rowsum_h[y] / rows_h[y, 3]) if rows_h[y, 3] else 0.0 for y in range(H)]
+    label = [1 if rows_h[y, 1] > 0 else 0 for y in range(H)]
+    if self.dataset[0] not in self.healthy_sets:
+        with _quiet():
+            AUCs, _, _, _ = compute_roc(np.array(score_rows), np.array(label))
+            AUPRCs, _, _, _ = compute_prc(np.array(score_rows), np.array(label))
+        ed["AUCAnomalyRecoPerSlice"].append(AUCs)
+        ed["AUPRCAnomalyRecoPerSlice"].append(AUPRCs)
+        ed["labelPerSlice"].extend(label)
+        ed["AnomalyScoreRecoPerSlice"].extend(score_rows)
+    if cfg.get("use_postprocessed_score", True):
+        for k in ("AnomalyScoreRecoPerVol", "AnomalyScoreCombPerVol", "AnomalyScoreCombiPerVol",
+                  "AnomalyScoreCombPriorPerVol", "AnomalyScoreCombiPriorPerVol"):
+            ed[k].append(score_vol)
+    ed["labelPerVol"].append(label_vol.item() if hasattr(label_vol, "item") else label_vol)
+    return vol
+
+
+_MEAN_STD = [
+    ("l1recoErrorAll", "l1recoErrorAll", True), ("l2recoErrorAll", "l2recoErrorAll", True),
+    ("l1recoErrorHealthy", "l1recoErrorHealthy", True), ("l1recoErrorUnhealthy", "l1recoErrorUnhealthy", True),
+    ("l2recoErrorHealthy", "l2recoErrorHealthy", True), ("l2recoErrorUnhealthy", "l2recoErrorUnhealthy", True),
+    ("AUPRCPerVol", "AUPRCPerVol", True), ("AUCPerVol", "AUCPerVol", True), ("DicePerVol", "DiceScorePerVol", True),
+    ("BestDicePerVol", "BestDicePerVol", False), ("BestThresholdPerVol", "BestThresholdPerVol", False),
+    ("TPPerVol", "TPPerVol", True), ("FPPerVol", "FPPerVol", True), ("TNPerVol", "TNPerVol", True),
+    ("FNPerVol", "FNPerVol", True), ("TPRPerVol", "TPRPerVol", True), ("FPRPerVol", "FPRPerVol", True),
+]
+_MEAN_STD_PLAIN = ["PrecisionPerVol", "RecallPerVol", "PrecisionPerSlice", "RecallPerSlice", "AccuracyPerVol",
+                   "SpecificityPerVol"]
+
+
+def _test_end(self):
+    ed = self.eval_dict
+    with np.errstate(invalid="ignore", divide="ignore"), _quiet():
+        for out, src, nan_aware in _MEAN_STD:
+            vals = ed[src]
+            ed[out + "Mean"] = (np.nanmean if nan_aware else np.mean)(vals)
+            ed[out + "Std"] = (np.nanstd if nan_aware else np.std)(vals)
+        haus = np.array(ed["HausPerVol"], dtype=np.float64)
+        haus = haus[np.isfinite(haus)]
+        ed["HausPerVolMean"] = np.nanmean(haus)
+        ed["HausPerVolStd"] = np.nanstd(haus)
+        for k in _MEAN_STD_PLAIN:
+            ed[k + "Mean"] = np.mean(ed[k])
+            ed[k + "Std"] = np.std(ed[k])
+    if "test" in self.stage:
+        del self.threshold
+    if "val" in self.stage:
+        vols: List[_Volume] = list(self.diffs_list) if isinstance(self.diffs_list, list) else []
+        if self.dataset[0] not in self.healthy_sets:
+            # global Dice-optimal threshold over every validation voxel; counts are summed over volumes and, in a
+            # sharded sweep, over ranks — the same decisions as the reference's concatenated arrays (:262-271)
+            top = _device_max(vols, _dist_max)
+            _, bestThresh = _bisect(lambda qs: _counts(vols, qs, _dist_sum), (0, top), 10)
+            self.threshold["total"] = bestThresh
+            if self.cfg.get("KLDBackprop", False):
+                raise NotImplementedError("KLDBackprop thresholds belong to other model families of the reference")
+        else:
+            diffs = np.concatenate([v.diff.permute(1, 2, 0).reshape(-1).cpu().numpy() for v in vols])
+            fpr_h, _, threshs = _roc_curve_host(diffs, np.zeros_like(diffs, dtype=int))
+            self.threshholds_healthy = {
+                "thresh_1p": threshs[np.argmax(fpr_h > 0.01)],
+                "thresh_5p": threshs[np.argmax(fpr_h > 0.05)],
+                "thresh_10p": threshs[np.argmax(fpr_h > 0.10)],
+            }
+            ed["t_1p"] = self.threshholds_healthy["thresh_1p"]
+            ed["t_5p"] = self.threshholds_healthy["thresh_5p"]
+            ed["t_10p"] = self.threshholds_healthy["thresh_10p"]
+
+
+class _quiet:
+    def __enter__(self):
+        import warnings
+
+        self._cm = warnings.catch_warnings()
+        self._cm.__enter__()
+        warnings.simplefilter("ignore")
+
+    def __exit__(self, *a):
+        return self._cm.__exit__(*a)

@@ -7,6 +7,7 @@
 #include "diffusion.cuh"
 #include "elementwise.cuh"
 #include "simplex.cuh"
+#include "tail.cuh"
 #include "unet_engine.cuh"
 
 namespace cddpm {
@@ -143,6 +144,53 @@ int cddpm_simplex_noise(const uint8_t* perm_host, void* out_f16, float* out_f32,
                         double persistence, double frequency, void* stream) {
   return launch_simplex_noise(perm_host, out_f16, out_f32, B, H, W, octaves, persistence, frequency,
                               static_cast<cudaStream_t>(stream));
+}
+
+static VolView to_view(const cddpm_vol_view* v) {
+  VolView o;
+  if (v) {
+    o.p = v->ptr;
+    o.sy = v->sy;
+    o.sx = v->sx;
+    o.sd = v->sd;
+  }
+  return o;
+}
+
+int cddpm_residual_erode(const cddpm_vol_view* orig, const cddpm_vol_view* reco, const cddpm_vol_view* seg,
+                         const cddpm_vol_view* mask, int H, int W, int D, int iterations, int erode,
+                         float* diff_masked_dhw, double* sums, void* stream) {
+  if (!orig || !reco) return fail(kInvalidArgument, "residual_erode: null view");
+  return launch_residual_erode(to_view(orig), to_view(reco), to_view(seg), to_view(mask), H, W, D, iterations, erode,
+                               diff_masked_dhw, sums, static_cast<cudaStream_t>(stream));
+}
+int cddpm_median3d(const float* in_dhw, float* out_dhw, int H, int W, int D, int k, void* stream) {
+  return launch_median3d(in_dhw, out_dhw, H, W, D, k, static_cast<cudaStream_t>(stream));
+}
+int cddpm_max(const float* x, int64_t n, float* out_max, void* stream) {
+  return launch_max(x, n, out_max, static_cast<cudaStream_t>(stream));
+}
+int cddpm_threshold_counts(const float* x_dhw, const cddpm_vol_view* seg, int H, int W, int D, const float* q_host,
+                           int nq, uint64_t* counts, void* stream) {
+  if (!seg) return fail(kInvalidArgument, "threshold_counts: null view");
+  return launch_threshold_counts(x_dhw, to_view(seg), H, W, D, q_host, nq,
+                                 reinterpret_cast<unsigned long long*>(counts), static_cast<cudaStream_t>(stream));
+}
+int cddpm_threshold_mask(const float* x, int64_t n, float thr, uint8_t* out, void* stream) {
+  return launch_threshold_mask(x, n, thr, out, static_cast<cudaStream_t>(stream));
+}
+int cddpm_row_stats(const float* x_dhw, const cddpm_vol_view* seg, const cddpm_vol_view* mask, int H, int W, int D,
+                    float thr, uint64_t* rows, double* rowsum, void* stream) {
+  if (!mask) return fail(kInvalidArgument, "row_stats: null view");
+  return launch_row_stats(x_dhw, to_view(seg), to_view(mask), H, W, D, thr,
+                          reinterpret_cast<unsigned long long*>(rows), rowsum, static_cast<cudaStream_t>(stream));
+}
+int64_t cddpm_ranking_workspace_bytes(int64_t n) { return static_cast<int64_t>(ranking_workspace_bytes(n)); }
+int cddpm_ranking_metrics(const float* x_dhw, const cddpm_vol_view* seg, int H, int W, int D, void* workspace,
+                          int64_t workspace_bytes, double* result, void* stream) {
+  if (!seg) return fail(kInvalidArgument, "ranking_metrics: null view");
+  return launch_ranking_metrics(x_dhw, to_view(seg), H, W, D, workspace, static_cast<size_t>(workspace_bytes), result,
+                                static_cast<cudaStream_t>(stream));
 }
 
 struct cddpm_unet {

@@ -1,0 +1,442 @@
+// Anomaly-scoring tail kernels (see tail.cuh).  The volumes are ~0.5 M voxels: these kernels are latency- and
+// launch-bound, not bandwidth-bound; the win over the reference is removing ~1 s of host scipy/sklearn per volume.
+#include "tail.cuh"
+
+#include <cub/cub.cuh>
+
+namespace cddpm {
+
+namespace {
+
+struct View {
+  const float* p;
+  long long sy, sx, sd;
+  __device__ __forceinline__ float at(int y, int x, int d) const { return p[y * sy + x * sx + d * sd]; }
+};
+View dev_view(const VolView& v) { return View{v.p, v.sy, v.sx, v.sd}; }
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (warp == 0) {
+    r = (lane < (blockDim.x >> 5)) ? sh[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  }
+  return r;  // valid in thread 0
+}
+__device__ __forceinline__ unsigned long long block_sum_u(unsigned long long v, unsigned long long* sh) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  unsigned long long r = 0;
+  if (warp == 0) {
+    r = (lane < (blockDim.x >> 5)) ? sh[lane] : 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  }
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------- residual + erosion
+__global__ void __launch_bounds__(256) residual_erode_kernel(View orig, View reco, View seg, View mask, int H, int W,
+                                                             int D, int iterations, int erode,
+                                                             float* __restrict__ out, double* __restrict__ sums) {
+  __shared__ double sh[8];
+  const long long n = static_cast<long long>(H) * W * D;
+  double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < n;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(idx % W);
+    const int y = static_cast<int>((idx / W) % H);
+    const int d = static_cast<int>(idx / (static_cast<long long>(W) * H));
+    const float o = orig.at(y, x, d), r = reco.at(y, x, d);
+    const float a = fabsf(o - r);
+    const double ad = static_cast<double>(a), sq = static_cast<double>(r - o) * static_cast<double>(r - o);
+    acc[0] += ad;
+    acc[1] += sq;
+    if (seg.p != nullptr && seg.at(y, x, d) > 0.f) {
+      acc[2] += ad;
+      acc[3] += sq;
+      acc[6] += 1.0;
+    } else {
+      acc[4] += ad;
+      acc[5] += sq;
+    }
+    float v = a;
+    if (erode) {
+      bool keep = iterations >= 1;
+      if (keep) {
+        for (int dy = -iterations; dy <= iterations && keep; ++dy) {
+          const int span = iterations - abs(dy);
+          const int yy = y + dy;
+          for (int dx = -span; dx <= span; ++dx) {
+            const int xx = x + dx;
+            if (yy < 0 || yy >= H || xx < 0 || xx >= W || !(mask.at(yy, xx, d) > 0.f)) {
+              keep = false;
+              break;
+            }
+          }
+        }
+      }
+      v = keep ? a : 0.f;
+    }
+    out[idx] = v;
+  }
+  if (sums != nullptr) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      const double t = block_sum(acc[k], sh);
+      if (threadIdx.x == 0) atomicAdd(&sums[k], t);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- 3-D median
+__device__ __forceinline__ uint32_t sort_key(float v) {
+  const uint32_t u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_value(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+__device__ __forceinline__ int reflect(int i, int n) {
+  // scipy 'reflect' == numpy 'symmetric': (d c b a | a b c d | d c b a)
+  if (i < 0) i = -i - 1;
+  if (i >= n) i = 2 * n - i - 1;
+  return min(max(i, 0), n - 1);
+}
+
+template <int K>
+__global__ void __launch_bounds__(256) median3d_kernel(const float* __restrict__ in, float* __restrict__ out, int H,
+                                                       int W, int D) {
+  constexpr int R = K / 2;
+  constexpr int TX = 16, TY = 4, TD = 4;  // 256 output voxels per CTA
+  constexpr int SX = TX + 2 * R, SY = TY + 2 * R, SD = TD + 2 * R;
+  constexpr int NV = K * K * K;
+  constexpr int RANK = NV / 2;
+  __shared__ uint32_t tile[SD][SY][SX];
+  const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY, d0 = blockIdx.z * TD;
+  for (int i = threadIdx.x; i < SD * SY * SX; i += blockDim.x) {
+    const int tx = i % SX, ty = (i / SX) % SY, td = i / (SX * SY);
+    const int gx = reflect(x0 + tx - R, W), gy = reflect(y0 + ty - R, H), gd = reflect(d0 + td - R, D);
+    tile[td][ty][tx] = sort_key(in[(static_cast<size_t>(gd) * H + gy) * W + gx]);
+  }
+  __syncthreads();
+  const int lx = threadIdx.x % TX, ly = (threadIdx.x / TX) % TY, ld = threadIdx.x / (TX * TY);
+  const int x = x0 + lx, y = y0 + ly, d = d0 + ld;
+  if (x >= W || y >= H || d >= D) return;
+  uint32_t key[NV];
+  int zeros = 0;
+  const uint32_t zero_key = 0x80000000u;
+#pragma unroll
+  for (int a = 0; a < K; ++a)
+#pragma unroll
+    for (int b = 0; b < K; ++b)
+#pragma unroll
+      for (int c = 0; c < K; ++c) {
+        const uint32_t kv = tile[ld + a][ly + b][lx + c];
+        key[(a * K + b) * K + c] = kv;
+        zeros += (kv == zero_key);
+      }
+  const size_t oidx = (static_cast<size_t>(d) * H + y) * W + x;
+  // the residual volume is >= 0 and mostly exactly 0 outside the eroded brain mask: then the median is 0 as soon as
+  // more than half of the window is 0 and nothing is negative
+  if (zeros > RANK) {
+    int neg = 0;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) neg += (key[i] < zero_key);
+    if (neg == 0) {
+      out[oidx] = 0.f;
+      return;
+    }
+  }
+  // exact rank selection by radix descent over the 32 key bits
+  uint32_t result = 0;
+  int k = RANK;
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t hi_mask = (bit == 31) ? 0u : (0xFFFFFFFFu << (bit + 1));
+    int cnt0 = 0;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) cnt0 += (((key[i] & hi_mask) == result) && (((key[i] >> bit) & 1u) == 0u));
+    if (k >= cnt0) {
+      k -= cnt0;
+      result |= (1u << bit);
+    }
+  }
+  out[oidx] = key_value(result);
+}
+
+// ---------------------------------------------------------------------------------------------- small reductions
+__global__ void max_key_kernel(const float* __restrict__ x, long long n, unsigned int* __restrict__ out) {
+  unsigned int m = 0;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    m = max(m, sort_key(x[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+__global__ void max_decode_kernel(unsigned int* inout) {
+  const unsigned int k = *inout;
+  *reinterpret_cast<float*>(inout) = key_value(k);
+}
+
+struct QList {
+  float q[4];
+  int nq;
+};
+
+__global__ void __launch_bounds__(256) threshold_counts_kernel(const float* __restrict__ x, View seg, int H, int W,
+                                                               int D, QList ql, unsigned long long* __restrict__ counts) {
+  __shared__ unsigned long long sh[8];
+  const long long n = static_cast<long long>(H) * W * D;
+  unsigned long long c[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < n;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int xx = static_cast<int>(idx % W);
+    const int y = static_cast<int>((idx / W) % H);
+    const int d = static_cast<int>(idx / (static_cast<long long>(W) * H));
+    const bool g = seg.at(y, xx, d) > 0.f;
+    const float v = x[idx];
+    c[0] += g;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (i < ql.nq) {
+        const bool p = v > ql.q[i];
+        c[1 + 2 * i] += p;
+        c[2 + 2 * i] += (p && g);
+      }
+    }
+  }
+  for (int k = 0; k < 1 + 2 * ql.nq; ++k) {
+    const unsigned long long t = block_sum_u(c[k], sh);
+    if (threadIdx.x == 0 && t) atomicAdd(&counts[k], t);
+  }
+}
+
+__global__ void threshold_mask_kernel(const float* __restrict__ x, long long n, float thr, unsigned char* __restrict__ out) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i < n) out[i] = x[i] > thr ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256) row_stats_kernel(const float* __restrict__ x, View seg, View mask, int H, int W,
+                                                        int D, float thr, unsigned long long* __restrict__ rows,
+                                                        double* __restrict__ rowsum) {
+  __shared__ unsigned long long shu[8];
+  __shared__ double shd[8];
+  const int y = blockIdx.x;
+  unsigned long long c[4] = {0, 0, 0, 0};
+  double s = 0.0;
+  for (int i = threadIdx.x; i < W * D; i += blockDim.x) {
+    const int xx = i % W, d = i / W;
+    const float v = x[(static_cast<size_t>(d) * H + y) * W + xx];
+    const bool g = seg.p != nullptr && seg.at(y, xx, d) > 0.f;
+    const bool m = mask.at(y, xx, d) > 0.f;
+    const bool p = v > thr;
+    c[0] += p;
+    c[1] += g;
+    c[2] += (p && g);
+    c[3] += m;
+    if (m) s += static_cast<double>(v);
+  }
+  for (int k = 0; k < 4; ++k) {
+    const unsigned long long t = block_sum_u(c[k], shu);
+    if (threadIdx.x == 0) rows[y * 4 + k] = t;
+  }
+  const double t = block_sum(s, shd);
+  if (threadIdx.x == 0) rowsum[y] = t;
+}
+
+// ---------------------------------------------------------------------------------------------- ranking metrics
+__global__ void gather_scores_kernel(const float* __restrict__ x, View seg, int H, int W, int D,
+                                     float* __restrict__ keys, unsigned int* __restrict__ labels) {
+  const long long n = static_cast<long long>(H) * W * D;
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= n) return;
+  const int xx = static_cast<int>(idx % W);
+  const int y = static_cast<int>((idx / W) % H);
+  const int d = static_cast<int>(idx / (static_cast<long long>(W) * H));
+  keys[idx] = x[idx];
+  labels[idx] = seg.at(y, xx, d) > 0.f ? 1 : 0;
+}
+
+struct MaxOp {
+  __host__ __device__ int operator()(int a, int b) const { return a > b ? a : b; }
+};
+
+__global__ void end_index_kernel(const float* __restrict__ s, int n, int* __restrict__ endidx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const bool end = (i == n - 1) || (s[i] != s[i + 1]);
+  endidx[i] = end ? i : -1;
+}
+
+__global__ void ranking_terms_kernel(const float* __restrict__ s, const unsigned int* __restrict__ tps,
+                                     const int* __restrict__ lastend, int n, double* __restrict__ auc_terms,
+                                     double* __restrict__ ap_terms) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const bool end = (i == n - 1) || (s[i] != s[i + 1]);
+  double a = 0.0, p = 0.0;
+  if (end) {
+    const double P = static_cast<double>(tps[n - 1]);
+    const double N = static_cast<double>(n) - P;
+    const int j = (i > 0) ? lastend[i - 1] : -1;
+    const double tp = tps[i], fp = static_cast<double>(i + 1) - tp;
+    const double tp0 = (j >= 0) ? static_cast<double>(tps[j]) : 0.0;
+    const double fp0 = (j >= 0) ? (static_cast<double>(j + 1) - tp0) : 0.0;
+    a = (fp / N - fp0 / N) * (tp / P + tp0 / P) * 0.5;
+    p = (tp / P - tp0 / P) * (tp / (tp + fp));
+  }
+  auc_terms[i] = a;
+  ap_terms[i] = p;
+}
+
+struct RankingLayout {
+  size_t keys_in, keys_out, lab_in, lab_out, tps, endidx, lastend, auc, ap, cub, total, cub_bytes;
+};
+RankingLayout ranking_layout(int64_t n) {
+  RankingLayout L{};
+  auto align = [](size_t v) { return (v + 255) & ~size_t(255); };
+  size_t off = 0;
+  L.keys_in = off; off = align(off + n * 4);
+  L.keys_out = off; off = align(off + n * 4);
+  L.lab_in = off; off = align(off + n * 4);
+  L.lab_out = off; off = align(off + n * 4);
+  L.tps = off; off = align(off + n * 4);
+  L.endidx = off; off = align(off + n * 4);
+  L.lastend = off; off = align(off + n * 4);
+  L.auc = off; off = align(off + n * 8);
+  L.ap = off; off = align(off + n * 8);
+  size_t b_sort = 0, b_scan = 0, b_scan2 = 0, b_red = 0;
+  cub::DeviceRadixSort::SortPairsDescending(nullptr, b_sort, (const float*)nullptr, (float*)nullptr,
+                                            (const unsigned int*)nullptr, (unsigned int*)nullptr, static_cast<int>(n));
+  cub::DeviceScan::InclusiveSum(nullptr, b_scan, (const unsigned int*)nullptr, (unsigned int*)nullptr,
+                                static_cast<int>(n));
+  cub::DeviceScan::InclusiveScan(nullptr, b_scan2, (const int*)nullptr, (int*)nullptr, MaxOp(), static_cast<int>(n));
+  cub::DeviceReduce::Sum(nullptr, b_red, (const double*)nullptr, (double*)nullptr, static_cast<int>(n));
+  L.cub_bytes = std::max(std::max(b_sort, b_scan), std::max(b_scan2, b_red));
+  L.cub = off;
+  off = align(off + L.cub_bytes);
+  L.total = off;
+  return L;
+}
+
+}  // namespace
+
+int launch_residual_erode(const VolView& orig, const VolView& reco, const VolView& seg, const VolView& mask, int H,
+                          int W, int D, int iterations, int erode, float* diff_masked, double* sums,
+                          cudaStream_t stream) {
+  if (!orig.p || !reco.p || !diff_masked) return fail(kInvalidArgument, "residual: null pointer");
+  if (erode && !mask.p) return fail(kInvalidArgument, "residual: erosion needs the brain mask");
+  if (sums) CDDPM_CUDA(cudaMemsetAsync(sums, 0, 7 * sizeof(double), stream));
+  const long long n = static_cast<long long>(H) * W * D;
+  const int blocks = static_cast<int>(std::min<long long>((n + 255) / 256, 148 * 8));
+  residual_erode_kernel<<<blocks, 256, 0, stream>>>(dev_view(orig), dev_view(reco), dev_view(seg), dev_view(mask), H, W,
+                                                    D, iterations, erode, diff_masked, sums);
+  return check_launch("residual_erode_kernel");
+}
+
+int launch_median3d(const float* in, float* out, int H, int W, int D, int k, cudaStream_t stream) {
+  if (!in || !out) return fail(kInvalidArgument, "median: null pointer");
+  if (in == out) return fail(kInvalidArgument, "median: in-place filtering is not supported");
+  dim3 grid((W + 15) / 16, (H + 3) / 4, (D + 3) / 4);
+  if (k == 5) {
+    median3d_kernel<5><<<grid, 256, 0, stream>>>(in, out, H, W, D);
+  } else if (k == 3) {
+    median3d_kernel<3><<<grid, 256, 0, stream>>>(in, out, H, W, D);
+  } else if (k == 1) {
+    return check_cuda(cudaMemcpyAsync(out, in, static_cast<size_t>(H) * W * D * 4, cudaMemcpyDeviceToDevice, stream),
+                      "median k=1 copy");
+  } else {
+    return fail(kUnsupported, "median: kernel size must be 1, 3 or 5");
+  }
+  return check_launch("median3d_kernel");
+}
+
+int launch_max(const float* x, int64_t n, float* out_max, cudaStream_t stream) {
+  if (!x || !out_max) return fail(kInvalidArgument, "max: null pointer");
+  CDDPM_CUDA(cudaMemsetAsync(out_max, 0, 4, stream));
+  const int blocks = static_cast<int>(std::min<long long>((n + 255) / 256, 148 * 4));
+  max_key_kernel<<<blocks, 256, 0, stream>>>(x, n, reinterpret_cast<unsigned int*>(out_max));
+  max_decode_kernel<<<1, 1, 0, stream>>>(reinterpret_cast<unsigned int*>(out_max));
+  return check_launch("max kernels");
+}
+
+int launch_threshold_counts(const float* x, const VolView& seg, int H, int W, int D, const float* q_host, int nq,
+                            unsigned long long* counts, cudaStream_t stream) {
+  if (!x || !seg.p || !q_host || !counts) return fail(kInvalidArgument, "threshold_counts: null pointer");
+  if (nq < 1 || nq > 4) return fail(kInvalidArgument, "threshold_counts: 1..4 thresholds per call");
+  QList ql{};
+  ql.nq = nq;
+  for (int i = 0; i < nq; ++i) ql.q[i] = q_host[i];
+  const long long n = static_cast<long long>(H) * W * D;
+  const int blocks = static_cast<int>(std::min<long long>((n + 255) / 256, 148 * 4));
+  threshold_counts_kernel<<<blocks, 256, 0, stream>>>(x, dev_view(seg), H, W, D, ql, counts);
+  return check_launch("threshold_counts_kernel");
+}
+
+int launch_threshold_mask(const float* x, int64_t n, float thr, unsigned char* out, cudaStream_t stream) {
+  if (!x || !out) return fail(kInvalidArgument, "threshold_mask: null pointer");
+  threshold_mask_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, stream>>>(x, n, thr, out);
+  return check_launch("threshold_mask_kernel");
+}
+
+int launch_row_stats(const float* x, const VolView& seg, const VolView& mask, int H, int W, int D, float thr,
+                     unsigned long long* rows, double* rowsum, cudaStream_t stream) {
+  if (!x || !mask.p || !rows || !rowsum) return fail(kInvalidArgument, "row_stats: null pointer");
+  row_stats_kernel<<<H, 256, 0, stream>>>(x, dev_view(seg), dev_view(mask), H, W, D, thr, rows, rowsum);
+  return check_launch("row_stats_kernel");
+}
+
+size_t ranking_workspace_bytes(int64_t n) { return ranking_layout(n).total; }
+
+int launch_ranking_metrics(const float* x, const VolView& seg, int H, int W, int D, void* workspace,
+                           size_t workspace_bytes, double* result, cudaStream_t stream) {
+  if (!x || !seg.p || !workspace || !result) return fail(kInvalidArgument, "ranking: null pointer");
+  const int64_t n64 = static_cast<int64_t>(H) * W * D;
+  if (n64 > (1ll << 30)) return fail(kUnsupported, "ranking: too many voxels");
+  const int n = static_cast<int>(n64);
+  const RankingLayout L = ranking_layout(n);
+  if (workspace_bytes < L.total) return fail(kInvalidArgument, "ranking: workspace too small");
+  char* ws = reinterpret_cast<char*>(workspace);
+  float* keys_in = reinterpret_cast<float*>(ws + L.keys_in);
+  float* keys_out = reinterpret_cast<float*>(ws + L.keys_out);
+  unsigned int* lab_in = reinterpret_cast<unsigned int*>(ws + L.lab_in);
+  unsigned int* lab_out = reinterpret_cast<unsigned int*>(ws + L.lab_out);
+  unsigned int* tps = reinterpret_cast<unsigned int*>(ws + L.tps);
+  int* endidx = reinterpret_cast<int*>(ws + L.endidx);
+  int* lastend = reinterpret_cast<int*>(ws + L.lastend);
+  double* auc = reinterpret_cast<double*>(ws + L.auc);
+  double* ap = reinterpret_cast<double*>(ws + L.ap);
+  void* cubtmp = ws + L.cub;
+  size_t cb = L.cub_bytes;
+  const int blocks = (n + 255) / 256;
+  gather_scores_kernel<<<blocks, 256, 0, stream>>>(x, dev_view(seg), H, W, D, keys_in, lab_in);
+  CDDPM_TRY(check_launch("gather_scores_kernel"));
+  CDDPM_CUDA(cub::DeviceRadixSort::SortPairsDescending(cubtmp, cb, keys_in, keys_out, lab_in, lab_out, n, 0, 32, stream));
+  cb = L.cub_bytes;
+  CDDPM_CUDA(cub::DeviceScan::InclusiveSum(cubtmp, cb, lab_out, tps, n, stream));
+  end_index_kernel<<<blocks, 256, 0, stream>>>(keys_out, n, endidx);
+  CDDPM_TRY(check_launch("end_index_kernel"));
+  cb = L.cub_bytes;
+  CDDPM_CUDA(cub::DeviceScan::InclusiveScan(cubtmp, cb, endidx, lastend, MaxOp(), n, stream));
+  ranking_terms_kernel<<<blocks, 256, 0, stream>>>(keys_out, tps, lastend, n, auc, ap);
+  CDDPM_TRY(check_launch("ranking_terms_kernel"));
+  cb = L.cub_bytes;
+  CDDPM_CUDA(cub::DeviceReduce::Sum(cubtmp, cb, auc, result, n, stream));
+  cb = L.cub_bytes;
+  CDDPM_CUDA(cub::DeviceReduce::Sum(cubtmp, cb, ap, result + 1, n, stream));
+  return kOk;
+}
+
+}  // namespace cddpm

@@ -156,6 +156,45 @@ int cddpm_recon_finish(const float* model_out, const float* img, const float* x_
                        const float* sqrt_one_minus_alphas_cumprod, const float* p2_loss_weight, const int64_t* t,
                        int t_shared, int B, int HW, int pred_noise, int l2, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Anomaly-scoring tail: _test_step of src/utils/utils_eval.py:18-194.
+ * A volume is addressed logically as (y, x, d) = [H, W, D] like the reference's squeezed tensors.  Inputs carry
+ * element strides (sy, sx, sd) so the dataloader layout [H,W,D] and the UNet output layout [D,1,H,W] are both read
+ * in place; work buffers written here ("[D,H,W] buffers") are slice-major with x fastest.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct cddpm_vol_view {
+  const float* ptr;
+  int64_t sy, sx, sd;
+} cddpm_vol_view;
+
+/* diff = |orig - reco| (utils_eval.py:31), multiplied by the brain mask eroded per axial slice with a 3x3 cross,
+ * `iterations` times, zero border (apply_brainmask_volume :447-460; the reference passes W // 25; iterations < 1
+ * means scipy's "until stable").  erode == 0 skips the mask.  sums (7 doubles, may be NULL) receive
+ * sum|d|, sum d^2 over all voxels / seg>0 / seg==0 and count(seg>0) for the l1/l2 errors (:36-49). */
+int cddpm_residual_erode(const cddpm_vol_view* orig, const cddpm_vol_view* reco, const cddpm_vol_view* seg,
+                         const cddpm_vol_view* mask, int H, int W, int D, int iterations, int erode,
+                         float* diff_masked_dhw, double* sums, void* stream);
+/* scipy.ndimage.median_filter(vol, (k,k,k)) with mode='reflect' (apply_3d_median_filter :462-464), k in {1,3,5}. */
+int cddpm_median3d(const float* in_dhw, float* out_dhw, int H, int W, int D, int k, void* stream);
+/* np.max of a buffer (val_range top of find_best_val, :86); out_max: one float on the device. */
+int cddpm_max(const float* x, int64_t n, float* out_max, void* stream);
+/* Dice counts for find_best_val (:508-545): counts[0] += #(seg>0); counts[1+2i] += #(x > q[i]);
+ * counts[2+2i] += #(x > q[i] and seg>0), i < nq <= 4.  Accumulates (caller zeroes), so several volumes / ranks can
+ * share the counters of the global threshold search (_test_end :262-271).  q_host is in HOST memory. */
+int cddpm_threshold_counts(const float* x_dhw, const cddpm_vol_view* seg, int H, int W, int D, const float* q_host,
+                           int nq, uint64_t* counts, void* stream);
+/* out[i] = x[i] > thr (uint8), the "diffs_thresholded" volume (:95-98). */
+int cddpm_threshold_mask(const float* x, int64_t n, float thr, uint8_t* out, void* stream);
+/* Per image row y (the reference's per-"slice" loops run over axis 0, :138-144, :160-174):
+ * rows[y][0..3] = #(x>thr), #(seg>0), #(both), #(mask>0); rowsum[y] = sum of x over mask>0. */
+int cddpm_row_stats(const float* x_dhw, const cddpm_vol_view* seg, const cddpm_vol_view* mask, int H, int W, int D,
+                    float thr, uint64_t* rows, double* rowsum, void* stream);
+/* ROC-AUC and average precision with sklearn's tie semantics (compute_roc / compute_prc, :548-557):
+ * result[0] = AUC, result[1] = AP (doubles on the device). */
+int64_t cddpm_ranking_workspace_bytes(int64_t n);
+int cddpm_ranking_metrics(const float* x_dhw, const cddpm_vol_view* seg, int H, int W, int D, void* workspace,
+                          int64_t workspace_bytes, double* result, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,159 @@
+"""GPU parity of the anomaly-scoring tail (residual, eroded brain mask, 5x5x5 median, Dice bisection, AUC/AP, counts)
+against (1) golden vectors from the live reference's utils_eval (tests/golden/stencil.npz, tail.json) and (2) the numpy
+oracle port on full-size 96x96x50 volumes.  Integer / index / threshold results must be bit-exact.
+
+Reference: src/utils/utils_eval.py:18-194 (_test_step), :196-297 (_test_end), :447-464, :508-557."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+pytestmark = pytest.mark.gpu
+
+
+class Cfg(dict):
+    __getattr__ = dict.get
+
+
+def _cfg(**over):
+    c = Cfg(resizedEvaluation=True, erodeBrainmask=True, medianFiltering=True, saveOutputImages=False, evalSeg=True,
+            threshold="auto")
+    c.update(over)
+    return c
+
+
+class Host:
+    pass
+
+
+def _host(stage):
+    from cddpm.eval_tail import get_eval_dictionary
+
+    h = Host()
+    h.cfg = _cfg()
+    h.eval_dict = get_eval_dictionary()
+    h.threshold = {}
+    h.dataset = ["Brats21"]
+    h.stage = stage
+    h.diffs_list, h.seg_list = [], []
+    return h
+
+
+@pytest.mark.parametrize("hw", [32, 56, 24])
+def test_stencils_bit_exact_vs_reference_golden(hw):
+    from cddpm.eval_tail import apply_3d_median_filter, apply_brainmask_volume
+
+    g = np.load(os.path.join(GOLD, "stencil.npz"))
+    vol = torch.from_numpy(g[f"vol{hw}"]).cuda()
+    mask = torch.from_numpy(g[f"mask{hw}"].astype(np.float32)).cuda()
+    masked = apply_brainmask_volume(vol.clone()[None, None], mask[None, None]).squeeze()
+    assert np.array_equal(masked.cpu().numpy(), g[f"masked{hw}"])
+    filt = apply_3d_median_filter(masked)
+    assert np.array_equal(filt.cpu().numpy(), g[f"filtered{hw}"])
+    # numpy in / numpy out form used by the reference's call site (utils_eval.py:69)
+    filt_np = apply_3d_median_filter(g[f"masked{hw}"], kernelsize=5)
+    assert isinstance(filt_np, np.ndarray) and np.array_equal(filt_np, g[f"filtered{hw}"])
+
+
+def test_median_properties_full_size():
+    from cddpm.eval_tail import apply_3d_median_filter
+
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(96, 96, 50, generator=g).cuda()
+    m = apply_3d_median_filter(x)
+    assert torch.equal(apply_3d_median_filter(x * 2), m * 2)  # commutes with exact monotone maps
+    assert torch.equal(apply_3d_median_filter(-x), -m)  # odd window: median(-x) = -median(x)
+    c = torch.full((96, 96, 50), 0.37, device="cuda")
+    assert torch.equal(apply_3d_median_filter(c), c)
+    assert float(m.min()) >= float(x.min()) and float(m.max()) <= float(x.max())
+    # kernel 3 against scipy directly (scipy is the reference's own implementation and ships in this image)
+    from scipy import ndimage
+
+    xs = x[:40, :40, :9].contiguous()
+    ref3 = ndimage.median_filter(xs.cpu().numpy(), (3, 3, 3))
+    assert np.array_equal(apply_3d_median_filter(xs, kernelsize=3).cpu().numpy(), ref3)
+
+
+@pytest.mark.parametrize("depth", [50, 4])
+def test_volume_tail_matches_oracle_port_and_reference(depth):
+    from cddpm import eval_tail
+    from oracle import tail_port
+    from oracle.weights import synthetic_volume
+
+    gold = json.load(open(os.path.join(GOLD, "tail.json")))[f"d{depth}"]
+    host = _host("val")
+    vols = [synthetic_volume(s, depth=depth) for s in (0, 1)]
+    for i, v in enumerate(vols):
+        out = eval_tail._test_step(host, v["reco"].cuda(), v["vol"].cuda(), v["seg_orig"].cuda(), v["mask_orig"].cuda(), i,
+                                   [f"v{i}"], torch.tensor([1]))
+        port = tail_port.volume_tail(v["reco"][0, 0].numpy(), v["vol"][0, 0].numpy(), v["seg_orig"][0, 0].numpy(),
+                                     v["mask_orig"][0, 0].numpy(), stage="val")
+        # bit-exact volumes
+        assert np.array_equal(out.diff_hwd().cpu().numpy(), port["diff_filtered"])
+        ed = host.eval_dict
+        assert ed["BestThresholdPerVol"][i] == port["BestThreshold"] == np.float32(gold["val"]["BestThresholdPerVol"][i])
+        assert ed["BestDicePerVol"][i] == port["BestDice"] == gold["val"]["BestDicePerVol"][i]
+        assert ed["DiceScorePerVol"][i] == port["Dice"] == gold["val"]["DiceScorePerVol"][i]
+        for k, pk in (("TPPerVol", "TP"), ("FPPerVol", "FP"), ("TNPerVol", "TN"), ("FNPerVol", "FN")):
+            assert ed[k][i] == port[pk] == int(gold["val"][k][i])
+        assert abs(ed["AUCPerVol"][i] - gold["val"]["AUCPerVol"][i]) < 1e-9
+        assert abs(ed["AUPRCPerVol"][i] - gold["val"]["AUPRCPerVol"][i]) < 1e-9
+        for k in ("l1recoErrorAll", "l2recoErrorAll", "l1recoErrorUnhealthy", "l1recoErrorHealthy"):
+            assert abs(ed[k][i] - gold["val"][k][i]) < 1e-6 * max(1.0, abs(gold["val"][k][i]))
+        assert abs(ed["AnomalyScoreRecoPerVol"][i] - gold["val"]["AnomalyScoreRecoPerVol"][i]) < 1e-6
+        assert ed["lesionSizePerVol"][i] == int(gold["val"]["lesionSizePerVol"][i])
+        assert abs(ed["TPRPerVol"][i] - gold["val"]["TPRPerVol"][i]) < 1e-12
+        assert abs(ed["SpecificityPerVol"][i] - gold["val"]["SpecificityPerVol"][i]) < 1e-12
+    ed = host.eval_dict
+    assert np.allclose(ed["DiceScorePerSlice"], gold["val"]["DiceScorePerSlice"], rtol=0, atol=1e-12)
+    assert ed["labelPerSlice"] == [int(v) for v in gold["val"]["labelPerSlice"]]
+    assert np.allclose(ed["AnomalyScoreRecoPerSlice"], gold["val"]["AnomalyScoreRecoPerSlice"], rtol=1e-5, atol=1e-7)
+    assert np.allclose(ed["AUCAnomalyRecoPerSlice"], gold["val"]["AUCAnomalyRecoPerSlice"], atol=1e-9)
+    assert np.allclose(ed["AUPRCAnomalyRecoPerSlice"], gold["val"]["AUPRCAnomalyRecoPerSlice"], atol=1e-9)
+    # global threshold over all validation voxels (_test_end), then the test stage with it
+    eval_tail._test_end(host)
+    assert host.threshold["total"] == np.float32(gold["threshold_total"])
+    total = host.threshold["total"]
+    host2 = _host("test")
+    host2.threshold = {"total": total}
+    v = vols[0]
+    eval_tail._test_step(host2, v["reco"].cuda(), v["vol"].cuda(), v["seg_orig"].cuda(), v["mask_orig"].cuda(), 0, ["v0"],
+                         torch.tensor([1]))
+    assert host2.eval_dict["DiceScorePerVol"][0] == gold["test_dice"]
+    assert [host2.eval_dict[k][0] for k in ("TPPerVol", "FPPerVol", "TNPerVol", "FNPerVol")] == gold["test_counts"]
+    eval_tail._test_end(host2)
+    assert not hasattr(host2, "threshold")  # the reference deletes it after the test stage (utils_eval.py:259-260)
+
+
+def test_reco_in_unet_layout_is_read_in_place():
+    """final_volume arrives as reco[D,1,H,W].squeeze().permute(1,2,0) (DDPM_2D.py:256-257): a strided view."""
+    from cddpm import eval_tail
+    from oracle.weights import synthetic_volume
+
+    v = synthetic_volume(2, depth=12)
+    reco_dhw = v["reco"][0, 0].permute(2, 0, 1).contiguous().cuda()  # what the UNet produces: [D,H,W]
+    view = reco_dhw.permute(1, 2, 0)[None, None]  # [1,1,H,W,D] non-contiguous
+    a, _ = eval_tail.residual_and_filter(view, v["vol"].cuda(), v["seg_orig"].cuda(), v["mask_orig"].cuda())
+    b, _ = eval_tail.residual_and_filter(v["reco"].cuda(), v["vol"].cuda(), v["seg_orig"].cuda(), v["mask_orig"].cuda())
+    assert torch.equal(a.diff, b.diff)
+
+
+def test_find_best_val_and_ranking_standalone():
+    from cddpm import eval_tail
+    from oracle import tail_port
+
+    rng = np.random.default_rng(3)
+    x = rng.random(20000).astype(np.float32)
+    x[rng.random(20000) < 0.5] = 0.0  # many exact ties, like a masked residual
+    y = (rng.random(20000) < 0.1 + 0.5 * x)
+    bd, bt = eval_tail.find_best_val(x, y, val_range=(0, np.max(x)), max_steps=10)
+    pd, pt = tail_port.find_best_val(x, y, val_range=(0, np.max(x)), max_steps=10)
+    assert bd == pd and bt == pt
+    auc, *_ = eval_tail.compute_roc(torch.from_numpy(x).cuda(), y)
+    ap, *_ = eval_tail.compute_prc(torch.from_numpy(x).cuda(), y)
+    assert abs(auc - tail_port.roc_auc(x, y)) < 1e-12 and abs(ap - tail_port.average_precision(x, y)) < 1e-12
