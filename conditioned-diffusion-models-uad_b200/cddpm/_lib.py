@@ -69,6 +69,12 @@ def _signatures(c):
         "cddpm_unet_film": (i32, [vp, pvp, pi32]),
         "cddpm_unet_conv_flops": (i64, [vp]),
         "cddpm_unet_launches": (i32, [vp]),
+        "cddpm_encoder_create": (i32, [i32, i32, i32, i32, pvp]),
+        "cddpm_encoder_destroy": (None, [vp]),
+        "cddpm_encoder_param_count": (i32, [vp]),
+        "cddpm_encoder_param_info": (i32, [vp, i32, c.POINTER(c.c_char_p), c.POINTER(i64)]),
+        "cddpm_encoder_set_param": (i32, [vp, c.c_char_p, vp, i64, vp]),
+        "cddpm_encoder_forward": (i32, [vp, vp, vp, i32, vp]),
         "cddpm_simplex_noise": (i32, [c.c_char_p, vp, vp, i32, i32, i32, i32, c.c_double, c.c_double, vp]),
         "cddpm_q_sample": (i32, [vp, vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
         "cddpm_posterior_step": (i32, [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]),

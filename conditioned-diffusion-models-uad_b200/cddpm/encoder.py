@@ -1,0 +1,168 @@
+"""Condition encoder — drop-in for src.models.modules.DDPM_encoder.get_encoder (DDPM_encoder.py:6-29) and
+src.models.modules.spark.Spark_2D.SparK_2D_encoder (spark/Spark_2D.py:268-290).
+
+The reference builds `timm.create_model('resnet50', in_chans=1, num_classes=cond_dim, drop_path_rate=0.05)`
+(spark/models.py:89-109) and calls its monkey-patched forward(x, pyramid=0) (spark/resnet.py:13-46).  timm is not
+vendored in the reference; the modules below are parameter holders with timm's / torchvision's ResNet-50 key names
+(conv1, bn1, layerN.i.{conv1,bn1,conv2,bn2,conv3,bn3,downsample.{0,1}}, fc — 320 state_dict entries), initialised like
+timm (kaiming-normal convs, zero_init_last on bn3).  forward runs in the CUDA engine (cddpm_encoder_forward) with
+BatchNorm folded from the running statistics, i.e. eval-mode arithmetic; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import CddpmError, check, current_stream, lib, ptr
+
+_LAYERS = {"resnet50": (3, 4, 6, 3)}
+_WIDTHS = (64, 128, 256, 512)
+
+
+def _no_eager(self, *a, **k):
+    raise CddpmError("this module is a parameter holder; the encoder executes inside the CUDA engine")
+
+
+class _Bottleneck(nn.Module):
+    def __init__(self, cin, width, stride, downsample):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, width, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(width)
+        self.conv2 = nn.Conv2d(width, width, 3, stride=stride, padding=1, bias=False)
+        self.bn2 = nn.BatchNorm2d(width)
+        self.conv3 = nn.Conv2d(width, width * 4, 1, bias=False)
+        self.bn3 = nn.BatchNorm2d(width * 4)
+        if downsample:
+            self.downsample = nn.Sequential(nn.Conv2d(cin, width * 4, 1, stride=stride, bias=False),
+                                            nn.BatchNorm2d(width * 4))
+        else:
+            self.downsample = None
+        nn.init.zeros_(self.bn3.weight)  # timm zero_init_last
+
+    forward = _no_eager
+
+
+class ResNet(nn.Module):
+    """ResNet-50 parameter holder + CUDA engine handle."""
+
+    def __init__(self, name="resnet50", in_chans=1, num_classes=128, image_size=(96, 96), engine_dtype=torch.float16):
+        super().__init__()
+        if name not in _LAYERS:
+            raise NotImplementedError(f"encoder backbone {name}: only resnet50 (the cDDPM configuration) is built")
+        if in_chans != 1:
+            raise NotImplementedError("the cDDPM encoder takes single-channel slices")
+        self.num_classes = num_classes
+        self.image_size = tuple(int(s) for s in image_size)
+        self.engine_dtype = engine_dtype
+        self.drop_rate = 0.0
+        self.conv1 = nn.Conv2d(in_chans, 64, 7, stride=2, padding=3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        cin = 64
+        for li, (n, w) in enumerate(zip(_LAYERS[name], _WIDTHS)):
+            blocks = []
+            for bi in range(n):
+                blocks.append(_Bottleneck(cin, w, 2 if (bi == 0 and li > 0) else 1, bi == 0))
+                cin = w * 4
+            setattr(self, f"layer{li + 1}", nn.Sequential(*blocks))
+        self.fc = nn.Linear(cin, num_classes)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+        self._h: Optional[ctypes.c_void_p] = None
+        self._versions = None
+        self._items = None
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                lib().cddpm_encoder_destroy(h)
+            except Exception:
+                pass
+
+    def _apply(self, fn, *args, **kwargs):
+        self._items = None
+        self._versions = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def _engine_items(self) -> List[Tuple[str, torch.Tensor]]:
+        if self._items is None:
+            self._items = [(k, v) for k, v in self.state_dict(keep_vars=True).items()
+                           if not k.endswith("num_batches_tracked")]
+        return self._items
+
+    def _sync(self):
+        items = self._engine_items()
+        dev = items[0][1].device
+        if dev.type != "cuda":
+            raise CddpmError("the encoder is on the CPU; the cDDPM engine has no CPU path — move the module to CUDA")
+        if self._h is None:
+            h = ctypes.c_void_p()
+            check(lib().cddpm_encoder_create(self.image_size[0], self.image_size[1], self.num_classes,
+                                             _lib.fmt_of(self.engine_dtype), ctypes.byref(h)), "cddpm_encoder_create")
+            self._h = h
+            n = lib().cddpm_encoder_param_count(h)
+            name, numel = ctypes.c_char_p(), ctypes.c_int64()
+            names = []
+            for i in range(n):
+                check(lib().cddpm_encoder_param_info(h, i, ctypes.byref(name), ctypes.byref(numel)))
+                names.append(name.value.decode())
+            if names != [k for k, _ in items]:
+                raise CddpmError("encoder engine parameter list differs from the module's state_dict layout")
+        if self._versions is None:
+            self._versions = [None] * len(items)
+        for i, (k, p) in enumerate(items):
+            v = (p.data_ptr(), p._version)
+            if self._versions[i] != v:
+                t = p.detach()
+                if t.dtype != torch.float32 or not t.is_contiguous():
+                    t = t.float().contiguous()
+                check(lib().cddpm_encoder_set_param(self._h, k.encode(), ptr(t), t.numel(), current_stream()),
+                      f"cddpm_encoder_set_param({k})")
+                self._versions[i] = v
+
+    def forward(self, x, pyramid=0):
+        if pyramid != 0:
+            raise NotImplementedError("pyramid features are only used by SparK pre-training (out of scope)")
+        if self.training and torch.is_grad_enabled():
+            raise NotImplementedError("training-mode BatchNorm / DropPath (the training step) is not part of this "
+                                      "build; call .eval() and run under torch.no_grad()")
+        if not x.is_cuda:
+            raise CddpmError("encoder forward needs CUDA tensors (there is no CPU path)")
+        self._sync()
+        x = x.float().contiguous()
+        B = x.shape[0]
+        if tuple(x.shape[1:]) != (1, *self.image_size):
+            raise CddpmError(f"expected [B,1,{self.image_size[0]},{self.image_size[1]}], got {tuple(x.shape)}")
+        out = torch.empty(B, self.num_classes, dtype=torch.float32, device=x.device)
+        check(lib().cddpm_encoder_forward(self._h, ptr(x), ptr(out), B, current_stream()), "cddpm_encoder_forward")
+        return out
+
+
+class SparK_2D_encoder(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.pyramid = cfg.get("pyramid", 4)
+        self.cfg = cfg
+        size = (int(cfg.imageDim[0] / cfg.rescaleFactor), int(cfg.imageDim[1] / cfg.rescaleFactor))
+        dtype = {"bf16": torch.bfloat16, "bfloat16": torch.bfloat16}.get(str(cfg.get("engine_dtype", "fp16")), torch.float16)
+        self.encoder = ResNet(cfg.version, in_chans=1, num_classes=cfg.get("cond_dim", 128), image_size=size,
+                              engine_dtype=dtype)
+
+    def forward(self, x):
+        return self.encoder(x)
+
+
+def get_encoder(cfg):
+    """(encoder, out_features) — DDPM_encoder.get_encoder."""
+    backbone = cfg.get("backbone", "resnet50")
+    if "spark" in backbone.lower():
+        encoder = SparK_2D_encoder(cfg)
+    else:
+        size = (int(cfg.imageDim[0] / cfg.rescaleFactor), int(cfg.imageDim[1] / cfg.rescaleFactor))
+        encoder = ResNet(backbone, in_chans=1, num_classes=cfg.get("cond_dim", 256), image_size=size)
+    return encoder, cfg.get("cond_dim", 256)

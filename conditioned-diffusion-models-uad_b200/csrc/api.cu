@@ -6,6 +6,7 @@
 #include "conv_igemm.cuh"
 #include "diffusion.cuh"
 #include "elementwise.cuh"
+#include "resnet_engine.cuh"
 #include "simplex.cuh"
 #include "tail.cuh"
 #include "unet_engine.cuh"
@@ -144,6 +145,35 @@ int cddpm_simplex_noise(const uint8_t* perm_host, void* out_f16, float* out_f32,
                         double persistence, double frequency, void* stream) {
   return launch_simplex_noise(perm_host, out_f16, out_f32, B, H, W, octaves, persistence, frequency,
                               static_cast<cudaStream_t>(stream));
+}
+
+struct cddpm_encoder {
+  ResNetEngine engine;
+};
+int cddpm_encoder_create(int image_h, int image_w, int cond_dim, int fmt, cddpm_encoder_t** out) {
+  if (!out) return fail(kInvalidArgument, "encoder_create: null pointer");
+  cddpm_encoder* h = new cddpm_encoder();
+  int st = h->engine.init(image_h, image_w, cond_dim, fmt);
+  if (st != kOk) {
+    delete h;
+    return st;
+  }
+  *out = h;
+  return kOk;
+}
+void cddpm_encoder_destroy(cddpm_encoder_t* h) { delete h; }
+int cddpm_encoder_param_count(const cddpm_encoder_t* h) { return h ? h->engine.param_count() : 0; }
+int cddpm_encoder_param_info(const cddpm_encoder_t* h, int index, const char** name, int64_t* numel) {
+  if (!h || !name || !numel) return fail(kInvalidArgument, "encoder_param_info: null pointer");
+  return h->engine.param_info(index, name, numel);
+}
+int cddpm_encoder_set_param(cddpm_encoder_t* h, const char* name, const float* value, int64_t numel, void* stream) {
+  if (!h || !name) return fail(kInvalidArgument, "encoder_set_param: null pointer");
+  return h->engine.set_param(name, value, numel, static_cast<cudaStream_t>(stream));
+}
+int cddpm_encoder_forward(cddpm_encoder_t* h, const float* x, float* c, int B, void* stream) {
+  if (!h) return fail(kInvalidArgument, "encoder_forward: null handle");
+  return h->engine.forward(x, c, B, static_cast<cudaStream_t>(stream));
 }
 
 static VolView to_view(const cddpm_vol_view* v) {

@@ -111,6 +111,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
               uint8_t* a_dst = smem + stage * stage_bytes;
               uint8_t* b_dst = a_dst + kAStageBytes;
               mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
+              if (p.flat) {
+                tma_load_2d(a_dst, &p.tmap_a[s], &full_bar[stage], ch * kConvBlockK, m_tile * kConvTileM);
+              } else
               for (int b = 0; b < p.boxes_per_tile; ++b) {
                 const int box = m_tile * p.boxes_per_tile + b;
                 const int n = box / boxes_per_img;
@@ -185,8 +188,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
       const int tx = r - ty * p.tiles_w;
       const int y = ty * p.box_h + rr / p.box_w;
       const int x = tx * p.box_w + rr % p.box_w;
-      const bool valid = (box < p.total_boxes);
-      const size_t pix = (static_cast<size_t>(n) * p.H + y) * p.W + x;
+      bool valid = (box < p.total_boxes) && (y < p.H) && (x < p.W);
+      size_t pix = (static_cast<size_t>(n) * p.H + y) * p.W + x;
+      if (p.flat) {
+        pix = static_cast<size_t>(m_tile) * kConvTileM + row;
+        valid = pix < static_cast<size_t>(p.M);
+      }
       const size_t off = pix * p.Cout + static_cast<size_t>(n_idx) * p.n_tile;
 
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -230,6 +237,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
                 f[q * 8 + e * 2 + 1] += t.y;
               }
             }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
           }
           if (p.out_is_f32) {
             float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off + c * 32);
@@ -312,23 +323,38 @@ int conv_num_boxes(int B, int H, int W) {
 
 int build_conv_params(const ConvDesc& d, ConvIgemmParams* p) {
   if (d.num_src < 1 || d.num_src > kConvMaxSrc) return fail(kInvalidArgument, "conv: num_src must be 1..3");
-  if (d.B < 1 || d.H < 1 || d.W < 1) return fail(kInvalidArgument, "conv: empty problem");
   memset(p, 0, sizeof(*p));
-  int bw, bh;
-  if (!pick_box(d.H, d.W, &bw, &bh))
-    return fail(kUnsupported, "conv: H and W must be multiples of 8 for the tcgen05 implicit-GEMM path");
+  const bool flat = d.flat_rows > 0;
+  int bw = 16, bh = 8;
   p->num_src = d.num_src;
-  p->B = d.B;
-  p->H = d.H;
-  p->W = d.W;
   p->Cout = d.Cout;
-  p->box_w = bw;
-  p->box_h = bh;
-  p->boxes_per_tile = kConvTileM / (bw * bh);
-  p->tiles_w = d.W / bw;
-  p->tiles_h = d.H / bh;
-  p->total_boxes = d.B * p->tiles_w * p->tiles_h;
-  p->num_m_tiles = (p->total_boxes + p->boxes_per_tile - 1) / p->boxes_per_tile;
+  p->relu = d.relu;
+  if (flat) {
+    if (d.num_src != 1 || d.src_taps[0] != 1) return fail(kInvalidArgument, "conv: flat GEMM takes one 1-tap source");
+    p->flat = 1;
+    p->M = d.flat_rows;
+    p->B = p->H = p->W = 1;
+    p->box_w = bw;
+    p->box_h = bh;
+    p->boxes_per_tile = 1;
+    p->tiles_w = p->tiles_h = 1;
+    p->num_m_tiles = (d.flat_rows + kConvTileM - 1) / kConvTileM;
+    p->total_boxes = p->num_m_tiles;
+  } else {
+    if (d.B < 1 || d.H < 1 || d.W < 1) return fail(kInvalidArgument, "conv: empty problem");
+    if (!pick_box(d.H, d.W, &bw, &bh))
+      return fail(kUnsupported, "conv: H and W must be multiples of 8 for the tcgen05 implicit-GEMM path");
+    p->B = d.B;
+    p->H = d.H;
+    p->W = d.W;
+    p->box_w = bw;
+    p->box_h = bh;
+    p->boxes_per_tile = kConvTileM / (bw * bh);
+    p->tiles_w = d.W / bw;
+    p->tiles_h = d.H / bh;
+    p->total_boxes = d.B * p->tiles_w * p->tiles_h;
+    p->num_m_tiles = (p->total_boxes + p->boxes_per_tile - 1) / p->boxes_per_tile;
+  }
   // N tile: the largest of 256/192/128/64/32 dividing Cout
   int n_tile = 0;
   const int cands[] = {256, 192, 128, 96, 64, 32};
@@ -364,10 +390,17 @@ int build_conv_params(const ConvDesc& d, ConvIgemmParams* p) {
     p->src_c[s] = d.src_c[s];
     p->src_taps[s] = d.src_taps[s];
     const uint64_t C = static_cast<uint64_t>(d.src_c[s]);
-    const uint64_t dims[4] = {C, static_cast<uint64_t>(d.W), static_cast<uint64_t>(d.H), static_cast<uint64_t>(d.B)};
-    const uint64_t strides[3] = {C * 2, C * 2 * d.W, C * 2 * d.W * d.H};
-    const uint32_t box[4] = {static_cast<uint32_t>(kConvBlockK), static_cast<uint32_t>(bw), static_cast<uint32_t>(bh), 1u};
-    CDDPM_TRY(encode_tmap_16bit(&p->tmap_a[s], d.src[s], 4, dims, strides, box));
+    if (flat) {
+      const uint64_t dims[2] = {C, static_cast<uint64_t>(d.flat_rows)};
+      const uint64_t strides[1] = {C * 2};
+      const uint32_t box[2] = {static_cast<uint32_t>(kConvBlockK), static_cast<uint32_t>(kConvTileM)};
+      CDDPM_TRY(encode_tmap_16bit(&p->tmap_a[s], d.src[s], 2, dims, strides, box));
+    } else {
+      const uint64_t dims[4] = {C, static_cast<uint64_t>(d.W), static_cast<uint64_t>(d.H), static_cast<uint64_t>(d.B)};
+      const uint64_t strides[3] = {C * 2, C * 2 * d.W, C * 2 * d.W * d.H};
+      const uint32_t box[4] = {static_cast<uint32_t>(kConvBlockK), static_cast<uint32_t>(bw), static_cast<uint32_t>(bh), 1u};
+      CDDPM_TRY(encode_tmap_16bit(&p->tmap_a[s], d.src[s], 4, dims, strides, box));
+    }
     ktot += d.src_taps[s] * d.src_c[s];
   }
   {

@@ -37,6 +37,9 @@ struct ConvIgemmParams {
   void* out;             // [B,H,W,Cout] 16-bit, or fp32 when out_is_f32
   float* gn_partial;     // optional [num_boxes][Cout/gn_cpg][2] per-box (sum, sumsq) of the stored output
   int gn_cpg;            // channels per statistics bucket (divides 32)
+  int flat;              // plain GEMM: A is a row-major [M][C] matrix (2-D tensor map), one source, taps == 1
+  int M;                 // rows of the flat problem
+  int relu;              // clamp the result at 0 after bias and residual
 };
 
 // Describes one convolution launch in host terms; build_conv_params() turns it into ConvIgemmParams.
@@ -54,6 +57,9 @@ struct ConvDesc {
   int ab_format = 1;
   float* gn_partial = nullptr;
   int gn_cpg = 0;
+  int flat_rows = 0;  // > 0: plain GEMM over src[0] = [flat_rows][src_c[0]] (B/H/W ignored), e.g. nn.Linear or an
+                      // im2col'ed convolution
+  int relu = 0;
 };
 
 int conv_ktot(const ConvDesc& d);

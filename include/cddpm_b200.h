@@ -118,6 +118,21 @@ int64_t cddpm_unet_conv_flops(const cddpm_unet_t* h);
 int cddpm_unet_launches(const cddpm_unet_t* h);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Condition encoder: SparK_2D_encoder.forward (spark/Spark_2D.py:285-290) = timm ResNet-50 (v1.5, in_chans=1,
+ * num_classes=cond_dim) in eval mode, forward(x, pyramid=0) (spark/resnet.py:13-46).  Parameter names are the
+ * timm / torchvision keys under `encoder.encoder.` (conv1.weight, bn1.running_mean, layer3.0.downsample.1.bias, ...;
+ * num_batches_tracked is not a parameter here).  BatchNorm is folded into the convolutions.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct cddpm_encoder cddpm_encoder_t;
+int cddpm_encoder_create(int image_h, int image_w, int cond_dim, int fmt, cddpm_encoder_t** out);
+void cddpm_encoder_destroy(cddpm_encoder_t* h);
+int cddpm_encoder_param_count(const cddpm_encoder_t* h);
+int cddpm_encoder_param_info(const cddpm_encoder_t* h, int index, const char** name, int64_t* numel);
+int cddpm_encoder_set_param(cddpm_encoder_t* h, const char* name, const float* value, int64_t numel, void* stream);
+/* x [B,1,H,W] fp32 -> c [B,cond_dim] fp32 */
+int cddpm_encoder_forward(cddpm_encoder_t* h, const float* x, float* c, int B, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * gen_noise (src/utils/generate_noise.py:8-52): OpenSimplex-2D fractal field (octaves 6, persistence 0.8,
  * frequency 64 in the reference), bit-identical to the reference's float64 numba code.  perm_host is the 256-entry
  * permutation of generate_noise.py:214-232 in HOST memory.  out_f16 [B,1,H,W] (same field for every b) and/or
