@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py — denoised MRI slices/sec of the cDDPM reconstruction hot path on B200.
+
+Workload (BASELINE.json configs[1]): conditioned UNet (43.9 M params) + ResNet-50 condition encoder, batch of 32
+synthetic 96x96 slices per GPU, full reverse loop from T0 = test_timesteps = 500 (GaussianDiffusion.sample ->
+p_sample_loop, cond_DDPM.py:446-464) with a fresh simplex-noise field per step, random-init weights.
+One "step" = encoder + 500 UNet forwards + 500 posterior steps for one batch.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Prints ONE JSON line (rank 0).  `value` = device-timed whole-job throughput with inputs resident in HBM; `e2e` = the same
+through the public drop-in API with host buffers (H2D of the slices and D2H of the reconstructions inside the timed
+region); `roofline` = tensor-core rate of the dominant kernel (the tcgen05 implicit-GEMM convolution) from CUDA events
+bracketing its launches inside the timed region; `cpu_baseline` = the oracle port (plain PyTorch fp32) on the host cores
+for a bounded sample.  `--impl reference` times that CPU implementation alone.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "conditioned-diffusion-models-uad_b200")]
+
+METRIC = "denoised MRI slices/sec (cDDPM: ResNet-50 encoder + conditioned UNet, reverse loop from T0)"
+UNET_GFLOP = 149.138  # algorithmic GFLOP per UNet forward per 96x96 slice (SURVEY.md §8d / BASELINE.md §2)
+ENC_GFLOP = 1.473
+
+
+class Cfg(dict):
+    __getattr__ = dict.get
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+def model_cfg():
+    return Cfg(imageDim=[192, 192, 100], rescaleFactor=2, unet_dim=128, dim_mults=[1, 2, 2], condition=True,
+               backbone="Spark_Encoder_2D", version="resnet50", cond_dim=128, noisetype="simplex", noise_ensemble=True,
+               test_timesteps=500, lr=1e-4, resizedEvaluation=True, erodeBrainmask=True, medianFiltering=True,
+               saveOutputImages=False, evalSeg=True, threshold="auto", spatial_transformer=False,
+               pretrained_encoder=False, objective="pred_x0")
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"tflops": float(p.get("bf16_tflops_sustained", 1395.6)), "tflops_burst": float(p.get("bf16_tflops", 1619.1)),
+                "hbm_gbs": float(p.get("hbm_gbs", 6557.8)), "source": "MEASURED_PEAKS.json (sustained, of measured)"}
+    return {"tflops": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0, "source": "B200_PROFILING.md fallback (of fallback)"}
+
+
+# ---------------------------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 7:
+                    continue
+                try:
+                    sm.append(float(parts[0]))
+                    mx.append(float(parts[1]))
+                except ValueError:
+                    continue
+                for nme, val in zip(names, parts[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nme)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ---------------------------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_sample(batch: int, rev_steps: int, start_t: int, threads: int):
+    """Oracle port (plain PyTorch fp32, the restatement of the reference's own CPU path) on the host cores: encoder +
+    `rev_steps` reverse steps for `batch` slices, extrapolated to the full start_t-step loop.  Returns slices/s."""
+    import numpy as np
+    import torch
+
+    from oracle import diffusion_port, resnet_port, unet_port
+    from oracle.simplex_port import gen_noise_port
+    from oracle.weights import make_state_dict, synthetic_slices
+
+    torch.set_num_threads(threads)
+    spec = unet_port.UNetSpec()
+    sd = make_state_dict(unet_port.param_shapes(spec), seed=1)
+    esd = make_state_dict(resnet_port.param_shapes(128), seed=3)
+    sched = diffusion_port.schedule_buffers()
+    x = synthetic_slices(batch, 96, seed=0)
+    np.random.seed(0)
+    model = lambda xt, t, c: unet_port.unet_forward(sd, spec, xt, t, c)  # noqa: E731
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        cond = resnet_port.resnet_forward(esd, x)
+        t_enc = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        # reverse_loop runs `rev_steps` steps when started at index rev_steps; the schedule index only changes scalars
+        diffusion_port.reverse_loop(model, sched, x * 2 - 1, cond, rev_steps, lambda: gen_noise_port((batch, 1, 96, 96)))
+        t_rev = time.perf_counter() - t0
+    per_step = t_rev / rev_steps
+    total = t_enc + per_step * start_t
+    return batch / total, {"t_encoder_s": t_enc, "t_per_reverse_step_s": per_step}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    B, S = 2, 2
+    for _ in range(args.warmup):
+        cpu_reference_sample(B, 1, args.start_t, threads)
+    vals = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        v, _ = cpu_reference_sample(B, S, args.start_t, threads)
+        vals.append(v)
+    dt = (time.perf_counter() - t0) / max(1, args.steps)
+    v = statistics.median(vals)
+    sample = (f"oracle port (fp32 PyTorch restatement of the reference CPU path), {B} slices x {S} reverse steps + encoder "
+              f"per step, extrapolated x{args.start_t // S} to the {args.start_t}-step loop")
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "slices/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, 32),
+            "cpu_baseline": {"value": v, "unit": "slices/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, batch):
+    return {"workload": f"configs[1]: cDDPM (DDPM_cond_spark_2D) conditioned UNet + ResNet-50 encoder, batch {batch} "
+                        f"synthetic 96x96 slices per GPU, full reverse loop from T0={args.start_t} on B200",
+            "batch_per_gpu": batch, "start_t": args.start_t, "image": "1x96x96", "objective": "pred_x0",
+            "noise": "simplex (GPU, one field per step)", "parallelism": f"slice-sharded x{args.gpus}, no data-path collective",
+            "l2": "streaming working set ~1.9 GB per UNet forward >> 126 MB L2 (no flush needed)"}
+
+
+# ---------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the cDDPM engine has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from cddpm.ddpm_2d import DDPM_2D
+
+    B, T0 = args.batch, args.start_t
+    torch.manual_seed(1234 + rank)
+    np.random.seed(1234 + rank)
+    model = DDPM_2D(model_cfg(), prefix="bench/")
+    with torch.no_grad():  # random-init every tensor, including the reference's zero-initialised output convolutions
+        for name, p in model.named_parameters():
+            if p.dim() >= 2 and float(p.abs().sum()) == 0.0:
+                fan_in = p[0].numel()
+                p.normal_(0.0, 1.0 / fan_in ** 0.5)
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.fill_(1.0)
+    model = model.to(dev).eval()
+    diffusion = model.diffusion
+    unet = diffusion.model
+
+    g = torch.Generator().manual_seed(7 + rank)
+    x_host = torch.rand(B, 1, 96, 96, generator=g).pin_memory()
+    out_host = torch.empty(B, 1, 96, 96).pin_memory()
+    x_dev = x_host.to(dev)
+
+    def step(x):
+        with torch.no_grad():
+            cond = model(x)
+            return diffusion.sample(cond=cond, x_start=x * 2 - 1, start_t=T0, noise=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(x_dev)
+    barrier()
+    eng = unet.engine()
+
+    # ---------------- timed region 1: inputs resident in HBM
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    conv_ms, conv_launches = [], 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        eng.profile_arm()  # the first UNet forward of this step is bracketed per convolution launch
+        res = step(x_dev)
+        ms, n = eng.profile_read()
+        conv_ms.append(ms)
+        conv_launches = n
+    e1.record()
+    barrier()
+    dt_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else {}
+
+    # ---------------- timed region 2: end to end through the public API with host buffers
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        xd = x_host.to(dev, non_blocking=True)
+        res = step(xd)
+        out_host.copy_(res, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        _ = float(out_host[0, 0, 0, 0])  # the host consumes the result
+    f1.record()
+    barrier()
+    e2e_ms = f0.elapsed_time(f1)
+
+    t = torch.tensor([dt_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # the only collective of the sweep: gather per-slice scores (here the mean reconstruction) to every rank
+        score = res.mean(dim=(1, 2, 3)).contiguous()
+        gathered = [torch.empty_like(score) for _ in range(world)]
+        dist.all_gather(gathered, score)
+    dt_ms, e2e_ms = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    slices = B * world * args.steps
+    value = slices / (dt_ms / 1e3)
+    e2e_value = slices / (e2e_ms / 1e3)
+    pk = peaks()
+    conv_flops_fwd = eng.conv_flops_per_sample * B
+    conv_ms_fwd = statistics.median(conv_ms)
+    achieved = conv_flops_fwd / (conv_ms_fwd / 1e3) / 1e12
+    enc_launches = 1 + 1 + 16 * 4 + 4 + 3 + 2  # stem, pool, (3 GEMM + im2col) x 16 blocks, 4 downsample GEMMs, 3 strided gathers, pool + fc
+    launches_per_step = enc_launches + 2 + T0 * (eng.launches_per_forward + 2)
+    roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel (tcgen05 implicit GEMM, all 56 conv launches of a UNet forward)",
+                "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
+                "peak_source": pk["source"], "flops_per_launch": conv_flops_fwd / max(1, conv_launches),
+                "avg_launch_ms": conv_ms_fwd / max(1, conv_launches), "launches_timed": conv_launches * len(conv_ms),
+                "traffic": None,
+                "unet_forward_tflops": UNET_GFLOP * B * world * T0 * args.steps / 1e3 / (dt_ms / 1e3),
+                "unet_forward_frac_of_peak": UNET_GFLOP * B * T0 * args.steps / 1e3 / (dt_ms / 1e3) / pk["tflops"]}
+    line = {"metric": METRIC, "value": value, "unit": "slices/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16", "data": "synthetic", "config": workload_config(args, B),
+            "roofline": roofline,
+            "e2e": {"value": e2e_value, "unit": "slices/s", "h2d_bytes_per_step": x_host.numel() * 4,
+                    "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
+            "single_step_equiv_slices_per_s": value * T0}
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, parts = cpu_reference_sample(2, 2, T0, threads)
+        line["cpu_baseline"] = {"value": v, "unit": "slices/s", "cores": threads, "kind": "port",
+                                "sample": f"oracle port (fp32 PyTorch) on the host: 2 slices x 2 reverse steps + encoder, "
+                                          f"extrapolated to the {T0}-step loop", **parts}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--start-t", dest="start_t", type=int, default=500)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        print(f"note: --warmup {args.warmup} < 3 breaks the timing rules; use >= 3 for a reportable number", file=sys.stderr)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

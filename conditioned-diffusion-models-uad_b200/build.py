@@ -43,7 +43,7 @@ def build(force: bool = False, verbose: bool = True) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
     os.makedirs(OBJDIR, exist_ok=True)
     srcs = _sources()
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))] + [
         os.path.join(HERE, "..", "include", "cddpm_b200.h")
     ]
     stamp = os.path.join(OBJDIR, "stamp.txt")

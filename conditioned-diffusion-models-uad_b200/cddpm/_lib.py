@@ -69,6 +69,8 @@ def _signatures(c):
         "cddpm_unet_film": (i32, [vp, pvp, pi32]),
         "cddpm_unet_conv_flops": (i64, [vp]),
         "cddpm_unet_launches": (i32, [vp]),
+        "cddpm_unet_profile_arm": (i32, [vp]),
+        "cddpm_unet_profile_read": (i32, [vp, c.POINTER(c.c_double), pi32]),
         "cddpm_encoder_create": (i32, [i32, i32, i32, i32, pvp]),
         "cddpm_encoder_destroy": (None, [vp]),
         "cddpm_encoder_param_count": (i32, [vp]),

@@ -117,6 +117,15 @@ class UNetEngine:
         _cudart_memcpy(buf.data_ptr(), p.value, batch * stride.value * 4)
         return buf
 
+    def profile_arm(self) -> None:
+        """Time every convolution launch of the next forward with CUDA events (bench roofline)."""
+        check(lib().cddpm_unet_profile_arm(self._h), "cddpm_unet_profile_arm")
+
+    def profile_read(self) -> Tuple[float, int]:
+        ms, n = ctypes.c_double(), ctypes.c_int()
+        check(lib().cddpm_unet_profile_read(self._h, ctypes.byref(ms), ctypes.byref(n)), "cddpm_unet_profile_read")
+        return float(ms.value), int(n.value)
+
     @property
     def conv_flops_per_sample(self) -> int:
         return int(lib().cddpm_unet_conv_flops(self._h))

@@ -263,5 +263,13 @@ int cddpm_unet_film(const cddpm_unet_t* h, const float** ptr, int* stride) {
 }
 int64_t cddpm_unet_conv_flops(const cddpm_unet_t* h) { return h ? h->engine.conv_flops_per_sample() : 0; }
 int cddpm_unet_launches(const cddpm_unet_t* h) { return h ? h->engine.launches_per_forward() : 0; }
+int cddpm_unet_profile_arm(cddpm_unet_t* h) {
+  if (!h) return fail(kInvalidArgument, "unet_profile_arm: null handle");
+  return h->engine.profile_arm();
+}
+int cddpm_unet_profile_read(cddpm_unet_t* h, double* conv_ms, int* conv_launches) {
+  if (!h) return fail(kInvalidArgument, "unet_profile_read: null handle");
+  return h->engine.profile_read(conv_ms, conv_launches);
+}
 
 }  // extern "C"

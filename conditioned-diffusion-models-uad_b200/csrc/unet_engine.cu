@@ -305,7 +305,20 @@ void UNetEngine::push_conv(const ConvDesc& d, int* status) {
   *status = build_conv_params(d, p.get());
   if (*status != kOk) return;
   conv_flops_ += 2ll * d.H * d.W * d.Cout * conv_ktot(d);
-  ops_.push_back([p](cudaStream_t s) { return launch_conv_igemm(*p, s); });
+  // Optional per-launch timing (bench roofline): events bracket the convolution launches of ONE forward.
+  UNetEngine* self = this;
+  ops_.push_back([p, self](cudaStream_t s) {
+    if (!self->profile_armed_) return launch_conv_igemm(*p, s);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    CDDPM_CUDA(cudaEventCreate(&e0));
+    CDDPM_CUDA(cudaEventCreate(&e1));
+    CDDPM_CUDA(cudaEventRecord(e0, s));
+    int st = launch_conv_igemm(*p, s);
+    CDDPM_CUDA(cudaEventRecord(e1, s));
+    self->profile_events_.push_back(e0);
+    self->profile_events_.push_back(e1);
+    return st;
+  });
 }
 
 int UNetEngine::plan_res(const ResLayer& L, const ActTensor& a0, const ActTensor* a1, ActTensor* out, int B) {
@@ -639,6 +652,31 @@ int UNetEngine::forward(const float* x, const int64_t* t, const float* cond, flo
   cur_cond_ = cond;
   cur_out_ = out;
   for (auto& op : ops_) CDDPM_TRY(op(stream));
+  if (profile_armed_) profile_armed_ = false;  // one forward per arming
+  return kOk;
+}
+
+int UNetEngine::profile_arm() {
+  for (cudaEvent_t e : profile_events_) cudaEventDestroy(e);
+  profile_events_.clear();
+  profile_armed_ = true;
+  return kOk;
+}
+
+int UNetEngine::profile_read(double* conv_ms, int* conv_launches) {
+  double total = 0.0;
+  int n = 0;
+  for (size_t i = 0; i + 1 < profile_events_.size(); i += 2) {
+    CDDPM_CUDA(cudaEventSynchronize(profile_events_[i + 1]));
+    float ms = 0.f;
+    CDDPM_CUDA(cudaEventElapsedTime(&ms, profile_events_[i], profile_events_[i + 1]));
+    total += ms;
+    ++n;
+  }
+  for (cudaEvent_t e : profile_events_) cudaEventDestroy(e);
+  profile_events_.clear();
+  if (conv_ms) *conv_ms = total;
+  if (conv_launches) *conv_launches = n;
   return kOk;
 }
 

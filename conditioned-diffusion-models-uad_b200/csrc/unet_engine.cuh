@@ -33,6 +33,9 @@ class UNetEngine {
   int forward(const float* x, const int64_t* t, const float* cond, float* out, int B, cudaStream_t stream);
   int tap(const char* layer, void** ptr, int* C, int* H, int* W) const;
   int film(const float** ptr, int* stride) const;
+  // Arm per-launch CUDA-event timing of the convolution kernels for the NEXT forward; read it back afterwards.
+  int profile_arm();
+  int profile_read(double* conv_ms, int* conv_launches);
   int64_t conv_flops_per_sample() const { return conv_flops_; }
   int launches_per_forward() const { return static_cast<int>(ops_.size()); }
   int fmt() const { return cfg_.fmt; }
@@ -107,6 +110,8 @@ class UNetEngine {
   float *sinus_ = nullptr, *hid_t_ = nullptr, *hid_c_ = nullptr, *emb_act_ = nullptr, *film_out_ = nullptr,
         *gn_partial_ = nullptr;
   int64_t conv_flops_ = 0;
+  bool profile_armed_ = false;
+  std::vector<cudaEvent_t> profile_events_;
 };
 
 }  // namespace cddpm

@@ -116,6 +116,10 @@ int cddpm_unet_film(const cddpm_unet_t* h, const float** ptr, int* stride);
 /* Algorithmic tensor-core FLOPs of the implicit-GEMM convolutions per sample, and kernel launches per forward. */
 int64_t cddpm_unet_conv_flops(const cddpm_unet_t* h);
 int cddpm_unet_launches(const cddpm_unet_t* h);
+/* Measurement aid: bracket every convolution launch of the NEXT forward with CUDA events on its stream, then read
+ * the summed device time (ms) and the launch count (this synchronises on the recorded events). */
+int cddpm_unet_profile_arm(cddpm_unet_t* h);
+int cddpm_unet_profile_read(cddpm_unet_t* h, double* conv_ms, int* conv_launches);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Condition encoder: SparK_2D_encoder.forward (spark/Spark_2D.py:285-290) = timm ResNet-50 (v1.5, in_chans=1,

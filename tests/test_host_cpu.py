@@ -1,0 +1,214 @@
+"""CPU tests (no GPU) of the host side: the C-ABI library loads and exports every symbol include/cddpm_b200.h declares,
+the drop-in modules keep the reference's state_dict layout, the product path fails loudly without CUDA, host-only logic
+(permutation LCG, bisection control flow, eval dictionary), and the world-size-2 gloo path of the global threshold."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "conditioned-diffusion-models-uad_b200")
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+class Cfg(dict):
+    __getattr__ = dict.get
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+def _cfg(**over):
+    c = Cfg(imageDim=[192, 192, 100], rescaleFactor=2, unet_dim=128, dim_mults=[1, 2, 2], condition=True,
+            backbone="Spark_Encoder_2D", version="resnet50", cond_dim=128, noisetype="simplex", noise_ensemble=True,
+            test_timesteps=500, lr=1e-4, resizedEvaluation=True, erodeBrainmask=True, medianFiltering=True,
+            saveOutputImages=False, evalSeg=True, threshold="auto")
+    c.update(over)
+    return c
+
+
+def test_library_exports_every_declared_symbol():
+    import ctypes
+
+    from cddpm import _lib
+
+    header = open(os.path.join(ROOT, "include", "cddpm_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(cddpm_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 40
+    lib = _lib.lib()  # resolves every symbol in the ctypes table
+    table = set(_lib._signatures(ctypes).keys())
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+        assert name in table, f"{name} declared in the header but missing from the ctypes table"
+    assert table <= set(declared)
+    assert b"sm_100a" in lib.cddpm_version()
+
+
+def test_no_oracle_import_in_product():
+    """The product path must never route through the oracle (test infrastructure)."""
+    for base, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(base, f), errors="ignore").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), os.path.join(base, f)
+
+
+def test_dropin_state_dict_layout_and_roundtrip():
+    from oracle import diffusion_port, resnet_port, unet_port
+    from oracle.weights import make_state_dict
+    from src.models.DDPM_2D import DDPM_2D
+
+    m = DDPM_2D(_cfg(), prefix="p/")
+    exp = (["encoder.encoder." + k for k, _ in resnet_port.param_shapes(128)]
+           + ["diffusion." + k for k in diffusion_port.BUFFER_NAMES]
+           + ["diffusion.model." + k for k, _ in unet_port.param_shapes(unet_port.UNetSpec())])
+    sd = m.state_dict()
+    assert list(sd.keys()) == exp and len(exp) == 649
+    shapes = dict(unet_port.param_shapes(unet_port.UNetSpec()))
+    for k, s in shapes.items():
+        assert tuple(sd["diffusion.model." + k].shape) == s
+    # zero-initialised output convolutions, as in the reference (zero_module)
+    assert float(sd["diffusion.model.out.2.weight"].abs().sum()) == 0.0
+    assert float(sd["diffusion.model.middle_block.1.proj_out.weight"].abs().sum()) == 0.0
+    full = {k: torch.randn_like(v) if v.dtype.is_floating_point else v for k, v in sd.items()}
+    m.load_state_dict(full, strict=True)
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, full[k])
+    assert m.test_timesteps == 500 and m.prefix == "p/"
+    m.update_prefix("q/")
+    assert m.prefix == "q/"
+    assert isinstance(m.configure_optimizers(), torch.optim.Adam)
+
+
+def test_unconditioned_layout():
+    from oracle import unet_port
+    from src.models.DDPM_2D import DDPM_2D
+
+    m = DDPM_2D(_cfg(condition=False), prefix=None)
+    keys = [k for k in m.state_dict() if k.startswith("diffusion.model.")]
+    assert keys == ["diffusion.model." + k for k, _ in unet_port.param_shapes(unet_port.UNetSpec(num_classes=None))]
+    assert not hasattr(m, "encoder")
+    assert m(torch.zeros(1, 1, 96, 96)) is None
+
+
+def test_product_fails_loudly_without_cuda():
+    from cddpm import CddpmError
+    from src.models.DDPM_2D import DDPM_2D
+    from src.utils.utils_eval import apply_3d_median_filter
+
+    m = DDPM_2D(_cfg(), prefix="p/").eval()
+    with torch.no_grad():
+        with pytest.raises(CddpmError):
+            m(torch.zeros(1, 1, 96, 96))
+        with pytest.raises(CddpmError):
+            m.diffusion(torch.zeros(1, 1, 96, 96), cond=torch.zeros(1, 128), t=10, noise=torch.zeros(1, 1, 96, 96))
+    with pytest.raises((CddpmError, RuntimeError, AssertionError)):
+        apply_3d_median_filter(torch.zeros(8, 8, 8))
+    with pytest.raises(NotImplementedError):
+        m.training_step({}, 0)
+
+
+def test_schedule_buffers_are_reference_bit_exact():
+    from cddpm.diffusion import GaussianDiffusion
+
+    d = GaussianDiffusion(torch.nn.Identity(), image_size=(96, 96), timesteps=1000, objective="pred_x0", channels=1)
+    g = np.load(os.path.join(GOLD, "schedule.npz"))
+    sd = d.state_dict()
+    assert list(sd.keys()) == list(g.keys())
+    for k in sd:
+        assert np.array_equal(sd[k].numpy(), g[k]), k
+    with pytest.raises(ValueError):
+        GaussianDiffusion(torch.nn.Identity(), image_size=(96, 96), beta_schedule="nope")
+    with pytest.raises(AssertionError):
+        GaussianDiffusion(torch.nn.Identity(), image_size=(96, 96), objective="pred_v")
+
+
+def test_permutation_matches_oracle_and_rng_stream():
+    from cddpm import noise
+    from oracle import simplex_port
+
+    for seed in (1, -5, 9999999999, -10000000000):
+        assert list(noise.permutation(seed)) == simplex_port.permutation_from_seed(seed).tolist()
+    # two draws from numpy's global RNG per gen_noise call, like the reference
+    np.random.seed(3)
+    a, b = noise._new_seed(), noise._new_seed()
+    np.random.seed(3)
+    assert (simplex_port.draw_seed(), simplex_port.draw_seed()) == (a, b)
+
+
+def test_bisection_control_flow_matches_oracle():
+    from cddpm import eval_tail
+    from oracle import tail_port
+
+    rng = np.random.default_rng(0)
+    x = rng.random(4000).astype(np.float32)
+    x[rng.random(4000) < 0.5] = 0
+    y = rng.random(4000) < 0.2 + 0.5 * x
+
+    def counts(qs):
+        return [int(y.sum()), int((x > qs[0]).sum()), int(((x > qs[0]) & y).sum()), int((x > qs[1]).sum()),
+                int(((x > qs[1]) & y).sum())]
+
+    assert eval_tail._bisect(counts, (0, np.max(x)), 10) == tail_port.find_best_val(x, y, (0, np.max(x)), 10)
+    ed = eval_tail.get_eval_dictionary()
+    assert len(ed) == 108 and all(v == [] for v in ed.values())
+    assert "AnomalyScoreRegPerVol" in ed and "DiceScorePerSlice" in ed
+
+
+def test_host_side_small_rankings_match_sklearn():
+    from sklearn.metrics import auc, average_precision_score, roc_curve
+
+    from cddpm import eval_tail
+
+    rng = np.random.default_rng(2)
+    s = rng.random(96)
+    s[::5] = 0.0
+    lab = (rng.random(96) < 0.3).astype(int)
+    a, fpr, tpr, thr = eval_tail.compute_roc(s, lab)
+    f2, t2, th2 = roc_curve(lab, s, pos_label=1)
+    assert np.allclose(fpr, f2) and np.allclose(tpr, t2) and abs(a - auc(f2, t2)) < 1e-12
+    p, *_ = eval_tail.compute_prc(s, lab)
+    assert abs(p - average_precision_score(lab, s)) < 1e-12
+
+
+_GLOO_WORKER = r"""
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path[:0] = [os.environ["CDDPM_ROOT"], os.path.join(os.environ["CDDPM_ROOT"], "conditioned-diffusion-models-uad_b200")]
+from cddpm import eval_tail
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+rng = np.random.default_rng(0)
+x = rng.random(8000).astype(np.float32); x[rng.random(8000) < 0.5] = 0
+y = rng.random(8000) < 0.2 + 0.5 * x
+lo, hi = (0, 4000) if rank == 0 else (4000, 8000)   # each rank owns half of the validation voxels
+def counts(qs):
+    xs, ys = x[lo:hi], y[lo:hi]
+    c = torch.tensor([int(ys.sum()), int((xs > qs[0]).sum()), int(((xs > qs[0]) & ys).sum()),
+                      int((xs > qs[1]).sum()), int(((xs > qs[1]) & ys).sum())], dtype=torch.int64)
+    eval_tail._dist_sum(c)       # the all-reduce the sharded sweep uses (NCCL on GPUs, gloo here)
+    return c.numpy()
+top = torch.tensor([float(np.max(x[lo:hi]))]); eval_tail._dist_max(top)
+got = eval_tail._bisect(counts, (0, np.float32(top.item())), 10)
+from oracle import tail_port
+want = tail_port.find_best_val(x, y, (0, np.max(x)), 10)
+assert got == want, (got, want)
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_global_threshold_world_size_2_gloo(tmp_path):
+    """The sharded sweep's global Dice threshold (all-reduced counts) equals the serial search over all voxels."""
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    env = dict(os.environ, CDDPM_ROOT=ROOT, MASTER_ADDR="127.0.0.1", MASTER_PORT="29513", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0].decode() for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o

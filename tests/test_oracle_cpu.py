@@ -1,0 +1,155 @@
+"""CPU tests (no GPU): the oracle restatements against the golden vectors generated from the live reference
+(oracle/make_golden.py), and against scipy / sklearn where the reference calls those libraries directly."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def test_schedule_port_bit_exact():
+    from oracle import diffusion_port
+
+    g = np.load(os.path.join(GOLD, "schedule.npz"))
+    s = diffusion_port.schedule_buffers()
+    assert list(s.keys()) == diffusion_port.BUFFER_NAMES == list(g.keys())
+    for k in s:
+        assert np.array_equal(s[k].numpy(), g[k]), k
+    # survey probe values
+    assert abs(float(s["sqrt_alphas_cumprod"][499]) - 0.70274) < 1e-5
+
+
+def test_simplex_port_bit_exact():
+    from oracle.simplex_port import gen_noise_port
+
+    g = np.load(os.path.join(GOLD, "simplex.npz"))
+    for seed in (0, 7):
+        np.random.seed(seed)
+        n = gen_noise_port((2, 1, 96, 96))
+        assert n.dtype == torch.float16
+        assert np.array_equal(n[0, 0].numpy(), g[f"field_seed{seed}"])
+        assert torch.equal(n[0], n[1])  # one field shared by the whole batch
+
+
+def test_unet_port_small_matches_reference():
+    from oracle import unet_port
+    from oracle.weights import make_state_dict
+
+    spec = unet_port.UNetSpec(model_channels=64, channel_mult=(1, 2), num_res_blocks=1, num_classes=128)
+    sd = make_state_dict(unet_port.param_shapes(spec), seed=2)
+    g = np.load(os.path.join(GOLD, "unet_small_32.npz"))
+    with torch.no_grad():
+        y = unet_port.unet_forward(sd, spec, torch.from_numpy(g["x"]), torch.from_numpy(g["t"]), torch.from_numpy(g["cond"]))
+    assert (y - torch.from_numpy(g["y"])).abs().max().item() < 1e-4
+
+
+def test_unet_key_layout_matches_reference():
+    from oracle import unet_port
+
+    keys = json.load(open(os.path.join(GOLD, "unet_cond_keys.json")))
+    mine = unet_port.param_shapes(unet_port.UNetSpec())
+    assert [[k, list(s)] for k, s in mine] == keys
+    assert len(mine) == 316 and sum(int(np.prod(s)) for _, s in mine) == 43871873
+
+
+def test_diffusion_port_matches_reference():
+    from oracle import diffusion_port, unet_port
+    from oracle.weights import make_state_dict
+
+    spec = unet_port.UNetSpec(model_channels=64, channel_mult=(1, 2), num_res_blocks=1, num_classes=128)
+    sd = make_state_dict(unet_port.param_shapes(spec), seed=2)
+    g = np.load(os.path.join(GOLD, "diffusion_small_32.npz"))
+    img, cond, noise = (torch.from_numpy(g[k]) for k in ("img", "cond", "noise"))
+    model = lambda x, t, c: unet_port.unet_forward(sd, spec, x, t, c)  # noqa: E731
+    sched = diffusion_port.schedule_buffers()
+    with torch.no_grad():
+        for obj in ("pred_x0", "pred_noise"):
+            loss, reco = diffusion_port.reconstruct(model, sched, img, 499, cond, noise, objective=obj)
+            assert (reco - torch.from_numpy(g[f"reco_{obj}"])).abs().max().item() < 1e-4
+            assert abs(loss.item() - float(g[f"loss_{obj}"])) < 1e-5
+        feed = list(torch.from_numpy(g["reverse_noises"]))
+        rec = diffusion_port.reverse_loop(model, sched, img * 2 - 1, cond, int(g["reverse_T0"]), lambda: feed.pop(0))
+    assert (rec - torch.from_numpy(g["reverse_out"])).abs().max().item() < 1e-4
+
+
+def test_stencil_ports_vs_golden_and_scipy():
+    from scipy import ndimage
+
+    from oracle import tail_port
+
+    g = np.load(os.path.join(GOLD, "stencil.npz"))
+    for hw in (32, 56, 24):
+        vol, mask = g[f"vol{hw}"], g[f"mask{hw}"].astype(np.float32)
+        masked = tail_port.apply_brainmask_volume(vol, mask)
+        assert np.array_equal(masked, g[f"masked{hw}"])
+        assert np.array_equal(tail_port.median_filter_3d(masked, 5), g[f"filtered{hw}"])
+    # the equivalences the restatement relies on, directly against scipy (the reference's own callee)
+    rng = np.random.default_rng(0)
+    m = rng.random((40, 40)) > 0.1
+    assert np.array_equal(tail_port.erode_cross(m, 3),
+                          ndimage.binary_erosion(m, structure=ndimage.generate_binary_structure(2, 1), iterations=3))
+    v = rng.random((20, 18, 7)).astype(np.float32)
+    assert np.array_equal(tail_port.median_filter_3d(v, 5), ndimage.median_filter(v, (5, 5, 5)))
+    assert np.array_equal(tail_port.median_filter_3d(v, 3), ndimage.median_filter(v, (3, 3, 3)))
+
+
+def test_ranking_ports_vs_sklearn():
+    from sklearn.metrics import auc, average_precision_score, roc_curve
+
+    from oracle import tail_port
+
+    rng = np.random.default_rng(1)
+    x = rng.random(5000).astype(np.float32)
+    x[rng.random(5000) < 0.6] = 0.0  # heavy ties, like a masked residual volume
+    y = rng.random(5000) < (0.05 + 0.4 * x)
+    fpr, tpr, _ = roc_curve(y.astype(int), x, pos_label=1)
+    assert abs(tail_port.roc_auc(x, y) - auc(fpr, tpr)) < 1e-12
+    assert abs(tail_port.average_precision(x, y) - average_precision_score(y.astype(int), x)) < 1e-12
+
+
+def test_find_best_val_quirks():
+    from oracle import tail_port
+
+    x = np.array([0.0, 0.1, 0.2, 0.9, 0.95], dtype=np.float32)
+    y = np.array([0, 0, 0, 1, 1], dtype=bool)
+    d, t = tail_port.find_best_val(x, y, val_range=(0, np.max(x)), max_steps=10)
+    assert d == 1.0 and 0.2 <= t < 0.9
+    # degenerate range (all-zero residual): (lo, 1) is searched instead (utils_eval.py:512-513)
+    d0, t0 = tail_port.find_best_val(np.zeros(4, np.float32), np.array([1, 0, 0, 0], bool), val_range=(0, 0.0), max_steps=3)
+    assert d0 == 0.0
+    # empty segmentation: Dice is NaN everywhere and the (0, 0) initialisation is returned (Appendix B.16)
+    with np.errstate(all="ignore"):
+        dn, tn = tail_port.find_best_val(np.zeros(4, np.float32), np.zeros(4, bool), val_range=(0, 1.0), max_steps=3)
+    assert (dn, tn) == (0, 0)
+
+
+def test_volume_tail_port_matches_reference_golden():
+    from oracle import tail_port
+    from oracle.weights import synthetic_volume
+
+    gold = json.load(open(os.path.join(GOLD, "tail.json")))["d4"]
+    for i in (0, 1):
+        v = synthetic_volume(i, depth=4)
+        p = tail_port.volume_tail(v["reco"][0, 0].numpy(), v["vol"][0, 0].numpy(), v["seg_orig"][0, 0].numpy(),
+                                  v["mask_orig"][0, 0].numpy(), stage="val")
+        assert p["BestThreshold"] == np.float32(gold["val"]["BestThresholdPerVol"][i])
+        assert p["Dice"] == gold["val"]["DiceScorePerVol"][i]
+        assert (p["TP"], p["FP"], p["TN"], p["FN"]) == tuple(int(gold["val"][k][i]) for k in ("TPPerVol", "FPPerVol", "TNPerVol", "FNPerVol"))
+        assert abs(p["AUPRC"] - gold["val"]["AUPRCPerVol"][i]) < 1e-12
+        assert abs(float(p["diff_filtered"].astype(np.float64).sum()) - gold["filtered_sum"][i]) < 1e-9
+
+
+def test_encoder_port_matches_golden():
+    from oracle import resnet_port
+    from oracle.weights import make_state_dict
+
+    sd = make_state_dict(resnet_port.param_shapes(128), seed=3)
+    g = np.load(os.path.join(GOLD, "encoder_96.npz"))
+    with torch.no_grad():
+        c = resnet_port.resnet_forward(sd, torch.from_numpy(g["x"]))
+    assert (c - torch.from_numpy(g["c"])).abs().max().item() < 1e-4
+    assert len(resnet_port.param_shapes(128)) == 320
