@@ -144,23 +144,41 @@ def cpu_reference_sample(batch: int, rev_steps: int, start_t: int, threads: int)
     return batch / total, {"t_encoder_s": t_enc, "t_per_reverse_step_s": per_step}
 
 
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def best_cpu_sample(start_t, threads, rev_steps=2):
+    """oneDNN picks very different convolution paths for batch 1 and batch 2 on some hosts; report the faster one."""
+    best = None
+    for b in (1, 2):
+        v, parts = cpu_reference_sample(b, rev_steps, start_t, threads)
+        if best is None or v > best[0]:
+            best = (v, parts, b)
+    return best
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    B, S = 2, 2
+    threads = host_threads()
+    S = 2
     for _ in range(args.warmup):
-        cpu_reference_sample(B, 1, args.start_t, threads)
+        cpu_reference_sample(1, 1, args.start_t, threads)
     vals = []
     t0 = time.perf_counter()
+    B = 1
     for _ in range(args.steps):
-        v, _ = cpu_reference_sample(B, S, args.start_t, threads)
+        v, _, B = best_cpu_sample(args.start_t, threads, S)
         vals.append(v)
     dt = (time.perf_counter() - t0) / max(1, args.steps)
     v = statistics.median(vals)
-    sample = (f"oracle port (fp32 PyTorch restatement of the reference CPU path), {B} slices x {S} reverse steps + encoder "
-              f"per step, extrapolated x{args.start_t // S} to the {args.start_t}-step loop")
+    sample = (f"oracle port (fp32 PyTorch restatement of the reference CPU path), best of batch 1 / batch 2 (here {B}) x {S} "
+              f"reverse steps + encoder per step, extrapolated x{args.start_t // S} to the {args.start_t}-step loop")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "slices/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -303,11 +321,11 @@ def run_ours(args):
             "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
             "single_step_equiv_slices_per_s": value * T0}
     if world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        v, parts = cpu_reference_sample(2, 2, T0, threads)
+        threads = host_threads()
+        v, parts, bb = best_cpu_sample(T0, threads, 2)
         line["cpu_baseline"] = {"value": v, "unit": "slices/s", "cores": threads, "kind": "port",
-                                "sample": f"oracle port (fp32 PyTorch) on the host: 2 slices x 2 reverse steps + encoder, "
-                                          f"extrapolated to the {T0}-step loop", **parts}
+                                "sample": f"oracle port (fp32 PyTorch) on the host: best of batch 1 / batch 2 (here {bb}) x 2 "
+                                          f"reverse steps + encoder, extrapolated to the {T0}-step loop", **parts}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
