@@ -23,6 +23,8 @@ namespace {
 
 constexpr int kAStageBytes = kConvTileM * kConvBlockK * 2;  // 16 KiB
 constexpr int kSmemBudget = 227 * 1024;
+constexpr int kStatW = 128;                      // (n_tile / 32) chunks x 16 values, n_tile <= 256
+constexpr int kStatBytes = 2 * 4 * kStatW * 4;   // two accumulator stages x four epilogue warps
 
 struct TapShift {
   int dy, dx;
@@ -61,6 +63,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
   uint64_t* tfull_bar = empty_bar + num_stages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  // [2 accumulator stages][4 epilogue warps][kStatW] staging of GroupNorm partial sums
+  float* stat_sh = reinterpret_cast<float*>(smem + num_stages * stage_bytes + 256);
 
   int num_ksteps = 0;
   for (int s = 0; s < p.num_src; ++s) num_ksteps += p.src_taps[s] * (p.src_c[s] / kConvBlockK);
@@ -242,6 +246,36 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
           }
+          if (p.gn_stats != nullptr) {
+            // GroupNorm statistics of the tensor being produced, at 4-channel granularity: per thread 8 buckets of
+            // (sum, sum of squares) over its pixel, then a butterfly over the warp's 32 pixels (16 shuffles) that leaves
+            // value (lane >> 1) & 15 in each lane; the four epilogue warps meet in shared memory below.
+            float v16[16];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              float s = 0.f, q = 0.f;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                s += f[4 * k + j];
+                q = fmaf(f[4 * k + j], f[4 * k + j], q);
+              }
+              v16[k] = s;
+              v16[8 + k] = q;
+            }
+#pragma unroll
+            for (int w = 8; w >= 1; w >>= 1) {
+              const int m = w * 2;
+              const bool hi = (lane & m) != 0;
+#pragma unroll
+              for (int k = 0; k < w; ++k) {
+                const float keep = hi ? v16[k + w] : v16[k];
+                const float send = hi ? v16[k] : v16[k + w];
+                v16[k] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+              }
+            }
+            const float tot = v16[0] + __shfl_xor_sync(0xffffffffu, v16[0], 1);
+            if ((lane & 1) == 0) stat_sh[(acc * 4 + quarter) * kStatW + c * 16 + (lane >> 1)] = tot;
+          }
           if (p.out_is_f32) {
             float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off + c * 32);
 #pragma unroll
@@ -257,6 +291,27 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
               o.w = pack_16bit(f[q * 8 + 6], f[q * 8 + 7], fmt);
               op[q] = o;
             }
+          }
+        }
+      }
+      if (p.gn_stats != nullptr) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+        const int nvals = nchunks * 16;
+        if (row < nvals) {
+          const int within = row & 15;
+          const int is_q = within >> 3;
+          const int bucket = (row >> 4) * 8 + (within & 7);
+          const float* sp = stat_sh + acc * 4 * kStatW + row;
+          const int gb = n_idx * (p.n_tile >> 2) + bucket;
+          const int nb4 = p.Cout >> 2;
+          const int wpb = 4 / p.boxes_per_tile;  // warps per spatial box (4 or 2)
+          for (int b2 = 0; b2 < p.boxes_per_tile; ++b2) {
+            const int bx = m_tile * p.boxes_per_tile + b2;
+            if (bx >= p.total_boxes) continue;
+            const int nimg = bx / boxes_per_img;
+            float t = 0.f;
+            for (int w = 0; w < wpb; ++w) t += sp[(b2 * wpb + w) * kStatW];
+            atomicAdd(&p.gn_stats[(static_cast<size_t>(nimg) * nb4 + gb) * 2 + is_q], static_cast<double>(t));
           }
         }
       }
@@ -371,7 +426,7 @@ int build_conv_params(const ConvDesc& d, ConvIgemmParams* p) {
   while (cols < 2 * n_tile) cols *= 2;
   p->tmem_cols = cols;
   const int stage_bytes = kAStageBytes + n_tile * kConvBlockK * 2;
-  int stages = (kSmemBudget - 2048) / stage_bytes;
+  int stages = (kSmemBudget - 2048 - kStatBytes) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) return fail(kUnsupported, "conv: not enough shared memory for a 2-stage pipeline");
   p->num_stages = stages;
@@ -380,8 +435,8 @@ int build_conv_params(const ConvDesc& d, ConvIgemmParams* p) {
   p->bias = d.bias;
   p->residual = reinterpret_cast<const bf16*>(d.residual);
   p->out = d.out;
-  p->gn_partial = d.gn_partial;
-  p->gn_cpg = d.gn_cpg;
+  p->gn_stats = flat ? nullptr : d.gn_stats;
+  if (p->gn_stats != nullptr && (d.out_is_f32 || d.Cout % 32 != 0)) return fail(kUnsupported, "conv: gn_stats needs a 16-bit output");
 
   int ktot = 0;
   for (int s = 0; s < d.num_src; ++s) {
@@ -419,7 +474,7 @@ int launch_conv_igemm(const ConvIgemmParams& p, cudaStream_t stream, int max_cta
     attr_set = true;
   }
   const int stage_bytes = kAStageBytes + p.n_tile * kConvBlockK * 2;
-  const int smem = p.num_stages * stage_bytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  const int smem = p.num_stages * stage_bytes + 1024 /*alignment slack*/ + 256 /*barriers*/ + kStatBytes;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   int grid = device_sm_count();
   if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;

@@ -35,8 +35,8 @@ struct ConvIgemmParams {
   const float* bias;     // [Cout] or nullptr
   const bf16* residual;  // [B,H,W,Cout] or nullptr (same 16-bit type as the activations)
   void* out;             // [B,H,W,Cout] 16-bit, or fp32 when out_is_f32
-  float* gn_partial;     // optional [num_boxes][Cout/gn_cpg][2] per-box (sum, sumsq) of the stored output
-  int gn_cpg;            // channels per statistics bucket (divides 32)
+  double* gn_stats;      // optional [B][Cout/4][2]: (sum, sum of squares) of the produced tensor per image and
+                         // 4-channel bucket, accumulated with atomics (the caller zeroes it) — feeds the next GroupNorm
   int flat;              // plain GEMM: A is a row-major [M][C] matrix (2-D tensor map), one source, taps == 1
   int M;                 // rows of the flat problem
   int relu;              // clamp the result at 0 after bias and residual
@@ -55,8 +55,7 @@ struct ConvDesc {
   void* out = nullptr;
   int out_is_f32 = 0;
   int ab_format = 1;
-  float* gn_partial = nullptr;
-  int gn_cpg = 0;
+  double* gn_stats = nullptr;
   int flat_rows = 0;  // > 0: plain GEMM over src[0] = [flat_rows][src_c[0]] (B/H/W ignored), e.g. nn.Linear or an
                       // im2col'ed convolution
   int relu = 0;

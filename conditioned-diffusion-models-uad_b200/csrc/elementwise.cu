@@ -38,7 +38,8 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8], int fmt) {
   o.w = pack2(f[6], f[7], fmt);
   return o;
 }
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// SiLU with the approximate exp / divide units: ~2 ulp, far below the 16-bit rounding of the stored activation.
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 // ---------------------------------------------------------------------------------------------- GroupNorm stats
 __global__ void __launch_bounds__(256) gn_stats_kernel(const uint16_t* __restrict__ p0, const uint16_t* __restrict__ p1,
@@ -102,6 +103,8 @@ struct GnApplyDev {
   const uint16_t* p1;
   int c0, c1, H, W, Ho, Wo, Pout, nchunks_stats, P_stats;
   const float* partial;
+  const double* stats0;
+  const double* stats1;
   const float* gamma;
   const float* beta;
   const float* film;
@@ -109,6 +112,35 @@ struct GnApplyDev {
   uint16_t* out;
   uint16_t* raw_out;
 };
+
+// (sum, sum of squares) per image and 4-channel bucket of an NHWC tensor, accumulated into stats[B][C/4][2] (double
+// atomics; the caller zeroes it).  Used for tensors whose producer is not the tcgen05 convolution (the stem).
+__global__ void __launch_bounds__(256) gn_stats4_kernel(const uint16_t* __restrict__ x, int C, int HW, int P,
+                                                        double* __restrict__ stats, int fmt) {
+  const int nvec = C >> 3;
+  const int lanes = blockDim.x / nvec;
+  const int chunk = blockIdx.x, b = blockIdx.y;
+  const int v = threadIdx.x % nvec;
+  const int pl = threadIdx.x / nvec;
+  if (pl >= lanes) return;
+  float s[2] = {0.f, 0.f}, q[2] = {0.f, 0.f};
+  const size_t base = static_cast<size_t>(b) * HW;
+  for (int p = chunk * P + pl; p < (chunk + 1) * P; p += lanes) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + (base + p) * C + v * 8));
+    float f[8];
+    unpack8(u, fmt, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j >> 2] += f[j];
+      q[j >> 2] = fmaf(f[j], f[j], q[j >> 2]);
+    }
+  }
+  double* o = stats + (static_cast<size_t>(b) * (C >> 2) + v * 2) * 2;
+  atomicAdd(o + 0, static_cast<double>(s[0]));
+  atomicAdd(o + 1, static_cast<double>(q[0]));
+  atomicAdd(o + 2, static_cast<double>(s[1]));
+  atomicAdd(o + 3, static_cast<double>(q[1]));
+}
 
 __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyDev a) {
   extern __shared__ float sh[];  // A[C], Bc[C], mean[32], rstd[32]
@@ -121,10 +153,21 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyDev a) {
   const int cpg = C / kGnGroups;
   if (threadIdx.x < kGnGroups) {
     double s = 0.0, q = 0.0;
-    const float* pp = a.partial + (static_cast<size_t>(b) * a.nchunks_stats * kGnGroups + threadIdx.x) * 2;
-    for (int k = 0; k < a.nchunks_stats; ++k) {
-      s += static_cast<double>(pp[static_cast<size_t>(k) * kGnGroups * 2]);
-      q += static_cast<double>(pp[static_cast<size_t>(k) * kGnGroups * 2 + 1]);
+    if (a.stats0 != nullptr) {
+      // statistics emitted by the producers' epilogues at 4-channel granularity, one array per concat member
+      const int nb0 = a.c0 >> 2;
+      for (int j = threadIdx.x * (cpg >> 2); j < (threadIdx.x + 1) * (cpg >> 2); ++j) {
+        const double* sp = (j < nb0) ? a.stats0 + (static_cast<size_t>(b) * nb0 + j) * 2
+                                     : a.stats1 + (static_cast<size_t>(b) * (a.c1 >> 2) + (j - nb0)) * 2;
+        s += sp[0];
+        q += sp[1];
+      }
+    } else {
+      const float* pp = a.partial + (static_cast<size_t>(b) * a.nchunks_stats * kGnGroups + threadIdx.x) * 2;
+      for (int k = 0; k < a.nchunks_stats; ++k) {
+        s += static_cast<double>(pp[static_cast<size_t>(k) * kGnGroups * 2]);
+        q += static_cast<double>(pp[static_cast<size_t>(k) * kGnGroups * 2 + 1]);
+      }
     }
     const double n = static_cast<double>(a.H) * a.W * cpg;
     const double mean = s / n;
@@ -199,16 +242,36 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnApplyDev a) {
         r[j] *= 0.25f;
       }
     } else {
-      const int iy = (a.mode == kResampleUp2) ? (oy >> 1) : oy;
-      const int ix = (a.mode == kResampleUp2) ? (ox >> 1) : ox;
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + (in_base + static_cast<size_t>(iy) * a.W + ix) * cs + cbs));
-      unpack8(u, a.fmt, r);
+      // batch four pixels per thread: all loads first, so four 16-byte requests are in flight per thread
+      constexpr int kU = 4;
+      uint4 u[kU];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float t = fmaf(r[j], A[j], Bc[j]);
-        if (a.silu) t = silu_f(t);
-        y[j] = t;
+      for (int k = 0; k < kU; ++k) {
+        const int opk = op + k * lanes;
+        if (opk < p_end) {
+          const int oyk = opk / a.Wo, oxk = opk - oyk * a.Wo;
+          const int iy = (a.mode == kResampleUp2) ? (oyk >> 1) : oyk;
+          const int ix = (a.mode == kResampleUp2) ? (oxk >> 1) : oxk;
+          u[k] = __ldg(reinterpret_cast<const uint4*>(src + (in_base + static_cast<size_t>(iy) * a.W + ix) * cs + cbs));
+        }
       }
+#pragma unroll
+      for (int k = 0; k < kU; ++k) {
+        const int opk = op + k * lanes;
+        if (opk < p_end) {
+          unpack8(u[k], a.fmt, r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float t = fmaf(r[j], A[j], Bc[j]);
+            if (a.silu) t = silu_f(t);
+            y[j] = t;
+          }
+          *reinterpret_cast<uint4*>(a.out + (out_base + opk) * C + cb) = pack8(y, a.fmt);
+          if (a.raw_out != nullptr) *reinterpret_cast<uint4*>(a.raw_out + (out_base + opk) * C + cb) = pack8(r, a.fmt);
+        }
+      }
+      op += (kU - 1) * lanes;
+      continue;
     }
     *reinterpret_cast<uint4*>(a.out + (out_base + op) * C + cb) = pack8(y, a.fmt);
     if (a.raw_out != nullptr) *reinterpret_cast<uint4*>(a.raw_out + (out_base + op) * C + cb) = pack8(r, a.fmt);
@@ -220,7 +283,8 @@ constexpr int kLinBT = 8;
 __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ in, int in_stride,
                                                      const float* __restrict__ W, const float* __restrict__ bias,
                                                      float* __restrict__ out, int out_stride, int B, int I, int O,
-                                                     int act_in, int act_out) {
+                                                     int act_in, int act_out, uint16_t* __restrict__ out16,
+                                                     int out16_stride, int fmt) {
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int warp_global = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
@@ -250,7 +314,18 @@ __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ i
         if (lane == 0 && b0 + j < B) {
           v += (bias != nullptr) ? bias[o] : 0.f;
           if (act_out) v = v / (1.0f + expf(-v));
-          out[static_cast<size_t>(b0 + j) * out_stride + o] = v;
+          if (out != nullptr) out[static_cast<size_t>(b0 + j) * out_stride + o] = v;
+          if (out16 != nullptr) {
+            uint16_t bits;
+            if (fmt == 1) {
+              __nv_bfloat16 h = __float2bfloat16_rn(v);
+              bits = *reinterpret_cast<uint16_t*>(&h);
+            } else {
+              __half h = __float2half_rn(v);
+              bits = *reinterpret_cast<uint16_t*>(&h);
+            }
+            out16[static_cast<size_t>(b0 + j) * out16_stride + o] = bits;
+          }
         }
       }
     }
@@ -286,20 +361,28 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
   const int pl = threadIdx.x / ngrp;
   if (pl >= ppb) return;
   const size_t total = static_cast<size_t>(B) * H * W;
+  // this thread always produces the same 8 output channels: keep its 72 weights + 8 biases in registers
+  float wr[9][8], br[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) br[j] = sw[9 * Cout + g * 8 + j];
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wr[tap][j] = sw[tap * Cout + g * 8 + j];
   for (size_t pix = static_cast<size_t>(blockIdx.x) * ppb + pl; pix < total; pix += static_cast<size_t>(gridDim.x) * ppb) {
     const int xw = static_cast<int>(pix % W);
     const int yh = static_cast<int>((pix / W) % H);
     const size_t n = pix / (static_cast<size_t>(W) * H);
     float acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = sw[9 * Cout + g * 8 + j];
+    for (int j = 0; j < 8; ++j) acc[j] = br[j];
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
       const int iy = yh + tap / 3 - 1, ix = xw + tap % 3 - 1;
       float v = 0.f;
       if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(x + (n * H + iy) * W + ix);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, sw[tap * Cout + g * 8 + j], acc[j]);
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wr[tap][j], acc[j]);
     }
     *reinterpret_cast<uint4*>(out + pix * Cout + g * 8) = pack8(acc, fmt);
   }
@@ -314,34 +397,39 @@ __global__ void __launch_bounds__(256) conv_out_kernel(const uint16_t* __restric
     sw[i] = w[c * 9 + tap];
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int wpb = blockDim.x >> 5;
+  // a group of G = min(16, C/8) threads shares one pixel; each thread owns 8-channel vectors v, v+G, ...
+  const int nvec = C >> 3;
+  const int G = nvec < 16 ? nvec : 16;  // power of two for C in {64, 128, 256, ...}
+  const int sub = threadIdx.x % G;
+  const int ppb = blockDim.x / G;
   const size_t total = static_cast<size_t>(B) * H * W;
-  for (size_t pix = static_cast<size_t>(blockIdx.x) * wpb + (threadIdx.x >> 5); pix < total;
-       pix += static_cast<size_t>(gridDim.x) * wpb) {
-    const int xw = static_cast<int>(pix % W);
-    const int yh = static_cast<int>((pix / W) % H);
-    const size_t n = pix / (static_cast<size_t>(W) * H);
+  const size_t rounds = (total + static_cast<size_t>(gridDim.x) * ppb - 1) / (static_cast<size_t>(gridDim.x) * ppb);
+  for (size_t r = 0; r < rounds; ++r) {
+    const size_t pix = (r * gridDim.x + blockIdx.x) * ppb + threadIdx.x / G;
+    const bool live = pix < total;
     float acc = 0.f;
-    for (int tap = 0; tap < 9; ++tap) {
-      const int iy = yh + tap / 3 - 1, ix = xw + tap % 3 - 1;
-      if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
-      const uint16_t* row = x + ((n * H + iy) * W + ix) * C;
-      for (int c = lane * 2; c < C; c += 64) {
-        const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(row + c));
-        float2 f;
-        if (fmt == 1) {
-          f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
-        } else {
-          f = __half22float2(*reinterpret_cast<const __half2*>(&u));
+    if (live) {
+      const int xw = static_cast<int>(pix % W);
+      const int yh = static_cast<int>((pix / W) % H);
+      const size_t n = pix / (static_cast<size_t>(W) * H);
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int iy = yh + tap / 3 - 1, ix = xw + tap % 3 - 1;
+        if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+        const uint16_t* row = x + ((n * H + iy) * W + ix) * C;
+        for (int v = sub; v < nvec; v += G) {
+          const uint4 u = __ldg(reinterpret_cast<const uint4*>(row + v * 8));
+          float f[8];
+          unpack8(u, fmt, f);
+          const float* wv = &sw[tap * C + v * 8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc = fmaf(f[j], wv[j], acc);
         }
-        acc = fmaf(f.x, sw[tap * C + c], acc);
-        acc = fmaf(f.y, sw[tap * C + c + 1], acc);
       }
     }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (lane == 0) out[pix] = acc + bias[0];
+    // all 32 lanes take part in the shuffles (dead pixels contribute 0)
+    for (int off = G >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (live && sub == 0) out[pix] = acc + bias[0];
   }
 }
 
@@ -390,9 +478,23 @@ int launch_gn_stats(const CatView& x, int B, int HW, float* partial, int fmt, cu
   return check_launch("gn_stats_kernel");
 }
 
+int launch_gn_stats4(const void* x, int C, int B, int HW, double* stats, int fmt, cudaStream_t stream) {
+  if (!x || !stats) return fail(kInvalidArgument, "gn_stats4: null pointer");
+  if (C % 8 != 0 || C / 8 > 256 || HW % 64 != 0) return fail(kUnsupported, "gn_stats4: unsupported shape");
+  const int k = gn_pick_chunks(B, HW);
+  const int nvec = C / 8;
+  const int threads = (256 / nvec) * nvec;
+  dim3 grid(k, B);
+  gn_stats4_kernel<<<grid, threads, 0, stream>>>(reinterpret_cast<const uint16_t*>(x), C, HW, HW / k, stats, fmt);
+  return check_launch("gn_stats4_kernel");
+}
+
 int launch_gn_apply(const GnApplyArgs& a, cudaStream_t stream) {
   CDDPM_TRY(check_view(a.x, "gn_apply"));
-  if (!a.partial || !a.gamma || !a.beta || !a.out) return fail(kInvalidArgument, "gn_apply: null pointer");
+  if ((!a.partial && !a.stats0) || !a.gamma || !a.beta || !a.out) return fail(kInvalidArgument, "gn_apply: null pointer");
+  if (a.stats0 && a.x.c1 > 0 && !a.stats1) return fail(kInvalidArgument, "gn_apply: missing statistics of the second source");
+  if (a.stats0 && ((a.x.C() / kGnGroups) % 4 != 0 || a.x.c0 % 4 != 0))
+    return fail(kUnsupported, "gn_apply: 4-channel statistics need group size and concat split to be multiples of 4");
   const int HW = a.H * a.W;
   if (HW % 64 != 0) return fail(kUnsupported, "gn_apply: H*W must be a multiple of 64");
   if (a.mode == kResampleDown2 && ((a.H | a.W) & 1)) return fail(kInvalidArgument, "gn_apply: odd size for avg-pool");
@@ -408,6 +510,8 @@ int launch_gn_apply(const GnApplyArgs& a, cudaStream_t stream) {
   d.nchunks_stats = gn_pick_chunks(a.B, HW);
   d.P_stats = HW / d.nchunks_stats;
   d.partial = a.partial;
+  d.stats0 = a.stats0;
+  d.stats1 = a.stats1;
   d.gamma = a.gamma;
   d.beta = a.beta;
   d.film = a.film;
@@ -420,7 +524,7 @@ int launch_gn_apply(const GnApplyArgs& a, cudaStream_t stream) {
   d.raw_out = reinterpret_cast<uint16_t*>(a.raw_out);
   const int C = a.x.C();
   const int HWo = d.Ho * d.Wo;
-  d.Pout = 128;
+  d.Pout = 256;
   const int nvec = C / 8;
   const int threads = (256 / nvec) * nvec;
   dim3 grid((HWo + d.Pout - 1) / d.Pout, a.B);
@@ -430,11 +534,18 @@ int launch_gn_apply(const GnApplyArgs& a, cudaStream_t stream) {
 
 int launch_linear_ex(const float* in, int in_stride, const float* W, const float* bias, float* out, int out_stride,
                      int B, int I, int O, int act_in, int act_out, cudaStream_t stream) {
-  if (!in || !W || !out) return fail(kInvalidArgument, "linear: null pointer");
+  return launch_linear_16(in, in_stride, W, bias, out, out_stride, B, I, O, act_in, act_out, nullptr, 0, 0, stream);
+}
+
+int launch_linear_16(const float* in, int in_stride, const float* W, const float* bias, float* out, int out_stride,
+                     int B, int I, int O, int act_in, int act_out, void* out16, int out16_stride, int fmt,
+                     cudaStream_t stream) {
+  if (!in || !W || (!out && !out16)) return fail(kInvalidArgument, "linear: null pointer");
   int blocks = (O + 7) / 8;
   if (blocks > 8192) blocks = 8192;
   if (blocks < 1) blocks = 1;
-  linear_kernel<<<blocks, 256, 0, stream>>>(in, in_stride, W, bias, out, out_stride, B, I, O, act_in, act_out);
+  linear_kernel<<<blocks, 256, 0, stream>>>(in, in_stride, W, bias, out, out_stride, B, I, O, act_in, act_out,
+                                            reinterpret_cast<uint16_t*>(out16), out16_stride, fmt);
   return check_launch("linear_kernel");
 }
 
@@ -467,7 +578,9 @@ int launch_conv_out(const void* x, const float* w, const float* bias, float* out
                     int fmt, cudaStream_t stream) {
   if (C % 64 != 0) return fail(kUnsupported, "conv_out: C must be a multiple of 64");
   const size_t total = static_cast<size_t>(B) * H * W;
-  int blocks = static_cast<int>((total + 7) / 8);
+  const int G = (C / 8) < 16 ? (C / 8) : 16;
+  const int ppb = 256 / G;
+  int blocks = static_cast<int>((total + ppb - 1) / ppb);
   if (blocks > 148 * 16) blocks = 148 * 16;
   conv_out_kernel<<<blocks, 256, 9 * C * sizeof(float), stream>>>(reinterpret_cast<const uint16_t*>(x), w, bias, out, B, H,
                                                                  W, C, fmt);

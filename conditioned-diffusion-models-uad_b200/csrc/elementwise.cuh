@@ -25,11 +25,15 @@ int gn_num_chunks(int B, int HW);
 // partial[b][chunk][32][2] = (sum, sum of squares) over the chunk's pixels and the group's channels.
 // GroupNorm32 statistics: src/models/LDM/modules/diffusionmodules/util.py:214-216 (fp32, eps 1e-5).
 int launch_gn_stats(const CatView& x, int B, int HW, float* partial, int fmt, cudaStream_t stream);
+// stats[B][C/4][2] += (sum, sumsq) per image and 4-channel bucket (double atomics; zero it first).
+int launch_gn_stats4(const void* x, int C, int B, int HW, double* stats, int fmt, cudaStream_t stream);
 
 struct GnApplyArgs {
   CatView x;
   int B = 0, H = 0, W = 0;    // input spatial size
-  const float* partial = nullptr;  // from launch_gn_stats over the same view
+  const float* partial = nullptr;  // from launch_gn_stats over the same view, OR
+  const double* stats0 = nullptr;  // [B][c0/4][2] (sum, sumsq) per 4-channel bucket of the first source (conv epilogue /
+  const double* stats1 = nullptr;  // launch_gn_stats4), and of the second source when the view is a concat
   const float* gamma = nullptr;    // [C]
   const float* beta = nullptr;     // [C]
   const float* film = nullptr;     // optional [B][film_stride]: scale at [film_off + c], shift at [film_off + C + c]
@@ -51,6 +55,10 @@ int launch_linear(const float* in, int in_stride, const float* W, const float* b
 // Same with an optional SiLU on the output as well (lets the embedding MLP keep only activated values).
 int launch_linear_ex(const float* in, int in_stride, const float* W, const float* bias, float* out, int out_stride,
                      int B, int I, int O, int act_in, int act_out, cudaStream_t stream);
+// ... and an optional 16-bit copy of the result (the tensor-core operand of the FiLM projection); `out` may be NULL.
+int launch_linear_16(const float* in, int in_stride, const float* W, const float* bias, float* out, int out_stride,
+                     int B, int I, int O, int act_in, int act_out, void* out16, int out16_stride, int fmt,
+                     cudaStream_t stream);
 
 // emb[b][0:half] = cos(t_b * f_i), emb[b][half:] = sin(t_b * f_i), f_i = exp(-ln(1e4) * i / half) (util.py:151-171).
 int launch_timestep_embedding(const int64_t* t, float* emb, int B, int dim, cudaStream_t stream);

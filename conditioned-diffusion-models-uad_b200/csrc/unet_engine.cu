@@ -102,10 +102,9 @@ int UNetEngine::add_res(const std::string& prefix, int c0, int c1, int cout, int
     UNetEngine* self = this;
     CDDPM_TRY(add_param(prefix + ".emb_layers.1.weight", static_cast<int64_t>(2) * cout * E,
                         [=](const float* src, cudaStream_t s) {
-                          return check_cuda(cudaMemcpyAsync(self->film_w + static_cast<size_t>(off) * E, src,
-                                                            static_cast<size_t>(2) * cout * E * sizeof(float),
-                                                            cudaMemcpyDeviceToDevice, s),
-                                            "film weight copy");
+                          // rows [off, off + 2*cout) of the 16-bit K-major FiLM panel (a 1x1 "conv" over E channels)
+                          return launch_pack_conv_weight(src, 2 * cout, E, 1, 0, E,
+                                                         self->film_w16 + static_cast<size_t>(off) * E, E, 0, fmt, s);
                         }));
     CDDPM_TRY(add_param(prefix + ".emb_layers.1.bias", 2 * cout, [=](const float* src, cudaStream_t s) {
       return check_cuda(cudaMemcpyAsync(self->film_b + off, src, static_cast<size_t>(2) * cout * sizeof(float),
@@ -267,7 +266,7 @@ int UNetEngine::build_layers() {
   CDDPM_TRY(add_copy_param("out.2.bias", cfg_.out_channels, &head_b));
   if (ch != mc) return fail(kUnsupported, "UNet head expects model_channels at the output");
   // concatenated FiLM projection
-  CDDPM_TRY(dalloc(&film_w, static_cast<size_t>(film_total_) * emb_dim_));
+  CDDPM_TRY(dalloc(&film_w16, static_cast<size_t>(film_total_) * emb_dim_));
   CDDPM_TRY(dalloc(&film_b, static_cast<size_t>(film_total_)));
   return kOk;
 }
@@ -287,16 +286,39 @@ int UNetEngine::init(const cddpm_unet_config& cfg) {
 }
 
 // ------------------------------------------------------------------------------------------------ planning
-int UNetEngine::act_alloc(ActTensor* t, int C, int H, int W, int B, bool scratch_f32) {
+int UNetEngine::act_alloc(ActTensor* t, int C, int H, int W, int B, bool with_stats) {
   void* q = nullptr;
-  const size_t bytes = static_cast<size_t>(B) * H * W * C * (scratch_f32 ? 4 : 2) + 256;
+  const size_t bytes = static_cast<size_t>(B) * H * W * C * 2 + 256;
   CDDPM_CUDA(cudaMalloc(&q, bytes));
   act_owned_.push_back(q);
   t->p = q;
   t->C = C;
   t->H = H;
   t->W = W;
+  t->stats = nullptr;
+  if (with_stats && fused_stats_) {
+    // GroupNorm statistics of this tensor: [B][C/4][2] doubles in the per-forward arena (zeroed by the first op)
+    const size_t n = static_cast<size_t>(B) * (C / 4) * 2;
+    if (stats_used_ + n > stats_cap_) return fail(kCudaError, "statistics arena exhausted");
+    t->stats = stats_arena_ + stats_used_;
+    stats_used_ += n;
+  }
   return kOk;
+}
+
+// GroupNorm (+FiLM +SiLU +resample).  With fused statistics the (sum, sumsq) buckets were emitted by the producing
+// convolution's epilogue; otherwise (group size not a multiple of 4, i.e. model_channels % 128 != 0) a separate
+// statistics pass over the input runs first.
+void UNetEngine::push_gn(GnApplyArgs g) {
+  if (!fused_stats_) {
+    g.stats0 = g.stats1 = nullptr;
+    g.partial = gn_partial_;
+    const CatView v = g.x;
+    const int B = g.B, HW = g.H * g.W, fmt = g.fmt;
+    float* partial = gn_partial_;
+    ops_.push_back([=](cudaStream_t s) { return launch_gn_stats(v, B, HW, partial, fmt, s); });
+  }
+  ops_.push_back([=](cudaStream_t s) { return launch_gn_apply(g, s); });
 }
 
 void UNetEngine::push_conv(const ConvDesc& d, int* status) {
@@ -336,20 +358,21 @@ int UNetEngine::plan_res(const ResLayer& L, const ActTensor& a0, const ActTensor
   if (v.C() != L.cin) return fail(kInvalidArgument, "plan_res: channel mismatch at " + L.prefix);
   ActTensor tA, tH, tB, tS;
   CDDPM_TRY(act_alloc(&tA, L.cin, Ho, Wo, B));
-  CDDPM_TRY(act_alloc(&tH, L.cout, Ho, Wo, B));
+  CDDPM_TRY(act_alloc(&tH, L.cout, Ho, Wo, B, true));
   CDDPM_TRY(act_alloc(&tB, L.cout, Ho, Wo, B));
   if (L.mode != kResampleNone) CDDPM_TRY(act_alloc(&tS, L.cin, Ho, Wo, B));
-  CDDPM_TRY(act_alloc(out, L.cout, Ho, Wo, B));
-  float* partial = gn_partial_;
-  // 1-2. in_layers: GroupNorm + SiLU (+ resample of both the normalised and the raw input)
-  ops_.push_back([=](cudaStream_t s) { return launch_gn_stats(v, B, H * W, partial, fmt, s); });
+  CDDPM_TRY(act_alloc(out, L.cout, Ho, Wo, B, true));
+  if (fused_stats_ && (!a0.stats || (a1 && !a1->stats))) return fail(kInvalidArgument, "plan_res: input without statistics at " + L.prefix);
+  // 1-2. in_layers: GroupNorm (statistics came out of the producers' epilogues) + SiLU (+ resample of both the
+  //      normalised and the raw input)
   {
     GnApplyArgs g;
     g.x = v;
     g.B = B;
     g.H = H;
     g.W = W;
-    g.partial = partial;
+    g.stats0 = a0.stats;
+    g.stats1 = a1 ? a1->stats : nullptr;
     g.gamma = L.gn1_w;
     g.beta = L.gn1_b;
     g.silu = 1;
@@ -357,7 +380,7 @@ int UNetEngine::plan_res(const ResLayer& L, const ActTensor& a0, const ActTensor
     g.out = tA.p;
     g.raw_out = (L.mode != kResampleNone) ? tS.p : nullptr;
     g.fmt = fmt;
-    ops_.push_back([=](cudaStream_t s) { return launch_gn_apply(g, s); });
+    push_gn(g);
   }
   int st = kOk;
   // 3. in_layers conv 3x3
@@ -375,6 +398,7 @@ int UNetEngine::plan_res(const ResLayer& L, const ActTensor& a0, const ActTensor
     d.bias = L.b1;
     d.out = tH.p;
     d.ab_format = fmt;
+    d.gn_stats = tH.stats;
     push_conv(d, &st);
     CDDPM_TRY(st);
   }
@@ -383,13 +407,12 @@ int UNetEngine::plan_res(const ResLayer& L, const ActTensor& a0, const ActTensor
     CatView hv;
     hv.p0 = tH.p;
     hv.c0 = L.cout;
-    ops_.push_back([=](cudaStream_t s) { return launch_gn_stats(hv, B, Ho * Wo, partial, fmt, s); });
     GnApplyArgs g;
     g.x = hv;
     g.B = B;
     g.H = Ho;
     g.W = Wo;
-    g.partial = partial;
+    g.stats0 = tH.stats;
     g.gamma = L.gn2_w;
     g.beta = L.gn2_b;
     g.film = film_out_;
@@ -399,7 +422,7 @@ int UNetEngine::plan_res(const ResLayer& L, const ActTensor& a0, const ActTensor
     g.mode = kResampleNone;
     g.out = tB.p;
     g.fmt = fmt;
-    ops_.push_back([=](cudaStream_t s) { return launch_gn_apply(g, s); });
+    push_gn(g);
   }
   // 6. out_layers conv 3x3 + skip (identity residual, or 1x1 over the raw input fused as extra K columns)
   {
@@ -433,6 +456,7 @@ int UNetEngine::plan_res(const ResLayer& L, const ActTensor& a0, const ActTensor
       d.bias = L.b2sum;
       d.residual = (L.mode != kResampleNone) ? tS.p : a0.p;
     }
+    d.gn_stats = out->stats;
     push_conv(d, &st);
     CDDPM_TRY(st);
   }
@@ -448,25 +472,24 @@ int UNetEngine::plan_attn(const AttnLayer& L, const ActTensor& x, ActTensor* out
   CDDPM_TRY(act_alloc(&tN, C, H, W, B));
   CDDPM_TRY(act_alloc(&tQ, 3 * C, H, W, B));
   CDDPM_TRY(act_alloc(&tA, C, H, W, B));
-  CDDPM_TRY(act_alloc(out, C, H, W, B));
-  float* partial = gn_partial_;
+  CDDPM_TRY(act_alloc(out, C, H, W, B, true));
+  if (fused_stats_ && !x.stats) return fail(kInvalidArgument, "plan_attn: input without statistics at " + L.prefix);
   CatView v;
   v.p0 = x.p;
   v.c0 = C;
-  ops_.push_back([=](cudaStream_t s) { return launch_gn_stats(v, B, H * W, partial, fmt, s); });
   {
     GnApplyArgs g;
     g.x = v;
     g.B = B;
     g.H = H;
     g.W = W;
-    g.partial = partial;
+    g.stats0 = x.stats;
     g.gamma = L.gn_w;
     g.beta = L.gn_b;
     g.silu = 0;
     g.out = tN.p;
     g.fmt = fmt;
-    ops_.push_back([=](cudaStream_t s) { return launch_gn_apply(g, s); });
+    push_gn(g);
   }
   int st = kOk;
   {
@@ -506,6 +529,7 @@ int UNetEngine::plan_attn(const AttnLayer& L, const ActTensor& x, ActTensor* out
     d.residual = x.p;
     d.out = out->p;
     d.ab_format = fmt;
+    d.gn_stats = out->stats;
     push_conv(d, &st);
     CDDPM_TRY(st);
   }
@@ -534,8 +558,28 @@ int UNetEngine::plan(int B) {
   CDDPM_TRY(falloc(&hid_t_, static_cast<size_t>(B) * half_dim_));
   CDDPM_TRY(falloc(&hid_c_, static_cast<size_t>(B) * half_dim_));
   CDDPM_TRY(falloc(&emb_act_, static_cast<size_t>(B) * emb_dim_));
+  {
+    float* tmp = nullptr;  // 16-bit copy of SiLU(emb): the A operand of the FiLM GEMM
+    CDDPM_TRY(falloc(&tmp, (static_cast<size_t>(B) * emb_dim_ + 1) / 2));
+    emb_act16_ = reinterpret_cast<uint16_t*>(tmp);
+  }
   CDDPM_TRY(falloc(&film_out_, static_cast<size_t>(B) * film_total_));
-  CDDPM_TRY(falloc(&gn_partial_, static_cast<size_t>(B) * kGnMaxChunks * kGnGroups * 2));
+  fused_stats_ = (mc % 128 == 0);  // every GroupNorm group (C/32 channels) is then a whole number of 4-channel buckets
+  if (!fused_stats_) CDDPM_TRY(falloc(&gn_partial_, static_cast<size_t>(B) * kGnMaxChunks * kGnGroups * 2));
+  if (fused_stats_) {
+    // arena for the per-tensor GroupNorm statistics ([B][C/4][2] doubles each), cleared once per forward
+    const size_t tensors = 2 * (res_.size() + attn_.size()) + 8;
+    stats_cap_ = tensors * static_cast<size_t>(B) * 192 * 2;
+    stats_used_ = 0;
+    void* q = nullptr;
+    CDDPM_CUDA(cudaMalloc(&q, stats_cap_ * sizeof(double)));
+    act_owned_.push_back(q);
+    stats_arena_ = reinterpret_cast<double*>(q);
+    UNetEngine* self = this;
+    ops_.push_back([self](cudaStream_t s) {
+      return check_cuda(cudaMemsetAsync(self->stats_arena_, 0, self->stats_used_ * sizeof(double), s), "stats memset");
+    });
+  }
 
   // ---- embedding: emb_act = SiLU([time_embed(sin(t)) | label_emb(cond)]); film = emb_layers(emb_act) for all blocks
   ops_.push_back([=](cudaStream_t s) { return launch_timestep_embedding(cur_t_, sinus_, B, mc, s); });
@@ -543,7 +587,8 @@ int UNetEngine::plan(int B) {
     return launch_linear_ex(sinus_, mc, te0_w, te0_b, hid_t_, half_dim_, B, mc, half_dim_, 0, 1, s);
   });
   ops_.push_back([=](cudaStream_t s) {
-    return launch_linear_ex(hid_t_, half_dim_, te2_w, te2_b, emb_act_, emb_dim_, B, half_dim_, half_dim_, 0, 1, s);
+    return launch_linear_16(hid_t_, half_dim_, te2_w, te2_b, emb_act_, emb_dim_, B, half_dim_, half_dim_, 0, 1,
+                            emb_act16_, emb_dim_, fmt, s);
   });
   if (cfg_.num_classes > 0) {
     const int nc = cfg_.num_classes;
@@ -552,13 +597,28 @@ int UNetEngine::plan(int B) {
       return launch_linear_ex(cur_cond_, nc, le0_w, le0_b, hid_c_, half_dim_, B, nc, half_dim_, 0, 1, s);
     });
     ops_.push_back([=](cudaStream_t s) {
-      return launch_linear_ex(hid_c_, half_dim_, le2_w, le2_b, emb_act_ + half_dim_, emb_dim_, B, half_dim_,
-                              half_dim_, 0, 1, s);
+      return launch_linear_16(hid_c_, half_dim_, le2_w, le2_b, emb_act_ + half_dim_, emb_dim_, B, half_dim_,
+                              half_dim_, 0, 1, emb_act16_ + half_dim_, emb_dim_, fmt, s);
     });
   }
-  ops_.push_back([=](cudaStream_t s) {
-    return launch_linear_ex(emb_act_, emb_dim_, film_w, film_b, film_out_, film_total_, B, emb_dim_, film_total_, 0, 0, s);
-  });
+  {
+    // all 27 emb_layers as ONE tensor-core GEMM: film[B, 11776] = SiLU(emb)[B, E] x Wcat^T + bias (fp32 out)
+    ConvDesc d;
+    d.num_src = 1;
+    d.src[0] = emb_act16_;
+    d.src_c[0] = emb_dim_;
+    d.src_taps[0] = 1;
+    d.flat_rows = B;
+    d.Cout = film_total_;
+    d.wpacked = film_w16;
+    d.bias = film_b;
+    d.out = film_out_;
+    d.out_is_f32 = 1;
+    d.ab_format = fmt;
+    int st = kOk;
+    push_conv(d, &st);
+    CDDPM_TRY(st);
+  }
 
   // ---- input blocks
   std::vector<ActTensor> hs;
@@ -567,9 +627,12 @@ int UNetEngine::plan(int B) {
     for (const Layer& l : in_blocks_[bi]) {
       ActTensor o;
       if (l.kind == 0) {
-        CDDPM_TRY(act_alloc(&o, mc, H, W, B));
+        CDDPM_TRY(act_alloc(&o, mc, H, W, B, true));
         void* op = o.p;
+        double* ost = o.stats;
         ops_.push_back([=](cudaStream_t s) { return launch_conv_in(cur_x_, stem_w, stem_b, op, B, H, W, mc, fmt, s); });
+        // the stem is a direct (non tensor-core) kernel: its GroupNorm statistics take one extra pass
+        if (fused_stats_) ops_.push_back([=](cudaStream_t s) { return launch_gn_stats4(op, mc, B, H * W, ost, fmt, s); });
         taps_["input_blocks.0.0"] = o;
       } else if (l.kind == 1) {
         CDDPM_TRY(plan_res(res_[l.idx], h, nullptr, &o, B));
@@ -611,21 +674,19 @@ int UNetEngine::plan(int B) {
     CatView v;
     v.p0 = h.p;
     v.c0 = h.C;
-    float* partial = gn_partial_;
     const int hh = h.H, ww = h.W, cc = h.C;
-    ops_.push_back([=](cudaStream_t s) { return launch_gn_stats(v, B, hh * ww, partial, fmt, s); });
     GnApplyArgs g;
     g.x = v;
     g.B = B;
     g.H = hh;
     g.W = ww;
-    g.partial = partial;
+    g.stats0 = h.stats;
     g.gamma = head_gn_w;
     g.beta = head_gn_b;
     g.silu = 1;
     g.out = tN.p;
     g.fmt = fmt;
-    ops_.push_back([=](cudaStream_t s) { return launch_gn_apply(g, s); });
+    push_gn(g);
     void* np = tN.p;
     ops_.push_back([=](cudaStream_t s) { return launch_conv_out(np, head_w, head_b, cur_out_, B, hh, ww, cc, fmt, s); });
   }

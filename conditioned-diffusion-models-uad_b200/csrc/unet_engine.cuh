@@ -20,6 +20,7 @@ namespace cddpm {
 struct ActTensor {
   void* p = nullptr;
   int C = 0, H = 0, W = 0;
+  double* stats = nullptr;  // [B][C/4][2] GroupNorm (sum, sumsq) buckets emitted by the producer, or nullptr
   size_t elems(int B) const { return static_cast<size_t>(B) * H * W * C; }
 };
 
@@ -77,9 +78,11 @@ class UNetEngine {
   int plan(int B);
   int plan_res(const ResLayer& L, const ActTensor& a0, const ActTensor* a1, ActTensor* out, int B);
   int plan_attn(const AttnLayer& L, const ActTensor& x, ActTensor* out, int B);
-  int act_alloc(ActTensor* t, int C, int H, int W, int B, bool scratch_f32 = false);
+  int act_alloc(ActTensor* t, int C, int H, int W, int B, bool with_stats = false);
   void free_acts();
   void push_conv(const ConvDesc& d, int* status);
+  void push_gn(GnApplyArgs g);
+  bool fused_stats_ = true;
 
   cddpm_unet_config cfg_{};
   int emb_dim_ = 0, half_dim_ = 0, film_total_ = 0;
@@ -95,7 +98,9 @@ class UNetEngine {
   // embedding parameters
   float *te0_w = nullptr, *te0_b = nullptr, *te2_w = nullptr, *te2_b = nullptr;
   float *le0_w = nullptr, *le0_b = nullptr, *le2_w = nullptr, *le2_b = nullptr;
-  float *film_w = nullptr, *film_b = nullptr;
+  uint16_t* film_w16 = nullptr;  // [film_total][emb_dim] 16-bit K-major
+  float* film_b = nullptr;
+  uint16_t* emb_act16_ = nullptr;
   float *stem_w = nullptr, *stem_b = nullptr, *head_gn_w = nullptr, *head_gn_b = nullptr, *head_w = nullptr,
         *head_b = nullptr;
   // per-forward bindings
@@ -109,6 +114,8 @@ class UNetEngine {
   std::map<std::string, ActTensor> taps_;
   float *sinus_ = nullptr, *hid_t_ = nullptr, *hid_c_ = nullptr, *emb_act_ = nullptr, *film_out_ = nullptr,
         *gn_partial_ = nullptr;
+  double* stats_arena_ = nullptr;
+  size_t stats_cap_ = 0, stats_used_ = 0;
   int64_t conv_flops_ = 0;
   bool profile_armed_ = false;
   std::vector<cudaEvent_t> profile_events_;
