@@ -198,7 +198,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         pix = static_cast<size_t>(m_tile) * kConvTileM + row;
         valid = pix < static_cast<size_t>(p.M);
       }
-      const size_t off = pix * p.Cout + static_cast<size_t>(n_idx) * p.n_tile;
+      const size_t roff = pix * p.Cout + static_cast<size_t>(n_idx) * p.n_tile;              // residual [.., Cout]
+      const size_t off = pix * p.out_stride + p.out_col_off + static_cast<size_t>(n_idx) * p.n_tile;  // output row
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
             }
           }
           if (p.residual != nullptr) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off + c * 32);
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + roff + c * 32);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const uint4 rv = __ldg(rp + q);
@@ -242,9 +243,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
               }
             }
           }
-          if (p.relu) {
+          if (p.relu == 1) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+          } else if (p.relu == 2) {  // SiLU (embedding MLPs)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.0f + __expf(-f[j]));
           }
           if (p.gn_stats != nullptr) {
             // GroupNorm statistics of the tensor being produced, at 4-channel granularity: per thread 8 buckets of
@@ -384,6 +388,8 @@ int build_conv_params(const ConvDesc& d, ConvIgemmParams* p) {
   p->num_src = d.num_src;
   p->Cout = d.Cout;
   p->relu = d.relu;
+  p->out_stride = d.out_stride > 0 ? d.out_stride : d.Cout;
+  p->out_col_off = d.out_col_off;
   if (flat) {
     if (d.num_src != 1 || d.src_taps[0] != 1) return fail(kInvalidArgument, "conv: flat GEMM takes one 1-tap source");
     p->flat = 1;

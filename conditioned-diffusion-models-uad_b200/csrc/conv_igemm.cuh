@@ -39,7 +39,9 @@ struct ConvIgemmParams {
                          // 4-channel bucket, accumulated with atomics (the caller zeroes it) — feeds the next GroupNorm
   int flat;              // plain GEMM: A is a row-major [M][C] matrix (2-D tensor map), one source, taps == 1
   int M;                 // rows of the flat problem
-  int relu;              // clamp the result at 0 after bias and residual
+  int relu;              // activation after bias and residual: 0 none, 1 ReLU, 2 SiLU
+  int out_stride;        // elements between consecutive output rows (pixels); Cout unless writing into a wider matrix
+  int out_col_off;       // first output column within the row
 };
 
 // Describes one convolution launch in host terms; build_conv_params() turns it into ConvIgemmParams.
@@ -58,7 +60,9 @@ struct ConvDesc {
   double* gn_stats = nullptr;
   int flat_rows = 0;  // > 0: plain GEMM over src[0] = [flat_rows][src_c[0]] (B/H/W ignored), e.g. nn.Linear or an
                       // im2col'ed convolution
-  int relu = 0;
+  int relu = 0;         // 0 none, 1 ReLU, 2 SiLU
+  int out_stride = 0;   // 0 = Cout
+  int out_col_off = 0;
 };
 
 int conv_ktot(const ConvDesc& d);

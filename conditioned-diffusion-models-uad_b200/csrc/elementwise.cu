@@ -332,16 +332,38 @@ __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ i
   }
 }
 
-__global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, float* __restrict__ emb, int B, int dim) {
+__device__ __forceinline__ uint16_t f2h16(float v, int fmt) {
+  if (fmt == 1) {
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    return *reinterpret_cast<uint16_t*>(&h);
+  }
+  __half h = __float2half_rn(v);
+  return *reinterpret_cast<uint16_t*>(&h);
+}
+
+__global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, float* __restrict__ emb, int B, int dim,
+                                          uint16_t* __restrict__ emb16, int fmt) {
   const int half = dim / 2;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * half) return;
   const int b = idx / half, i = idx - b * half;
   const float freq = expf(-logf(10000.0f) * static_cast<float>(i) / static_cast<float>(half));
   const float arg = static_cast<float>(t[b]) * freq;
-  emb[static_cast<size_t>(b) * dim + i] = cosf(arg);
-  emb[static_cast<size_t>(b) * dim + half + i] = sinf(arg);
-  if ((dim & 1) && i == 0) emb[static_cast<size_t>(b) * dim + dim - 1] = 0.f;
+  const float c = cosf(arg), s = sinf(arg);
+  if (emb != nullptr) {
+    emb[static_cast<size_t>(b) * dim + i] = c;
+    emb[static_cast<size_t>(b) * dim + half + i] = s;
+    if ((dim & 1) && i == 0) emb[static_cast<size_t>(b) * dim + dim - 1] = 0.f;
+  }
+  if (emb16 != nullptr) {
+    emb16[static_cast<size_t>(b) * dim + i] = f2h16(c, fmt);
+    emb16[static_cast<size_t>(b) * dim + half + i] = f2h16(s, fmt);
+  }
+}
+
+__global__ void to16_kernel(const float* __restrict__ in, uint16_t* __restrict__ out, int n, int fmt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = f2h16(in[i], fmt);
 }
 
 // ---------------------------------------------------------------------------------------------- stem / head convs
@@ -555,9 +577,19 @@ int launch_linear(const float* in, int in_stride, const float* W, const float* b
 }
 
 int launch_timestep_embedding(const int64_t* t, float* emb, int B, int dim, cudaStream_t stream) {
+  return launch_timestep_embedding16(t, emb, nullptr, 0, B, dim, stream);
+}
+
+int launch_timestep_embedding16(const int64_t* t, float* emb, void* emb16, int fmt, int B, int dim, cudaStream_t stream) {
   const int n = B * (dim / 2);
-  timestep_embedding_kernel<<<(n + 255) / 256, 256, 0, stream>>>(t, emb, B, dim);
+  timestep_embedding_kernel<<<(n + 255) / 256, 256, 0, stream>>>(t, emb, B, dim, reinterpret_cast<uint16_t*>(emb16), fmt);
   return check_launch("timestep_embedding_kernel");
+}
+
+int launch_to16(const float* in, void* out, int n, int fmt, cudaStream_t stream) {
+  if (!in || !out) return fail(kInvalidArgument, "to16: null pointer");
+  to16_kernel<<<(n + 255) / 256, 256, 0, stream>>>(in, reinterpret_cast<uint16_t*>(out), n, fmt);
+  return check_launch("to16_kernel");
 }
 
 int launch_conv_in(const float* x, const float* w, const float* bias, void* out, int B, int H, int W, int Cout,

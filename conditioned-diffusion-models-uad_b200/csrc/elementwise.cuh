@@ -62,6 +62,9 @@ int launch_linear_16(const float* in, int in_stride, const float* W, const float
 
 // emb[b][0:half] = cos(t_b * f_i), emb[b][half:] = sin(t_b * f_i), f_i = exp(-ln(1e4) * i / half) (util.py:151-171).
 int launch_timestep_embedding(const int64_t* t, float* emb, int B, int dim, cudaStream_t stream);
+// ... with an optional 16-bit copy (tensor-core operand); emb may be NULL.
+int launch_timestep_embedding16(const int64_t* t, float* emb, void* emb16, int fmt, int B, int dim, cudaStream_t stream);
+int launch_to16(const float* in, void* out, int n, int fmt, cudaStream_t stream);
 
 // Stem: x fp32 [B,1,H,W] -> NHWC 16-bit [B,H,W,Cout], 3x3 pad 1 (OpenAI_Unet.py:609).
 int launch_conv_in(const float* x, const float* w, const float* bias, void* out, int B, int H, int W, int Cout,

@@ -189,15 +189,27 @@ int UNetEngine::build_layers() {
     return false;
   };
   // registration order follows the reference module tree: label_emb, time_embed, input_blocks, middle, output, out
+  // embedding MLP weights: fp32 copy (SIMT fallback for odd sizes) + 16-bit K-major panel (tensor-core GEMM)
+  auto add_linear = [&](const std::string& name, int O, int I, float** w32, uint16_t** w16) -> int {
+    CDDPM_TRY(dalloc(w32, static_cast<size_t>(O) * I));
+    CDDPM_TRY(dalloc(w16, static_cast<size_t>(O) * I));
+    float* d32 = *w32;
+    uint16_t* d16 = *w16;
+    const int fmt = cfg_.fmt;
+    return add_param(name, static_cast<int64_t>(O) * I, [=](const float* src, cudaStream_t s) {
+      CDDPM_CUDA(cudaMemcpyAsync(d32, src, static_cast<size_t>(O) * I * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      return launch_pack_conv_weight(src, O, I, 1, 0, I, d16, I, 0, fmt, s);
+    });
+  };
   if (cfg_.num_classes > 0) {
-    CDDPM_TRY(add_copy_param("label_emb.0.weight", static_cast<int64_t>(half_dim_) * cfg_.num_classes, &le0_w));
+    CDDPM_TRY(add_linear("label_emb.0.weight", half_dim_, cfg_.num_classes, &le0_w, &le0_w16));
     CDDPM_TRY(add_copy_param("label_emb.0.bias", half_dim_, &le0_b));
-    CDDPM_TRY(add_copy_param("label_emb.2.weight", static_cast<int64_t>(half_dim_) * half_dim_, &le2_w));
+    CDDPM_TRY(add_linear("label_emb.2.weight", half_dim_, half_dim_, &le2_w, &le2_w16));
     CDDPM_TRY(add_copy_param("label_emb.2.bias", half_dim_, &le2_b));
   }
-  CDDPM_TRY(add_copy_param("time_embed.0.weight", static_cast<int64_t>(half_dim_) * mc, &te0_w));
+  CDDPM_TRY(add_linear("time_embed.0.weight", half_dim_, mc, &te0_w, &te0_w16));
   CDDPM_TRY(add_copy_param("time_embed.0.bias", half_dim_, &te0_b));
-  CDDPM_TRY(add_copy_param("time_embed.2.weight", static_cast<int64_t>(half_dim_) * half_dim_, &te2_w));
+  CDDPM_TRY(add_linear("time_embed.2.weight", half_dim_, half_dim_, &te2_w, &te2_w16));
   CDDPM_TRY(add_copy_param("time_embed.2.bias", half_dim_, &te2_b));
 
   CDDPM_TRY(add_copy_param("input_blocks.0.0.weight", static_cast<int64_t>(mc) * cfg_.in_channels * 9, &stem_w));
@@ -582,6 +594,53 @@ int UNetEngine::plan(int B) {
   }
 
   // ---- embedding: emb_act = SiLU([time_embed(sin(t)) | label_emb(cond)]); film = emb_layers(emb_act) for all blocks
+  const bool gemm_embed = (mc % 64 == 0) && (half_dim_ % 64 == 0) && (cfg_.num_classes % 64 == 0);
+  if (gemm_embed) {
+    // the four small linears as tensor-core GEMMs with a SiLU epilogue, 16-bit hand-off between them
+    uint16_t *sin16 = nullptr, *hid16 = nullptr, *hidc16 = nullptr, *cond16 = nullptr;
+    auto h16alloc = [&](uint16_t** p, size_t n) {
+      float* tmp = nullptr;
+      int st = falloc(&tmp, (n + 1) / 2);
+      *p = reinterpret_cast<uint16_t*>(tmp);
+      return st;
+    };
+    CDDPM_TRY(h16alloc(&sin16, static_cast<size_t>(B) * mc));
+    CDDPM_TRY(h16alloc(&hid16, static_cast<size_t>(B) * half_dim_));
+    auto lin = [&](const uint16_t* in, int I, const uint16_t* w16, const float* bias, uint16_t* out, int O, int stride,
+                   int col) -> int {
+      ConvDesc d;
+      d.num_src = 1;
+      d.src[0] = in;
+      d.src_c[0] = I;
+      d.src_taps[0] = 1;
+      d.flat_rows = B;
+      d.Cout = O;
+      d.wpacked = w16;
+      d.bias = bias;
+      d.out = out;
+      d.ab_format = fmt;
+      d.relu = 2;  // SiLU
+      d.out_stride = stride;
+      d.out_col_off = col;
+      int st = kOk;
+      push_conv(d, &st);
+      return st;
+    };
+    ops_.push_back([=](cudaStream_t s) { return launch_timestep_embedding16(cur_t_, nullptr, sin16, fmt, B, mc, s); });
+    CDDPM_TRY(lin(sin16, mc, te0_w16, te0_b, hid16, half_dim_, half_dim_, 0));
+    CDDPM_TRY(lin(hid16, half_dim_, te2_w16, te2_b, emb_act16_, half_dim_, emb_dim_, 0));
+    if (cfg_.num_classes > 0) {
+      const int nc = cfg_.num_classes;
+      CDDPM_TRY(h16alloc(&hidc16, static_cast<size_t>(B) * half_dim_));
+      CDDPM_TRY(h16alloc(&cond16, static_cast<size_t>(B) * nc));
+      ops_.push_back([=](cudaStream_t s) {
+        if (cur_cond_ == nullptr) return fail(kInvalidArgument, "conditioned UNet called without cond");
+        return launch_to16(cur_cond_, cond16, B * nc, fmt, s);
+      });
+      CDDPM_TRY(lin(cond16, nc, le0_w16, le0_b, hidc16, half_dim_, half_dim_, 0));
+      CDDPM_TRY(lin(hidc16, half_dim_, le2_w16, le2_b, emb_act16_, half_dim_, emb_dim_, half_dim_));
+    }
+  } else {
   ops_.push_back([=](cudaStream_t s) { return launch_timestep_embedding(cur_t_, sinus_, B, mc, s); });
   ops_.push_back([=](cudaStream_t s) {
     return launch_linear_ex(sinus_, mc, te0_w, te0_b, hid_t_, half_dim_, B, mc, half_dim_, 0, 1, s);
@@ -600,6 +659,7 @@ int UNetEngine::plan(int B) {
       return launch_linear_16(hid_c_, half_dim_, le2_w, le2_b, emb_act_ + half_dim_, emb_dim_, B, half_dim_,
                               half_dim_, 0, 1, emb_act16_ + half_dim_, emb_dim_, fmt, s);
     });
+  }
   }
   {
     // all 27 emb_layers as ONE tensor-core GEMM: film[B, 11776] = SiLU(emb)[B, E] x Wcat^T + bias (fp32 out)

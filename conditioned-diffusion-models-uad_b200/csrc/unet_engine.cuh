@@ -98,6 +98,7 @@ class UNetEngine {
   // embedding parameters
   float *te0_w = nullptr, *te0_b = nullptr, *te2_w = nullptr, *te2_b = nullptr;
   float *le0_w = nullptr, *le0_b = nullptr, *le2_w = nullptr, *le2_b = nullptr;
+  uint16_t *te0_w16 = nullptr, *te2_w16 = nullptr, *le0_w16 = nullptr, *le2_w16 = nullptr;
   uint16_t* film_w16 = nullptr;  // [film_total][emb_dim] 16-bit K-major
   float* film_b = nullptr;
   uint16_t* emb_act16_ = nullptr;
