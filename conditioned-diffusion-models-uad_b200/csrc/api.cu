@@ -59,6 +59,11 @@ int cddpm_conv_igemm(int num_src, const void* const* src, const int* src_c, cons
   d.out = out;
   d.out_is_f32 = out_f32;
   d.ab_format = fmt;
+  if (conv2_enabled() && conv2_supported(d)) {  // macro-tile kernel where the geometry allows it
+    std::shared_ptr<void> holder;
+    CDDPM_TRY(build_conv2(d, &holder));
+    return launch_conv2(holder, static_cast<cudaStream_t>(stream));
+  }
   ConvIgemmParams p;
   CDDPM_TRY(build_conv_params(d, &p));
   return launch_conv_igemm(p, static_cast<cudaStream_t>(stream));

@@ -13,6 +13,8 @@
 #include "conv_igemm.cuh"
 
 #include <cuda_fp16.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "ptx.cuh"
@@ -47,6 +49,10 @@ __device__ __forceinline__ float2 unpack_16bit(uint32_t u, int ab_format) {
   }
 }
 
+// kPair: launched as 2-CTA clusters; the pair issues tcgen05.mma.cta_group::2 with M = 256 (each CTA owns one
+// 128-pixel M tile and stages half of the weight slab), which halves both the shared-memory operand reads per MMA and
+// the weight bytes each SM pulls from L2.  Without it the SS-mode MMA is limited by shared-memory bandwidth.
+template <bool kPair>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvIgemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled operand tiles need 1024-byte alignment.
@@ -55,8 +61,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_stages = p.num_stages;
-  const int b_stage_bytes = p.n_tile * kConvBlockK * 2;
+  const int b_stage_bytes = (kPair ? p.n_tile / 2 : p.n_tile) * kConvBlockK * 2;
   const int stage_bytes = kAStageBytes + b_stage_bytes;
+  const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
+  const bool leader = (cta_rank == 0);
+  // work decomposition: a "work item" is one M tile (kPair: two adjacent M tiles, one per CTA) x one N tile
+  const int work_stride = kPair ? gridDim.x / 2 : gridDim.x;
+  const int work_first = kPair ? blockIdx.x / 2 : blockIdx.x;
+  const int num_work = (kPair ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles) * p.num_n_tiles;
 
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + num_stages * stage_bytes);
   uint64_t* empty_bar = full_bar + num_stages;
@@ -76,22 +88,31 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     for (int s = 0; s < p.num_src; ++s) tma_prefetch_desc(&p.tmap_a[s]);
     tma_prefetch_desc(&p.tmap_b);
   }
+  if (kPair) cluster_sync_all();  // both CTAs are resident before TMEM is allocated for the pair
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < num_stages; ++i) {
-      mbar_init(&full_bar[i], 1);
+      mbar_init(&full_bar[i], kPair ? 2 : 1);  // pair: the leader's barrier collects both producers
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 128);
+      mbar_init(&tempty_bar[i], kPair ? 256 : 128);  // pair: both epilogues release the leader's accumulator stage
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
+    if (kPair) {
+      tmem_alloc_pair(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
+    } else {
+      tmem_alloc(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (kPair) {
+    cluster_sync_all();
+  } else {
+    __syncthreads();
+  }
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -100,9 +121,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.num_n_tiles;
-        const int n_idx = tile % p.num_n_tiles;
+      for (int work = work_first; work < num_work; work += work_stride) {
+        const int m_tile = kPair ? 2 * (work / p.num_n_tiles) + static_cast<int>(cta_rank) : work / p.num_n_tiles;
+        const int n_idx = work % p.num_n_tiles;
         int kstep = 0;
         for (int s = 0; s < p.num_src; ++s) {
           const int chunks = p.src_c[s] / kConvBlockK;
@@ -114,20 +135,45 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
               mbar_wait(&empty_bar[stage], phase ^ 1);
               uint8_t* a_dst = smem + stage * stage_bytes;
               uint8_t* b_dst = a_dst + kAStageBytes;
-              mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
-              if (p.flat) {
-                tma_load_2d(a_dst, &p.tmap_a[s], &full_bar[stage], ch * kConvBlockK, m_tile * kConvTileM);
-              } else
-              for (int b = 0; b < p.boxes_per_tile; ++b) {
-                const int box = m_tile * p.boxes_per_tile + b;
-                const int n = box / boxes_per_img;
-                const int r = box - n * boxes_per_img;
-                const int ty = r / p.tiles_w;
-                const int tx = r - ty * p.tiles_w;
-                tma_load_4d(a_dst + b * box_px * 128, &p.tmap_a[s], &full_bar[stage], ch * kConvBlockK,
-                            tx * p.box_w + dx, ty * p.box_h + dy, n);
+              if (kPair) {
+                // both producers arrive on the LEADER's barrier, which expects the bytes of both CTAs
+                if (leader) {
+                  mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(2 * stage_bytes));
+                } else {
+                  mbar_arrive_cluster(&full_bar[stage], 0);
+                }
+              } else {
+                mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
               }
-              tma_load_2d(b_dst, &p.tmap_b, &full_bar[stage], kstep * kConvBlockK, n_idx * p.n_tile);
+              if (p.flat) {
+                if (kPair) {
+                  tma_load_2d_pair(a_dst, &p.tmap_a[s], &full_bar[stage], ch * kConvBlockK, m_tile * kConvTileM);
+                } else {
+                  tma_load_2d(a_dst, &p.tmap_a[s], &full_bar[stage], ch * kConvBlockK, m_tile * kConvTileM);
+                }
+              } else {
+                for (int b = 0; b < p.boxes_per_tile; ++b) {
+                  const int box = m_tile * p.boxes_per_tile + b;
+                  const int n = box / boxes_per_img;
+                  const int r = box - n * boxes_per_img;
+                  const int ty = r / p.tiles_w;
+                  const int tx = r - ty * p.tiles_w;
+                  if (kPair) {
+                    tma_load_4d_pair(a_dst + b * box_px * 128, &p.tmap_a[s], &full_bar[stage], ch * kConvBlockK,
+                                     tx * p.box_w + dx, ty * p.box_h + dy, n);
+                  } else {
+                    tma_load_4d(a_dst + b * box_px * 128, &p.tmap_a[s], &full_bar[stage], ch * kConvBlockK,
+                                tx * p.box_w + dx, ty * p.box_h + dy, n);
+                  }
+                }
+              }
+              if (kPair) {
+                // this CTA's half of the weight rows of the N tile
+                tma_load_2d_pair(b_dst, &p.tmap_b_half, &full_bar[stage], kstep * kConvBlockK,
+                                 n_idx * p.n_tile + static_cast<int>(cta_rank) * (p.n_tile / 2));
+              } else {
+                tma_load_2d(b_dst, &p.tmap_b, &full_bar[stage], kstep * kConvBlockK, n_idx * p.n_tile);
+              }
               if (++stage == num_stages) {
                 stage = 0;
                 phase ^= 1;
@@ -137,33 +183,49 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    const uint32_t idesc = umma_idesc_f16(kConvTileM, static_cast<uint32_t>(p.n_tile), static_cast<uint32_t>(p.ab_format));
+  } else if (warp == 1 && leader) {
+    // ------------------------------------------------------------------ MMA issuer (pair: leader CTA only)
+    // All MMA operands are warp-uniform (shuffled bases, descriptors advanced by constants) and the issuing lane is
+    // elected: the compiler then emits back-to-back UTCHMMA from uniform registers, ~45 cycles of issue per MMA
+    // instead of ~160 with per-thread operands under `lane == 0` (tools/ubench_mma.cu).
+    const uint32_t idesc = umma_idesc_f16(kPair ? 2 * kConvTileM : kConvTileM, static_cast<uint32_t>(p.n_tile),
+                                          static_cast<uint32_t>(p.ab_format));
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t smem_u = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+    const bool elected = elect_one_sync();
     int stage = 0;
     uint32_t phase = 0;
     int iter = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+    for (int work = work_first; work < num_work; work += work_stride, ++iter) {
       const int acc = iter & 1;
       const uint32_t acc_phase = (iter >> 1) & 1;
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * p.n_tile);
+      const uint32_t tmem_d = tmem_u + static_cast<uint32_t>(acc * p.n_tile);
+      uint32_t accum = 0;
       for (int kstep = 0; kstep < num_ksteps; ++kstep) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
-          const uint32_t b_addr = a_addr + kAStageBytes;
+        if (elected) {
+          const uint64_t ad = umma_desc_k128(smem_u + stage * stage_bytes);
+          const uint64_t bd = umma_desc_k128(smem_u + stage * stage_bytes + kAStageBytes);
 #pragma unroll
           for (int k = 0; k < kConvBlockK / 16; ++k) {
-            umma_f16_ss(tmem_d, umma_desc_k128(a_addr + k * 32), umma_desc_k128(b_addr + k * 32), idesc,
-                        (kstep | k) != 0 ? 1u : 0u);
+            if (kPair) {
+              umma_f16_ss_pair(tmem_d, ad + 2 * k, bd + 2 * k, idesc, k == 0 ? accum : 1u);
+            } else {
+              umma_f16_ss(tmem_d, ad + 2 * k, bd + 2 * k, idesc, k == 0 ? accum : 1u);
+            }
           }
-          umma_commit(&empty_bar[stage]);
-          if (kstep == num_ksteps - 1) umma_commit(&tfull_bar[acc]);
+          if (kPair) {
+            umma_commit_pair(&empty_bar[stage]);  // frees the stage in both CTAs
+            if (kstep == num_ksteps - 1) umma_commit_pair(&tfull_bar[acc]);
+          } else {
+            umma_commit(&empty_bar[stage]);
+            if (kstep == num_ksteps - 1) umma_commit(&tfull_bar[acc]);
+          }
         }
-        __syncwarp();
+        accum = 1;
         if (++stage == num_stages) {
           stage = 0;
           phase ^= 1;
@@ -176,11 +238,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     const int row = quarter * 32 + lane;
     const int fmt = p.ab_format;
     int iter = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+    for (int work = work_first; work < num_work; work += work_stride, ++iter) {
       const int acc = iter & 1;
       const uint32_t acc_phase = (iter >> 1) & 1;
-      const int m_tile = tile / p.num_n_tiles;
-      const int n_idx = tile % p.num_n_tiles;
+      const int m_tile = kPair ? 2 * (work / p.num_n_tiles) + static_cast<int>(cta_rank) : work / p.num_n_tiles;
+      const int n_idx = work % p.num_n_tiles;
 
       // pixel owned by this thread
       const int b = row / box_px;
@@ -212,7 +274,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         if (c == nchunks - 1) {
           // every TMEM read of this accumulator stage has completed: hand it back to the MMA warp
           tc_fence_before();
-          mbar_arrive(&tempty_bar[acc]);
+          if (kPair) {
+            mbar_arrive_cluster(&tempty_bar[acc], 0);  // the leader's MMA warp owns the accumulator hand-off
+          } else {
+            mbar_arrive(&tempty_bar[acc]);
+          }
         }
         if (valid) {
           const int co = n_idx * p.n_tile + c * 32;
@@ -323,10 +389,18 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (kPair) {
+    cluster_sync_all();  // the peer may still be reading operands / TMEM that belong to the pair
+  } else {
+    __syncthreads();
+  }
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+    if (kPair) {
+      tmem_dealloc_pair(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+    } else {
+      tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+    }
   }
 }
 
@@ -431,7 +505,8 @@ int build_conv_params(const ConvDesc& d, ConvIgemmParams* p) {
   int cols = 32;
   while (cols < 2 * n_tile) cols *= 2;
   p->tmem_cols = cols;
-  const int stage_bytes = kAStageBytes + n_tile * kConvBlockK * 2;
+  p->pair = pair_enabled() ? 1 : 0;
+  const int stage_bytes = kAStageBytes + (p->pair ? n_tile / 2 : n_tile) * kConvBlockK * 2;
   int stages = (kSmemBudget - 2048 - kStatBytes) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) return fail(kUnsupported, "conv: not enough shared memory for a 2-stage pipeline");
@@ -469,24 +544,56 @@ int build_conv_params(const ConvDesc& d, ConvIgemmParams* p) {
     const uint64_t strides[1] = {static_cast<uint64_t>(ktot) * 2};
     const uint32_t box[2] = {static_cast<uint32_t>(kConvBlockK), static_cast<uint32_t>(n_tile)};
     CDDPM_TRY(encode_tmap_16bit(&p->tmap_b, d.wpacked, 2, dims, strides, box));
+    const uint32_t box_half[2] = {static_cast<uint32_t>(kConvBlockK), static_cast<uint32_t>(n_tile / 2)};
+    CDDPM_TRY(encode_tmap_16bit(&p->tmap_b_half, d.wpacked, 2, dims, strides, box_half));
   }
   return kOk;
+}
+
+bool pair_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CDDPM_CONV_PAIR");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 int launch_conv_igemm(const ConvIgemmParams& p, cudaStream_t stream, int max_ctas) {
   static bool attr_set = false;
   if (!attr_set) {
-    CDDPM_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    CDDPM_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    CDDPM_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     attr_set = true;
   }
-  const int stage_bytes = kAStageBytes + p.n_tile * kConvBlockK * 2;
+  const int stage_bytes = kAStageBytes + (p.pair ? p.n_tile / 2 : p.n_tile) * kConvBlockK * 2;
   const int smem = p.num_stages * stage_bytes + 1024 /*alignment slack*/ + 256 /*barriers*/ + kStatBytes;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-  int grid = device_sm_count();
-  if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
-  if (num_tiles < grid) grid = num_tiles;
-  conv_igemm_kernel<<<grid, kConvThreads, smem, stream>>>(p);
-  return check_launch("conv_igemm_kernel");
+  int sms = device_sm_count();
+  if (max_ctas > 0 && max_ctas < sms) sms = max_ctas;
+  if (!p.pair) {
+    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+    const int grid = num_tiles < sms ? num_tiles : sms;
+    conv_igemm_kernel<false><<<grid, kConvThreads, smem, stream>>>(p);
+    return check_launch("conv_igemm_kernel");
+  }
+  // CTA pairs: a cluster of two CTAs per work item (two adjacent M tiles x one N tile), persistent over SM pairs
+  const int num_work = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
+  const int pairs = num_work < sms / 2 ? num_work : sms / 2;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(kConvThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CDDPM_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true>, p));
+  return check_launch("conv_igemm_kernel<pair>");
 }
 
 int launch_pack_conv_weight(const float* w_oihw, int Cout, int Cin_total, int ksize, int cin_off, int C_s,

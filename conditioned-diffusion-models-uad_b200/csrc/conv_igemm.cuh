@@ -6,6 +6,8 @@
 // branch) share one accumulator.  GEMM view: M = B*H*W pixels, N = Cout, K = sum_s taps_s * C_s.
 // This is the kernel behind nn.Conv2d 3x3/1x1 in the reference UNet (OpenAI_Unet.py:231,257,268,367,375).
 #pragma once
+#include <memory>
+
 #include "common.h"
 
 namespace cddpm {
@@ -18,6 +20,7 @@ constexpr int kConvThreads = 256; // warp0 TMA, warp1 MMA, warp2 TMEM alloc, war
 struct ConvIgemmParams {
   CUtensorMap tmap_a[kConvMaxSrc];  // 4-D maps {C, W, H, B} over each NHWC source, box {64, box_w, box_h, 1}
   CUtensorMap tmap_b;               // 2-D map {Ktot, Cout} over the packed weights, box {64, n_tile}
+  CUtensorMap tmap_b_half;          // same matrix, box {64, n_tile / 2}: each CTA of a pair stages half of the rows
   int num_src;
   int src_c[kConvMaxSrc];     // channels of each source (multiple of 64)
   int src_taps[kConvMaxSrc];  // 9 (3x3, pad 1) or 1 (1x1)
@@ -42,7 +45,10 @@ struct ConvIgemmParams {
   int relu;              // activation after bias and residual: 0 none, 1 ReLU, 2 SiLU
   int out_stride;        // elements between consecutive output rows (pixels); Cout unless writing into a wider matrix
   int out_col_off;       // first output column within the row
+  int pair;              // launched as 2-CTA clusters issuing tcgen05.mma.cta_group::2 (M = 256)
 };
+// true unless the environment sets CDDPM_CONV_PAIR=0 (A/B switch for measurements)
+bool pair_enabled();
 
 // Describes one convolution launch in host terms; build_conv_params() turns it into ConvIgemmParams.
 struct ConvDesc {
@@ -64,6 +70,15 @@ struct ConvDesc {
   int out_stride = 0;   // 0 = Cout
   int out_col_off = 0;
 };
+
+// Second-generation kernel (conv_igemm2.cu): 16x16-pixel macro tiles x 128 channels; one staged 18x18 halo tile per
+// 64-channel chunk serves all nine taps through row-shifted UMMA descriptors.  Applies when W % 16 == 0, H % 16 == 0,
+// Cout % 128 == 0 and the output is a plain 16-bit NHWC tensor.
+bool conv2_supported(const ConvDesc& d);
+int build_conv2(const ConvDesc& d, std::shared_ptr<void>* holder);
+int launch_conv2(const std::shared_ptr<void>& holder, cudaStream_t stream);
+// true unless the environment sets CDDPM_CONV_V2=0 (A/B switch for measurements)
+bool conv2_enabled();
 
 int conv_ktot(const ConvDesc& d);
 int build_conv_params(const ConvDesc& d, ConvIgemmParams* p);

@@ -1,0 +1,439 @@
+// Second-generation tcgen05 implicit-GEMM convolution: one staged halo tile serves all nine taps.
+//
+// Measured on B200 (profiles/r01_*, tools/ubench_mma.cu): the first kernel (conv_igemm.cu) streams a 16 KB activation
+// tile per tap and 64-channel chunk - every activation byte crosses L2->SM nine times - and sits on the chip-wide
+// L2->SM limit (~6300 B/cycle, i.e. ~43 B/cycle/SM) at 35-50 % tensor-pipe utilisation.  Two measured facts of the
+// UMMA shared-memory descriptor remove that traffic:
+//   * the 128-byte swizzle is applied to the absolute shared-memory address of each operand row, so the descriptor's
+//     start address may point at ANY 128-byte row of a staged tile, and
+//   * the stride between 8-row groups (SBO) may be any multiple of 128 bytes.
+// So a CTA stages, per 64-channel chunk, ONE TMA box of 18 x 18 pixels (a 16 x 16 output macro tile plus its 3x3 halo,
+// zero-filled outside the image by TMA) and issues the nine taps as MMAs whose A descriptors differ only in their
+// start row: M tile m (8 pixels wide, 16 high) and tap (dy, dx) read rows starting at halo pixel (dy, dx + 8 m), one
+// 8-pixel group per image row, group stride = the halo row pitch (18 x 128 B).  Activation traffic drops from 9x to
+// 1.27x; the weight slab of each (tap, chunk) feeds two M tiles (8 MMAs per commit).
+// Bytes per 64-channel chunk and macro tile (256 px x 128 ch x 9 taps = 4608 tensor cycles): 41.5 KB activations +
+// 147 KB weights, ~41 B/cycle/SM - under the L2 limit, where the first kernel needs 96-128 B/cycle/SM.
+// Warp roles as in conv_igemm.cu: warp 0 TMA producer (two rings: halo tiles, weight slabs), warp 1 MMA issuer with
+// warp-uniform operands, warp 2 TMEM allocator, warps 4-7 epilogue (bias, residual, activation, GroupNorm partial
+// sums, 16-bit NHWC store); two TMEM accumulator stages of 2 x 128 columns.
+#include <cuda_fp16.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "conv_igemm.cuh"
+#include "ptx.cuh"
+
+namespace cddpm {
+
+namespace {
+
+constexpr int kTileW = 16;                // macro tile (output pixels)
+constexpr int kTileH = 16;
+constexpr int kHaloW = kTileW + 2;
+constexpr int kHaloH = kTileH + 2;
+constexpr int kMTiles = 2;                // M tiles per macro tile, side by side, each 8 wide x 16 high
+constexpr int kNTile = 128;               // output channels per CTA tile
+constexpr int kRowBytes = 128;            // 64 channels x 16 bit
+constexpr int kHaloPitch = kHaloW * kRowBytes;          // 2304 B between the 8-pixel row groups of an M tile
+constexpr int kABytes = kHaloW * kHaloH * kRowBytes;    // 41472 B per staged halo tile
+constexpr int kASlotBytes = (kABytes + 1023) & ~1023;   // slots stay 1 KB aligned (swizzle atom)
+constexpr int kBSlotBytes = kNTile * kRowBytes;         // 16384
+constexpr int kStagesA = 2;
+constexpr int kStagesB = 7;
+constexpr int kStatW2 = 64;               // (128 / 32) chunks x 16 values
+constexpr int kStatBytes2 = 2 * 4 * kStatW2 * 4;
+constexpr int kSmemBytes2 = kStagesA * kASlotBytes + kStagesB * kBSlotBytes + 256 + kStatBytes2 + 1024;
+constexpr int kTmemCols = 512;            // 2 stages x 2 M tiles x 128 columns
+
+struct Conv2Params {
+  CUtensorMap tmap_a[kConvMaxSrc];  // {C, W, H, B}; box {64, 18, 18, 1}
+  CUtensorMap tmap_b;               // {Ktot, Cout}; box {64, 128}
+  int num_src;
+  int src_c[kConvMaxSrc];
+  int src_taps[kConvMaxSrc];
+  int B, H, W, Cout;
+  int tiles_w, tiles_h;  // macro tiles per image
+  int num_m_tiles, num_n_tiles;
+  int ab_format, relu;
+  const float* bias;
+  const uint16_t* residual;
+  uint16_t* out;
+  double* gn_stats;
+};
+
+__device__ __forceinline__ uint32_t pack16(float a, float b, int fmt) {
+  if (fmt == 1) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+  __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack16(uint32_t u, int fmt) {
+  if (fmt == 1) return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+  return __half22float2(*reinterpret_cast<__half2*>(&u));
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1) conv_igemm2_kernel(const __grid_constant__ Conv2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_ring = smem;
+  uint8_t* b_ring = smem + kStagesA * kASlotBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_ring + kStagesB * kBSlotBytes);
+  uint64_t* full_a = bars;
+  uint64_t* empty_a = full_a + kStagesA;
+  uint64_t* full_b = empty_a + kStagesA;
+  uint64_t* empty_b = full_b + kStagesB;
+  uint64_t* tfull = empty_b + kStagesB;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* stat_sh = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.num_src; ++s) tma_prefetch_desc(&p.tmap_a[s]);
+    tma_prefetch_desc(&p.tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStagesA; ++i) {
+      mbar_init(&full_a[i], 1);
+      mbar_init(&empty_a[i], 1);
+    }
+    for (int i = 0; i < kStagesB; ++i) {
+      mbar_init(&full_b[i], 1);
+      mbar_init(&empty_b[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.num_n_tiles;
+        const int n_idx = tile - m_tile * p.num_n_tiles;
+        const int n = m_tile / tiles_per_img;
+        const int r = m_tile - n * tiles_per_img;
+        const int ty = r / p.tiles_w;
+        const int tx = r - ty * p.tiles_w;
+        int koff = 0;
+        for (int s = 0; s < p.num_src; ++s) {
+          const int C = p.src_c[s];
+          const int ntaps = p.src_taps[s];
+          for (int ch = 0; ch < C / kConvBlockK; ++ch) {
+            mbar_wait(&empty_a[sa], pa ^ 1);
+            mbar_arrive_expect_tx(&full_a[sa], kABytes);
+            tma_load_4d(a_ring + sa * kASlotBytes, &p.tmap_a[s], &full_a[sa], ch * kConvBlockK, tx * kTileW - 1,
+                        ty * kTileH - 1, n);
+            if (++sa == kStagesA) {
+              sa = 0;
+              pa ^= 1;
+            }
+            for (int tap = 0; tap < ntaps; ++tap) {
+              mbar_wait(&empty_b[sb], pb ^ 1);
+              mbar_arrive_expect_tx(&full_b[sb], kBSlotBytes);
+              tma_load_2d(b_ring + sb * kBSlotBytes, &p.tmap_b, &full_b[sb], koff + tap * C + ch * kConvBlockK,
+                          n_idx * kNTile);
+              if (++sb == kStagesB) {
+                sb = 0;
+                pb ^= 1;
+              }
+            }
+          }
+          koff += ntaps * C;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    // Every operand of the MMAs is warp-uniform (shuffled bases, descriptors advanced by constants) and the issuing
+    // lane is elected, so the compiler emits back-to-back UTCHMMA from uniform registers: ~45 cycles of issue per MMA
+    // against 64 cycles of tensor time (tools/ubench_mma.cu; per-thread operands cost ~160 cycles per MMA).
+    const uint32_t idesc = umma_idesc_f16(128, kNTile, static_cast<uint32_t>(p.ab_format));
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t a_ring_u = __shfl_sync(0xffffffffu, smem_u32(a_ring), 0);
+    const uint32_t b_ring_u = __shfl_sync(0xffffffffu, smem_u32(b_ring), 0);
+    const bool elected = elect_one_sync();
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+      const int acc = iter & 1;
+      const uint32_t acc_phase = (iter >> 1) & 1;
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_u + static_cast<uint32_t>(acc * kMTiles * kNTile);
+      uint32_t accum = 0;
+      for (int s = 0; s < p.num_src; ++s) {
+        const int chunks = p.src_c[s] / kConvBlockK;
+        const bool c3 = p.src_taps[s] == 9;
+        const int ntaps = c3 ? 9 : 1;
+        for (int ch = 0; ch < chunks; ++ch) {
+          mbar_wait(&full_a[sa], pa);
+          const uint64_t a_desc = umma_desc_k128_sbo(a_ring_u + sa * kASlotBytes, kHaloPitch);
+          for (int tap = 0; tap < ntaps; ++tap) {
+            const int t = c3 ? tap : 4;  // a 1x1 source reads the centre of the halo tile
+            const int dy = t / 3;
+            const int dx = t - 3 * dy;
+            mbar_wait(&full_b[sb], pb);
+            tc_fence_after();
+            const bool last_tap = tap == ntaps - 1;
+            const bool last_step = last_tap && ch == chunks - 1 && s == p.num_src - 1;
+            if (elected) {
+              const uint64_t ad = a_desc + static_cast<uint64_t>((dy * kHaloW + dx) * (kRowBytes / 16));
+              const uint64_t bd = umma_desc_k128(b_ring_u + sb * kBSlotBytes);
+#pragma unroll
+              for (int m = 0; m < kMTiles; ++m) {
+#pragma unroll
+                for (int kk = 0; kk < kConvBlockK / 16; ++kk) {
+                  umma_f16_ss(tmem_d + m * kNTile, ad + (m * 8 * (kRowBytes / 16) + kk * 2), bd + kk * 2, idesc,
+                              kk == 0 ? accum : 1u);
+                }
+              }
+              umma_commit(&empty_b[sb]);
+              if (last_tap) umma_commit(&empty_a[sa]);
+              if (last_step) umma_commit(&tfull[acc]);
+            }
+            accum = 1;
+            if (++sb == kStagesB) {
+              sb = 0;
+              pb ^= 1;
+            }
+          }
+          if (++sa == kStagesA) {
+            sa = 0;
+            pa ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;  // pixel within an M tile: (row / 8, row % 8)
+    const int fmt = p.ab_format;
+    const int nb4 = p.Cout >> 2;
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+      const int acc = iter & 1;
+      const uint32_t acc_phase = (iter >> 1) & 1;
+      const int m_tile = tile / p.num_n_tiles;
+      const int n_idx = tile - m_tile * p.num_n_tiles;
+      const int n = m_tile / tiles_per_img;
+      const int r = m_tile - n * tiles_per_img;
+      const int ty = r / p.tiles_w;
+      const int tx = r - ty * p.tiles_w;
+      const int x0 = tx * kTileW + (row & 7);
+      const int y = ty * kTileH + (row >> 3);
+
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                             static_cast<uint32_t>(acc * kMTiles * kNTile);
+#pragma unroll 1
+      for (int c = 0; c < kNTile / 32; ++c) {
+        const int co = n_idx * kNTile + c * 32;
+        float v16[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v16[j] = 0.f;
+#pragma unroll
+        for (int m = 0; m < kMTiles; ++m) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + m * kNTile + c * 32, v);
+          tmem_ld_wait();
+          if (c == kNTile / 32 - 1 && m == kMTiles - 1) {
+            tc_fence_before();
+            mbar_arrive(&tempty[acc]);
+          }
+          const size_t off = ((static_cast<size_t>(n) * p.H + y) * p.W + x0 + m * 8) * p.Cout + co;
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + co + j));
+              f[j] += bv.x;
+              f[j + 1] += bv.y;
+              f[j + 2] += bv.z;
+              f[j + 3] += bv.w;
+            }
+          }
+          if (p.residual != nullptr) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 rv = __ldg(rp + q);
+              const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 t = unpack16(w[e], fmt);
+                f[q * 8 + e * 2] += t.x;
+                f[q * 8 + e * 2 + 1] += t.y;
+              }
+            }
+          }
+          if (p.relu == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+          } else if (p.relu == 2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.0f + __expf(-f[j]));
+          }
+          if (p.gn_stats != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                v16[k] += f[4 * k + j];
+                v16[8 + k] = fmaf(f[4 * k + j], f[4 * k + j], v16[8 + k]);
+              }
+            }
+          }
+          uint4* op = reinterpret_cast<uint4*>(p.out + off);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 o;
+            o.x = pack16(f[q * 8 + 0], f[q * 8 + 1], fmt);
+            o.y = pack16(f[q * 8 + 2], f[q * 8 + 3], fmt);
+            o.z = pack16(f[q * 8 + 4], f[q * 8 + 5], fmt);
+            o.w = pack16(f[q * 8 + 6], f[q * 8 + 7], fmt);
+            op[q] = o;
+          }
+        }
+        if (p.gn_stats != nullptr) {
+          // butterfly over the warp's 32 pixels: 16 shuffles leave value (lane >> 1) & 15 in every lane
+#pragma unroll
+          for (int w = 8; w >= 1; w >>= 1) {
+            const int msk = w * 2;
+            const bool hi = (lane & msk) != 0;
+#pragma unroll
+            for (int k = 0; k < w; ++k) {
+              const float keep = hi ? v16[k + w] : v16[k];
+              const float send = hi ? v16[k] : v16[k + w];
+              v16[k] = keep + __shfl_xor_sync(0xffffffffu, send, msk);
+            }
+          }
+          const float tot = v16[0] + __shfl_xor_sync(0xffffffffu, v16[0], 1);
+          if ((lane & 1) == 0) stat_sh[(acc * 4 + quarter) * kStatW2 + c * 16 + (lane >> 1)] = tot;
+        }
+      }
+      if (p.gn_stats != nullptr) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (row < kStatW2) {
+          const int within = row & 15;
+          const int is_q = within >> 3;
+          const int bucket = (row >> 4) * 8 + (within & 7);
+          const float* sp = stat_sh + acc * 4 * kStatW2 + row;
+          const float t = sp[0] + sp[kStatW2] + sp[2 * kStatW2] + sp[3 * kStatW2];
+          atomicAdd(&p.gn_stats[(static_cast<size_t>(n) * nb4 + n_idx * (kNTile >> 2) + bucket) * 2 + is_q],
+                    static_cast<double>(t));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace
+
+bool conv2_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CDDPM_CONV_V2");  // A/B switch for measurements: 0 = first-generation kernel everywhere
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+bool conv2_supported(const ConvDesc& d) {
+  if (d.flat_rows > 0 || d.out_is_f32 || d.out_stride > 0 || d.out_col_off != 0) return false;
+  if (d.W % kTileW != 0 || d.H % kTileH != 0) return false;
+  if (d.Cout % kNTile != 0) return false;
+  for (int s = 0; s < d.num_src; ++s)
+    if (d.src_c[s] % kConvBlockK != 0 || (d.src_taps[s] != 1 && d.src_taps[s] != 9)) return false;
+  return true;
+}
+
+struct Conv2Launch {
+  Conv2Params p;
+};
+
+int build_conv2(const ConvDesc& d, std::shared_ptr<void>* holder) {
+  auto L = std::make_shared<Conv2Launch>();
+  Conv2Params& p = L->p;
+  memset(&p, 0, sizeof(p));
+  p.num_src = d.num_src;
+  p.B = d.B;
+  p.H = d.H;
+  p.W = d.W;
+  p.Cout = d.Cout;
+  p.tiles_w = d.W / kTileW;
+  p.tiles_h = d.H / kTileH;
+  p.num_m_tiles = d.B * p.tiles_w * p.tiles_h;
+  p.num_n_tiles = d.Cout / kNTile;
+  p.ab_format = d.ab_format;
+  p.relu = d.relu;
+  p.bias = d.bias;
+  p.residual = reinterpret_cast<const uint16_t*>(d.residual);
+  p.out = reinterpret_cast<uint16_t*>(d.out);
+  p.gn_stats = d.gn_stats;
+  int ktot = 0;
+  for (int s = 0; s < d.num_src; ++s) {
+    p.src_c[s] = d.src_c[s];
+    p.src_taps[s] = d.src_taps[s];
+    const uint64_t C = static_cast<uint64_t>(d.src_c[s]);
+    const uint64_t dims[4] = {C, static_cast<uint64_t>(d.W), static_cast<uint64_t>(d.H), static_cast<uint64_t>(d.B)};
+    const uint64_t strides[3] = {C * 2, C * 2 * d.W, C * 2 * d.W * d.H};
+    const uint32_t box[4] = {static_cast<uint32_t>(kConvBlockK), static_cast<uint32_t>(kHaloW),
+                             static_cast<uint32_t>(kHaloH), 1u};
+    CDDPM_TRY(encode_tmap_16bit(&p.tmap_a[s], d.src[s], 4, dims, strides, box));
+    ktot += d.src_taps[s] * d.src_c[s];
+  }
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(ktot), static_cast<uint64_t>(d.Cout)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(ktot) * 2};
+    const uint32_t box[2] = {static_cast<uint32_t>(kConvBlockK), static_cast<uint32_t>(kNTile)};
+    CDDPM_TRY(encode_tmap_16bit(&p.tmap_b, d.wpacked, 2, dims, strides, box));
+  }
+  *holder = L;
+  return kOk;
+}
+
+int launch_conv2(const std::shared_ptr<void>& holder, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CDDPM_CUDA(cudaFuncSetAttribute(conv_igemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2));
+    attr_set = true;
+  }
+  const Conv2Launch* L = reinterpret_cast<const Conv2Launch*>(holder.get());
+  const int num_tiles = L->p.num_m_tiles * L->p.num_n_tiles;
+  int grid = device_sm_count();
+  if (num_tiles < grid) grid = num_tiles;
+  conv_igemm2_kernel<<<grid, kConvThreads, kSmemBytes2, stream>>>(L->p);
+  return check_launch("conv_igemm2_kernel");
+}
+
+}  // namespace cddpm

@@ -167,6 +167,76 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// ----------------------------------------------------------------------------------------------
+// CTA pairs (cta_group::2): two CTAs of a 2-CTA cluster issue ONE tcgen05.mma of M = 256.  Each CTA stages its own
+// 128 rows of A and HALF of the B rows; accumulator rows live in each CTA's own TMEM.  Only the leader (cluster rank
+// 0) issues MMAs; TMA transactions of both CTAs are counted on the leader's barrier; commits are multicast.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
+      "}"
+      ::"r"(smem_u32(bar)), "r"(rank)
+      : "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> leader CTA
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* desc, uint64_t* leader_bar, int32_t c0,
+                                                 int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(desc), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(void* smem_dst, const void* desc, uint64_t* leader_bar, int32_t c0,
+                                                 int32_t c1, int32_t c2, int32_t c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+      "%5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(desc), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all MMAs issued so far have completed) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+
 // Shared-memory matrix descriptor for a K-major operand tile stored as rows of 128 bytes (64 x 16-bit) with the
 // 128-byte hardware swizzle (what TMA SWIZZLE_128B writes): 8-row atoms of 1024 bytes, atoms contiguous along M/N.
 //   bits [0,14)  start address >> 4        bits [16,30) leading byte offset >> 4 (unused for swizzled K-major)
@@ -179,6 +249,29 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(2) << 61;
   return d;
+}
+// Same layout with an explicit stride between 8-row groups.  The hardware applies the 128B swizzle to the ABSOLUTE
+// shared-memory address of every row (measured, tools/ubench_mma.cu), so the start address may sit on any 128-byte
+// row and the group stride may be any multiple of 128 bytes: rows 8g..8g+7 are read from start + g*sbo + j*128.
+__device__ __forceinline__ uint64_t umma_desc_k128_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// One lane of the (converged) warp; unlike `lane == 0` the compiler keeps the guarded code in the uniform datapath.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 // Instruction descriptor for kind::f16: fp32 accumulator, both operands K-major, 16-bit type selected at run time

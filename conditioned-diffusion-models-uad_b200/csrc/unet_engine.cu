@@ -335,19 +335,28 @@ void UNetEngine::push_gn(GnApplyArgs g) {
 
 void UNetEngine::push_conv(const ConvDesc& d, int* status) {
   if (*status != kOk) return;
-  auto p = std::make_shared<ConvIgemmParams>();
-  *status = build_conv_params(d, p.get());
-  if (*status != kOk) return;
+  std::function<int(cudaStream_t)> launch;
+  if (conv2_enabled() && conv2_supported(d)) {
+    std::shared_ptr<void> holder;
+    *status = build_conv2(d, &holder);
+    if (*status != kOk) return;
+    launch = [holder](cudaStream_t s) { return launch_conv2(holder, s); };
+  } else {
+    auto p = std::make_shared<ConvIgemmParams>();
+    *status = build_conv_params(d, p.get());
+    if (*status != kOk) return;
+    launch = [p](cudaStream_t s) { return launch_conv_igemm(*p, s); };
+  }
   conv_flops_ += 2ll * d.H * d.W * d.Cout * conv_ktot(d);
   // Optional per-launch timing (bench roofline): events bracket the convolution launches of ONE forward.
   UNetEngine* self = this;
-  ops_.push_back([p, self](cudaStream_t s) {
-    if (!self->profile_armed_) return launch_conv_igemm(*p, s);
+  ops_.push_back([launch, self](cudaStream_t s) {
+    if (!self->profile_armed_) return launch(s);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     CDDPM_CUDA(cudaEventCreate(&e0));
     CDDPM_CUDA(cudaEventCreate(&e1));
     CDDPM_CUDA(cudaEventRecord(e0, s));
-    int st = launch_conv_igemm(*p, s);
+    int st = launch(s);
     CDDPM_CUDA(cudaEventRecord(e1, s));
     self->profile_events_.push_back(e0);
     self->profile_events_.push_back(e1);
