@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     for (int s = 0; s < p.num_src; ++s) tma_prefetch_desc(&p.tmap_a[s]);
     tma_prefetch_desc(&p.tmap_b);
   }
-  if (kPair) cluster_sync_all();  // both CTAs are resident before TMEM is allocated for the pair
+  if (kPair) cluster_sync_relaxed();  // both CTAs are resident before TMEM is allocated for the pair
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < num_stages; ++i) {
       mbar_init(&full_bar[i], kPair ? 2 : 1);  // pair: the leader's barrier collects both producers
@@ -109,7 +109,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
   }
   tc_fence_before();
   if (kPair) {
-    cluster_sync_all();
+    __syncthreads();
+    cluster_sync_relaxed();
   } else {
     __syncthreads();
   }
@@ -390,7 +391,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
 
   tc_fence_before();
   if (kPair) {
-    cluster_sync_all();  // the peer may still be reading operands / TMEM that belong to the pair
+    __syncthreads();
+    cluster_sync_relaxed();  // the peer may still be reading operands / TMEM that belong to the pair
   } else {
     __syncthreads();
   }

@@ -1,9 +1,10 @@
-// Second-generation tcgen05 implicit-GEMM convolution: one staged halo tile serves all nine taps.
+// Second-generation tcgen05 implicit-GEMM convolution: one staged halo tile serves all nine taps, CTA pairs share
+// the weight slab.
 //
 // Measured on B200 (profiles/r01_*, tools/ubench_mma.cu): the first kernel (conv_igemm.cu) streams a 16 KB activation
 // tile per tap and 64-channel chunk - every activation byte crosses L2->SM nine times - and sits on the chip-wide
-// L2->SM limit (~6300 B/cycle, i.e. ~43 B/cycle/SM) at 35-50 % tensor-pipe utilisation.  Two measured facts of the
-// UMMA shared-memory descriptor remove that traffic:
+// L2->SM limit (~6300 B/cycle, ~43 B/cycle/SM) at 35-50 % tensor-pipe utilisation.  Two measured facts of the UMMA
+// shared-memory descriptor remove that traffic:
 //   * the 128-byte swizzle is applied to the absolute shared-memory address of each operand row, so the descriptor's
 //     start address may point at ANY 128-byte row of a staged tile, and
 //   * the stride between 8-row groups (SBO) may be any multiple of 128 bytes.
@@ -11,12 +12,24 @@
 // zero-filled outside the image by TMA) and issues the nine taps as MMAs whose A descriptors differ only in their
 // start row: M tile m (8 pixels wide, 16 high) and tap (dy, dx) read rows starting at halo pixel (dy, dx + 8 m), one
 // 8-pixel group per image row, group stride = the halo row pitch (18 x 128 B).  Activation traffic drops from 9x to
-// 1.27x; the weight slab of each (tap, chunk) feeds two M tiles (8 MMAs per commit).
-// Bytes per 64-channel chunk and macro tile (256 px x 128 ch x 9 taps = 4608 tensor cycles): 41.5 KB activations +
-// 147 KB weights, ~41 B/cycle/SM - under the L2 limit, where the first kernel needs 96-128 B/cycle/SM.
-// Warp roles as in conv_igemm.cu: warp 0 TMA producer (two rings: halo tiles, weight slabs), warp 1 MMA issuer with
-// warp-uniform operands, warp 2 TMEM allocator, warps 4-7 epilogue (bias, residual, activation, GroupNorm partial
-// sums, 16-bit NHWC store); two TMEM accumulator stages of 2 x 128 columns.
+// 1.27x.
+//
+// A single-CTA N = 128 MMA reads 8 KB of operands per 64 tensor cycles - all of the SM's 128 B/cycle shared-memory
+// bandwidth, so every TMA write stalls the tensor pipe (measured 56-66 % active).  The kernel therefore runs as 2-CTA
+// clusters issuing tcgen05.mma.cta_group::2 (M = 256: one M tile of each CTA; N = 128 with each CTA staging 64 of the
+// weight rows): 6 KB of operand reads per 64 cycles and half the weight bytes per SM.
+//
+// Per CTA and 64-channel chunk (256 px x 128 ch x 9 taps = 4608 tensor cycles): 41.5 KB activations + 74 KB weights,
+// ~25 B/cycle/SM from L2.  Weight slabs travel in stages of three taps (one kernel row), so the issuing thread waits
+// on one barrier and commits once per 24 MMAs.
+//
+// With both changes the kernel sits on the shared-memory roofline: operand reads (96 B/cycle) plus TMA writes
+// (~25 B/cycle) use ~95 % of the 128 B/cycle.  (Folding the preceding GroupNorm+SiLU into the staged tiles was built
+// and measured: any extra pass over the tile in shared memory costs more than the HBM pass it saves.)
+// Warp roles: warp 0 weight producer, warp 3 halo-tile producer (its own thread, so tile loads run ahead by the
+// depth of the tile ring), warp 1 MMA issuer (leader CTA only, warp-uniform operands), warp 2 TMEM allocator,
+// warps 4-11 epilogue (one warpgroup per M tile: bias, residual, activation, GroupNorm partial sums, 16-bit NHWC
+// store); two TMEM accumulator stages of 2 x 128 columns.
 #include <cuda_fp16.h>
 #include <stdlib.h>
 #include <string.h>
@@ -28,27 +41,31 @@ namespace cddpm {
 
 namespace {
 
-constexpr int kTileW = 16;                // macro tile (output pixels)
+constexpr int kThreads2 = 384;
+constexpr int kTileW = 16;                // macro tile (output pixels) of one CTA
 constexpr int kTileH = 16;
 constexpr int kHaloW = kTileW + 2;
 constexpr int kHaloH = kTileH + 2;
 constexpr int kMTiles = 2;                // M tiles per macro tile, side by side, each 8 wide x 16 high
-constexpr int kNTile = 128;               // output channels per CTA tile
+constexpr int kNTile = 128;               // output channels per work item
 constexpr int kRowBytes = 128;            // 64 channels x 16 bit
 constexpr int kHaloPitch = kHaloW * kRowBytes;          // 2304 B between the 8-pixel row groups of an M tile
 constexpr int kABytes = kHaloW * kHaloH * kRowBytes;    // 41472 B per staged halo tile
 constexpr int kASlotBytes = (kABytes + 1023) & ~1023;   // slots stay 1 KB aligned (swizzle atom)
-constexpr int kBSlotBytes = kNTile * kRowBytes;         // 16384
-constexpr int kStagesA = 2;
-constexpr int kStagesB = 7;
-constexpr int kStatW2 = 64;               // (128 / 32) chunks x 16 values
-constexpr int kStatBytes2 = 2 * 4 * kStatW2 * 4;
+constexpr int kBTapBytes = (kNTile / 2) * kRowBytes;    // 8192: this CTA's 64 weight rows of one tap
+constexpr int kTapsPerStage = 3;
+constexpr int kBSlotBytes = kTapsPerStage * kBTapBytes; // 24576
+constexpr int kStagesA = 3;
+constexpr int kStagesB = 4;
+constexpr int kEpiWarps = 8;
+constexpr int kStatW2 = 64;               // (128 / 32) chunks x 16 values per warp
+constexpr int kStatBytes2 = 2 * kEpiWarps * kStatW2 * 4;
 constexpr int kSmemBytes2 = kStagesA * kASlotBytes + kStagesB * kBSlotBytes + 256 + kStatBytes2 + 1024;
 constexpr int kTmemCols = 512;            // 2 stages x 2 M tiles x 128 columns
 
 struct Conv2Params {
   CUtensorMap tmap_a[kConvMaxSrc];  // {C, W, H, B}; box {64, 18, 18, 1}
-  CUtensorMap tmap_b;               // {Ktot, Cout}; box {64, 128}
+  CUtensorMap tmap_b;               // {Ktot, Cout}; box {64, 64}
   int num_src;
   int src_c[kConvMaxSrc];
   int src_taps[kConvMaxSrc];
@@ -75,7 +92,7 @@ __device__ __forceinline__ float2 unpack16(uint32_t u, int fmt) {
   return __half22float2(*reinterpret_cast<__half2*>(&u));
 }
 
-__global__ void __launch_bounds__(kConvThreads, 1) conv_igemm2_kernel(const __grid_constant__ Conv2Params p) {
+__global__ void __launch_bounds__(kThreads2, 1) conv_igemm2_kernel(const __grid_constant__ Conv2Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_ring = smem;
@@ -92,64 +109,65 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm2_kernel(const __gr
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  // a work item is two adjacent macro tiles (one per CTA of the pair) x one 128-channel N tile
+  const int num_work = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
+  const int work_first = blockIdx.x / 2;
+  const int work_stride = gridDim.x / 2;
   const int tiles_per_img = p.tiles_w * p.tiles_h;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.num_src; ++s) tma_prefetch_desc(&p.tmap_a[s]);
     tma_prefetch_desc(&p.tmap_b);
   }
+  cluster_sync_relaxed();  // both CTAs are resident before TMEM is allocated for the pair
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStagesA; ++i) {
-      mbar_init(&full_a[i], 1);
+      mbar_init(&full_a[i], 2);  // the leader's barrier collects both producers
       mbar_init(&empty_a[i], 1);
     }
     for (int i = 0; i < kStagesB; ++i) {
-      mbar_init(&full_b[i], 1);
+      mbar_init(&full_b[i], 2);
       mbar_init(&empty_b[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 128);
+      mbar_init(&tempty[i], 2 * kEpiWarps * 32);  // both epilogues release the leader's accumulator stage
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+  if (warp == 2) tmem_alloc_pair(tmem_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
+  cluster_sync_relaxed();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ weight producer (one per CTA)
     if (lane == 0) {
-      int sa = 0, sb = 0;
-      uint32_t pa = 0, pb = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.num_n_tiles;
-        const int n_idx = tile - m_tile * p.num_n_tiles;
-        const int n = m_tile / tiles_per_img;
-        const int r = m_tile - n * tiles_per_img;
-        const int ty = r / p.tiles_w;
-        const int tx = r - ty * p.tiles_w;
+      int sb = 0;
+      uint32_t pb = 0;
+      for (int work = work_first; work < num_work; work += work_stride) {
+        const int n_idx = work % p.num_n_tiles;
+        const int b_row = n_idx * kNTile + static_cast<int>(cta_rank) * (kNTile / 2);
         int koff = 0;
         for (int s = 0; s < p.num_src; ++s) {
           const int C = p.src_c[s];
           const int ntaps = p.src_taps[s];
           for (int ch = 0; ch < C / kConvBlockK; ++ch) {
-            mbar_wait(&empty_a[sa], pa ^ 1);
-            mbar_arrive_expect_tx(&full_a[sa], kABytes);
-            tma_load_4d(a_ring + sa * kASlotBytes, &p.tmap_a[s], &full_a[sa], ch * kConvBlockK, tx * kTileW - 1,
-                        ty * kTileH - 1, n);
-            if (++sa == kStagesA) {
-              sa = 0;
-              pa ^= 1;
-            }
-            for (int tap = 0; tap < ntaps; ++tap) {
+            for (int tap0 = 0; tap0 < ntaps; tap0 += kTapsPerStage) {
+              const int nt = ntaps - tap0 < kTapsPerStage ? ntaps - tap0 : kTapsPerStage;
               mbar_wait(&empty_b[sb], pb ^ 1);
-              mbar_arrive_expect_tx(&full_b[sb], kBSlotBytes);
-              tma_load_2d(b_ring + sb * kBSlotBytes, &p.tmap_b, &full_b[sb], koff + tap * C + ch * kConvBlockK,
-                          n_idx * kNTile);
+              if (leader) {
+                mbar_arrive_expect_tx(&full_b[sb], static_cast<uint32_t>(2 * nt * kBTapBytes));
+              } else {
+                mbar_arrive_cluster(&full_b[sb], 0);
+              }
+              for (int t = 0; t < nt; ++t)
+                tma_load_2d_pair(b_ring + sb * kBSlotBytes + t * kBTapBytes, &p.tmap_b, &full_b[sb],
+                                 koff + (tap0 + t) * C + ch * kConvBlockK, b_row);
               if (++sb == kStagesB) {
                 sb = 0;
                 pb ^= 1;
@@ -160,12 +178,43 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm2_kernel(const __gr
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ halo-tile producer (one per CTA)
+    // Its own thread, so tile loads run ahead by the depth of the tile ring instead of trailing the weight ring.
+    if (lane == 0) {
+      int sa = 0;
+      uint32_t pa = 0;
+      for (int work = work_first; work < num_work; work += work_stride) {
+        const int m_tile = 2 * (work / p.num_n_tiles) + static_cast<int>(cta_rank);
+        // an odd trailing tile has no partner: its coordinates fall outside the batch and TMA fills zeros
+        const int n = m_tile / tiles_per_img;
+        const int r = m_tile - n * tiles_per_img;
+        const int ty = r / p.tiles_w;
+        const int tx = r - ty * p.tiles_w;
+        for (int s = 0; s < p.num_src; ++s) {
+          for (int ch = 0; ch < p.src_c[s] / kConvBlockK; ++ch) {
+            mbar_wait(&empty_a[sa], pa ^ 1);
+            if (leader) {
+              mbar_arrive_expect_tx(&full_a[sa], 2 * kABytes);
+            } else {
+              mbar_arrive_cluster(&full_a[sa], 0);
+            }
+            tma_load_4d_pair(a_ring + sa * kASlotBytes, &p.tmap_a[s], &full_a[sa], ch * kConvBlockK, tx * kTileW - 1,
+                             ty * kTileH - 1, n);
+            if (++sa == kStagesA) {
+              sa = 0;
+              pa ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && leader) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
     // Every operand of the MMAs is warp-uniform (shuffled bases, descriptors advanced by constants) and the issuing
     // lane is elected, so the compiler emits back-to-back UTCHMMA from uniform registers: ~45 cycles of issue per MMA
     // against 64 cycles of tensor time (tools/ubench_mma.cu; per-thread operands cost ~160 cycles per MMA).
-    const uint32_t idesc = umma_idesc_f16(128, kNTile, static_cast<uint32_t>(p.ab_format));
+    const uint32_t idesc = umma_idesc_f16(256, kNTile, static_cast<uint32_t>(p.ab_format));
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t a_ring_u = __shfl_sync(0xffffffffu, smem_u32(a_ring), 0);
     const uint32_t b_ring_u = __shfl_sync(0xffffffffu, smem_u32(b_ring), 0);
@@ -173,7 +222,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm2_kernel(const __gr
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
     int iter = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+    for (int work = work_first; work < num_work; work += work_stride, ++iter) {
       const int acc = iter & 1;
       const uint32_t acc_phase = (iter >> 1) & 1;
       mbar_wait(&tempty[acc], acc_phase ^ 1);
@@ -183,32 +232,48 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm2_kernel(const __gr
       for (int s = 0; s < p.num_src; ++s) {
         const int chunks = p.src_c[s] / kConvBlockK;
         const bool c3 = p.src_taps[s] == 9;
-        const int ntaps = c3 ? 9 : 1;
+        const bool last_src = s == p.num_src - 1;
         for (int ch = 0; ch < chunks; ++ch) {
           mbar_wait(&full_a[sa], pa);
           const uint64_t a_desc = umma_desc_k128_sbo(a_ring_u + sa * kASlotBytes, kHaloPitch);
-          for (int tap = 0; tap < ntaps; ++tap) {
-            const int t = c3 ? tap : 4;  // a 1x1 source reads the centre of the halo tile
-            const int dy = t / 3;
-            const int dx = t - 3 * dy;
+          const int nrows = c3 ? 3 : 1;
+          for (int row = 0; row < nrows; ++row) {
             mbar_wait(&full_b[sb], pb);
             tc_fence_after();
-            const bool last_tap = tap == ntaps - 1;
-            const bool last_step = last_tap && ch == chunks - 1 && s == p.num_src - 1;
+            const bool last_row = row == nrows - 1;
+            const bool last_step = last_row && last_src && ch == chunks - 1;
             if (elected) {
-              const uint64_t ad = a_desc + static_cast<uint64_t>((dy * kHaloW + dx) * (kRowBytes / 16));
               const uint64_t bd = umma_desc_k128(b_ring_u + sb * kBSlotBytes);
+              if (c3) {
+                // kernel row `row`: taps (row, 0..2) read the halo tile from pixel (row, dx + 8 m)
+                const uint64_t ad = a_desc + static_cast<uint64_t>(row * kHaloW * (kRowBytes / 16));
 #pragma unroll
-              for (int m = 0; m < kMTiles; ++m) {
+                for (int dx = 0; dx < 3; ++dx) {
 #pragma unroll
-                for (int kk = 0; kk < kConvBlockK / 16; ++kk) {
-                  umma_f16_ss(tmem_d + m * kNTile, ad + (m * 8 * (kRowBytes / 16) + kk * 2), bd + kk * 2, idesc,
-                              kk == 0 ? accum : 1u);
+                  for (int m = 0; m < kMTiles; ++m) {
+#pragma unroll
+                    for (int kk = 0; kk < kConvBlockK / 16; ++kk) {
+                      umma_f16_ss_pair(tmem_d + m * kNTile, ad + ((dx + m * 8) * (kRowBytes / 16) + kk * 2),
+                                       bd + (dx * (kBTapBytes / 16) + kk * 2), idesc,
+                                       (dx == 0 && kk == 0) ? accum : 1u);
+                    }
+                  }
+                }
+              } else {
+                // 1x1 source: the centre of the halo tile
+                const uint64_t ad = a_desc + static_cast<uint64_t>((kHaloW + 1) * (kRowBytes / 16));
+#pragma unroll
+                for (int m = 0; m < kMTiles; ++m) {
+#pragma unroll
+                  for (int kk = 0; kk < kConvBlockK / 16; ++kk) {
+                    umma_f16_ss_pair(tmem_d + m * kNTile, ad + (m * 8 * (kRowBytes / 16) + kk * 2), bd + kk * 2, idesc,
+                                     kk == 0 ? accum : 1u);
+                  }
                 }
               }
-              umma_commit(&empty_b[sb]);
-              if (last_tap) umma_commit(&empty_a[sa]);
-              if (last_step) umma_commit(&tfull[acc]);
+              umma_commit_pair(&empty_b[sb]);
+              if (last_row) umma_commit_pair(&empty_a[sa]);
+              if (last_step) umma_commit_pair(&tfull[acc]);
             }
             accum = 1;
             if (++sb == kStagesB) {
@@ -224,89 +289,95 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm2_kernel(const __gr
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue
-    const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;  // pixel within an M tile: (row / 8, row % 8)
+    // ------------------------------------------------------------------ epilogue (one warpgroup per M tile)
+    const int quarter = warp & 3;     // TMEM lane quarter this warp may read
+    const int m = (warp - 4) >> 2;    // M tile of this warpgroup
+    const int ew = warp - 4;
+    const int row = quarter * 32 + lane;  // pixel within the M tile: (row / 8, row % 8)
     const int fmt = p.ab_format;
     const int nb4 = p.Cout >> 2;
+    const int epi_tid = threadIdx.x - 128;
     int iter = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+    for (int work = work_first; work < num_work; work += work_stride, ++iter) {
       const int acc = iter & 1;
       const uint32_t acc_phase = (iter >> 1) & 1;
-      const int m_tile = tile / p.num_n_tiles;
-      const int n_idx = tile - m_tile * p.num_n_tiles;
+      const int m_tile = 2 * (work / p.num_n_tiles) + static_cast<int>(cta_rank);
+      const int n_idx = work % p.num_n_tiles;
+      const bool valid = m_tile < p.num_m_tiles;
       const int n = m_tile / tiles_per_img;
       const int r = m_tile - n * tiles_per_img;
       const int ty = r / p.tiles_w;
       const int tx = r - ty * p.tiles_w;
-      const int x0 = tx * kTileW + (row & 7);
+      const int x = tx * kTileW + m * 8 + (row & 7);
       const int y = ty * kTileH + (row >> 3);
+      const size_t off0 = ((static_cast<size_t>(n) * p.H + y) * p.W + x) * p.Cout + n_idx * kNTile;
+      const bool has_res = p.residual != nullptr && valid;
 
+      uint4 rnext[4];
+      if (has_res) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) rnext[q] = __ldg(rp + q);
+      }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                             static_cast<uint32_t>(acc * kMTiles * kNTile);
+                             static_cast<uint32_t>((acc * kMTiles + m) * kNTile);
 #pragma unroll 1
       for (int c = 0; c < kNTile / 32; ++c) {
         const int co = n_idx * kNTile + c * 32;
-        float v16[16];
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c * 32, v);
+        uint4 rcur[4];
+        if (has_res) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v16[j] = 0.f;
+          for (int q = 0; q < 4; ++q) rcur[q] = rnext[q];
+          if (c + 1 < kNTile / 32) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off0 + (c + 1) * 32);
 #pragma unroll
-        for (int m = 0; m < kMTiles; ++m) {
-          uint32_t v[32];
-          tmem_ld_32x32(taddr + m * kNTile + c * 32, v);
-          tmem_ld_wait();
-          if (c == kNTile / 32 - 1 && m == kMTiles - 1) {
-            tc_fence_before();
-            mbar_arrive(&tempty[acc]);
+            for (int q = 0; q < 4; ++q) rnext[q] = __ldg(rp + q);
           }
-          const size_t off = ((static_cast<size_t>(n) * p.H + y) * p.W + x0 + m * 8) * p.Cout + co;
-          float f[32];
+        }
+        tmem_ld_wait();
+        if (c == kNTile / 32 - 1) {
+          // every TMEM read of this accumulator stage has completed: hand it back to the leader's MMA warp
+          tc_fence_before();
+          mbar_arrive_cluster(&tempty[acc], 0);
+        }
+        float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (p.bias != nullptr) {
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.bias != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + co + j));
-              f[j] += bv.x;
-              f[j + 1] += bv.y;
-              f[j + 2] += bv.z;
-              f[j + 3] += bv.w;
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + co + j));
+            f[j] += bv.x;
+            f[j + 1] += bv.y;
+            f[j + 2] += bv.z;
+            f[j + 3] += bv.w;
+          }
+        }
+        if (has_res) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t w[4] = {rcur[q].x, rcur[q].y, rcur[q].z, rcur[q].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 t = unpack16(w[e], fmt);
+              f[q * 8 + e * 2] += t.x;
+              f[q * 8 + e * 2 + 1] += t.y;
             }
           }
-          if (p.residual != nullptr) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off);
+        }
+        if (p.relu == 1) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 rv = __ldg(rp + q);
-              const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        } else if (p.relu == 2) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 t = unpack16(w[e], fmt);
-                f[q * 8 + e * 2] += t.x;
-                f[q * 8 + e * 2 + 1] += t.y;
-              }
-            }
-          }
-          if (p.relu == 1) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-          } else if (p.relu == 2) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.0f + __expf(-f[j]));
-          }
-          if (p.gn_stats != nullptr) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                v16[k] += f[4 * k + j];
-                v16[8 + k] = fmaf(f[4 * k + j], f[4 * k + j], v16[8 + k]);
-              }
-            }
-          }
-          uint4* op = reinterpret_cast<uint4*>(p.out + off);
+          for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.0f + __expf(-f[j]));
+        }
+        if (valid) {
+          uint4* op = reinterpret_cast<uint4*>(p.out + off0 + c * 32);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             uint4 o;
@@ -318,7 +389,19 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm2_kernel(const __gr
           }
         }
         if (p.gn_stats != nullptr) {
-          // butterfly over the warp's 32 pixels: 16 shuffles leave value (lane >> 1) & 15 in every lane
+          // per 4-channel bucket: sum and sum of squares of this pixel, then a butterfly over the warp's 32 pixels
+          // (16 shuffles leave value (lane >> 1) & 15 in every lane)
+          float v16[16];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            v16[k] = 0.f;
+            v16[8 + k] = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              v16[k] += f[4 * k + j];
+              v16[8 + k] = fmaf(f[4 * k + j], f[4 * k + j], v16[8 + k]);
+            }
+          }
 #pragma unroll
           for (int w = 8; w >= 1; w >>= 1) {
             const int msk = w * 2;
@@ -331,17 +414,19 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm2_kernel(const __gr
             }
           }
           const float tot = v16[0] + __shfl_xor_sync(0xffffffffu, v16[0], 1);
-          if ((lane & 1) == 0) stat_sh[(acc * 4 + quarter) * kStatW2 + c * 16 + (lane >> 1)] = tot;
+          if ((lane & 1) == 0) stat_sh[(acc * kEpiWarps + ew) * kStatW2 + c * 16 + (lane >> 1)] = tot;
         }
       }
       if (p.gn_stats != nullptr) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (row < kStatW2) {
-          const int within = row & 15;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (epi_tid < kStatW2 && valid) {
+          const int within = epi_tid & 15;
           const int is_q = within >> 3;
-          const int bucket = (row >> 4) * 8 + (within & 7);
-          const float* sp = stat_sh + acc * 4 * kStatW2 + row;
-          const float t = sp[0] + sp[kStatW2] + sp[2 * kStatW2] + sp[3 * kStatW2];
+          const int bucket = (epi_tid >> 4) * 8 + (within & 7);
+          const float* sp = stat_sh + acc * kEpiWarps * kStatW2 + epi_tid;
+          float t = 0.f;
+#pragma unroll
+          for (int w = 0; w < kEpiWarps; ++w) t += sp[w * kStatW2];
           atomicAdd(&p.gn_stats[(static_cast<size_t>(n) * nb4 + n_idx * (kNTile >> 2) + bucket) * 2 + is_q],
                     static_cast<double>(t));
         }
@@ -351,9 +436,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm2_kernel(const __gr
 
   tc_fence_before();
   __syncthreads();
+  cluster_sync_relaxed();  // the peer may still be reading operands / TMEM that belong to the pair
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    tmem_dealloc_pair(tmem_base, kTmemCols);
   }
 }
 
@@ -415,7 +501,7 @@ int build_conv2(const ConvDesc& d, std::shared_ptr<void>* holder) {
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(ktot), static_cast<uint64_t>(d.Cout)};
     const uint64_t strides[1] = {static_cast<uint64_t>(ktot) * 2};
-    const uint32_t box[2] = {static_cast<uint32_t>(kConvBlockK), static_cast<uint32_t>(kNTile)};
+    const uint32_t box[2] = {static_cast<uint32_t>(kConvBlockK), static_cast<uint32_t>(kNTile / 2)};
     CDDPM_TRY(encode_tmap_16bit(&p.tmap_b, d.wpacked, 2, dims, strides, box));
   }
   *holder = L;
@@ -429,10 +515,22 @@ int launch_conv2(const std::shared_ptr<void>& holder, cudaStream_t stream) {
     attr_set = true;
   }
   const Conv2Launch* L = reinterpret_cast<const Conv2Launch*>(holder.get());
-  const int num_tiles = L->p.num_m_tiles * L->p.num_n_tiles;
-  int grid = device_sm_count();
-  if (num_tiles < grid) grid = num_tiles;
-  conv_igemm2_kernel<<<grid, kConvThreads, kSmemBytes2, stream>>>(L->p);
+  const int num_work = ((L->p.num_m_tiles + 1) / 2) * L->p.num_n_tiles;
+  int pairs = device_sm_count() / 2;
+  if (num_work < pairs) pairs = num_work;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(kThreads2);
+  cfg.dynamicSmemBytes = kSmemBytes2;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CDDPM_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm2_kernel, L->p));
   return check_launch("conv_igemm2_kernel");
 }
 

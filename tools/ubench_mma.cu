@@ -171,6 +171,66 @@ __global__ void __launch_bounds__(128, 1) shift_kernel(int shift, int group_rows
   if (warp == 0) tmem_dealloc(tmem_base, 64);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// 3. MN-major B operand (what P x V of attention needs: V is stored [key][head_dim], i.e. N contiguous).
+//    A = P [128 x 64 keys] K-major SW128; B = V [64 keys][64 dims] as TMA SWIZZLE_128B would stage it (one 128-byte row
+//    per key); D = P x V.  The instruction descriptor's B-major bit (16) is set; (lbo, sbo) are swept by the host.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) mnmajor_kernel(int lbo, int sbo, int kstep_bytes, float* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t done_bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* a_sm = smem;              // P: 128 rows x 128 B
+  uint8_t* b_sm = smem + 128 * 128;  // V: 64 keys x 128 B
+  for (int i = threadIdx.x; i < 128 * 64; i += blockDim.x) {
+    const int r = i / 64, c = i % 64;
+    const int off = r * 128 + (((c / 8) ^ (r % 8)) * 16) + (c % 8) * 2;
+    *reinterpret_cast<__half*>(a_sm + off) = __float2half(static_cast<float>((r + c) % 3));
+  }
+  for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
+    const int k = i / 64, d = i % 64;
+    const int off = k * 128 + (((d / 8) ^ (k % 8)) * 16) + (d % 8) * 2;
+    *reinterpret_cast<__half*>(b_sm + off) = __float2half(static_cast<float>((k * 7 + d) % 5));
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(&done_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, 64);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  if (threadIdx.x == 32) {
+    const uint32_t idesc = umma_idesc_f16(128, 64, 0) | (1u << 16);
+    for (int k = 0; k < 4; ++k) {
+      uint64_t bd = 0;
+      const uint32_t b_addr = smem_u32(b_sm) + k * kstep_bytes;
+      bd |= static_cast<uint64_t>((b_addr & 0x3FFFF) >> 4);
+      bd |= static_cast<uint64_t>(lbo >> 4) << 16;
+      bd |= static_cast<uint64_t>(sbo >> 4) << 32;
+      bd |= static_cast<uint64_t>(1) << 46;
+      bd |= static_cast<uint64_t>(2) << 61;
+      umma_f16_ss(tmem_base, umma_desc_k128(smem_u32(a_sm) + k * 32), bd, idesc, k != 0 ? 1u : 0u);
+    }
+    umma_commit(&done_bar);
+  }
+  mbar_wait(&done_bar, 0);
+  tc_fence_after();
+  for (int c0 = 0; c0 < 64; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c0, v);
+    tmem_ld_wait();
+    for (int j = 0; j < 32; ++j) out[(warp * 32 + lane) * 64 + c0 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 64);
+}
+
 template <bool kCommit, int kAccs, int kWarps, bool kPair, int kPerGroup>
 static void run_issue(int n_tile, int grid, unsigned long long* d_out) {
   const int groups = 2000, stages = 4;
@@ -242,6 +302,25 @@ int main() {
         }
       printf("shift %3d rows, group stride %2d rows, base_offset field %s: %s (%d of 8192 wrong)\n", shift, group_rows,
              ubo ? "set" : "zero", bad ? "MISMATCH" : "exact", bad);
+    }
+  }
+  {
+    const int smem2 = 128 * 128 + 64 * 128 + 1024;
+    const int combos[][3] = {{0, 1024, 2048}, {1024, 1024, 2048}, {128, 1024, 2048}, {2048, 1024, 2048},
+                             {1024, 2048, 2048}, {0, 2048, 2048}, {1024, 128, 2048}, {8192, 1024, 2048}};
+    for (const auto& c : combos) {
+      mnmajor_kernel<<<1, 128, smem2>>>(c[0], c[1], c[2], d_f);
+      CK(cudaDeviceSynchronize());
+      CK(cudaMemcpy(h.data(), d_f, h.size() * sizeof(float), cudaMemcpyDeviceToHost));
+      int bad = 0;
+      for (int m = 0; m < 128; ++m)
+        for (int n = 0; n < 64; ++n) {
+          float want = 0.f;
+          for (int k = 0; k < 64; ++k) want += static_cast<float>((m + k) % 3) * static_cast<float>((k * 7 + n) % 5);
+          if (h[m * 64 + n] != want) ++bad;
+        }
+      printf("MN-major B: lbo %5d sbo %5d k-step %5d B: %s (%d of 8192 wrong)\n", c[0], c[1], c[2],
+             bad ? "MISMATCH" : "exact", bad);
     }
   }
   return 0;
