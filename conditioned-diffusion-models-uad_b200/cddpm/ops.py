@@ -59,3 +59,13 @@ def conv_igemm(
         "cddpm_conv_igemm",
     )
     return out
+
+
+def attention(qkv: torch.Tensor, channels: int) -> torch.Tensor:
+    """QKVAttention over qkv [B, L, 3*C] (q | k | v, heads of 64 channels) -> [B, L, C] (OpenAI_Unet.py:457-476)."""
+    B, L, c3 = qkv.shape
+    assert c3 == 3 * channels
+    out = torch.empty(B, L, channels, device=qkv.device, dtype=qkv.dtype)
+    check(lib().cddpm_attention(ptr(qkv), ptr(out), B, L, channels, fmt_of(qkv.dtype), current_stream()),
+          "cddpm_attention")
+    return out
