@@ -42,26 +42,31 @@ namespace cddpm {
 namespace {
 
 constexpr int kThreads2 = 384;
-constexpr int kTileW = 16;                // macro tile (output pixels) of one CTA
-constexpr int kTileH = 16;
-constexpr int kHaloW = kTileW + 2;
+constexpr int kTileH = 16;                // rows of a macro tile (= the 16 row groups of an M tile)
 constexpr int kHaloH = kTileH + 2;
-constexpr int kMTiles = 2;                // M tiles per macro tile, side by side, each 8 wide x 16 high
 constexpr int kNTile = 128;               // output channels per work item
 constexpr int kRowBytes = 128;            // 64 channels x 16 bit
-constexpr int kHaloPitch = kHaloW * kRowBytes;          // 2304 B between the 8-pixel row groups of an M tile
-constexpr int kABytes = kHaloW * kHaloH * kRowBytes;    // 41472 B per staged halo tile
-constexpr int kASlotBytes = (kABytes + 1023) & ~1023;   // slots stay 1 KB aligned (swizzle atom)
 constexpr int kBTapBytes = (kNTile / 2) * kRowBytes;    // 8192: this CTA's 64 weight rows of one tap
 constexpr int kTapsPerStage = 3;
 constexpr int kBSlotBytes = kTapsPerStage * kBTapBytes; // 24576
 constexpr int kStagesA = 3;
 constexpr int kStagesB = 4;
-constexpr int kEpiWarps = 8;
 constexpr int kStatW2 = 64;               // (128 / 32) chunks x 16 values per warp
-constexpr int kStatBytes2 = 2 * kEpiWarps * kStatW2 * 4;
-constexpr int kSmemBytes2 = kStagesA * kASlotBytes + kStagesB * kBSlotBytes + 256 + kStatBytes2 + 1024;
-constexpr int kTmemCols = 512;            // 2 stages x 2 M tiles x 128 columns
+constexpr int kTmemCols = 512;            // 2 stages x (up to) 2 M tiles x 128 columns
+
+// Geometry for kMT M tiles (each 8 pixels wide x 16 high) side by side per CTA: 2 where the image width is a multiple
+// of 16, 1 for the 24 x 24 level (rows past the image bottom are computed on zero padding and masked on the way out).
+template <int kMT>
+struct Geo {
+  static constexpr int kTileW = 8 * kMT;                           // macro tile (output pixels) of one CTA
+  static constexpr int kHaloW = kTileW + 2;
+  static constexpr int kHaloPitch = kHaloW * kRowBytes;            // bytes between the 8-pixel row groups of an M tile
+  static constexpr int kABytes = kHaloW * kHaloH * kRowBytes;      // one staged halo tile (41472 B for kMT = 2)
+  static constexpr int kASlotBytes = (kABytes + 1023) & ~1023;     // slots stay 1 KB aligned (swizzle atom)
+  static constexpr int kEpiWarps = 4 * kMT;
+  static constexpr int kStatBytes = 2 * kEpiWarps * kStatW2 * 4;
+  static constexpr int kSmemBytes = kStagesA * kASlotBytes + kStagesB * kBSlotBytes + 256 + kStatBytes + 1024;
+};
 
 struct Conv2Params {
   CUtensorMap tmap_a[kConvMaxSrc];  // {C, W, H, B}; box {64, 18, 18, 1}
@@ -72,6 +77,7 @@ struct Conv2Params {
   int B, H, W, Cout;
   int tiles_w, tiles_h;  // macro tiles per image
   int num_m_tiles, num_n_tiles;
+  int mt;  // M tiles per CTA (kernel template argument)
   int ab_format, relu;
   const float* bias;
   const uint16_t* residual;
@@ -92,7 +98,16 @@ __device__ __forceinline__ float2 unpack16(uint32_t u, int fmt) {
   return __half22float2(*reinterpret_cast<__half2*>(&u));
 }
 
+template <int kMT>
 __global__ void __launch_bounds__(kThreads2, 1) conv_igemm2_kernel(const __grid_constant__ Conv2Params p) {
+  using G = Geo<kMT>;
+  constexpr int kMTiles = kMT;
+  constexpr int kTileW = G::kTileW;
+  constexpr int kHaloW = G::kHaloW;
+  constexpr int kHaloPitch = G::kHaloPitch;
+  constexpr int kABytes = G::kABytes;
+  constexpr int kASlotBytes = G::kASlotBytes;
+  constexpr int kEpiWarps = G::kEpiWarps;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_ring = smem;
@@ -288,7 +303,7 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_igemm2_kernel(const __grid_
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 4 + kEpiWarps) {
     // ------------------------------------------------------------------ epilogue (one warpgroup per M tile)
     const int quarter = warp & 3;     // TMEM lane quarter this warp may read
     const int m = (warp - 4) >> 2;    // M tile of this warpgroup
@@ -311,7 +326,8 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_igemm2_kernel(const __grid_
       const int x = tx * kTileW + m * 8 + (row & 7);
       const int y = ty * kTileH + (row >> 3);
       const size_t off0 = ((static_cast<size_t>(n) * p.H + y) * p.W + x) * p.Cout + n_idx * kNTile;
-      const bool has_res = p.residual != nullptr && valid;
+      const bool in_img = valid && y < p.H;  // the bottom tile of a 24-row image hangs over its edge
+      const bool has_res = p.residual != nullptr && in_img;
 
       uint4 rnext[4];
       if (has_res) {
@@ -376,7 +392,7 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_igemm2_kernel(const __grid_
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.0f + __expf(-f[j]));
         }
-        if (valid) {
+        if (in_img) {
           uint4* op = reinterpret_cast<uint4*>(p.out + off0 + c * 32);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -398,8 +414,9 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_igemm2_kernel(const __grid_
             v16[8 + k] = 0.f;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              v16[k] += f[4 * k + j];
-              v16[8 + k] = fmaf(f[4 * k + j], f[4 * k + j], v16[8 + k]);
+              const float fv = in_img ? f[4 * k + j] : 0.f;
+              v16[k] += fv;
+              v16[8 + k] = fmaf(fv, fv, v16[8 + k]);
             }
           }
 #pragma unroll
@@ -418,7 +435,7 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_igemm2_kernel(const __grid_
         }
       }
       if (p.gn_stats != nullptr) {
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
         if (epi_tid < kStatW2 && valid) {
           const int within = epi_tid & 15;
           const int is_q = within >> 3;
@@ -456,7 +473,7 @@ bool conv2_enabled() {
 
 bool conv2_supported(const ConvDesc& d) {
   if (d.flat_rows > 0 || d.out_is_f32 || d.out_stride > 0 || d.out_col_off != 0) return false;
-  if (d.W % kTileW != 0 || d.H % kTileH != 0) return false;
+  if (d.W % 8 != 0 || d.H % 8 != 0) return false;
   if (d.Cout % kNTile != 0) return false;
   for (int s = 0; s < d.num_src; ++s)
     if (d.src_c[s] % kConvBlockK != 0 || (d.src_taps[s] != 1 && d.src_taps[s] != 9)) return false;
@@ -476,8 +493,9 @@ int build_conv2(const ConvDesc& d, std::shared_ptr<void>* holder) {
   p.H = d.H;
   p.W = d.W;
   p.Cout = d.Cout;
-  p.tiles_w = d.W / kTileW;
-  p.tiles_h = d.H / kTileH;
+  p.mt = (d.W % 16 == 0 && d.H % 16 == 0) ? 2 : 1;
+  p.tiles_w = d.W / (8 * p.mt);
+  p.tiles_h = (d.H + kTileH - 1) / kTileH;
   p.num_m_tiles = d.B * p.tiles_w * p.tiles_h;
   p.num_n_tiles = d.Cout / kNTile;
   p.ab_format = d.ab_format;
@@ -493,7 +511,7 @@ int build_conv2(const ConvDesc& d, std::shared_ptr<void>* holder) {
     const uint64_t C = static_cast<uint64_t>(d.src_c[s]);
     const uint64_t dims[4] = {C, static_cast<uint64_t>(d.W), static_cast<uint64_t>(d.H), static_cast<uint64_t>(d.B)};
     const uint64_t strides[3] = {C * 2, C * 2 * d.W, C * 2 * d.W * d.H};
-    const uint32_t box[4] = {static_cast<uint32_t>(kConvBlockK), static_cast<uint32_t>(kHaloW),
+    const uint32_t box[4] = {static_cast<uint32_t>(kConvBlockK), static_cast<uint32_t>(8 * p.mt + 2),
                              static_cast<uint32_t>(kHaloH), 1u};
     CDDPM_TRY(encode_tmap_16bit(&p.tmap_a[s], d.src[s], 4, dims, strides, box));
     ktot += d.src_taps[s] * d.src_c[s];
@@ -511,7 +529,10 @@ int build_conv2(const ConvDesc& d, std::shared_ptr<void>* holder) {
 int launch_conv2(const std::shared_ptr<void>& holder, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    CDDPM_CUDA(cudaFuncSetAttribute(conv_igemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2));
+    CDDPM_CUDA(cudaFuncSetAttribute(conv_igemm2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    Geo<1>::kSmemBytes));
+    CDDPM_CUDA(cudaFuncSetAttribute(conv_igemm2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    Geo<2>::kSmemBytes));
     attr_set = true;
   }
   const Conv2Launch* L = reinterpret_cast<const Conv2Launch*>(holder.get());
@@ -521,7 +542,7 @@ int launch_conv2(const std::shared_ptr<void>& holder, cudaStream_t stream) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * pairs);
   cfg.blockDim = dim3(kThreads2);
-  cfg.dynamicSmemBytes = kSmemBytes2;
+  cfg.dynamicSmemBytes = L->p.mt == 2 ? Geo<2>::kSmemBytes : Geo<1>::kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -530,7 +551,11 @@ int launch_conv2(const std::shared_ptr<void>& holder, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CDDPM_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm2_kernel, L->p));
+  if (L->p.mt == 2) {
+    CDDPM_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm2_kernel<2>, L->p));
+  } else {
+    CDDPM_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm2_kernel<1>, L->p));
+  }
   return check_launch("conv_igemm2_kernel");
 }
 
