@@ -69,6 +69,7 @@ struct ConvDesc {
   int relu = 0;         // 0 none, 1 ReLU, 2 SiLU
   int out_stride = 0;   // 0 = Cout
   int out_col_off = 0;
+  int identity_k = 0;   // K columns that only add a tensor through an identity weight block (not counted as FLOPs)
 };
 
 // Second-generation kernel (conv_igemm2.cu): 16x16-pixel macro tiles x 128 channels; one staged 18x18 halo tile per
