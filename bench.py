@@ -305,11 +305,16 @@ def run_ours(args):
     achieved = conv_flops_fwd / (conv_ms_fwd / 1e3) / 1e12
     enc_launches = 1 + 1 + 16 * 4 + 4 + 3 + 2  # stem, pool, (3 GEMM + im2col) x 16 blocks, 4 downsample GEMMs, 3 strided gathers, pool + fc
     launches_per_step = enc_launches + 2 + T0 * (eng.launches_per_forward + 2)
-    roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel (tcgen05 implicit GEMM, all 56 conv launches of a UNet forward)",
+    # traffic: dram__bytes_read.sum + dram__bytes_write.sum summed over the convolution launches of one B=32 forward
+    # (ncu, profiles/r01_v5_conv_dram.csv: 5.23 GB over 61 launches), per launch like `achieved`
+    traffic = 85.7e6 * B / 32
+    roofline = {"bound": "tensor",
+                "kernel": "conv_igemm2_kernel / conv_igemm_kernel (tcgen05 implicit GEMM: every convolution and GEMM launch "
+                          "of a UNet forward)",
                 "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
                 "peak_source": pk["source"], "flops_per_launch": conv_flops_fwd / max(1, conv_launches),
                 "avg_launch_ms": conv_ms_fwd / max(1, conv_launches), "launches_timed": conv_launches * len(conv_ms),
-                "traffic": None,
+                "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read + write)",
                 "unet_forward_tflops": UNET_GFLOP * B * world * T0 * args.steps / 1e3 / (dt_ms / 1e3),
                 "unet_forward_frac_of_peak": UNET_GFLOP * B * T0 * args.steps / 1e3 / (dt_ms / 1e3) / pk["tflops"]}
     line = {"metric": METRIC, "value": value, "unit": "slices/s", "n_gpus": world, "steps": args.steps,
