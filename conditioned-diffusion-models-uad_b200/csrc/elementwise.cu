@@ -383,92 +383,218 @@ __global__ void to16_kernel(const float* __restrict__ in, uint16_t* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------- stem / head convs
+// Both are HBM-bound (75 MB written / read at B=32) and far too thin for the tensor cores (K = 9, N = 1); what they
+// must not be is instruction-bound.  A warp owns a run of 32 consecutive pixels of one image; lane l owns channels
+// [l*NPER, (l+1)*NPER) (NPER = C/32), so every access to the NHWC tensor is one contiguous 2*C-byte row per pixel and
+// the lane's 9*NPER weights live in registers.  The 3x3 window slides along the run: three new loads per pixel, the
+// column slots rotate at compile time (the loop over the run is fully unrolled), and the window is re-primed where
+// a run wraps onto the next image row.
+
+// Stem 1 -> C: the inputs of a pixel are warp-uniform broadcast loads.  Also emits the GroupNorm (sum, sumsq)
+// buckets of the tensor it writes (on the rounded values, exactly what a separate pass over the output would see).
+template <int NPER>
 __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                       const float* __restrict__ bias, uint16_t* __restrict__ out,
-                                                      int B, int H, int W, int Cout, int fmt) {
-  extern __shared__ float sw[];  // [9][Cout] weights, [Cout] bias
-  for (int i = threadIdx.x; i < 9 * Cout; i += blockDim.x) {
-    const int tap = i / Cout, co = i - tap * Cout;
-    sw[i] = w[co * 9 + tap];
+                                                      double* __restrict__ stats, int H, int W, int fmt) {
+  constexpr int C = 32 * NPER;
+  constexpr int NB = NPER >= 4 ? NPER / 4 : 1;  // 4-channel statistic buckets (partly) owned by a lane
+  __shared__ float red[8][32][2 * NB];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y, HW = H * W;
+  float wr[9][NPER], br[NPER];
+#pragma unroll
+  for (int j = 0; j < NPER; ++j) {
+    br[j] = __ldg(bias + lane * NPER + j);
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) wr[tap][j] = __ldg(w + (lane * NPER + j) * 9 + tap);
   }
-  for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[9 * Cout + i] = bias[i];
-  __syncthreads();
-  const int ngrp = Cout >> 3;
-  const int ppb = blockDim.x / ngrp;
-  const int g = threadIdx.x % ngrp;
-  const int pl = threadIdx.x / ngrp;
-  if (pl >= ppb) return;
-  const size_t total = static_cast<size_t>(B) * H * W;
-  // this thread always produces the same 8 output channels: keep its 72 weights + 8 biases in registers
-  float wr[9][8], br[8];
+  float sum[NB], sq[NB];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) br[j] = sw[9 * Cout + g * 8 + j];
+  for (int k = 0; k < NB; ++k) sum[k] = sq[k] = 0.f;
+  const float* xb = x + static_cast<size_t>(b) * HW;
+  const int p0 = (blockIdx.x * 8 + warp) * 32;
+  int yh = p0 / W, xw = p0 - yh * W;
+  float win[3][3];  // [row dy+1][column slot]
+  auto load_col = [&](int slot, int xx) {
 #pragma unroll
-  for (int tap = 0; tap < 9; ++tap)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) wr[tap][j] = sw[tap * Cout + g * 8 + j];
-  for (size_t pix = static_cast<size_t>(blockIdx.x) * ppb + pl; pix < total; pix += static_cast<size_t>(gridDim.x) * ppb) {
-    const int xw = static_cast<int>(pix % W);
-    const int yh = static_cast<int>((pix / W) % H);
-    const size_t n = pix / (static_cast<size_t>(W) * H);
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = br[j];
-#pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-      const int iy = yh + tap / 3 - 1, ix = xw + tap % 3 - 1;
-      float v = 0.f;
-      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(x + (n * H + iy) * W + ix);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wr[tap][j], acc[j]);
+    for (int r = 0; r < 3; ++r) {
+      const int iy = yh + r - 1;
+      win[r][slot] = (iy >= 0 && iy < H && xx >= 0 && xx < W) ? __ldg(xb + iy * W + xx) : 0.f;
     }
-    *reinterpret_cast<uint4*>(out + pix * Cout + g * 8) = pack8(acc, fmt);
+  };
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int p = p0 + j;
+    if (p < HW) {
+      // column x + d lives in slot (j + d + 1) % 3
+      if (j == 0 || xw == 0) {
+        load_col(j % 3, xw - 1);
+        load_col((j + 1) % 3, xw);
+      }
+      load_col((j + 2) % 3, xw + 1);
+      float acc[NPER];
+#pragma unroll
+      for (int c = 0; c < NPER; ++c) acc[c] = br[c];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const float v = win[r][(j + d) % 3];
+#pragma unroll
+          for (int c = 0; c < NPER; ++c) acc[c] = fmaf(v, wr[r * 3 + d][c], acc[c]);
+        }
+      uint32_t pk[NPER / 2];
+#pragma unroll
+      for (int c = 0; c < NPER; c += 2) {
+        pk[c / 2] = pack2(acc[c], acc[c + 1], fmt);
+        float2 rr;
+        if (fmt == 1) {
+          rr = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk[c / 2]));
+        } else {
+          rr = __half22float2(*reinterpret_cast<const __half2*>(&pk[c / 2]));
+        }
+        constexpr int kLast = NB - 1;
+        const int k = c / 4 < kLast ? c / 4 : kLast;
+        sum[k] += rr.x + rr.y;
+        sq[k] = fmaf(rr.x, rr.x, fmaf(rr.y, rr.y, sq[k]));
+      }
+      uint16_t* op = out + (static_cast<size_t>(b) * HW + p) * C + lane * NPER;
+      if (NPER == 2) {
+        *reinterpret_cast<uint32_t*>(op) = pk[0];
+      } else if (NPER == 4) {
+        *reinterpret_cast<uint2*>(op) = make_uint2(pk[0], pk[1 % (NPER / 2)]);
+      } else {
+        *reinterpret_cast<uint4*>(op) = make_uint4(pk[0], pk[1 % (NPER / 2)], pk[2 % (NPER / 2)], pk[3 % (NPER / 2)]);
+      }
+    }
+    if (++xw == W) {
+      xw = 0;
+      ++yh;
+    }
+  }
+  if (stats == nullptr) return;
+  if (NPER == 2) {  // two lanes share a bucket
+    sum[0] += __shfl_xor_sync(0xffffffffu, sum[0], 1);
+    sq[0] += __shfl_xor_sync(0xffffffffu, sq[0], 1);
+  }
+#pragma unroll
+  for (int k = 0; k < NB; ++k) {
+    red[warp][lane][2 * k] = sum[k];
+    red[warp][lane][2 * k + 1] = sq[k];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * 2 * NB; i += blockDim.x) {
+    const int l = i / (2 * NB), kq = i - l * (2 * NB);
+    if (NPER == 2 && (l & 1)) continue;
+    float t = 0.f;
+#pragma unroll
+    for (int wq = 0; wq < 8; ++wq) t += red[wq][l][kq];
+    const int bucket = NPER == 2 ? (l >> 1) : l * NB + (kq >> 1);
+    atomicAdd(&stats[(static_cast<size_t>(b) * (C / 4) + bucket) * 2 + (kq & 1)], static_cast<double>(t));
   }
 }
 
-__global__ void __launch_bounds__(256) conv_out_kernel(const uint16_t* __restrict__ x, const float* __restrict__ w,
-                                                       const float* __restrict__ bias, float* __restrict__ out, int B,
-                                                       int H, int W, int C, int fmt) {
-  extern __shared__ float sw[];  // [9][C]
-  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) {
-    const int tap = i / C, c = i - tap * C;
-    sw[i] = w[c * 9 + tap];
+// Head C -> 1.  A block owns a 32 x 8 pixel tile: it first stages the 34 x 10 halo of pixel rows in shared memory
+// with 16-byte cp.async copies (21 in flight per thread - the kernel was latency-bound when every warp fetched its own
+// window from global memory, 171 us for 75 MB), then warp r slides the 3x3 window along tile row r out of shared
+// memory: one partial sum per pixel and lane (its NPER channels x 9 taps), and a 31-shuffle butterfly over the run
+// leaves lane l with the total of pixel l.
+constexpr int kHeadTW = 32, kHeadTH = 8;
+template <int NPER>
+__global__ void __launch_bounds__(256, 2) conv_out_kernel(const uint16_t* __restrict__ x, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, float* __restrict__ out,
+                                                       int H, int W, int tiles_w, int fmt) {
+  constexpr int C = 32 * NPER;
+  constexpr int kRow = 2 * C;                    // bytes per pixel
+  constexpr int kHW = kHeadTW + 2, kHH = kHeadTH + 2;
+  constexpr int kChunks = kRow / 16;             // 16-byte chunks per pixel
+  extern __shared__ __align__(16) uint8_t tile[];  // [kHH][kHW][kRow]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  const int ty = blockIdx.x / tiles_w, tx = blockIdx.x - ty * tiles_w;
+  const int x0 = tx * kHeadTW, y0 = ty * kHeadTH;
+  const uint16_t* xb = x + static_cast<size_t>(b) * H * W * C;
+  const uint32_t tile_s = static_cast<uint32_t>(__cvta_generic_to_shared(tile));
+  for (int i = threadIdx.x; i < kHH * kHW * kChunks; i += blockDim.x) {
+    const int px = i / kChunks, ch = i - px * kChunks;
+    const int hy = px / kHW, hx = px - hy * kHW;
+    const int iy = y0 + hy - 1, ix = x0 + hx - 1;
+    const uint32_t dst = tile_s + px * kRow + ch * 16;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+      const uint16_t* src = xb + (static_cast<size_t>(iy) * W + ix) * C + ch * 8;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    } else {
+      asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
+    }
   }
+  float wr[9][NPER];
+#pragma unroll
+  for (int j = 0; j < NPER; ++j)
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) wr[tap][j] = __ldg(w + (lane * NPER + j) * 9 + tap);
+  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
-  // a group of G = min(16, C/8) threads shares one pixel; each thread owns 8-channel vectors v, v+G, ...
-  const int nvec = C >> 3;
-  const int G = nvec < 16 ? nvec : 16;  // power of two for C in {64, 128, 256, ...}
-  const int sub = threadIdx.x % G;
-  const int ppb = blockDim.x / G;
-  const size_t total = static_cast<size_t>(B) * H * W;
-  const size_t rounds = (total + static_cast<size_t>(gridDim.x) * ppb - 1) / (static_cast<size_t>(gridDim.x) * ppb);
-  for (size_t r = 0; r < rounds; ++r) {
-    const size_t pix = (r * gridDim.x + blockIdx.x) * ppb + threadIdx.x / G;
-    const bool live = pix < total;
-    float acc = 0.f;
-    if (live) {
-      const int xw = static_cast<int>(pix % W);
-      const int yh = static_cast<int>((pix / W) % H);
-      const size_t n = pix / (static_cast<size_t>(W) * H);
+
+  // warp `warp` = tile row; window column slot of halo column hx is hx % 3
+  float win[3][3][NPER];
+  auto load_col = [&](int hx) {
 #pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
-        const int iy = yh + tap / 3 - 1, ix = xw + tap % 3 - 1;
-        if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
-        const uint16_t* row = x + ((n * H + iy) * W + ix) * C;
-        for (int v = sub; v < nvec; v += G) {
-          const uint4 u = __ldg(reinterpret_cast<const uint4*>(row + v * 8));
-          float f[8];
-          unpack8(u, fmt, f);
-          const float* wv = &sw[tap * C + v * 8];
+    for (int r = 0; r < 3; ++r) {
+      const uint8_t* src = tile + ((warp + r) * kHW + hx) * kRow + lane * NPER * 2;
+      uint32_t u[NPER / 2];
+      if (NPER == 2) {
+        u[0] = *reinterpret_cast<const uint32_t*>(src);
+      } else if (NPER == 4) {
+        const uint2 t = *reinterpret_cast<const uint2*>(src);
+        u[0] = t.x;
+        u[1 % (NPER / 2)] = t.y;
+      } else {
+        const uint4 t = *reinterpret_cast<const uint4*>(src);
+        u[0] = t.x;
+        u[1 % (NPER / 2)] = t.y;
+        u[2 % (NPER / 2)] = t.z;
+        u[3 % (NPER / 2)] = t.w;
+      }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc = fmaf(f[j], wv[j], acc);
+      for (int c = 0; c < NPER; c += 2) {
+        float2 f;
+        if (fmt == 1) {
+          f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[c / 2]));
+        } else {
+          f = __half22float2(*reinterpret_cast<const __half2*>(&u[c / 2]));
         }
+        win[r][hx % 3][c] = f.x;
+        win[r][hx % 3][c + 1] = f.y;
       }
     }
-    // all 32 lanes take part in the shuffles (dead pixels contribute 0)
-    for (int off = G >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (live && sub == 0) out[pix] = acc + bias[0];
+  };
+  float acc[32];
+  load_col(0);
+  load_col(1);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    load_col(j + 2);
+    float a = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int c = 0; c < NPER; ++c) a = fmaf(win[r][(j + d) % 3][c], wr[r * 3 + d][c], a);
+    acc[j] = a;
   }
+#pragma unroll
+  for (int wd = 16; wd >= 1; wd >>= 1) {
+    const bool hi = (lane & wd) != 0;
+#pragma unroll
+    for (int k = 0; k < wd; ++k) {
+      const float keep = hi ? acc[k + wd] : acc[k];
+      const float send = hi ? acc[k] : acc[k + wd];
+      acc[k] = keep + __shfl_xor_sync(0xffffffffu, send, wd);
+    }
+  }
+  const int oy = y0 + warp, ox = x0 + lane;
+  if (oy < H && ox < W) out[(static_cast<size_t>(b) * H + oy) * W + ox] = acc[0] + __ldg(bias);
 }
 
 __global__ void vec_add_kernel(const float* a, const float* b, float* out, int n) {
@@ -614,30 +740,38 @@ int launch_to16(const float* in, void* out, int n, int fmt, cudaStream_t stream)
   return check_launch("to16_kernel");
 }
 
-int launch_conv_in(const float* x, const float* w, const float* bias, void* out, int B, int H, int W, int Cout,
-                   int fmt, cudaStream_t stream) {
-  if (Cout % 8 != 0 || Cout > 2048) return fail(kUnsupported, "conv_in: Cout must be a multiple of 8");
-  const int ngrp = Cout / 8;
-  const int threads = (256 / ngrp) * ngrp;
-  const int ppb = threads / ngrp;
-  const size_t total = static_cast<size_t>(B) * H * W;
-  int blocks = static_cast<int>((total + ppb - 1) / ppb);
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  conv_in_kernel<<<blocks, threads, (10 * Cout) * sizeof(float), stream>>>(x, w, bias, reinterpret_cast<uint16_t*>(out), B,
-                                                                         H, W, Cout, fmt);
+int launch_conv_in(const float* x, const float* w, const float* bias, void* out, double* stats, int B, int H, int W,
+                   int Cout, int fmt, cudaStream_t stream) {
+  dim3 grid((H * W + 255) / 256, B);
+  uint16_t* o = reinterpret_cast<uint16_t*>(out);
+  switch (Cout) {
+    case 64: conv_in_kernel<2><<<grid, 256, 0, stream>>>(x, w, bias, o, stats, H, W, fmt); break;
+    case 128: conv_in_kernel<4><<<grid, 256, 0, stream>>>(x, w, bias, o, stats, H, W, fmt); break;
+    case 256: conv_in_kernel<8><<<grid, 256, 0, stream>>>(x, w, bias, o, stats, H, W, fmt); break;
+    default: return fail(kUnsupported, "conv_in: model_channels must be 64, 128 or 256");
+  }
   return check_launch("conv_in_kernel");
 }
 
 int launch_conv_out(const void* x, const float* w, const float* bias, float* out, int B, int H, int W, int C,
                     int fmt, cudaStream_t stream) {
-  if (C % 64 != 0) return fail(kUnsupported, "conv_out: C must be a multiple of 64");
-  const size_t total = static_cast<size_t>(B) * H * W;
-  const int G = (C / 8) < 16 ? (C / 8) : 16;
-  const int ppb = 256 / G;
-  int blocks = static_cast<int>((total + ppb - 1) / ppb);
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  conv_out_kernel<<<blocks, 256, 9 * C * sizeof(float), stream>>>(reinterpret_cast<const uint16_t*>(x), w, bias, out, B, H,
-                                                                 W, C, fmt);
+  const int tiles_w = (W + kHeadTW - 1) / kHeadTW, tiles_h = (H + kHeadTH - 1) / kHeadTH;
+  dim3 grid(tiles_w * tiles_h, B);
+  const int smem = (kHeadTW + 2) * (kHeadTH + 2) * 2 * C;
+  const uint16_t* xi = reinterpret_cast<const uint16_t*>(x);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CDDPM_CUDA(cudaFuncSetAttribute(conv_out_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 340 * 128));
+    CDDPM_CUDA(cudaFuncSetAttribute(conv_out_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 340 * 256));
+    CDDPM_CUDA(cudaFuncSetAttribute(conv_out_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 340 * 512));
+    attr_set = true;
+  }
+  switch (C) {
+    case 64: conv_out_kernel<2><<<grid, 256, smem, stream>>>(xi, w, bias, out, H, W, tiles_w, fmt); break;
+    case 128: conv_out_kernel<4><<<grid, 256, smem, stream>>>(xi, w, bias, out, H, W, tiles_w, fmt); break;
+    case 256: conv_out_kernel<8><<<grid, 256, smem, stream>>>(xi, w, bias, out, H, W, tiles_w, fmt); break;
+    default: return fail(kUnsupported, "conv_out: model_channels must be 64, 128 or 256");
+  }
   return check_launch("conv_out_kernel");
 }
 

@@ -67,8 +67,8 @@ int launch_timestep_embedding16(const int64_t* t, float* emb, void* emb16, int f
 int launch_to16(const float* in, void* out, int n, int fmt, cudaStream_t stream);
 
 // Stem: x fp32 [B,1,H,W] -> NHWC 16-bit [B,H,W,Cout], 3x3 pad 1 (OpenAI_Unet.py:609).
-int launch_conv_in(const float* x, const float* w, const float* bias, void* out, int B, int H, int W, int Cout,
-                   int fmt, cudaStream_t stream);
+int launch_conv_in(const float* x, const float* w, const float* bias, void* out, double* stats, int B, int H, int W,
+                   int Cout, int fmt, cudaStream_t stream);
 // Head: NHWC 16-bit [B,H,W,C] -> fp32 [B,1,H,W], 3x3 pad 1, one output channel (OpenAI_Unet.py:796).
 int launch_conv_out(const void* x, const float* w, const float* bias, float* out, int B, int H, int W, int C,
                     int fmt, cudaStream_t stream);

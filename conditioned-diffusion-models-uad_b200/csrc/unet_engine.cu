@@ -715,9 +715,9 @@ int UNetEngine::plan(int B) {
         CDDPM_TRY(act_alloc(&o, mc, H, W, B, true));
         void* op = o.p;
         double* ost = o.stats;
-        ops_.push_back([=](cudaStream_t s) { return launch_conv_in(cur_x_, stem_w, stem_b, op, B, H, W, mc, fmt, s); });
-        // the stem is a direct (non tensor-core) kernel: its GroupNorm statistics take one extra pass
-        if (fused_stats_) ops_.push_back([=](cudaStream_t s) { return launch_gn_stats4(op, mc, B, H * W, ost, fmt, s); });
+        // the stem is a direct (non tensor-core) kernel; it emits its GroupNorm statistics itself
+        ops_.push_back(
+            [=](cudaStream_t s) { return launch_conv_in(cur_x_, stem_w, stem_b, op, ost, B, H, W, mc, fmt, s); });
         taps_["input_blocks.0.0"] = o;
       } else if (l.kind == 1) {
         CDDPM_TRY(plan_res(res_[l.idx], h, nullptr, &o, B));
