@@ -152,8 +152,10 @@ __global__ void __launch_bounds__(256) gn_stats4_kernel(const uint16_t* __restri
 // kPlain: no resampling and no raw copy - the shape of 50 of the 56 launches of a forward; the specialisation keeps
 // the kernel at <= 64 registers, i.e. four resident blocks per SM (the general body needs 102: two blocks, and too few
 // loads in flight to cover HBM latency - measured 3.5 TB/s).
-template <bool kPlain>
-__global__ void __launch_bounds__(256, kPlain ? 4 : 2) gn_apply_kernel(const GnApplyDev a) {
+// kMode 0: plain; 1: nearest x2 upsampling (or a raw copy without resampling); 2: 2x2 average pooling.
+template <int kMode>
+__global__ void __launch_bounds__(256, kMode == 0 ? 4 : 3) gn_apply_kernel(const GnApplyDev a) {
+  constexpr bool kPlain = kMode == 0;
   extern __shared__ float sh[];  // A[C], Bc[C], mean[32], rstd[32]
   const int C = a.c0 + a.c1;
   float* sA = sh;
@@ -230,7 +232,7 @@ __global__ void __launch_bounds__(256, kPlain ? 4 : 2) gn_apply_kernel(const GnA
   for (int op = blockIdx.x * a.Pout + pl; op < p_end; op += lanes) {
     const int oy = op / a.Wo, ox = op - oy * a.Wo;
     float y[8], r[8];
-    if (!kPlain && a.mode == kResampleDown2) {
+    if (kMode == 2) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) y[j] = r[j] = 0.f;
 #pragma unroll
@@ -695,9 +697,11 @@ int launch_gn_apply(const GnApplyArgs& a, cudaStream_t stream) {
   dim3 grid((HWo + d.Pout - 1) / d.Pout, a.B);
   const size_t shmem = (2 * C + 2 * kGnGroups) * sizeof(float);
   if (a.mode == kResampleNone && a.raw_out == nullptr) {
-    gn_apply_kernel<true><<<grid, threads, shmem, stream>>>(d);
+    gn_apply_kernel<0><<<grid, threads, shmem, stream>>>(d);
+  } else if (a.mode == kResampleDown2) {
+    gn_apply_kernel<2><<<grid, threads, shmem, stream>>>(d);
   } else {
-    gn_apply_kernel<false><<<grid, threads, shmem, stream>>>(d);
+    gn_apply_kernel<1><<<grid, threads, shmem, stream>>>(d);
   }
   return check_launch("gn_apply_kernel");
 }

@@ -120,6 +120,15 @@ class UNetEngine {
   int64_t conv_flops_ = 0;
   bool profile_armed_ = false;
   std::vector<cudaEvent_t> profile_events_;
+  // CUDA-graph replay of the planned launch sequence: captured on the second forward of a plan (the first runs
+  // directly and finishes every one-time setup), replayed afterwards.  Inputs and the output go through engine-owned
+  // staging buffers because the graph bakes pointers in.  CDDPM_GRAPH=0 disables it.
+  void drop_graph();
+  cudaStream_t cap_stream_ = nullptr;
+  cudaGraphExec_t graph_exec_ = nullptr;
+  int forwards_on_plan_ = 0;
+  float *stage_x_ = nullptr, *stage_cond_ = nullptr, *stage_out_ = nullptr;
+  int64_t* stage_t_ = nullptr;
 };
 
 }  // namespace cddpm
