@@ -129,3 +129,28 @@ def test_missing_parameter_is_an_error():
     with pytest.raises(CddpmError):
         eng.forward(torch.zeros(1, 1, 32, 32, device="cuda"), torch.zeros(1, dtype=torch.long, device="cuda"),
                     torch.zeros(1, 128, device="cuda"))
+
+
+def test_graph_replay_matches_direct_launches():
+    """The first forward of a plan launches every kernel directly; later ones replay the captured CUDA graph through
+    the engine's staging buffers.  Same kernels, same order: results agree to the order of the GroupNorm atomics."""
+    from oracle import unet_port
+    from oracle.weights import make_state_dict
+
+    spec = unet_port.UNetSpec()
+    sd = make_state_dict(unet_port.param_shapes(spec), seed=3)
+    g = torch.Generator().manual_seed(11)
+    xs = [torch.rand(2, 1, 96, 96, generator=g).cuda() for _ in range(2)]
+    ts = [torch.tensor([499, 17]).cuda(), torch.tensor([3, 250]).cuda()]
+    cs = [torch.randn(2, 128, generator=g).cuda() for _ in range(2)]
+    eng = _engine(spec, 96)
+    _load(eng, sd)
+    direct0 = eng.forward(xs[0], ts[0], cs[0]).clone()  # direct launches
+    graph1 = eng.forward(xs[1], ts[1], cs[1]).clone()   # capture + first replay
+    graph0 = eng.forward(xs[0], ts[0], cs[0]).clone()   # replay with other inputs
+    eng2 = _engine(spec, 96)
+    _load(eng2, sd)
+    direct1 = eng2.forward(xs[1], ts[1], cs[1]).clone()
+    assert (graph0 - direct0).abs().max().item() < 1e-4
+    assert (graph1 - direct1).abs().max().item() < 1e-4
+    assert (graph1 - graph0).abs().max().item() > 1e-3  # the replay really consumed the new inputs
