@@ -69,3 +69,36 @@ def attention(qkv: torch.Tensor, channels: int) -> torch.Tensor:
     check(lib().cddpm_attention(ptr(qkv), ptr(out), B, L, channels, fmt_of(qkv.dtype), current_stream()),
           "cddpm_attention")
     return out
+
+
+def pack_conv_weight_t(weight: torch.Tensor, dtype=torch.bfloat16) -> torch.Tensor:
+    """OIHW fp32 weight -> panel [Cin, k*k*Cout] of the data-gradient convolution (flipped taps, channels exchanged)."""
+    cout, cin, kh, kw = weight.shape
+    out = torch.empty(cin, kh * kw * cout, device=weight.device, dtype=dtype)
+    check(lib().cddpm_pack_conv_weight_t(ptr(weight.contiguous()), cout, cin, kh, 0, cin, ptr(out), kh * kw * cout, 0,
+                                         fmt_of(dtype), current_stream()), "cddpm_pack_conv_weight_t")
+    return out
+
+
+def conv_wgrad(srcs: Sequence[torch.Tensor], taps: Sequence[int], dy: torch.Tensor,
+               skip: Optional[Sequence[int]] = None) -> torch.Tensor:
+    """Packed fp32 weight gradient [Cout, sum_s taps_s*C_s] of out = sum_s conv(srcs[s]) given dy (NHWC 16-bit)."""
+    B, H, W, cout = dy.shape
+    ktot = sum(t * s.shape[3] for t, s in zip(taps, srcs))
+    dw = torch.zeros(cout, ktot, device=dy.device, dtype=torch.float32)
+    check(lib().cddpm_conv_wgrad(len(srcs), ptr_array([ptr(s) for s in srcs]), int_array([s.shape[3] for s in srcs]),
+                                 int_array(list(taps)), int_array(list(skip) if skip else [0] * len(srcs)), ptr(dy),
+                                 B, H, W, cout, ptr(dw), fmt_of(dy.dtype), current_stream()), "cddpm_conv_wgrad")
+    return dw
+
+
+def unpack_conv_grad(dw: torch.Tensor, cout: int, cin: int, ksize: int, splits: Sequence[int]) -> torch.Tensor:
+    """Packed gradient [Cout, Ktot] -> OIHW fp32 (inverse of pack_conv_weight)."""
+    g = torch.zeros(cout, cin, ksize, ksize, device=dw.device, dtype=torch.float32)
+    cin_off = koff = 0
+    for c_s in splits:
+        check(lib().cddpm_unpack_conv_grad(ptr(dw), cout, cin, ksize, cin_off, c_s, ptr(g), dw.shape[1], koff,
+                                           current_stream()), "cddpm_unpack_conv_grad")
+        cin_off += c_s
+        koff += c_s * ksize * ksize
+    return g

@@ -3,6 +3,7 @@
 
 #include "common.h"
 #include "attention.cuh"
+#include "conv_bwd.cuh"
 #include "conv_igemm.cuh"
 #include "diffusion.cuh"
 #include "elementwise.cuh"
@@ -67,6 +68,47 @@ int cddpm_conv_igemm(int num_src, const void* const* src, const int* src_c, cons
   ConvIgemmParams p;
   CDDPM_TRY(build_conv_params(d, &p));
   return launch_conv_igemm(p, static_cast<cudaStream_t>(stream));
+}
+
+int cddpm_pack_conv_weight_t(const float* w_oihw, int cout, int cin_total, int ksize, int cin_off, int c_s,
+                             void* wpacked_t, int ktot, int koff, int fmt, void* stream) {
+  if (!w_oihw || !wpacked_t) return fail(kInvalidArgument, "pack_conv_weight_t: null pointer");
+  if (ksize != 1 && ksize != 3) return fail(kInvalidArgument, "pack_conv_weight_t: ksize must be 1 or 3");
+  if (cin_off < 0 || cin_off + c_s > cin_total || koff < 0 || koff + ksize * ksize * cout > ktot)
+    return fail(kInvalidArgument, "pack_conv_weight_t: slice out of range");
+  return launch_pack_conv_weight_T(w_oihw, cout, cin_total, ksize, cin_off, c_s, wpacked_t, ktot, koff, fmt,
+                                   static_cast<cudaStream_t>(stream));
+}
+
+int cddpm_conv_wgrad(int num_src, const void* const* src, const int* src_c, const int* src_taps, const int* skip,
+                     const void* dy, int B, int H, int W, int cout, float* dw, int fmt, void* stream) {
+  if (!src || !src_c || !src_taps || !dy || !dw) return fail(kInvalidArgument, "conv_wgrad: null pointer");
+  if (num_src < 1 || num_src > kConvMaxSrc) return fail(kInvalidArgument, "conv_wgrad: num_src must be 1..3");
+  WgradDesc d;
+  d.num_src = num_src;
+  for (int s = 0; s < num_src; ++s) {
+    d.src[s] = src[s];
+    d.src_c[s] = src_c[s];
+    d.src_taps[s] = src_taps[s];
+    d.src_skip[s] = skip ? skip[s] : 0;
+  }
+  d.dy = dy;
+  d.B = B;
+  d.H = H;
+  d.W = W;
+  d.Cout = cout;
+  d.dw = dw;
+  d.ab_format = fmt;
+  std::shared_ptr<void> holder;
+  CDDPM_TRY(build_wgrad(d, &holder));
+  return launch_wgrad(holder, static_cast<cudaStream_t>(stream));
+}
+
+int cddpm_unpack_conv_grad(const float* dw_packed, int cout, int cin_total, int ksize, int cin_off, int c_s,
+                           float* grad_oihw, int ktot, int koff, void* stream) {
+  if (!dw_packed || !grad_oihw) return fail(kInvalidArgument, "unpack_conv_grad: null pointer");
+  return launch_unpack_conv_grad(dw_packed, cout, cin_total, ksize, cin_off, c_s, grad_oihw, ktot, koff,
+                                 static_cast<cudaStream_t>(stream));
 }
 
 int64_t cddpm_gn_workspace_floats(int B, int HW) {

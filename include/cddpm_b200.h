@@ -54,6 +54,21 @@ int cddpm_conv_igemm(int num_src, const void* const* src, const int* src_c, cons
                      int W, int cout, const void* wpacked, const float* bias, const void* residual, void* out,
                      int out_f32, int fmt, void* stream);
 
+/* Backward of the convolutions (training step: DDPM_2D.py:114-138 -> loss.backward(), torch autograd of nn.Conv2d).
+ * Data gradient = the forward kernel over the transposed / flipped panel built here:
+ *   wpacked_t[ci - cin_off][koff + tap' * cout + co] = w[co][ci][k*k - 1 - tap']. */
+int cddpm_pack_conv_weight_t(const float* w_oihw, int cout, int cin_total, int ksize, int cin_off, int c_s,
+                             void* wpacked_t, int ktot, int koff, int fmt, void* stream);
+/* Weight gradient (tcgen05, both operands MN-major straight from NHWC): for every source s with skip[s] == 0
+ *   dw[co][koff_s + tap * c_s + ci] += sum_{n,y,x} dy[n,y,x,co] * src_s[n, y + dy(tap), x + dx(tap), ci]
+ * dw is [cout][sum_s taps_s * c_s] fp32 in the K order of the packed forward panel; the caller zeroes it.
+ * cout and every src_c multiples of 128; H, W multiples of 8. */
+int cddpm_conv_wgrad(int num_src, const void* const* src, const int* src_c, const int* src_taps, const int* skip,
+                     const void* dy, int B, int H, int W, int cout, float* dw, int fmt, void* stream);
+/* grad_oihw[co][cin_off + ci][tap] = dw_packed[co][koff + tap * c_s + ci] (inverse of cddpm_pack_conv_weight). */
+int cddpm_unpack_conv_grad(const float* dw_packed, int cout, int cin_total, int ksize, int cin_off, int c_s,
+                           float* grad_oihw, int ktot, int koff, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Bandwidth-bound UNet pieces, exposed one by one for the parity tests.
  * ---------------------------------------------------------------------------------------------------------- */
