@@ -74,6 +74,13 @@ def _signatures(c):
         "cddpm_unet_launches": (i32, [vp]),
         "cddpm_unet_profile_arm": (i32, [vp]),
         "cddpm_unet_profile_read": (i32, [vp, c.POINTER(c.c_double), pi32]),
+        "cddpm_unet_grad_total": (i64, [vp]),
+        "cddpm_unet_grad_offset": (i32, [vp, i32, c.POINTER(i64)]),
+        "cddpm_unet_backward": (i32, [vp, vp, vp, vp, i32, vp]),
+        "cddpm_unet_bwd_flops": (i64, [vp]),
+        "cddpm_unet_bwd_launches": (i32, [vp]),
+        "cddpm_attention_bwd_scratch_bytes": (i64, [i32, i32, i32]),
+        "cddpm_attention_bwd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
         "cddpm_encoder_create": (i32, [i32, i32, i32, i32, pvp]),
         "cddpm_encoder_destroy": (None, [vp]),
         "cddpm_encoder_param_count": (i32, [vp]),

@@ -106,7 +106,7 @@ class DDPM_2D(LightningModule):
     def forward(self, x):
         return self.encoder(x) if self.cfg.get("condition", True) else None
 
-    # ------------------------------------------------------------------ train / val (forward-only this round)
+    # ------------------------------------------------------------------ train / val
     def _loss_step(self, batch):
         input = batch["vol"][DATA].squeeze(-1)
         features = self(input)
@@ -115,8 +115,12 @@ class DDPM_2D(LightningModule):
         return loss, input.shape[0]
 
     def training_step(self, batch, batch_idx: int):
-        raise NotImplementedError("the training step needs the backward kernels of the CUDA engine, which are not "
-                                  "part of this build (SURVEY.md §8 a-14); evaluation paths are complete")
+        """DDPM_2D.py:114-138.  The returned loss carries the autograd tape: loss.backward() (Lightning's automatic
+        optimisation) runs the UNet engine's backward kernels and, for the condition encoder, torch autograd."""
+        loss, n = self._loss_step(batch)
+        self.log(f"{self.prefix}train/Loss", loss, prog_bar=False, on_step=False, on_epoch=True, batch_size=n,
+                 sync_dist=True)
+        return {"loss": loss}
 
     def validation_step(self, batch: Any, batch_idx: int):
         with torch.no_grad():

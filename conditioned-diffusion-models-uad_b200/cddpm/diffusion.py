@@ -145,6 +145,21 @@ class GaussianDiffusion(nn.Module):
         model_out = self.model(x_t, t, cond=cond)
         nz, f16 = _noise_arg(noise)
         reco = _reco_out if _reco_out is not None else torch.empty_like(x_t)
+        if model_out.requires_grad:
+            # training step (cond_DDPM.py:606-645): the loss stays on the autograd tape that ends in the UNet node;
+            # [B,1,H,W] elementwise work, the reconstruction itself comes from the fused kernel without a loss
+            target = noise.float() if self.objective == "pred_noise" else img * 2 - 1
+            diff = model_out - target
+            per = (diff * diff if self.loss_type == "l2" else diff.abs()).flatten(1).mean(1)
+            loss = (per * self.p2_loss_weight.gather(-1, t)).mean()
+            with torch.no_grad():
+                check(lib().cddpm_recon_finish(ptr(model_out.detach()), ptr(img), ptr(x_t), ptr(nz), f16, ptr(reco),
+                                               float(_reco_alpha), float(_reco_beta), None,
+                                               ptr(self.sqrt_one_minus_alphas_cumprod), ptr(self.p2_loss_weight),
+                                               ptr(t), 0, B, hw, 1 if self.objective == "pred_noise" else 0,
+                                               1 if self.loss_type == "l2" else 0, current_stream()),
+                      "cddpm_recon_finish")
+            return loss, reco
         loss = torch.empty(B, dtype=torch.float32, device=x_t.device)
         check(lib().cddpm_recon_finish(ptr(model_out), ptr(img), ptr(x_t), ptr(nz), f16, ptr(reco),
                                        float(_reco_alpha), float(_reco_beta), ptr(loss),

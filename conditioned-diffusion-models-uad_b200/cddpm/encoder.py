@@ -128,11 +128,10 @@ class ResNet(nn.Module):
     def forward(self, x, pyramid=0):
         if pyramid != 0:
             raise NotImplementedError("pyramid features are only used by SparK pre-training (out of scope)")
-        if self.training and torch.is_grad_enabled():
-            raise NotImplementedError("training-mode BatchNorm / DropPath (the training step) is not part of this "
-                                      "build; call .eval() and run under torch.no_grad()")
         if not x.is_cuda:
             raise CddpmError("encoder forward needs CUDA tensors (there is no CPU path)")
+        if self.training and torch.is_grad_enabled():
+            return self._train_forward(x)
         self._sync()
         x = x.float().contiguous()
         B = x.shape[0]
@@ -141,6 +140,33 @@ class ResNet(nn.Module):
         out = torch.empty(B, self.num_classes, dtype=torch.float32, device=x.device)
         check(lib().cddpm_encoder_forward(self._h, ptr(x), ptr(out), B, current_stream()), "cddpm_encoder_forward")
         return out
+
+
+    def _train_forward(self, x):
+        """Training-mode forward WITH an autograd tape (batch-statistics BatchNorm, running-stat updates): ~1 % of the
+        training step's FLOPs, evaluated with torch's library kernels (cuDNN convolutions under bf16 autocast) — the
+        hand-written engine covers the eval-mode forward only (DESIGN.md §8 lists the encoder backward under "next").
+        timm's DropPath(0.05) is not applied (timm is not available to pin it; the oracle stand-in has none either)."""
+        import torch.nn.functional as F
+
+        def bn(m, t):
+            return F.batch_norm(t, m.running_mean, m.running_var, m.weight, m.bias, True, m.momentum, m.eps)
+
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            h = F.relu(bn(self.bn1, F.conv2d(x.float(), self.conv1.weight, None, 2, 3)))
+            h = F.max_pool2d(h, 3, 2, 1)
+            for li in range(1, 5):
+                for blk in getattr(self, f"layer{li}"):
+                    idt = h
+                    o = F.relu(bn(blk.bn1, F.conv2d(h, blk.conv1.weight)))
+                    o = F.relu(bn(blk.bn2, F.conv2d(o, blk.conv2.weight, None, blk.conv2.stride, 1)))
+                    o = bn(blk.bn3, F.conv2d(o, blk.conv3.weight))
+                    if blk.downsample is not None:
+                        idt = bn(blk.downsample[1], F.conv2d(h, blk.downsample[0].weight, None, blk.downsample[0].stride))
+                    h = F.relu(o + idt)
+            h = h.mean((2, 3))
+            out = F.linear(h, self.fc.weight, self.fc.bias)
+        return out.float()
 
 
 class SparK_2D_encoder(nn.Module):

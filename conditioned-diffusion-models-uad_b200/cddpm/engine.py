@@ -93,7 +93,42 @@ class UNetEngine:
             out = torch.empty_like(x)
         check(lib().cddpm_unet_forward(self._h, ptr(x), ptr(t), ptr(cond), ptr(out), B, current_stream()),
               "cddpm_unet_forward")
+        self.forward_serial = getattr(self, "forward_serial", 0) + 1
         return out
+
+    # ------------------------------------------------------------------ backward (training step)
+    def grad_layout(self) -> Tuple[int, List[int]]:
+        """(floats in the flat gradient buffer, offset of every parameter in param_names() order)."""
+        if getattr(self, "_grad_layout", None) is None:
+            total = int(lib().cddpm_unet_grad_total(self._h))
+            offs = []
+            off = ctypes.c_int64()
+            for i in range(lib().cddpm_unet_param_count(self._h)):
+                check(lib().cddpm_unet_grad_offset(self._h, i, ctypes.byref(off)), "cddpm_unet_grad_offset")
+                offs.append(int(off.value))
+            self._grad_layout = (total, offs)
+        return self._grad_layout
+
+    def backward(self, dout: torch.Tensor, want_dcond: bool = False):
+        """Backward of the LAST forward: dout = dL/d out [B,1,H,W].  Returns (flat fp32 gradient buffer, dcond)."""
+        if not dout.is_cuda:
+            raise CddpmError("UNet backward needs CUDA tensors (there is no CPU path)")
+        if self.dtype != torch.bfloat16:
+            raise CddpmError("the training step runs on a bf16 engine")
+        B = dout.shape[0]
+        dout = dout.float().contiguous()
+        total, _ = self.grad_layout()
+        grads = torch.empty(total, dtype=torch.float32, device=dout.device)
+        dcond = None
+        if want_dcond and self.num_classes:
+            dcond = torch.empty(B, self.num_classes, dtype=torch.float32, device=dout.device)
+        check(lib().cddpm_unet_backward(self._h, ptr(dout), ptr(grads), ptr(dcond), B, current_stream()),
+              "cddpm_unet_backward")
+        return grads, dcond
+
+    @property
+    def bwd_flops_per_sample(self) -> int:
+        return int(lib().cddpm_unet_bwd_flops(self._h))
 
     # ------------------------------------------------------------------ introspection (parity tests, bench)
     def tap(self, layer: str, batch: int) -> torch.Tensor:

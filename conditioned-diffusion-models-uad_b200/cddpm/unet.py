@@ -207,6 +207,8 @@ class UNetModel(nn.Module):
 
         self._engine: Optional[UNetEngine] = None
         self._engine_versions = None
+        self._train_engine: Optional[UNetEngine] = None
+        self._train_versions = None
         self._items = None
 
     # ------------------------------------------------------------------ reference API
@@ -229,6 +231,7 @@ class UNetModel(nn.Module):
         # .to()/.cuda()/.float() may re-seat parameter storage: drop the cached view and re-push everything
         self._items = None
         self._engine_versions = None if self._engine is None else [None] * len(self._engine_versions)
+        self._train_versions = None if self._train_engine is None else [None] * len(self._train_versions)
         return super()._apply(fn, *args, **kwargs)
 
     def engine(self) -> UNetEngine:
@@ -254,12 +257,70 @@ class UNetModel(nn.Module):
                 self._engine_versions[i] = v
         return self._engine
 
+    def train_engine(self) -> UNetEngine:
+        """The bf16 engine the training step runs on (forward + backward kernels); shares nothing with the inference
+        engine when that one is fp16.  Parameters are re-pushed when the optimizer changed them."""
+        if self.engine_dtype == torch.bfloat16:
+            return self.engine()
+        items = self._param_items()
+        if items[0][1].device.type != "cuda":
+            raise CddpmError("UNetModel is on the CPU; the cDDPM engine has no CPU path — move the module to CUDA")
+        if self._train_engine is None:
+            self._train_engine = UNetEngine(
+                image_size=self.image_size, in_channels=self.in_channels, model_channels=self.model_channels,
+                out_channels=self.out_channels, num_res_blocks=self.num_res_blocks,
+                attention_resolutions=self.attention_resolutions, channel_mult=self.channel_mult,
+                num_classes=self.num_classes, num_head_channels=self.num_head_channels, dtype=torch.bfloat16)
+            self._train_versions = [None] * len(items)
+        for i, (name, p) in enumerate(items):
+            v = (p.data_ptr(), p._version)
+            if self._train_versions[i] != v:
+                self._train_engine.set_param(name, p)
+                self._train_versions[i] = v
+        return self._train_engine
+
     def forward(self, x, timesteps, cond=None, context=None):
-        """model(x, t, cond): x [B,1,H,W], timesteps [B], cond [B,num_classes] -> [B,1,H,W] fp32."""
+        """model(x, t, cond): x [B,1,H,W], timesteps [B], cond [B,num_classes] -> [B,1,H,W] fp32.
+        In train() mode with autograd enabled and parameters that require gradients, the call is recorded as one autograd node whose
+        backward runs the engine's backward kernels (DDPM_2D.training_step -> loss.backward())."""
         self.features_info.clear()
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
-            raise NotImplementedError("the backward pass of the CUDA UNet engine is not part of this build; "
-                                      "run inference under torch.no_grad() / model.eval()")
         if self.num_classes is None:
             cond = None
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            params = [p for _, p in self._param_items()]
+            return _UNetTrainFunction.apply(self, x, timesteps, cond, *params)
         return self.engine().forward(x, timesteps, cond)
+
+
+class _UNetTrainFunction(torch.autograd.Function):
+    """UNetModel.forward as ONE autograd node: forward = cddpm_unet_forward on the bf16 engine (which keeps every
+    layer output), backward = cddpm_unet_backward.  Parameter gradients come back as views of one flat fp32 buffer in
+    the reference's parameter layouts; d cond flows on to the condition encoder."""
+
+    @staticmethod
+    def forward(ctx, module, x, t, cond, *params):
+        eng = module.train_engine()
+        x = x.detach().float().contiguous()
+        t = t.to(device=x.device, dtype=torch.int64).contiguous()
+        c = cond.detach().float().contiguous() if cond is not None else None
+        out = eng.forward(x, t, c)
+        ctx.engine = eng
+        ctx.serial = eng.forward_serial
+        ctx.shapes = [tuple(p.shape) for p in params]
+        ctx.numels = [p.numel() for p in params]
+        ctx.needs = [p.requires_grad for p in params]
+        ctx.want_dcond = cond is not None and cond.requires_grad
+        ctx.save_for_backward(x, t, *([c] if c is not None else []))  # the engine reads them again in backward
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        eng = ctx.engine
+        if eng.forward_serial != ctx.serial:
+            raise CddpmError("the UNet engine keeps the activations of its LAST forward only: call backward() before "
+                             "running the model again")
+        flat, dcond = eng.backward(dout, want_dcond=ctx.want_dcond)
+        _, offs = eng.grad_layout()
+        grads = [flat[o:o + n].view(s) if need else None
+                 for o, n, s, need in zip(offs, ctx.numels, ctx.shapes, ctx.needs)]
+        return (None, None, None, dcond, *grads)

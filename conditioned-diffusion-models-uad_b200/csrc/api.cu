@@ -319,4 +319,21 @@ int cddpm_unet_profile_read(cddpm_unet_t* h, double* conv_ms, int* conv_launches
   return h->engine.profile_read(conv_ms, conv_launches);
 }
 
+int64_t cddpm_unet_grad_total(const cddpm_unet_t* h) { return h ? h->engine.grad_total() : 0; }
+int cddpm_unet_grad_offset(const cddpm_unet_t* h, int index, int64_t* offset) {
+  if (!h || !offset) return fail(kInvalidArgument, "unet_grad_offset: null pointer");
+  return h->engine.grad_offset(index, offset);
+}
+int cddpm_unet_backward(cddpm_unet_t* h, const float* dout, float* grads, float* dcond, int B, void* stream) {
+  if (!h) return fail(kInvalidArgument, "unet_backward: null handle");
+  return h->engine.backward(dout, grads, dcond, B, static_cast<cudaStream_t>(stream));
+}
+int64_t cddpm_unet_bwd_flops(const cddpm_unet_t* h) { return h ? h->engine.bwd_flops_per_sample() : 0; }
+int cddpm_unet_bwd_launches(const cddpm_unet_t* h) { return h ? h->engine.bwd_launches() : 0; }
+int64_t cddpm_attention_bwd_scratch_bytes(int B, int L, int C) { return attention_bwd_scratch_elems(B, L, C) * 2; }
+int cddpm_attention_bwd(const void* qkv, const void* dout, void* dqkv, void* scratch, int B, int L, int C, int fmt,
+                        void* stream) {
+  return launch_attention_bwd(qkv, dout, dqkv, scratch, B, L, C, fmt, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -10,3 +10,11 @@ namespace cddpm {
 int launch_attention(const void* qkv, void* out, int B, int L, int C, int fmt, cudaStream_t stream);
 
 }  // namespace cddpm
+
+namespace cddpm {
+// Backward of launch_attention (bf16 only): dqkv [B, L, 3*C] from dout [B, L, C] and the forward's qkv.
+// scratch: attention_bwd_scratch_elems(B, L, C) 16-bit elements (probabilities and score gradients).
+int64_t attention_bwd_scratch_elems(int B, int L, int C);
+int launch_attention_bwd(const void* qkv, const void* dout, void* dqkv, void* scratch, int B, int L, int C, int fmt,
+                         cudaStream_t stream);
+}  // namespace cddpm

@@ -1,0 +1,726 @@
+// Bandwidth-bound kernels of the UNet backward pass (see backward.cuh).  Same conventions as elementwise.cu:
+// 16-byte vector accesses along the channel dimension, fp32 math, one rounding to the 16-bit type on store.
+#include "backward.cuh"
+
+#include <cuda_fp16.h>
+
+namespace cddpm {
+
+namespace {
+
+__device__ __forceinline__ void unpack8(const uint4& u, int fmt, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float2 t;
+    if (fmt == 1) {
+      t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+    } else {
+      t = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
+    }
+    f[2 * e] = t.x;
+    f[2 * e + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b, int fmt) {
+  if (fmt == 1) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+  __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8], int fmt) {
+  uint4 o;
+  o.x = pack2(f[0], f[1], fmt);
+  o.y = pack2(f[2], f[3], fmt);
+  o.z = pack2(f[4], f[5], fmt);
+  o.w = pack2(f[6], f[7], fmt);
+  return o;
+}
+__device__ __forceinline__ float sigmoid_f(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return fmaf(0.5f, t, 0.5f);
+}
+// d/dz (z * sigmoid(z))
+__device__ __forceinline__ float silu_grad(float z) {
+  const float s = sigmoid_f(z);
+  return s * fmaf(z, 1.0f - s, 1.0f);
+}
+__device__ __forceinline__ float silu_precise(float z) { return z / (1.0f + __expf(-z)); }
+__device__ __forceinline__ float silu_grad_precise(float z) {
+  const float s = 1.0f / (1.0f + __expf(-z));
+  return s * (1.0f + z * (1.0f - s));
+}
+
+struct GnBwdDev {
+  const uint16_t* p0;
+  const uint16_t* p1;
+  int c0, c1;
+  int B, HW;
+  const double* stats0;
+  const double* stats1;
+  const float* gamma;
+  const float* beta;
+  const float* film;
+  int film_stride, film_off;
+  int silu;
+  const uint16_t* dy;
+  const uint16_t* add0;
+  const uint16_t* add1;
+  float* sums;
+  uint16_t* out0;
+  uint16_t* out1;
+  float* bsum0;
+  float* bsum1;
+  float* dgamma;
+  float* dbeta;
+  float* dfilm;
+  int fmt;
+  int P;  // pixels per block
+};
+
+// Shared prologue: per-channel affine of the forward (z = A x + Bc), mean and rstd of the channel's group.
+// sh layout: A[C], Bc[C], Mean[C], Rstd[C]
+__device__ __forceinline__ void gn_bwd_prologue(const GnBwdDev& a, int b, float* sh, float* sGm, float* sGr) {
+  const int C = a.c0 + a.c1;
+  const int cpg = C / kGnGroups;
+  if (threadIdx.x < kGnGroups) {
+    double s = 0.0, q = 0.0;
+    const int nb0 = a.c0 >> 2;
+    for (int j = threadIdx.x * (cpg >> 2); j < (threadIdx.x + 1) * (cpg >> 2); ++j) {
+      const double* sp = (j < nb0) ? a.stats0 + (static_cast<size_t>(b) * nb0 + j) * 2
+                                   : a.stats1 + (static_cast<size_t>(b) * (a.c1 >> 2) + (j - nb0)) * 2;
+      s += sp[0];
+      q += sp[1];
+    }
+    const double n = static_cast<double>(a.HW) * cpg;
+    const double mean = s / n;
+    double var = q / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    sGm[threadIdx.x] = static_cast<float>(mean);
+    sGr[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + 1e-5));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    float A = sGr[g] * a.gamma[c];
+    float Bc = a.beta[c] - sGm[g] * A;
+    if (a.film != nullptr) {
+      const float* f = a.film + static_cast<size_t>(b) * a.film_stride + a.film_off;
+      const float sc = 1.0f + f[c];
+      A *= sc;
+      Bc = Bc * sc + f[C + c];
+    }
+    sh[c] = A;
+    sh[C + c] = Bc;
+    sh[2 * C + c] = sGm[g];
+    sh[3 * C + c] = sGr[g];
+  }
+  __syncthreads();
+}
+
+// sums[b][c] = (sum_p g, sum_p g * xhat), g = dy * act'(z)
+__global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const GnBwdDev a) {
+  extern __shared__ float sh[];
+  __shared__ float sGm[kGnGroups], sGr[kGnGroups];
+  const int C = a.c0 + a.c1;
+  const int b = blockIdx.y;
+  gn_bwd_prologue(a, b, sh, sGm, sGr);
+  const int nvec = C >> 3;
+  const int lanes = blockDim.x / nvec;
+  const int v = threadIdx.x % nvec;
+  const int pl = threadIdx.x / nvec;
+  const int cb = v << 3;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  if (pl < lanes) {
+    const uint16_t* src;
+    int cs, cbs;
+    if (cb < a.c0) {
+      src = a.p0; cs = a.c0; cbs = cb;
+    } else {
+      src = a.p1; cs = a.c1; cbs = cb - a.c0;
+    }
+    float A[8], Bc[8], Mn[8], Rs[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      A[j] = sh[cb + j];
+      Bc[j] = sh[C + cb + j];
+      Mn[j] = sh[2 * C + cb + j];
+      Rs[j] = sh[3 * C + cb + j];
+    }
+    const size_t base = static_cast<size_t>(b) * a.HW;
+    const int p_end = min((static_cast<int>(blockIdx.x) + 1) * a.P, a.HW);
+    for (int p = blockIdx.x * a.P + pl; p < p_end; p += 2 * lanes) {
+      uint4 ux[2], ud[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int pk = p + k * lanes;
+        if (pk < p_end) {
+          ux[k] = __ldg(reinterpret_cast<const uint4*>(src + (base + pk) * cs + cbs));
+          ud[k] = __ldg(reinterpret_cast<const uint4*>(a.dy + (base + pk) * C + cb));
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        if (p + k * lanes < p_end) {
+          float x[8], d[8];
+          unpack8(ux[k], a.fmt, x);
+          unpack8(ud[k], a.fmt, d);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float g = d[j];
+            if (a.silu) g *= silu_grad(fmaf(x[j], A[j], Bc[j]));
+            s1[j] += g;
+            s2[j] = fmaf(g, (x[j] - Mn[j]) * Rs[j], s2[j]);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();  // the prologue's coefficients are dead: reuse the buffer for the block reduction
+  float* red = sh;  // [lanes][C][2]
+  if (pl < lanes) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      red[(pl * C + cb + j) * 2] = s1[j];
+      red[(pl * C + cb + j) * 2 + 1] = s2[j];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    float t = 0.f;
+    for (int l = 0; l < lanes; ++l) t += red[l * 2 * C + i];
+    atomicAdd(&a.sums[static_cast<size_t>(b) * 2 * C + i], t);
+  }
+}
+
+// dx = rstd * (gamma' g - (P1 + xhat P2) / N) + add0 + add1
+__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdDev a) {
+  extern __shared__ float sh[];  // A, Bc, Mean, Rstd, K1, K2 (per channel), later the column-sum scratch
+  __shared__ float sGm[kGnGroups], sGr[kGnGroups], sP1[kGnGroups], sP2[kGnGroups];
+  const int C = a.c0 + a.c1;
+  const int cpg = C / kGnGroups;
+  const int b = blockIdx.y;
+  gn_bwd_prologue(a, b, sh, sGm, sGr);
+  const float* S = a.sums + static_cast<size_t>(b) * 2 * C;
+  if (threadIdx.x < kGnGroups) {
+    // group sums of gamma' * (S1, S2), gamma' = A / rstd
+    float p1 = 0.f, p2 = 0.f;
+    for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c) {
+      float gm = a.gamma[c];
+      if (a.film != nullptr) gm *= 1.0f + a.film[static_cast<size_t>(b) * a.film_stride + a.film_off + c];
+      p1 = fmaf(gm, S[2 * c], p1);
+      p2 = fmaf(gm, S[2 * c + 1], p2);
+    }
+    const float inv_n = 1.0f / (static_cast<float>(a.HW) * cpg);
+    sP1[threadIdx.x] = sGr[threadIdx.x] * p1 * inv_n;
+    sP2[threadIdx.x] = sGr[threadIdx.x] * p2 * inv_n;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    sh[4 * C + c] = sP1[g];
+    sh[5 * C + c] = sP2[g];
+    if (blockIdx.x == 0) {
+      // parameter gradients: one block per image owns them
+      const float s1 = S[2 * c], s2 = S[2 * c + 1];
+      float sc = 1.0f;
+      if (a.film != nullptr) {
+        sc = 1.0f + a.film[static_cast<size_t>(b) * a.film_stride + a.film_off + c];
+        if (a.dfilm != nullptr) {
+          float* df = a.dfilm + static_cast<size_t>(b) * a.film_stride + a.film_off;
+          df[c] = fmaf(a.gamma[c], s2, a.beta[c] * s1);  // d scale = sum g * (gamma xhat + beta)
+          df[C + c] = s1;                                 // d shift
+        }
+      }
+      atomicAdd(&a.dgamma[c], sc * s2);
+      atomicAdd(&a.dbeta[c], sc * s1);
+    }
+  }
+  __syncthreads();
+
+  const int nvec = C >> 3;
+  const int lanes = blockDim.x / nvec;
+  const int v = threadIdx.x % nvec;
+  const int pl = threadIdx.x / nvec;
+  const int cb = v << 3;
+  float bs[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bs[j] = 0.f;
+  const bool first = cb < a.c0;
+  if (pl < lanes) {
+    const uint16_t* src = first ? a.p0 : a.p1;
+    const int cs = first ? a.c0 : a.c1;
+    const int cbs = first ? cb : cb - a.c0;
+    uint16_t* dst = first ? a.out0 : a.out1;
+    float A[8], Bc[8], Mn[8], Rs[8], K1[8], K2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      A[j] = sh[cb + j];
+      Bc[j] = sh[C + cb + j];
+      Mn[j] = sh[2 * C + cb + j];
+      Rs[j] = sh[3 * C + cb + j];
+      K1[j] = sh[4 * C + cb + j];
+      K2[j] = sh[5 * C + cb + j];
+    }
+    const size_t base = static_cast<size_t>(b) * a.HW;
+    const int p_end = min((static_cast<int>(blockIdx.x) + 1) * a.P, a.HW);
+    for (int p = blockIdx.x * a.P + pl; p < p_end; p += 2 * lanes) {
+      uint4 ux[2], ud[2], u0[2], u1[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int pk = p + k * lanes;
+        if (pk < p_end) {
+          ux[k] = __ldg(reinterpret_cast<const uint4*>(src + (base + pk) * cs + cbs));
+          ud[k] = __ldg(reinterpret_cast<const uint4*>(a.dy + (base + pk) * C + cb));
+          if (a.add0 != nullptr) u0[k] = __ldg(reinterpret_cast<const uint4*>(a.add0 + (base + pk) * C + cb));
+          if (a.add1 != nullptr) u1[k] = __ldg(reinterpret_cast<const uint4*>(a.add1 + (base + pk) * C + cb));
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int pk = p + k * lanes;
+        if (pk < p_end) {
+          float x[8], d[8], o[8];
+          unpack8(ux[k], a.fmt, x);
+          unpack8(ud[k], a.fmt, d);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float g = d[j];
+            if (a.silu) g *= silu_grad(fmaf(x[j], A[j], Bc[j]));
+            const float xh = (x[j] - Mn[j]) * Rs[j];
+            o[j] = fmaf(g, A[j], -K1[j]) - xh * K2[j];
+          }
+          if (a.add0 != nullptr) {
+            float t[8];
+            unpack8(u0[k], a.fmt, t);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] += t[j];
+          }
+          if (a.add1 != nullptr) {
+            float t[8];
+            unpack8(u1[k], a.fmt, t);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] += t[j];
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bs[j] += o[j];
+          *reinterpret_cast<uint4*>(dst + (base + pk) * cs + cbs) = pack8(o, a.fmt);
+        }
+      }
+    }
+  }
+  if (a.bsum0 == nullptr && a.bsum1 == nullptr) return;
+  __syncthreads();
+  float* red = sh;  // [lanes][C]
+  if (pl < lanes) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[pl * C + cb + j] = bs[j];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float t = 0.f;
+    for (int l = 0; l < lanes; ++l) t += red[l * C + c];
+    if (c < a.c0) {
+      if (a.bsum0 != nullptr) atomicAdd(&a.bsum0[c], t);
+    } else {
+      if (a.bsum1 != nullptr) atomicAdd(&a.bsum1[c - a.c0], t);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) resample_bwd_kernel(const uint16_t* __restrict__ dy, uint16_t* __restrict__ dx,
+                                                           int B, int H, int W, int C, int mode, int fmt) {
+  const int nvec = C >> 3;
+  const size_t total = static_cast<size_t>(B) * H * W * nvec;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % nvec);
+    size_t r = i / nvec;
+    const int x = static_cast<int>(r % W);
+    r /= W;
+    const int y = static_cast<int>(r % H);
+    const int b = static_cast<int>(r / H);
+    float o[8];
+    if (mode == kResampleUp2) {
+      const int Ho = 2 * H, Wo = 2 * W;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = 0.f;
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        const int oy = 2 * y + (d >> 1), ox = 2 * x + (d & 1);
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(dy + ((static_cast<size_t>(b) * Ho + oy) * Wo + ox) * C + v * 8));
+        float f[8];
+        unpack8(u, fmt, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += f[j];
+      }
+    } else {
+      const int Ho = H / 2, Wo = W / 2;
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(dy + ((static_cast<size_t>(b) * Ho + (y >> 1)) * Wo + (x >> 1)) * C + v * 8));
+      unpack8(u, fmt, o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] *= 0.25f;
+    }
+    *reinterpret_cast<uint4*>(dx + ((static_cast<size_t>(b) * H + y) * W + x) * C + v * 8) = pack8(o, fmt);
+  }
+}
+
+__global__ void __launch_bounds__(256) col_sum_kernel(const uint16_t* __restrict__ x, int64_t rows, int C, int P,
+                                                      float* __restrict__ out, int fmt) {
+  extern __shared__ float sh[];
+  const int nvec = C >> 3;
+  const int lanes = blockDim.x / nvec;
+  const int v = threadIdx.x % nvec;
+  const int pl = threadIdx.x / nvec;
+  float s[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = 0.f;
+  if (pl < lanes) {
+    const int64_t r_end = min(static_cast<int64_t>(blockIdx.x + 1) * P, rows);
+    for (int64_t r = static_cast<int64_t>(blockIdx.x) * P + pl; r < r_end; r += lanes) {
+      float f[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(x + r * C + v * 8)), fmt, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] += f[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sh[pl * C + v * 8 + j] = s[j];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float t = 0.f;
+    for (int l = 0; l < lanes; ++l) t += sh[l * C + c];
+    atomicAdd(&out[c], t);
+  }
+}
+
+__global__ void __launch_bounds__(256) sum_f32_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
+  __shared__ float red[8];
+  float s = 0.f;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    s += x[i];
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) s += __shfl_xor_sync(0xffffffffu, s, w);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    atomicAdd(out, t);
+  }
+}
+
+// One thread owns 8 channels x 9 taps of partial sums over its pixels; pairs of lanes, then the 8 warps, are reduced
+// before the atomics.  C == 128 (nvec == 16): lane l and l ^ 16 share a channel vector.
+__global__ void __launch_bounds__(256) wgrad_1ch_kernel(const uint16_t* __restrict__ act, const float* __restrict__ img,
+                                                        float* __restrict__ out, int B, int H, int W, int C, int sgn,
+                                                        int P, int fmt) {
+  __shared__ float red[8][16][72];
+  const int nvec = C >> 3;  // 16
+  const int v = threadIdx.x % nvec;
+  const int pl = threadIdx.x / nvec;
+  const int lanes = blockDim.x / nvec;
+  float acc[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+  const int64_t total = static_cast<int64_t>(B) * H * W;
+  const int64_t p_end = min(static_cast<int64_t>(blockIdx.x + 1) * P, total);
+  for (int64_t p = static_cast<int64_t>(blockIdx.x) * P + pl; p < p_end; p += lanes) {
+    const int x = static_cast<int>(p % W);
+    const int y = static_cast<int>((p / W) % H);
+    const int64_t nb = p / (static_cast<int64_t>(W) * H) * H * W;
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(act + p * C + v * 8)), fmt, f);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int yy = y + sgn * (t / 3 - 1), xx = x + sgn * (t % 3 - 1);
+      const float im = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(img + nb + static_cast<int64_t>(yy) * W + xx) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(f[j], im, acc[t][j]);
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float s = acc[t][j] + __shfl_xor_sync(0xffffffffu, acc[t][j], 16);
+      if (lane < 16) red[warp][lane][j * 9 + t] = s;
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 16 * 72; i += blockDim.x) {
+    const int vv = i / 72, k = i % 72;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][vv][k];
+    atomicAdd(&out[(vv * 8 + k / 9) * 9 + k % 9], s);
+  }
+}
+
+__global__ void __launch_bounds__(256) head_bwd_data_kernel(const float* __restrict__ dout, const float* __restrict__ w,
+                                                            uint16_t* __restrict__ dact, int B, int H, int W, int C,
+                                                            int fmt) {
+  extern __shared__ float sw[];  // [C][9]
+  for (int i = threadIdx.x; i < C * 9; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const int nvec = C >> 3;
+  const int64_t total = static_cast<int64_t>(B) * H * W * nvec;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % nvec);
+    const int64_t p = i / nvec;
+    const int x = static_cast<int>(p % W);
+    const int y = static_cast<int>((p / W) % H);
+    const int64_t nb = p / (static_cast<int64_t>(W) * H) * H * W;
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int yy = y - (t / 3 - 1), xx = x - (t % 3 - 1);
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+        const float d = __ldg(dout + nb + static_cast<int64_t>(yy) * W + xx);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(d, sw[(v * 8 + j) * 9 + t], o[j]);
+      }
+    }
+    *reinterpret_cast<uint4*>(dact + p * C + v * 8) = pack8(o, fmt);
+  }
+}
+
+constexpr int kLbBT = 8;
+// thread = one input column i, kLbBT batch rows; dy rows are staged through shared memory in chunks of 128 outputs
+__global__ void __launch_bounds__(128) linear_bwd_input_kernel(const float* __restrict__ dy, int dy_stride,
+                                                               const float* __restrict__ w32,
+                                                               const uint16_t* __restrict__ w16, int fmt,
+                                                               float* __restrict__ dx, int dx_stride,
+                                                               const float* __restrict__ z, int z_stride, int B, int I,
+                                                               int O) {
+  __shared__ float sdy[kLbBT][128];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b0 = blockIdx.y * kLbBT;
+  float acc[kLbBT];
+#pragma unroll
+  for (int k = 0; k < kLbBT; ++k) acc[k] = 0.f;
+  for (int o0 = 0; o0 < O; o0 += 128) {
+    __syncthreads();
+    for (int k = 0; k < kLbBT; ++k) {
+      const int o = o0 + threadIdx.x;
+      sdy[k][threadIdx.x] = (b0 + k < B && o < O) ? dy[static_cast<size_t>(b0 + k) * dy_stride + o] : 0.f;
+    }
+    __syncthreads();
+    if (i < I) {
+      const int on = min(128, O - o0);
+      for (int oo = 0; oo < on; ++oo) {
+        float wv;
+        if (w16 != nullptr) {
+          const uint16_t bits = w16[static_cast<size_t>(o0 + oo) * I + i];
+          wv = fmt == 1 ? __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&bits))
+                        : __half2float(*reinterpret_cast<const __half*>(&bits));
+        } else {
+          wv = w32[static_cast<size_t>(o0 + oo) * I + i];
+        }
+#pragma unroll
+        for (int k = 0; k < kLbBT; ++k) acc[k] = fmaf(sdy[k][oo], wv, acc[k]);
+      }
+    }
+  }
+  if (i < I) {
+#pragma unroll
+    for (int k = 0; k < kLbBT; ++k) {
+      if (b0 + k < B) {
+        float r = acc[k];
+        if (z != nullptr) r *= silu_grad_precise(z[static_cast<size_t>(b0 + k) * z_stride + i]);
+        dx[static_cast<size_t>(b0 + k) * dx_stride + i] = r;
+      }
+    }
+  }
+}
+
+// thread = one input column i, 4 output rows o; loop over the batch
+__global__ void __launch_bounds__(128) linear_bwd_weight_kernel(const float* __restrict__ dy, int dy_stride,
+                                                                const float* __restrict__ x, int x_stride, int act_x,
+                                                                float* __restrict__ dw, float* __restrict__ db, int B,
+                                                                int I, int O) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int o0 = blockIdx.y * 4;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float bacc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (i >= I) return;
+  for (int b = 0; b < B; ++b) {
+    float xv = x[static_cast<size_t>(b) * x_stride + i];
+    if (act_x) xv = silu_precise(xv);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (o0 + k < O) {
+        const float d = __ldg(dy + static_cast<size_t>(b) * dy_stride + o0 + k);
+        acc[k] = fmaf(d, xv, acc[k]);
+        bacc[k] += d;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (o0 + k < O) {
+      dw[static_cast<size_t>(o0 + k) * I + i] = acc[k];
+      if (i == 0 && db != nullptr) db[o0 + k] = bacc[k];
+    }
+  }
+}
+
+__global__ void copy_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    dst[i] = src[i];
+}
+
+int pick_blocks(int B, int HW, int lanes) {
+  int chunks = (4 * device_sm_count() + B - 1) / B;
+  const int max_chunks = (HW + 4 * lanes - 1) / (4 * lanes);
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  return chunks;
+}
+
+}  // namespace
+
+int launch_gn_bwd(const GnBwdArgs& g, cudaStream_t stream) {
+  const int C = g.x.C();
+  if (C % 32 != 0 || C % 8 != 0 || 256 % (C / 8) != 0 && (C / 8) > 256)
+    return fail(kUnsupported, "gn_bwd: unsupported channel count");
+  if ((C / kGnGroups) % 4 != 0) return fail(kUnsupported, "gn_bwd: group size must be a multiple of 4");
+  if (g.x.c0 % 8 != 0 || g.x.c1 % 8 != 0) return fail(kUnsupported, "gn_bwd: concat members must be multiples of 8");
+  if (!g.stats0 || (g.x.c1 > 0 && !g.stats1) || !g.dy || !g.sums || !g.out0 || (g.x.c1 > 0 && !g.out1) ||
+      !g.dgamma || !g.dbeta || !g.gamma || !g.beta)
+    return fail(kInvalidArgument, "gn_bwd: null pointer");
+  GnBwdDev a;
+  a.p0 = reinterpret_cast<const uint16_t*>(g.x.p0);
+  a.p1 = reinterpret_cast<const uint16_t*>(g.x.p1);
+  a.c0 = g.x.c0;
+  a.c1 = g.x.c1;
+  a.B = g.B;
+  a.HW = g.H * g.W;
+  a.stats0 = g.stats0;
+  a.stats1 = g.stats1;
+  a.gamma = g.gamma;
+  a.beta = g.beta;
+  a.film = g.film;
+  a.film_stride = g.film_stride;
+  a.film_off = g.film_off;
+  a.silu = g.silu;
+  a.dy = reinterpret_cast<const uint16_t*>(g.dy);
+  a.add0 = reinterpret_cast<const uint16_t*>(g.add0);
+  a.add1 = reinterpret_cast<const uint16_t*>(g.add1);
+  a.sums = g.sums;
+  a.out0 = reinterpret_cast<uint16_t*>(g.out0);
+  a.out1 = reinterpret_cast<uint16_t*>(g.out1);
+  a.bsum0 = g.bsum0;
+  a.bsum1 = g.bsum1;
+  a.dgamma = g.dgamma;
+  a.dbeta = g.dbeta;
+  a.dfilm = g.dfilm;
+  a.fmt = g.fmt;
+  const int nvec = C / 8;
+  const int threads = 256;
+  const int lanes = threads / nvec;
+  if (lanes < 1) return fail(kUnsupported, "gn_bwd: too many channels");
+  const int chunks = pick_blocks(g.B, a.HW, lanes);
+  a.P = (a.HW + chunks - 1) / chunks;
+  const dim3 grid((a.HW + a.P - 1) / a.P, g.B);
+  size_t sh_reduce = static_cast<size_t>(lanes) * C * 2 * sizeof(float);
+  if (sh_reduce < static_cast<size_t>(4) * C * sizeof(float)) sh_reduce = static_cast<size_t>(4) * C * sizeof(float);
+  gn_bwd_reduce_kernel<<<grid, threads, sh_reduce, stream>>>(a);
+  CDDPM_TRY(check_launch("gn_bwd_reduce_kernel"));
+  size_t sh_apply = static_cast<size_t>(lanes) * C * sizeof(float);
+  if (sh_apply < static_cast<size_t>(6) * C * sizeof(float)) sh_apply = static_cast<size_t>(6) * C * sizeof(float);
+  gn_bwd_apply_kernel<<<grid, threads, sh_apply, stream>>>(a);
+  return check_launch("gn_bwd_apply_kernel");
+}
+
+int launch_resample_bwd(const void* dy, void* dx, int B, int H, int W, int C, int mode, int fmt, cudaStream_t stream) {
+  if (mode != kResampleUp2 && mode != kResampleDown2) return fail(kInvalidArgument, "resample_bwd: bad mode");
+  if (C % 8 != 0 || (mode == kResampleDown2 && (H % 2 != 0 || W % 2 != 0)))
+    return fail(kUnsupported, "resample_bwd: unsupported geometry");
+  const size_t total = static_cast<size_t>(B) * H * W * (C / 8);
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > 8 * device_sm_count()) blocks = 8 * device_sm_count();
+  resample_bwd_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const uint16_t*>(dy),
+                                                  reinterpret_cast<uint16_t*>(dx), B, H, W, C, mode, fmt);
+  return check_launch("resample_bwd_kernel");
+}
+
+int launch_col_sum(const void* x, int64_t rows, int C, float* out, int fmt, cudaStream_t stream) {
+  if (C % 8 != 0 || C / 8 > 256) return fail(kUnsupported, "col_sum: unsupported channel count");
+  const int lanes = 256 / (C / 8);
+  int blocks = 4 * device_sm_count();
+  const int64_t max_blocks = (rows + lanes - 1) / lanes;
+  if (blocks > max_blocks) blocks = static_cast<int>(max_blocks);
+  if (blocks < 1) blocks = 1;
+  const int P = static_cast<int>((rows + blocks - 1) / blocks);
+  col_sum_kernel<<<blocks, 256, static_cast<size_t>(lanes) * C * sizeof(float), stream>>>(
+      reinterpret_cast<const uint16_t*>(x), rows, C, P, out, fmt);
+  return check_launch("col_sum_kernel");
+}
+
+int launch_sum_f32(const float* x, int64_t n, float* out, cudaStream_t stream) {
+  int blocks = static_cast<int>((n + 1023) / 1024);
+  if (blocks > 2 * device_sm_count()) blocks = 2 * device_sm_count();
+  if (blocks < 1) blocks = 1;
+  sum_f32_kernel<<<blocks, 256, 0, stream>>>(x, n, out);
+  return check_launch("sum_f32_kernel");
+}
+
+int launch_wgrad_1ch(const void* act, const float* img, float* out, int B, int H, int W, int C, int sgn, int fmt,
+                     cudaStream_t stream) {
+  if (C != 128) return fail(kUnsupported, "wgrad_1ch: the stem / head gradient kernel expects 128 channels");
+  const int64_t total = static_cast<int64_t>(B) * H * W;
+  int blocks = 2 * device_sm_count();
+  if (blocks > (total + 15) / 16) blocks = static_cast<int>((total + 15) / 16);
+  const int P = static_cast<int>((total + blocks - 1) / blocks);
+  wgrad_1ch_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const uint16_t*>(act), img, out, B, H, W, C, sgn, P, fmt);
+  return check_launch("wgrad_1ch_kernel");
+}
+
+int launch_head_bwd_data(const float* dout, const float* w, void* dact, int B, int H, int W, int C, int fmt,
+                         cudaStream_t stream) {
+  if (C % 8 != 0) return fail(kUnsupported, "head_bwd_data: C must be a multiple of 8");
+  const int64_t total = static_cast<int64_t>(B) * H * W * (C / 8);
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > 8 * device_sm_count()) blocks = 8 * device_sm_count();
+  head_bwd_data_kernel<<<blocks, 256, static_cast<size_t>(C) * 9 * sizeof(float), stream>>>(
+      dout, w, reinterpret_cast<uint16_t*>(dact), B, H, W, C, fmt);
+  return check_launch("head_bwd_data_kernel");
+}
+
+int launch_linear_bwd_input(const float* dy, int dy_stride, const float* w32, const void* w16, int fmt, float* dx,
+                            int dx_stride, const float* z, int z_stride, int B, int I, int O, cudaStream_t stream) {
+  const dim3 grid((I + 127) / 128, (B + kLbBT - 1) / kLbBT);
+  linear_bwd_input_kernel<<<grid, 128, 0, stream>>>(dy, dy_stride, w32, reinterpret_cast<const uint16_t*>(w16), fmt, dx,
+                                                    dx_stride, z, z_stride, B, I, O);
+  return check_launch("linear_bwd_input_kernel");
+}
+
+int launch_linear_bwd_weight(const float* dy, int dy_stride, const float* x, int x_stride, int act_x, float* dw,
+                             float* db, int B, int I, int O, cudaStream_t stream) {
+  const dim3 grid((I + 127) / 128, (O + 3) / 4);
+  linear_bwd_weight_kernel<<<grid, 128, 0, stream>>>(dy, dy_stride, x, x_stride, act_x, dw, db, B, I, O);
+  return check_launch("linear_bwd_weight_kernel");
+}
+
+int launch_copy_f32(const float* src, float* dst, int64_t n, cudaStream_t stream) {
+  int blocks = static_cast<int>((n + 255) / 256);
+  if (blocks > 1024) blocks = 1024;
+  if (blocks < 1) blocks = 1;
+  copy_f32_kernel<<<blocks, 256, 0, stream>>>(src, dst, n);
+  return check_launch("copy_f32_kernel");
+}
+
+}  // namespace cddpm

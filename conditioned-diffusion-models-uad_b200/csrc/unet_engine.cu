@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include "attention.cuh"
+#include "conv_bwd.cuh"
 
 namespace cddpm {
 
@@ -33,6 +34,11 @@ void UNetEngine::free_acts() {
   for (void* p : act_owned_) cudaFree(p);
   act_owned_.clear();
   ops_.clear();
+  bwd_ops_.clear();
+  bwd_planned_ = false;
+  res_plans_.clear();
+  attn_plans_.clear();
+  steps_.clear();
   taps_.clear();
   planned_B_ = 0;
 }
@@ -52,6 +58,8 @@ int UNetEngine::add_param(const std::string& name, int64_t numel,
   p.name = name;
   p.numel = numel;
   p.load = std::move(load);
+  p.goff = grad_total_;
+  grad_total_ += (numel + 63) / 64 * 64;  // 256-byte aligned gradient slots
   param_index_[name] = static_cast<int>(params_.size());
   params_.push_back(std::move(p));
   return kOk;
@@ -104,11 +112,14 @@ int UNetEngine::add_res(const std::string& prefix, int c0, int c1, int cout, int
   CDDPM_TRY(add_copy_param(prefix + ".in_layers.0.weight", cin, &L.gn1_w));
   CDDPM_TRY(add_copy_param(prefix + ".in_layers.0.bias", cin, &L.gn1_b));
   {
-    uint16_t* w = nullptr;
+    uint16_t *w = nullptr, *wt = nullptr;
     CDDPM_TRY(dalloc(&w, static_cast<size_t>(cout) * 9 * cin));
+    CDDPM_TRY(dalloc(&wt, static_cast<size_t>(cin) * 9 * cout));
     L.w1 = w;
+    L.w1t = wt;
     CDDPM_TRY(add_param(prefix + ".in_layers.2.weight", static_cast<int64_t>(cout) * cin * 9,
                         [=](const float* src, cudaStream_t s) {
+                          CDDPM_TRY(launch_pack_conv_weight_T(src, cout, cin, 3, 0, cin, wt, 9 * cout, 0, fmt, s));
                           return launch_pack_conv_weight(src, cout, cin, 3, 0, cin, w, 9 * cin, 0, fmt, s);
                         }));
   }
@@ -138,9 +149,15 @@ int UNetEngine::add_res(const std::string& prefix, int c0, int c1, int cout, int
   // the epilogue it made that the critical path (87 vs 68 us per 128->128 @ 96x96 launch).
   const int k2 = 9 * cout + cin;
   {
-    uint16_t* w = nullptr;
+    uint16_t *w = nullptr, *wt = nullptr, *wst = nullptr;
     CDDPM_TRY(dalloc(&w, static_cast<size_t>(cout) * k2));
+    CDDPM_TRY(dalloc(&wt, static_cast<size_t>(cout) * 9 * cout));
     L.w2 = w;
+    L.w2t = wt;
+    if (L.has_skip) {
+      CDDPM_TRY(dalloc(&wst, static_cast<size_t>(cin) * cout));
+      L.wskipt = wst;
+    }
     if (!L.has_skip) {
       std::vector<uint16_t> eye(static_cast<size_t>(cout) * cout, 0);
       const uint16_t one = fmt == 1 ? 0x3F80 : 0x3C00;  // 1.0 in bf16 / fp16
@@ -150,6 +167,7 @@ int UNetEngine::add_res(const std::string& prefix, int c0, int c1, int cout, int
     }
     CDDPM_TRY(add_param(prefix + ".out_layers.3.weight", static_cast<int64_t>(cout) * cout * 9,
                         [=](const float* src, cudaStream_t s) {
+                          CDDPM_TRY(launch_pack_conv_weight_T(src, cout, cout, 3, 0, cout, wt, 9 * cout, 0, fmt, s));
                           return launch_pack_conv_weight(src, cout, cout, 3, 0, cout, w, k2, 0, fmt, s);
                         }));
     CDDPM_TRY(dalloc(&L.b2, static_cast<size_t>(cout)));
@@ -170,6 +188,7 @@ int UNetEngine::add_res(const std::string& prefix, int c0, int c1, int cout, int
       // 1x1 skip over the (possibly concatenated) raw input: extra K columns after the 3x3 block
       CDDPM_TRY(add_param(prefix + ".skip_connection.weight", static_cast<int64_t>(cout) * cin,
                           [=](const float* src, cudaStream_t s) {
+                            CDDPM_TRY(launch_pack_conv_weight_T(src, cout, cin, 1, 0, cin, wst, cout, 0, fmt, s));
                             CDDPM_TRY(launch_pack_conv_weight(src, cout, cin, 1, 0, c0, w, k2, 9 * cout, fmt, s));
                             if (c1 > 0)
                               CDDPM_TRY(launch_pack_conv_weight(src, cout, cin, 1, c0, c1, w, k2, 9 * cout + c0, fmt, s));
@@ -196,13 +215,20 @@ int UNetEngine::add_attn(const std::string& prefix, int ch) {
   uint16_t *wq = nullptr, *wp = nullptr;
   CDDPM_TRY(dalloc(&wq, static_cast<size_t>(3) * ch * ch));
   CDDPM_TRY(dalloc(&wp, static_cast<size_t>(ch) * ch));
+  uint16_t *wqt = nullptr, *wpt = nullptr;
+  CDDPM_TRY(dalloc(&wqt, static_cast<size_t>(3) * ch * ch));
+  CDDPM_TRY(dalloc(&wpt, static_cast<size_t>(ch) * ch));
   L.wqkv = wq;
   L.wproj = wp;
+  L.wqkvt = wqt;
+  L.wprojt = wpt;
   CDDPM_TRY(add_param(prefix + ".qkv.weight", static_cast<int64_t>(3) * ch * ch, [=](const float* src, cudaStream_t s) {
+    CDDPM_TRY(launch_pack_conv_weight_T(src, 3 * ch, ch, 1, 0, ch, wqt, 3 * ch, 0, fmt, s));
     return launch_pack_conv_weight(src, 3 * ch, ch, 1, 0, ch, wq, ch, 0, fmt, s);
   }));
   CDDPM_TRY(add_copy_param(prefix + ".qkv.bias", 3 * ch, &L.bqkv));
   CDDPM_TRY(add_param(prefix + ".proj_out.weight", static_cast<int64_t>(ch) * ch, [=](const float* src, cudaStream_t s) {
+    CDDPM_TRY(launch_pack_conv_weight_T(src, ch, ch, 1, 0, ch, wpt, ch, 0, fmt, s));
     return launch_pack_conv_weight(src, ch, ch, 1, 0, ch, wp, ch, 0, fmt, s);
   }));
   CDDPM_TRY(add_copy_param(prefix + ".proj_out.bias", ch, &L.bproj));
@@ -517,6 +543,20 @@ int UNetEngine::plan_res(const ResLayer& L, const ActTensor& a0, const ActTensor
   }
   taps_[L.prefix] = *out;
   taps_[L.prefix + "/in_conv"] = tH;
+  {
+    ResPlan rp;
+    rp.layer = static_cast<int>(&L - res_.data());
+    rp.has_a1 = a1 != nullptr;
+    rp.a0 = a0;
+    if (a1) rp.a1 = *a1;
+    rp.tA = tA;
+    rp.tH = tH;
+    rp.tB = tB;
+    rp.tS = tS;
+    rp.out = *out;
+    steps_.push_back(Step{1, static_cast<int>(res_plans_.size())});
+    res_plans_.push_back(rp);
+  }
   return kOk;
 }
 
@@ -591,6 +631,17 @@ int UNetEngine::plan_attn(const AttnLayer& L, const ActTensor& x, ActTensor* out
   taps_[L.prefix] = *out;
   taps_[L.prefix + "/qkv"] = tQ;
   taps_[L.prefix + "/attn"] = tA;
+  {
+    AttnPlan ap;
+    ap.layer = static_cast<int>(&L - attn_.data());
+    ap.x = x;
+    ap.tN = tN;
+    ap.tQ = tQ;
+    ap.tA = tA;
+    ap.out = *out;
+    steps_.push_back(Step{2, static_cast<int>(attn_plans_.size())});
+    attn_plans_.push_back(ap);
+  }
   return kOk;
 }
 
@@ -737,6 +788,7 @@ int UNetEngine::plan(int B) {
         ops_.push_back(
             [=](cudaStream_t s) { return launch_conv_in(cur_x_, stem_w, stem_b, op, ost, B, H, W, mc, fmt, s); });
         taps_["input_blocks.0.0"] = o;
+        stem_out_ = o;
       } else if (l.kind == 1) {
         CDDPM_TRY(plan_res(res_[l.idx], h, nullptr, &o, B));
       } else {
@@ -790,6 +842,8 @@ int UNetEngine::plan(int B) {
     g.out = tN.p;
     g.fmt = fmt;
     push_gn(g);
+    head_in_ = h;
+    head_tN_ = tN;
     void* np = tN.p;
     ops_.push_back([=](cudaStream_t s) { return launch_conv_out(np, head_w, head_b, cur_out_, B, hh, ww, cc, fmt, s); });
   }

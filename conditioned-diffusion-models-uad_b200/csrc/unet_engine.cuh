@@ -40,6 +40,14 @@ class UNetEngine {
   int64_t conv_flops_per_sample() const { return conv_flops_; }
   int launches_per_forward() const { return static_cast<int>(ops_.size()); }
   int fmt() const { return cfg_.fmt; }
+  // Backward of the LAST forward (training step): dout = dL/d out [B,1,H,W] fp32; every parameter gradient is written
+  // into the flat fp32 buffer `grads` (grad_total() floats, parameter i at grad_offset(i), reference layouts);
+  // dcond (optional) receives dL/d cond [B, num_classes].
+  int backward(const float* dout, float* grads, float* dcond, int B, cudaStream_t stream);
+  int64_t grad_total() const { return grad_total_; }
+  int grad_offset(int i, int64_t* off) const;
+  int64_t bwd_flops_per_sample() const { return bwd_flops_; }
+  int bwd_launches() const { return static_cast<int>(bwd_ops_.size()); }
 
  private:
   struct Param {
@@ -47,6 +55,7 @@ class UNetEngine {
     int64_t numel = 0;
     bool set = false;
     std::function<int(const float*, cudaStream_t)> load;
+    int64_t goff = 0;  // offset of this parameter's gradient in the flat gradient buffer
   };
   struct ResLayer {
     std::string prefix;
@@ -54,6 +63,7 @@ class UNetEngine {
     bool has_skip = false;
     float *gn1_w = nullptr, *gn1_b = nullptr, *gn2_w = nullptr, *gn2_b = nullptr;
     void *w1 = nullptr, *w2 = nullptr;
+    void *w1t = nullptr, *w2t = nullptr, *wskipt = nullptr;  // data-gradient panels (transposed, taps flipped)
     float *b1 = nullptr, *b2 = nullptr, *bskip = nullptr, *b2sum = nullptr;
     int in_c0 = 0, in_c1 = 0;  // channel split of the (possibly concatenated) block input
   };
@@ -62,11 +72,40 @@ class UNetEngine {
     int ch = 0;
     float *gn_w = nullptr, *gn_b = nullptr, *bqkv = nullptr, *bproj = nullptr;
     void *wqkv = nullptr, *wproj = nullptr;
+    void *wqkvt = nullptr, *wprojt = nullptr;
   };
   struct Layer {
     int kind = 0;  // 0 stem conv, 1 res, 2 attn
     int idx = 0;
   };
+
+  // what the backward pass needs to know about one planned layer (forward order)
+  struct ResPlan {
+    int layer = 0;
+    bool has_a1 = false;
+    ActTensor a0, a1, tA, tH, tB, tS, out;
+  };
+  struct AttnPlan {
+    int layer = 0;
+    ActTensor x, tN, tQ, tA, out;
+  };
+  struct Step {
+    int kind = 0;  // 1 res, 2 attn
+    int idx = 0;   // index into res_plans_ / attn_plans_
+  };
+  std::vector<ResPlan> res_plans_;
+  std::vector<AttnPlan> attn_plans_;
+  std::vector<Step> steps_;
+  ActTensor stem_out_, head_in_, head_tN_;
+  int plan_backward(int B);
+  float* grad_of(const std::string& name) const;
+  std::vector<std::function<int(cudaStream_t)>> bwd_ops_;
+  bool bwd_planned_ = false;
+  float* cur_grads_ = nullptr;
+  const float* cur_dout_ = nullptr;
+  float* cur_dcond_ = nullptr;
+  int64_t grad_total_ = 0;
+  int64_t bwd_flops_ = 0;
 
   template <typename T>
   int dalloc(T** p, size_t n);

@@ -136,6 +136,23 @@ int cddpm_unet_launches(const cddpm_unet_t* h);
 int cddpm_unet_profile_arm(cddpm_unet_t* h);
 int cddpm_unet_profile_read(cddpm_unet_t* h, double* conv_ms, int* conv_launches);
 
+/* Training step (DDPM_2D.training_step, DDPM_2D.py:114-138: loss.backward() through UNetModel.forward).
+ * Backward of the LAST forward of this handle (bf16 engines, model_channels 128): dout = dL/d out [B,1,H,W] fp32.
+ * Every parameter gradient is written (not accumulated) into the flat fp32 buffer `grads` of
+ * cddpm_unet_grad_total() floats: parameter i (cddpm_unet_param_info order) at cddpm_unet_grad_offset(i), in the
+ * reference's parameter layout.  dcond (optional) receives dL/d cond [B,num_classes]. */
+int64_t cddpm_unet_grad_total(const cddpm_unet_t* h);
+int cddpm_unet_grad_offset(const cddpm_unet_t* h, int index, int64_t* offset);
+int cddpm_unet_backward(cddpm_unet_t* h, const float* dout, float* grads, float* dcond, int B, void* stream);
+/* Algorithmic tensor-core FLOPs of the backward per sample, and its kernel-launching plan steps (after the first
+ * backward of a batch size). */
+int64_t cddpm_unet_bwd_flops(const cddpm_unet_t* h);
+int cddpm_unet_bwd_launches(const cddpm_unet_t* h);
+/* Backward of cddpm_attention (bf16): dqkv [B,L,3C] from dout [B,L,C]; scratch = cddpm_attention_bwd_scratch_bytes. */
+int64_t cddpm_attention_bwd_scratch_bytes(int B, int L, int C);
+int cddpm_attention_bwd(const void* qkv, const void* dout, void* dqkv, void* scratch, int B, int L, int C, int fmt,
+                        void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Condition encoder: SparK_2D_encoder.forward (spark/Spark_2D.py:285-290) = timm ResNet-50 (v1.5, in_chans=1,
  * num_classes=cond_dim) in eval mode, forward(x, pyramid=0) (spark/resnet.py:13-46).  Parameter names are the

@@ -108,8 +108,9 @@ def test_product_fails_loudly_without_cuda():
             m.diffusion(torch.zeros(1, 1, 96, 96), cond=torch.zeros(1, 128), t=10, noise=torch.zeros(1, 1, 96, 96))
     with pytest.raises((CddpmError, RuntimeError, AssertionError)):
         apply_3d_median_filter(torch.zeros(8, 8, 8))
-    with pytest.raises(NotImplementedError):
-        m.training_step({}, 0)
+    with pytest.raises(CddpmError):  # the training step has no CPU path either
+        m.train()
+        m.training_step({"vol": {"data": torch.zeros(1, 1, 96, 96, 1)}}, 0)
 
 
 def test_schedule_buffers_are_reference_bit_exact():

@@ -1,0 +1,174 @@
+"""GPU parity of the training step (DDPM_2D.training_step, DDPM_2D.py:114-138 -> loss.backward())
+against torch autograd over the fp32 oracle port of the reference UNet (oracle/unet_port.py, pinned bit-exactly to the
+live reference forward by tests/golden/unet_*.npz).
+
+Tolerance: the engine computes activations AND activation gradients in bf16 (fp32 accumulation; GroupNorm statistics
+fp64); BASELINE config 5 names bf16 fwd+bwd.  Per parameter tensor we require a relative L2 error
+||g - g_ref|| / ||g_ref|| <= 4e-2 and a cosine >= 0.998 against the fp32 reference gradient."""
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 4e-2
+COS_TOL = 0.998
+
+
+def _setup():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def _rel(a, b):
+    return ((a - b).norm() / b.norm().clamp_min(1e-20)).item()
+
+
+def _cos(a, b):
+    return (torch.dot(a.flatten(), b.flatten()) / (a.norm() * b.norm()).clamp_min(1e-30)).item()
+
+
+def test_attention_backward_matches_autograd():
+    import ctypes
+
+    from cddpm._lib import check, current_stream, lib, ptr
+
+    _setup()
+    B, L, C = 2, 256, 256
+    g = torch.Generator(device="cuda").manual_seed(3)
+    qkv = torch.randn(B, L, 3 * C, device="cuda", generator=g).to(torch.bfloat16)
+    dout = torch.randn(B, L, C, device="cuda", generator=g).to(torch.bfloat16)
+    ref_in = qkv.float().requires_grad_(True)
+    q, k, v = ref_in.split(C, dim=2)
+
+    def heads(t):
+        return t.view(B, L, C // 64, 64).permute(0, 2, 1, 3)
+
+    w = torch.softmax(heads(q) @ heads(k).transpose(-1, -2) * 0.125, dim=-1)
+    out = (w @ heads(v)).permute(0, 2, 1, 3).reshape(B, L, C)
+    out.backward(dout.float())
+    dqkv = torch.empty_like(qkv)
+    scratch = torch.empty(lib().cddpm_attention_bwd_scratch_bytes(B, L, C), dtype=torch.uint8, device="cuda")
+    check(lib().cddpm_attention_bwd(ptr(qkv), ptr(dout), ptr(dqkv), ptr(scratch), B, L, C, 1, current_stream()),
+          "cddpm_attention_bwd")
+    torch.cuda.synchronize()
+    for name, sl in (("dq", slice(0, C)), ("dk", slice(C, 2 * C)), ("dv", slice(2 * C, 3 * C))):
+        got, ref = dqkv[..., sl].float(), ref_in.grad[..., sl]
+        assert _rel(got, ref) <= 2e-2, f"{name}: rel {_rel(got, ref):.4g}"
+
+
+def _unet_grads(spec, image, B, seed, report=None):
+    from cddpm.engine import UNetEngine
+    from oracle import unet_port
+    from oracle.weights import make_state_dict
+
+    _setup()
+    sd = {k: v.cuda() for k, v in make_state_dict(unet_port.param_shapes(spec), seed=seed).items()}
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn(B, 1, image, image, device="cuda", generator=g)
+    t = torch.randint(0, 1000, (B,), device="cuda", generator=g)
+    cond = torch.randn(B, spec.num_classes, device="cuda", generator=g) if spec.num_classes else None
+    dout = torch.randn(B, 1, image, image, device="cuda", generator=g) / (B * image * image)
+
+    # fp32 oracle + autograd
+    sd_ref = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    cond_ref = cond.clone().requires_grad_(True) if cond is not None else None
+    out_ref = unet_port.unet_forward(sd_ref, spec, x, t, cond_ref)
+    out_ref.backward(dout)
+
+    eng = UNetEngine(image_size=(image, image), in_channels=1, model_channels=spec.model_channels, out_channels=1,
+                     num_res_blocks=spec.num_res_blocks, attention_resolutions=spec.attention_resolutions,
+                     channel_mult=spec.channel_mult, num_classes=spec.num_classes, num_head_channels=64,
+                     dtype=torch.bfloat16)
+    eng.load_state_dict(sd)
+    out = eng.forward(x, t, cond)
+    flat, dcond = eng.backward(dout, want_dcond=cond is not None)
+    torch.cuda.synchronize()
+    assert (out - out_ref).abs().max().item() <= 5e-2
+    _, offs = eng.grad_layout()
+    rows = []
+    for (name, numel), off in zip(eng.param_names(), offs):
+        got = flat[off:off + numel]
+        ref = sd_ref[name].grad.flatten()
+        rows.append((name, _rel(got, ref), _cos(got, ref), ref.norm().item()))
+    if cond is not None:
+        rows.append(("d cond", _rel(dcond, cond_ref.grad), _cos(dcond, cond_ref.grad), cond_ref.grad.norm().item()))
+    return rows
+
+
+def _check(rows):
+    bad = [r for r in rows if not (r[1] <= REL_TOL and r[2] >= COS_TOL)]
+    msg = "\n".join(f"{n:48s} rel {r:.4g} cos {c:.6f} |ref| {m:.4g}" for n, r, c, m in (bad[:40] or rows[:5]))
+    assert not bad, f"{len(bad)} of {len(rows)} gradients off:\n{msg}"
+
+
+def test_unet_backward_small_geometry():
+    """128-channel two-level UNet on 32x32 (ResBlocks with identity / 1x1 skips, down / up blocks, middle attention)."""
+    from oracle import unet_port
+
+    spec = unet_port.UNetSpec(model_channels=128, channel_mult=(1, 2), num_res_blocks=1, num_classes=128)
+    _check(_unet_grads(spec, 32, 2, seed=5))
+
+
+def test_unet_backward_unconditioned():
+    from oracle import unet_port
+
+    spec = unet_port.UNetSpec(model_channels=128, channel_mult=(1, 2), num_res_blocks=1, num_classes=None)
+    _check(_unet_grads(spec, 32, 3, seed=6))
+
+
+def test_unet_backward_full_geometry():
+    """The cDDPM UNet itself (96x96, 128 x [1,2,2], 3 ResBlocks per level, 316 parameter tensors), batch 2."""
+    from oracle import unet_port
+
+    _check(_unet_grads(unet_port.UNetSpec(), 96, 2, seed=7))
+
+
+class Cfg(dict):
+    __getattr__ = dict.get
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+def test_training_step_lightning_surface():
+    """DDPM_2D.training_step -> loss.backward() -> Adam step through the reference's LightningModule surface; the
+    loss equals the oracle's for the same weights / noise / t, every parameter receives a finite gradient and the
+    loss falls over a few steps on a fixed batch."""
+    import numpy as np
+
+    from cddpm.ddpm_2d import DDPM_2D
+
+    _setup()
+    torch.manual_seed(0)
+    np.random.seed(0)
+    cfg = Cfg(imageDim=[192, 192, 100], rescaleFactor=2, unet_dim=128, dim_mults=[1, 2, 2], condition=True,
+              backbone="Spark_Encoder_2D", version="resnet50", cond_dim=128, noisetype="simplex", test_timesteps=500,
+              lr=1e-4, objective="pred_x0", pretrained_encoder=False)
+    m = DDPM_2D(cfg).cuda().train()
+    with torch.no_grad():  # the reference zero-initialises these; give the loss something to move
+        for name, p in m.diffusion.model.named_parameters():
+            if name.endswith(("out.2.weight", "out_layers.3.weight", "proj_out.weight")):
+                p.normal_(0, 0.02)
+    opt = m.configure_optimizers()
+    from oracle.weights import synthetic_slices
+
+    batch = {"vol": {"data": synthetic_slices(4, 96, seed=1).cuda().unsqueeze(-1)}}
+    losses = []
+    for step in range(4):
+        torch.manual_seed(100)  # same t every step
+        np.random.seed(100)     # same simplex field every step
+        opt.zero_grad(set_to_none=True)
+        loss = m.training_step(batch, step)["loss"]
+        loss.backward()
+        if step == 0:
+            missing = [n for n, p in m.named_parameters() if p.grad is None or not torch.isfinite(p.grad).all()]
+            assert not missing, f"parameters without a finite gradient: {missing[:8]}"
+        opt.step()
+        losses.append(float(loss))
+    assert all(np.isfinite(losses)), losses
+    assert losses[-1] < losses[0], f"loss did not fall: {losses}"
