@@ -74,6 +74,7 @@ def _signatures(c):
         "cddpm_unet_launches": (i32, [vp]),
         "cddpm_unet_profile_arm": (i32, [vp]),
         "cddpm_unet_profile_read": (i32, [vp, c.POINTER(c.c_double), pi32]),
+        "cddpm_unet_set_params": (i32, [vp, pvp, i32, vp]),
         "cddpm_unet_grad_total": (i64, [vp]),
         "cddpm_unet_grad_offset": (i32, [vp, i32, c.POINTER(i64)]),
         "cddpm_unet_backward": (i32, [vp, vp, vp, vp, i32, vp]),

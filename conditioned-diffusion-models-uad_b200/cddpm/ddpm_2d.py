@@ -205,7 +205,9 @@ class DDPM_2D(LightningModule):
         _test_end(self)
 
     def configure_optimizers(self):
-        return optim.Adam(self.parameters(), lr=self.cfg.lr)
+        # same optimizer as the reference (DDPM_2D.py:305-306); the fused multi-tensor implementation when on CUDA
+        params = list(self.parameters())
+        return optim.Adam(params, lr=self.cfg.lr, fused=all(p.is_cuda for p in params))
 
     def update_prefix(self, prefix):
         self.prefix = prefix

@@ -65,6 +65,24 @@ class UNetEngine:
         check(lib().cddpm_unet_set_param(self._h, name.encode(), ptr(v), v.numel(), current_stream()),
               f"cddpm_unet_set_param({name})")
 
+    def set_params(self, values: Sequence[Optional[torch.Tensor]]) -> None:
+        """Bulk push in param_names() order (None = unchanged): one C call instead of one per tensor."""
+        keep = []
+        ptrs = []
+        for v in values:
+            if v is None:
+                ptrs.append(None)
+                continue
+            t = v.detach()
+            if not t.is_cuda:
+                raise CddpmError("the cDDPM engine needs CUDA tensors")
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.float().contiguous()
+                keep.append(t)
+            ptrs.append(t.data_ptr())
+        check(lib().cddpm_unet_set_params(self._h, _lib.ptr_array(ptrs), len(ptrs), current_stream()),
+              "cddpm_unet_set_params")
+
     def load_state_dict(self, sd: Dict[str, torch.Tensor], prefix: str = "") -> None:
         for name, _ in self.param_names():
             self.set_param(name, sd[prefix + name])

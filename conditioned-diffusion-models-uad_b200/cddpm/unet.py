@@ -240,7 +240,6 @@ class UNetModel(nn.Module):
         dev = items[0][1].device
         if dev.type != "cuda":
             raise CddpmError("UNetModel is on the CPU; the cDDPM engine has no CPU path — move the module to CUDA")
-        versions = [(p.data_ptr(), p._version) for _, p in items]
         if self._engine is None:
             self._engine = UNetEngine(
                 image_size=self.image_size, in_channels=self.in_channels, model_channels=self.model_channels,
@@ -251,10 +250,7 @@ class UNetModel(nn.Module):
             if names != [n for n, _ in items]:
                 raise CddpmError("engine parameter list differs from the module's state_dict layout")
             self._engine_versions = [None] * len(items)
-        for i, ((name, p), v) in enumerate(zip(items, versions)):
-            if self._engine_versions[i] != v:
-                self._engine.set_param(name, p)
-                self._engine_versions[i] = v
+        self._push(self._engine, self._engine_versions, items)
         return self._engine
 
     def train_engine(self) -> UNetEngine:
@@ -272,12 +268,25 @@ class UNetModel(nn.Module):
                 attention_resolutions=self.attention_resolutions, channel_mult=self.channel_mult,
                 num_classes=self.num_classes, num_head_channels=self.num_head_channels, dtype=torch.bfloat16)
             self._train_versions = [None] * len(items)
-        for i, (name, p) in enumerate(items):
-            v = (p.data_ptr(), p._version)
-            if self._train_versions[i] != v:
-                self._train_engine.set_param(name, p)
-                self._train_versions[i] = v
+        self._push(self._train_engine, self._train_versions, items)
         return self._train_engine
+
+    @staticmethod
+    def _push(engine, seen, items):
+        """Re-push the parameters whose storage or version changed since the last call (all of them after an
+        optimizer step) with one bulk call."""
+        changed = []
+        any_changed = False
+        for i, (_, p) in enumerate(items):
+            v = (p.data_ptr(), p._version)
+            if seen[i] != v:
+                changed.append(p)
+                seen[i] = v
+                any_changed = True
+            else:
+                changed.append(None)
+        if any_changed:
+            engine.set_params(changed)
 
     def forward(self, x, timesteps, cond=None, context=None):
         """model(x, t, cond): x [B,1,H,W], timesteps [B], cond [B,num_classes] -> [B,1,H,W] fp32.

@@ -319,6 +319,18 @@ int cddpm_unet_profile_read(cddpm_unet_t* h, double* conv_ms, int* conv_launches
   return h->engine.profile_read(conv_ms, conv_launches);
 }
 
+int cddpm_unet_set_params(cddpm_unet_t* h, const float* const* values, int count, void* stream) {
+  if (!h || !values) return fail(kInvalidArgument, "unet_set_params: null pointer");
+  if (count != h->engine.param_count()) return fail(kInvalidArgument, "unet_set_params: wrong parameter count");
+  for (int i = 0; i < count; ++i) {
+    if (values[i] == nullptr) continue;
+    const char* name = nullptr;
+    int64_t numel = 0;
+    CDDPM_TRY(h->engine.param_info(i, &name, &numel));
+    CDDPM_TRY(h->engine.set_param(name, values[i], numel, static_cast<cudaStream_t>(stream)));
+  }
+  return kOk;
+}
 int64_t cddpm_unet_grad_total(const cddpm_unet_t* h) { return h ? h->engine.grad_total() : 0; }
 int cddpm_unet_grad_offset(const cddpm_unet_t* h, int index, int64_t* offset) {
   if (!h || !offset) return fail(kInvalidArgument, "unet_grad_offset: null pointer");

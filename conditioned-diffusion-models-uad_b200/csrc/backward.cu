@@ -81,9 +81,12 @@ struct GnBwdDev {
   int P;  // pixels per block
 };
 
-// Shared prologue: per-channel affine of the forward (z = A x + Bc), mean and rstd of the channel's group.
-// sh layout: A[C], Bc[C], Mean[C], Rstd[C]
-__device__ __forceinline__ void gn_bwd_prologue(const GnBwdDev& a, int b, float* sh, float* sGm, float* sGr) {
+// Shared prologue.  The forward computed z = gp * xhat + bp with xhat = x * rs - mr (rs = rstd of the channel's group,
+// mr = mean * rstd), gp = gamma * (1 + scale), bp = beta * (1 + scale) + shift.  Per channel we keep (gp, bp); the
+// group constants are shared by each aligned run of four channels (the group size is a multiple of four), which keeps
+// the kernels' coefficient registers at 16 + 2 * (2 or 4) per thread instead of 32 / 48.
+// sh layout: gp[C], bp[C]; sG: rs[32], mr[32]
+__device__ __forceinline__ void gn_bwd_prologue(const GnBwdDev& a, int b, float* sh, float* sRs, float* sMr) {
   const int C = a.c0 + a.c1;
   const int cpg = C / kGnGroups;
   if (threadIdx.x < kGnGroups) {
@@ -99,35 +102,33 @@ __device__ __forceinline__ void gn_bwd_prologue(const GnBwdDev& a, int b, float*
     const double mean = s / n;
     double var = q / n - mean * mean;
     if (var < 0.0) var = 0.0;
-    sGm[threadIdx.x] = static_cast<float>(mean);
-    sGr[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + 1e-5));
+    const double rstd = 1.0 / sqrt(var + 1e-5);
+    sRs[threadIdx.x] = static_cast<float>(rstd);
+    sMr[threadIdx.x] = static_cast<float>(mean * rstd);
   }
-  __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cpg;
-    float A = sGr[g] * a.gamma[c];
-    float Bc = a.beta[c] - sGm[g] * A;
+    float gp = a.gamma[c];
+    float bp = a.beta[c];
     if (a.film != nullptr) {
       const float* f = a.film + static_cast<size_t>(b) * a.film_stride + a.film_off;
       const float sc = 1.0f + f[c];
-      A *= sc;
-      Bc = Bc * sc + f[C + c];
+      gp *= sc;
+      bp = bp * sc + f[C + c];
     }
-    sh[c] = A;
-    sh[C + c] = Bc;
-    sh[2 * C + c] = sGm[g];
-    sh[3 * C + c] = sGr[g];
+    sh[c] = gp;
+    sh[C + c] = bp;
   }
   __syncthreads();
 }
 
 // sums[b][c] = (sum_p g, sum_p g * xhat), g = dy * act'(z)
-__global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const GnBwdDev a) {
+__global__ void __launch_bounds__(256, 3) gn_bwd_reduce_kernel(const GnBwdDev a) {
   extern __shared__ float sh[];
-  __shared__ float sGm[kGnGroups], sGr[kGnGroups];
+  __shared__ float sRs[kGnGroups], sMr[kGnGroups];
   const int C = a.c0 + a.c1;
+  const int cpg = C / kGnGroups;
   const int b = blockIdx.y;
-  gn_bwd_prologue(a, b, sh, sGm, sGr);
+  gn_bwd_prologue(a, b, sh, sRs, sMr);
   const int nvec = C >> 3;
   const int lanes = blockDim.x / nvec;
   const int v = threadIdx.x % nvec;
@@ -144,13 +145,16 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const GnBwdDev a) {
     } else {
       src = a.p1; cs = a.c1; cbs = cb - a.c0;
     }
-    float A[8], Bc[8], Mn[8], Rs[8];
+    float gp[8], bp[8], rs[2], mr[2];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      A[j] = sh[cb + j];
-      Bc[j] = sh[C + cb + j];
-      Mn[j] = sh[2 * C + cb + j];
-      Rs[j] = sh[3 * C + cb + j];
+      gp[j] = sh[cb + j];
+      bp[j] = sh[C + cb + j];
+    }
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      rs[hf] = sRs[(cb + 4 * hf) / cpg];
+      mr[hf] = sMr[(cb + 4 * hf) / cpg];
     }
     const size_t base = static_cast<size_t>(b) * a.HW;
     const int p_end = min((static_cast<int>(blockIdx.x) + 1) * a.P, a.HW);
@@ -172,10 +176,11 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const GnBwdDev a) {
           unpack8(ud[k], a.fmt, d);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
+            const float xh = fmaf(x[j], rs[j >> 2], -mr[j >> 2]);
             float g = d[j];
-            if (a.silu) g *= silu_grad(fmaf(x[j], A[j], Bc[j]));
+            if (a.silu) g *= silu_grad(fmaf(gp[j], xh, bp[j]));
             s1[j] += g;
-            s2[j] = fmaf(g, (x[j] - Mn[j]) * Rs[j], s2[j]);
+            s2[j] = fmaf(g, xh, s2[j]);
           }
         }
       }
@@ -199,34 +204,28 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const GnBwdDev a) {
 }
 
 // dx = rstd * (gamma' g - (P1 + xhat P2) / N) + add0 + add1
-__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdDev a) {
-  extern __shared__ float sh[];  // A, Bc, Mean, Rstd, K1, K2 (per channel), later the column-sum scratch
-  __shared__ float sGm[kGnGroups], sGr[kGnGroups], sP1[kGnGroups], sP2[kGnGroups];
+__global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(const GnBwdDev a) {
+  extern __shared__ float sh[];  // gp, bp (per channel), later the column-sum scratch
+  __shared__ float sRs[kGnGroups], sMr[kGnGroups], sK1[kGnGroups], sK2[kGnGroups];
   const int C = a.c0 + a.c1;
   const int cpg = C / kGnGroups;
   const int b = blockIdx.y;
-  gn_bwd_prologue(a, b, sh, sGm, sGr);
+  gn_bwd_prologue(a, b, sh, sRs, sMr);
   const float* S = a.sums + static_cast<size_t>(b) * 2 * C;
   if (threadIdx.x < kGnGroups) {
-    // group sums of gamma' * (S1, S2), gamma' = A / rstd
+    // group sums of gamma' * (S1, S2)
     float p1 = 0.f, p2 = 0.f;
     for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c) {
-      float gm = a.gamma[c];
-      if (a.film != nullptr) gm *= 1.0f + a.film[static_cast<size_t>(b) * a.film_stride + a.film_off + c];
-      p1 = fmaf(gm, S[2 * c], p1);
-      p2 = fmaf(gm, S[2 * c + 1], p2);
+      p1 = fmaf(sh[c], S[2 * c], p1);
+      p2 = fmaf(sh[c], S[2 * c + 1], p2);
     }
     const float inv_n = 1.0f / (static_cast<float>(a.HW) * cpg);
-    sP1[threadIdx.x] = sGr[threadIdx.x] * p1 * inv_n;
-    sP2[threadIdx.x] = sGr[threadIdx.x] * p2 * inv_n;
+    sK1[threadIdx.x] = sRs[threadIdx.x] * p1 * inv_n;
+    sK2[threadIdx.x] = sRs[threadIdx.x] * p2 * inv_n;
   }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cpg;
-    sh[4 * C + c] = sP1[g];
-    sh[5 * C + c] = sP2[g];
-    if (blockIdx.x == 0) {
-      // parameter gradients: one block per image owns them
+  if (blockIdx.x == 0) {
+    // parameter gradients: one block per image owns them
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
       const float s1 = S[2 * c], s2 = S[2 * c + 1];
       float sc = 1.0f;
       if (a.film != nullptr) {
@@ -257,15 +256,19 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdDev a) {
     const int cs = first ? a.c0 : a.c1;
     const int cbs = first ? cb : cb - a.c0;
     uint16_t* dst = first ? a.out0 : a.out1;
-    float A[8], Bc[8], Mn[8], Rs[8], K1[8], K2[8];
+    float gp[8], bp[8], rs[2], mr[2], k1[2], k2[2];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      A[j] = sh[cb + j];
-      Bc[j] = sh[C + cb + j];
-      Mn[j] = sh[2 * C + cb + j];
-      Rs[j] = sh[3 * C + cb + j];
-      K1[j] = sh[4 * C + cb + j];
-      K2[j] = sh[5 * C + cb + j];
+      gp[j] = sh[cb + j];
+      bp[j] = sh[C + cb + j];
+    }
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const int g = (cb + 4 * hf) / cpg;
+      rs[hf] = sRs[g];
+      mr[hf] = sMr[g];
+      k1[hf] = sK1[g];
+      k2[hf] = sK2[g];
     }
     const size_t base = static_cast<size_t>(b) * a.HW;
     const int p_end = min((static_cast<int>(blockIdx.x) + 1) * a.P, a.HW);
@@ -290,10 +293,10 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const GnBwdDev a) {
           unpack8(ud[k], a.fmt, d);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
+            const float xh = fmaf(x[j], rs[j >> 2], -mr[j >> 2]);
             float g = d[j];
-            if (a.silu) g *= silu_grad(fmaf(x[j], A[j], Bc[j]));
-            const float xh = (x[j] - Mn[j]) * Rs[j];
-            o[j] = fmaf(g, A[j], -K1[j]) - xh * K2[j];
+            if (a.silu) g *= silu_grad(fmaf(gp[j], xh, bp[j]));
+            o[j] = fmaf(g * gp[j], rs[j >> 2], -k1[j >> 2]) - xh * k2[j >> 2];
           }
           if (a.add0 != nullptr) {
             float t[8];
@@ -433,18 +436,30 @@ __global__ void __launch_bounds__(256) wgrad_1ch_kernel(const uint16_t* __restri
     for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
   const int64_t total = static_cast<int64_t>(B) * H * W;
   const int64_t p_end = min(static_cast<int64_t>(blockIdx.x + 1) * P, total);
-  for (int64_t p = static_cast<int64_t>(blockIdx.x) * P + pl; p < p_end; p += lanes) {
-    const int x = static_cast<int>(p % W);
-    const int y = static_cast<int>((p / W) % H);
-    const int64_t nb = p / (static_cast<int64_t>(W) * H) * H * W;
-    float f[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(act + p * C + v * 8)), fmt, f);
+  constexpr int kU = 4;  // pixels in flight per thread
+  for (int64_t p0 = static_cast<int64_t>(blockIdx.x) * P + pl; p0 < p_end; p0 += kU * lanes) {
+    uint4 u[kU];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const int yy = y + sgn * (t / 3 - 1), xx = x + sgn * (t % 3 - 1);
-      const float im = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(img + nb + static_cast<int64_t>(yy) * W + xx) : 0.f;
+    for (int k = 0; k < kU; ++k) {
+      const int64_t p = p0 + k * lanes;
+      if (p < p_end) u[k] = __ldg(reinterpret_cast<const uint4*>(act + p * C + v * 8));
+    }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(f[j], im, acc[t][j]);
+    for (int k = 0; k < kU; ++k) {
+      const int64_t p = p0 + k * lanes;
+      if (p >= p_end) continue;
+      const int x = static_cast<int>(p % W);
+      const int y = static_cast<int>((p / W) % H);
+      const int64_t nb = p / (static_cast<int64_t>(W) * H) * H * W;
+      float f[8];
+      unpack8(u[k], fmt, f);
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int yy = y + sgn * (t / 3 - 1), xx = x + sgn * (t % 3 - 1);
+        const float im = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(img + nb + static_cast<int64_t>(yy) * W + xx) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(f[j], im, acc[t][j]);
+      }
     }
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -465,18 +480,21 @@ __global__ void __launch_bounds__(256) wgrad_1ch_kernel(const uint16_t* __restri
   }
 }
 
+// One thread owns one 8-channel vector (fixed for its whole grid-stride loop) and keeps its 72 weights in registers.
 __global__ void __launch_bounds__(256) head_bwd_data_kernel(const float* __restrict__ dout, const float* __restrict__ w,
                                                             uint16_t* __restrict__ dact, int B, int H, int W, int C,
                                                             int fmt) {
-  extern __shared__ float sw[];  // [C][9]
-  for (int i = threadIdx.x; i < C * 9; i += blockDim.x) sw[i] = w[i];
-  __syncthreads();
-  const int nvec = C >> 3;
-  const int64_t total = static_cast<int64_t>(B) * H * W * nvec;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int v = static_cast<int>(i % nvec);
-    const int64_t p = i / nvec;
+  const int nvec = C >> 3;  // divides the block size and therefore the grid stride
+  const int v = threadIdx.x % nvec;
+  float wr[8][9];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wr[j][t] = __ldg(w + (v * 8 + j) * 9 + t);
+  const int64_t npix = static_cast<int64_t>(B) * H * W;
+  const int lanes = blockDim.x / nvec;
+  for (int64_t p = static_cast<int64_t>(blockIdx.x) * lanes + threadIdx.x / nvec; p < npix;
+       p += static_cast<int64_t>(gridDim.x) * lanes) {
     const int x = static_cast<int>(p % W);
     const int y = static_cast<int>((p / W) % H);
     const int64_t nb = p / (static_cast<int64_t>(W) * H) * H * W;
@@ -486,11 +504,9 @@ __global__ void __launch_bounds__(256) head_bwd_data_kernel(const float* __restr
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       const int yy = y - (t / 3 - 1), xx = x - (t % 3 - 1);
-      if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-        const float d = __ldg(dout + nb + static_cast<int64_t>(yy) * W + xx);
+      const float d = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(dout + nb + static_cast<int64_t>(yy) * W + xx) : 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = fmaf(d, sw[(v * 8 + j) * 9 + t], o[j]);
-      }
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(d, wr[j][t], o[j]);
     }
     *reinterpret_cast<uint4*>(dact + p * C + v * 8) = pack8(o, fmt);
   }
@@ -545,35 +561,59 @@ __global__ void __launch_bounds__(128) linear_bwd_input_kernel(const float* __re
   }
 }
 
-// thread = one input column i, 4 output rows o; loop over the batch
+// Block = 128 input columns x 32 output rows; the batch rows of dy and act(x) for the tile are staged in shared
+// memory once, then every thread (one column) accumulates its 32 outputs with float4 broadcast reads of dy.
+constexpr int kLwO = 32;
+constexpr int kLwBMax = 64;
 __global__ void __launch_bounds__(128) linear_bwd_weight_kernel(const float* __restrict__ dy, int dy_stride,
                                                                 const float* __restrict__ x, int x_stride, int act_x,
                                                                 float* __restrict__ dw, float* __restrict__ db, int B,
                                                                 int I, int O) {
+  __shared__ __align__(16) float sdy[kLwBMax][kLwO];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int o0 = blockIdx.y * 4;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  float bacc[4] = {0.f, 0.f, 0.f, 0.f};
-  if (i >= I) return;
-  for (int b = 0; b < B; ++b) {
-    float xv = x[static_cast<size_t>(b) * x_stride + i];
-    if (act_x) xv = silu_precise(xv);
+  const int o0 = blockIdx.y * kLwO;
+  float acc[kLwO];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (o0 + k < O) {
-        const float d = __ldg(dy + static_cast<size_t>(b) * dy_stride + o0 + k);
-        acc[k] = fmaf(d, xv, acc[k]);
-        bacc[k] += d;
+  for (int k = 0; k < kLwO; ++k) acc[k] = 0.f;
+  for (int b0 = 0; b0 < B; b0 += kLwBMax) {
+    const int nb = min(kLwBMax, B - b0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < nb * kLwO; e += blockDim.x) {
+      const int bb = e / kLwO, oo = e % kLwO;
+      sdy[bb][oo] = (o0 + oo < O) ? dy[static_cast<size_t>(b0 + bb) * dy_stride + o0 + oo] : 0.f;
+    }
+    __syncthreads();
+    if (i < I) {
+      for (int bb = 0; bb < nb; ++bb) {
+        float xv = x[static_cast<size_t>(b0 + bb) * x_stride + i];
+        if (act_x) xv = silu_precise(xv);
+#pragma unroll
+        for (int k = 0; k < kLwO; k += 4) {
+          const float4 d = *reinterpret_cast<const float4*>(&sdy[bb][k]);
+          acc[k] = fmaf(d.x, xv, acc[k]);
+          acc[k + 1] = fmaf(d.y, xv, acc[k + 1]);
+          acc[k + 2] = fmaf(d.z, xv, acc[k + 2]);
+          acc[k + 3] = fmaf(d.w, xv, acc[k + 3]);
+        }
       }
     }
-  }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    if (o0 + k < O) {
-      dw[static_cast<size_t>(o0 + k) * I + i] = acc[k];
-      if (i == 0 && db != nullptr) db[o0 + k] = bacc[k];
+    if (db != nullptr && blockIdx.x == 0 && threadIdx.x < kLwO && o0 + threadIdx.x < O) {
+      float t = b0 == 0 ? 0.f : db[o0 + threadIdx.x];
+      for (int bb = 0; bb < nb; ++bb) t += sdy[bb][threadIdx.x];
+      db[o0 + threadIdx.x] = t;
     }
   }
+  if (i < I) {
+#pragma unroll
+    for (int k = 0; k < kLwO; ++k)
+      if (o0 + k < O) dw[static_cast<size_t>(o0 + k) * I + i] = acc[k];
+  }
+}
+
+__global__ void mul_silu_grad_kernel(float* __restrict__ dx, const float* __restrict__ z, int64_t n) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    dx[i] *= silu_grad_precise(z[i]);
 }
 
 __global__ void copy_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n) {
@@ -582,20 +622,32 @@ __global__ void copy_f32_kernel(const float* __restrict__ src, float* __restrict
     dst[i] = src[i];
 }
 
+// Chunks per image for the GroupNorm backward kernels: the grid (chunks x B blocks, 3 resident per SM) should fill
+// whole waves - at 10 chunks x 64 images the second wave ran 44 % full and cost a quarter of the kernel's time.
 int pick_blocks(int B, int HW, int lanes) {
-  int chunks = (4 * device_sm_count() + B - 1) / B;
-  const int max_chunks = (HW + 4 * lanes - 1) / (4 * lanes);
-  if (chunks > max_chunks) chunks = max_chunks;
-  if (chunks < 1) chunks = 1;
-  return chunks;
+  const int slots = 3 * device_sm_count();
+  int max_chunks = HW / (24 * lanes);
+  if (max_chunks > 64) max_chunks = 64;
+  if (max_chunks < 1) max_chunks = 1;
+  int best = 1;
+  double best_eff = 0.0;
+  for (int ch = 1; ch <= max_chunks; ++ch) {
+    const int blocks = ch * B;
+    const int waves = (blocks + slots - 1) / slots;
+    const double eff = static_cast<double>(blocks) / (static_cast<double>(waves) * slots);
+    if (eff > best_eff + 0.02 || (eff >= best_eff && ch <= 2 * best)) {
+      best_eff = eff > best_eff ? eff : best_eff;
+      best = ch;
+    }
+  }
+  return best;
 }
 
 }  // namespace
 
 int launch_gn_bwd(const GnBwdArgs& g, cudaStream_t stream) {
   const int C = g.x.C();
-  if (C % 32 != 0 || C % 8 != 0 || 256 % (C / 8) != 0 && (C / 8) > 256)
-    return fail(kUnsupported, "gn_bwd: unsupported channel count");
+  if (C % 32 != 0 || C / 8 > 256) return fail(kUnsupported, "gn_bwd: unsupported channel count");
   if ((C / kGnGroups) % 4 != 0) return fail(kUnsupported, "gn_bwd: group size must be a multiple of 4");
   if (g.x.c0 % 8 != 0 || g.x.c1 % 8 != 0) return fail(kUnsupported, "gn_bwd: concat members must be multiples of 8");
   if (!g.stats0 || (g.x.c1 > 0 && !g.stats1) || !g.dy || !g.sums || !g.out0 || (g.x.c1 > 0 && !g.out1) ||
@@ -636,11 +688,11 @@ int launch_gn_bwd(const GnBwdArgs& g, cudaStream_t stream) {
   a.P = (a.HW + chunks - 1) / chunks;
   const dim3 grid((a.HW + a.P - 1) / a.P, g.B);
   size_t sh_reduce = static_cast<size_t>(lanes) * C * 2 * sizeof(float);
-  if (sh_reduce < static_cast<size_t>(4) * C * sizeof(float)) sh_reduce = static_cast<size_t>(4) * C * sizeof(float);
+  if (sh_reduce < static_cast<size_t>(2) * C * sizeof(float)) sh_reduce = static_cast<size_t>(2) * C * sizeof(float);
   gn_bwd_reduce_kernel<<<grid, threads, sh_reduce, stream>>>(a);
   CDDPM_TRY(check_launch("gn_bwd_reduce_kernel"));
   size_t sh_apply = static_cast<size_t>(lanes) * C * sizeof(float);
-  if (sh_apply < static_cast<size_t>(6) * C * sizeof(float)) sh_apply = static_cast<size_t>(6) * C * sizeof(float);
+  if (sh_apply < static_cast<size_t>(2) * C * sizeof(float)) sh_apply = static_cast<size_t>(2) * C * sizeof(float);
   gn_bwd_apply_kernel<<<grid, threads, sh_apply, stream>>>(a);
   return check_launch("gn_bwd_apply_kernel");
 }
@@ -691,11 +743,11 @@ int launch_wgrad_1ch(const void* act, const float* img, float* out, int B, int H
 
 int launch_head_bwd_data(const float* dout, const float* w, void* dact, int B, int H, int W, int C, int fmt,
                          cudaStream_t stream) {
-  if (C % 8 != 0) return fail(kUnsupported, "head_bwd_data: C must be a multiple of 8");
+  if (C % 8 != 0 || 256 % (C / 8) != 0) return fail(kUnsupported, "head_bwd_data: unsupported channel count");
   const int64_t total = static_cast<int64_t>(B) * H * W * (C / 8);
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > 8 * device_sm_count()) blocks = 8 * device_sm_count();
-  head_bwd_data_kernel<<<blocks, 256, static_cast<size_t>(C) * 9 * sizeof(float), stream>>>(
+  head_bwd_data_kernel<<<blocks, 256, 0, stream>>>(
       dout, w, reinterpret_cast<uint16_t*>(dact), B, H, W, C, fmt);
   return check_launch("head_bwd_data_kernel");
 }
@@ -710,9 +762,17 @@ int launch_linear_bwd_input(const float* dy, int dy_stride, const float* w32, co
 
 int launch_linear_bwd_weight(const float* dy, int dy_stride, const float* x, int x_stride, int act_x, float* dw,
                              float* db, int B, int I, int O, cudaStream_t stream) {
-  const dim3 grid((I + 127) / 128, (O + 3) / 4);
+  const dim3 grid((I + 127) / 128, (O + kLwO - 1) / kLwO);
   linear_bwd_weight_kernel<<<grid, 128, 0, stream>>>(dy, dy_stride, x, x_stride, act_x, dw, db, B, I, O);
   return check_launch("linear_bwd_weight_kernel");
+}
+
+int launch_mul_silu_grad(float* dx, const float* z, int64_t n, cudaStream_t stream) {
+  int blocks = static_cast<int>((n + 255) / 256);
+  if (blocks > 1024) blocks = 1024;
+  if (blocks < 1) blocks = 1;
+  mul_silu_grad_kernel<<<blocks, 256, 0, stream>>>(dx, z, n);
+  return check_launch("mul_silu_grad_kernel");
 }
 
 int launch_copy_f32(const float* src, float* dst, int64_t n, cudaStream_t stream) {

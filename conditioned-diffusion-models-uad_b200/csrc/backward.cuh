@@ -61,6 +61,8 @@ int launch_linear_bwd_input(const float* dy, int dy_stride, const float* w32, co
 //   dw[o][i] = sum_b dy[b][o] * act(x[b][i]);  db[o] = sum_b dy[b][o]     (act: 0 none, 1 SiLU)
 int launch_linear_bwd_weight(const float* dy, int dy_stride, const float* x, int x_stride, int act_x, float* dw,
                              float* db, int B, int I, int O, cudaStream_t stream);
+// dx[i] *= silu'(z[i])
+int launch_mul_silu_grad(float* dx, const float* z, int64_t n, cudaStream_t stream);
 // dst[i] = src[i] for i < n (fp32), plain device copy helper that is graph-capturable
 int launch_copy_f32(const float* src, float* dst, int64_t n, cudaStream_t stream);
 

@@ -64,6 +64,13 @@ __device__ __forceinline__ uint64_t umma_desc_mn128(uint32_t smem_addr, uint32_t
   return d;
 }
 
+// fire-and-forget vector reduction (sm_90+): four consecutive floats per instruction
+__device__ __forceinline__ void red_add_v4(float* addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(__uint_as_float(a)),
+               "f"(__uint_as_float(b)), "f"(__uint_as_float(c)), "f"(__uint_as_float(d))
+               : "memory");
+}
+
 __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_constant__ WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -193,7 +200,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
           tmem_ld_32x32(taddr + c * 32, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(dst + c * 32 + j, __uint_as_float(v[j]));
+          for (int j = 0; j < 32; j += 4) red_add_v4(dst + c * 32 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
       }
     }

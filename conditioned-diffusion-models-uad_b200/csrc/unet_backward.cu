@@ -466,22 +466,51 @@ int UNetEngine::plan_backward(int B) {
       CDDPM_TRY(offset_of("label_emb.2.weight", &o_le2w));
       CDDPM_TRY(offset_of("label_emb.2.bias", &o_le2b));
     }
-    // recompute the pre-activations of the two MLPs in fp32 (the forward keeps only SiLU(emb) in 16 bits)
-    bwd_ops_.push_back([=](cudaStream_t s) {
-      CDDPM_TRY(launch_timestep_embedding(self->cur_t_, sinus, B, mc, s));
-      CDDPM_TRY(launch_linear_ex(sinus, mc, self->te0_w, self->te0_b, z1t, Hd, B, mc, Hd, 0, 0, s));
-      CDDPM_TRY(launch_linear_ex(z1t, Hd, self->te2_w, self->te2_b, z2, E, B, Hd, Hd, 1, 0, s));
-      if (nc > 0) {
-        CDDPM_TRY(launch_linear_ex(self->cur_cond_, nc, self->le0_w, self->le0_b, z1c, Hd, B, nc, Hd, 0, 0, s));
-        CDDPM_TRY(launch_linear_ex(z1c, Hd, self->le2_w, self->le2_b, z2 + Hd, E, B, Hd, Hd, 1, 0, s));
-      }
-      return static_cast<int>(kOk);
-    });
+    // recompute the pre-activations of the two MLPs (the forward keeps only SiLU(.) in 16 bits): the same tensor-core
+    // GEMMs as the forward, without the activation, fp32 out
+    if (sin16_ == nullptr) return fail(kUnsupported, "backward: needs the tensor-core embedding path");
+    auto push_flat = [&](const void* in16, int I, const void* w16, const float* bias, float* out, int O, int stride,
+                         int col) {
+      if (st != kOk) return;
+      ConvDesc d;
+      d.num_src = 1;
+      d.src[0] = in16;
+      d.src_c[0] = I;
+      d.src_taps[0] = 1;
+      d.flat_rows = B;
+      d.Cout = O;
+      d.wpacked = w16;
+      d.bias = bias;
+      d.out = out;
+      d.out_is_f32 = 1;
+      d.ab_format = fmt;
+      d.out_stride = stride;
+      d.out_col_off = col;
+      auto p = std::make_shared<ConvIgemmParams>();
+      st = build_conv_params(d, p.get());
+      if (st != kOk) return;
+      bwd_ops_.push_back([p](cudaStream_t s) { return launch_conv_igemm(*p, s); });
+    };
+    bwd_ops_.push_back([=](cudaStream_t s) { return launch_timestep_embedding(self->cur_t_, sinus, B, mc, s); });
+    push_flat(sin16_, mc, te0_w16, te0_b, z1t, Hd, Hd, 0);
+    push_flat(hid16_, Hd, te2_w16, te2_b, z2, Hd, E, 0);
+    if (nc > 0) {
+      push_flat(cond16_, nc, le0_w16, le0_b, z1c, Hd, Hd, 0);
+      push_flat(hidc16_, Hd, le2_w16, le2_b, z2, Hd, E, Hd);
+    }
+    CDDPM_TRY(st);
     // FiLM projection: film = SiLU(z2) Wf^T + bf.  Every emb_layers.1 parameter is a row block of Wf.
+    // d SiLU(z2) = dfilm Wf: one tensor-core GEMM over the transposed panel (K = all 2 * sum(cout) FiLM outputs)
     const int ftot = film_total_;
-    bwd_ops_.push_back([=](cudaStream_t s) {
-      return launch_linear_bwd_input(dfilm, ftot, nullptr, self->film_w16, fmt, dz2, E, z2, E, B, E, ftot, s);
-    });
+    {
+      void* q = nullptr;
+      CDDPM_TRY(balloc(&q, static_cast<size_t>(B) * ftot * 2));
+      void* dfilm16 = q;
+      bwd_ops_.push_back([=](cudaStream_t s) { return launch_to16(dfilm, dfilm16, B * ftot, fmt, s); });
+      push_flat(dfilm16, ftot, film_w16t, nullptr, dz2, E, E, 0);
+      CDDPM_TRY(st);
+      bwd_ops_.push_back([=](cudaStream_t s) { return launch_mul_silu_grad(dz2, z2, static_cast<int64_t>(B) * E, s); });
+    }
     for (const ResLayer& L : res_) {
       int64_t ow = 0, ob = 0;
       CDDPM_TRY(offset_of(L.prefix + ".emb_layers.1.weight", &ow));

@@ -132,6 +132,8 @@ int UNetEngine::add_res(const std::string& prefix, int c0, int c1, int cout, int
     CDDPM_TRY(add_param(prefix + ".emb_layers.1.weight", static_cast<int64_t>(2) * cout * E,
                         [=](const float* src, cudaStream_t s) {
                           // rows [off, off + 2*cout) of the 16-bit K-major FiLM panel (a 1x1 "conv" over E channels)
+                          CDDPM_TRY(launch_pack_conv_weight_T(src, 2 * cout, E, 1, 0, E, self->film_w16t,
+                                                              self->film_total_, off, fmt, s));
                           return launch_pack_conv_weight(src, 2 * cout, E, 1, 0, E,
                                                          self->film_w16 + static_cast<size_t>(off) * E, E, 0, fmt, s);
                         }));
@@ -334,6 +336,7 @@ int UNetEngine::build_layers() {
   if (ch != mc) return fail(kUnsupported, "UNet head expects model_channels at the output");
   // concatenated FiLM projection
   CDDPM_TRY(dalloc(&film_w16, static_cast<size_t>(film_total_) * emb_dim_));
+  CDDPM_TRY(dalloc(&film_w16t, static_cast<size_t>(film_total_) * emb_dim_));
   CDDPM_TRY(dalloc(&film_b, static_cast<size_t>(film_total_)));
   return kOk;
 }
@@ -689,6 +692,7 @@ int UNetEngine::plan(int B) {
 
   // ---- embedding: emb_act = SiLU([time_embed(sin(t)) | label_emb(cond)]); film = emb_layers(emb_act) for all blocks
   const bool gemm_embed = (mc % 64 == 0) && (half_dim_ % 64 == 0) && (cfg_.num_classes % 64 == 0);
+  sin16_ = hid16_ = cond16_ = hidc16_ = nullptr;
   if (gemm_embed) {
     // the four small linears as tensor-core GEMMs with a SiLU epilogue, 16-bit hand-off between them
     uint16_t *sin16 = nullptr, *hid16 = nullptr, *hidc16 = nullptr, *cond16 = nullptr;
@@ -700,6 +704,9 @@ int UNetEngine::plan(int B) {
     };
     CDDPM_TRY(h16alloc(&sin16, static_cast<size_t>(B) * mc));
     CDDPM_TRY(h16alloc(&hid16, static_cast<size_t>(B) * half_dim_));
+    sin16_ = sin16;
+    hid16_ = hid16;
+    cond16_ = hidc16_ = nullptr;
     auto lin = [&](const uint16_t* in, int I, const uint16_t* w16, const float* bias, uint16_t* out, int O, int stride,
                    int col) -> int {
       ConvDesc d;
@@ -727,6 +734,8 @@ int UNetEngine::plan(int B) {
       const int nc = cfg_.num_classes;
       CDDPM_TRY(h16alloc(&hidc16, static_cast<size_t>(B) * half_dim_));
       CDDPM_TRY(h16alloc(&cond16, static_cast<size_t>(B) * nc));
+      cond16_ = cond16;
+      hidc16_ = hidc16;
       ops_.push_back([=](cudaStream_t s) {
         if (cur_cond_ == nullptr) return fail(kInvalidArgument, "conditioned UNet called without cond");
         return launch_to16(cur_cond_, cond16, B * nc, fmt, s);

@@ -139,6 +139,8 @@ class UNetEngine {
   float *le0_w = nullptr, *le0_b = nullptr, *le2_w = nullptr, *le2_b = nullptr;
   uint16_t *te0_w16 = nullptr, *te2_w16 = nullptr, *le0_w16 = nullptr, *le2_w16 = nullptr;
   uint16_t* film_w16 = nullptr;  // [film_total][emb_dim] 16-bit K-major
+  uint16_t* film_w16t = nullptr; // [emb_dim][film_total]: the panel of the FiLM projection's data gradient
+  uint16_t *sin16_ = nullptr, *hid16_ = nullptr, *cond16_ = nullptr, *hidc16_ = nullptr;  // 16-bit MLP hand-offs
   float* film_b = nullptr;
   uint16_t* emb_act16_ = nullptr;
   float *stem_w = nullptr, *stem_b = nullptr, *head_gn_w = nullptr, *head_gn_b = nullptr, *head_w = nullptr,

@@ -120,6 +120,9 @@ int cddpm_unet_param_count(const cddpm_unet_t* h);
 int cddpm_unet_param_info(const cddpm_unet_t* h, int index, const char** name, int64_t* numel);
 /* Copy / re-layout one fp32 parameter (device pointer, reference shape, contiguous) into the engine. */
 int cddpm_unet_set_param(cddpm_unet_t* h, const char* name, const float* value, int64_t numel, void* stream);
+/* Bulk form of cddpm_unet_set_param: values[i] (device pointer, fp32, reference shape) for parameter i in
+ * cddpm_unet_param_info order; NULL entries are left unchanged.  One call per optimizer step. */
+int cddpm_unet_set_params(cddpm_unet_t* h, const float* const* values, int count, void* stream);
 /* model(x, timesteps, cond): x [B,1,H,W] fp32, t [B] int64, cond [B,num_classes] fp32 or NULL -> out [B,1,H,W] fp32. */
 int cddpm_unet_forward(cddpm_unet_t* h, const float* x, const int64_t* t, const float* cond, float* out, int B,
                        void* stream);
