@@ -145,28 +145,68 @@ class ResNet(nn.Module):
     def _train_forward(self, x):
         """Training-mode forward WITH an autograd tape (batch-statistics BatchNorm, running-stat updates): ~1 % of the
         training step's FLOPs, evaluated with torch's library kernels (cuDNN convolutions under bf16 autocast) — the
-        hand-written engine covers the eval-mode forward only (DESIGN.md §8 lists the encoder backward under "next").
+        hand-written engine covers the eval-mode forward only (DESIGN.md lists the encoder backward under "next").
+        The ~500 small launches of the forward and the backward are replayed as CUDA graphs
+        (torch.cuda.make_graphed_callables, one pair per input shape; CDDPM_ENCODER_GRAPH=0 disables it).
         timm's DropPath(0.05) is not applied (timm is not available to pin it; the oracle stand-in has none either)."""
-        import torch.nn.functional as F
+        import os
 
-        def bn(m, t):
-            return F.batch_norm(t, m.running_mean, m.running_var, m.weight, m.bias, True, m.momentum, m.eps)
+        if os.environ.get("CDDPM_ENCODER_GRAPH", "1") == "0":
+            return _encoder_train_eager(self, x)
+        key = (tuple(x.shape), x.device.index)
+        graphs = self.__dict__.setdefault("_train_graphs", {})
+        if key not in graphs:
+            holder = _EncoderTrainModule(self)
+            # capture runs warm-up iterations: keep them out of the BatchNorm running statistics
+            saved = {k: v.clone() for k, v in self.state_dict().items() if "running_" in k or "num_batches" in k}
+            try:
+                graphs[key] = torch.cuda.make_graphed_callables(holder, (x.detach().float().clone(),))
+            except Exception:  # capture is an optimisation of the library path, never a requirement
+                graphs[key] = None
+            with torch.no_grad():
+                sd = self.state_dict()
+                for k, v in saved.items():
+                    sd[k].copy_(v)
+        fn = graphs[key]
+        if fn is None:
+            return _encoder_train_eager(self, x)
+        return fn(x.detach().float())
 
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            h = F.relu(bn(self.bn1, F.conv2d(x.float(), self.conv1.weight, None, 2, 3)))
-            h = F.max_pool2d(h, 3, 2, 1)
-            for li in range(1, 5):
-                for blk in getattr(self, f"layer{li}"):
-                    idt = h
-                    o = F.relu(bn(blk.bn1, F.conv2d(h, blk.conv1.weight)))
-                    o = F.relu(bn(blk.bn2, F.conv2d(o, blk.conv2.weight, None, blk.conv2.stride, 1)))
-                    o = bn(blk.bn3, F.conv2d(o, blk.conv3.weight))
-                    if blk.downsample is not None:
-                        idt = bn(blk.downsample[1], F.conv2d(h, blk.downsample[0].weight, None, blk.downsample[0].stride))
-                    h = F.relu(o + idt)
-            h = h.mean((2, 3))
-            out = F.linear(h, self.fc.weight, self.fc.bias)
-        return out.float()
+
+class _EncoderTrainModule(nn.Module):
+    """nn.Module face of the eager training forward (make_graphed_callables collects parameters from modules)."""
+
+    def __init__(self, net):
+        super().__init__()
+        self.net = net
+
+    def forward(self, x):
+        return _encoder_train_eager(self.net, x)
+
+
+def _encoder_train_eager(self, x):
+    import torch.nn.functional as F
+
+    def bn(m, t):
+        if m.num_batches_tracked is not None:
+            m.num_batches_tracked.add_(1)
+        return F.batch_norm(t, m.running_mean, m.running_var, m.weight, m.bias, True, m.momentum, m.eps)
+
+    with torch.autocast("cuda", dtype=torch.bfloat16, cache_enabled=False):
+        h = F.relu(bn(self.bn1, F.conv2d(x.float(), self.conv1.weight, None, 2, 3)))
+        h = F.max_pool2d(h, 3, 2, 1)
+        for li in range(1, 5):
+            for blk in getattr(self, f"layer{li}"):
+                idt = h
+                o = F.relu(bn(blk.bn1, F.conv2d(h, blk.conv1.weight)))
+                o = F.relu(bn(blk.bn2, F.conv2d(o, blk.conv2.weight, None, blk.conv2.stride, 1)))
+                o = bn(blk.bn3, F.conv2d(o, blk.conv3.weight))
+                if blk.downsample is not None:
+                    idt = bn(blk.downsample[1], F.conv2d(h, blk.downsample[0].weight, None, blk.downsample[0].stride))
+                h = F.relu(o + idt)
+        h = h.mean((2, 3))
+        out = F.linear(h, self.fc.weight, self.fc.bias)
+    return out.float()
 
 
 class SparK_2D_encoder(nn.Module):

@@ -81,6 +81,9 @@ struct GnBwdDev {
   int P;  // pixels per block
 };
 
+constexpr int kGnU = 4;   // pixels (16-byte loads per tensor) in flight per thread: apply (3-4 tensors)
+constexpr int kGnUr = 6;  // ... reduce (2 tensors)
+
 // Shared prologue.  The forward computed z = gp * xhat + bp with xhat = x * rs - mr (rs = rstd of the channel's group,
 // mr = mean * rstd), gp = gamma * (1 + scale), bp = beta * (1 + scale) + shift.  Per channel we keep (gp, bp); the
 // group constants are shared by each aligned run of four channels (the group size is a multiple of four), which keeps
@@ -122,7 +125,7 @@ __device__ __forceinline__ void gn_bwd_prologue(const GnBwdDev& a, int b, float*
 }
 
 // sums[b][c] = (sum_p g, sum_p g * xhat), g = dy * act'(z)
-__global__ void __launch_bounds__(256, 3) gn_bwd_reduce_kernel(const GnBwdDev a) {
+__global__ void __launch_bounds__(256, 2) gn_bwd_reduce_kernel(const GnBwdDev a) {
   extern __shared__ float sh[];
   __shared__ float sRs[kGnGroups], sMr[kGnGroups];
   const int C = a.c0 + a.c1;
@@ -158,10 +161,10 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_reduce_kernel(const GnBwdDev a)
     }
     const size_t base = static_cast<size_t>(b) * a.HW;
     const int p_end = min((static_cast<int>(blockIdx.x) + 1) * a.P, a.HW);
-    for (int p = blockIdx.x * a.P + pl; p < p_end; p += 2 * lanes) {
-      uint4 ux[2], ud[2];
+    for (int p = blockIdx.x * a.P + pl; p < p_end; p += kGnUr * lanes) {
+      uint4 ux[kGnUr], ud[kGnUr];
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
+      for (int k = 0; k < kGnUr; ++k) {
         const int pk = p + k * lanes;
         if (pk < p_end) {
           ux[k] = __ldg(reinterpret_cast<const uint4*>(src + (base + pk) * cs + cbs));
@@ -169,7 +172,7 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_reduce_kernel(const GnBwdDev a)
         }
       }
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
+      for (int k = 0; k < kGnUr; ++k) {
         if (p + k * lanes < p_end) {
           float x[8], d[8];
           unpack8(ux[k], a.fmt, x);
@@ -204,7 +207,7 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_reduce_kernel(const GnBwdDev a)
 }
 
 // dx = rstd * (gamma' g - (P1 + xhat P2) / N) + add0 + add1
-__global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(const GnBwdDev a) {
+__global__ void __launch_bounds__(256, 2) gn_bwd_apply_kernel(const GnBwdDev a) {
   extern __shared__ float sh[];  // gp, bp (per channel), later the column-sum scratch
   __shared__ float sRs[kGnGroups], sMr[kGnGroups], sK1[kGnGroups], sK2[kGnGroups];
   const int C = a.c0 + a.c1;
@@ -272,10 +275,10 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(const GnBwdDev a) 
     }
     const size_t base = static_cast<size_t>(b) * a.HW;
     const int p_end = min((static_cast<int>(blockIdx.x) + 1) * a.P, a.HW);
-    for (int p = blockIdx.x * a.P + pl; p < p_end; p += 2 * lanes) {
-      uint4 ux[2], ud[2], u0[2], u1[2];
+    for (int p = blockIdx.x * a.P + pl; p < p_end; p += kGnU * lanes) {
+      uint4 ux[kGnU], ud[kGnU], u0[kGnU], u1[kGnU];
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
+      for (int k = 0; k < kGnU; ++k) {
         const int pk = p + k * lanes;
         if (pk < p_end) {
           ux[k] = __ldg(reinterpret_cast<const uint4*>(src + (base + pk) * cs + cbs));
@@ -285,7 +288,7 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(const GnBwdDev a) 
         }
       }
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
+      for (int k = 0; k < kGnU; ++k) {
         const int pk = p + k * lanes;
         if (pk < p_end) {
           float x[8], d[8], o[8];
@@ -622,10 +625,10 @@ __global__ void copy_f32_kernel(const float* __restrict__ src, float* __restrict
     dst[i] = src[i];
 }
 
-// Chunks per image for the GroupNorm backward kernels: the grid (chunks x B blocks, 3 resident per SM) should fill
+// Chunks per image for the GroupNorm backward kernels: the grid (chunks x B blocks, 2 resident per SM) should fill
 // whole waves - at 10 chunks x 64 images the second wave ran 44 % full and cost a quarter of the kernel's time.
 int pick_blocks(int B, int HW, int lanes) {
-  const int slots = 3 * device_sm_count();
+  const int slots = 2 * device_sm_count();
   int max_chunks = HW / (24 * lanes);
   if (max_chunks > 64) max_chunks = 64;
   if (max_chunks < 1) max_chunks = 1;

@@ -213,3 +213,44 @@ def test_global_threshold_world_size_2_gloo(tmp_path):
     outs = [p.communicate(timeout=180)[0].decode() for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+_GLOO_TRAIN_WORKER = r"""
+import os, sys
+import torch, torch.distributed as dist
+sys.path[:0] = [os.environ["CDDPM_ROOT"], os.path.join(os.environ["CDDPM_ROOT"], "conditioned-diffusion-models-uad_b200")]
+from cddpm.dist_train import sync_gradients
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+torch.manual_seed(0)
+m = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Linear(16, 4), torch.nn.Linear(4, 2))
+# the first two layers get gradients that are views of ONE flat buffer (what the UNet engine's backward returns),
+# the last one a loose tensor (what torch autograd returns for the encoder)
+flat = torch.arange(8 * 16 + 16 + 16 * 4 + 4, dtype=torch.float32) * (rank + 1)
+off = 0
+for p in list(m[0].parameters()) + list(m[1].parameters()):
+    p.grad = flat[off:off + p.numel()].view(p.shape); off += p.numel()
+for p in m[2].parameters():
+    p.grad = torch.full_like(p, float(rank + 1))
+calls = sync_gradients(m)
+assert calls == 2, calls
+want = torch.arange(flat.numel(), dtype=torch.float32) * 1.5   # mean of x1 and x2
+assert torch.equal(flat, want)
+assert torch.equal(m[0].weight.grad.flatten(), want[:128])
+for p in m[2].parameters():
+    assert torch.equal(p.grad, torch.full_like(p, 1.5))
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_gradient_sync_world_size_2_gloo(tmp_path):
+    """Data-parallel training: the engine's flat gradient buffer travels as one all-reduce, the rest as one more."""
+    script = tmp_path / "train_worker.py"
+    script.write_text(_GLOO_TRAIN_WORKER)
+    env = dict(os.environ, CDDPM_ROOT=ROOT, MASTER_ADDR="127.0.0.1", MASTER_PORT="29517", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0].decode() for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
