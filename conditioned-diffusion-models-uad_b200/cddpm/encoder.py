@@ -185,7 +185,14 @@ class _EncoderTrainModule(nn.Module):
 
 
 def _encoder_train_eager(self, x):
+    import os
+
     import torch.nn.functional as F
+
+    nhwc = os.environ.get("CDDPM_ENCODER_NHWC", "1") != "0"
+
+    def cl(w):  # channels-last weights keep cuDNN on its NHWC tensor-core kernels (no layout transposes per layer)
+        return w.contiguous(memory_format=torch.channels_last) if nhwc else w
 
     def bn(m, t):
         if m.num_batches_tracked is not None:
@@ -193,16 +200,19 @@ def _encoder_train_eager(self, x):
         return F.batch_norm(t, m.running_mean, m.running_var, m.weight, m.bias, True, m.momentum, m.eps)
 
     with torch.autocast("cuda", dtype=torch.bfloat16, cache_enabled=False):
-        h = F.relu(bn(self.bn1, F.conv2d(x.float(), self.conv1.weight, None, 2, 3)))
+        x = x.float()
+        if nhwc:
+            x = x.contiguous(memory_format=torch.channels_last)
+        h = F.relu(bn(self.bn1, F.conv2d(x, cl(self.conv1.weight), None, 2, 3)))
         h = F.max_pool2d(h, 3, 2, 1)
         for li in range(1, 5):
             for blk in getattr(self, f"layer{li}"):
                 idt = h
-                o = F.relu(bn(blk.bn1, F.conv2d(h, blk.conv1.weight)))
-                o = F.relu(bn(blk.bn2, F.conv2d(o, blk.conv2.weight, None, blk.conv2.stride, 1)))
-                o = bn(blk.bn3, F.conv2d(o, blk.conv3.weight))
+                o = F.relu(bn(blk.bn1, F.conv2d(h, cl(blk.conv1.weight))))
+                o = F.relu(bn(blk.bn2, F.conv2d(o, cl(blk.conv2.weight), None, blk.conv2.stride, 1)))
+                o = bn(blk.bn3, F.conv2d(o, cl(blk.conv3.weight)))
                 if blk.downsample is not None:
-                    idt = bn(blk.downsample[1], F.conv2d(h, blk.downsample[0].weight, None, blk.downsample[0].stride))
+                    idt = bn(blk.downsample[1], F.conv2d(h, cl(blk.downsample[0].weight), None, blk.downsample[0].stride))
                 h = F.relu(o + idt)
         h = h.mean((2, 3))
         out = F.linear(h, self.fc.weight, self.fc.bias)

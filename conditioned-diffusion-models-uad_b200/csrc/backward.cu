@@ -571,10 +571,16 @@ constexpr int kLwBMax = 64;
 __global__ void __launch_bounds__(128) linear_bwd_weight_kernel(const float* __restrict__ dy, int dy_stride,
                                                                 const float* __restrict__ x, int x_stride, int act_x,
                                                                 float* __restrict__ dw, float* __restrict__ db, int B,
-                                                                int I, int O) {
+                                                                int I, int O, const int64_t* __restrict__ tile_w_off,
+                                                                const int64_t* __restrict__ tile_b_off) {
   __shared__ __align__(16) float sdy[kLwBMax][kLwO];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int o0 = blockIdx.y * kLwO;
+  if (tile_w_off != nullptr) {
+    // rows [o0, o0 + 32) of the concatenated matrix live at their own offsets of the gradient buffer
+    dw += tile_w_off[blockIdx.y] - static_cast<int64_t>(o0) * I;
+    db += tile_b_off[blockIdx.y] - o0;
+  }
   float acc[kLwO];
 #pragma unroll
   for (int k = 0; k < kLwO; ++k) acc[k] = 0.f;
@@ -766,7 +772,18 @@ int launch_linear_bwd_input(const float* dy, int dy_stride, const float* w32, co
 int launch_linear_bwd_weight(const float* dy, int dy_stride, const float* x, int x_stride, int act_x, float* dw,
                              float* db, int B, int I, int O, cudaStream_t stream) {
   const dim3 grid((I + 127) / 128, (O + kLwO - 1) / kLwO);
-  linear_bwd_weight_kernel<<<grid, 128, 0, stream>>>(dy, dy_stride, x, x_stride, act_x, dw, db, B, I, O);
+  linear_bwd_weight_kernel<<<grid, 128, 0, stream>>>(dy, dy_stride, x, x_stride, act_x, dw, db, B, I, O, nullptr,
+                                                     nullptr);
+  return check_launch("linear_bwd_weight_kernel");
+}
+
+int launch_linear_bwd_weight_tiled(const float* dy, int dy_stride, const float* x, int x_stride, int act_x,
+                                   float* grads, const int64_t* tile_w_off, const int64_t* tile_b_off, int B, int I,
+                                   int O, cudaStream_t stream) {
+  if (O % kLwO != 0) return fail(kInvalidArgument, "linear_bwd_weight_tiled: rows must come in tiles of 32");
+  const dim3 grid((I + 127) / 128, O / kLwO);
+  linear_bwd_weight_kernel<<<grid, 128, 0, stream>>>(dy, dy_stride, x, x_stride, act_x, grads, grads, B, I, O,
+                                                     tile_w_off, tile_b_off);
   return check_launch("linear_bwd_weight_kernel");
 }
 

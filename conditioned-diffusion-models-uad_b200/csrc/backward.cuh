@@ -61,6 +61,11 @@ int launch_linear_bwd_input(const float* dy, int dy_stride, const float* w32, co
 //   dw[o][i] = sum_b dy[b][o] * act(x[b][i]);  db[o] = sum_b dy[b][o]     (act: 0 none, 1 SiLU)
 int launch_linear_bwd_weight(const float* dy, int dy_stride, const float* x, int x_stride, int act_x, float* dw,
                              float* db, int B, int I, int O, cudaStream_t stream);
+// Same over the row-wise concatenation of several Linear layers (the FiLM projection): rows [32 t, 32 t + 32) of the
+// weight gradient go to grads + tile_w_off[t] (row-major [..][I]), their bias gradients to grads + tile_b_off[t].
+int launch_linear_bwd_weight_tiled(const float* dy, int dy_stride, const float* x, int x_stride, int act_x,
+                                   float* grads, const int64_t* tile_w_off, const int64_t* tile_b_off, int B, int I,
+                                   int O, cudaStream_t stream);
 // dx[i] *= silu'(z[i])
 int launch_mul_silu_grad(float* dx, const float* z, int64_t n, cudaStream_t stream);
 // dst[i] = src[i] for i < n (fp32), plain device copy helper that is graph-capturable

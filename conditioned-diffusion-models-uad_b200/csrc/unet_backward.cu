@@ -9,6 +9,8 @@
 //   attention         - attention_bwd.cu.
 #include <string.h>
 
+#include <vector>
+
 #include "attention.cuh"
 #include "backward.cuh"
 #include "conv_bwd.cuh"
@@ -511,14 +513,28 @@ int UNetEngine::plan_backward(int B) {
       CDDPM_TRY(st);
       bwd_ops_.push_back([=](cudaStream_t s) { return launch_mul_silu_grad(dz2, z2, static_cast<int64_t>(B) * E, s); });
     }
-    for (const ResLayer& L : res_) {
-      int64_t ow = 0, ob = 0;
-      CDDPM_TRY(offset_of(L.prefix + ".emb_layers.1.weight", &ow));
-      CDDPM_TRY(offset_of(L.prefix + ".emb_layers.1.bias", &ob));
-      const int off = L.film_off, rows = 2 * L.cout;
+    {
+      // all emb_layers.1 weight / bias gradients in ONE launch: per 32-row tile of the concatenated projection, the
+      // offset of those rows inside the flat gradient buffer
+      std::vector<int64_t> tw(ftot / 32), tb(ftot / 32);
+      for (const ResLayer& L : res_) {
+        int64_t ow = 0, ob = 0;
+        CDDPM_TRY(offset_of(L.prefix + ".emb_layers.1.weight", &ow));
+        CDDPM_TRY(offset_of(L.prefix + ".emb_layers.1.bias", &ob));
+        if (L.film_off % 32 != 0 || (2 * L.cout) % 32 != 0) return fail(kUnsupported, "backward: FiLM rows not tiled by 32");
+        for (int r = 0; r < 2 * L.cout; r += 32) {
+          tw[(L.film_off + r) / 32] = ow + static_cast<int64_t>(r) * E;
+          tb[(L.film_off + r) / 32] = ob + r;
+        }
+      }
+      void* q = nullptr;
+      CDDPM_TRY(balloc(&q, tw.size() * 2 * sizeof(int64_t)));
+      int64_t* d_tw = reinterpret_cast<int64_t*>(q);
+      int64_t* d_tb = d_tw + tw.size();
+      CDDPM_CUDA(cudaMemcpy(d_tw, tw.data(), tw.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+      CDDPM_CUDA(cudaMemcpy(d_tb, tb.data(), tb.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
       bwd_ops_.push_back([=](cudaStream_t s) {
-        return launch_linear_bwd_weight(dfilm + off, ftot, z2, E, 1, self->cur_grads_ + ow, self->cur_grads_ + ob, B, E,
-                                        rows, s);
+        return launch_linear_bwd_weight_tiled(dfilm, ftot, z2, E, 1, self->cur_grads_, d_tw, d_tb, B, E, ftot, s);
       });
     }
     // time_embed: z2_t = W2 SiLU(z1_t) + b2, z1_t = W0 sin + b0
