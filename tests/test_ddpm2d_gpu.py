@@ -111,3 +111,40 @@ def test_cpu_module_fails_loudly():
     with pytest.raises(CddpmError):
         with torch.no_grad():
             model(torch.zeros(1, 1, 96, 96))
+
+
+def test_sweep_driver_val_then_test():
+    """train.py:182-237 through cddpm.sweep.test_sweep: the validation stage finds threshold['total'], the test stage
+    consumes it; eval_dict keeps the reference's keys; preds_dict.pkl is written."""
+    import pickle
+    import tempfile
+
+    from cddpm import sweep
+    from oracle.weights import synthetic_volume
+    from src.models.DDPM_2D import DDPM_2D
+
+    full, _ = _full_state_dict()
+    model = DDPM_2D(_cfg(), prefix="t/")
+    model.load_state_dict(full, strict=True)
+    model = model.cuda().eval()
+
+    def loader(stage, seeds):
+        out = []
+        for sd in seeds:
+            v = synthetic_volume(sd, depth=8)
+            out.append({"Dataset": ["Brats21"], "vol": {"data": v["vol"]}, "vol_orig": {"data": v["vol"].clone()},
+                        "seg_orig": {"data": v["seg_orig"]}, "mask_orig": {"data": v["mask_orig"]}, "ID": [f"{stage}{sd}"],
+                        "age": torch.tensor([50]), "stage": stage, "label": torch.tensor([1]), "seg_available": True})
+        return out
+
+    np.random.seed(3)
+    with tempfile.TemporaryDirectory() as d:
+        preds, logs = sweep.test_sweep(model, {"Datamodules_eval.Brats21": (loader("val", [0, 1]), loader("test", [2, 3]))},
+                                       fold=0, log_dir=d)
+        with open(os.path.join(d, "1_preds_dict.pkl"), "rb") as f:
+            assert set(pickle.load(f)) == {"val", "test"}
+    val, test = preds["val"]["Datamodules_eval.Brats21"], preds["test"]["Datamodules_eval.Brats21"]
+    assert len(val["DiceScorePerVol"]) == 2 and len(test["DiceScorePerVol"]) == 2
+    assert np.isfinite(test["DiceScorePerVolMean"]) and np.isfinite(val["AUPRCPerVolMean"])
+    assert "1/Datamodules_eval.Brats21/test/DiceScorePerVolMean" in logs
+    assert not hasattr(model, "threshold")  # deleted after the test stage, as in the reference (utils_eval.py:258-259)

@@ -254,3 +254,64 @@ def test_gradient_sync_world_size_2_gloo(tmp_path):
     outs = [p.communicate(timeout=180)[0].decode() for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+_GLOO_SWEEP_WORKER = r"""
+import os, sys, pickle
+import torch, torch.distributed as dist
+sys.path[:0] = [os.environ["CDDPM_ROOT"], os.path.join(os.environ["CDDPM_ROOT"], "conditioned-diffusion-models-uad_b200")]
+from cddpm import sweep
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+
+class Stub(torch.nn.Module):
+    # the hooks of the LightningModule drop-in, with per-volume and per-slice lists like get_eval_dictionary()
+    def __init__(self):
+        super().__init__(); self.w = torch.nn.Parameter(torch.zeros(1)); self.threshold = {}
+    def on_test_start(self):
+        self.eval_dict = {"IDs": [], "DiceScorePerVol": [], "PerSlice": []}
+    def test_step(self, batch, idx):
+        self.stage = batch["stage"]
+        self.eval_dict["IDs"].append(batch["ID"][0])
+        self.eval_dict["DiceScorePerVol"].append(float(batch["vol"].sum()))
+        self.eval_dict["PerSlice"].extend([idx] * (1 + idx % 2))
+    def on_test_end(self):
+        v = self.eval_dict["DiceScorePerVol"]
+        self.eval_dict["DiceScorePerVolMean"] = sum(v) / len(v)
+        if "val" in self.stage: self.threshold["total"] = max(v)
+
+def loader(stage, n):
+    return [{"ID": [f"{stage}{i}"], "vol": torch.full((2, 2), float(i)), "stage": stage} for i in range(n)]
+
+m = Stub()
+preds, logs = sweep.test_sweep(m, {"Datamodules_eval.Brats21": (loader("val", 5), loader("test", 7))}, fold=0,
+                               log_dir=os.environ["OUT_DIR"])
+ev = preds["test"]["Datamodules_eval.Brats21"]
+assert ev["IDs"] == [f"test{i}" for i in range(7)], ev["IDs"]                       # loader order restored
+assert ev["DiceScorePerVol"] == [4.0 * i for i in range(7)]
+assert sorted(ev["PerSlice"]) == sorted(sum(([i] * (1 + i % 2) for i in range(7)), []))
+assert abs(ev["DiceScorePerVolMean"] - 12.0) < 1e-9                                  # mean over ALL volumes
+assert m.threshold["total"] == 16.0                                                  # val stage: 4 * max(0..4)
+assert logs["1/Datamodules_eval.Brats21/test/DiceScorePerVolMean"] == ev["DiceScorePerVolMean"]
+assert "1/Datamodules_eval.Brats21/val/DiceScorePerVolMean" in logs and not any(type(v) is list for v in logs.values())
+dist.barrier()
+if rank == 0:
+    with open(os.path.join(os.environ["OUT_DIR"], "1_preds_dict.pkl"), "rb") as f:
+        assert set(pickle.load(f)) == {"val", "test"}
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_sharded_test_sweep_world_size_2_gloo(tmp_path):
+    """train.py:182-237 without a Trainer: volumes dealt round-robin to 2 ranks, per-volume lists gathered back in
+    loader order, means over all volumes, val -> test threshold hand-off, preds_dict.pkl on rank 0."""
+    script = tmp_path / "sweep_worker.py"
+    script.write_text(_GLOO_SWEEP_WORKER)
+    env = dict(os.environ, CDDPM_ROOT=ROOT, MASTER_ADDR="127.0.0.1", MASTER_PORT="29519", WORLD_SIZE="2",
+               OUT_DIR=str(tmp_path / "logs"))
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0].decode() for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
