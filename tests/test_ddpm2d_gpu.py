@@ -145,6 +145,6 @@ def test_sweep_driver_val_then_test():
             assert set(pickle.load(f)) == {"val", "test"}
     val, test = preds["val"]["Datamodules_eval.Brats21"], preds["test"]["Datamodules_eval.Brats21"]
     assert len(val["DiceScorePerVol"]) == 2 and len(test["DiceScorePerVol"]) == 2
-    assert np.isfinite(test["DiceScorePerVolMean"]) and np.isfinite(val["AUPRCPerVolMean"])
-    assert "1/Datamodules_eval.Brats21/test/DiceScorePerVolMean" in logs
+    assert np.isfinite(test["DicePerVolMean"]) and np.isfinite(val["AUPRCPerVolMean"])
+    assert "1/Datamodules_eval.Brats21/test/DicePerVolMean" in logs
     assert not hasattr(model, "threshold")  # deleted after the test stage, as in the reference (utils_eval.py:258-259)
