@@ -41,6 +41,36 @@ def _noise_arg(noise: torch.Tensor):
     return noise.float().contiguous(), 0
 
 
+class _LossFunction(torch.autograd.Function):
+    """mean_b(loss[b]) of cddpm_recon_finish with d/d model_out from cddpm_loss_backward (no torch elementwise ops on
+    the tape)."""
+
+    @staticmethod
+    def forward(ctx, model_out, diff, img, x_t, nz, f16, t, reco, alpha, beta):
+        B, hw = model_out.shape[0], model_out[0].numel()
+        mo = model_out.detach().contiguous()
+        loss = torch.empty(B, dtype=torch.float32, device=mo.device)
+        pn = 1 if diff.objective == "pred_noise" else 0
+        l2 = 1 if diff.loss_type == "l2" else 0
+        check(lib().cddpm_recon_finish(ptr(mo), ptr(img), ptr(x_t), ptr(nz), f16, ptr(reco), alpha, beta, ptr(loss),
+                                       ptr(diff.sqrt_one_minus_alphas_cumprod), ptr(diff.p2_loss_weight), ptr(t), 0,
+                                       B, hw, pn, l2, current_stream()), "cddpm_recon_finish")
+        ctx.save_for_backward(mo, img, nz if nz is not None else img, t, diff.p2_loss_weight)
+        ctx.cfg = (f16, pn, l2, nz is not None)
+        return loss.mean()
+
+    @staticmethod
+    def backward(ctx, g):
+        mo, img, nz, t, p2w = ctx.saved_tensors
+        f16, pn, l2, has_nz = ctx.cfg
+        B, hw = mo.shape[0], mo[0].numel()
+        dout = torch.empty_like(mo)
+        g = g.detach().float().reshape(1).contiguous()
+        check(lib().cddpm_loss_backward(ptr(mo), ptr(img), ptr(nz) if has_nz else None, f16, ptr(p2w), ptr(t), ptr(g),
+                                        ptr(dout), B, hw, pn, l2, current_stream()), "cddpm_loss_backward")
+        return (dout,) + (None,) * 9
+
+
 class GaussianDiffusion(nn.Module):
     def __init__(self, model, *, image_size, channels=3, timesteps=1000, sampling_timesteps=None, loss_type="l1",
                  objective="pred_noise", beta_schedule="cosine", p2_loss_weight_gamma=0.0, p2_loss_weight_k=1,
@@ -146,19 +176,9 @@ class GaussianDiffusion(nn.Module):
         nz, f16 = _noise_arg(noise)
         reco = _reco_out if _reco_out is not None else torch.empty_like(x_t)
         if model_out.requires_grad:
-            # training step (cond_DDPM.py:606-645): the loss stays on the autograd tape that ends in the UNet node;
-            # [B,1,H,W] elementwise work, the reconstruction itself comes from the fused kernel without a loss
-            target = noise.float() if self.objective == "pred_noise" else img * 2 - 1
-            diff = model_out - target
-            per = (diff * diff if self.loss_type == "l2" else diff.abs()).flatten(1).mean(1)
-            loss = (per * self.p2_loss_weight.gather(-1, t)).mean()
-            with torch.no_grad():
-                check(lib().cddpm_recon_finish(ptr(model_out.detach()), ptr(img), ptr(x_t), ptr(nz), f16, ptr(reco),
-                                               float(_reco_alpha), float(_reco_beta), None,
-                                               ptr(self.sqrt_one_minus_alphas_cumprod), ptr(self.p2_loss_weight),
-                                               ptr(t), 0, B, hw, 1 if self.objective == "pred_noise" else 0,
-                                               1 if self.loss_type == "l2" else 0, current_stream()),
-                      "cddpm_recon_finish")
+            # training step (cond_DDPM.py:606-645): loss and reconstruction from the fused kernel, recorded as one
+            # autograd node whose backward is cddpm_loss_backward -> the UNet node -> the encoder
+            loss = _LossFunction.apply(model_out, self, img, x_t, nz, f16, t, reco, float(_reco_alpha), float(_reco_beta))
             return loss, reco
         loss = torch.empty(B, dtype=torch.float32, device=x_t.device)
         check(lib().cddpm_recon_finish(ptr(model_out), ptr(img), ptr(x_t), ptr(nz), f16, ptr(reco),

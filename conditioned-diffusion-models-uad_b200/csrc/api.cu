@@ -179,6 +179,13 @@ int cddpm_posterior_step(const float* model_out, const float* x_t, const void* n
                                static_cast<cudaStream_t>(stream));
 }
 
+int cddpm_loss_backward(const float* model_out, const float* img, const void* noise, int noise_f16,
+                        const float* p2_loss_weight, const int64_t* t, const float* grad_loss, float* dout, int B,
+                        int HW, int pred_noise, int l2, void* stream) {
+  return launch_loss_backward(model_out, img, noise, noise_f16, p2_loss_weight, t, grad_loss, dout, B, HW, pred_noise,
+                              l2, static_cast<cudaStream_t>(stream));
+}
+
 int cddpm_recon_finish(const float* model_out, const float* img, const float* x_t, const void* noise, int noise_f16,
                        float* reco, float reco_alpha, float reco_beta, float* loss,
                        const float* sqrt_one_minus_alphas_cumprod, const float* p2_loss_weight, const int64_t* t,

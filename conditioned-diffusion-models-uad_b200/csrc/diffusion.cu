@@ -94,7 +94,34 @@ __global__ void __launch_bounds__(256) recon_finish_kernel(
   if (threadIdx.x == 0 && loss != nullptr) loss[b] = red[0] / static_cast<float>(HW) * p2w[tb];
 }
 
+// d loss / d model_out for loss = mean_b(mean_i |o - target| (or squared) * p2w[t_b]), times the upstream scalar.
+__global__ void __launch_bounds__(256) loss_backward_kernel(
+    const float* __restrict__ model_out, const float* __restrict__ img, const void* __restrict__ noise, int noise_f16,
+    const float* __restrict__ p2w, const int64_t* __restrict__ t, const float* __restrict__ grad_loss,
+    float* __restrict__ dout, int B, int HW, int pred_noise, int l2) {
+  const int b = blockIdx.y;
+  const float scale = grad_loss[0] * p2w[t[b]] / (static_cast<float>(HW) * static_cast<float>(B));
+  const size_t base = static_cast<size_t>(b) * HW;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+    const float o = model_out[base + i];
+    const float target = pred_noise ? load_noise(noise, noise_f16, base + i) : img[base + i] * 2.0f - 1.0f;
+    const float d = o - target;
+    dout[base + i] = scale * (l2 ? 2.0f * d : (d > 0.f ? 1.0f : (d < 0.f ? -1.0f : 0.0f)));
+  }
+}
+
 }  // namespace
+
+int launch_loss_backward(const float* model_out, const float* img, const void* noise, int noise_f16, const float* p2w,
+                         const int64_t* t, const float* grad_loss, float* dout, int B, int HW, int pred_noise, int l2,
+                         cudaStream_t stream) {
+  if (!model_out || !p2w || !t || !grad_loss || !dout) return fail(kInvalidArgument, "loss_backward: null pointer");
+  if (pred_noise ? !noise : !img) return fail(kInvalidArgument, "loss_backward: missing target");
+  dim3 grid((HW + 1023) / 1024, B);
+  loss_backward_kernel<<<grid, 256, 0, stream>>>(model_out, img, noise, noise_f16, p2w, t, grad_loss, dout, B, HW,
+                                                 pred_noise, l2);
+  return check_launch("loss_backward_kernel");
+}
 
 int launch_q_sample(const float* img, const void* noise, int noise_f16, float* out, const float* sqrt_ac,
                     const float* sqrt_1mac, const int64_t* t, int t_shared, int B, int HW, int normalize,

@@ -24,4 +24,9 @@ int launch_recon_finish(const float* model_out, const float* img, const float* x
                         const float* p2w, const int64_t* t, int t_shared, int B, int HW, int pred_noise, int l2,
                         cudaStream_t stream);
 
+// dout = grad_loss[0] * d/d model_out of mean_b(loss[b]) with loss[b] as in launch_recon_finish (training step).
+int launch_loss_backward(const float* model_out, const float* img, const void* noise, int noise_f16, const float* p2w,
+                         const int64_t* t, const float* grad_loss, float* dout, int B, int HW, int pred_noise, int l2,
+                         cudaStream_t stream);
+
 }  // namespace cddpm

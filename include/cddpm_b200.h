@@ -210,6 +210,13 @@ int cddpm_recon_finish(const float* model_out, const float* img, const float* x_
                        const float* sqrt_one_minus_alphas_cumprod, const float* p2_loss_weight, const int64_t* t,
                        int t_shared, int B, int HW, int pred_noise, int l2, void* stream);
 
+/* Backward of the loss of cddpm_recon_finish averaged over the batch (p_losses, cond_DDPM.py:636-645, as differentiated
+ * by DDPM_2D.training_step): dout[b,i] = grad_loss[0] * p2_loss_weight[t_b] / (B*HW) * sign(model_out - target)
+ * (l2: 2 (model_out - target)); target = 2 img - 1 (pred_x0) or the noise (pred_noise).  grad_loss: device scalar. */
+int cddpm_loss_backward(const float* model_out, const float* img, const void* noise, int noise_f16,
+                        const float* p2_loss_weight, const int64_t* t, const float* grad_loss, float* dout, int B,
+                        int HW, int pred_noise, int l2, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Anomaly-scoring tail: _test_step of src/utils/utils_eval.py:18-194.
  * A volume is addressed logically as (y, x, d) = [H, W, D] like the reference's squeezed tensors.  Inputs carry

@@ -172,3 +172,38 @@ def test_training_step_lightning_surface():
         losses.append(float(loss))
     assert all(np.isfinite(losses)), losses
     assert losses[-1] < losses[0], f"loss did not fall: {losses}"
+
+
+@pytest.mark.parametrize("objective,loss_type", [("pred_x0", "l1"), ("pred_noise", "l2")])
+def test_loss_node_matches_torch(objective, loss_type):
+    """cddpm_recon_finish + cddpm_loss_backward as an autograd node vs the same loss written in torch
+    (cond_DDPM.py:636-645)."""
+    from cddpm.diffusion import GaussianDiffusion, _LossFunction, _noise_arg
+
+    _setup()
+
+    class Dummy(torch.nn.Module):
+        def forward(self, x, t, cond=None):
+            return x
+
+    d = GaussianDiffusion(Dummy(), image_size=(32, 32), timesteps=1000, objective=objective, channels=1,
+                          loss_type=loss_type, p2_loss_weight_gamma=0.5, cfg={}).cuda()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    B = 3
+    img = torch.rand(B, 1, 32, 32, device="cuda", generator=g)
+    noise = torch.randn(B, 1, 32, 32, device="cuda", generator=g).half()
+    t = torch.tensor([10, 500, 900], device="cuda")
+    x_t = torch.randn(B, 1, 32, 32, device="cuda", generator=g)
+    mo = torch.randn(B, 1, 32, 32, device="cuda", generator=g, requires_grad=True)
+    nz, f16 = _noise_arg(noise)
+    reco = torch.empty_like(x_t)
+    loss = _LossFunction.apply(mo, d, img, x_t, nz, f16, t, reco, 1.0, 0.0)
+    (loss * 3.0).backward()
+    ref_in = mo.detach().clone().requires_grad_(True)
+    target = noise.float() if objective == "pred_noise" else img * 2 - 1
+    diff = ref_in - target
+    per = (diff * diff if loss_type == "l2" else diff.abs()).flatten(1).mean(1)
+    ref = (per * d.p2_loss_weight.gather(-1, t)).mean()
+    (ref * 3.0).backward()
+    assert abs(float(loss) - float(ref)) <= 1e-6 * max(1.0, abs(float(ref)))
+    assert (mo.grad - ref_in.grad).abs().max().item() <= 1e-7 + 1e-5 * ref_in.grad.abs().max().item()
