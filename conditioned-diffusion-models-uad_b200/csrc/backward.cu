@@ -3,6 +3,9 @@
 #include "backward.cuh"
 
 #include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include "ptx.cuh"
 
 namespace cddpm {
 
@@ -339,6 +342,234 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_apply_kernel(const GnBwdDev a) 
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Ring versions of the two GroupNorm backward kernels.  The register-fed kernels above are latency-bound (ncu: issue
+// slots 45 % busy, DRAM 44 %): a warp issues no loads while it chews through the SiLU' / normalisation math of the
+// pixels it holds.  Here one producer thread streams whole pixel tiles (x | dy | skip-path gradients: contiguous NHWC
+// row ranges) into a shared-memory ring with cp.async.bulk + mbarriers, so the bytes in flight (6 stages x 16-32 KB per
+// SM) no longer depend on registers or on what the 16 consumer warps are doing.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kRingConsumers = 512;
+constexpr int kRingThreads = kRingConsumers + 32;
+constexpr int kRingStages = 6;
+
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))),
+               "l"(gsrc), "r"(bytes), "r"(static_cast<uint32_t>(__cvta_generic_to_shared(bar)))
+               : "memory");
+}
+
+template <bool kApply>
+__global__ void __launch_bounds__(kRingThreads, 1) gn_bwd_ring_kernel(const GnBwdDev a, int TP, int stage_bytes) {
+  extern __shared__ __align__(128) uint8_t ring_raw[];
+  __shared__ float sRs[kGnGroups], sMr[kGnGroups], sK1[kGnGroups], sK2[kGnGroups];
+  __shared__ __align__(8) uint64_t full[kRingStages], empty[kRingStages];
+  const int C = a.c0 + a.c1;
+  const int cpg = C / kGnGroups;
+  const int b = blockIdx.y;
+  uint8_t* ring = ring_raw;
+  float* sh = reinterpret_cast<float*>(ring_raw + static_cast<size_t>(kRingStages) * stage_bytes);  // gp[C], bp[C]
+  const int p_begin = blockIdx.x * a.P;
+  const int p_end = min(p_begin + a.P, a.HW);
+  const int ntiles = (p_end - p_begin + TP - 1) / TP;
+  const size_t base = static_cast<size_t>(b) * a.HW;
+  const int off_x1 = TP * a.c0 * 2;
+  const int off_dy = TP * C * 2;
+  const int off_a0 = 2 * TP * C * 2;
+  const int off_a1 = off_a0 + (a.add0 != nullptr ? TP * C * 2 : 0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool producer = warp == kRingConsumers / 32 && lane == 0;
+  auto issue_tile = [&](int t, int st) {
+    const int ps = p_begin + t * TP;
+    const int np = min(TP, p_end - ps);
+    uint32_t bytes = static_cast<uint32_t>(np) * C * 2 * 2;
+    if (kApply && a.add0 != nullptr) bytes += static_cast<uint32_t>(np) * C * 2;
+    if (kApply && a.add1 != nullptr) bytes += static_cast<uint32_t>(np) * C * 2;
+    mbar_arrive_expect_tx(&full[st], bytes);
+    uint8_t* dst = ring + static_cast<size_t>(st) * stage_bytes;
+    bulk_load(dst, a.p0 + (base + ps) * a.c0, static_cast<uint32_t>(np) * a.c0 * 2, &full[st]);
+    if (a.c1 > 0) bulk_load(dst + off_x1, a.p1 + (base + ps) * a.c1, static_cast<uint32_t>(np) * a.c1 * 2, &full[st]);
+    bulk_load(dst + off_dy, a.dy + (base + ps) * C, static_cast<uint32_t>(np) * C * 2, &full[st]);
+    if (kApply && a.add0 != nullptr)
+      bulk_load(dst + off_a0, a.add0 + (base + ps) * C, static_cast<uint32_t>(np) * C * 2, &full[st]);
+    if (kApply && a.add1 != nullptr)
+      bulk_load(dst + off_a1, a.add1 + (base + ps) * C, static_cast<uint32_t>(np) * C * 2, &full[st]);
+  };
+  if (producer) {
+    for (int i = 0; i < kRingStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], kRingConsumers / 32);
+    }
+    fence_mbar_init();
+    // the first ring-full of tiles does not depend on the prologue: start it now
+    for (int t = 0; t < ntiles && t < kRingStages; ++t) issue_tile(t, t);
+  }
+  gn_bwd_prologue(a, b, sh, sRs, sMr);
+  const float* S = a.sums + static_cast<size_t>(b) * 2 * C;
+  if (kApply) {
+    if (threadIdx.x < kGnGroups) {
+      float p1 = 0.f, p2 = 0.f;
+      for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c) {
+        p1 = fmaf(sh[c], S[2 * c], p1);
+        p2 = fmaf(sh[c], S[2 * c + 1], p2);
+      }
+      const float inv_n = 1.0f / (static_cast<float>(a.HW) * cpg);
+      sK1[threadIdx.x] = sRs[threadIdx.x] * p1 * inv_n;
+      sK2[threadIdx.x] = sRs[threadIdx.x] * p2 * inv_n;
+    }
+    if (blockIdx.x == 0) {
+      for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float s1 = S[2 * c], s2 = S[2 * c + 1];
+        float sc = 1.0f;
+        if (a.film != nullptr) {
+          sc = 1.0f + a.film[static_cast<size_t>(b) * a.film_stride + a.film_off + c];
+          if (a.dfilm != nullptr) {
+            float* df = a.dfilm + static_cast<size_t>(b) * a.film_stride + a.film_off;
+            df[c] = fmaf(a.gamma[c], s2, a.beta[c] * s1);
+            df[C + c] = s1;
+          }
+        }
+        atomicAdd(&a.dgamma[c], sc * s2);
+        atomicAdd(&a.dbeta[c], sc * s1);
+      }
+    }
+    __syncthreads();
+  }
+
+  const int nvec = C >> 3;
+  const int lanes = kRingConsumers / nvec;
+
+  if (warp == kRingConsumers / 32) {
+    // ------------------------------------------------------------------ producer: the rest of the tiles
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 1;  // second pass over the ring
+      for (int t = kRingStages; t < ntiles; ++t) {
+        mbar_wait(&empty[st], ph ^ 1);
+        issue_tile(t, st);
+        if (++st == kRingStages) {
+          st = 0;
+          ph ^= 1;
+        }
+      }
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------- consumers
+  const int v = threadIdx.x % nvec;
+  const int pl = threadIdx.x / nvec;
+  const int cb = v << 3;
+  const bool active = pl < lanes;
+  const bool first = cb < a.c0;
+  const int cs = first ? a.c0 : a.c1;
+  const int cbs = first ? cb : cb - a.c0;
+  const int x_off = (first ? 0 : off_x1) + (pl * cs + cbs) * 2;
+  const int d_off = (pl * C + cb) * 2;
+  float gp[8], bp[8], rs[2], mr[2], k1[2], k2[2];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    gp[j] = sh[cb + j];
+    bp[j] = sh[C + cb + j];
+  }
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf) {
+    const int g = (cb + 4 * hf) / cpg;
+    rs[hf] = sRs[g];
+    mr[hf] = sMr[g];
+    k1[hf] = kApply ? sK1[g] : 0.f;
+    k2[hf] = kApply ? sK2[g] : 0.f;
+  }
+  float acc0[8], acc1[8];  // reduce: sum g, sum g * xhat; apply: column sums of dx (acc0 only)
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc0[j] = acc1[j] = 0.f;
+  uint16_t* dst = first ? a.out0 : a.out1;
+  int st = 0;
+  uint32_t ph = 0;
+  for (int t = 0; t < ntiles; ++t) {
+    const int pix = p_begin + t * TP + pl;
+    const bool valid = active && pix < p_end;
+    mbar_wait(&full[st], ph);
+    const uint8_t* sp = ring + static_cast<size_t>(st) * stage_bytes;
+    uint4 ux, ud, u0, u1;
+    if (valid) {
+      ux = *reinterpret_cast<const uint4*>(sp + x_off);
+      ud = *reinterpret_cast<const uint4*>(sp + off_dy + d_off);
+      if (kApply && a.add0 != nullptr) u0 = *reinterpret_cast<const uint4*>(sp + off_a0 + d_off);
+      if (kApply && a.add1 != nullptr) u1 = *reinterpret_cast<const uint4*>(sp + off_a1 + d_off);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[st]);  // the warp holds its part of the stage in registers
+    if (++st == kRingStages) {
+      st = 0;
+      ph ^= 1;
+    }
+    if (!valid) continue;
+    float x[8], d[8];
+    unpack8(ux, a.fmt, x);
+    unpack8(ud, a.fmt, d);
+    if (!kApply) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = fmaf(x[j], rs[j >> 2], -mr[j >> 2]);
+        float g = d[j];
+        if (a.silu) g *= silu_grad(fmaf(gp[j], xh, bp[j]));
+        acc0[j] += g;
+        acc1[j] = fmaf(g, xh, acc1[j]);
+      }
+    } else {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = fmaf(x[j], rs[j >> 2], -mr[j >> 2]);
+        float g = d[j];
+        if (a.silu) g *= silu_grad(fmaf(gp[j], xh, bp[j]));
+        o[j] = fmaf(g * gp[j], rs[j >> 2], -k1[j >> 2]) - xh * k2[j >> 2];
+      }
+      if (a.add0 != nullptr) {
+        float tt[8];
+        unpack8(u0, a.fmt, tt);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += tt[j];
+      }
+      if (a.add1 != nullptr) {
+        float tt[8];
+        unpack8(u1, a.fmt, tt);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += tt[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc0[j] += o[j];
+      *reinterpret_cast<uint4*>(dst + (base + pix) * cs + cbs) = pack8(o, a.fmt);
+    }
+  }
+  if (kApply && a.bsum0 == nullptr && a.bsum1 == nullptr) return;
+  // block reduction over the pixel lanes through the (now idle) ring
+  asm volatile("bar.sync 1, %0;" ::"n"(kRingConsumers) : "memory");
+  float* red = reinterpret_cast<float*>(ring);
+  const int nacc = kApply ? 1 : 2;
+  if (active) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      red[(pl * C + cb + j) * nacc] = acc0[j];
+      if (!kApply) red[(pl * C + cb + j) * nacc + 1] = acc1[j];
+    }
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(kRingConsumers) : "memory");
+  for (int i = threadIdx.x; i < nacc * C; i += kRingConsumers) {
+    float tsum = 0.f;
+    for (int l = 0; l < lanes; ++l) tsum += red[l * nacc * C + i];
+    if (!kApply) {
+      atomicAdd(&a.sums[static_cast<size_t>(b) * 2 * C + i], tsum);
+    } else if (i < a.c0) {
+      if (a.bsum0 != nullptr) atomicAdd(&a.bsum0[i], tsum);
+    } else {
+      if (a.bsum1 != nullptr) atomicAdd(&a.bsum1[i - a.c0], tsum);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) resample_bwd_kernel(const uint16_t* __restrict__ dy, uint16_t* __restrict__ dx,
                                                            int B, int H, int W, int C, int mode, int fmt) {
   const int nvec = C >> 3;
@@ -652,6 +883,15 @@ int pick_blocks(int B, int HW, int lanes) {
   return best;
 }
 
+bool gn_ring_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CDDPM_GN_BWD_RING");  // A/B switch for measurements: 0 = register-fed kernels everywhere
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 }  // namespace
 
 int launch_gn_bwd(const GnBwdArgs& g, cudaStream_t stream) {
@@ -690,6 +930,45 @@ int launch_gn_bwd(const GnBwdArgs& g, cudaStream_t stream) {
   a.dfilm = g.dfilm;
   a.fmt = g.fmt;
   const int nvec = C / 8;
+  if (gn_ring_enabled() && a.HW >= 2304 && kRingConsumers / nvec >= 1) {
+    const int rl = kRingConsumers / nvec;  // pixels per tile: one per consumer thread
+    const int ntens = 2 + (g.add0 != nullptr ? 1 : 0) + (g.add1 != nullptr ? 1 : 0);
+    const int stage_apply = rl * C * 2 * ntens;
+    const int stage_reduce = rl * C * 2 * 2;
+    const int slots = device_sm_count();
+    int max_chunks = a.HW / (16 * rl);
+    if (max_chunks < 1) max_chunks = 1;
+    if (max_chunks > 64) max_chunks = 64;
+    auto fill = [&](int ch) {
+      const int blocks = ch * g.B;
+      const int waves = (blocks + slots - 1) / slots;
+      return static_cast<double>(blocks) / (static_cast<double>(waves) * slots);
+    };
+    double best_eff = 0.0;
+    for (int ch = 1; ch <= max_chunks; ++ch) best_eff = fill(ch) > best_eff ? fill(ch) : best_eff;
+    int best = 1;
+    for (int ch = 1; ch <= max_chunks; ++ch)
+      if (fill(ch) >= best_eff - 0.03) {  // fewest chunks (least prologue work) within 3 % of the best wave fill
+        best = ch;
+        break;
+      }
+    a.P = (a.HW + best - 1) / best;
+    const dim3 rgrid((a.HW + a.P - 1) / a.P, g.B);
+    static bool attr_set = false;
+    if (!attr_set) {
+      CDDPM_CUDA(cudaFuncSetAttribute(gn_bwd_ring_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      CDDPM_CUDA(cudaFuncSetAttribute(gn_bwd_ring_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      attr_set = true;
+    }
+    const size_t sh_r = static_cast<size_t>(kRingStages) * stage_reduce + static_cast<size_t>(2) * C * sizeof(float);
+    const size_t sh_a = static_cast<size_t>(kRingStages) * stage_apply + static_cast<size_t>(2) * C * sizeof(float);
+    if (sh_a <= 220 * 1024) {
+      gn_bwd_ring_kernel<false><<<rgrid, kRingThreads, sh_r, stream>>>(a, rl, stage_reduce);
+      CDDPM_TRY(check_launch("gn_bwd_ring_kernel<reduce>"));
+      gn_bwd_ring_kernel<true><<<rgrid, kRingThreads, sh_a, stream>>>(a, rl, stage_apply);
+      return check_launch("gn_bwd_ring_kernel<apply>");
+    }
+  }
   const int threads = 256;
   const int lanes = threads / nvec;
   if (lanes < 1) return fail(kUnsupported, "gn_bwd: too many channels");
