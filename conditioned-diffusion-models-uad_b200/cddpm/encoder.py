@@ -144,7 +144,7 @@ class ResNet(nn.Module):
 
     def _train_forward(self, x):
         """Training-mode forward WITH an autograd tape (batch-statistics BatchNorm, running-stat updates): ~1 % of the
-        training step's FLOPs, evaluated with torch's library kernels (cuDNN convolutions under bf16 autocast) — the
+        training step's FLOPs, evaluated with torch's library kernels (cuDNN convolutions, TF32 by default) — the
         hand-written engine covers the eval-mode forward only (DESIGN.md lists the encoder backward under "next").
         The ~500 small launches of the forward and the backward are replayed as CUDA graphs
         (torch.cuda.make_graphed_callables, one pair per input shape; CDDPM_ENCODER_GRAPH=0 disables it).
@@ -153,7 +153,7 @@ class ResNet(nn.Module):
 
         if os.environ.get("CDDPM_ENCODER_GRAPH", "1") == "0":
             return _encoder_train_eager(self, x)
-        key = (tuple(x.shape), x.device.index)
+        key = (tuple(x.shape), x.device.index, os.environ.get("CDDPM_ENCODER_TRAIN_DTYPE", getattr(self, "train_dtype", "tf32")))
         graphs = self.__dict__.setdefault("_train_graphs", {})
         if key not in graphs:
             holder = _EncoderTrainModule(self)
@@ -199,7 +199,18 @@ def _encoder_train_eager(self, x):
             m.num_batches_tracked.add_(1)
         return F.batch_norm(t, m.running_mean, m.running_var, m.weight, m.bias, True, m.momentum, m.eps)
 
-    with torch.autocast("cuda", dtype=torch.bfloat16, cache_enabled=False):
+    # Arithmetic of the training-mode encoder: "tf32" (default: fp32 storage, TF32 tensor-core convolutions - the
+    # mantissa of the reference's fp16 autocast, and measured as fast as bf16 autocast at B=64: 41.56 vs 41.57 ms per
+    # step), "bf16" (autocast) or "fp32" (50.6 ms).  Batch-statistics BatchNorm over a handful of samples (layer4 sees
+    # 3x3 pixels per slice) amplifies operand rounding: at B=2 bf16 autocast moves the features by O(1) - on the CPU
+    # as much as here - so small-batch parity runs use fp32.
+    mode = os.environ.get("CDDPM_ENCODER_TRAIN_DTYPE", getattr(self, "train_dtype", "tf32"))
+    if mode == "bf16":
+        ctx = torch.autocast("cuda", dtype=torch.bfloat16, cache_enabled=False)
+    else:
+        ctx = torch.backends.cudnn.flags(enabled=True, benchmark=torch.backends.cudnn.benchmark, deterministic=False,
+                                         allow_tf32=(mode == "tf32"))
+    with ctx, torch.autocast("cuda", enabled=(mode == "bf16"), dtype=torch.bfloat16, cache_enabled=False):
         x = x.float()
         if nhwc:
             x = x.contiguous(memory_format=torch.channels_last)
@@ -228,6 +239,7 @@ class SparK_2D_encoder(nn.Module):
         dtype = {"bf16": torch.bfloat16, "bfloat16": torch.bfloat16}.get(str(cfg.get("engine_dtype", "fp16")), torch.float16)
         self.encoder = ResNet(cfg.version, in_chans=1, num_classes=cfg.get("cond_dim", 128), image_size=size,
                               engine_dtype=dtype)
+        self.encoder.train_dtype = str(cfg.get("encoder_train_dtype", "tf32"))  # "bf16" | "tf32" | "fp32"
 
     def forward(self, x):
         return self.encoder(x)

@@ -341,9 +341,45 @@ def golden_test_step():
     print({k: [float(x) for x in ed[k]] for k in keys})
 
 
+def golden_train_step():
+    """The reference's training arithmetic end to end (DDPM_2D.py:114-138 with a fixed timestep instead of the random
+    draw): encoder in train() mode (batch-statistics BatchNorm) -> gen_noise -> GaussianDiffusion.forward -> L1 loss ->
+    loss.backward() on CPU in fp32.  Stored: the loss, the L2 norm of every parameter gradient (649 - 13 buffers - BN
+    statistics) and a few small gradients in full."""
+    from src.models.DDPM_2D import DDPM_2D
+    from src.utils.generate_noise import gen_noise
+
+    cfg = base_cfg()
+    model = DDPM_2D(cfg, prefix="t/")
+    enc_sd = make_state_dict(resnet_port.param_shapes(128), seed=3)
+    unet_sd = make_state_dict(unet_port.param_shapes(unet_port.UNetSpec()), seed=1)
+    full = {"encoder.encoder." + k: v for k, v in enc_sd.items()}
+    full.update({"diffusion." + k: v for k, v in diffusion_port.schedule_buffers().items()})
+    full.update({"diffusion.model." + k: v for k, v in unet_sd.items()})
+    model.load_state_dict(full, strict=True)
+    model.train()
+    x = synthetic_slices(2, 96, seed=21)
+    np.random.seed(13)
+    features = model(x)
+    noise = gen_noise(cfg, x.shape)
+    loss, _ = model.diffusion(x, t=300, cond=features, noise=noise)
+    loss.backward()
+    names, norms = [], []
+    for n, p in model.named_parameters():
+        names.append(n)
+        norms.append(float(p.grad.norm()) if p.grad is not None else -1.0)
+    small = {"diffusion.model.out.2.weight", "diffusion.model.time_embed.0.bias", "diffusion.model.label_emb.2.bias",
+             "diffusion.model.middle_block.1.qkv.bias", "diffusion.model.input_blocks.0.0.weight",
+             "diffusion.model.output_blocks.11.0.in_layers.0.weight", "encoder.encoder.fc.bias"}
+    grads = {n.replace(".", "__"): p.grad for n, p in model.named_parameters() if n in small}
+    save("train_step_96.npz", loss=loss.detach(), features=features.detach(), grad_norms=np.asarray(norms),
+         names=np.asarray(names), **grads)
+    print("loss", float(loss), "grad norms", min(norms), max(norms))
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["schedule", "simplex", "unet", "encoder", "diffusion", "tail", "test_step"]
+    which = sys.argv[1:] or ["schedule", "simplex", "unet", "encoder", "diffusion", "tail", "test_step", "train_step"]
     torch.manual_seed(0)
     for w in which:
         print(f"== {w}")
