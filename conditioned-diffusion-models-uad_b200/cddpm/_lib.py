@@ -80,6 +80,7 @@ def _signatures(c):
         "cddpm_unet_backward": (i32, [vp, vp, vp, vp, i32, vp]),
         "cddpm_unet_bwd_flops": (i64, [vp]),
         "cddpm_unet_bwd_launches": (i32, [vp]),
+        "cddpm_adam_step": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, f32, f32, f32, f32, f32, f32, vp]),
         "cddpm_attention_bwd_scratch_bytes": (i64, [i32, i32, i32]),
         "cddpm_attention_bwd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
         "cddpm_encoder_create": (i32, [i32, i32, i32, i32, pvp]),

@@ -205,9 +205,15 @@ class DDPM_2D(LightningModule):
         _test_end(self)
 
     def configure_optimizers(self):
-        # same optimizer as the reference (DDPM_2D.py:305-306); the fused multi-tensor implementation when on CUDA
+        # the reference's optimizer (DDPM_2D.py:305-306: Adam(lr), default betas / eps).  On CUDA: the same update rule
+        # and state layout as ONE kernel launch over all 636 tensors (cddpm/optim.py); `optimizer: torch` in the
+        # config selects torch.optim.Adam itself.
         params = list(self.parameters())
-        return optim.Adam(params, lr=self.cfg.lr, fused=all(p.is_cuda for p in params))
+        if all(p.is_cuda for p in params) and str(self.cfg.get("optimizer", "cddpm")) != "torch":
+            from .optim import Adam
+
+            return Adam(params, lr=self.cfg.lr)
+        return optim.Adam(params, lr=self.cfg.lr)
 
     def update_prefix(self, prefix):
         self.prefix = prefix

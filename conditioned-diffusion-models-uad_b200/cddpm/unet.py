@@ -253,10 +253,23 @@ class UNetModel(nn.Module):
         self._push(self._engine, self._engine_versions, items)
         return self._engine
 
+    def train(self, mode: bool = True):
+        # leaving / entering training: the next engine call re-pushes every parameter (an optimizer may have changed
+        # them without advancing the version counters - torch's fused optimizers do)
+        if mode != self.training:
+            if self._engine_versions is not None:
+                self._engine_versions = [None] * len(self._engine_versions)
+            if self._train_versions is not None:
+                self._train_versions = [None] * len(self._train_versions)
+        return super().train(mode)
+
     def train_engine(self) -> UNetEngine:
         """The bf16 engine the training step runs on (forward + backward kernels); shares nothing with the inference
         engine when that one is fp16.  Parameters are re-pushed when the optimizer changed them."""
         if self.engine_dtype == torch.bfloat16:
+            if self._engine_versions is not None:
+                for i in range(len(self._engine_versions)):
+                    self._engine_versions[i] = None  # see below: always push in training
             return self.engine()
         items = self._param_items()
         if items[0][1].device.type != "cuda":
@@ -268,6 +281,10 @@ class UNetModel(nn.Module):
                 attention_resolutions=self.attention_resolutions, channel_mult=self.channel_mult,
                 num_classes=self.num_classes, num_head_channels=self.num_head_channels, dtype=torch.bfloat16)
             self._train_versions = [None] * len(items)
+        # training: push everything on every call.  Version counters are not a reliable change signal here - torch's
+        # fused optimizers update parameters without advancing them - and the bulk push replays one CUDA graph.
+        for i in range(len(self._train_versions)):
+            self._train_versions[i] = None
         self._push(self._train_engine, self._train_versions, items)
         return self._train_engine
 

@@ -3,6 +3,7 @@
 
 #include "common.h"
 #include "attention.cuh"
+#include "backward.cuh"
 #include "conv_bwd.cuh"
 #include "conv_igemm.cuh"
 #include "diffusion.cuh"
@@ -329,6 +330,9 @@ int cddpm_unet_profile_read(cddpm_unet_t* h, double* conv_ms, int* conv_launches
 int cddpm_unet_set_params(cddpm_unet_t* h, const float* const* values, int count, void* stream) {
   if (!h || !values) return fail(kInvalidArgument, "unet_set_params: null pointer");
   if (count != h->engine.param_count()) return fail(kInvalidArgument, "unet_set_params: wrong parameter count");
+  bool all = true;
+  for (int i = 0; i < count; ++i) all = all && values[i] != nullptr;
+  if (all) return h->engine.set_params_all(values, count, static_cast<cudaStream_t>(stream));
   for (int i = 0; i < count; ++i) {
     if (values[i] == nullptr) continue;
     const char* name = nullptr;
@@ -349,6 +353,12 @@ int cddpm_unet_backward(cddpm_unet_t* h, const float* dout, float* grads, float*
 }
 int64_t cddpm_unet_bwd_flops(const cddpm_unet_t* h) { return h ? h->engine.bwd_flops_per_sample() : 0; }
 int cddpm_unet_bwd_launches(const cddpm_unet_t* h) { return h ? h->engine.bwd_launches() : 0; }
+int cddpm_adam_step(float* const* p, const float* const* g, float* const* m, float* const* v, const int64_t* numel,
+                    const int* block_tensor, const int64_t* block_off, int total_blocks, float lr, float beta1,
+                    float beta2, float eps, float bc1, float bc2, void* stream) {
+  return launch_adam_step(p, g, m, v, numel, block_tensor, block_off, total_blocks, lr, beta1, beta2, eps, bc1, bc2,
+                          static_cast<cudaStream_t>(stream));
+}
 int64_t cddpm_attention_bwd_scratch_bytes(int B, int L, int C) { return attention_bwd_scratch_elems(B, L, C) * 2; }
 int cddpm_attention_bwd(const void* qkv, const void* dout, void* dqkv, void* scratch, int B, int L, int C, int fmt,
                         void* stream) {

@@ -856,6 +856,50 @@ __global__ void mul_silu_grad_kernel(float* __restrict__ dx, const float* __rest
     dx[i] *= silu_grad_precise(z[i]);
 }
 
+constexpr int kAdamChunk = 4096;
+__global__ void __launch_bounds__(256) adam_multi_kernel(float* const* __restrict__ pp, const float* const* __restrict__ gp,
+                                                         float* const* __restrict__ mp, float* const* __restrict__ vp,
+                                                         const int64_t* __restrict__ numel,
+                                                         const int* __restrict__ block_tensor,
+                                                         const int64_t* __restrict__ block_off, float step_size,
+                                                         float beta1, float beta2, float eps, float inv_sqrt_bc2) {
+  const int t = block_tensor[blockIdx.x];
+  const float* g = gp[t];
+  if (g == nullptr) return;
+  float* p = pp[t];
+  float* m = mp[t];
+  float* v = vp[t];
+  const int64_t n = numel[t];
+  const int64_t lo = block_off[blockIdx.x];
+  const int64_t hi = min(lo + kAdamChunk, n);
+  const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                     reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+  auto upd = [&](float& pe, float ge, float& me, float& ve) {
+    me = beta1 * me + (1.0f - beta1) * ge;
+    ve = beta2 * ve + (1.0f - beta2) * ge * ge;
+    pe -= step_size * me / (sqrtf(ve) * inv_sqrt_bc2 + eps);
+  };
+  if (vec) {
+    const int64_t hi4 = lo + ((hi - lo) & ~int64_t(3));
+    for (int64_t i = lo + 4 * threadIdx.x; i < hi4; i += 4 * blockDim.x) {
+      float4 p4 = *reinterpret_cast<float4*>(p + i);
+      const float4 g4 = *reinterpret_cast<const float4*>(g + i);
+      float4 m4 = *reinterpret_cast<float4*>(m + i);
+      float4 v4 = *reinterpret_cast<float4*>(v + i);
+      upd(p4.x, g4.x, m4.x, v4.x);
+      upd(p4.y, g4.y, m4.y, v4.y);
+      upd(p4.z, g4.z, m4.z, v4.z);
+      upd(p4.w, g4.w, m4.w, v4.w);
+      *reinterpret_cast<float4*>(p + i) = p4;
+      *reinterpret_cast<float4*>(m + i) = m4;
+      *reinterpret_cast<float4*>(v + i) = v4;
+    }
+    for (int64_t i = hi4 + threadIdx.x; i < hi; i += blockDim.x) upd(p[i], g[i], m[i], v[i]);
+  } else {
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) upd(p[i], g[i], m[i], v[i]);
+  }
+}
+
 __global__ void copy_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n) {
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x)
@@ -1072,6 +1116,16 @@ int launch_mul_silu_grad(float* dx, const float* z, int64_t n, cudaStream_t stre
   if (blocks < 1) blocks = 1;
   mul_silu_grad_kernel<<<blocks, 256, 0, stream>>>(dx, z, n);
   return check_launch("mul_silu_grad_kernel");
+}
+
+int launch_adam_step(float* const* p, const float* const* g, float* const* m, float* const* v, const int64_t* numel,
+                     const int* block_tensor, const int64_t* block_off, int total_blocks, float lr, float beta1,
+                     float beta2, float eps, float bc1, float bc2, cudaStream_t stream) {
+  if (!p || !g || !m || !v || !numel || !block_tensor || !block_off) return fail(kInvalidArgument, "adam_step: null pointer");
+  if (total_blocks <= 0) return kOk;
+  adam_multi_kernel<<<total_blocks, 256, 0, stream>>>(p, g, m, v, numel, block_tensor, block_off, lr / bc1, beta1, beta2,
+                                                      eps, 1.0f / sqrtf(bc2));
+  return check_launch("adam_multi_kernel");
 }
 
 int launch_copy_f32(const float* src, float* dst, int64_t n, cudaStream_t stream) {

@@ -68,6 +68,13 @@ int launch_linear_bwd_weight_tiled(const float* dy, int dy_stride, const float* 
                                    int O, cudaStream_t stream);
 // dx[i] *= silu'(z[i])
 int launch_mul_silu_grad(float* dx, const float* z, int64_t n, cudaStream_t stream);
+// torch.optim.Adam(lr, betas, eps) over many tensors in ONE launch (DDPM_2D.configure_optimizers, DDPM_2D.py:305-306):
+//   m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2;  p -= (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps)
+// p/g/m/v: device arrays of per-tensor device pointers (a NULL gradient skips the tensor), numel per tensor;
+// block b works on elements [block_off[b], block_off[b] + 4096) of tensor block_tensor[b].
+int launch_adam_step(float* const* p, const float* const* g, float* const* m, float* const* v, const int64_t* numel,
+                     const int* block_tensor, const int64_t* block_off, int total_blocks, float lr, float beta1,
+                     float beta2, float eps, float bc1, float bc2, cudaStream_t stream);
 // dst[i] = src[i] for i < n (fp32), plain device copy helper that is graph-capturable
 int launch_copy_f32(const float* src, float* dst, int64_t n, cudaStream_t stream);
 

@@ -1,6 +1,8 @@
 #include "unet_engine.cuh"
 
 #include <stdlib.h>
+
+#include <algorithm>
 #include <string.h>
 
 #include "attention.cuh"
@@ -10,6 +12,7 @@ namespace cddpm {
 
 UNetEngine::~UNetEngine() {
   free_acts();
+  if (push_graph_ != nullptr) cudaGraphExecDestroy(push_graph_);
   if (cap_stream_ != nullptr) cudaStreamDestroy(cap_stream_);
   for (void* p : owned_) cudaFree(p);
 }
@@ -91,6 +94,43 @@ int UNetEngine::set_param(const char* name, const float* dev_ptr, int64_t numel,
   CDDPM_TRY(p.load(dev_ptr, stream));
   p.set = true;
   return kOk;
+}
+
+int UNetEngine::set_params_all(const float* const* values, int count, cudaStream_t stream) {
+  if (count != param_count()) return fail(kInvalidArgument, "set_params_all: wrong parameter count");
+  for (int i = 0; i < count; ++i)
+    if (values[i] == nullptr) return fail(kInvalidArgument, "set_params_all: null parameter pointer");
+  const bool same = push_graph_ != nullptr && push_key_.size() == static_cast<size_t>(count) &&
+                    std::equal(push_key_.begin(), push_key_.end(), values);
+  if (!same || !graph_enabled()) {
+    if (push_graph_ != nullptr) {
+      cudaGraphExecDestroy(push_graph_);
+      push_graph_ = nullptr;
+    }
+    push_key_.clear();
+    if (!graph_enabled()) {
+      for (int i = 0; i < count; ++i) CDDPM_TRY(set_param(params_[i].name.c_str(), values[i], params_[i].numel, stream));
+      return kOk;
+    }
+    if (cap_stream_ == nullptr) CDDPM_CUDA(cudaStreamCreateWithFlags(&cap_stream_, cudaStreamNonBlocking));
+    CDDPM_CUDA(cudaStreamSynchronize(stream));  // the capture stream must see the optimizer's writes
+    CDDPM_CUDA(cudaStreamBeginCapture(cap_stream_, cudaStreamCaptureModeThreadLocal));
+    int st = kOk;
+    for (int i = 0; i < count && st == kOk; ++i)
+      st = set_param(params_[i].name.c_str(), values[i], params_[i].numel, cap_stream_);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(cap_stream_, &graph);
+    if (st != kOk) {
+      if (graph != nullptr) cudaGraphDestroy(graph);
+      return st;
+    }
+    CDDPM_TRY(check_cuda(ce, "cudaStreamEndCapture"));
+    const cudaError_t ie = cudaGraphInstantiate(&push_graph_, graph, 0);
+    cudaGraphDestroy(graph);
+    CDDPM_TRY(check_cuda(ie, "cudaGraphInstantiate"));
+    push_key_.assign(values, values + count);
+  }
+  return check_cuda(cudaGraphLaunch(push_graph_, stream), "cudaGraphLaunch");
 }
 
 // ------------------------------------------------------------------------------------------------ construction

@@ -31,6 +31,10 @@ class UNetEngine {
   int param_count() const { return static_cast<int>(params_.size()); }
   int param_info(int i, const char** name, int64_t* numel) const;
   int set_param(const char* name, const float* dev_ptr, int64_t numel, cudaStream_t stream);
+  // All parameters at once (values[i] for parameter i, no NULLs): the ~500 small re-layout launches are captured into
+  // a CUDA graph keyed by the pointer list (optimizers update in place, so the pointers are stable across steps) and
+  // replayed with one launch per step.
+  int set_params_all(const float* const* values, int count, cudaStream_t stream);
   int forward(const float* x, const int64_t* t, const float* cond, float* out, int B, cudaStream_t stream);
   int tap(const char* layer, void** ptr, int* C, int* H, int* W) const;
   int film(const float** ptr, int* stride) const;
@@ -167,6 +171,8 @@ class UNetEngine {
   void drop_graph();
   cudaStream_t cap_stream_ = nullptr;
   cudaGraphExec_t graph_exec_ = nullptr;
+  cudaGraphExec_t push_graph_ = nullptr;
+  std::vector<const float*> push_key_;
   int forwards_on_plan_ = 0;
   float *stage_x_ = nullptr, *stage_cond_ = nullptr, *stage_out_ = nullptr;
   int64_t* stage_t_ = nullptr;

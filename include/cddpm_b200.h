@@ -151,6 +151,14 @@ int cddpm_unet_backward(cddpm_unet_t* h, const float* dout, float* grads, float*
  * backward of a batch size). */
 int64_t cddpm_unet_bwd_flops(const cddpm_unet_t* h);
 int cddpm_unet_bwd_launches(const cddpm_unet_t* h);
+/* torch.optim.Adam(lr, betas, eps) - DDPM_2D.configure_optimizers (DDPM_2D.py:305-306) - over many fp32 tensors in
+ * ONE launch: m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; p -= (lr / bc1) m / (sqrt(v) / sqrt(bc2) + eps), with the
+ * bias corrections bc1 = 1 - b1^t, bc2 = 1 - b2^t passed by the host.  p, g, m, v: DEVICE arrays of per-tensor device
+ * pointers (a NULL gradient skips that tensor); numel: device array; block b updates elements
+ * [block_off[b], block_off[b] + 4096) of tensor block_tensor[b]. */
+int cddpm_adam_step(float* const* p, const float* const* g, float* const* m, float* const* v, const int64_t* numel,
+                    const int* block_tensor, const int64_t* block_off, int total_blocks, float lr, float beta1,
+                    float beta2, float eps, float bc1, float bc2, void* stream);
 /* Backward of cddpm_attention (bf16): dqkv [B,L,3C] from dout [B,L,C]; scratch = cddpm_attention_bwd_scratch_bytes. */
 int64_t cddpm_attention_bwd_scratch_bytes(int B, int L, int C);
 int cddpm_attention_bwd(const void* qkv, const void* dout, void* dqkv, void* scratch, int B, int L, int C, int fmt,

@@ -262,3 +262,70 @@ def test_training_step_matches_live_reference_golden():
         ref = torch.from_numpy(g[key]).cuda()
         rel = _rel(params[n].grad.float(), ref)
         assert rel <= (8e-2 if n.startswith("encoder.") else 5e-2), (n, rel)
+
+
+def test_adam_kernel_matches_torch_adam():
+    """cddpm.optim.Adam (one launch over all tensors) vs torch.optim.Adam on the same gradients, 5 steps, odd sizes
+    and a parameter without gradient."""
+    from cddpm.optim import Adam
+
+    g = torch.Generator(device="cuda").manual_seed(0)
+    shapes = [(5,), (4097,), (128, 64, 3, 3), (1, 1), (3000, 7)]
+    ours = [torch.nn.Parameter(torch.randn(s, device="cuda", generator=g)) for s in shapes]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ours]
+    oa, ot = Adam(ours, lr=1e-3), torch.optim.Adam(ref, lr=1e-3)
+    for step in range(5):
+        for i, (a, b) in enumerate(zip(ours, ref)):
+            if i == 3 and step % 2 == 0:
+                a.grad = b.grad = None  # skipped this step, like an unused parameter
+                continue
+            gr = torch.randn(a.shape, device="cuda", generator=g)
+            a.grad, b.grad = gr.clone(), gr.clone()
+        v0 = ours[0]._version
+        oa.step()
+        ot.step()
+        assert ours[0]._version > v0  # the engines watch the version counters
+    torch.cuda.synchronize()
+    for a, b in zip(ours[:3] + ours[4:], ref[:3] + ref[4:]):
+        assert (a - b).abs().max().item() <= 2e-6, (a.shape, (a - b).abs().max().item())
+    sd = oa.state_dict()
+    assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}
+
+
+@pytest.mark.parametrize("opt_kind", ["cddpm", "torch_fused"])
+def test_engine_sees_optimizer_updates(opt_kind):
+    """After an optimizer step the engine must run with the NEW weights - also for torch's fused Adam, which updates
+    parameters without advancing their version counters - in training and in the following eval forward."""
+    from cddpm.unet import UNetModel
+
+    torch.manual_seed(0)
+    m = UNetModel(image_size=(32, 32), in_channels=1, model_channels=128, out_channels=1, num_res_blocks=1,
+                  attention_resolutions=(3, 6, 12), channel_mult=[1, 2], num_classes=128, num_head_channels=64,
+                  use_scale_shift_norm=True, resblock_updown=True, use_new_attention_order=True).cuda()
+    with torch.no_grad():
+        for p in m.parameters():
+            if float(p.abs().sum()) == 0.0:
+                p.normal_(0, 0.05)
+    if opt_kind == "cddpm":
+        from cddpm.optim import Adam
+
+        opt = Adam(m.parameters(), lr=1e-2)
+    else:
+        opt = torch.optim.Adam(m.parameters(), lr=1e-2, fused=True)
+    x = torch.randn(2, 1, 32, 32, device="cuda")
+    t = torch.tensor([10, 700], device="cuda")
+    c = torch.randn(2, 128, device="cuda")
+    m.eval()
+    with torch.no_grad():
+        before_eval = m(x, t, c).clone()
+    m.train()
+    out0 = m(x, t, c)
+    out0.abs().mean().backward()
+    opt.step()
+    opt.zero_grad(set_to_none=True)
+    out1 = m(x, t, c)
+    assert (out1 - out0).abs().max().item() > 1e-3, "training forward still runs on the old weights"
+    m.eval()
+    with torch.no_grad():
+        after_eval = m(x, t, c)
+    assert (after_eval - before_eval).abs().max().item() > 1e-3, "eval forward still runs on the old weights"
