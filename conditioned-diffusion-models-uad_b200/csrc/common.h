@@ -45,4 +45,29 @@ int encode_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64
 
 int device_sm_count();
 
+// Parameter re-layout jobs.  While a recorder is installed (thread-local), the small re-layout launches behind
+// cddpm_unet_set_param (weight packing, plain copies, bias sums) append a job here instead of launching, so that a
+// whole-model push becomes two launches of one table-driven kernel (param_push.cu).
+enum ParamJobKind : int { kJobPack = 0, kJobPackT = 1, kJobCopy = 2, kJobVecAdd = 3 };
+struct ParamJob {
+  int kind;
+  int cout, cin_total, ksize, cin_off, c_s, ktot, koff, fmt;
+  const void* src;
+  const void* src2;
+  void* dst;
+  long long n;  // elements
+};
+struct ParamJobRecorder;
+ParamJobRecorder* job_recorder();              // nullptr when launches run directly
+void job_record(const ParamJob& j);
+// fp32 device copy that honours the recorder
+int copy_f32_or_record(float* dst, const float* src, long long n, cudaStream_t stream);
+// Record (begin .. end) the jobs of a whole-model push into a device-resident tile table, then replay it with two
+// launches per push.  `ok == false` at end discards the recording.
+struct ParamPushTable;
+int param_push_record_begin(ParamJobRecorder** rec);
+int param_push_record_end(ParamJobRecorder* rec, ParamPushTable** out, bool ok);
+int param_push_launch(const ParamPushTable* t, cudaStream_t stream);
+void param_push_table_free(ParamPushTable* t);
+
 }  // namespace cddpm

@@ -601,6 +601,12 @@ int launch_conv_igemm(const ConvIgemmParams& p, cudaStream_t stream, int max_cta
 int launch_pack_conv_weight(const float* w_oihw, int Cout, int Cin_total, int ksize, int cin_off, int C_s,
                             void* wpacked, int Ktot, int koff, int ab_format, cudaStream_t stream) {
   const size_t total = static_cast<size_t>(Cout) * ksize * ksize * C_s;
+  if (job_recorder() != nullptr) {
+    ParamJob j = {kJobPack, Cout, Cin_total, ksize, cin_off, C_s, Ktot, koff, ab_format, w_oihw, nullptr, wpacked,
+                  static_cast<long long>(total)};
+    job_record(j);
+    return kOk;
+  }
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > 4096) blocks = 4096;
   if (blocks < 1) blocks = 1;

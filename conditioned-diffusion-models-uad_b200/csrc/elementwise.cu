@@ -780,6 +780,11 @@ int launch_conv_out(const void* x, const float* w, const float* bias, float* out
 }
 
 int launch_vec_add(const float* a, const float* b, float* out, int n, cudaStream_t stream) {
+  if (job_recorder() != nullptr) {
+    ParamJob j = {kJobVecAdd, 0, 0, 0, 0, 0, 0, 0, 0, a, b, out, static_cast<long long>(n)};
+    job_record(j);
+    return kOk;
+  }
   vec_add_kernel<<<(n + 255) / 256, 256, 0, stream>>>(a, b, out, n);
   return check_launch("vec_add_kernel");
 }

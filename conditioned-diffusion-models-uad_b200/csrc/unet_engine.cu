@@ -12,7 +12,7 @@ namespace cddpm {
 
 UNetEngine::~UNetEngine() {
   free_acts();
-  if (push_graph_ != nullptr) cudaGraphExecDestroy(push_graph_);
+  param_push_table_free(push_table_);
   if (cap_stream_ != nullptr) cudaStreamDestroy(cap_stream_);
   for (void* p : owned_) cudaFree(p);
 }
@@ -72,7 +72,7 @@ int UNetEngine::add_copy_param(const std::string& name, int64_t numel, float** d
   CDDPM_TRY(dalloc(dst, static_cast<size_t>(numel)));
   float* d = *dst;
   return add_param(name, numel, [d, numel](const float* src, cudaStream_t s) {
-    return check_cuda(cudaMemcpyAsync(d, src, numel * sizeof(float), cudaMemcpyDeviceToDevice, s), "param copy");
+    return copy_f32_or_record(d, src, numel, s);
   });
 }
 
@@ -100,37 +100,25 @@ int UNetEngine::set_params_all(const float* const* values, int count, cudaStream
   if (count != param_count()) return fail(kInvalidArgument, "set_params_all: wrong parameter count");
   for (int i = 0; i < count; ++i)
     if (values[i] == nullptr) return fail(kInvalidArgument, "set_params_all: null parameter pointer");
-  const bool same = push_graph_ != nullptr && push_key_.size() == static_cast<size_t>(count) &&
+  // The parameters' device addresses are the key: torch optimizers update in place, so after the first push every
+  // later one replays the recorded tile table (two launches) instead of ~500 per-parameter launches.
+  const bool same = push_table_ != nullptr && push_key_.size() == static_cast<size_t>(count) &&
                     std::equal(push_key_.begin(), push_key_.end(), values);
-  if (!same || !graph_enabled()) {
-    if (push_graph_ != nullptr) {
-      cudaGraphExecDestroy(push_graph_);
-      push_graph_ = nullptr;
-    }
+  if (!same) {
+    param_push_table_free(push_table_);
+    push_table_ = nullptr;
     push_key_.clear();
-    if (!graph_enabled()) {
-      for (int i = 0; i < count; ++i) CDDPM_TRY(set_param(params_[i].name.c_str(), values[i], params_[i].numel, stream));
-      return kOk;
-    }
-    if (cap_stream_ == nullptr) CDDPM_CUDA(cudaStreamCreateWithFlags(&cap_stream_, cudaStreamNonBlocking));
-    CDDPM_CUDA(cudaStreamSynchronize(stream));  // the capture stream must see the optimizer's writes
-    CDDPM_CUDA(cudaStreamBeginCapture(cap_stream_, cudaStreamCaptureModeThreadLocal));
+    ParamJobRecorder* rec = nullptr;
+    CDDPM_TRY(param_push_record_begin(&rec));
     int st = kOk;
     for (int i = 0; i < count && st == kOk; ++i)
-      st = set_param(params_[i].name.c_str(), values[i], params_[i].numel, cap_stream_);
-    cudaGraph_t graph = nullptr;
-    const cudaError_t ce = cudaStreamEndCapture(cap_stream_, &graph);
-    if (st != kOk) {
-      if (graph != nullptr) cudaGraphDestroy(graph);
-      return st;
-    }
-    CDDPM_TRY(check_cuda(ce, "cudaStreamEndCapture"));
-    const cudaError_t ie = cudaGraphInstantiate(&push_graph_, graph, 0);
-    cudaGraphDestroy(graph);
-    CDDPM_TRY(check_cuda(ie, "cudaGraphInstantiate"));
+      st = set_param(params_[i].name.c_str(), values[i], params_[i].numel, stream);
+    const int st2 = param_push_record_end(rec, &push_table_, st == kOk);
+    if (st != kOk) return st;
+    CDDPM_TRY(st2);
     push_key_.assign(values, values + count);
   }
-  return check_cuda(cudaGraphLaunch(push_graph_, stream), "cudaGraphLaunch");
+  return param_push_launch(push_table_, stream);
 }
 
 // ------------------------------------------------------------------------------------------------ construction
@@ -178,9 +166,7 @@ int UNetEngine::add_res(const std::string& prefix, int c0, int c1, int cout, int
                                                          self->film_w16 + static_cast<size_t>(off) * E, E, 0, fmt, s);
                         }));
     CDDPM_TRY(add_param(prefix + ".emb_layers.1.bias", 2 * cout, [=](const float* src, cudaStream_t s) {
-      return check_cuda(cudaMemcpyAsync(self->film_b + off, src, static_cast<size_t>(2) * cout * sizeof(float),
-                                        cudaMemcpyDeviceToDevice, s),
-                        "film bias copy");
+      return copy_f32_or_record(self->film_b + off, src, 2ll * cout, s);
     }));
   }
   CDDPM_TRY(add_copy_param(prefix + ".out_layers.0.weight", cout, &L.gn2_w));
@@ -223,7 +209,7 @@ int UNetEngine::add_res(const std::string& prefix, int c0, int c1, int cout, int
     }
     float* bskip = L.bskip;
     CDDPM_TRY(add_param(prefix + ".out_layers.3.bias", cout, [=](const float* src, cudaStream_t s) {
-      CDDPM_CUDA(cudaMemcpyAsync(b2, src, cout * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      CDDPM_TRY(copy_f32_or_record(b2, src, cout, s));
       return launch_vec_add(b2, bskip, b2sum, cout, s);
     }));
     if (L.has_skip) {
@@ -237,7 +223,7 @@ int UNetEngine::add_res(const std::string& prefix, int c0, int c1, int cout, int
                             return static_cast<int>(kOk);
                           }));
       CDDPM_TRY(add_param(prefix + ".skip_connection.bias", cout, [=](const float* src, cudaStream_t s) {
-        CDDPM_CUDA(cudaMemcpyAsync(bskip, src, cout * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        CDDPM_TRY(copy_f32_or_record(bskip, src, cout, s));
         return launch_vec_add(b2, bskip, b2sum, cout, s);
       }));
     }
@@ -294,7 +280,7 @@ int UNetEngine::build_layers() {
     uint16_t* d16 = *w16;
     const int fmt = cfg_.fmt;
     return add_param(name, static_cast<int64_t>(O) * I, [=](const float* src, cudaStream_t s) {
-      CDDPM_CUDA(cudaMemcpyAsync(d32, src, static_cast<size_t>(O) * I * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      CDDPM_TRY(copy_f32_or_record(d32, src, static_cast<long long>(O) * I, s));
       return launch_pack_conv_weight(src, O, I, 1, 0, I, d16, I, 0, fmt, s);
     });
   };

@@ -171,7 +171,7 @@ class UNetEngine {
   void drop_graph();
   cudaStream_t cap_stream_ = nullptr;
   cudaGraphExec_t graph_exec_ = nullptr;
-  cudaGraphExec_t push_graph_ = nullptr;
+  ParamPushTable* push_table_ = nullptr;  // recorded re-layout jobs of a whole-model push (param_push.cu)
   std::vector<const float*> push_key_;
   int forwards_on_plan_ = 0;
   float *stage_x_ = nullptr, *stage_cond_ = nullptr, *stage_out_ = nullptr;
