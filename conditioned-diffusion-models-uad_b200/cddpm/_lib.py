@@ -103,6 +103,10 @@ def _signatures(c):
         "cddpm_row_stats": (i32, [vp, pview, pview, i32, i32, i32, f32, vp, vp, vp]),
         "cddpm_ranking_workspace_bytes": (i64, [i64]),
         "cddpm_ranking_metrics": (i32, [vp, pview, i32, i32, i32, vp, i64, vp, vp]),
+        "cddpm_filter_small_components": (i32, [vp, vp, i32, i32, i32, i32, vp]),
+        "cddpm_confusion_counts": (i32, [vp, pview, i32, i32, i32, vp, vp]),
+        "cddpm_hausdorff_workspace_bytes": (i64, [i32, i32, i32]),
+        "cddpm_hausdorff": (i32, [vp, pview, i32, i32, i32, vp, i64, vp, vp]),
     }
 
 

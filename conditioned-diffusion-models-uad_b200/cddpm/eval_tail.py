@@ -5,10 +5,11 @@ filter_3d_connected_components (:489-503), tpr / fpr (:566-575).
 
 Everything voxel-sized runs on the GPU (residual, eroded-mask multiply, 5x5x5 median, max, Dice counts for the
 threshold bisection, thresholding, row statistics, sort-based AUC / AP): kernels cddpm_residual_erode,
-cddpm_median3d, cddpm_max, cddpm_threshold_counts, cddpm_threshold_mask, cddpm_row_stats, cddpm_ranking_metrics.
-The host keeps only scalar control flow (the bisection decisions, in numpy float32/float64 exactly like the reference)
-and the connected-component filter, which stays on scipy this round.  PNG/wandb logging is out of
-scope.  The quirks of the reference are reproduced on purpose: per-"slice" loops run over image rows (axis 0), the
+cddpm_median3d, cddpm_max, cddpm_threshold_counts, cddpm_threshold_mask, cddpm_row_stats, cddpm_ranking_metrics, and
+ the small-connected-component filter, the confusion counts of the filtered prediction and monai's
+Hausdorff distance: cddpm_filter_small_components, cddpm_confusion_counts, cddpm_hausdorff.
+The host keeps only scalar control flow (the bisection decisions, in numpy float32/float64 exactly like the reference).
+PNG/wandb logging is out of scope.  The quirks of the reference are reproduced on purpose: per-"slice" loops run over image rows (axis 0), the
 confusion-matrix names are permuted (:108), fpr() is FP/(FP+TP) (:572-575).
 """
 from __future__ import annotations
@@ -316,26 +317,76 @@ def fpr(P, G):
         return fp / (fp + tp)
 
 
+def _filter_small_components_device(mask_dhw: torch.Tensor, max_size: int = 7) -> torch.Tensor:
+    """uint8 [D,H,W] on the GPU -> filtered uint8 [D,H,W] (cddpm_filter_small_components)."""
+    D, H, W = mask_dhw.shape
+    out = torch.empty_like(mask_dhw)
+    with torch.cuda.device(mask_dhw.device):
+        check(lib().cddpm_filter_small_components(ptr(mask_dhw), ptr(out), H, W, D, int(max_size), current_stream()),
+              "cddpm_filter_small_components")
+    return out
+
+
 def filter_3d_connected_components(volume):
-    """26-connected components whose hole-filled size is <= 7 are removed (utils_eval.py:489-503).  Host scipy this
-    round; scikit-image's exact `filled_area` is not available in this image (parity unpinned for this step)."""
-    from scipy import ndimage
+    """26-connected components whose hole-filled size is <= 7 are removed (utils_eval.py:489-503): scikit-image fills
+    holes with a full 3x3x3 element, so for components this small `filled_area` is the voxel count and the filter is
+    one GPU kernel in which every foreground voxel walks its own component up to the 8th voxel (csrc/tail_cc.cu).
+    Accepts what the reference passes (bool numpy array or tensor, 3-D, or 4-D folded to [a*b, c, d]); returns the
+    same kind on the same device."""
+    is_np = isinstance(volume, np.ndarray)
+    t = torch.as_tensor(volume)
+    if not t.is_cuda:
+        if not torch.cuda.is_available():
+            raise CddpmError("filter_3d_connected_components needs a CUDA device (no CPU fallback)")
+        t = t.cuda()
+    sz = None
+    if t.ndim > 3:
+        sz = t.shape
+        t = t.reshape(sz[0] * sz[1], sz[2], sz[3])
+    if t.ndim != 3:
+        raise ValueError("filter_3d_connected_components expects a 3-D (or 4-D) volume")
+    out = _filter_small_components_device((t != 0).to(torch.uint8).contiguous()).to(torch.bool)
+    if sz is not None:
+        out = out.reshape(sz)
+    return out.cpu().numpy() if is_np else out
 
-    vol = np.array(volume.cpu() if torch.is_tensor(volume) else volume, dtype=bool)
-    shape = vol.shape
-    if vol.ndim > 3:
-        vol = vol.reshape(shape[0] * shape[1], shape[2], shape[3])
-    lab, _ = ndimage.label(vol, structure=np.ones((3, 3, 3)))
-    for i, sl in enumerate(ndimage.find_objects(lab)):
-        if sl is None:
-            continue
-        region = lab[sl] == (i + 1)
-        if int(ndimage.binary_fill_holes(region).sum()) <= 7:
-            vol[sl][region] = False
-    return vol.reshape(shape)
+
+def _hausdorff_device(pred_dhw: torch.Tensor, v: "_Volume") -> float:
+    """monai compute_hausdorff_distance(pred, seg>0) (utils_eval.py:134) from cddpm_hausdorff's integer results."""
+    H, W, D = v.shape
+    dev = pred_dhw.device
+    with torch.cuda.device(dev):
+        nbytes = int(lib().cddpm_hausdorff_workspace_bytes(H, W, D))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        res = torch.empty(4, dtype=torch.int64, device=dev)
+        sv = v.seg_view
+        check(lib().cddpm_hausdorff(ptr(pred_dhw), ctypes.byref(sv), H, W, D, ptr(ws), nbytes, ptr(res),
+                                    current_stream()), "cddpm_hausdorff")
+    return hausdorff_from_counts(res.cpu().numpy())
 
 
-# ------------------------------------------------------------------------------------------------ _test_step / _test_end
+def hausdorff_from_counts(r) -> float:
+    """[max d^2 pred->seg, max d^2 seg->pred, #surface(pred), #surface(seg)] -> monai's value: nan when both masks are
+    empty, inf when exactly one is, else the float64 square root of the larger squared distance."""
+    if r[2] == 0 and r[3] == 0:
+        return float("nan")
+    if r[2] == 0 or r[3] == 0:
+        return float("inf")
+    return float(np.sqrt(np.float64(max(int(r[0]), int(r[1])))))
+
+
+def compute_hausdorff_distance(pred, seg) -> float:
+    """Public form of the per-volume Hausdorff distance for [H,W,D] volumes (prediction > 0 vs seg > 0)."""
+    if not torch.cuda.is_available():
+        raise CddpmError("compute_hausdorff_distance needs a CUDA device (no CPU fallback)")
+    p = _as_cuda_f32(pred, torch.device("cuda", torch.cuda.current_device()))
+    g = _as_cuda_f32(seg, p.device)
+    if p.ndim != 3 or g.shape != p.shape:
+        raise ValueError("compute_hausdorff_distance expects two [H,W,D] volumes of the same shape")
+    vol = _Volume(p.permute(2, 0, 1).contiguous(), g, g, tuple(p.shape))
+    return _hausdorff_device((vol.diff != 0).to(torch.uint8).contiguous(), vol)
+
+
 def _dist_sum(t: torch.Tensor):
     import torch.distributed as dist
 
@@ -385,22 +436,23 @@ def _test_step(self, final_volume, data_orig, data_seg, data_mask, batch_idx, ID
             tmask = torch.empty(D, H, W, dtype=torch.uint8, device=dev)
             check(lib().cddpm_threshold_mask(ptr(vol.diff), n, float(np.float32(thr)), ptr(tmask), current_stream()),
                   "cddpm_threshold_mask")
-        pred = tmask.cpu().numpy().astype(bool)  # [D,H,W]
-        if "node" not in self.dataset[0].lower():
-            pred = filter_3d_connected_components(pred)
-        g = (vol.seg.permute(2, 0, 1) > 0).cpu().numpy()  # [D,H,W]
-        p_, g_ = pred.ravel(), g.ravel()
-        c11 = int(np.count_nonzero(p_ & g_))
-        c10 = int(np.count_nonzero(p_ & ~g_))
-        c01 = int(np.count_nonzero(~p_ & g_))
-        c00 = int(p_.size - c11 - c10 - c01)
+        with torch.cuda.device(dev):
+            if "node" not in self.dataset[0].lower():
+                tmask = _filter_small_components_device(tmask)
+            cc = torch.zeros(3, dtype=torch.int64, device=dev)
+            sv = vol.seg_view
+            check(lib().cddpm_confusion_counts(ptr(tmask), ctypes.byref(sv), H, W, D, ptr(cc), current_stream()),
+                  "cddpm_confusion_counts")
+        haus = _hausdorff_device(tmask, vol)
+        c11, c10, c01 = (int(x) for x in cc.cpu().numpy())
+        c00 = int(n - c11 - c10 - c01)
         diceScore = _dice_counts(c11 + c10, c11 + c01, c11)
         # confusion_matrix(pred, truth).ravel() unpacked as TP, FP, TN, FN by the reference (:108)
         TP, FP, TN, FN = c00, c01, c10, c11
         with np.errstate(invalid="ignore", divide="ignore"):
             TPR = np.int64(c11) / (np.int64(c11) + np.int64(c01))
             FPR = np.int64(c10) / (np.int64(c10) + np.int64(c11))
-        ed["lesionSizePerVol"].append(int(np.count_nonzero(g_)))
+        ed["lesionSizePerVol"].append(c11 + c01)
         ed["DiceScorePerVol"].append(diceScore)
         ed["BestDicePerVol"].append(bestDice)
         ed["BestThresholdPerVol"].append(bestThresh)
@@ -413,11 +465,11 @@ def _test_step(self, final_volume, data_orig, data_seg, data_mask, batch_idx, ID
         ed["TPRPerVol"].append(TPR)
         ed["FPRPerVol"].append(FPR)
         ed["IDs"].append(ID[0])
-        ed["AccuracyPerVol"].append((c11 + c00) / p_.size)
+        ed["AccuracyPerVol"].append((c11 + c00) / n)
         ed["PrecisionPerVol"].append(c11 / (c11 + c10) if (c11 + c10) else 0.0)
         ed["RecallPerVol"].append(c11 / (c11 + c01) if (c11 + c01) else 0.0)
         ed["SpecificityPerVol"].append(TN / (TN + FP + 0.0000001))
-        ed["HausPerVol"].append(float("nan"))  # monai Hausdorff: SURVEY.md §8 f-4, reported as NaN
+        ed["HausPerVol"].append(haus)
         best_thresh = bestThresh
 
     # row ("slice") statistics in one pass: Dice / precision / recall per row with lesion, masked mean residual per row

@@ -277,6 +277,25 @@ int cddpm_ranking_metrics(const float* x_dhw, const cddpm_vol_view* seg, int H, 
   return launch_ranking_metrics(x_dhw, to_view(seg), H, W, D, workspace, static_cast<size_t>(workspace_bytes), result,
                                 static_cast<cudaStream_t>(stream));
 }
+int cddpm_filter_small_components(const uint8_t* mask_dhw, uint8_t* out_dhw, int H, int W, int D, int max_size,
+                                  void* stream) {
+  return launch_filter_small_components(mask_dhw, out_dhw, H, W, D, max_size, static_cast<cudaStream_t>(stream));
+}
+int cddpm_confusion_counts(const uint8_t* pred_dhw, const cddpm_vol_view* seg, int H, int W, int D, uint64_t* counts,
+                           void* stream) {
+  if (!seg) return fail(kInvalidArgument, "confusion_counts: null view");
+  return launch_confusion_counts(pred_dhw, to_view(seg), H, W, D, reinterpret_cast<unsigned long long*>(counts),
+                                 static_cast<cudaStream_t>(stream));
+}
+int64_t cddpm_hausdorff_workspace_bytes(int H, int W, int D) {
+  return static_cast<int64_t>(hausdorff_workspace_bytes(H, W, D));
+}
+int cddpm_hausdorff(const uint8_t* pred_dhw, const cddpm_vol_view* seg, int H, int W, int D, void* workspace,
+                    int64_t workspace_bytes, int64_t* result, void* stream) {
+  if (!seg) return fail(kInvalidArgument, "hausdorff: null view");
+  return launch_hausdorff(pred_dhw, to_view(seg), H, W, D, workspace, static_cast<size_t>(workspace_bytes),
+                          reinterpret_cast<long long*>(result), static_cast<cudaStream_t>(stream));
+}
 
 struct cddpm_unet {
   UNetEngine engine;

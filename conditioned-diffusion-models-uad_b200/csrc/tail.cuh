@@ -48,4 +48,13 @@ size_t ranking_workspace_bytes(int64_t n);
 int launch_ranking_metrics(const float* x, const VolView& seg, int H, int W, int D, void* workspace,
                            size_t workspace_bytes, double* result, cudaStream_t stream);
 
+// SURVEY.md §8 f-4 (tail_cc.cu): small-component filter, confusion counts, Hausdorff distance.  See include/cddpm_b200.h.
+int launch_filter_small_components(const unsigned char* in, unsigned char* out, int H, int W, int D, int max_size,
+                                   cudaStream_t stream);
+int launch_confusion_counts(const unsigned char* pred, const VolView& seg, int H, int W, int D,
+                            unsigned long long* counts, cudaStream_t stream);
+size_t hausdorff_workspace_bytes(int H, int W, int D);
+int launch_hausdorff(const unsigned char* pred, const VolView& seg, int H, int W, int D, void* workspace,
+                     size_t workspace_bytes, long long* result, cudaStream_t stream);
+
 }  // namespace cddpm

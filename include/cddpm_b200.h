@@ -264,6 +264,26 @@ int64_t cddpm_ranking_workspace_bytes(int64_t n);
 int cddpm_ranking_metrics(const float* x_dhw, const cddpm_vol_view* seg, int H, int W, int D, void* workspace,
                           int64_t workspace_bytes, double* result, void* stream);
 
+/* filter_3d_connected_components (utils_eval.py:489-503; called at :100-102): skimage label(connectivity=3) and
+ * regionprops.filled_area <= 7.  skimage fills holes with a full 3x3x3 element, so filled_area == area whenever
+ * area <= 25: the filter drops every 26-connected component of at most max_size (reference: 7; <= 15) voxels.
+ * mask_dhw / out_dhw: uint8 [D,H,W] buffers (0 / 1), not in place. */
+int cddpm_filter_small_components(const uint8_t* mask_dhw, uint8_t* out_dhw, int H, int W, int D, int max_size,
+                                  void* stream);
+/* counts[0] += #(pred and seg>0), counts[1] += #(pred and not seg>0), counts[2] += #(not pred and seg>0): the
+ * confusion_matrix / dice / tpr / fpr / precision / recall inputs of :105-129.  Accumulates (caller zeroes). */
+int cddpm_confusion_counts(const uint8_t* pred_dhw, const cddpm_vol_view* seg, int H, int W, int D, uint64_t* counts,
+                           void* stream);
+/* monai.metrics.compute_hausdorff_distance(pred, seg, include_background=False, 'euclidean', percentile=None,
+ * directed=False) (utils_eval.py:134) in integer-exact form.  result (4 x int64, device): [0] max over pred surface
+ * voxels of the squared distance to the seg surface, [1] the reverse, [2] / [3] number of surface voxels of pred /
+ * seg>0 (surface = mask minus its 6-neighbour erosion, zero border).  [0]/[1] are -1 when their own surface is
+ * empty and >= 2^28 when the other one is.  Distance = sqrt(max([0],[1])) in float64 on the host; monai's corner
+ * cases (nan when both are empty, inf when one is) follow from [2],[3]. */
+int64_t cddpm_hausdorff_workspace_bytes(int H, int W, int D);
+int cddpm_hausdorff(const uint8_t* pred_dhw, const cddpm_vol_view* seg, int H, int W, int D, void* workspace,
+                    int64_t workspace_bytes, int64_t* result, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

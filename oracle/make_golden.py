@@ -241,7 +241,7 @@ def golden_tail():
                      "l1recoErrorUnhealthy", "l1recoErrorHealthy", "l2recoErrorUnhealthy", "l2recoErrorHealthy",
                      "AccuracyPerVol", "PrecisionPerVol", "RecallPerVol", "SpecificityPerVol", "lesionSizePerVol",
                      "DiceScorePerSlice", "AnomalyScoreRecoPerSlice", "labelPerSlice", "AnomalyScoreRecoPerVol",
-                     "AUCAnomalyRecoPerSlice", "AUPRCAnomalyRecoPerSlice")}
+                     "AUCAnomalyRecoPerSlice", "AUPRCAnomalyRecoPerSlice", "HausPerVol")}
         utils_eval._test_end(host)
         total = host.threshold["total"]
         # port parity on the val stage
@@ -252,6 +252,7 @@ def golden_tail():
             assert (p["TP"], p["FP"], p["TN"], p["FN"]) == tuple(int(val_dict[k][i]) for k in ("TPPerVol", "FPPerVol", "TNPerVol", "FNPerVol"))
             assert abs(p["AUC"] - val_dict["AUCPerVol"][i]) < 1e-12 and abs(p["AUPRC"] - val_dict["AUPRCPerVol"][i]) < 1e-12
             assert abs(p["l1recoErrorAll"] - val_dict["l1recoErrorAll"][i]) < 1e-7
+            assert p["Haus"] == val_dict["HausPerVol"][i] or (np.isnan(p["Haus"]) and np.isnan(val_dict["HausPerVol"][i]))
             assert abs(float(p["AnomalyScoreRecoPerVol"]) - float(val_dict["AnomalyScoreRecoPerVol"][i])) < 1e-7
         flat = np.concatenate([p["diff_filtered"].flatten() for p in ports])
         gflat = np.concatenate([(v["seg_orig"][0, 0].numpy() > 0).flatten() for v in vols])

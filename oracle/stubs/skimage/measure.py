@@ -1,6 +1,7 @@
 """Stand-in for skimage.measure.{label, regionprops} built on scipy.ndimage (utils_eval.py:4,495-499).
-filled_area = voxel count of the component after hole filling inside its bounding box.  PARITY UNPINNED against
-real scikit-image (not installed here)."""
+filled_area = voxel count of the component after hole filling inside its bounding box, with scikit-image's structuring
+element (RegionProperties.image_filled: np.ones((3,) * ndim)).  PARITY UNPINNED against real scikit-image (not installed
+here)."""
 import numpy as np
 from scipy import ndimage
 
@@ -24,6 +25,6 @@ def regionprops(lab):
         if sl is None:
             continue
         region = lab[sl] == (i + 1)
-        filled = ndimage.binary_fill_holes(region)
+        filled = ndimage.binary_fill_holes(region, structure=np.ones((3,) * region.ndim))
         out.append(_Region(label=i + 1, filled_area=int(filled.sum()), area=int(region.sum())))
     return out

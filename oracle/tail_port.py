@@ -7,6 +7,8 @@ numpy restatement of the anomaly-scoring tail of the reference (src/utils/utils_
   find_best_val / dice                         :508-545
   compute_roc / compute_prc                    :548-557   (sklearn roc_curve+auc, average_precision_score)
   tpr / fpr                                    :566-575
+  filter_3d_connected_components               :489-503   (skimage label + filled_area, restated; scikit-image absent)
+  monai compute_hausdorff_distance             :134       (restated from monai's published source; monai absent)
   _test_step metric flow                       :18-194
 Where the reference calls scipy / sklearn (both present in this image) the restatement is ALSO checked against
 those libraries directly in tests/test_oracle_tail.py; against the live reference via tests/golden/tail_*.npz.
@@ -138,19 +140,65 @@ def fpr(P, G):
 
 
 def filter_small_components(vol: np.ndarray, max_size: int = 7) -> np.ndarray:
-    """filter_3d_connected_components (utils_eval.py:489-503) with the scipy stand-in for skimage (26-connectivity,
-    drop components whose hole-filled size <= 7).  PARITY UNPINNED against real scikit-image."""
+    """filter_3d_connected_components (utils_eval.py:489-503): skimage.measure.label(volume, connectivity=3), then every
+    region whose regionprops `filled_area` <= 7 is zeroed.  scikit-image is NOT in this image (PARITY UNPINNED against
+    it); restated from its published source: label(connectivity=ndim) = full 3x3x3 adjacency; RegionProperties.
+    image_filled = scipy.ndimage.binary_fill_holes(region.image, structure=np.ones((3,) * ndim)) on the bounding-box
+    crop, filled_area = its sum.  With the full structuring element the background leaks through every diagonal gap,
+    so a hole needs a closed 26-voxel shell: for components this small filled_area equals area (asserted below)."""
     from scipy import ndimage
 
     vol = np.array(vol, dtype=bool)
-    lab, _ = ndimage.label(vol, structure=np.ones((3, 3, 3)))
+    full = np.ones((3, 3, 3))
+    lab, _ = ndimage.label(vol, structure=full)
     for i, sl in enumerate(ndimage.find_objects(lab)):
         if sl is None:
             continue
         region = lab[sl] == (i + 1)
-        if int(ndimage.binary_fill_holes(region).sum()) <= max_size:
+        filled = int(ndimage.binary_fill_holes(region, structure=full).sum())
+        if filled <= max_size:
+            assert filled == int(region.sum())
             vol[sl][region] = False
     return vol
+
+
+def mask_edges(mask: np.ndarray) -> np.ndarray:
+    """monai.metrics.utils.get_mask_edges (monai 0.9, not installed here - PARITY UNPINNED, restated from the published
+    source): edges = binary_erosion(mask) ^ mask with scipy's default cross structuring element and border_value 0.
+    monai first crops both masks to the bounding box of their union; outside that box both are background, so the
+    erosion sees the same zeros either way and the crop only shifts coordinates."""
+    from scipy import ndimage
+
+    mask = np.asarray(mask, dtype=bool)
+    return ndimage.binary_erosion(mask) ^ mask
+
+
+def _surface_distance(edges_pred: np.ndarray, edges_gt: np.ndarray) -> np.ndarray:
+    """monai.metrics.utils.get_surface_distance(distance_metric='euclidean')."""
+    from scipy import ndimage
+
+    if not np.any(edges_gt):
+        dis = np.inf * np.ones_like(edges_gt, dtype=np.float64)
+    else:
+        if not np.any(edges_pred):
+            dis = np.inf * np.ones_like(edges_gt, dtype=np.float64)
+            return np.asarray(dis[edges_gt])
+        dis = ndimage.distance_transform_edt(~edges_gt)
+    return np.asarray(dis[edges_pred])
+
+
+def hausdorff_distance(pred: np.ndarray, gt: np.ndarray) -> float:
+    """monai.metrics.compute_hausdorff_distance(pred[None, None], gt[None, None], include_background=False,
+    distance_metric='euclidean', percentile=None, directed=False) for one binary volume pair (utils_eval.py:134):
+    max of the two directed distances, each the max over one surface of the Euclidean distance to the other surface;
+    nan when both masks are empty, inf when exactly one is."""
+    ep, eg = mask_edges(pred), mask_edges(gt)
+
+    def directed(a, b):
+        sd = _surface_distance(a, b)
+        return float("nan") if sd.shape == (0,) else float(sd.max())
+
+    return max(directed(ep, eg), directed(eg, ep))
 
 
 # ---------------------------------------------------------------------------------------------- _test_step flow
@@ -191,6 +239,7 @@ def volume_tail(reco: np.ndarray, orig: np.ndarray, seg: np.ndarray, mask: np.nd
     thr = diff > best_thresh
     thr = filter_small_components(thr)
     out["thresholded"] = thr
+    out["Haus"] = hausdorff_distance(thr, segb)
     out["Dice"] = dice(thr, g)
     p = thr.flatten()
     # confusion_matrix(pred, truth).ravel() with the reference's (permuted) names (utils_eval.py:108)

@@ -141,6 +141,55 @@ def test_volume_tail_port_matches_reference_golden():
         assert (p["TP"], p["FP"], p["TN"], p["FN"]) == tuple(int(gold["val"][k][i]) for k in ("TPPerVol", "FPPerVol", "TNPerVol", "FNPerVol"))
         assert abs(p["AUPRC"] - gold["val"]["AUPRCPerVol"][i]) < 1e-12
         assert abs(float(p["diff_filtered"].astype(np.float64).sum()) - gold["filtered_sum"][i]) < 1e-9
+        assert p["Haus"] == gold["val"]["HausPerVol"][i]
+        assert int(p["thresholded"].sum()) == gold["thresholded_count"][i]
+
+
+def test_component_filter_and_hausdorff_ports():
+    """The two restatements without a live library behind them (scikit-image, monai absent): checked against
+    independent brute-force statements of the published definitions."""
+    from scipy import ndimage
+
+    from oracle import tail_port
+
+    rng = np.random.default_rng(3)
+    v = rng.random((6, 14, 14)) < 0.12
+    got = tail_port.filter_small_components(v)
+    lab, n = ndimage.label(v, structure=np.ones((3, 3, 3)))
+    sizes = ndimage.sum(v, lab, index=np.arange(1, n + 1))
+    want = np.isin(lab, 1 + np.flatnonzero(sizes > 7))
+    assert np.array_equal(got, want) and 0 < want.sum() < v.sum()
+    # octahedron shell + 1: seven voxels around an empty centre are NOT a hole under skimage's full structuring element
+    o = np.zeros((7, 7, 7), bool)
+    for d in ((1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1)):
+        o[3 + d[0], 3 + d[1], 3 + d[2]] = True
+    o[5, 3, 3] = True
+    assert not tail_port.filter_small_components(o).any()
+
+    def brute(a, b):
+        def surf(m):
+            p = np.pad(m, 1)
+            inner = p[1:-1, 1:-1, 1:-1].copy()
+            for ax in range(3):
+                for sh in (-1, 1):
+                    inner &= np.roll(p, sh, axis=ax)[1:-1, 1:-1, 1:-1]
+            return np.argwhere(m & ~inner)
+        pa, pb = surf(a), surf(b)
+        if len(pa) == 0 and len(pb) == 0:
+            return float("nan")
+        if len(pa) == 0 or len(pb) == 0:
+            return float("inf")
+        d2 = ((pa[:, None, :] - pb[None, :, :]) ** 2).sum(-1)
+        return float(np.sqrt(np.float64(max(d2.min(1).max(), d2.min(0).max()))))
+
+    for seed in range(4):
+        r = np.random.default_rng(seed)
+        a = ndimage.binary_dilation(r.random((8, 12, 10)) < 0.01, iterations=2)
+        b = ndimage.binary_dilation(r.random((8, 12, 10)) < 0.01, iterations=1)
+        w, g = brute(a, b), tail_port.hausdorff_distance(a, b)
+        assert w == g or (np.isnan(w) and np.isnan(g))
+    z = np.zeros((4, 4, 4), bool)
+    assert np.isnan(tail_port.hausdorff_distance(z, z)) and tail_port.hausdorff_distance(~z, z) == float("inf")
 
 
 def test_encoder_port_matches_golden():

@@ -107,6 +107,7 @@ def test_volume_tail_matches_oracle_port_and_reference(depth):
             assert abs(ed[k][i] - gold["val"][k][i]) < 1e-6 * max(1.0, abs(gold["val"][k][i]))
         assert abs(ed["AnomalyScoreRecoPerVol"][i] - gold["val"]["AnomalyScoreRecoPerVol"][i]) < 1e-6
         assert ed["lesionSizePerVol"][i] == int(gold["val"]["lesionSizePerVol"][i])
+        assert ed["HausPerVol"][i] == port["Haus"] == gold["val"]["HausPerVol"][i]  # sqrt of an exact integer
         assert abs(ed["TPRPerVol"][i] - gold["val"]["TPRPerVol"][i]) < 1e-12
         assert abs(ed["SpecificityPerVol"][i] - gold["val"]["SpecificityPerVol"][i]) < 1e-12
     ed = host.eval_dict
@@ -157,3 +158,118 @@ def test_find_best_val_and_ranking_standalone():
     auc, *_ = eval_tail.compute_roc(torch.from_numpy(x).cuda(), y)
     ap, *_ = eval_tail.compute_prc(torch.from_numpy(x).cuda(), y)
     assert abs(auc - tail_port.roc_auc(x, y)) < 1e-12 and abs(ap - tail_port.average_precision(x, y)) < 1e-12
+
+
+def _octahedron_plus_one():
+    """Six face neighbours of an empty centre plus one attached voxel: 7 voxels.  With skimage's full structuring
+    element the centre is not a hole (filled_area 7 -> removed); a 6-connected fill would call it 8 and keep it."""
+    v = np.zeros((7, 7, 7), bool)
+    for d in ((1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1)):
+        v[3 + d[0], 3 + d[1], 3 + d[2]] = True
+    v[5, 3, 3] = True
+    return v
+
+
+@pytest.mark.parametrize("shape,density", [((50, 96, 96), 0.02), ((50, 96, 96), 0.08), ((4, 96, 96), 0.05),
+                                            ((3, 5, 7), 0.3), ((1, 1, 9), 0.6), ((20, 32, 32), 0.15)])
+def test_small_component_filter_bit_exact_vs_oracle(shape, density):
+    from cddpm.eval_tail import filter_3d_connected_components
+    from oracle import tail_port
+
+    rng = np.random.default_rng(hash((shape, density)) % (1 << 31))
+    v = rng.random(shape) < density
+    want = tail_port.filter_small_components(v)
+    got = filter_3d_connected_components(v.copy())
+    assert isinstance(got, np.ndarray) and got.dtype == bool
+    assert np.array_equal(got, want)
+    assert 0 < want.sum() < v.sum() or v.size < 200
+    # tensor in -> tensor out on the same device; idempotent; only removes voxels
+    t = filter_3d_connected_components(torch.from_numpy(v).cuda())
+    assert t.is_cuda and np.array_equal(t.cpu().numpy(), want)
+    assert np.array_equal(filter_3d_connected_components(want.copy()), want)
+    assert not (want & ~v).any()
+
+
+def test_small_component_filter_edge_cases():
+    from cddpm.eval_tail import filter_3d_connected_components
+    from oracle import tail_port
+
+    o = _octahedron_plus_one()
+    assert not tail_port.filter_small_components(o).any()
+    assert not filter_3d_connected_components(o.copy()).any()
+    # 8 voxels in a diagonal chain (26-connectivity only) stay, 7 go; components touching the border
+    chain = np.zeros((10, 10, 10), bool)
+    for i in range(8):
+        chain[i, i, i] = True
+    chain[9, 0, 0:7] = True
+    want = tail_port.filter_small_components(chain)
+    assert want.sum() == 8
+    assert np.array_equal(filter_3d_connected_components(chain.copy()), want)
+    # empty, full, 4-D input folded like the reference does (:491-493)
+    z = np.zeros((4, 6, 6), bool)
+    assert not filter_3d_connected_components(z).any()
+    assert filter_3d_connected_components(~z).all()
+    v4 = np.random.default_rng(5).random((2, 3, 8, 8)) < 0.2
+    want4 = tail_port.filter_small_components(v4.reshape(6, 8, 8)).reshape(v4.shape)
+    assert np.array_equal(filter_3d_connected_components(v4.copy()), want4)
+
+
+def _blobs(shape, seed, n, rmax):
+    rng = np.random.default_rng(seed)
+    zz, yy, xx = np.meshgrid(*(np.arange(s) for s in shape), indexing="ij")
+    v = np.zeros(shape, bool)
+    for _ in range(n):
+        c = [rng.integers(0, s) for s in shape]
+        r = rng.uniform(1, rmax)
+        v |= (zz - c[0]) ** 2 + (yy - c[1]) ** 2 + (xx - c[2]) ** 2 <= r * r
+    return v
+
+
+@pytest.mark.parametrize("shape", [(96, 96, 50), (96, 96, 4), (5, 7, 3), (1, 1, 1), (33, 17, 2)])
+def test_hausdorff_bit_exact_vs_oracle(shape):
+    from cddpm.eval_tail import compute_hausdorff_distance
+    from oracle import tail_port
+
+    for seed in range(3):
+        a = _blobs(shape, seed, 3, 9.0)
+        b = _blobs(shape, 100 + seed, 2, 7.0)
+        want = tail_port.hausdorff_distance(a, b)
+        got = compute_hausdorff_distance(torch.from_numpy(a).float().cuda(), torch.from_numpy(b).float().cuda())
+        assert got == want or (np.isnan(got) and np.isnan(want)), (shape, seed, got, want)
+        # symmetric, zero against itself
+        assert compute_hausdorff_distance(b.astype(np.float32), a.astype(np.float32)) == got or np.isnan(got)
+        if a.any():
+            assert compute_hausdorff_distance(a.astype(np.float32), a.astype(np.float32)) == 0.0
+    z = np.zeros(shape, np.float32)
+    one = z.copy()
+    one[0, 0, 0] = 1
+    assert np.isnan(compute_hausdorff_distance(z, z))          # monai: both empty -> nan
+    assert compute_hausdorff_distance(one, z) == float("inf")  # one empty -> inf
+    assert compute_hausdorff_distance(z, one) == float("inf")
+    far = z.copy()
+    far[-1, -1, -1] = 1
+    d2 = sum((s - 1) ** 2 for s in shape)
+    assert compute_hausdorff_distance(one, far) == float(np.sqrt(np.float64(d2)))
+
+
+def test_hausdorff_on_strided_seg_view_and_counts():
+    """seg arrives in the dataloader layout [H,W,D] while the prediction buffer is [D,H,W]."""
+    import ctypes
+
+    from cddpm import eval_tail
+    from cddpm._lib import check, current_stream, lib, ptr
+    from oracle import tail_port
+
+    shape = (40, 48, 12)
+    pred = _blobs(shape, 7, 4, 6.0)
+    seg = _blobs(shape, 8, 3, 8.0)
+    segt = torch.from_numpy(seg.astype(np.float32) * 3.0).cuda()  # any value > 0 counts
+    predt = torch.from_numpy(pred).cuda()
+    vol = eval_tail._Volume(predt.permute(2, 0, 1).float().contiguous(), segt, segt, shape)
+    p8 = predt.permute(2, 0, 1).to(torch.uint8).contiguous()
+    assert eval_tail._hausdorff_device(p8, vol) == tail_port.hausdorff_distance(pred, seg)
+    cc = torch.zeros(3, dtype=torch.int64, device="cuda")
+    sv = vol.seg_view
+    check(lib().cddpm_confusion_counts(ptr(p8), ctypes.byref(sv), shape[0], shape[1], shape[2], ptr(cc), current_stream()),
+          "cddpm_confusion_counts")
+    assert cc.tolist() == [int((pred & seg).sum()), int((pred & ~seg).sum()), int((~pred & seg).sum())]
