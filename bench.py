@@ -50,6 +50,29 @@ def model_cfg():
                pretrained_encoder=False, objective="pred_x0")
 
 
+def synthetic_volume(seed: int, depth: int = 50, size: int = 96):
+    """One synthetic BraTS21-shaped case, [1,1,H,W,D] float32 host tensors: a smooth 0.2-0.8
+    field inside an ellipsoid brain mask, 1-3 spherical lesions (+0.3) as the segmentation."""
+    import torch
+
+    g = torch.Generator().manual_seed(7000 + seed)
+    H = W = size
+    coarse = torch.rand(1, 1, 12, 12, max(2, depth // 5), generator=g)
+    field = 0.2 + 0.6 * torch.nn.functional.interpolate(coarse, size=(H, W, depth), mode="trilinear", align_corners=True)[0, 0]
+    y, x, z = torch.meshgrid(torch.arange(H), torch.arange(W), torch.arange(depth), indexing="ij")
+    c = ((H - 1) / 2, (W - 1) / 2, (depth - 1) / 2)
+    mask = ((y - c[0]) / (0.42 * H)) ** 2 + ((x - c[1]) / (0.36 * W)) ** 2 + ((z - c[2]) / (0.48 * depth)) ** 2 <= 1
+    seg = torch.zeros_like(mask)
+    for _ in range(int(torch.randint(1, 4, (1,), generator=g))):
+        r = float(torch.randint(3, 9, (1,), generator=g))
+        p = [c[i] + float(torch.randn(1, generator=g)) * f * n for i, (f, n) in enumerate(((0.12, H), (0.1, W), (0.12, depth)))]
+        seg |= (y - p[0]) ** 2 + (x - p[1]) ** 2 + (z - p[2]) ** 2 <= r * r
+    seg &= mask
+    vol = (field * mask + 0.3 * seg.float()).clamp(0, 1)
+    u = lambda t: t.float()[None, None].contiguous()  # noqa: E731
+    return {"vol": u(vol), "mask_orig": u(mask), "seg_orig": u(seg)}
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -485,6 +508,189 @@ def run_train(args):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------- volume workload
+VOLUME_METRIC = ("volumes/sec (cDDPM full-volume reconstruction + anomaly map: encoder, 3-step noise ensemble over all "
+                 "slices, residual, eroded brain mask, 5x5x5 median, threshold search, component filter, Dice/AUROC/AUPRC/"
+                 "Hausdorff)")
+# launches of the anomaly-scoring tail per volume: residual_erode, median, max, 10 bisection count launches, ranking
+# (gather, sort, 2 scans, 3 small), threshold mask, component filter, confusion counts, Hausdorff (6), row statistics
+TAIL_LAUNCHES = 1 + 1 + 1 + 10 + 8 + 1 + 1 + 1 + 6 + 1
+
+
+def cpu_volume_sample(depth: int, threads: int):
+    """Oracle port on the host cores: encoder + the three ensemble reconstructions for a 2-slice sample (extrapolated to
+    `depth` slices) + the whole numpy / scipy tail of one volume.  Returns volumes/s."""
+    import numpy as np
+    import torch
+
+    from oracle import diffusion_port, resnet_port, tail_port, unet_port
+    from oracle.simplex_port import gen_noise_port
+    from oracle.weights import make_state_dict
+
+    torch.set_num_threads(threads)
+    spec = unet_port.UNetSpec()
+    sd = make_state_dict(unet_port.param_shapes(spec), seed=1)
+    esd = make_state_dict(resnet_port.param_shapes(128), seed=3)
+    sched = diffusion_port.schedule_buffers()
+    v = synthetic_volume(0, depth)
+    vol = v["vol"][0, 0]
+    x = vol[..., depth // 2:depth // 2 + 2].permute(2, 0, 1)[:, None].contiguous()
+    np.random.seed(0)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        cond = resnet_port.resnet_forward(esd, x)
+        recos = []
+        for t in (250, 500, 750):
+            noise = gen_noise_port(tuple(x.shape))
+            tt = torch.full((x.shape[0],), t - 1, dtype=torch.long)
+            xt = diffusion_port.q_sample(sched, x * 2 - 1, tt, noise)
+            recos.append((unet_port.unet_forward(sd, spec, xt, tt, cond).clamp(-1, 1) + 1) / 2)
+        t_model = (time.perf_counter() - t0) * depth / x.shape[0]
+    reco = (vol * v["mask_orig"][0, 0]).numpy()
+    t0 = time.perf_counter()
+    tail_port.volume_tail(reco, vol.numpy(), v["seg_orig"][0, 0].numpy(), v["mask_orig"][0, 0].numpy(), stage="val")
+    t_tail = time.perf_counter() - t0
+    return 1.0 / (t_model + t_tail), {"t_model_s": t_model, "t_tail_s": t_tail}
+
+
+def run_volume(args):
+    """BASELINE.json configs[2] (not the headline line): `python bench.py --workload volume [--batch 8]`: per step,
+    `batch` synthetic BraTS21-shaped [1,1,96,96,50] volumes per GPU through the validation stage of the test sweep
+    (on_test_start, test_step per volume, on_test_end with the global threshold search)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the cDDPM engine has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from cddpm.ddpm_2d import DDPM_2D
+    from cddpm.sweep import run_stage
+
+    NV, D = args.batch, 50
+    torch.manual_seed(1234)
+    np.random.seed(1234 + rank)
+    cfg = model_cfg()
+    cfg["force_num_eval_slices"] = False  # all 50 slices, not the fork's hard-coded 4
+    model = DDPM_2D(cfg, prefix="bench/")
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if p.dim() >= 2 and float(p.abs().sum()) == 0.0:
+                p.normal_(0.0, 1.0 / p[0].numel() ** 0.5)
+    model = model.to(dev).eval()
+    unet = model.diffusion.model
+
+    def batch_of(v):
+        return {"Dataset": ["Brats21"], "vol": {"data": v["vol"]}, "vol_orig": {"data": v["vol"]},
+                "seg_orig": {"data": v["seg_orig"]}, "mask_orig": {"data": v["mask_orig"]}, "seg_available": True,
+                "ID": ["synthetic"], "stage": "val", "label": torch.tensor([1])}
+
+    # run_stage deals the list round-robin to ranks: NV volumes per GPU; only this rank's entries carry data
+    host, resident = [], []
+    for i in range(NV * world):
+        if i % world == rank:
+            v = {k: t.pin_memory() for k, t in synthetic_volume(i, D).items()}
+            host.append(batch_of(v))
+            resident.append(batch_of({k: t.to(dev) for k, t in v.items()}))
+        else:
+            host.append(None)
+            resident.append(None)
+
+    def step(batches):
+        ed = run_stage(model, batches, dev)
+        return float(model.threshold["total"]), ed
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(resident)
+    barrier()
+    eng = unet.engine()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    conv_ms, conv_launches = [], 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for it in range(args.steps):
+        if it == 0:
+            eng.profile_arm()  # the first UNet forward of the first step is bracketed per convolution launch
+        thr, ed = step(resident)
+        if it == 0:
+            ms, n = eng.profile_read()
+            conv_ms.append(ms)
+            conv_launches = n
+    e1.record()
+    barrier()
+    dt_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else {}
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        thr, ed = step(host)  # pinned host tensors in, eval_dict scalars out
+    f1.record()
+    barrier()
+    e2e_ms = f0.elapsed_time(f1)
+    t = torch.tensor([dt_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt_ms, e2e_ms = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    vols = NV * world * args.steps
+    pk = peaks()
+    conv_flops_fwd = eng.conv_flops_per_sample * D
+    conv_ms_fwd = statistics.median(conv_ms)
+    achieved = conv_flops_fwd / (conv_ms_fwd / 1e3) / 1e12
+    enc_launches = 1 + 1 + 16 * 4 + 4 + 3 + 2
+    per_volume = enc_launches + 3 * (eng.launches_per_forward + 3) + TAIL_LAUNCHES
+    line = {"metric": VOLUME_METRIC, "value": vols / (dt_ms / 1e3), "unit": "volumes/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": f"configs[2]: full-volume reconstruction + anomaly map, {NV} synthetic BraTS21-shaped "
+                                   f"[1,1,96,96,{D}] volumes per GPU per step, validation stage of the test sweep "
+                                   "(noise ensemble 250/500/750, all slices), global threshold search at the end",
+                       "volumes_per_gpu": NV, "slices_per_volume": D, "image": "1x96x96",
+                       "parallelism": f"volume-sharded x{world}; all-gather of per-volume results + all-reduce of the "
+                                      "threshold-search counts at the end of the stage",
+                       "l2": "streaming working set ~3 GB per B=50 UNet forward >> 126 MB L2 (no flush needed)"},
+            "roofline": {"bound": "tensor", "kernel": "conv_igemm2_kernel / conv_igemm_kernel (every convolution and GEMM "
+                                                       "launch of the first B=50 UNet forward of a step)",
+                         "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
+                         "peak_source": pk["source"], "flops_per_launch": conv_flops_fwd / max(1, conv_launches),
+                         "avg_launch_ms": conv_ms_fwd / max(1, conv_launches), "launches_timed": conv_launches * len(conv_ms),
+                         "traffic": None},
+            "e2e": {"value": vols / (e2e_ms / 1e3), "unit": "volumes/s", "h2d_bytes_per_step": NV * 4 * 96 * 96 * D * 4,
+                    "d2h_bytes_per_step": NV * (128 * 4 + 4 + 7 * 8 + 2 * 8 + 10 * 5 * 8 + 3 * 8 + 4 * 8 + 96 * 5 * 8 + 4),
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": per_volume * NV * args.steps, "clocks": clocks,
+            "slices_per_s": vols * D / (dt_ms / 1e3), "unet_slice_evaluations_per_s": vols * D * 3 / (dt_ms / 1e3),
+            "val_threshold": thr}
+    if not args.no_cpu_baseline and world == 1:
+        threads = host_threads()
+        v, parts = cpu_volume_sample(D, threads)
+        line["cpu_baseline"] = {"value": v, "unit": "volumes/s", "cores": threads, "kind": "port",
+                                "sample": "oracle port (fp32 PyTorch + numpy/scipy) on the host: encoder + 3 ensemble "
+                                          f"reconstructions of 2 slices extrapolated to {D}, plus the full tail of one volume",
+                                **parts}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def lib_bwd_launches(eng):
     from cddpm._lib import lib
 
@@ -498,19 +704,22 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=None)
-    ap.add_argument("--workload", default="reverse", choices=["reverse", "train"],
-                    help="reverse = BASELINE configs[1] (the headline line, default); train = configs[4]")
+    ap.add_argument("--workload", default="reverse", choices=["reverse", "train", "volume"],
+                    help="reverse = BASELINE configs[1] (the headline line, default); volume = configs[2] (--batch = "
+                         "volumes per GPU per step); train = configs[4]")
     ap.add_argument("--start-t", dest="start_t", type=int, default=500)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         print(f"note: --warmup {args.warmup} < 3 breaks the timing rules; use >= 3 for a reportable number", file=sys.stderr)
     if args.batch is None:
-        args.batch = 64 if args.workload == "train" else 32
+        args.batch = {"train": 64, "volume": 8}.get(args.workload, 32)
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "train":
         run_train(args)
+    elif args.workload == "volume":
+        run_volume(args)
     else:
         run_ours(args)
 

@@ -161,18 +161,23 @@ class DDPM_2D(LightningModule):
 
     @torch.no_grad()
     def test_step(self, batch: Any, batch_idx: int):
+        """DDPM_2D.test_step (DDPM_2D.py:171-286): reconstruction of every slice, then the model-independent tail."""
+        return self.test_step_finish(self.test_step_reconstruct(batch), batch_idx)
+
+    @torch.no_grad()
+    def test_step_reconstruct(self, batch: Any):
+        """First half of test_step: everything that only ENQUEUES GPU work (slice crop, encoder, noise ensemble).  No
+        host read of a device value happens here, so a sweep can enqueue volume i+1 before it scores volume i
+        (cddpm/sweep.py:run_stage).  Returns the state test_step_finish needs."""
         self.dataset = batch["Dataset"]
         input = batch["vol"][DATA]
         data_orig = batch["vol_orig"][DATA]
         data_seg = batch["seg_orig"][DATA] if batch["seg_available"] else torch.zeros_like(data_orig)
         data_mask = batch["mask_orig"][DATA]
-        ID = batch["ID"]
-        self.stage = batch["stage"]
-        label = batch["label"]
         dev = self.device
         if dev.type != "cuda":
             raise CddpmError("DDPM_2D.test_step needs the module on a CUDA device (there is no CPU path)")
-        input, data_orig, data_seg, data_mask = (t.to(dev) for t in (input, data_orig, data_seg, data_mask))
+        input, data_orig, data_seg, data_mask = (t.to(dev, non_blocking=True) for t in (input, data_orig, data_seg, data_mask))
 
         if self.cfg.get("force_num_eval_slices", True):
             self.cfg["num_eval_slices"] = 4  # the fork's hard-coded value (DDPM_2D.py:193)
@@ -185,7 +190,22 @@ class DDPM_2D(LightningModule):
         assert input.shape[0] == 1, "Batch size must be 1"
         input = input.squeeze(0).permute(3, 0, 1, 2).contiguous()  # [1,C,H,W,D] -> [D,C,H,W]
         reco, loss_diff, features = self.reconstruct_slices(input)
-        latent = features.mean(0).squeeze().detach().cpu() if self.cfg.condition else torch.tensor([0], dtype=float).repeat(input.shape[0])
+        latent = features.mean(0).squeeze() if self.cfg.condition else None
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream(dev))
+        return {"reco": reco, "loss_diff": loss_diff, "latent": latent, "n_slices": input.shape[0], "orig": data_orig,
+                "seg": data_seg, "mask": data_mask, "ID": batch["ID"], "stage": batch["stage"], "label": batch["label"],
+                "dataset": batch["Dataset"], "done": done}
+
+    @torch.no_grad()
+    def test_step_finish(self, st: Any, batch_idx: int):
+        """Second half of test_step: the host reads (latent, loss) and utils_eval._test_step.  Runs on the CURRENT
+        stream, which is made to wait for the reconstruction's event first."""
+        torch.cuda.current_stream(st["reco"].device).wait_event(st["done"])
+        self.dataset = st["dataset"]
+        self.stage = st["stage"]
+        reco, loss_diff = st["reco"], st["loss_diff"]
+        latent = st["latent"].detach().cpu() if self.cfg.condition else torch.tensor([0], dtype=float).repeat(st["n_slices"])
         self.latentSpace_slice.extend([latent])
         self.eval_dict["latentSpace"].append(torch.mean(torch.stack([latent]), 0))
         score = np.mean([loss_diff.cpu()])
@@ -198,7 +218,7 @@ class DDPM_2D(LightningModule):
             self.eval_dict["AnomalyScoreCombiPriorPerVol"].append(score * 0)
         # [D,1,H,W] -> logical [1,1,H,W,D] without a copy: the tail kernels read the strided view in place
         final_volume = reco.squeeze(1).permute(1, 2, 0).unsqueeze(0).unsqueeze(0)
-        _test_step(self, final_volume, data_orig, data_seg, data_mask, batch_idx, ID, label)
+        _test_step(self, final_volume, st["orig"], st["seg"], st["mask"], batch_idx, st["ID"], st["label"])
         return final_volume
 
     def on_test_end(self):

@@ -72,8 +72,26 @@ def run_stage(model, batches: Iterable[Mapping[str, Any]], device: Optional[torc
     model.on_test_start()
     batches = list(batches)
     mine = list(enumerate(batches))[rank::world]
-    for idx, batch in mine:
-        model.test_step(_to_device(batch, device), idx)
+    if hasattr(model, "test_step_reconstruct") and device.type == "cuda" and os.environ.get("CDDPM_SWEEP_PIPELINE", "1") != "0":
+        # Software pipeline over volumes: the reconstruction of volume i+1 (pure enqueue, ~26 ms of GPU work for 50
+        # slices) goes onto the main stream BEFORE volume i is scored; the scoring tail, whose threshold bisection reads
+        # a few counters back per step, runs on a high-priority side stream, so its host round trips no longer idle the
+        # GPU.  Results and their order are those of the plain loop (the host RNG draws all happen in the first half).
+        with torch.cuda.device(device):
+            tail = getattr(model, "_tail_stream", None)
+            if tail is None:
+                tail = model._tail_stream = torch.cuda.Stream(device=device, priority=-1)
+            pending = None
+            for idx, batch in mine + [(None, None)]:
+                nxt = (idx, model.test_step_reconstruct(_to_device(batch, device))) if batch is not None else None
+                if pending is not None:
+                    with torch.cuda.stream(tail):
+                        model.test_step_finish(pending[1], pending[0])
+                    tail.synchronize()  # volume i's tensors may be recycled by the main stream from here on
+                pending = nxt
+    else:
+        for idx, batch in mine:
+            model.test_step(_to_device(batch, device), idx)
     if world > 1:
         model.eval_dict.update(merge_lists(model.eval_dict, len(mine), len(batches)))
     model.on_test_end()

@@ -148,3 +148,37 @@ def test_sweep_driver_val_then_test():
     assert np.isfinite(test["DicePerVolMean"]) and np.isfinite(val["AUPRCPerVolMean"])
     assert "1/Datamodules_eval.Brats21/test/DicePerVolMean" in logs
     assert not hasattr(model, "threshold")  # deleted after the test stage, as in the reference (utils_eval.py:258-259)
+
+
+def test_pipelined_sweep_equals_plain_loop(monkeypatch):
+    """run_stage enqueues volume i+1 before it scores volume i (side stream for the tail): same eval_dict, same global
+    threshold as the one-volume-at-a-time loop, bit for bit."""
+    from cddpm import sweep
+    from oracle.weights import synthetic_volume
+    from src.models.DDPM_2D import DDPM_2D
+
+    full, _ = _full_state_dict()
+    cfg = _cfg()
+    cfg["force_num_eval_slices"] = False
+    model = DDPM_2D(cfg, prefix="t/")
+    model.load_state_dict(full, strict=True)
+    model = model.cuda().eval()
+    batches = []
+    for sd in range(5):
+        v = synthetic_volume(sd, depth=6)
+        batches.append({"Dataset": ["Brats21"], "vol": {"data": v["vol"]}, "vol_orig": {"data": v["vol"].clone()},
+                        "seg_orig": {"data": v["seg_orig"]}, "mask_orig": {"data": v["mask_orig"]}, "ID": [f"v{sd}"],
+                        "stage": "val", "label": torch.tensor([1]), "seg_available": True})
+    keys = ("DiceScorePerVol", "BestThresholdPerVol", "AUPRCPerVol", "HausPerVol", "TPPerVol", "FNPerVol",
+            "AnomalyScoreRegPerVol", "AnomalyScoreRecoPerVol", "DiceScorePerSlice", "IDs")
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("CDDPM_SWEEP_PIPELINE", mode)
+        np.random.seed(11)
+        ed = sweep.run_stage(model, batches)
+        res[mode] = ({k: [float(x) if not isinstance(x, str) else x for x in ed[k]] for k in keys},
+                     float(model.threshold["total"]))
+    assert res["0"][1] == res["1"][1]
+    for k in keys:
+        a, b = res["0"][0][k], res["1"][0][k]
+        assert len(a) == len(b) and all(x == y or (x != x and y != y) for x, y in zip(a, b)), k
