@@ -698,6 +698,8 @@ def lib_bwd_launches(eng):
 
 
 def main():
+    # stdout carries exactly one JSON line: NCCL's own banner / debug output ("NCCL version ...") goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
