@@ -78,6 +78,7 @@ def _signatures(c):
         "cddpm_unet_grad_total": (i64, [vp]),
         "cddpm_unet_grad_offset": (i32, [vp, i32, c.POINTER(i64)]),
         "cddpm_unet_backward": (i32, [vp, vp, vp, vp, i32, vp]),
+        "cddpm_unet_set_training": (i32, [vp, i32]),
         "cddpm_unet_bwd_flops": (i64, [vp]),
         "cddpm_unet_bwd_launches": (i32, [vp]),
         "cddpm_adam_step": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, f32, f32, f32, f32, f32, f32, vp]),

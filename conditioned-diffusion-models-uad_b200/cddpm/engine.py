@@ -16,7 +16,7 @@ class UNetEngine:
 
     def __init__(self, *, image_size: Tuple[int, int], in_channels: int, model_channels: int, out_channels: int,
                  num_res_blocks: int, attention_resolutions: Sequence[int], channel_mult: Sequence[int],
-                 num_classes: Optional[int], num_head_channels: int = 64, dtype=torch.float16):
+                 num_classes: Optional[int], num_head_channels: int = 64, dtype=torch.float16, training: bool = False):
         cfg = UNetConfig()
         cfg.image_h, cfg.image_w = int(image_size[0]), int(image_size[1])
         cfg.in_channels, cfg.model_channels, cfg.out_channels = in_channels, model_channels, out_channels
@@ -35,6 +35,10 @@ class UNetEngine:
         self.num_classes = cfg.num_classes
         self._h = ctypes.c_void_p()
         check(lib().cddpm_unet_create(ctypes.byref(cfg), ctypes.byref(self._h)), "cddpm_unet_create")
+        # training engines keep the intermediates backward() reads; inference engines fuse them away (cddpm_b200.h)
+        self.training = bool(training)
+        if self.training:
+            check(lib().cddpm_unet_set_training(self._h, 1), "cddpm_unet_set_training")
 
     def __del__(self):
         h = getattr(self, "_h", None)

@@ -279,7 +279,8 @@ class UNetModel(nn.Module):
                 image_size=self.image_size, in_channels=self.in_channels, model_channels=self.model_channels,
                 out_channels=self.out_channels, num_res_blocks=self.num_res_blocks,
                 attention_resolutions=self.attention_resolutions, channel_mult=self.channel_mult,
-                num_classes=self.num_classes, num_head_channels=self.num_head_channels, dtype=torch.bfloat16)
+                num_classes=self.num_classes, num_head_channels=self.num_head_channels, dtype=torch.bfloat16,
+                training=True)
             self._train_versions = [None] * len(items)
         # training: push everything on every call.  Version counters are not a reliable change signal here - torch's
         # fused optimizers update parameters without advancing them - and the bulk push replays one CUDA graph.

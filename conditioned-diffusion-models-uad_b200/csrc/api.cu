@@ -366,6 +366,10 @@ int cddpm_unet_grad_offset(const cddpm_unet_t* h, int index, int64_t* offset) {
   if (!h || !offset) return fail(kInvalidArgument, "unet_grad_offset: null pointer");
   return h->engine.grad_offset(index, offset);
 }
+int cddpm_unet_set_training(cddpm_unet_t* h, int training) {
+  if (!h) return fail(kInvalidArgument, "unet_set_training: null handle");
+  return h->engine.set_training(training != 0);
+}
 int cddpm_unet_backward(cddpm_unet_t* h, const float* dout, float* grads, float* dcond, int B, void* stream) {
   if (!h) return fail(kInvalidArgument, "unet_backward: null handle");
   return h->engine.backward(dout, grads, dcond, B, static_cast<cudaStream_t>(stream));

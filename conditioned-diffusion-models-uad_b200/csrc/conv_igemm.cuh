@@ -70,6 +70,15 @@ struct ConvDesc {
   int out_stride = 0;   // 0 = Cout
   int out_col_off = 0;
   int identity_k = 0;   // K columns that only add a tensor through an identity weight block (not counted as FLOPs)
+  // Inference only, conv_igemm2 only: finish the GroupNorm (+FiLM) + SiLU that FOLLOWS this convolution inside its
+  // epilogue.  `out` then receives act(GN(conv + bias) * (1 + scale) + shift); the raw result is never written.
+  // Needs gn_stats (the statistics rendezvous) and gn_counters ([B][Cout/128] 64-bit, zeroed with the statistics).
+  const float* gn_gamma = nullptr;
+  const float* gn_beta = nullptr;
+  const float* gn_film = nullptr;  // optional [B][gn_film_stride]: scale at [gn_film_off + c], shift at [+ Cout + c]
+  int gn_film_stride = 0;
+  int gn_film_off = 0;
+  unsigned long long* gn_counters = nullptr;
 };
 
 // Second-generation kernel (conv_igemm2.cu): 16x16-pixel macro tiles x 128 channels; one staged 18x18 halo tile per

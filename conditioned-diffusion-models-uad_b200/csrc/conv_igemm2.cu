@@ -65,7 +65,8 @@ struct Geo {
   static constexpr int kASlotBytes = (kABytes + 1023) & ~1023;     // slots stay 1 KB aligned (swizzle atom)
   static constexpr int kEpiWarps = 4 * kMT;
   static constexpr int kStatBytes = 2 * kEpiWarps * kStatW2 * 4;
-  static constexpr int kSmemBytes = kStagesA * kASlotBytes + kStagesB * kBSlotBytes + 256 + kStatBytes + 1024;
+  static constexpr int kCoefBytes = 2 * kNTile * 4;               // fused GroupNorm finish: A[128], B[128]
+  static constexpr int kSmemBytes = kStagesA * kASlotBytes + kStagesB * kBSlotBytes + 256 + kStatBytes + kCoefBytes + 1024;
 };
 
 struct Conv2Params {
@@ -83,6 +84,12 @@ struct Conv2Params {
   const uint16_t* residual;
   uint16_t* out;
   double* gn_stats;
+  // fused GroupNorm finish (ConvDesc::gn_gamma): see the epilogue
+  const float* gn_gamma;
+  const float* gn_beta;
+  const float* gn_film;
+  int gn_film_stride, gn_film_off;
+  unsigned long long* gn_counters;
 };
 
 __device__ __forceinline__ uint32_t pack16(float a, float b, int fmt) {
@@ -96,6 +103,47 @@ __device__ __forceinline__ uint32_t pack16(float a, float b, int fmt) {
 __device__ __forceinline__ float2 unpack16(uint32_t u, int fmt) {
   if (fmt == 1) return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
   return __half22float2(*reinterpret_cast<__half2*>(&u));
+}
+
+__device__ __forceinline__ float silu_tanh(float x) {  // the GroupNorm kernel's SiLU (elementwise.cu: one SFU op)
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return x * fmaf(0.5f, t, 0.5f);
+}
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Per 4-channel bucket: sum and sum of squares of this pixel's 32 channels, then a butterfly over the warp's 32 pixels
+// (16 shuffles leave value (lane >> 1) & 15 in every lane); lanes write the warp's 16 totals of chunk c.
+__device__ __forceinline__ void emit_stats(const float (&f)[32], bool in_img, int lane, float* stat_dst) {
+  float v16[16];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    v16[k] = 0.f;
+    v16[8 + k] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float fv = in_img ? f[4 * k + j] : 0.f;
+      v16[k] += fv;
+      v16[8 + k] = fmaf(fv, fv, v16[8 + k]);
+    }
+  }
+#pragma unroll
+  for (int w = 8; w >= 1; w >>= 1) {
+    const int msk = w * 2;
+    const bool hi = (lane & msk) != 0;
+#pragma unroll
+    for (int k = 0; k < w; ++k) {
+      const float keep = hi ? v16[k + w] : v16[k];
+      const float send = hi ? v16[k] : v16[k + w];
+      v16[k] = keep + __shfl_xor_sync(0xffffffffu, send, msk);
+    }
+  }
+  const float tot = v16[0] + __shfl_xor_sync(0xffffffffu, v16[0], 1);
+  if ((lane & 1) == 0) stat_dst[lane >> 1] = tot;
 }
 
 template <int kMT>
@@ -329,6 +377,141 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_igemm2_kernel(const __grid_
       const bool in_img = valid && y < p.H;  // the bottom tile of a 24-row image hangs over its edge
       const bool has_res = p.residual != nullptr && in_img;
 
+      if (p.gn_gamma != nullptr) {
+        // ---------------------------------------------------------------- fused GroupNorm (+FiLM) + SiLU finish
+        // The GroupNorm that follows this convolution needs whole-image statistics.  Phase 1 reads the accumulator,
+        // publishes this tile's partial sums (double atomics) and counts the tile in a per-(image, N tile) counter;
+        // the tile then waits until all tiles of its image are counted - they are all in flight: the grid is
+        // persistent, one CTA per SM, work items in image order - and phase 2 reads the accumulator AGAIN (it is still
+        // in TMEM: the stage is only released after the second read), normalises and stores the activated tensor.
+        // The raw convolution result never reaches memory and the separate GroupNorm pass disappears.
+        float* coef_sh = stat_sh + 2 * kEpiWarps * kStatW2;  // A[128], B[128]
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                               static_cast<uint32_t>((acc * kMTiles + m) * kNTile);
+        if (valid) {
+#pragma unroll 1
+          for (int c = 0; c < kNTile / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(taddr + c * 32, v);
+            tmem_ld_wait();
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bv = p.bias != nullptr ? __ldg(reinterpret_cast<const float4*>(p.bias + n_idx * kNTile + c * 32 + j))
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+              f[j] = __uint_as_float(v[j]) + bv.x;
+              f[j + 1] = __uint_as_float(v[j + 1]) + bv.y;
+              f[j + 2] = __uint_as_float(v[j + 2]) + bv.z;
+              f[j + 3] = __uint_as_float(v[j + 3]) + bv.w;
+            }
+            emit_stats(f, in_img, lane, stat_sh + (acc * kEpiWarps + ew) * kStatW2 + c * 16);
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+        if (valid) {
+          if (epi_tid < kStatW2) {
+            const int within = epi_tid & 15;
+            const int is_q = within >> 3;
+            const int bucket = (epi_tid >> 4) * 8 + (within & 7);
+            const float* sp = stat_sh + acc * kEpiWarps * kStatW2 + epi_tid;
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < kEpiWarps; ++w) t += sp[w * kStatW2];
+            atomicAdd(&p.gn_stats[(static_cast<size_t>(n) * nb4 + n_idx * (kNTile >> 2) + bucket) * 2 + is_q],
+                      static_cast<double>(t));
+            __threadfence();
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+        if (valid) {
+          bool timed_out = false;
+          if (epi_tid == 0) {
+            unsigned long long* ctr = p.gn_counters + static_cast<size_t>(n) * p.num_n_tiles + n_idx;
+            __threadfence();
+            atomicAdd(ctr, 1ull);
+            const unsigned long long want = static_cast<unsigned long long>(tiles_per_img);
+            int spins = 0;
+            while (ld_acquire_u64(ctr) < want) {
+              __nanosleep(64);
+              if (++spins > (1 << 21)) {  // ~0.2 s: a scheduling assumption broke; poison the output instead of hanging
+                timed_out = true;
+                break;
+              }
+            }
+            coef_sh[0] = timed_out ? __int_as_float(0x7fc00000) : 0.f;  // read back below by every thread
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+          const float poison = coef_sh[0];
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+          if (epi_tid < kNTile) {
+            const int cg = n_idx * kNTile + epi_tid;
+            const int cpg = p.Cout >> 5;  // GroupNorm32: 32 groups
+            const int g = cg / cpg;
+            double s = 0.0, q = 0.0;
+            for (int j = g * (cpg >> 2); j < (g + 1) * (cpg >> 2); ++j) {
+              const double* sp = p.gn_stats + (static_cast<size_t>(n) * nb4 + j) * 2;
+              s += __ldcg(sp);
+              q += __ldcg(sp + 1);
+            }
+            const double cnt = static_cast<double>(p.H) * p.W * cpg;
+            const double mean = s / cnt;
+            double var = q / cnt - mean * mean;
+            if (var < 0.0) var = 0.0;
+            float A = static_cast<float>(1.0 / sqrt(var + 1e-5)) * __ldg(p.gn_gamma + cg);
+            float Bc = __ldg(p.gn_beta + cg) - static_cast<float>(mean) * A;
+            if (p.gn_film != nullptr) {
+              const float* fp = p.gn_film + static_cast<size_t>(n) * p.gn_film_stride + p.gn_film_off;
+              const float sc = 1.0f + fp[cg];
+              const float shf = fp[p.Cout + cg];
+              A *= sc;
+              Bc = Bc * sc + shf;
+            }
+            coef_sh[epi_tid] = A + poison;
+            coef_sh[kNTile + epi_tid] = Bc;
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+        }
+#pragma unroll 1
+        for (int c = 0; c < kNTile / 32; ++c) {
+          uint32_t v[32];
+          if (valid) {
+            tmem_ld_32x32(taddr + c * 32, v);
+            tmem_ld_wait();
+          }
+          if (c == kNTile / 32 - 1) {
+            tc_fence_before();
+            mbar_arrive_cluster(&tempty[acc], 0);
+          }
+          if (in_img) {
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bv = p.bias != nullptr ? __ldg(reinterpret_cast<const float4*>(p.bias + n_idx * kNTile + c * 32 + j))
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+              const float4 av = *reinterpret_cast<const float4*>(coef_sh + c * 32 + j);
+              const float4 cv = *reinterpret_cast<const float4*>(coef_sh + kNTile + c * 32 + j);
+              f[j] = silu_tanh(fmaf(__uint_as_float(v[j]) + bv.x, av.x, cv.x));
+              f[j + 1] = silu_tanh(fmaf(__uint_as_float(v[j + 1]) + bv.y, av.y, cv.y));
+              f[j + 2] = silu_tanh(fmaf(__uint_as_float(v[j + 2]) + bv.z, av.z, cv.z));
+              f[j + 3] = silu_tanh(fmaf(__uint_as_float(v[j + 3]) + bv.w, av.w, cv.w));
+            }
+            uint4* op = reinterpret_cast<uint4*>(p.out + off0 + c * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 o;
+              o.x = pack16(f[q * 8 + 0], f[q * 8 + 1], fmt);
+              o.y = pack16(f[q * 8 + 2], f[q * 8 + 3], fmt);
+              o.z = pack16(f[q * 8 + 4], f[q * 8 + 5], fmt);
+              o.w = pack16(f[q * 8 + 6], f[q * 8 + 7], fmt);
+              op[q] = o;
+            }
+          }
+        }
+        continue;
+      }
+
       uint4 rnext[4];
       if (has_res) {
         const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off0);
@@ -404,35 +587,8 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_igemm2_kernel(const __grid_
             op[q] = o;
           }
         }
-        if (p.gn_stats != nullptr) {
-          // per 4-channel bucket: sum and sum of squares of this pixel, then a butterfly over the warp's 32 pixels
-          // (16 shuffles leave value (lane >> 1) & 15 in every lane)
-          float v16[16];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            v16[k] = 0.f;
-            v16[8 + k] = 0.f;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float fv = in_img ? f[4 * k + j] : 0.f;
-              v16[k] += fv;
-              v16[8 + k] = fmaf(fv, fv, v16[8 + k]);
-            }
-          }
-#pragma unroll
-          for (int w = 8; w >= 1; w >>= 1) {
-            const int msk = w * 2;
-            const bool hi = (lane & msk) != 0;
-#pragma unroll
-            for (int k = 0; k < w; ++k) {
-              const float keep = hi ? v16[k + w] : v16[k];
-              const float send = hi ? v16[k] : v16[k + w];
-              v16[k] = keep + __shfl_xor_sync(0xffffffffu, send, msk);
-            }
-          }
-          const float tot = v16[0] + __shfl_xor_sync(0xffffffffu, v16[0], 1);
-          if ((lane & 1) == 0) stat_sh[(acc * kEpiWarps + ew) * kStatW2 + c * 16 + (lane >> 1)] = tot;
-        }
+        if (p.gn_stats != nullptr)
+          emit_stats(f, in_img, lane, stat_sh + (acc * kEpiWarps + ew) * kStatW2 + c * 16);
       }
       if (p.gn_stats != nullptr) {
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
@@ -504,6 +660,17 @@ int build_conv2(const ConvDesc& d, std::shared_ptr<void>* holder) {
   p.residual = reinterpret_cast<const uint16_t*>(d.residual);
   p.out = reinterpret_cast<uint16_t*>(d.out);
   p.gn_stats = d.gn_stats;
+  if (d.gn_gamma != nullptr) {
+    if (d.gn_stats == nullptr || d.gn_counters == nullptr || d.gn_beta == nullptr || d.residual != nullptr || d.relu != 0 ||
+        d.Cout % 128 != 0 || (d.Cout / 32) % 4 != 0)
+      return fail(kInvalidArgument, "conv2: fused GroupNorm finish needs statistics, counters, no residual / activation");
+    p.gn_gamma = d.gn_gamma;
+    p.gn_beta = d.gn_beta;
+    p.gn_film = d.gn_film;
+    p.gn_film_stride = d.gn_film_stride;
+    p.gn_film_off = d.gn_film_off;
+    p.gn_counters = d.gn_counters;
+  }
   int ktot = 0;
   for (int s = 0; s < d.num_src; ++s) {
     p.src_c[s] = d.src_c[s];
@@ -538,6 +705,15 @@ int launch_conv2(const std::shared_ptr<void>& holder, cudaStream_t stream) {
   const Conv2Launch* L = reinterpret_cast<const Conv2Launch*>(holder.get());
   const int num_work = ((L->p.num_m_tiles + 1) / 2) * L->p.num_n_tiles;
   int pairs = device_sm_count() / 2;
+  if (L->p.gn_gamma != nullptr) {
+    // Fused GroupNorm finish: a tile waits for all tiles of its image.  Work items are dealt round-robin, so an image
+    // whose items straddle two rounds would hold its early tiles' accumulator stage for a whole extra round.  Use a
+    // pair count that is a multiple of the items of one image (of two images when the tile count is odd and a pair
+    // spans an image boundary): every image then lives inside one round.  (72 of 74 pairs for the three UNet levels.)
+    const int tiles_per_img = L->p.tiles_w * L->p.tiles_h;
+    const int group = (tiles_per_img % 2 == 0 ? tiles_per_img / 2 : tiles_per_img) * L->p.num_n_tiles;
+    if (group <= pairs) pairs = pairs / group * group;
+  }
   if (num_work < pairs) pairs = num_work;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * pairs);

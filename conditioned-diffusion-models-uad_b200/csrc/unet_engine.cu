@@ -23,6 +23,29 @@ void UNetEngine::drop_graph() {
   forwards_on_plan_ = 0;
 }
 
+static bool fuse_gn_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    // OFF by default: built, parity-green and measured on B200 (profiles/r01_v13_summary.md) - the rendezvous keeps the
+    // accumulator stage ~2x longer than the plain epilogue and the convolution loses more than the GroupNorm pass costs
+    // (B=32 forward 5.20 ms separate vs 5.43-5.46 ms fused).  CDDPM_FUSE_GN=1 enables it for inference engines.
+    const char* e = getenv("CDDPM_FUSE_GN");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+// Fuse only where the K loop of a work item is long enough to hide the rendezvous (statistics atomics, counter, poll,
+// coefficient loads: ~4 dependent L2 round trips while the accumulator stage is held).  CDDPM_FUSE_GN_MINK overrides.
+static int fuse_gn_min_k() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CDDPM_FUSE_GN_MINK");
+    v = e != nullptr ? atoi(e) : 0;
+  }
+  return v;
+}
+
 static bool graph_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -44,6 +67,17 @@ void UNetEngine::free_acts() {
   steps_.clear();
   taps_.clear();
   planned_B_ = 0;
+  plan_fused_ = false;
+}
+
+int UNetEngine::set_training(bool on) {
+  if (on == training_) return kOk;
+  if (planned_B_ != 0) {
+    CDDPM_CUDA(cudaDeviceSynchronize());
+    free_acts();
+  }
+  training_ = on;
+  return kOk;
 }
 
 template <typename T>
@@ -468,6 +502,20 @@ int UNetEngine::plan_res(const ResLayer& L, const ActTensor& a0, const ActTensor
   if (L.mode != kResampleNone) CDDPM_TRY(act_alloc(&tS, L.cin, Ho, Wo, B));
   CDDPM_TRY(act_alloc(out, L.cout, Ho, Wo, B, true));
   if (fused_stats_ && (!a0.stats || (a1 && !a1->stats))) return fail(kInvalidArgument, "plan_res: input without statistics at " + L.prefix);
+  bool fuse_gn2 = false;
+  if (fused_stats_ && !training_ && fuse_gn_enabled() && conv2_enabled() && L.cout % 128 == 0 && L.film_off >= 0 &&
+      film_out_ != nullptr) {
+    ConvDesc probe;
+    probe.num_src = 1;
+    probe.src_c[0] = L.cin;
+    probe.src_taps[0] = 9;
+    probe.B = B;
+    probe.H = Ho;
+    probe.W = Wo;
+    probe.Cout = L.cout;
+    fuse_gn2 = conv2_supported(probe) && 9 * L.cin >= fuse_gn_min_k();
+    if (fuse_gn2) plan_fused_ = true;
+  }
   // 1-2. in_layers: GroupNorm (statistics came out of the producers' epilogues) + SiLU (+ resample of both the
   //      normalised and the raw input)
   {
@@ -504,11 +552,25 @@ int UNetEngine::plan_res(const ResLayer& L, const ActTensor& a0, const ActTensor
     d.out = tH.p;
     d.ab_format = fmt;
     d.gn_stats = tH.stats;
+    if (fuse_gn2) {
+      // inference: the out_layers GroupNorm + FiLM + SiLU is finished inside this convolution's epilogue (cross-CTA
+      // rendezvous on the image's statistics, conv_igemm2.cu); tH is never written, tB comes straight out of the conv
+      d.out = tB.p;
+      d.gn_gamma = L.gn2_w;
+      d.gn_beta = L.gn2_b;
+      d.gn_film = film_out_;
+      d.gn_film_stride = film_total_;
+      d.gn_film_off = L.film_off;
+      const size_t nctr = static_cast<size_t>(B) * (L.cout / 128);
+      if (stats_used_ + nctr > stats_cap_) return fail(kCudaError, "statistics arena exhausted (counters)");
+      d.gn_counters = reinterpret_cast<unsigned long long*>(stats_arena_ + stats_used_);
+      stats_used_ += nctr;
+    }
     push_conv(d, &st);
     CDDPM_TRY(st);
   }
   // 4-5. out_layers: GroupNorm * (1 + scale) + shift, SiLU (dropout p = 0)
-  {
+  if (!fuse_gn2) {
     CatView hv;
     hv.p0 = tH.p;
     hv.c0 = L.cout;

@@ -48,6 +48,11 @@ class UNetEngine {
   // into the flat fp32 buffer `grads` (grad_total() floats, parameter i at grad_offset(i), reference layouts);
   // dcond (optional) receives dL/d cond [B, num_classes].
   int backward(const float* dout, float* grads, float* dcond, int B, cudaStream_t stream);
+  // Training engines keep every intermediate the backward pass reads; inference engines (the default) may plan
+  // inference-only fusions (the out_layers GroupNorm finished inside the producing convolution: its raw result is
+  // never stored).  Switching drops the current plan.
+  int set_training(bool on);
+  bool training() const { return training_; }
   int64_t grad_total() const { return grad_total_; }
   int grad_offset(int i, int64_t* off) const;
   int64_t bwd_flops_per_sample() const { return bwd_flops_; }
@@ -126,6 +131,8 @@ class UNetEngine {
   void push_conv(const ConvDesc& d, int* status);
   void push_gn(GnApplyArgs g);
   bool fused_stats_ = true;
+  bool training_ = false;
+  bool plan_fused_ = false;  // the current plan contains an inference-only fusion (backward refuses it)
 
   cddpm_unet_config cfg_{};
   int emb_dim_ = 0, half_dim_ = 0, film_total_ = 0;

@@ -147,6 +147,13 @@ int cddpm_unet_profile_read(cddpm_unet_t* h, double* conv_ms, int* conv_launches
 int64_t cddpm_unet_grad_total(const cddpm_unet_t* h);
 int cddpm_unet_grad_offset(const cddpm_unet_t* h, int index, int64_t* offset);
 int cddpm_unet_backward(cddpm_unet_t* h, const float* dout, float* grads, float* dcond, int B, void* stream);
+/* training != 0: the engine keeps every intermediate cddpm_unet_backward reads and never plans an inference-only
+ * fusion.  The one such fusion today is experimental and off unless CDDPM_FUSE_GN=1: the out_layers GroupNorm + FiLM +
+ * SiLU of a ResBlock (OpenAI_Unet.py:287-296) finished inside the epilogue of the convolution that produces its input,
+ * whose raw result is then never stored (a cross-CTA rendezvous per image: such forwards need the whole GPU and must not
+ * overlap another spinning kernel); cddpm_unet_backward refuses a plan that contains it.  Switching modes drops the
+ * current plan (the next forward re-plans). */
+int cddpm_unet_set_training(cddpm_unet_t* h, int training);
 /* Algorithmic tensor-core FLOPs of the backward per sample, and its kernel-launching plan steps (after the first
  * backward of a batch size). */
 int64_t cddpm_unet_bwd_flops(const cddpm_unet_t* h);

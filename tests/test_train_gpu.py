@@ -83,7 +83,7 @@ def _unet_grads(spec, image, B, seed, report=None):
     eng = UNetEngine(image_size=(image, image), in_channels=1, model_channels=spec.model_channels, out_channels=1,
                      num_res_blocks=spec.num_res_blocks, attention_resolutions=spec.attention_resolutions,
                      channel_mult=spec.channel_mult, num_classes=spec.num_classes, num_head_channels=64,
-                     dtype=torch.bfloat16)
+                     dtype=torch.bfloat16, training=True)
     eng.load_state_dict(sd)
     out = eng.forward(x, t, cond)
     flat, dcond = eng.backward(dout, want_dcond=cond is not None)

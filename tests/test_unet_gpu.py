@@ -154,3 +154,47 @@ def test_graph_replay_matches_direct_launches():
     assert (graph0 - direct0).abs().max().item() < 1e-4
     assert (graph1 - direct1).abs().max().item() < 1e-4
     assert (graph1 - graph0).abs().max().item() > 1e-3  # the replay really consumed the new inputs
+
+
+def test_fused_groupnorm_finish_matches_golden():
+    """CDDPM_FUSE_GN=1 (experimental, off by default): the out_layers GroupNorm + FiLM + SiLU finished inside the
+    producing convolution's epilogue (cross-CTA rendezvous per image).  Same golden vectors, same tolerance, fewer
+    launches; a backward on such a plan is refused.  The switch is read once per process, hence the subprocess."""
+    import subprocess
+    import sys
+
+    code = r'''
+import os, sys
+import numpy as np, torch
+ROOT = sys.argv[1]
+sys.path[:0] = [ROOT, os.path.join(ROOT, "conditioned-diffusion-models-uad_b200")]
+from cddpm.engine import UNetEngine
+from cddpm._lib import CddpmError
+from oracle import unet_port
+from oracle.weights import make_state_dict
+spec = unet_port.UNetSpec(num_classes=128)
+sd = make_state_dict(unet_port.param_shapes(spec), seed=1)
+g = np.load(os.path.join(ROOT, "tests", "golden", "unet_cond_96.npz"))
+x, t, y, cond = (torch.from_numpy(g[k]) for k in ("x", "t", "y", "cond"))
+eng = UNetEngine(image_size=(96, 96), in_channels=1, model_channels=128, out_channels=1, num_res_blocks=3,
+                 attention_resolutions=(3, 6, 12), channel_mult=(1, 2, 2), num_classes=128, dtype=torch.float16)
+eng.load_state_dict({k: v.cuda() for k, v in sd.items()})
+outs = [eng.forward(x.cuda(), t.cuda(), cond.cuda()).cpu() for _ in range(3)]  # direct launches, capture, replay
+err = max((o - y).abs().max().item() for o in outs)
+one = eng.forward(x[:1].cuda(), t[:1].cuda(), cond[:1].cuda()).cpu()
+err1 = (one - y[:1]).abs().max().item()
+refused = False
+try:
+    eng.backward(torch.zeros(1, 1, 96, 96, device="cuda"))
+except CddpmError:
+    refused = True
+print("RESULT", err, err1, eng.launches_per_forward, refused)
+'''
+    env = dict(os.environ, CDDPM_FUSE_GN="1")
+    r = subprocess.run([sys.executable, "-c", code, ROOT], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("RESULT")][-1].split()
+    err, err1, launches, refused = float(line[1]), float(line[2]), int(line[3]), line[4] == "True"
+    print(f"fused GroupNorm finish: max-abs {err:.4g} (B=1: {err1:.4g}), {launches} launches per forward")
+    assert err <= TOL_MODEL_OUT and err1 <= TOL_MODEL_OUT
+    assert launches < 123 and refused

@@ -24,7 +24,8 @@ def main():
     B = int(args[0]) if args else 64
     spec = unet_port.UNetSpec()
     eng = UNetEngine(image_size=(96, 96), in_channels=1, model_channels=128, out_channels=1, num_res_blocks=3,
-                     attention_resolutions=(3, 6, 12), channel_mult=(1, 2, 2), num_classes=128, dtype=torch.bfloat16)
+                     attention_resolutions=(3, 6, 12), channel_mult=(1, 2, 2), num_classes=128, dtype=torch.bfloat16,
+                     training=True)
     sd = make_state_dict(unet_port.param_shapes(spec), seed=1)
     eng.load_state_dict({k: v.cuda() for k, v in sd.items()})
     x = torch.randn(B, 1, 96, 96, device="cuda")
