@@ -338,7 +338,7 @@ def run_ours(args):
                 "peak_source": pk["source"], "flops_per_launch": conv_flops_fwd / max(1, conv_launches),
                 "avg_launch_ms": conv_ms_fwd / max(1, conv_launches), "launches_timed": conv_launches * len(conv_ms),
                 "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read + write)",
-                "unet_forward_tflops": UNET_GFLOP * B * world * T0 * args.steps / 1e3 / (dt_ms / 1e3),
+                "unet_forward_tflops": UNET_GFLOP * B * T0 * args.steps / 1e3 / (dt_ms / 1e3),  # per GPU
                 "unet_forward_frac_of_peak": UNET_GFLOP * B * T0 * args.steps / 1e3 / (dt_ms / 1e3) / pk["tflops"]}
     line = {"metric": METRIC, "value": value, "unit": "slices/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt_ms / args.steps, "higher_is_better": True, "scaling": "weak",

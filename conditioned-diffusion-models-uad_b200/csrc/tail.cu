@@ -92,10 +92,41 @@ __global__ void __launch_bounds__(256) residual_erode_kernel(View orig, View rec
     out[idx] = v;
   }
   if (sums != nullptr) {
+    // Run-to-run identical sums (a volume must score the same on whichever rank of a sharded sweep it lands, to the last
+    // bit - found by the 8-GPU sweep check: double atomics across blocks moved l1recoErrorAll by one ulp).  The per-thread
+    // and per-block sums are fixed-order fp64; across blocks the partials are added as 2^-32 fixed point in 64-bit
+    // INTEGER atomics (order-free; rounding <= 1.2e-10 per block), and the block that draws the last
+    // ticket (bits 48+ of slot 6, whose low bits carry the exact lesion count) converts the slots to doubles in place.
+    // A block partial that is not finite or >= 2^20 flags its slot (bits 40-45 of slot 6): that sum is reported as NaN.
+    double t[7];
 #pragma unroll
-    for (int k = 0; k < 7; ++k) {
-      const double t = block_sum(acc[k], sh);
-      if (threadIdx.x == 0) atomicAdd(&sums[k], t);
+    for (int k = 0; k < 7; ++k) t[k] = block_sum(acc[k], sh);
+    if (threadIdx.x == 0) {
+      unsigned long long* isums = reinterpret_cast<unsigned long long*>(sums);
+      constexpr double kScale = 4294967296.0;
+      unsigned long long flags = 0;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        if (!(fabs(t[k]) < 1048576.0)) {  // <= 1184 blocks x 2^20 x 2^32 stays inside 63 bits
+          flags |= 1ull << (40 + k);
+        } else {
+          atomicAdd(&isums[k], static_cast<unsigned long long>(__double2ll_rn(t[k] * kScale)));
+        }
+      }
+      if (flags) atomicOr(&isums[6], flags);
+      __threadfence();
+      const unsigned long long old = atomicAdd(&isums[6], static_cast<unsigned long long>(t[6]) + (1ull << 48));
+      if ((old >> 48) == gridDim.x - 1) {
+        __threadfence();
+        const unsigned long long s6 = atomicAdd(&isums[6], 0ull);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          const long long v = static_cast<long long>(atomicAdd(&isums[k], 0ull));
+          sums[k] = ((s6 >> (40 + k)) & 1ull) ? __longlong_as_double(0x7ff8000000000000ll)
+                                              : static_cast<double>(v) / kScale;
+        }
+        sums[6] = static_cast<double>(s6 & ((1ull << 40) - 1));
+      }
     }
   }
 }

@@ -14,6 +14,10 @@ UNetEngine::~UNetEngine() {
   free_acts();
   param_push_table_free(push_table_);
   if (cap_stream_ != nullptr) cudaStreamDestroy(cap_stream_);
+  for (cudaStream_t q : side_stream_)
+    if (q != nullptr) cudaStreamDestroy(q);
+  for (cudaEvent_t e : fork_ev_)
+    if (e != nullptr) cudaEventDestroy(e);
   for (void* p : owned_) cudaFree(p);
 }
 
@@ -555,6 +559,7 @@ int UNetEngine::plan_res(const ResLayer& L, const ActTensor& a0, const ActTensor
     if (fuse_gn2) {
       // inference: the out_layers GroupNorm + FiLM + SiLU is finished inside this convolution's epilogue (cross-CTA
       // rendezvous on the image's statistics, conv_igemm2.cu); tH is never written, tB comes straight out of the conv
+      if (first_film_use_ < 0) first_film_use_ = static_cast<int>(ops_.size());
       d.out = tB.p;
       d.gn_gamma = L.gn2_w;
       d.gn_beta = L.gn2_b;
@@ -589,6 +594,7 @@ int UNetEngine::plan_res(const ResLayer& L, const ActTensor& a0, const ActTensor
     g.mode = kResampleNone;
     g.out = tB.p;
     g.fmt = fmt;
+    if (first_film_use_ < 0) first_film_use_ = static_cast<int>(ops_.size());
     push_gn(g);
   }
   // 6. out_layers conv 3x3 + skip (identity residual, or 1x1 over the raw input fused as extra K columns)
@@ -781,6 +787,8 @@ int UNetEngine::plan(int B) {
   // ---- embedding: emb_act = SiLU([time_embed(sin(t)) | label_emb(cond)]); film = emb_layers(emb_act) for all blocks
   const bool gemm_embed = (mc % 64 == 0) && (half_dim_ % 64 == 0) && (cfg_.num_classes % 64 == 0);
   sin16_ = hid16_ = cond16_ = hidc16_ = nullptr;
+  emb_t_begin_ = emb_t_end_ = emb_c_begin_ = emb_c_end_ = static_cast<int>(ops_.size());
+  film_op_ = first_film_use_ = -1;
   if (gemm_embed) {
     // the four small linears as tensor-core GEMMs with a SiLU epilogue, 16-bit hand-off between them
     uint16_t *sin16 = nullptr, *hid16 = nullptr, *hidc16 = nullptr, *cond16 = nullptr;
@@ -818,6 +826,7 @@ int UNetEngine::plan(int B) {
     ops_.push_back([=](cudaStream_t s) { return launch_timestep_embedding16(cur_t_, nullptr, sin16, fmt, B, mc, s); });
     CDDPM_TRY(lin(sin16, mc, te0_w16, te0_b, hid16, half_dim_, half_dim_, 0));
     CDDPM_TRY(lin(hid16, half_dim_, te2_w16, te2_b, emb_act16_, half_dim_, emb_dim_, 0));
+    emb_t_end_ = emb_c_begin_ = emb_c_end_ = static_cast<int>(ops_.size());
     if (cfg_.num_classes > 0) {
       const int nc = cfg_.num_classes;
       CDDPM_TRY(h16alloc(&hidc16, static_cast<size_t>(B) * half_dim_));
@@ -830,6 +839,7 @@ int UNetEngine::plan(int B) {
       });
       CDDPM_TRY(lin(cond16, nc, le0_w16, le0_b, hidc16, half_dim_, half_dim_, 0));
       CDDPM_TRY(lin(hidc16, half_dim_, le2_w16, le2_b, emb_act16_, half_dim_, emb_dim_, half_dim_));
+      emb_c_end_ = static_cast<int>(ops_.size());
     }
   } else {
   ops_.push_back([=](cudaStream_t s) { return launch_timestep_embedding(cur_t_, sinus_, B, mc, s); });
@@ -867,6 +877,7 @@ int UNetEngine::plan(int B) {
     d.out_is_f32 = 1;
     d.ab_format = fmt;
     int st = kOk;
+    if (gemm_embed) film_op_ = static_cast<int>(ops_.size());
     push_conv(d, &st);
     CDDPM_TRY(st);
   }
@@ -961,6 +972,69 @@ int UNetEngine::plan(int B) {
   return kOk;
 }
 
+static bool fork_embed_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CDDPM_FORK_EMBED");  // A/B switch for measurements: 0 = the embedding path stays in line
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+// Records the planned launch list into the capturing stream.  The embedding path (timestep MLP, condition MLP, the FiLM
+// projection: seven latency-bound launches of 4-92 CTAs, ~127 us in line at B=32) has no consumer before the first
+// ResBlock's out_layers GroupNorm, so it is captured as two forked branches (timestep chain | condition chain, joined in
+// front of the FiLM projection) that run beside the stem convolution and the first GroupNorm / convolution, and the main
+// branch waits for the FiLM table right before its first reader.
+int UNetEngine::capture_ops() {
+  const int n = static_cast<int>(ops_.size());
+  const bool fork = fork_embed_enabled() && film_op_ >= 0 && first_film_use_ > film_op_ && emb_t_end_ > emb_t_begin_ &&
+                    film_op_ == emb_c_end_ && emb_c_begin_ == emb_t_end_;
+  if (!fork) {
+    for (auto& op : ops_) CDDPM_TRY(op(cap_stream_));
+    return kOk;
+  }
+  // highest priority: the side branches are a handful of small CTAs that must slip in between the blocks of the stem /
+  // GroupNorm kernels instead of queueing behind them (the priority is recorded into the captured kernel nodes)
+  int prio_lo = 0, prio_hi = 0;
+  CDDPM_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  for (int i = 0; i < 2; ++i)
+    if (side_stream_[i] == nullptr)
+      CDDPM_CUDA(cudaStreamCreateWithPriority(&side_stream_[i], cudaStreamNonBlocking, prio_hi));
+  for (int i = 0; i < 3; ++i)
+    if (fork_ev_[i] == nullptr) CDDPM_CUDA(cudaEventCreateWithFlags(&fork_ev_[i], cudaEventDisableTiming));
+  int st = kOk;
+  bool joined = false;
+  for (int i = 0; i < n && st == kOk; ++i) {
+    if (i == emb_t_begin_) {
+      // fork: both side branches start from this point of the main branch
+      CDDPM_CUDA(cudaEventRecord(fork_ev_[0], cap_stream_));
+      CDDPM_CUDA(cudaStreamWaitEvent(side_stream_[0], fork_ev_[0], 0));
+      if (emb_c_end_ > emb_c_begin_) CDDPM_CUDA(cudaStreamWaitEvent(side_stream_[1], fork_ev_[0], 0));
+    }
+    if (i >= emb_t_begin_ && i < emb_t_end_) {
+      st = ops_[i](side_stream_[0]);
+    } else if (i >= emb_c_begin_ && i < emb_c_end_) {
+      st = ops_[i](side_stream_[1]);
+    } else if (i == film_op_) {
+      if (emb_c_end_ > emb_c_begin_) {
+        CDDPM_CUDA(cudaEventRecord(fork_ev_[1], side_stream_[1]));
+        CDDPM_CUDA(cudaStreamWaitEvent(side_stream_[0], fork_ev_[1], 0));
+      }
+      st = ops_[i](side_stream_[0]);
+      CDDPM_CUDA(cudaEventRecord(fork_ev_[2], side_stream_[0]));
+    } else {
+      if (i == first_film_use_) {
+        CDDPM_CUDA(cudaStreamWaitEvent(cap_stream_, fork_ev_[2], 0));
+        joined = true;
+      }
+      st = ops_[i](cap_stream_);
+    }
+  }
+  if (st == kOk && !joined) CDDPM_CUDA(cudaStreamWaitEvent(cap_stream_, fork_ev_[2], 0));
+  return st;
+}
+
 int UNetEngine::forward(const float* x, const int64_t* t, const float* cond, float* out, int B, cudaStream_t stream) {
   if (!x || !t || !out) return fail(kInvalidArgument, "unet_forward: null pointer");
   if (B < 1) return fail(kInvalidArgument, "unet_forward: empty batch");
@@ -990,11 +1064,7 @@ int UNetEngine::forward(const float* x, const int64_t* t, const float* cond, flo
       cur_cond_ = n_cond ? stage_cond_ : nullptr;
       cur_out_ = stage_out_;
       CDDPM_CUDA(cudaStreamBeginCapture(cap_stream_, cudaStreamCaptureModeThreadLocal));
-      int st = kOk;
-      for (auto& op : ops_) {
-        st = op(cap_stream_);
-        if (st != kOk) break;
-      }
+      int st = capture_ops();
       cudaGraph_t graph = nullptr;
       const cudaError_t ce = cudaStreamEndCapture(cap_stream_, &graph);
       if (st != kOk) {

@@ -177,6 +177,12 @@ class UNetEngine {
   // staging buffers because the graph bakes pointers in.  CDDPM_GRAPH=0 disables it.
   void drop_graph();
   cudaStream_t cap_stream_ = nullptr;
+  // forked capture of the embedding path (capture_ops): op index ranges of the timestep chain, the condition chain,
+  // the FiLM projection and the first reader of the FiLM table
+  int capture_ops();
+  int emb_t_begin_ = 0, emb_t_end_ = 0, emb_c_begin_ = 0, emb_c_end_ = 0, film_op_ = -1, first_film_use_ = -1;
+  cudaStream_t side_stream_[2] = {nullptr, nullptr};
+  cudaEvent_t fork_ev_[3] = {nullptr, nullptr, nullptr};
   cudaGraphExec_t graph_exec_ = nullptr;
   ParamPushTable* push_table_ = nullptr;  // recorded re-layout jobs of a whole-model push (param_push.cu)
   std::vector<const float*> push_key_;

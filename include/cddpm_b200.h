@@ -246,7 +246,8 @@ typedef struct cddpm_vol_view {
 /* diff = |orig - reco| (utils_eval.py:31), multiplied by the brain mask eroded per axial slice with a 3x3 cross,
  * `iterations` times, zero border (apply_brainmask_volume :447-460; the reference passes W // 25; iterations < 1
  * means scipy's "until stable").  erode == 0 skips the mask.  sums (7 doubles, may be NULL) receive
- * sum|d|, sum d^2 over all voxels / seg>0 / seg==0 and count(seg>0) for the l1/l2 errors (:36-49). */
+ * sum|d|, sum d^2 over all voxels / seg>0 / seg==0 and count(seg>0) for the l1/l2 errors (:36-49); run-to-run identical
+ * (fixed-order fp64 per block, 2^-32 fixed-point integer atomics across blocks; a block partial >= 2^20 or not finite makes the sum read NaN). */
 int cddpm_residual_erode(const cddpm_vol_view* orig, const cddpm_vol_view* reco, const cddpm_vol_view* seg,
                          const cddpm_vol_view* mask, int H, int W, int D, int iterations, int erode,
                          float* diff_masked_dhw, double* sums, void* stream);

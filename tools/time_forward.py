@@ -29,7 +29,7 @@ def main():
         for _ in range(3):
             eng.forward(x, t, c, out)
         torch.cuda.synchronize()
-        n = 10 if B >= 8 else 30
+        n = int(os.environ.get("TIME_FORWARD_ITERS", 10 if B >= 8 else 30))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(n):
