@@ -379,6 +379,62 @@ __global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, float* 
   }
 }
 
+// Wide-K variant (the encoder head 2048 -> 128 took 830 us in linear_kernel: 128 warps, each walking its whole weight
+// row once per 8 batch rows with one dependent load per step).  A block owns 4 outputs x 8 batch rows; warp w owns batch
+// row w, its lanes stride the K axis with float4 loads (4 in flight per operand row), so the grid is O/4 x B/8 blocks
+// and the 4 weight rows of a block are shared by its 8 warps through L1.  fp32 throughout, like linear_kernel.
+constexpr int kLinWO = 4;
+__global__ void __launch_bounds__(256) linear_wide_kernel(const float* __restrict__ in, int in_stride,
+                                                          const float* __restrict__ W, const float* __restrict__ bias,
+                                                          float* __restrict__ out, int out_stride, int B, int I, int O,
+                                                          int act_in, int act_out, uint16_t* __restrict__ out16,
+                                                          int out16_stride, int fmt) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int o0 = blockIdx.x * kLinWO;
+  const int b = blockIdx.y * 8 + warp;
+  if (b >= B) return;
+  const float4* x4 = reinterpret_cast<const float4*>(in + static_cast<size_t>(b) * in_stride);
+  const float4* w4[kLinWO];
+#pragma unroll
+  for (int j = 0; j < kLinWO; ++j)
+    w4[j] = reinterpret_cast<const float4*>(W + static_cast<size_t>(o0 + j < O ? o0 + j : O - 1) * I);
+  float acc[kLinWO];
+#pragma unroll
+  for (int j = 0; j < kLinWO; ++j) acc[j] = 0.f;
+  const int n4 = I >> 2;
+#pragma unroll 4
+  for (int i = lane; i < n4; i += 32) {
+    float4 xv = __ldg(x4 + i);
+    if (act_in) {
+      xv.x = xv.x / (1.0f + expf(-xv.x));
+      xv.y = xv.y / (1.0f + expf(-xv.y));
+      xv.z = xv.z / (1.0f + expf(-xv.z));
+      xv.w = xv.w / (1.0f + expf(-xv.w));
+    }
+#pragma unroll
+    for (int j = 0; j < kLinWO; ++j) {
+      const float4 wv = __ldg(w4[j] + i);
+      acc[j] = fmaf(wv.x, xv.x, acc[j]);
+      acc[j] = fmaf(wv.y, xv.y, acc[j]);
+      acc[j] = fmaf(wv.z, xv.z, acc[j]);
+      acc[j] = fmaf(wv.w, xv.w, acc[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kLinWO; ++j) {
+    float v = acc[j];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    const int o = o0 + j;
+    if (lane == 0 && o < O) {
+      v += (bias != nullptr) ? bias[o] : 0.f;
+      if (act_out) v = v / (1.0f + expf(-v));
+      if (out != nullptr) out[static_cast<size_t>(b) * out_stride + o] = v;
+      if (out16 != nullptr) out16[static_cast<size_t>(b) * out16_stride + o] = f2h16(v, fmt);
+    }
+  }
+}
+
 __global__ void to16_kernel(const float* __restrict__ in, uint16_t* __restrict__ out, int n, int fmt) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = f2h16(in[i], fmt);
@@ -715,6 +771,13 @@ int launch_linear_16(const float* in, int in_stride, const float* W, const float
                      int B, int I, int O, int act_in, int act_out, void* out16, int out16_stride, int fmt,
                      cudaStream_t stream) {
   if (!in || !W || (!out && !out16)) return fail(kInvalidArgument, "linear: null pointer");
+  if (I >= 256 && I % 4 == 0 && in_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(W) & 15) == 0 && B >= 1 && O >= 1) {
+    dim3 grid((O + kLinWO - 1) / kLinWO, (B + 7) / 8);
+    linear_wide_kernel<<<grid, 256, 0, stream>>>(in, in_stride, W, bias, out, out_stride, B, I, O, act_in, act_out,
+                                                 reinterpret_cast<uint16_t*>(out16), out16_stride, fmt);
+    return check_launch("linear_wide_kernel");
+  }
   int blocks = (O + 7) / 8;
   if (blocks > 8192) blocks = 8192;
   if (blocks < 1) blocks = 1;

@@ -46,3 +46,28 @@ def test_attention_peaked_softmax_is_stable():
     ref = _reference(qkv, 64)
     assert torch.isfinite(out).all()
     assert (out - ref).abs().max().item() < 3e-2
+
+
+@pytest.mark.parametrize("B,I,O,silu_in,silu_out", [(50, 2048, 128, 0, 0), (32, 2048, 128, 0, 0), (3, 512, 130, 1, 1),
+                                                    (9, 256, 5, 0, 1), (4, 100, 7, 1, 0), (1, 128, 512, 0, 1)])
+def test_linear_matches_fp32_reference(B, I, O, silu_in, silu_out):
+    """cddpm_linear (nn.Linear on fp32 rows with optional SiLU either side: time_embed / label_emb,
+    OpenAI_Unet.py:583-602; the condition encoder's fc head): both the wide-K kernel (I >= 256, I % 4 == 0 - the
+    2048 -> 128 head) and the narrow one, ragged O and B."""
+    import ctypes
+
+    from cddpm._lib import check, current_stream, lib, ptr
+
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + I + O)
+    x = torch.randn(B, I, device="cuda", generator=g)
+    w = torch.randn(O, I, device="cuda", generator=g) / I ** 0.5
+    bias = torch.randn(O, device="cuda", generator=g)
+    out = torch.full((B, O), float("nan"), device="cuda")
+    check(lib().cddpm_linear(ptr(x), I, ptr(w), ptr(bias), ptr(out), O, B, I, O, silu_in, silu_out, current_stream()),
+          "cddpm_linear")
+    xin = torch.nn.functional.silu(x.double()) if silu_in else x.double()
+    ref = xin @ w.double().t() + bias.double()
+    if silu_out:
+        ref = torch.nn.functional.silu(ref)
+    err = (out.double() - ref).abs().max().item()
+    assert err < 2e-5, f"max abs err {err}"
