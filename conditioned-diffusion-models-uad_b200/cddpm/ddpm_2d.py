@@ -147,6 +147,13 @@ class DDPM_2D(LightningModule):
             features = self(input)
         if self.cfg.get("noise_ensemble", False):
             timesteps = self.cfg.get("step_ensemble", [250, 500, 750])
+            if self.cfg.get("stack_ensemble", True) and not torch.is_grad_enabled():
+                # the k members as one UNet forward over k x D stacked slices (same noise draws, in the same order)
+                noises = [gen_noise(self.cfg, input.shape, device=input.device) if self.cfg.get("noisetype") is not None
+                          else None for _ in timesteps]
+                loss_diff, reco = self.diffusion.ensemble_reconstruct(input, [t - 1 for t in timesteps], cond=features,
+                                                                      noises=noises)
+                return reco, loss_diff, features
             reco = torch.empty_like(input, dtype=torch.float32)
             k = len(timesteps)
             for i, t in enumerate(timesteps):

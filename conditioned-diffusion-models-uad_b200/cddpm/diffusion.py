@@ -188,6 +188,45 @@ class GaussianDiffusion(nn.Module):
                                        1 if self.loss_type == "l2" else 0, current_stream()), "cddpm_recon_finish")
         return loss.mean(), reco
 
+    @torch.no_grad()
+    def ensemble_reconstruct(self, img, timesteps, cond=None, noises=None):
+        """Noise-ensemble reconstruction (DDPM_2D.py:214-232: one forward(img, t=t_i - 1, noise_i) per member, the
+        member reconstructions averaged) as ONE UNet forward over the k x B stacked noised slices: the members are
+        independent samples of the batch (per-sample timestep, GroupNorm statistics per sample), so stacking only
+        changes the launch geometry - k x fewer launches and fuller waves (B=150: 25.6 ms vs 3 x 8.9 ms at B=50 on
+        B200).  `timesteps` are the 0-based t of each member, `noises` one tensor per member (None -> randn).  Returns
+        (loss of the LAST member, mean reconstruction), like the reference loop leaves them."""
+        self._check_cuda(img)
+        k = len(timesteps)
+        x = img.float().contiguous()
+        B = x.shape[0]
+        hw = x[0].numel()
+        dev = x.device
+        if noises is None:
+            noises = [None] * k
+        nzs = [_noise_arg(torch.randn_like(x) if n is None else (n.expand_as(x) if n.shape != x.shape else n))
+               for n in noises]
+        t_all = torch.cat([torch.full((B,), int(t), dtype=torch.int64, device=dev) for t in timesteps])
+        x_t = torch.empty((k * B,) + tuple(x.shape[1:]), dtype=torch.float32, device=dev)
+        for i in range(k):
+            nz, f16 = nzs[i]
+            check(lib().cddpm_q_sample(ptr(x), ptr(nz), f16, ptr(x_t[i * B:(i + 1) * B]), ptr(self.sqrt_alphas_cumprod),
+                                       ptr(self.sqrt_one_minus_alphas_cumprod), ptr(t_all[i * B:(i + 1) * B]), 0, B, hw,
+                                       1, current_stream()), "cddpm_q_sample")
+        cond_all = None if cond is None else cond.repeat(k, *([1] * (cond.dim() - 1)))
+        model_out = self.model(x_t, t_all, cond=cond_all)
+        reco = torch.empty_like(x)
+        loss = torch.empty(B, dtype=torch.float32, device=dev)
+        for i in range(k):
+            nz, f16 = nzs[i]
+            check(lib().cddpm_recon_finish(ptr(model_out[i * B:(i + 1) * B]), ptr(x), ptr(x_t[i * B:(i + 1) * B]), ptr(nz),
+                                           f16, ptr(reco), 1.0 / k, 0.0 if i == 0 else 1.0, ptr(loss),
+                                           ptr(self.sqrt_one_minus_alphas_cumprod), ptr(self.p2_loss_weight),
+                                           ptr(t_all[i * B:(i + 1) * B]), 0, B, hw,
+                                           1 if self.objective == "pred_noise" else 0,
+                                           1 if self.loss_type == "l2" else 0, current_stream()), "cddpm_recon_finish")
+        return loss.mean(), reco
+
     def forward(self, img, t=None, *args, **kwargs):
         b = img.shape[0]
         device = img.device

@@ -182,3 +182,30 @@ def test_pipelined_sweep_equals_plain_loop(monkeypatch):
     for k in keys:
         a, b = res["0"][0][k], res["1"][0][k]
         assert len(a) == len(b) and all(x == y or (x != x and y != y) for x, y in zip(a, b)), k
+
+
+def test_stacked_ensemble_equals_member_loop():
+    """reconstruct_slices with the noise ensemble as ONE UNet forward over the 3 x D stacked slices
+    (GaussianDiffusion.ensemble_reconstruct) against the reference's loop of three forwards (DDPM_2D.py:214-232;
+    cfg stack_ensemble=False): same noise draws, every slice an independent sample, so only the summation order of the
+    GroupNorm partials may move - reconstruction within 2e-3, the last member's loss within 1e-4."""
+    from src.models.DDPM_2D import DDPM_2D
+
+    full, _ = _full_state_dict()
+    model = DDPM_2D(_cfg(), prefix="t/")
+    model.load_state_dict(full, strict=True)
+    model = model.cuda().eval()
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(6, 1, 96, 96, generator=g).cuda()
+    out = {}
+    with torch.no_grad():
+        for stacked in (True, False):
+            model.cfg["stack_ensemble"] = stacked
+            np.random.seed(21)
+            reco, loss, feats = model.reconstruct_slices(x)
+            out[stacked] = (reco.cpu(), float(loss), feats.cpu())
+    assert torch.equal(out[True][2], out[False][2])
+    err = (out[True][0] - out[False][0]).abs().max().item()
+    print(f"stacked vs loop: reco max-abs {err:.3g}, loss {out[True][1]:.6f} vs {out[False][1]:.6f}")
+    assert err <= 2e-3
+    assert abs(out[True][1] - out[False][1]) <= 1e-4
