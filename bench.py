@@ -652,11 +652,16 @@ def run_volume(args):
         return
     vols = NV * world * args.steps
     pk = peaks()
-    conv_flops_fwd = eng.conv_flops_per_sample * D
+    # the 3-member noise ensemble of a volume is ONE UNet forward over the 3 x D stacked slices unless the reference's
+    # member loop is selected (cfg stack_ensemble: False)
+    k_ens = len(cfg.get("step_ensemble", [250, 500, 750]))
+    stacked = bool(cfg.get("stack_ensemble", True))
+    fwd_batch = D * k_ens if stacked else D
+    conv_flops_fwd = eng.conv_flops_per_sample * fwd_batch
     conv_ms_fwd = statistics.median(conv_ms)
     achieved = conv_flops_fwd / (conv_ms_fwd / 1e3) / 1e12
     enc_launches = 1 + 1 + 16 * 4 + 4 + 3 + 2
-    per_volume = enc_launches + 3 * (eng.launches_per_forward + 3) + TAIL_LAUNCHES
+    per_volume = enc_launches + (1 if stacked else k_ens) * eng.launches_per_forward + k_ens * 3 + TAIL_LAUNCHES
     line = {"metric": VOLUME_METRIC, "value": vols / (dt_ms / 1e3), "unit": "volumes/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
@@ -666,9 +671,10 @@ def run_volume(args):
                        "volumes_per_gpu": NV, "slices_per_volume": D, "image": "1x96x96",
                        "parallelism": f"volume-sharded x{world}; all-gather of per-volume results + all-reduce of the "
                                       "threshold-search counts at the end of the stage",
-                       "l2": "streaming working set ~3 GB per B=50 UNet forward >> 126 MB L2 (no flush needed)"},
+                       "ensemble": ("one UNet forward over the 3 x D stacked slices" if stacked else "one UNet forward per member"),
+                       "l2": f"streaming working set ~{0.06 * fwd_batch:.0f} GB per B={fwd_batch} UNet forward >> 126 MB L2 (no flush needed)"},
             "roofline": {"bound": "tensor", "kernel": "conv_igemm2_kernel / conv_igemm_kernel (every convolution and GEMM "
-                                                       "launch of the first B=50 UNet forward of a step)",
+                                                       f"launch of the first B={fwd_batch} UNet forward of a step)",
                          "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
                          "peak_source": pk["source"], "flops_per_launch": conv_flops_fwd / max(1, conv_launches),
                          "avg_launch_ms": conv_ms_fwd / max(1, conv_launches), "launches_timed": conv_launches * len(conv_ms),
