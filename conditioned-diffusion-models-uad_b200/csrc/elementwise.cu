@@ -435,6 +435,67 @@ __global__ void __launch_bounds__(256) linear_wide_kernel(const float* __restric
   }
 }
 
+// 16-bit small-batch linear with SiLU (the four embedding MLP layers: M = batch <= 64 rows, K <= 1024).  These ran as
+// flat tcgen05 GEMMs of 4 CTAs (25 us each: barrier / TMEM / tensor-map prologue and a serial K loop) whose 200 KB of
+// shared memory kept them from slipping in beside the stem kernel on the forked graph branches; one warp per output
+// channel with 16-byte loads needs no shared memory and ~32 registers, and finishes in a few microseconds.
+__device__ __forceinline__ float dot8_16(const uint4& a, const uint4& b, int fmt) {
+  const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+  float acc = 0.f;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float2 fa, fb;
+    if (fmt == 1) {
+      fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[e]));
+      fb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&bw[e]));
+    } else {
+      fa = __half22float2(*reinterpret_cast<const __half2*>(&aw[e]));
+      fb = __half22float2(*reinterpret_cast<const __half2*>(&bw[e]));
+    }
+    acc = fmaf(fa.x, fb.x, acc);
+    acc = fmaf(fa.y, fb.y, acc);
+  }
+  return acc;
+}
+constexpr int kLin16BT = 4;
+__global__ void __launch_bounds__(256) linear16_kernel(const uint16_t* __restrict__ in, const uint16_t* __restrict__ w,
+                                                       const float* __restrict__ bias, uint16_t* __restrict__ out,
+                                                       int out_stride, int col_off, int B, int I, int O, int fmt,
+                                                       int silu) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int o = blockIdx.x * 8 + warp;
+  if (o >= O) return;
+  const uint4* wr = reinterpret_cast<const uint4*>(w + static_cast<size_t>(o) * I);
+  const int n8 = I >> 3;
+  const float bv = bias != nullptr ? __ldg(bias + o) : 0.f;
+  for (int b0 = 0; b0 < B; b0 += kLin16BT) {
+    float acc[kLin16BT];
+#pragma unroll
+    for (int j = 0; j < kLin16BT; ++j) acc[j] = 0.f;
+    for (int i = lane; i < n8; i += 32) {
+      const uint4 wv = __ldg(wr + i);
+#pragma unroll
+      for (int j = 0; j < kLin16BT; ++j) {
+        if (b0 + j < B) {
+          const uint4 xv = *(reinterpret_cast<const uint4*>(in + static_cast<size_t>(b0 + j) * I) + i);
+          acc[j] += dot8_16(wv, xv, fmt);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kLin16BT; ++j) {
+      float v = acc[j];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      if (lane == j && b0 + j < B) {
+        v += bv;
+        if (silu) v = v / (1.0f + __expf(-v));
+        out[static_cast<size_t>(b0 + j) * out_stride + col_off + o] = f2h16(v, fmt);
+      }
+    }
+  }
+}
+
 __global__ void to16_kernel(const float* __restrict__ in, uint16_t* __restrict__ out, int n, int fmt) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = f2h16(in[i], fmt);
@@ -799,6 +860,17 @@ int launch_timestep_embedding16(const int64_t* t, float* emb, void* emb16, int f
   const int n = B * (dim / 2);
   timestep_embedding_kernel<<<(n + 255) / 256, 256, 0, stream>>>(t, emb, B, dim, reinterpret_cast<uint16_t*>(emb16), fmt);
   return check_launch("timestep_embedding_kernel");
+}
+
+int launch_linear16(const void* in, const void* w16, const float* bias, void* out, int out_stride, int col_off, int B,
+                    int I, int O, int fmt, int silu, cudaStream_t stream) {
+  if (!in || !w16 || !out) return fail(kInvalidArgument, "linear16: null pointer");
+  if (I % 8 != 0 || ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(w16)) & 15) != 0)
+    return fail(kInvalidArgument, "linear16: K must be a multiple of 8 and the operands 16-byte aligned");
+  linear16_kernel<<<(O + 7) / 8, 256, 0, stream>>>(reinterpret_cast<const uint16_t*>(in),
+                                                   reinterpret_cast<const uint16_t*>(w16), bias,
+                                                   reinterpret_cast<uint16_t*>(out), out_stride, col_off, B, I, O, fmt, silu);
+  return check_launch("linear16_kernel");
 }
 
 int launch_to16(const float* in, void* out, int n, int fmt, cudaStream_t stream) {

@@ -65,6 +65,9 @@ int launch_timestep_embedding(const int64_t* t, float* emb, int B, int dim, cuda
 // ... with an optional 16-bit copy (tensor-core operand); emb may be NULL.
 int launch_timestep_embedding16(const int64_t* t, float* emb, void* emb16, int fmt, int B, int dim, cudaStream_t stream);
 int launch_to16(const float* in, void* out, int n, int fmt, cudaStream_t stream);
+// out16[b][col_off + o] = act(sum_k in16[b][k] w16[o][k] + bias[o]) for small batches (embedding MLPs); fp32 accumulation
+int launch_linear16(const void* in, const void* w16, const float* bias, void* out, int out_stride, int col_off, int B,
+                    int I, int O, int fmt, int silu, cudaStream_t stream);
 
 // Stem: x fp32 [B,1,H,W] -> NHWC 16-bit [B,H,W,Cout], 3x3 pad 1 (OpenAI_Unet.py:609).
 int launch_conv_in(const float* x, const float* w, const float* bias, void* out, double* stats, int B, int H, int W,

@@ -803,8 +803,18 @@ int UNetEngine::plan(int B) {
     sin16_ = sin16;
     hid16_ = hid16;
     cond16_ = hidc16_ = nullptr;
+    // small batches: one-warp-per-output SIMT kernel (elementwise.cu:linear16_kernel); the tcgen05 GEMM keeps the large
+    // batches, where its M tile fills up (CDDPM_EMBED_SIMT=0 forces the GEMM for A/B measurements)
+    static const bool simt_ok = [] {
+      const char* e = getenv("CDDPM_EMBED_SIMT");
+      return !(e != nullptr && e[0] == '0');
+    }();
     auto lin = [&](const uint16_t* in, int I, const uint16_t* w16, const float* bias, uint16_t* out, int O, int stride,
                    int col) -> int {
+      if (simt_ok && B <= 64 && I % 8 == 0) {
+        ops_.push_back([=](cudaStream_t s) { return launch_linear16(in, w16, bias, out, stride, col, B, I, O, fmt, 1, s); });
+        return kOk;
+      }
       ConvDesc d;
       d.num_src = 1;
       d.src[0] = in;
