@@ -61,6 +61,20 @@ int cddpm_conv_igemm(int num_src, const void* const* src, const int* src_c, cons
   d.out = out;
   d.out_is_f32 = out_f32;
   d.ab_format = fmt;
+  {
+    // measurement aid (tools/bench_conv.py): CDDPM_CONV_BENCH_STATS=1 makes the epilogue also emit its GroupNorm
+    // (sum, sumsq) partials, into a scratch table, the way every convolution planned by the UNet engine does
+    static const bool bench_stats = [] {
+      const char* e = getenv("CDDPM_CONV_BENCH_STATS");
+      return e != nullptr && e[0] == '1';
+    }();
+    static double* scratch = nullptr;
+    const size_t need = static_cast<size_t>(B) * (cout / 4 + 1) * 2;
+    if (bench_stats && !out_f32 && need <= (1u << 20)) {
+      if (scratch == nullptr) CDDPM_CUDA(cudaMalloc(&scratch, (1u << 20) * sizeof(double)));
+      d.gn_stats = scratch;
+    }
+  }
   if (conv2_enabled() && conv2_supported(d)) {  // macro-tile kernel where the geometry allows it
     std::shared_ptr<void> holder;
     CDDPM_TRY(build_conv2(d, &holder));

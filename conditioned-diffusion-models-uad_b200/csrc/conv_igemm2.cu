@@ -116,6 +116,22 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
   return v;
 }
 
+// One step of the 4 x 4 transpose of 16-byte items inside every group of four lanes: lanes whose `hi` bit is set trade
+// item a for their partner's, the others item b (partner = lane ^ mask).
+__device__ __forceinline__ void quad_exchange(uint4& a, uint4& b, bool hi, int mask) {
+  const uint4 send = hi ? a : b;
+  uint4 recv;
+  recv.x = __shfl_xor_sync(0xffffffffu, send.x, mask);
+  recv.y = __shfl_xor_sync(0xffffffffu, send.y, mask);
+  recv.z = __shfl_xor_sync(0xffffffffu, send.z, mask);
+  recv.w = __shfl_xor_sync(0xffffffffu, send.w, mask);
+  if (hi) {
+    a = recv;
+  } else {
+    b = recv;
+  }
+}
+
 // Per 4-channel bucket: sum and sum of squares of this pixel's 32 channels, then a butterfly over the warp's 32 pixels
 // (16 shuffles leave value (lane >> 1) & 15 in every lane); lanes write the warp's 16 totals of chunk c.
 __device__ __forceinline__ void emit_stats(const float (&f)[32], bool in_img, int lane, float* stat_dst) {
@@ -575,16 +591,29 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_igemm2_kernel(const __grid_
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.0f + __expf(-f[j]));
         }
-        if (in_img) {
-          uint4* op = reinterpret_cast<uint4*>(p.out + off0 + c * 32);
+        {
+          // A lane holds 64 contiguous bytes of ITS pixel; stored as is, every 16-byte store instruction of the warp
+          // touches 32 different lines (measured: the scattered stores made the epilogue, not the MMAs, the per-item
+          // critical path at K = 1152).  Transposing the four 16-byte items inside each group of four lanes first lets
+          // the group write one pixel's 64 bytes per instruction: 8 lines per store instead of 32.
+          uint4 o[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            uint4 o;
-            o.x = pack16(f[q * 8 + 0], f[q * 8 + 1], fmt);
-            o.y = pack16(f[q * 8 + 2], f[q * 8 + 3], fmt);
-            o.z = pack16(f[q * 8 + 4], f[q * 8 + 5], fmt);
-            o.w = pack16(f[q * 8 + 6], f[q * 8 + 7], fmt);
-            op[q] = o;
+            o[q].x = pack16(f[q * 8 + 0], f[q * 8 + 1], fmt);
+            o[q].y = pack16(f[q * 8 + 2], f[q * 8 + 3], fmt);
+            o[q].z = pack16(f[q * 8 + 4], f[q * 8 + 5], fmt);
+            o[q].w = pack16(f[q * 8 + 6], f[q * 8 + 7], fmt);
+          }
+          const int e = lane & 3;
+          quad_exchange(o[0], o[1], (e & 1) != 0, 1);
+          quad_exchange(o[2], o[3], (e & 1) != 0, 1);
+          quad_exchange(o[0], o[2], (e & 2) != 0, 2);
+          quad_exchange(o[1], o[3], (e & 2) != 0, 2);
+          if (in_img) {  // uniform over the group: its four pixels share an image row
+            // item k now is bytes [16 e, 16 e + 16) of the pixel of lane (lane & ~3) + k
+            uint16_t* ob = p.out + (off0 - static_cast<size_t>(e) * p.Cout) + c * 32 + e * 8;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(ob + static_cast<size_t>(k) * p.Cout) = o[k];
           }
         }
         if (p.gn_stats != nullptr)
