@@ -208,7 +208,7 @@ def run_reference(args):
             "config": workload_config(args, 32),
             "cpu_baseline": {"value": v, "unit": "slices/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, batch):
@@ -354,7 +354,7 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": v, "unit": "slices/s", "cores": threads, "kind": "port",
                                 "sample": f"oracle port (fp32 PyTorch) on the host: best of batch 1 / batch 2 (here {bb}) x 2 "
                                           f"reverse steps + encoder, extrapolated to the {T0}-step loop", **parts}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -503,7 +503,7 @@ def run_train(args):
         line["cpu_baseline"] = {"value": v, "unit": "slices/s", "cores": threads, "kind": "port",
                                 "sample": "oracle port (fp32 PyTorch autograd) on the host: UNet forward + backward of one "
                                           "slice, best of 2 after a warm-up"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -692,7 +692,7 @@ def run_volume(args):
                                 "sample": "oracle port (fp32 PyTorch + numpy/scipy) on the host: encoder + 3 ensemble "
                                           f"reconstructions of 2 slices extrapolated to {D}, plus the full tail of one volume",
                                 **parts}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -703,9 +703,24 @@ def lib_bwd_launches(eng):
     return lib().cddpm_unet_bwd_launches(eng._h)
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    """The one JSON line of this run, on the process's ORIGINAL stdout."""
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
-    # stdout carries exactly one JSON line: NCCL's own banner / debug output ("NCCL version ...") goes to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # stdout carries exactly one JSON line.  NCCL prints its banner ("NCCL version ...") to file descriptor 1 from native
+    # code (NCCL_DEBUG_FILE does not move it), so keep a private copy of the real stdout for the JSON line and point
+    # descriptor 1 at stderr for everything else.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
