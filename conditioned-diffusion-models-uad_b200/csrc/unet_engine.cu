@@ -30,9 +30,10 @@ void UNetEngine::drop_graph() {
 static bool fuse_gn_enabled() {
   static int v = -1;
   if (v < 0) {
-    // OFF by default: built, parity-green and measured on B200 (profiles/r01_v13_summary.md) - the rendezvous keeps the
-    // accumulator stage ~2x longer than the plain epilogue and the convolution loses more than the GroupNorm pass costs
-    // (B=32 forward 5.20 ms separate vs 5.43-5.46 ms fused).  CDDPM_FUSE_GN=1 enables it for inference engines.
+    // OFF by default: built, parity-green and measured on B200 (profiles/r01_v13_summary.md, r01_v15_fuse_ab_bench.log) -
+    // the rendezvous keeps the accumulator stage ~2x longer than the plain epilogue and the convolution loses more than
+    // the GroupNorm pass costs (B=32 forward 5.38 ms separate vs 5.38-5.60 ms fused; 500-step loop 10.82 vs 10.55-10.62
+    // slices/s on the same box).  CDDPM_FUSE_GN=1 enables it for inference engines.
     const char* e = getenv("CDDPM_FUSE_GN");
     v = (e != nullptr && e[0] == '1') ? 1 : 0;
   }
