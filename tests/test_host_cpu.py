@@ -315,3 +315,25 @@ def test_sharded_test_sweep_world_size_2_gloo(tmp_path):
     outs = [p.communicate(timeout=180)[0].decode() for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py's stdout contract: ONE JSON line on the process's stdout, everything else (library banners, notes) on
+    stderr - main() keeps a private copy of the real stdout and points descriptor 1 at stderr, because NCCL writes its
+    banner to descriptor 1 from native code.  Exercised here through the CPU-runnable reference arm (the oracle port
+    timed on the host), which must also carry the keys the driver pairs with our arm's line."""
+    import json
+    import subprocess
+    import sys
+
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["unit"] == "slices/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["n_gpus"] == 1 and line["steps"] == 1
+    assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["config"]["workload"].startswith("configs[1]")
