@@ -162,7 +162,9 @@ __device__ __forceinline__ void emit_stats(const float (&f)[32], bool in_img, in
   if ((lane & 1) == 0) stat_dst[lane >> 1] = tot;
 }
 
-template <int kMT>
+// kFuse: the experimental GroupNorm finish inside the epilogue (ConvDesc::gn_gamma) is its own instantiation, so the
+// default kernel does not carry its registers.
+template <int kMT, bool kFuse = false>
 __global__ void __launch_bounds__(kThreads2, 1) conv_igemm2_kernel(const __grid_constant__ Conv2Params p) {
   using G = Geo<kMT>;
   constexpr int kMTiles = kMT;
@@ -393,7 +395,7 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_igemm2_kernel(const __grid_
       const bool in_img = valid && y < p.H;  // the bottom tile of a 24-row image hangs over its edge
       const bool has_res = p.residual != nullptr && in_img;
 
-      if (p.gn_gamma != nullptr) {
+      if constexpr (kFuse) {
         // ---------------------------------------------------------------- fused GroupNorm (+FiLM) + SiLU finish
         // The GroupNorm that follows this convolution needs whole-image statistics.  Phase 1 reads the accumulator,
         // publishes this tile's partial sums (double atomics) and counts the tile in a per-(image, N tile) counter;
@@ -729,6 +731,10 @@ int launch_conv2(const std::shared_ptr<void>& holder, cudaStream_t stream) {
                                     Geo<1>::kSmemBytes));
     CDDPM_CUDA(cudaFuncSetAttribute(conv_igemm2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     Geo<2>::kSmemBytes));
+    CDDPM_CUDA(cudaFuncSetAttribute(conv_igemm2_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    Geo<1>::kSmemBytes));
+    CDDPM_CUDA(cudaFuncSetAttribute(conv_igemm2_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    Geo<2>::kSmemBytes));
     attr_set = true;
   }
   const Conv2Launch* L = reinterpret_cast<const Conv2Launch*>(holder.get());
@@ -756,10 +762,19 @@ int launch_conv2(const std::shared_ptr<void>& holder, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  const bool fuse = L->p.gn_gamma != nullptr;
   if (L->p.mt == 2) {
-    CDDPM_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm2_kernel<2>, L->p));
+    if (fuse) {
+      CDDPM_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm2_kernel<2, true>, L->p));
+    } else {
+      CDDPM_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm2_kernel<2>, L->p));
+    }
   } else {
-    CDDPM_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm2_kernel<1>, L->p));
+    if (fuse) {
+      CDDPM_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm2_kernel<1, true>, L->p));
+    } else {
+      CDDPM_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm2_kernel<1>, L->p));
+    }
   }
   return check_launch("conv_igemm2_kernel");
 }
