@@ -202,3 +202,33 @@ def test_encoder_port_matches_golden():
         c = resnet_port.resnet_forward(sd, torch.from_numpy(g["x"]))
     assert (c - torch.from_numpy(g["c"])).abs().max().item() < 1e-4
     assert len(resnet_port.param_shapes(128)) == 320
+
+
+def test_noise_ensemble_members_are_independent_batch_samples():
+    """Why the product may run the noise ensemble (DDPM_2D.py:214-232) as ONE UNet forward over the stacked members:
+    in the reference's own arithmetic (oracle port, fp32 CPU) every sample of a batch is independent - per-sample
+    timestep embedding, GroupNorm statistics per sample, attention per sample - so k forwards at (t_i, noise_i) over D
+    slices equal one forward over the k x D stacked slices with a per-sample t vector."""
+    from oracle import diffusion_port, unet_port
+    from oracle.weights import make_state_dict
+
+    spec = unet_port.UNetSpec(model_channels=64, channel_mult=(1, 2), num_res_blocks=1, num_classes=128)
+    sd = make_state_dict(unet_port.param_shapes(spec), seed=2)
+    sched = diffusion_port.schedule_buffers()
+    g = torch.Generator().manual_seed(0)
+    D, steps = 3, (249, 499, 749)
+    img = torch.rand(D, 1, 32, 32, generator=g)
+    cond = torch.randn(D, 128, generator=g)
+    noises = [0.6 * torch.randn(D, 1, 32, 32, generator=g) for _ in steps]
+    model = lambda x, t, c: unet_port.unet_forward(sd, spec, x, t, c)  # noqa: E731
+    with torch.no_grad():
+        loop = [diffusion_port.reconstruct(model, sched, img, t, cond, n)[1] for t, n in zip(steps, noises)]
+        x0 = img * 2 - 1
+        tt = torch.cat([torch.full((D,), t, dtype=torch.long) for t in steps])
+        xt = torch.cat([diffusion_port.q_sample(sched, x0, tt[i * D:(i + 1) * D], n) for i, n in enumerate(noises)])
+        out = model(xt, tt, cond.repeat(len(steps), 1))
+        stacked = ((out + 1) * 0.5).reshape(len(steps), D, 1, 32, 32)
+    for i in range(len(steps)):
+        assert (stacked[i] - loop[i]).abs().max().item() <= 2e-5
+    mean_loop = sum(loop) / len(steps)
+    assert (stacked.mean(0) - mean_loop).abs().max().item() <= 2e-5
