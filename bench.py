@@ -240,7 +240,10 @@ def run_ours(args):
     B, T0 = args.batch, args.start_t
     torch.manual_seed(1234 + rank)
     np.random.seed(1234 + rank)
-    model = DDPM_2D(model_cfg(), prefix="bench/")
+    cfg = model_cfg()
+    if args.dtype == "bf16":
+        cfg["engine_dtype"] = "bf16"  # same tcgen05 rate; fp16 is the default because it is 10x closer to the fp32 reference
+    model = DDPM_2D(cfg, prefix="bench/")
     with torch.no_grad():  # random-init every tensor, including the reference's zero-initialised output convolutions
         for name, p in model.named_parameters():
             if p.dim() >= 2 and float(p.abs().sum()) == 0.0:
@@ -342,7 +345,8 @@ def run_ours(args):
                 "unet_forward_frac_of_peak": UNET_GFLOP * B * T0 * args.steps / 1e3 / (dt_ms / 1e3) / pk["tflops"]}
     line = {"metric": METRIC, "value": value, "unit": "slices/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f16", "data": "synthetic", "config": workload_config(args, B),
+            "vs_baseline": None, "dtype": "bf16" if args.dtype == "bf16" else "f16", "data": "synthetic",
+            "config": workload_config(args, B),
             "roofline": roofline,
             "e2e": {"value": e2e_value, "unit": "slices/s", "h2d_bytes_per_step": x_host.numel() * 4,
                     "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": e2e_ms / args.steps},
@@ -578,6 +582,8 @@ def run_volume(args):
     np.random.seed(1234 + rank)
     cfg = model_cfg()
     cfg["force_num_eval_slices"] = False  # all 50 slices, not the fork's hard-coded 4
+    if args.dtype == "bf16":
+        cfg["engine_dtype"] = "bf16"
     model = DDPM_2D(cfg, prefix="bench/")
     with torch.no_grad():
         for name, p in model.named_parameters():
@@ -664,7 +670,7 @@ def run_volume(args):
     per_volume = enc_launches + (1 if stacked else k_ens) * eng.launches_per_forward + k_ens * 3 + TAIL_LAUNCHES
     line = {"metric": VOLUME_METRIC, "value": vols / (dt_ms / 1e3), "unit": "volumes/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.dtype == "bf16" else "f16", "data": "synthetic",
             "config": {"workload": f"configs[2]: full-volume reconstruction + anomaly map, {NV} synthetic BraTS21-shaped "
                                    f"[1,1,96,96,{D}] volumes per GPU per step, validation stage of the test sweep "
                                    "(noise ensemble 250/500/750, all slices), global threshold search at the end",
@@ -732,6 +738,10 @@ def main():
                          "volumes per GPU per step); train = configs[4]")
     ap.add_argument("--start-t", dest="start_t", type=int, default=500)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"],
+                    help="16-bit storage / tensor-core operand type of the inference engines (reverse, volume); fp32 "
+                         "accumulation either way.  The reference runs fp16 autocast (trainer/default.yaml:7); training is "
+                         "always bf16")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         print(f"note: --warmup {args.warmup} < 3 breaks the timing rules; use >= 3 for a reportable number", file=sys.stderr)
