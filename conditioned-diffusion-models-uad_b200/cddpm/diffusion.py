@@ -127,6 +127,14 @@ class GaussianDiffusion(nn.Module):
         if not t.is_cuda or not self.betas.is_cuda:
             raise CddpmError("GaussianDiffusion needs CUDA tensors and a CUDA module (no CPU path)")
 
+    def _check_t(self, lo: int, hi: Optional[int] = None):
+        """The reference indexes its [T] schedule buffers with t and raises IndexError outside [0, T)
+        (cond_DDPM.py:272-275 `extract`); the kernels index raw pointers, so the check lives on the host."""
+        hi = lo if hi is None else hi
+        if lo < 0 or hi >= self.num_timesteps:
+            raise IndexError(f"timestep index {lo if lo < 0 else hi} is out of range for the {self.num_timesteps}-entry "
+                             f"schedule")
+
     @property
     def loss_fn(self):
         if self.loss_type == "l1":
@@ -144,6 +152,8 @@ class GaussianDiffusion(nn.Module):
         x = x_start.float().contiguous()
         B = x.shape[0]
         hw = x[0].numel()
+        if not t.is_cuda:  # host-side indices are checked here; device-side ones by the callers that made them
+            self._check_t(int(t.min()), int(t.max()))
         t = t.to(device=x.device, dtype=torch.int64).contiguous()
         shared = 1 if (t.numel() == 1 and B != 1) else 0
         nz, f16 = _noise_arg(noise.expand_as(x) if noise.shape != x.shape else noise)
@@ -162,6 +172,8 @@ class GaussianDiffusion(nn.Module):
         self._check_cuda(ref)
         if noise is None:
             noise = torch.randn_like(ref)
+        elif noise.shape != ref.shape:  # broadcast-shaped noise: one expansion for q_sample AND the finishing kernels
+            noise = noise.expand_as(ref).contiguous()
         B = ref.shape[0]
         hw = ref[0].numel()
         t = t.to(device=ref.device, dtype=torch.int64).contiguous()
@@ -233,6 +245,10 @@ class GaussianDiffusion(nn.Module):
         if t is None:
             t = torch.randint(0, self.num_timesteps, (b,), device=device).long()
         else:
+            if isinstance(t, (int, float)):
+                self._check_t(int(t))
+            elif torch.is_tensor(t):
+                self._check_t(int(t.min()), int(t.max()))
             t = (torch.ones([b], device=device) * t).long()
         # normalize_to_neg_one_to_one (cond_DDPM.py:653) is fused into the q_sample kernel
         return self.p_losses(None, t, *args, _img=img, **kwargs)
@@ -267,6 +283,7 @@ class GaussianDiffusion(nn.Module):
         self._check_cuda(x)
         if not clip_denoised:
             raise NotImplementedError("clip_denoised=False is never used by the reference")
+        self._check_t(int(t))
         B = x.shape[0]
         hw = x[0].numel()
         bt = torch.full((B,), t, device=x.device, dtype=torch.long)
@@ -297,6 +314,7 @@ class GaussianDiffusion(nn.Module):
         T = self.num_timesteps if start_t == 0 else start_t
         if noise is not None:
             nz = gen_noise(self.cfg, shape, device=device)
+            self._check_t(T)  # start_t=0 means T=num_timesteps: the reference raises IndexError here too
             img = self.q_sample(x_start=x_start, t=torch.tensor([T], device=device), noise=nz)
         else:
             img = torch.randn(shape, device=device)

@@ -89,6 +89,12 @@ class ResNet(nn.Module):
         self._versions = None
         return super()._apply(fn, *args, **kwargs)
 
+    def train(self, mode: bool = True):
+        # The training forward updates running_mean / running_var inside CUDA-graph replays, which do not advance the
+        # tensors' _version (the change signal _sync() uses): re-push everything after every mode change.
+        self._versions = None
+        return super().train(mode)
+
     def _engine_items(self) -> List[Tuple[str, torch.Tensor]]:
         if self._items is None:
             self._items = [(k, v) for k, v in self.state_dict(keep_vars=True).items()

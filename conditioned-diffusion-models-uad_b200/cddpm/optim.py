@@ -24,6 +24,8 @@ class Adam(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
         self._tables = {}
 
+    _RING = 4  # pinned gradient-pointer tables in flight (one CUDA event each)
+
     def _init_group(self, gi, group):
         ps = [p for p in group["params"] if p.requires_grad]
         for p in ps:
@@ -36,6 +38,10 @@ class Adam(torch.optim.Optimizer):
                 st["step"] = torch.zeros((), dtype=torch.float32)
                 st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                 st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+            elif not st["exp_avg"].is_cuda or not st["exp_avg"].is_contiguous() or \
+                    not st["exp_avg_sq"].is_contiguous():  # e.g. a checkpoint loaded with map_location="cpu"
+                st["exp_avg"] = st["exp_avg"].to(dev, torch.float32).contiguous()
+                st["exp_avg_sq"] = st["exp_avg_sq"].to(dev, torch.float32).contiguous()
         numel = [p.numel() for p in ps]
         block_tensor, block_off = [], []
         for t, n in enumerate(numel):
@@ -51,12 +57,50 @@ class Adam(torch.optim.Optimizer):
             "numel": torch.tensor(numel, **i64),
             "block_tensor": torch.tensor(block_tensor, dtype=torch.int32, device=dev),
             "block_off": torch.tensor(block_off, **i64),
-            "g_host": torch.zeros(len(ps), dtype=torch.int64).pin_memory(),
-            "g": torch.zeros(len(ps), **i64),
-            "ptrs": [p.data_ptr() for p in ps],
+            # gradient tensors are new every backward: their pointer table is refreshed per launch through a ring of
+            # pinned host buffers + device copies, each guarded by an event recorded after the kernel that reads it, so a
+            # host running ahead of the GPU never overwrites a table a pending copy / kernel still needs
+            "g_host": [torch.zeros(len(ps), dtype=torch.int64).pin_memory() for _ in range(self._RING)],
+            "g": [torch.zeros(len(ps), **i64) for _ in range(self._RING)],
+            "g_event": [None] * self._RING,
+            "slot": 0,
+            "key": self._key(ps),
         }
         self._tables[gi] = tab
         return tab
+
+    def _key(self, ps):
+        """Everything the cached device tables point at: parameter storages AND the moment buffers (load_state_dict
+        replaces the latter)."""
+        key = []
+        for p in ps:
+            st = self.state.get(p, {})
+            m, v = st.get("exp_avg"), st.get("exp_avg_sq")
+            key.append((p.data_ptr(), m.data_ptr() if m is not None else 0, v.data_ptr() if v is not None else 0))
+        return key
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._tables = {}  # the moment tensors were replaced: every cached pointer table is stale
+
+    def _launch(self, tab, group, ptrs, step):
+        slot = tab["slot"]
+        tab["slot"] = (slot + 1) % self._RING
+        ev = tab["g_event"][slot]
+        if ev is not None:
+            ev.synchronize()
+        tab["g_host"][slot].copy_(torch.tensor(ptrs, dtype=torch.int64))
+        tab["g"][slot].copy_(tab["g_host"][slot], non_blocking=True)
+        b1, b2 = group["betas"]
+        bc1 = 1.0 - b1 ** step
+        bc2 = 1.0 - b2 ** step
+        check(lib().cddpm_adam_step(ptr(tab["p"]), ptr(tab["g"][slot]), ptr(tab["m"]), ptr(tab["v"]), ptr(tab["numel"]),
+                                    ptr(tab["block_tensor"]), ptr(tab["block_off"]), tab["block_tensor"].numel(),
+                                    float(group["lr"]), float(b1), float(b2), float(group["eps"]), bc1, bc2,
+                                    current_stream()), "cddpm_adam_step")
+        if ev is None:
+            ev = tab["g_event"][slot] = torch.cuda.Event()
+        ev.record()
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -66,9 +110,9 @@ class Adam(torch.optim.Optimizer):
                 loss = closure()
         for gi, group in enumerate(self.param_groups):
             tab = self._tables.get(gi)
-            if tab is None or tab["ptrs"] != [p.data_ptr() for p in tab["params"]] or \
-                    len(tab["params"]) != sum(1 for p in group["params"] if p.requires_grad):
-                tab = self._init_group(gi, group)  # first step, or .to()/.cuda() re-seated the storages
+            if tab is None or len(tab["params"]) != sum(1 for p in group["params"] if p.requires_grad) or \
+                    tab["key"] != self._key(tab["params"]):
+                tab = self._init_group(gi, group)  # first step, .to()/.cuda() re-seated storages, or load_state_dict
             ps = tab["params"]
             keep = []
             ptrs = []
@@ -81,19 +125,23 @@ class Adam(torch.optim.Optimizer):
                     g = g.float().contiguous()
                     keep.append(g)
                 ptrs.append(g.data_ptr())
-            tab["g_host"].copy_(torch.tensor(ptrs, dtype=torch.int64))
-            tab["g"].copy_(tab["g_host"], non_blocking=True)
-            steps = [self.state[p]["step"] for p in ps]
-            step = float(steps[0]) + 1.0  # one counter per group (every parameter receives a gradient every step)
+            # like torch.optim.Adam, only parameters that received a gradient advance their step counter; tensors whose
+            # counters differ (a parameter that sat out some steps) are updated by separate launches of the same table
+            active = [i for i, a in enumerate(ptrs) if a]
+            if not active:
+                continue
+            steps = [self.state[ps[i]]["step"] for i in active]
             torch._foreach_add_(steps, 1.0)
-            b1, b2 = group["betas"]
-            bc1 = 1.0 - b1 ** step
-            bc2 = 1.0 - b2 ** step
-            check(lib().cddpm_adam_step(ptr(tab["p"]), ptr(tab["g"]), ptr(tab["m"]), ptr(tab["v"]), ptr(tab["numel"]),
-                                        ptr(tab["block_tensor"]), ptr(tab["block_off"]), tab["block_tensor"].numel(),
-                                        float(group["lr"]), float(b1), float(b2), float(group["eps"]), bc1, bc2,
-                                        current_stream()), "cddpm_adam_step")
-            _bump_versions(ps)  # in-place update through raw pointers: tell the engines the values changed
+            vals = [float(s) for s in steps]
+            if all(v == vals[0] for v in vals):
+                self._launch(tab, group, ptrs, vals[0])
+            else:
+                for sv in sorted(set(vals)):
+                    members = {i for i, v in zip(active, vals) if v == sv}
+                    self._launch(tab, group, [a if i in members else 0 for i, a in enumerate(ptrs)], sv)
+            _bump_versions([ps[i] for i in active])  # in-place update through raw pointers: tell the engines
+            if keep:  # converted copies must outlive the kernel that reads them
+                torch.cuda.current_stream().synchronize()
             del keep
         return loss
 

@@ -1068,12 +1068,14 @@ int UNetEngine::forward(const float* x, const int64_t* t, const float* cond, flo
     CDDPM_CUDA(cudaMemcpyAsync(stage_x_, x, n_x * sizeof(float), cudaMemcpyDeviceToDevice, stream));
     CDDPM_CUDA(cudaMemcpyAsync(stage_t_, t, static_cast<size_t>(B) * sizeof(int64_t), cudaMemcpyDeviceToDevice, stream));
     if (n_cond) CDDPM_CUDA(cudaMemcpyAsync(stage_cond_, cond, n_cond * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    // every replay reads the staging buffers: the backward ops (unet_backward.cu) follow cur_*, and an eager forward
+    // in between (profile_arm) repoints them at the caller's tensors
+    cur_x_ = stage_x_;
+    cur_t_ = stage_t_;
+    cur_cond_ = n_cond ? stage_cond_ : nullptr;
+    cur_out_ = stage_out_;
     if (graph_exec_ == nullptr) {
       if (cap_stream_ == nullptr) CDDPM_CUDA(cudaStreamCreateWithFlags(&cap_stream_, cudaStreamNonBlocking));
-      cur_x_ = stage_x_;
-      cur_t_ = stage_t_;
-      cur_cond_ = n_cond ? stage_cond_ : nullptr;
-      cur_out_ = stage_out_;
       CDDPM_CUDA(cudaStreamBeginCapture(cap_stream_, cudaStreamCaptureModeThreadLocal));
       int st = capture_ops();
       cudaGraph_t graph = nullptr;

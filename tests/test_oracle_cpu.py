@@ -232,3 +232,37 @@ def test_noise_ensemble_members_are_independent_batch_samples():
         assert (stacked[i] - loop[i]).abs().max().item() <= 2e-5
     mean_loop = sum(loop) / len(steps)
     assert (stacked.mean(0) - mean_loop).abs().max().item() <= 2e-5
+
+
+def test_ports_reproduce_headline_geometry_goldens():
+    """The oracle ports at BASELINE's own geometry (conditioned 128-channel UNet, 96x96) against goldens of the LIVE
+    reference: the encoder's condition vector, the T0 = 50 reverse loop of configs[1] (50 UNet forwards of batch 2,
+    ~30 s of host time) and configs[0]'s unconditioned single step - all bit-identical, simplex noise regenerated from
+    the stored numpy seed."""
+    from oracle import diffusion_port, resnet_port, unet_port
+    from oracle.simplex_port import gen_noise_port
+    from oracle.weights import make_state_dict, synthetic_slices
+
+    sched = diffusion_port.schedule_buffers()
+    with torch.no_grad():
+        g = np.load(os.path.join(GOLD, "uncond_step_96.npz"))
+        spec = unet_port.UNetSpec(num_classes=None)
+        sd = make_state_dict(unet_port.param_shapes(spec), seed=1)
+        x = synthetic_slices(1, 96, seed=41)
+        np.random.seed(int(g["seed"]))
+        loss, reco = diffusion_port.reconstruct(lambda a, t, c: unet_port.unet_forward(sd, spec, a, t, c), sched, x, 499,
+                                                None, gen_noise_port((1, 1, 96, 96)))
+        assert (reco - torch.from_numpy(g["reco"])).abs().max().item() <= 1e-6
+        assert abs(float(loss) - float(g["loss"])) <= 1e-6
+
+        g = np.load(os.path.join(GOLD, "reverse_96.npz"))
+        spec = unet_port.UNetSpec()
+        sd = make_state_dict(unet_port.param_shapes(spec), seed=1)
+        enc = make_state_dict(resnet_port.param_shapes(128), seed=3)
+        x = synthetic_slices(2, 96, seed=31)
+        cond = resnet_port.resnet_forward(enc, x)
+        assert (cond - torch.from_numpy(g["cond"])).abs().max().item() <= 1e-6
+        np.random.seed(int(g["seed_T50"]))
+        rec = diffusion_port.reverse_loop(lambda a, t, c: unet_port.unet_forward(sd, spec, a, t, c), sched, x * 2 - 1,
+                                          cond, 50, lambda: gen_noise_port((2, 1, 96, 96)))
+        assert (rec - torch.from_numpy(g["out_T50"])).abs().max().item() <= 1e-5

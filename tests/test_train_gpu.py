@@ -286,10 +286,79 @@ def test_adam_kernel_matches_torch_adam():
         ot.step()
         assert ours[0]._version > v0  # the engines watch the version counters
     torch.cuda.synchronize()
-    for a, b in zip(ours[:3] + ours[4:], ref[:3] + ref[4:]):
+    # the parameter that sat out three of the five steps advanced its own step counter twice, like torch's
+    for a, b in zip(ours, ref):
         assert (a - b).abs().max().item() <= 2e-6, (a.shape, (a - b).abs().max().item())
     sd = oa.state_dict()
     assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}
+    assert float(sd["state"][3]["step"]) == 2.0 and float(sd["state"][0]["step"]) == 5.0
+
+
+def test_adam_load_state_dict_reseats_the_moment_tables():
+    """Optimizer.load_state_dict replaces exp_avg / exp_avg_sq: the cached device pointer tables must follow (ADVICE r1:
+    the kernel kept writing the old, freed moment buffers).  A stepped optimizer restored from a checkpoint has to
+    continue exactly like torch.optim.Adam restored from the same checkpoint."""
+    import copy
+
+    from cddpm.optim import Adam
+
+    g = torch.Generator(device="cuda").manual_seed(1)
+    shapes = [(33,), (4097,), (64, 32, 3, 3)]
+    ours = [torch.nn.Parameter(torch.randn(s, device="cuda", generator=g)) for s in shapes]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ours]
+    oa, ot = Adam(ours, lr=1e-3), torch.optim.Adam(ref, lr=1e-3)
+
+    def step_both(n):
+        for _ in range(n):
+            for a, b in zip(ours, ref):
+                gr = torch.randn(a.shape, device="cuda", generator=g)
+                a.grad, b.grad = gr.clone(), gr.clone()
+            oa.step()
+            ot.step()
+
+    step_both(3)
+    ck_o, ck_t = copy.deepcopy(oa.state_dict()), copy.deepcopy(ot.state_dict())
+    pk = [p.detach().clone() for p in ours]
+    step_both(2)  # move on, then rewind both to the checkpoint
+    with torch.no_grad():
+        for a, b, v in zip(ours, ref, pk):
+            a.copy_(v)
+            b.copy_(v)
+    oa.load_state_dict(ck_o)
+    ot.load_state_dict(ck_t)
+    step_both(2)
+    torch.cuda.synchronize()
+    for a, b in zip(ours, ref):
+        assert (a - b).abs().max().item() <= 2e-6
+    for i in range(len(ours)):  # the moments the optimizer would checkpoint are the live ones
+        assert (oa.state[ours[i]]["exp_avg"] - ot.state[ref[i]]["exp_avg"]).abs().max().item() <= 1e-6
+        assert float(oa.state[ours[i]]["step"]) == 5.0
+
+
+def test_adam_pointer_tables_survive_a_host_running_ahead():
+    """Many steps enqueued back to back behind a long-running kernel: the per-step gradient pointer tables go through a
+    ring of pinned buffers guarded by events, so no table is overwritten before the GPU has consumed it."""
+    from cddpm.optim import Adam
+
+    g = torch.Generator(device="cuda").manual_seed(2)
+    ours = [torch.nn.Parameter(torch.randn(1000, device="cuda", generator=g)) for _ in range(8)]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ours]
+    oa, ot = Adam(ours, lr=1e-2), torch.optim.Adam(ref, lr=1e-2)
+    grads = [[torch.randn(1000, device="cuda", generator=g) for _ in ours] for _ in range(12)]
+    big = torch.randn(8192, 8192, device="cuda")
+    for _ in range(20):  # ~tens of ms of queued GPU work: the host gets far ahead of the device
+        big = big @ big * 1e-4
+    for step in grads:
+        for a, gr in zip(ours, step):
+            a.grad = gr.clone()  # a fresh allocation per step, like a real backward
+        oa.step()
+    for step in grads:
+        for b, gr in zip(ref, step):
+            b.grad = gr.clone()
+        ot.step()
+    torch.cuda.synchronize()
+    for a, b in zip(ours, ref):
+        assert (a - b).abs().max().item() <= 5e-6
 
 
 @pytest.mark.parametrize("opt_kind", ["cddpm", "torch_fused"])
@@ -329,3 +398,38 @@ def test_engine_sees_optimizer_updates(opt_kind):
     with torch.no_grad():
         after_eval = m(x, t, c)
     assert (after_eval - before_eval).abs().max().item() > 1e-3, "eval forward still runs on the old weights"
+
+
+def test_encoder_eval_after_graphed_training_sees_new_bn_statistics():
+    """the training forward updates the BatchNorm running statistics inside CUDA-graph replays, which
+    never advance the tensors' _version; the eval engine must still fold the NEW statistics after train() -> eval().
+    Compared with a fresh engine loaded from state_dict()."""
+    from cddpm.encoder import get_encoder
+
+    cfg = Cfg(imageDim=[192, 192, 100], rescaleFactor=2, backbone="Spark_Encoder_2D", version="resnet50", cond_dim=128)
+    torch.manual_seed(3)
+    enc, _ = get_encoder(cfg)
+    with torch.no_grad():
+        for n, p in enc.named_parameters():
+            if n.endswith("bn3.weight"):
+                p.fill_(0.5)  # timm's zero_init_last would silence every residual branch
+    enc = enc.cuda()
+    x = torch.rand(4, 1, 96, 96, device="cuda")
+    enc.eval()
+    with torch.no_grad():
+        y_before = enc(x).clone()  # the engine now holds the initial statistics
+    enc.train()
+    for _ in range(3):  # first call captures, the others replay
+        enc(x * (1.0 + torch.rand(1, device="cuda"))).square().mean().backward()
+    rm = enc.state_dict()["encoder.bn1.running_mean"]
+    assert float(rm.abs().max()) > 0  # training moved the statistics
+    enc.eval()
+    with torch.no_grad():
+        y_after = enc(x).clone()
+    fresh, _ = get_encoder(cfg)
+    fresh.load_state_dict(enc.state_dict(), strict=True)
+    fresh = fresh.cuda().eval()
+    with torch.no_grad():
+        y_fresh = fresh(x)
+    assert (y_after - y_before).abs().max().item() > 1e-4, "eval output did not react to three training steps"
+    assert torch.equal(y_after, y_fresh), (y_after - y_fresh).abs().max().item()
