@@ -92,11 +92,13 @@ def _signatures(c):
         "cddpm_encoder_forward": (i32, [vp, vp, vp, i32, vp]),
         "cddpm_simplex_noise": (i32, [c.c_char_p, vp, vp, i32, i32, i32, i32, c.c_double, c.c_double, vp]),
         "cddpm_q_sample": (i32, [vp, vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
-        "cddpm_posterior_step": (i32, [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]),
+        "cddpm_posterior_step": (i32, [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, vp]),
+        "cddpm_ddim_step": (i32, [vp, vp, vp, i32, vp, f32, f32, f32, f32, f32, i32, i32, i32, i32, i32, vp]),
         "cddpm_loss_backward": (i32, [vp, vp, vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
         "cddpm_recon_finish": (
             i32, [vp, vp, vp, vp, i32, vp, f32, f32, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
         "cddpm_residual_erode": (i32, [pview, pview, pview, pview, i32, i32, i32, i32, i32, vp, vp, vp]),
+        "cddpm_trilinear_resize": (i32, [pview, i32, i32, i32, vp, i32, i32, i32, vp]),
         "cddpm_median3d": (i32, [vp, vp, i32, i32, i32, i32, vp]),
         "cddpm_max": (i32, [vp, i64, vp, vp]),
         "cddpm_threshold_counts": (i32, [vp, pview, i32, i32, i32, c.POINTER(f32), i32, vp, vp]),

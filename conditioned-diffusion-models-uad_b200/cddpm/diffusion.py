@@ -34,6 +34,11 @@ def linear_beta_schedule(timesteps):
     return torch.linspace(scale * 0.0001, scale * 0.02, timesteps, dtype=torch.float64)
 
 
+def _randn(shape, device):
+    """Gaussian draws of the sampling loops (one seam, so tests can pin the stream)."""
+    return torch.randn(tuple(shape), device=device)
+
+
 def _noise_arg(noise: torch.Tensor):
     """(tensor, is_f16) for the kernels: fp16 noise is consumed as is, anything else as fp32."""
     if noise.dtype == torch.float16:
@@ -281,15 +286,13 @@ class GaussianDiffusion(nn.Module):
         """One reverse step.  As in the reference, a non-None `noise` only selects simplex noise: a fresh field is
         drawn with gen_noise for every step (cond_DDPM.py:442); None selects Gaussian noise."""
         self._check_cuda(x)
-        if not clip_denoised:
-            raise NotImplementedError("clip_denoised=False is never used by the reference")
         self._check_t(int(t))
         B = x.shape[0]
         hw = x[0].numel()
         bt = torch.full((B,), t, device=x.device, dtype=torch.long)
         model_out = self.model.forward_with_cond_scale(x, bt, cond=cond, cond_scale=cond_scale)
         if noise is None:
-            nz = torch.randn_like(x) if t > 0 else None
+            nz = _randn(x.shape, x.device) if t > 0 else None
         else:
             nz = gen_noise(self.cfg, x.shape, device=x.device)  # drawn even at t == 0, like the reference
             if t == 0:
@@ -303,7 +306,8 @@ class GaussianDiffusion(nn.Module):
                                          ptr(self.posterior_log_variance_clipped),
                                          ptr(self.sqrt_recip_alphas_cumprod), ptr(self.sqrt_recipm1_alphas_cumprod),
                                          int(t), B, hw, 1 if self.objective == "pred_noise" else 0,
-                                         1 if _final else 0, current_stream()), "cddpm_posterior_step")
+                                         1 if clip_denoised else 0, 1 if _final else 0, current_stream()),
+              "cddpm_posterior_step")
         return out
 
     @torch.no_grad()
@@ -317,7 +321,7 @@ class GaussianDiffusion(nn.Module):
             self._check_t(T)  # start_t=0 means T=num_timesteps: the reference raises IndexError here too
             img = self.q_sample(x_start=x_start, t=torch.tensor([T], device=device), noise=nz)
         else:
-            img = torch.randn(shape, device=device)
+            img = _randn(shape, device)
         bufs = (torch.empty_like(img), torch.empty_like(img))
         for i, t in enumerate(reversed(range(0, T))):
             img = self.p_sample(img, t, cond=cond, cond_scale=cond_scale, noise=noise, _final=(t == 0),
@@ -325,9 +329,59 @@ class GaussianDiffusion(nn.Module):
         return img
 
     @torch.no_grad()
-    def ddim_sample(self, *a, **k):
-        raise NotImplementedError("DDIM sampling is only reached when sampling_timesteps < timesteps, which no "
-                                  "reference config sets (DDPM_2D.py:63)")
+    def ddim_sample(self, shape, clip_denoised=True, cond=None, cond_scale=1.0, x_start=None, start_t=0, noise=None):
+        """cond_DDPM.py:466-515, reached from sample() when sampling_timesteps < timesteps.  Kept quirks: the time grid
+        is linspace(0, total, S + 2)[:-1] truncated to ints; the schedule is read from alphas_cumprod_PREV; the first
+        gen_noise / randn draw is made and discarded; with start_t != 0 the caller's `noise` argument itself goes into
+        q_sample, so the flag value True noises x_start with the constant 1 (tensor * True); the per-step noise type
+        follows cfg.noisetype, not the argument.  Each update is ONE fused kernel (cddpm_ddim_step) whose five scalars
+        are computed here in fp32 exactly as the reference computes them."""
+        device = self.betas.device
+        batch = shape[0]
+        total = start_t if start_t > 0 else self.num_timesteps
+        times = torch.linspace(0.0, total, steps=self.sampling_timesteps + 2)[:-1]
+        times = list(reversed(times.int().tolist()))
+        pairs = list(zip(times[:-1], times[1:]))
+        eta = self.ddim_sampling_eta
+        if noise is not None:
+            gen_noise(self.cfg, shape, device=device)  # drawn and discarded (cond_DDPM.py:476-477)
+        else:
+            _randn(shape, device)
+        if start_t != 0:
+            self._check_t(start_t)
+            if noise is None:
+                nz = _randn(shape, device)
+            elif torch.is_tensor(noise):
+                nz = noise.to(device)
+            else:  # a flag: `sqrt(1 - acp) * True` in the reference
+                nz = torch.full(shape, float(noise), device=device)
+            img = self.q_sample(x_start=x_start, t=torch.tensor([start_t], device=device), noise=nz)
+        else:
+            img = _randn(shape, device)
+        acp_prev = self.alphas_cumprod_prev.detach().cpu()
+        sr, srm1 = self.sqrt_recip_alphas_cumprod.detach().cpu(), self.sqrt_recipm1_alphas_cumprod.detach().cpu()
+        hw = img[0].numel()
+        simplex = self.cfg is not None and self.cfg.get("noisetype") == "simplex"
+        bufs = (torch.empty_like(img), torch.empty_like(img))
+        for i, (time, time_next) in enumerate(pairs):
+            self._check_t(time)
+            alpha, alpha_next = acp_prev[time], acp_prev[time_next]
+            sigma = eta * ((1 - alpha / alpha_next) * (1 - alpha_next) / (1 - alpha)).sqrt()
+            c = ((1 - alpha_next) - sigma ** 2).sqrt()
+            bt = torch.full((batch,), time, device=device, dtype=torch.long)
+            model_out = self.model.forward_with_cond_scale(img, bt, cond=cond, cond_scale=cond_scale)
+            nz, f16 = None, 0
+            if time_next > 0:
+                nz, f16 = _noise_arg(gen_noise(self.cfg, shape, device=device) if simplex else _randn(shape, device))
+            out = bufs[i & 1]
+            check(lib().cddpm_ddim_step(ptr(model_out), ptr(img.contiguous()), ptr(nz), f16, ptr(out), float(sr[time]),
+                                        float(srm1[time]), float(alpha_next.sqrt()), float(c), float(sigma), batch, hw,
+                                        1 if self.objective == "pred_noise" else 0, 1 if clip_denoised else 0,
+                                        1 if i == len(pairs) - 1 else 0, current_stream()), "cddpm_ddim_step")
+            img = out
+        if not pairs:
+            img = (img + 1) * 0.5
+        return img
 
     @torch.no_grad()
     def sample(self, batch_size=1, cond=None, cond_scale=1.0, box=None, x_start=None, start_t=0, noise=None):

@@ -89,6 +89,21 @@ class _Volume:
         return self.diff.permute(1, 2, 0)
 
 
+def trilinear_resize(volume, size) -> torch.Tensor:
+    """F.interpolate(volume, size=size, mode="trilinear", align_corners=True) for a [1,1,H,W,D] (or [H,W,D]) CUDA
+    volume, read in place through its strides (the UNet output arrives as a permuted [D,1,H,W] view); returns a
+    contiguous [1,1,Ho,Wo,Do] fp32 tensor."""
+    src = _as_cuda_f32(volume)
+    view, (H, W, D), keep = _view3(src)
+    Ho, Wo, Do = (int(v) for v in size)
+    with torch.cuda.device(src.device):
+        out = torch.empty(1, 1, Ho, Wo, Do, dtype=torch.float32, device=src.device)
+        check(lib().cddpm_trilinear_resize(ctypes.byref(view), H, W, D, ptr(out), Ho, Wo, Do, current_stream()),
+              "cddpm_trilinear_resize")
+    del keep
+    return out
+
+
 def residual_and_filter(final_volume, data_orig, data_seg, data_mask, *, erode=True, median=True, kernelsize=5):
     """Steps (i)-(v) of _test_step: |orig - reco|, l1/l2 error sums, eroded-mask multiply, 3-D median.
     Returns (_Volume, sums[7] float64 numpy)."""
@@ -404,9 +419,8 @@ def _dist_max(t: torch.Tensor):
 def _test_step(self, final_volume, data_orig, data_seg, data_mask, batch_idx, ID, label_vol):
     self.healthy_sets = ["IXI"]
     cfg = self.cfg
-    if not cfg.resizedEvaluation:
-        raise NotImplementedError("full-resolution evaluation (trilinear resize to new_size) belongs to the "
-                                  "datamodule side (SURVEY.md §8 f-3); use resizedEvaluation=True")
+    if not cfg.resizedEvaluation:  # full-resolution evaluation (utils_eval.py:24-25)
+        final_volume = trilinear_resize(final_volume, self.new_size)
     vol, sums = residual_and_filter(final_volume, data_orig, data_seg, data_mask, erode=bool(cfg["erodeBrainmask"]),
                                     median=bool(cfg["medianFiltering"]), kernelsize=cfg.get("kernelsize_median", 5))
     H, W, D = vol.shape

@@ -187,11 +187,20 @@ int cddpm_posterior_step(const float* model_out, const float* x_t, const void* n
                          const float* posterior_mean_coef1, const float* posterior_mean_coef2,
                          const float* posterior_log_variance_clipped, const float* sqrt_recip_alphas_cumprod,
                          const float* sqrt_recipm1_alphas_cumprod, int64_t t, int B, int HW, int pred_noise,
-                         int final_unnormalize, void* stream) {
+                         int clip_denoised, int final_unnormalize, void* stream) {
   return launch_posterior_step(model_out, x_t, noise, noise_f16, x_prev, posterior_mean_coef1, posterior_mean_coef2,
                                posterior_log_variance_clipped, sqrt_recip_alphas_cumprod,
-                               sqrt_recipm1_alphas_cumprod, t, B, HW, pred_noise, final_unnormalize,
+                               sqrt_recipm1_alphas_cumprod, t, B, HW, pred_noise, clip_denoised, final_unnormalize,
                                static_cast<cudaStream_t>(stream));
+}
+
+int cddpm_ddim_step(const float* model_out, const float* x_t, const void* noise, int noise_f16, float* x_next,
+                    float sqrt_recip_alphas_cumprod_t, float sqrt_recipm1_alphas_cumprod_t, float sqrt_alpha_next,
+                    float c, float sigma, int B, int HW, int pred_noise, int clip_denoised, int final_unnormalize,
+                    void* stream) {
+  return launch_ddim_step(model_out, x_t, noise, noise_f16, x_next, sqrt_recip_alphas_cumprod_t,
+                          sqrt_recipm1_alphas_cumprod_t, sqrt_alpha_next, c, sigma, B, HW, pred_noise, clip_denoised,
+                          final_unnormalize, static_cast<cudaStream_t>(stream));
 }
 
 int cddpm_loss_backward(const float* model_out, const float* img, const void* noise, int noise_f16,
@@ -262,6 +271,11 @@ int cddpm_residual_erode(const cddpm_vol_view* orig, const cddpm_vol_view* reco,
   if (!orig || !reco) return fail(kInvalidArgument, "residual_erode: null view");
   return launch_residual_erode(to_view(orig), to_view(reco), to_view(seg), to_view(mask), H, W, D, iterations, erode,
                                diff_masked_dhw, sums, static_cast<cudaStream_t>(stream));
+}
+int cddpm_trilinear_resize(const cddpm_vol_view* src, int H, int W, int D, float* dst_hwd, int Ho, int Wo, int Do,
+                           void* stream) {
+  if (!src) return fail(kInvalidArgument, "trilinear_resize: null view");
+  return launch_trilinear_resize(to_view(src), H, W, D, dst_hwd, Ho, Wo, Do, static_cast<cudaStream_t>(stream));
 }
 int cddpm_median3d(const float* in_dhw, float* out_dhw, int H, int W, int D, int k, void* stream) {
   return launch_median3d(in_dhw, out_dhw, H, W, D, k, static_cast<cudaStream_t>(stream));

@@ -177,6 +177,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kTcQ;
   const int L = p.L, C = p.C, kc = p.kc, fmt = p.fmt;
+  pdl_trigger();
   const int nchunks = L / kc;
   const int row = threadIdx.x;  // query row of this thread = TMEM lane
 
@@ -210,6 +211,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
     umma_commit(&bar_s[buf]);
   };
 
+  pdl_wait();  // qkv is the predecessor's output (prologue above ran under its tail)
   if (threadIdx.x == 0) {
     mbar_arrive_expect_tx(bar_load, static_cast<uint32_t>(kTcQ * 128 + 2 * L * 128));
     tma_load_2d(q_sm, &p.tmap_q, bar_load, h * kHeadDim, b * L + q0);
@@ -350,8 +352,7 @@ int launch_attention_tc(const void* qkv, void* out, int B, int L, int C, int fmt
   CDDPM_TRY(encode_tmap_16bit(&p.tmap_q, qkv, 2, dims, strides, box_q));
   CDDPM_TRY(encode_tmap_16bit(&p.tmap_kv, qkv, 2, dims, strides, box_kv));
   dim3 grid((L + kTcQ - 1) / kTcQ, C / kHeadDim, B);
-  attention_tc_kernel<<<grid, kTcThreads, kTcSmem, stream>>>(p);
-  return check_launch("attention_tc_kernel");
+  return check_cuda(launch_k(attention_tc_kernel, grid, dim3(kTcThreads), kTcSmem, stream, p), "attention_tc_kernel");
 }
 
 }  // namespace

@@ -2,6 +2,8 @@
 
 #include <cudaTypedefs.h>
 
+#include <stdlib.h>
+
 #include <mutex>
 
 namespace cddpm {
@@ -63,6 +65,22 @@ int encode_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64
     return fail(kCudaError, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
   }
   return kOk;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CDDPM_PDL");  // A/B switch for measurements: 0 = plain stream-ordered launches
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+static thread_local bool g_pdl_next = false;
+void pdl_set_next(bool on) { g_pdl_next = on && pdl_enabled(); }
+bool pdl_take_next() {
+  const bool v = g_pdl_next;
+  g_pdl_next = false;
+  return v;
 }
 
 int device_sm_count() {

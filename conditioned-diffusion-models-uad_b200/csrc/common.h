@@ -45,6 +45,41 @@ int encode_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64
 
 int device_sm_count();
 
+// ---- Programmatic dependent launch (PDL).  A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization
+// may start while its stream predecessor is still draining: its CTAs are placed as the predecessor's CTAs retire, run
+// their prologue (barrier init, TMEM allocation, tensor-map prefetch, weight loads) and block in
+// `griddepcontrol.wait` until the predecessor has completed and flushed.  The engines set the thread-local flag in
+// front of an op whose stream predecessor is a kernel; launch_k consumes it.  ONLY kernels that execute pdl_wait()
+// before their first dependent access may be launched through launch_k.  CDDPM_PDL=0 disables the attribute.
+bool pdl_enabled();
+void pdl_set_next(bool on);
+bool pdl_take_next();
+
+template <typename... P, typename... A>
+inline cudaError_t launch_k(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  int n = 0;
+  if (pdl_take_next()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+}
+
+#ifdef __CUDACC__
+// Device side of PDL: no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 // Parameter re-layout jobs.  While a recorder is installed (thread-local), the small re-layout launches behind
 // cddpm_unet_set_param (weight packing, plain copies, bias sums) append a job here instead of launching, so that a
 // whole-model push becomes two launches of one table-driven kernel (param_push.cu).

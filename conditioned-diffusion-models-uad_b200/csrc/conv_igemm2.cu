@@ -90,6 +90,7 @@ struct Conv2Params {
   const float* gn_film;
   int gn_film_stride, gn_film_off;
   unsigned long long* gn_counters;
+  int a_evict_first;  // L2 hint for the activation tiles (CDDPM_L2_HINTS)
 };
 
 __device__ __forceinline__ uint32_t pack16(float a, float b, int fmt) {
@@ -198,6 +199,10 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_igemm2_kernel(const __grid_
   const int work_stride = gridDim.x / 2;
   const int tiles_per_img = p.tiles_w * p.tiles_h;
 
+  // Programmatic dependent launch: let the next kernel's CTAs be scheduled as ours retire; everything up to the first
+  // read of the predecessor's output (barrier init, TMEM allocation, descriptor prefetch, the weight ring) runs under
+  // the predecessor's tail.  The waits sit in the halo-tile producer and in the epilogue warps.
+  pdl_trigger();
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.num_src; ++s) tma_prefetch_desc(&p.tmap_a[s]);
     tma_prefetch_desc(&p.tmap_b);
@@ -265,6 +270,9 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_igemm2_kernel(const __grid_
     if (lane == 0) {
       int sa = 0;
       uint32_t pa = 0;
+      pdl_wait();  // the activations are the predecessor's output
+      const uint64_t pol = l2_policy_evict_first();
+      const bool hint = p.a_evict_first != 0;
       for (int work = work_first; work < num_work; work += work_stride) {
         const int m_tile = 2 * (work / p.num_n_tiles) + static_cast<int>(cta_rank);
         // an odd trailing tile has no partner: its coordinates fall outside the batch and TMA fills zeros
@@ -280,8 +288,13 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_igemm2_kernel(const __grid_
             } else {
               mbar_arrive_cluster(&full_a[sa], 0);
             }
-            tma_load_4d_pair(a_ring + sa * kASlotBytes, &p.tmap_a[s], &full_a[sa], ch * kConvBlockK, tx * kTileW - 1,
-                             ty * kTileH - 1, n);
+            if (hint) {
+              tma_load_4d_pair_hint(a_ring + sa * kASlotBytes, &p.tmap_a[s], &full_a[sa], ch * kConvBlockK,
+                                    tx * kTileW - 1, ty * kTileH - 1, n, pol);
+            } else {
+              tma_load_4d_pair(a_ring + sa * kASlotBytes, &p.tmap_a[s], &full_a[sa], ch * kConvBlockK, tx * kTileW - 1,
+                               ty * kTileH - 1, n);
+            }
             if (++sa == kStagesA) {
               sa = 0;
               pa ^= 1;
@@ -379,6 +392,7 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_igemm2_kernel(const __grid_
     const int nb4 = p.Cout >> 2;
     const int epi_tid = threadIdx.x - 128;
     int iter = 0;
+    pdl_wait();  // residual reads, statistics atomics and the output stores are ordered after the predecessor
     for (int work = work_first; work < num_work; work += work_stride, ++iter) {
       const int acc = iter & 1;
       const uint32_t acc_phase = (iter >> 1) & 1;
@@ -691,6 +705,15 @@ int build_conv2(const ConvDesc& d, std::shared_ptr<void>* holder) {
   p.residual = reinterpret_cast<const uint16_t*>(d.residual);
   p.out = reinterpret_cast<uint16_t*>(d.out);
   p.gn_stats = d.gn_stats;
+  {
+    // The activation operand is read once per forward (concurrently by the N tiles and the halo neighbours): marking
+    // its L2 lines evict-first leaves the cache to the OUTPUT, which the following GroupNorm pass reads back to front.
+    static const int hints = [] {
+      const char* e = getenv("CDDPM_L2_HINTS");
+      return (e != nullptr && e[0] == '0') ? 0 : 1;
+    }();
+    p.a_evict_first = hints;
+  }
   if (d.gn_gamma != nullptr) {
     if (d.gn_stats == nullptr || d.gn_counters == nullptr || d.gn_beta == nullptr || d.residual != nullptr || d.relu != 0 ||
         d.Cout % 128 != 0 || (d.Cout / 32) % 4 != 0)
@@ -755,13 +778,18 @@ int launch_conv2(const std::shared_ptr<void>& holder, cudaStream_t stream) {
   cfg.blockDim = dim3(kThreads2);
   cfg.dynamicSmemBytes = L->p.mt == 2 ? Geo<2>::kSmemBytes : Geo<1>::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (pdl_take_next()) {
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
   const bool fuse = L->p.gn_gamma != nullptr;
   if (L->p.mt == 2) {
     if (fuse) {

@@ -38,7 +38,8 @@ __global__ void __launch_bounds__(256) posterior_step_kernel(
     const float* __restrict__ model_out, const float* __restrict__ x_t, const void* __restrict__ noise, int noise_f16,
     float* __restrict__ x_prev, const float* __restrict__ coef1, const float* __restrict__ coef2,
     const float* __restrict__ logvar, const float* __restrict__ sqrt_recip_ac,
-    const float* __restrict__ sqrt_recipm1_ac, int64_t t, int HW, int pred_noise, int final_unnormalize) {
+    const float* __restrict__ sqrt_recipm1_ac, int64_t t, int HW, int pred_noise, int clip_denoised,
+    int final_unnormalize) {
   const int b = blockIdx.y;
   const float c1 = coef1[t], c2 = coef2[t];
   const float sigma = (t > 0 && noise != nullptr) ? expf(0.5f * logvar[t]) : 0.f;
@@ -48,11 +49,43 @@ __global__ void __launch_bounds__(256) posterior_step_kernel(
     const float xt = x_t[base + i];
     float x0 = model_out[base + i];
     if (pred_noise) x0 = __fsub_rn(__fmul_rn(sr, xt), __fmul_rn(srm1, x0));
-    x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+    if (clip_denoised) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
     float v = __fadd_rn(__fmul_rn(c1, x0), __fmul_rn(c2, xt));
     if (sigma != 0.f) v = __fadd_rn(v, __fmul_rn(sigma, load_noise(noise, noise_f16, base + i)));
     if (final_unnormalize) v = (v + 1.0f) * 0.5f;
     x_prev[base + i] = v;
+  }
+}
+
+// One DDIM update (cond_DDPM.py:487-511).  The step's scalars are computed by the host in fp32 exactly as the reference
+// computes them from its 0-dim tensors; the association below is the reference's: model_predictions (:400-420, no
+// clipping inside), x_start.clamp_ (:495-496, AFTER pred_noise was derived from the unclamped prediction), then
+// ((x_start * sqrt(alpha_next)) + (c * pred_noise)) + (sigma * noise).
+__global__ void __launch_bounds__(256) ddim_step_kernel(const float* __restrict__ model_out,
+                                                        const float* __restrict__ x_t, const void* __restrict__ noise,
+                                                        int noise_f16, float* __restrict__ x_next, float sqrt_recip,
+                                                        float sqrt_recipm1, float sqrt_alpha_next, float c, float sigma,
+                                                        int HW, int pred_noise, int clip_denoised,
+                                                        int final_unnormalize) {
+  const int b = blockIdx.y;
+  const size_t base = static_cast<size_t>(b) * HW;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+    const float xt = x_t[base + i];
+    const float o = model_out[base + i];
+    float x0, pn;
+    if (pred_noise) {
+      pn = o;
+      x0 = __fsub_rn(__fmul_rn(sqrt_recip, xt), __fmul_rn(sqrt_recipm1, o));
+    } else {
+      pn = __fdiv_rn(__fsub_rn(__fmul_rn(sqrt_recip, xt), o), sqrt_recipm1);
+      x0 = o;
+    }
+    if (clip_denoised) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+    float v = __fadd_rn(__fmul_rn(x0, sqrt_alpha_next), __fmul_rn(c, pn));
+    // the reference adds sigma * noise even when noise is the Python float 0. (a zero tensor): v + 0 == v
+    if (noise != nullptr) v = __fadd_rn(v, __fmul_rn(sigma, load_noise(noise, noise_f16, base + i)));
+    if (final_unnormalize) v = (v + 1.0f) * 0.5f;
+    x_next[base + i] = v;
   }
 }
 
@@ -134,7 +167,7 @@ int launch_q_sample(const float* img, const void* noise, int noise_f16, float* o
 
 int launch_posterior_step(const float* model_out, const float* x_t, const void* noise, int noise_f16, float* x_prev,
                           const float* coef1, const float* coef2, const float* logvar, const float* sqrt_recip_ac,
-                          const float* sqrt_recipm1_ac, int64_t t, int B, int HW, int pred_noise,
+                          const float* sqrt_recipm1_ac, int64_t t, int B, int HW, int pred_noise, int clip_denoised,
                           int final_unnormalize, cudaStream_t stream) {
   if (!model_out || !x_t || !x_prev || !coef1 || !coef2 || !logvar)
     return fail(kInvalidArgument, "posterior_step: null pointer");
@@ -142,8 +175,20 @@ int launch_posterior_step(const float* model_out, const float* x_t, const void* 
     return fail(kInvalidArgument, "posterior_step: pred_noise needs sqrt_recip(m1)_alphas_cumprod");
   dim3 grid((HW + 1023) / 1024, B);
   posterior_step_kernel<<<grid, 256, 0, stream>>>(model_out, x_t, noise, noise_f16, x_prev, coef1, coef2, logvar,
-                                                  sqrt_recip_ac, sqrt_recipm1_ac, t, HW, pred_noise, final_unnormalize);
+                                                  sqrt_recip_ac, sqrt_recipm1_ac, t, HW, pred_noise, clip_denoised,
+                                                  final_unnormalize);
   return check_launch("posterior_step_kernel");
+}
+
+int launch_ddim_step(const float* model_out, const float* x_t, const void* noise, int noise_f16, float* x_next,
+                     float sqrt_recip, float sqrt_recipm1, float sqrt_alpha_next, float c, float sigma, int B, int HW,
+                     int pred_noise, int clip_denoised, int final_unnormalize, cudaStream_t stream) {
+  if (!model_out || !x_t || !x_next) return fail(kInvalidArgument, "ddim_step: null pointer");
+  if (B < 1 || HW < 1) return fail(kInvalidArgument, "ddim_step: empty batch");
+  dim3 grid((HW + 1023) / 1024, B);
+  ddim_step_kernel<<<grid, 256, 0, stream>>>(model_out, x_t, noise, noise_f16, x_next, sqrt_recip, sqrt_recipm1,
+                                             sqrt_alpha_next, c, sigma, HW, pred_noise, clip_denoised, final_unnormalize);
+  return check_launch("ddim_step_kernel");
 }
 
 int launch_recon_finish(const float* model_out, const float* img, const float* x_t, const void* noise, int noise_f16,

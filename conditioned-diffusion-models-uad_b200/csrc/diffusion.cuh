@@ -10,12 +10,18 @@ int launch_q_sample(const float* img, const void* noise, int noise_f16, float* o
                     cudaStream_t stream);
 
 // x_{t-1} = coef1[t]*clamp(x0_hat,-1,1) + coef2[t]*x_t + (t>0 ? exp(logvar[t]/2)*noise : 0); noise may be NULL.
+// clip_denoised == 0 skips the clamp (p_mean_variance, cond_DDPM.py:422-430).
 // x0_hat = model_out (pred_x0) or sqrt_recip_ac[t]*x_t - sqrt_recipm1_ac[t]*model_out (pred_noise).
 // final_unnormalize additionally maps the result through (v+1)/2 (last step of p_sample_loop).
 int launch_posterior_step(const float* model_out, const float* x_t, const void* noise, int noise_f16, float* x_prev,
                           const float* coef1, const float* coef2, const float* logvar, const float* sqrt_recip_ac,
-                          const float* sqrt_recipm1_ac, int64_t t, int B, int HW, int pred_noise,
+                          const float* sqrt_recipm1_ac, int64_t t, int B, int HW, int pred_noise, int clip_denoised,
                           int final_unnormalize, cudaStream_t stream);
+
+// One DDIM update (cond_DDPM.py:487-511) with host-computed step scalars; noise may be NULL (time_next == 0).
+int launch_ddim_step(const float* model_out, const float* x_t, const void* noise, int noise_f16, float* x_next,
+                     float sqrt_recip, float sqrt_recipm1, float sqrt_alpha_next, float c, float sigma, int B, int HW,
+                     int pred_noise, int clip_denoised, int final_unnormalize, cudaStream_t stream);
 
 // reco = reco*beta + alpha * ((model_out+1)/2  |  (x_t - sqrt_1mac[t]*model_out + 1)/2);
 // loss[b] = mean_i |model_out - target| (or squared) * p2w[t_b], target = 2*img-1 | noise.

@@ -118,6 +118,8 @@ struct GnApplyDev {
   int film_stride, film_off, silu, mode, fmt;
   uint16_t* out;
   uint16_t* raw_out;
+  int reverse;  // walk images and pixel chunks back to front (see launch_gn_apply)
+  int stream_loads;  // read x with the evict-first (ld.global.cs) policy
 };
 
 // (sum, sum of squares) per image and 4-channel bucket of an NHWC tensor, accumulated into stats[B][C/4][2] (double
@@ -162,8 +164,53 @@ __global__ void __launch_bounds__(256, kMode == 0 ? 4 : 3) gn_apply_kernel(const
   float* sB = sh + C;
   float* sMean = sh + 2 * C;
   float* sRstd = sMean + kGnGroups;
-  const int b = blockIdx.y;
+  const int b = a.reverse ? static_cast<int>(gridDim.y - 1 - blockIdx.y) : static_cast<int>(blockIdx.y);
+  const int chunk = a.reverse ? static_cast<int>(gridDim.x - 1 - blockIdx.x) : static_cast<int>(blockIdx.x);
   const int cpg = C / kGnGroups;
+  pdl_trigger();
+  pdl_wait();  // the statistics and x come from the preceding convolution
+
+  // ---- pixel / channel assignment, and the FIRST batch of loads before the coefficient prologue: the prologue is two
+  // dependent L2 round trips + a block barrier each (~1 us), as long as the whole data phase of a 64-pixel block
+  const int nvec = C >> 3;
+  const int lanes = blockDim.x / nvec;
+  const int v = threadIdx.x % nvec;
+  const int pl = threadIdx.x / nvec;
+  const bool worker = pl < lanes;
+  const int cb = v << 3;
+  const uint16_t* src;
+  int cs, cbs;
+  if (cb < a.c0) {
+    src = a.p0; cs = a.c0; cbs = cb;
+  } else {
+    src = a.p1; cs = a.c1; cbs = cb - a.c0;
+  }
+  const size_t in_base = static_cast<size_t>(b) * a.H * a.W;
+  const size_t out_base = static_cast<size_t>(b) * a.Ho * a.Wo;
+  const int HWo = a.Ho * a.Wo;
+  const int p_end = min((chunk + 1) * a.Pout, HWo);
+  constexpr int kU = 4;  // four pixels per thread and batch: four 16-byte requests in flight
+  uint4 u[kU];
+  auto issue = [&](int op0) {
+#pragma unroll
+    for (int k = 0; k < kU; ++k) {
+      const int opk = op0 + k * lanes;
+      if (opk < p_end) {
+        if (kPlain) {
+          const uint4* lp = reinterpret_cast<const uint4*>(src + (in_base + opk) * cs + cbs);
+          u[k] = a.stream_loads ? __ldcs(lp) : __ldg(lp);
+        } else {
+          const int oyk = opk / a.Wo, oxk = opk - oyk * a.Wo;
+          const int iy = (a.mode == kResampleUp2) ? (oyk >> 1) : oyk;
+          const int ix = (a.mode == kResampleUp2) ? (oxk >> 1) : oxk;
+          u[k] = __ldg(reinterpret_cast<const uint4*>(src + (in_base + static_cast<size_t>(iy) * a.W + ix) * cs + cbs));
+        }
+      }
+    }
+  };
+  int op = chunk * a.Pout + pl;
+  if (kMode != 2 && worker) issue(op);
+
   if (threadIdx.x < kGnGroups) {
     double s = 0.0, q = 0.0;
     if (a.stats0 != nullptr) {
@@ -206,76 +253,20 @@ __global__ void __launch_bounds__(256, kMode == 0 ? 4 : 3) gn_apply_kernel(const
   }
   __syncthreads();
 
-  const int nvec = C >> 3;
-  const int lanes = blockDim.x / nvec;
-  const int v = threadIdx.x % nvec;
-  const int pl = threadIdx.x / nvec;
-  if (pl >= lanes) return;
-  const int cb = v << 3;
-  const uint16_t* src;
-  int cs, cbs;
-  if (cb < a.c0) {
-    src = a.p0; cs = a.c0; cbs = cb;
-  } else {
-    src = a.p1; cs = a.c1; cbs = cb - a.c0;
-  }
+  if (!worker) return;
   float A[8], Bc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     A[j] = sA[cb + j];
     Bc[j] = sB[cb + j];
   }
-  const size_t in_base = static_cast<size_t>(b) * a.H * a.W;
-  const size_t out_base = static_cast<size_t>(b) * a.Ho * a.Wo;
-  const int HWo = a.Ho * a.Wo;
-  const int p_end = min((static_cast<int>(blockIdx.x) + 1) * a.Pout, HWo);
-  for (int op = blockIdx.x * a.Pout + pl; op < p_end; op += lanes) {
-    const int oy = op / a.Wo, ox = op - oy * a.Wo;
-    float y[8], r[8];
-    if (kMode == 2) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) y[j] = r[j] = 0.f;
-#pragma unroll
-      for (int d = 0; d < 4; ++d) {
-        const int iy = 2 * oy + (d >> 1), ix = 2 * ox + (d & 1);
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + (in_base + static_cast<size_t>(iy) * a.W + ix) * cs + cbs));
-        float f[8];
-        unpack8(u, a.fmt, f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float t = fmaf(f[j], A[j], Bc[j]);
-          if (a.silu) t = silu_f(t);
-          y[j] += t;
-          r[j] += f[j];
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        y[j] *= 0.25f;
-        r[j] *= 0.25f;
-      }
-    } else {
-      // batch four pixels per thread: all loads first, so four 16-byte requests are in flight per thread
-      constexpr int kU = 4;
-      uint4 u[kU];
+  if (kMode != 2) {
+    for (;;) {
 #pragma unroll
       for (int k = 0; k < kU; ++k) {
         const int opk = op + k * lanes;
         if (opk < p_end) {
-          if (kPlain) {
-            u[k] = __ldg(reinterpret_cast<const uint4*>(src + (in_base + opk) * cs + cbs));
-          } else {
-            const int oyk = opk / a.Wo, oxk = opk - oyk * a.Wo;
-            const int iy = (a.mode == kResampleUp2) ? (oyk >> 1) : oyk;
-            const int ix = (a.mode == kResampleUp2) ? (oxk >> 1) : oxk;
-            u[k] = __ldg(reinterpret_cast<const uint4*>(src + (in_base + static_cast<size_t>(iy) * a.W + ix) * cs + cbs));
-          }
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < kU; ++k) {
-        const int opk = op + k * lanes;
-        if (opk < p_end) {
+          float y[8], r[8];
           unpack8(u[k], a.fmt, r);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -288,8 +279,40 @@ __global__ void __launch_bounds__(256, kMode == 0 ? 4 : 3) gn_apply_kernel(const
             *reinterpret_cast<uint4*>(a.raw_out + (out_base + opk) * C + cb) = pack8(r, a.fmt);
         }
       }
-      op += (kU - 1) * lanes;
-      continue;
+      op += kU * lanes;
+      if (op >= p_end) break;
+      issue(op);
+    }
+    return;
+  }
+  // 2x2 average pooling of the activated tensor (and of the raw input): all four source pixels of an output pixel first
+  for (; op < p_end; op += lanes) {
+    const int oy = op / a.Wo, ox = op - oy * a.Wo;
+    uint4 q[4];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      const int iy = 2 * oy + (d >> 1), ix = 2 * ox + (d & 1);
+      q[d] = __ldg(reinterpret_cast<const uint4*>(src + (in_base + static_cast<size_t>(iy) * a.W + ix) * cs + cbs));
+    }
+    float y[8], r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) y[j] = r[j] = 0.f;
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      float f[8];
+      unpack8(q[d], a.fmt, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float t = fmaf(f[j], A[j], Bc[j]);
+        if (a.silu) t = silu_f(t);
+        y[j] += t;
+        r[j] += f[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      y[j] *= 0.25f;
+      r[j] *= 0.25f;
     }
     *reinterpret_cast<uint4*>(a.out + (out_base + op) * C + cb) = pack8(y, a.fmt);
     if (a.raw_out != nullptr) *reinterpret_cast<uint4*>(a.raw_out + (out_base + op) * C + cb) = pack8(r, a.fmt);
@@ -520,6 +543,7 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
   __shared__ float red[8][32][2 * NB];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.y, HW = H * W;
+  pdl_trigger();
   float wr[9][NPER], br[NPER];
 #pragma unroll
   for (int j = 0; j < NPER; ++j) {
@@ -530,6 +554,7 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
   float sum[NB], sq[NB];
 #pragma unroll
   for (int k = 0; k < NB; ++k) sum[k] = sq[k] = 0.f;
+  pdl_wait();
   const float* xb = x + static_cast<size_t>(b) * HW;
   const int p0 = (blockIdx.x * 8 + warp) * 32;
   int yh = p0 / W, xw = p0 - yh * W;
@@ -613,17 +638,117 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
   }
 }
 
+// Stem, second generation (the kernel above needed 67 us for 75 MB of output: every lane wrote 8 bytes per pixel and the
+// window loads were serialised behind each other).  A block owns 256 consecutive pixels of one image; thread =
+// (pixel lane, group of 8 output channels): its 72 weights + 8 biases stay in registers, the few input rows the block
+// touches are staged once in shared memory (zero-padded columns and rows), and every pixel costs 9 broadcast shared
+// loads, 72 FMAs and ONE 16-byte store - a warp writes whole 256-byte pixel rows.  Same accumulation order as the
+// first kernel (bias, then taps row-major), same statistics of the ROUNDED values: results are bit-identical.
+template <int CG>  // channel groups of 8: C = 8 * CG
+__global__ void __launch_bounds__(256, 2) conv_in2_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, uint16_t* __restrict__ out,
+                                                          double* __restrict__ stats, int H, int W, int fmt) {
+  constexpr int C = 8 * CG;
+  constexpr int kLanes = 256 / CG;   // pixels in flight per block
+  constexpr int kPix = 256;          // pixels per block
+  extern __shared__ float rows[];    // [nrows + 2][W + 2], zero border
+  __shared__ float red[8][CG][4];
+  const int b = blockIdx.y, HW = H * W;
+  const int cg = threadIdx.x % CG, pl = threadIdx.x / CG;
+  const int p_first = blockIdx.x * kPix;
+  const int p_last = min(p_first + kPix, HW) - 1;
+  const int y_first = p_first / W, y_last = p_last / W;
+  const int nrows = y_last - y_first + 3;  // rows y_first-1 .. y_last+1
+  const int pitch = W + 2;
+  pdl_trigger();
+  float wr[9][8], br[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    br[j] = __ldg(bias + cg * 8 + j);
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) wr[tap][j] = __ldg(w + (cg * 8 + j) * 9 + tap);
+  }
+  pdl_wait();
+  const float* xb = x + static_cast<size_t>(b) * HW;
+  for (int i = threadIdx.x; i < nrows * pitch; i += blockDim.x) {
+    const int r = i / pitch, cx = i - r * pitch;
+    const int iy = y_first - 1 + r, ix = cx - 1;
+    rows[i] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(xb + iy * W + ix) : 0.f;
+  }
+  __syncthreads();
+  float sum[2] = {0.f, 0.f}, sq[2] = {0.f, 0.f};
+  for (int p = p_first + pl; p <= p_last; p += kLanes) {
+    const int y = p / W, xx = p - y * W;
+    const float* rp = rows + (y - y_first) * pitch + xx;  // window origin (y-1, x-1) in the padded rows
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = br[c];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const float v = rp[r * pitch + d];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] = fmaf(v, wr[r * 3 + d][c], acc[c]);
+      }
+    uint32_t pk[4];
+#pragma unroll
+    for (int c = 0; c < 8; c += 2) {
+      pk[c / 2] = pack2(acc[c], acc[c + 1], fmt);
+      float2 rr;
+      if (fmt == 1) {
+        rr = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk[c / 2]));
+      } else {
+        rr = __half22float2(*reinterpret_cast<const __half2*>(&pk[c / 2]));
+      }
+      sum[c / 4] += rr.x + rr.y;
+      sq[c / 4] = fmaf(rr.x, rr.x, fmaf(rr.y, rr.y, sq[c / 4]));
+    }
+    *reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * HW + p) * C + cg * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+  if (stats == nullptr) return;
+  // lanes of a warp that share a channel group differ in the bits above log2(CG)
+  float v4[4] = {sum[0], sq[0], sum[1], sq[1]};
+#pragma unroll
+  for (int m = CG; m < 32; m <<= 1)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v4[k] += __shfl_xor_sync(0xffffffffu, v4[k], m);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane < CG || CG >= 32) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) red[warp][lane % CG][k] = v4[k];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < CG * 4; i += blockDim.x) {
+    const int g = i >> 2, k = i & 3;
+    float t = 0.f;
+#pragma unroll
+    for (int wq = 0; wq < 8; ++wq) t += red[wq][g][k];
+    // k: 0 sum / 1 sumsq of bucket 2g, 2 sum / 3 sumsq of bucket 2g + 1
+    atomicAdd(&stats[(static_cast<size_t>(b) * (C / 4) + g * 2 + (k >> 1)) * 2 + (k & 1)], static_cast<double>(t));
+  }
+}
+
 // Head C -> 1.  A block owns a 32 x 8 pixel tile: it first stages the 34 x 10 halo of pixel rows in shared memory
 // with 16-byte cp.async copies (21 in flight per thread - the kernel was latency-bound when every warp fetched its own
 // window from global memory, 171 us for 75 MB), then warp r slides the 3x3 window along tile row r out of shared
 // memory: one partial sum per pixel and lane (its NPER channels x 9 taps), and a 31-shuffle butterfly over the run
 // leaves lane l with the total of pixel l.
 constexpr int kHeadTW = 32, kHeadTH = 8;
-template <int NPER>
+// kNorm: the head's GroupNorm + SiLU (out.0 / out.1, OpenAI_Unet.py:790-797) applied to the staged tile in shared memory
+// - the separate gn_apply pass over the last 75 MB tensor of the forward (read + write) disappears.  Coefficients and
+// rounding are those of gn_apply_kernel (fp64 finalize of the producer's 4-channel buckets, one rounding to the 16-bit
+// activation type), so the result is bit-identical to the two-pass path.  Pixels outside the image stay zero: the
+// convolution pads the NORMALISED tensor.
+template <int NPER, bool kNorm = false>
 __global__ void __launch_bounds__(256, 2) conv_out_kernel(const uint16_t* __restrict__ x, const float* __restrict__ w,
                                                        const float* __restrict__ bias, float* __restrict__ out,
-                                                       int H, int W, int tiles_w, int fmt) {
+                                                       int H, int W, int tiles_w, int fmt,
+                                                       const double* __restrict__ stats = nullptr,
+                                                       const float* __restrict__ gamma = nullptr,
+                                                       const float* __restrict__ beta = nullptr) {
   constexpr int C = 32 * NPER;
+  __shared__ float sA[kNorm ? C : 1], sB[kNorm ? C : 1], sMean[kGnGroups], sRstd[kGnGroups];
   constexpr int kRow = 2 * C;                    // bytes per pixel
   constexpr int kHW = kHeadTW + 2, kHH = kHeadTH + 2;
   constexpr int kChunks = kRow / 16;             // 16-byte chunks per pixel
@@ -634,6 +759,8 @@ __global__ void __launch_bounds__(256, 2) conv_out_kernel(const uint16_t* __rest
   const int x0 = tx * kHeadTW, y0 = ty * kHeadTH;
   const uint16_t* xb = x + static_cast<size_t>(b) * H * W * C;
   const uint32_t tile_s = static_cast<uint32_t>(__cvta_generic_to_shared(tile));
+  pdl_trigger();
+  pdl_wait();
   for (int i = threadIdx.x; i < kHH * kHW * kChunks; i += blockDim.x) {
     const int px = i / kChunks, ch = i - px * kChunks;
     const int hy = px / kHW, hx = px - hy * kHW;
@@ -651,8 +778,48 @@ __global__ void __launch_bounds__(256, 2) conv_out_kernel(const uint16_t* __rest
   for (int j = 0; j < NPER; ++j)
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) wr[tap][j] = __ldg(w + (lane * NPER + j) * 9 + tap);
+  if (kNorm) {  // coefficients while the tile copies are in flight
+    constexpr int cpg = C / kGnGroups;
+    if (threadIdx.x < kGnGroups) {
+      double s = 0.0, q = 0.0;
+      for (int j = threadIdx.x * (cpg >> 2); j < (threadIdx.x + 1) * (cpg >> 2); ++j) {
+        const double* sp = stats + (static_cast<size_t>(b) * (C >> 2) + j) * 2;
+        s += sp[0];
+        q += sp[1];
+      }
+      const double n = static_cast<double>(H) * W * cpg;
+      const double mean = s / n;
+      double var = q / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      sMean[threadIdx.x] = static_cast<float>(mean);
+      sRstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + 1e-5));
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const int g = c / cpg;
+      const float A = sRstd[g] * gamma[c];
+      sA[c] = A;
+      sB[c] = beta[c] - sMean[g] * A;
+    }
+  }
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
+  if (kNorm) {
+    for (int i = threadIdx.x; i < kHH * kHW * kChunks; i += blockDim.x) {
+      const int px = i / kChunks, ch = i - px * kChunks;
+      const int hy = px / kHW, hx = px - hy * kHW;
+      const int iy = y0 + hy - 1, ix = x0 + hx - 1;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+        uint4* tp = reinterpret_cast<uint4*>(tile + px * kRow + ch * 16);
+        float f[8], y[8];
+        unpack8(*tp, fmt, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = silu_f(fmaf(f[j], sA[ch * 8 + j], sB[ch * 8 + j]));
+        *tp = pack8(y, fmt);
+      }
+    }
+    __syncthreads();
+  }
 
   // warp `warp` = tile row; window column slot of halo column hx is hx % 3
   float win[3][3][NPER];
@@ -805,22 +972,50 @@ int launch_gn_apply(const GnApplyArgs& a, cudaStream_t stream) {
   d.fmt = a.fmt;
   d.out = reinterpret_cast<uint16_t*>(a.out);
   d.raw_out = reinterpret_cast<uint16_t*>(a.raw_out);
+  // Back-to-front traversal: the producing convolution wrote image B-1 last, so at B=32 (75-151 MB per tensor against
+  // 126 MB of L2) its tail is what is still cached; reading it first, and thereby writing image 0 LAST - the image the
+  // consuming convolution reads first - turns part of both HBM passes into L2 hits.  CDDPM_GN_REVERSE=0/1.
+  static const int reverse = [] {
+    const char* e = getenv("CDDPM_GN_REVERSE");
+    return (e != nullptr && e[0] == '0') ? 0 : 1;
+  }();
+  d.reverse = reverse;
+  static const int hints = [] {
+    const char* e = getenv("CDDPM_L2_HINTS");
+    return (e != nullptr && e[0] == '0') ? 0 : 1;
+  }();
+  d.stream_loads = hints;
   const int C = a.x.C();
   const int HWo = d.Ho * d.Wo;
-  // 256 output pixels per block when that already fills the GPU (4 x 148 blocks), else 64 (small images / batches)
-  d.Pout = (static_cast<long long>(HWo / 256) * a.B >= 592) ? 256 : 64;
+  // Output pixels per block: the largest of 256 .. 16 that still gives two full waves of 4 x 148 resident blocks.  (The
+  // 24 x 24 level at B = 32 ran as 288 blocks of 64 pixels - half the block slots empty, 8.7 us for a 9 MB tensor.)
+  d.Pout = 16;
+  for (int pout = 256; pout >= 16; pout >>= 1) {
+    if (static_cast<long long>((HWo + pout - 1) / pout) * a.B >= 1100) {  // ~2 waves; B=32 at 96x96 keeps 256
+      d.Pout = pout;
+      break;
+    }
+  }
+  {
+    static const int legacy = [] {
+      const char* e = getenv("CDDPM_GN_POUT_LEGACY");  // A/B switch: 1 = the round-1 rule (256 or 64)
+      return (e != nullptr && e[0] == '1') ? 1 : 0;
+    }();
+    if (legacy) d.Pout = (static_cast<long long>(HWo / 256) * a.B >= 592) ? 256 : 64;
+  }
   const int nvec = C / 8;
   const int threads = (256 / nvec) * nvec;
   dim3 grid((HWo + d.Pout - 1) / d.Pout, a.B);
   const size_t shmem = (2 * C + 2 * kGnGroups) * sizeof(float);
+  cudaError_t e;
   if (a.mode == kResampleNone && a.raw_out == nullptr) {
-    gn_apply_kernel<0><<<grid, threads, shmem, stream>>>(d);
+    e = launch_k(gn_apply_kernel<0>, grid, dim3(threads), shmem, stream, d);
   } else if (a.mode == kResampleDown2) {
-    gn_apply_kernel<2><<<grid, threads, shmem, stream>>>(d);
+    e = launch_k(gn_apply_kernel<2>, grid, dim3(threads), shmem, stream, d);
   } else {
-    gn_apply_kernel<1><<<grid, threads, shmem, stream>>>(d);
+    e = launch_k(gn_apply_kernel<1>, grid, dim3(threads), shmem, stream, d);
   }
-  return check_launch("gn_apply_kernel");
+  return check_cuda(e, "gn_apply_kernel");
 }
 
 int launch_linear_ex(const float* in, int in_stride, const float* W, const float* bias, float* out, int out_stride,
@@ -883,13 +1078,49 @@ int launch_conv_in(const float* x, const float* w, const float* bias, void* out,
                    int Cout, int fmt, cudaStream_t stream) {
   dim3 grid((H * W + 255) / 256, B);
   uint16_t* o = reinterpret_cast<uint16_t*>(out);
+  static const bool v2 = [] {
+    const char* e = getenv("CDDPM_STEM_V2");  // A/B switch: 0 = first-generation stem kernel
+    return !(e != nullptr && e[0] == '0');
+  }();
+  if (v2 && W >= 8) {
+    // rows touched by 256 consecutive pixels: at most 256 / W + 2, plus the two halo rows
+    const int max_rows = 256 / W + 2 + 2;
+    const size_t smem = static_cast<size_t>(max_rows) * (W + 2) * sizeof(float);
+    if (smem <= 40 * 1024) {
+      switch (Cout) {
+        case 64: return check_cuda(launch_k(conv_in2_kernel<8>, grid, dim3(256), smem, stream, x, w, bias, o, stats, H, W, fmt), "conv_in2_kernel");
+        case 128: return check_cuda(launch_k(conv_in2_kernel<16>, grid, dim3(256), smem, stream, x, w, bias, o, stats, H, W, fmt), "conv_in2_kernel");
+        case 256: return check_cuda(launch_k(conv_in2_kernel<32>, grid, dim3(256), smem, stream, x, w, bias, o, stats, H, W, fmt), "conv_in2_kernel");
+        default: return fail(kUnsupported, "conv_in: model_channels must be 64, 128 or 256");
+      }
+    }
+  }
   switch (Cout) {
-    case 64: conv_in_kernel<2><<<grid, 256, 0, stream>>>(x, w, bias, o, stats, H, W, fmt); break;
-    case 128: conv_in_kernel<4><<<grid, 256, 0, stream>>>(x, w, bias, o, stats, H, W, fmt); break;
-    case 256: conv_in_kernel<8><<<grid, 256, 0, stream>>>(x, w, bias, o, stats, H, W, fmt); break;
+    case 64: return check_cuda(launch_k(conv_in_kernel<2>, grid, dim3(256), 0, stream, x, w, bias, o, stats, H, W, fmt), "conv_in_kernel");
+    case 128: return check_cuda(launch_k(conv_in_kernel<4>, grid, dim3(256), 0, stream, x, w, bias, o, stats, H, W, fmt), "conv_in_kernel");
+    case 256: return check_cuda(launch_k(conv_in_kernel<8>, grid, dim3(256), 0, stream, x, w, bias, o, stats, H, W, fmt), "conv_in_kernel");
     default: return fail(kUnsupported, "conv_in: model_channels must be 64, 128 or 256");
   }
-  return check_launch("conv_in_kernel");
+}
+
+int launch_conv_out_gn(const void* x, const double* stats, const float* gamma, const float* beta, const float* w,
+                       const float* bias, float* out, int B, int H, int W, int C, int fmt, cudaStream_t stream) {
+  if (!x || !stats || !gamma || !beta || !w || !bias || !out) return fail(kInvalidArgument, "conv_out_gn: null pointer");
+  const int tiles_w = (W + kHeadTW - 1) / kHeadTW, tiles_h = (H + kHeadTH - 1) / kHeadTH;
+  dim3 grid(tiles_w * tiles_h, B);
+  const int smem = (kHeadTW + 2) * (kHeadTH + 2) * 2 * C;
+  const uint16_t* xi = reinterpret_cast<const uint16_t*>(x);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CDDPM_CUDA(cudaFuncSetAttribute(conv_out_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 340 * 256));
+    CDDPM_CUDA(cudaFuncSetAttribute(conv_out_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 340 * 512));
+    attr_set = true;
+  }
+  switch (C) {  // 4-channel statistic buckets need C / 32 to be a multiple of 4
+    case 128: return check_cuda(launch_k(conv_out_kernel<4, true>, grid, dim3(256), smem, stream, xi, w, bias, out, H, W, tiles_w, fmt, stats, gamma, beta), "conv_out_kernel");
+    case 256: return check_cuda(launch_k(conv_out_kernel<8, true>, grid, dim3(256), smem, stream, xi, w, bias, out, H, W, tiles_w, fmt, stats, gamma, beta), "conv_out_kernel");
+    default: return fail(kUnsupported, "conv_out_gn: model_channels must be 128 or 256");
+  }
 }
 
 int launch_conv_out(const void* x, const float* w, const float* bias, float* out, int B, int H, int W, int C,
@@ -900,18 +1131,17 @@ int launch_conv_out(const void* x, const float* w, const float* bias, float* out
   const uint16_t* xi = reinterpret_cast<const uint16_t*>(x);
   static bool attr_set = false;
   if (!attr_set) {
-    CDDPM_CUDA(cudaFuncSetAttribute(conv_out_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 340 * 128));
-    CDDPM_CUDA(cudaFuncSetAttribute(conv_out_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 340 * 256));
-    CDDPM_CUDA(cudaFuncSetAttribute(conv_out_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 340 * 512));
+    CDDPM_CUDA(cudaFuncSetAttribute(conv_out_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 340 * 128));
+    CDDPM_CUDA(cudaFuncSetAttribute(conv_out_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 340 * 256));
+    CDDPM_CUDA(cudaFuncSetAttribute(conv_out_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 340 * 512));
     attr_set = true;
   }
   switch (C) {
-    case 64: conv_out_kernel<2><<<grid, 256, smem, stream>>>(xi, w, bias, out, H, W, tiles_w, fmt); break;
-    case 128: conv_out_kernel<4><<<grid, 256, smem, stream>>>(xi, w, bias, out, H, W, tiles_w, fmt); break;
-    case 256: conv_out_kernel<8><<<grid, 256, smem, stream>>>(xi, w, bias, out, H, W, tiles_w, fmt); break;
+    case 64: return check_cuda(launch_k(conv_out_kernel<2, false>, grid, dim3(256), smem, stream, xi, w, bias, out, H, W, tiles_w, fmt, static_cast<const double*>(nullptr), static_cast<const float*>(nullptr), static_cast<const float*>(nullptr)), "conv_out_kernel");
+    case 128: return check_cuda(launch_k(conv_out_kernel<4, false>, grid, dim3(256), smem, stream, xi, w, bias, out, H, W, tiles_w, fmt, static_cast<const double*>(nullptr), static_cast<const float*>(nullptr), static_cast<const float*>(nullptr)), "conv_out_kernel");
+    case 256: return check_cuda(launch_k(conv_out_kernel<8, false>, grid, dim3(256), smem, stream, xi, w, bias, out, H, W, tiles_w, fmt, static_cast<const double*>(nullptr), static_cast<const float*>(nullptr), static_cast<const float*>(nullptr)), "conv_out_kernel");
     default: return fail(kUnsupported, "conv_out: model_channels must be 64, 128 or 256");
   }
-  return check_launch("conv_out_kernel");
 }
 
 int launch_vec_add(const float* a, const float* b, float* out, int n, cudaStream_t stream) {

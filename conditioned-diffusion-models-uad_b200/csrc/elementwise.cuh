@@ -76,6 +76,10 @@ int launch_conv_in(const float* x, const float* w, const float* bias, void* out,
 int launch_conv_out(const void* x, const float* w, const float* bias, float* out, int B, int H, int W, int C,
                     int fmt, cudaStream_t stream);
 
+// Head with its GroupNorm + SiLU folded in: x is the RAW input of out.0, stats its [B][C/4][2] (sum, sumsq) buckets.
+int launch_conv_out_gn(const void* x, const double* stats, const float* gamma, const float* beta, const float* w,
+                       const float* bias, float* out, int B, int H, int W, int C, int fmt, cudaStream_t stream);
+
 int launch_vec_add(const float* a, const float* b, float* out, int n, cudaStream_t stream);
 
 }  // namespace cddpm

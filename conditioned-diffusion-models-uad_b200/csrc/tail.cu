@@ -2,6 +2,7 @@
 // launch-bound, not bandwidth-bound; the win over the reference is removing ~1 s of host scipy/sklearn per volume.
 #include "tail.cuh"
 
+#include <algorithm>
 #include <cub/cub.cuh>
 
 namespace cddpm {
@@ -44,6 +45,43 @@ __device__ __forceinline__ unsigned long long block_sum_u(unsigned long long v, 
     for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
   }
   return r;
+}
+
+// ---------------------------------------------------------------------------------------------- trilinear resize
+// F.interpolate(vol[None, None], size=(Ho, Wo, Do), mode="trilinear", align_corners=True) (utils_eval.py:24-25): source
+// coordinate = i * (in - 1) / (out - 1) in fp32, lower index = floor, upper = lower + (lower < in - 1), weights
+// (1 - l, l); the three axes are folded outermost-first like ATen's upsample kernel:
+// wy0 (wx0 (wd0 a + wd1 b) + wx1 (...)) + wy1 (...).  dst is [Ho][Wo][Do] contiguous (d fastest), the layout of the
+// reference's squeezed tensor.
+struct Lerp {
+  int i0, i1;
+  float w0, w1;
+};
+__device__ __forceinline__ Lerp lerp_coord(int o, int in, int out) {
+  Lerp r;
+  const float scale = out > 1 ? static_cast<float>(in - 1) / static_cast<float>(out - 1) : 0.f;
+  const float src = scale * static_cast<float>(o);
+  r.i0 = min(static_cast<int>(src), in - 1);
+  r.i1 = r.i0 + (r.i0 < in - 1 ? 1 : 0);
+  r.w1 = src - static_cast<float>(r.i0);
+  r.w0 = 1.0f - r.w1;
+  return r;
+}
+__global__ void __launch_bounds__(256) trilinear_kernel(View src, int H, int W, int D, float* __restrict__ dst, int Ho,
+                                                        int Wo, int Do) {
+  const long long n = static_cast<long long>(Ho) * Wo * Do;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < n;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int d = static_cast<int>(idx % Do);
+    const int x = static_cast<int>((idx / Do) % Wo);
+    const int y = static_cast<int>(idx / (static_cast<long long>(Do) * Wo));
+    const Lerp ly = lerp_coord(y, H, Ho), lx = lerp_coord(x, W, Wo), ld = lerp_coord(d, D, Do);
+    auto line = [&](int yy, int xx) {
+      return __fadd_rn(__fmul_rn(ld.w0, src.at(yy, xx, ld.i0)), __fmul_rn(ld.w1, src.at(yy, xx, ld.i1)));
+    };
+    auto plane = [&](int yy) { return __fadd_rn(__fmul_rn(lx.w0, line(yy, lx.i0)), __fmul_rn(lx.w1, line(yy, lx.i1))); };
+    dst[idx] = __fadd_rn(__fmul_rn(ly.w0, plane(ly.i0)), __fmul_rn(ly.w1, plane(ly.i1)));
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- residual + erosion
@@ -375,6 +413,16 @@ int launch_residual_erode(const VolView& orig, const VolView& reco, const VolVie
   residual_erode_kernel<<<blocks, 256, 0, stream>>>(dev_view(orig), dev_view(reco), dev_view(seg), dev_view(mask), H, W,
                                                     D, iterations, erode, diff_masked, sums);
   return check_launch("residual_erode_kernel");
+}
+
+int launch_trilinear_resize(const VolView& src, int H, int W, int D, float* dst, int Ho, int Wo, int Do,
+                            cudaStream_t stream) {
+  if (!src.p || !dst) return fail(kInvalidArgument, "trilinear_resize: null pointer");
+  if (H < 1 || W < 1 || D < 1 || Ho < 1 || Wo < 1 || Do < 1) return fail(kInvalidArgument, "trilinear_resize: empty extent");
+  const long long n = static_cast<long long>(Ho) * Wo * Do;
+  const int blocks = static_cast<int>(std::min<long long>((n + 255) / 256, 148 * 16));
+  trilinear_kernel<<<blocks, 256, 0, stream>>>(dev_view(src), H, W, D, dst, Ho, Wo, Do);
+  return check_launch("trilinear_kernel");
 }
 
 int launch_median3d(const float* in, float* out, int H, int W, int D, int k, cudaStream_t stream) {

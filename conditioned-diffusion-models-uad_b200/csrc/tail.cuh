@@ -20,6 +20,10 @@ int launch_residual_erode(const VolView& orig, const VolView& reco, const VolVie
                           int W, int D, int iterations, int erode, float* diff_masked, double* sums,
                           cudaStream_t stream);
 
+// dst[Ho][Wo][Do] = trilinear resize of the [H,W,D] view with align_corners=True (F.interpolate, utils_eval.py:24-25).
+int launch_trilinear_resize(const VolView& src, int H, int W, int D, float* dst, int Ho, int Wo, int Do,
+                            cudaStream_t stream);
+
 // scipy.ndimage.median_filter(vol, (k,k,k), mode='reflect') for k = 5 (or 3) on a [D,H,W] buffer: symmetric padding,
 // element of rank k^3/2 (utils_eval.py:462-464).
 int launch_median3d(const float* in, float* out, int H, int W, int D, int k, cudaStream_t stream);

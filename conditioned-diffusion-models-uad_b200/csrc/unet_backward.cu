@@ -560,9 +560,10 @@ int UNetEngine::plan_backward(int B) {
 
 int UNetEngine::backward(const float* dout, float* grads, float* dcond, int B, cudaStream_t stream) {
   if (!dout || !grads) return fail(kInvalidArgument, "unet_backward: null pointer");
-  if (plan_fused_)
-    return fail(kNotReady, "unet_backward: the forward ran with an inference-only fusion (CDDPM_FUSE_GN=1); call "
-                           "cddpm_unet_set_training(h, 1) before the forward of a training step");
+  if (plan_fused_ || plan_fused_head_)
+    return fail(kNotReady, "unet_backward: the forward ran with an inference-only fusion (the head's GroupNorm inside "
+                           "conv_out, or CDDPM_FUSE_GN=1); call cddpm_unet_set_training(h, 1) before the forward of a "
+                           "training step");
   if (B != planned_B_ || forwards_on_plan_ < 1)
     return fail(kNotReady, "unet_backward: run the forward of this batch first");
   if (!bwd_planned_) {

@@ -746,6 +746,7 @@ int UNetEngine::plan_attn(const AttnLayer& L, const ActTensor& x, ActTensor* out
 int UNetEngine::plan(int B) {
   free_acts();
   conv_flops_ = 0;
+  memset_op_ = -1;
   const int fmt = cfg_.fmt;
   const int mc = cfg_.model_channels;
   const int H = cfg_.image_h, W = cfg_.image_w;
@@ -780,6 +781,7 @@ int UNetEngine::plan(int B) {
     act_owned_.push_back(q);
     stats_arena_ = reinterpret_cast<double*>(q);
     UNetEngine* self = this;
+    memset_op_ = static_cast<int>(ops_.size());
     ops_.push_back([self](cudaStream_t s) {
       return check_cuda(cudaMemsetAsync(self->stats_arena_, 0, self->stats_used_ * sizeof(double), s), "stats memset");
     });
@@ -942,7 +944,24 @@ int UNetEngine::plan(int B) {
     }
   }
   // ---- head: GroupNorm + SiLU + conv 3x3 -> 1 channel, fp32 NCHW
-  {
+  static const bool fuse_head_ok = [] {
+    const char* e = getenv("CDDPM_FUSE_HEAD");  // A/B switch: 0 keeps the separate GroupNorm pass in front of the head
+    return !(e != nullptr && e[0] == '0');
+  }();
+  if (fuse_head_ok && !training_ && fused_stats_ && h.stats != nullptr && (h.C == 128 || h.C == 256)) {
+    // inference: out.0 / out.1 run inside the head convolution's staged tile (elementwise.cu conv_out_kernel<.., true>);
+    // training engines keep the normalised tensor for the backward pass
+    const int hh = h.H, ww = h.W, cc = h.C;
+    const void* hp = h.p;
+    const double* hst = h.stats;
+    head_in_ = h;
+    head_tN_ = ActTensor();
+    plan_fused_head_ = true;
+    ops_.push_back([=](cudaStream_t s) {
+      return launch_conv_out_gn(hp, hst, head_gn_w, head_gn_b, head_w, head_b, cur_out_, B, hh, ww, cc, fmt, s);
+    });
+  } else {
+    plan_fused_head_ = false;
     ActTensor tN;
     CDDPM_TRY(act_alloc(&tN, h.C, h.H, h.W, B));
     CatView v;
@@ -983,6 +1002,31 @@ int UNetEngine::plan(int B) {
   return kOk;
 }
 
+// Measured on B200 (profiles/r02_c2_ab.log): programmatic launches shorten the B=1 forward by 2.3 % (1.284 -> 1.254 ms:
+// 123 launch gaps) and LENGTHEN the B=32 forward by 1 % (5.52 -> 5.58 ms: the persistent convolutions leave no tail to
+// hide a prologue under), so the attribute is only offered to small batches (CDDPM_PDL_MAX_B overrides, default 4).
+static bool pdl_batch_ok(int B) {
+  static const int max_b = [] {
+    const char* e = getenv("CDDPM_PDL_MAX_B");
+    return e != nullptr ? atoi(e) : 4;
+  }();
+  return B <= max_b;
+}
+
+// The planned launch list on ONE stream.  Every op whose predecessor is a kernel is offered a programmatic dependent
+// launch (only the kernels that carry a griddepcontrol.wait take it: common.h launch_k).  Per-launch profiling events
+// sit between the kernels, so an armed forward runs without it.
+int UNetEngine::run_ops_inline(cudaStream_t stream) {
+  const int n = static_cast<int>(ops_.size());
+  for (int i = 0; i < n; ++i) {
+    pdl_set_next(i > 0 && (i - 1) != memset_op_ && !profile_armed_ && pdl_batch_ok(planned_B_));
+    const int st = ops_[i](stream);
+    pdl_set_next(false);
+    CDDPM_TRY(st);
+  }
+  return kOk;
+}
+
 static bool fork_embed_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -1001,10 +1045,7 @@ int UNetEngine::capture_ops() {
   const int n = static_cast<int>(ops_.size());
   const bool fork = fork_embed_enabled() && film_op_ >= 0 && first_film_use_ > film_op_ && emb_t_end_ > emb_t_begin_ &&
                     film_op_ == emb_c_end_ && emb_c_begin_ == emb_t_end_;
-  if (!fork) {
-    for (auto& op : ops_) CDDPM_TRY(op(cap_stream_));
-    return kOk;
-  }
+  if (!fork) return run_ops_inline(cap_stream_);
   // highest priority: the side branches are a handful of small CTAs that must slip in between the blocks of the stem /
   // GroupNorm kernels instead of queueing behind them (the priority is recorded into the captured kernel nodes)
   int prio_lo = 0, prio_hi = 0;
@@ -1016,6 +1057,7 @@ int UNetEngine::capture_ops() {
     if (fork_ev_[i] == nullptr) CDDPM_CUDA(cudaEventCreateWithFlags(&fork_ev_[i], cudaEventDisableTiming));
   int st = kOk;
   bool joined = false;
+  bool main_prev_kernel = false;
   for (int i = 0; i < n && st == kOk; ++i) {
     if (i == emb_t_begin_) {
       // fork: both side branches start from this point of the main branch
@@ -1039,7 +1081,12 @@ int UNetEngine::capture_ops() {
         CDDPM_CUDA(cudaStreamWaitEvent(cap_stream_, fork_ev_[2], 0));
         joined = true;
       }
+      // programmatic dependent launch along the main branch: op i may start under the tail of the main branch's
+      // previous kernel - not behind the memset, and not at the join (two predecessors)
+      pdl_set_next(main_prev_kernel && i != first_film_use_ && pdl_batch_ok(planned_B_));
       st = ops_[i](cap_stream_);
+      pdl_set_next(false);
+      main_prev_kernel = (i != memset_op_);
     }
   }
   if (st == kOk && !joined) CDDPM_CUDA(cudaStreamWaitEvent(cap_stream_, fork_ev_[2], 0));
@@ -1097,7 +1144,7 @@ int UNetEngine::forward(const float* x, const int64_t* t, const float* cond, flo
   cur_t_ = t;
   cur_cond_ = cond;
   cur_out_ = out;
-  for (auto& op : ops_) CDDPM_TRY(op(stream));
+  CDDPM_TRY(run_ops_inline(stream));
   if (profile_armed_) profile_armed_ = false;  // one forward per arming
   ++forwards_on_plan_;
   return kOk;

@@ -133,6 +133,7 @@ class UNetEngine {
   bool fused_stats_ = true;
   bool training_ = false;
   bool plan_fused_ = false;  // the current plan contains an inference-only fusion (backward refuses it)
+  bool plan_fused_head_ = false;  // ... the head's GroupNorm inside conv_out (no normalised tensor kept)
 
   cddpm_unet_config cfg_{};
   int emb_dim_ = 0, half_dim_ = 0, film_total_ = 0;
@@ -180,6 +181,8 @@ class UNetEngine {
   // forked capture of the embedding path (capture_ops): op index ranges of the timestep chain, the condition chain,
   // the FiLM projection and the first reader of the FiLM table
   int capture_ops();
+  int run_ops_inline(cudaStream_t stream);
+  int memset_op_ = -1;  // index of the statistics-arena memset in ops_ (not a kernel: no programmatic launch behind it)
   int emb_t_begin_ = 0, emb_t_end_ = 0, emb_c_begin_ = 0, emb_c_end_ = 0, film_op_ = -1, first_film_use_ = -1;
   cudaStream_t side_stream_[2] = {nullptr, nullptr};
   cudaEvent_t fork_ev_[3] = {nullptr, nullptr, nullptr};

@@ -207,14 +207,24 @@ int cddpm_q_sample(const float* img, const void* noise, int noise_f16, float* ou
                    const float* sqrt_one_minus_alphas_cumprod, const int64_t* t, int t_shared, int B, int HW,
                    int normalize, void* stream);
 
-/* p_sample (cond_DDPM.py:432-444): model_predictions (:400-420, clip to [-1,1]) + q_posterior (:391-398) +
- * sigma_t * noise for t > 0.  noise may be NULL (t == 0).  pred_noise selects the objective.  final_unnormalize
- * applies unnormalize_to_zero_to_one (:78, :463) to the result of the last step. */
+/* p_sample (cond_DDPM.py:432-444): model_predictions (:400-420) + the clamp of p_mean_variance (:422-430, only when
+ * clip_denoised != 0) + q_posterior (:391-398) + sigma_t * noise for t > 0.  noise may be NULL (t == 0).  pred_noise
+ * selects the objective.  final_unnormalize applies unnormalize_to_zero_to_one (:78, :463) to the last step's result. */
 int cddpm_posterior_step(const float* model_out, const float* x_t, const void* noise, int noise_f16, float* x_prev,
                          const float* posterior_mean_coef1, const float* posterior_mean_coef2,
                          const float* posterior_log_variance_clipped, const float* sqrt_recip_alphas_cumprod,
                          const float* sqrt_recipm1_alphas_cumprod, int64_t t, int B, int HW, int pred_noise,
-                         int final_unnormalize, void* stream);
+                         int clip_denoised, int final_unnormalize, void* stream);
+
+/* One update of ddim_sample (cond_DDPM.py:487-511): pred_noise / x_start from model_predictions (:400-420; pred_noise
+ * is derived from the UNclamped prediction), x_start.clamp_ when clip_denoised, then
+ * x_next = x_start * sqrt_alpha_next + c * pred_noise + sigma * noise.  The five step scalars are fp32 values the host
+ * computes exactly as the reference does from its schedule buffers (sqrt_recip(m1)_alphas_cumprod[time],
+ * alphas_cumprod_prev[time / time_next], ddim_sampling_eta); noise may be NULL (time_next == 0). */
+int cddpm_ddim_step(const float* model_out, const float* x_t, const void* noise, int noise_f16, float* x_next,
+                    float sqrt_recip_alphas_cumprod_t, float sqrt_recipm1_alphas_cumprod_t, float sqrt_alpha_next,
+                    float c, float sigma, int B, int HW, int pred_noise, int clip_denoised, int final_unnormalize,
+                    void* stream);
 
 /* Tail of p_losses (cond_DDPM.py:636-645): reco = reco*reco_beta + reco_alpha * unnormalize(model_out) (pred_x0) or
  * unnormalize(x_t - sqrt(1-acp)*model_out) (pred_noise, as the reference computes it); loss[b] = mean |out-target|
@@ -251,6 +261,11 @@ typedef struct cddpm_vol_view {
 int cddpm_residual_erode(const cddpm_vol_view* orig, const cddpm_vol_view* reco, const cddpm_vol_view* seg,
                          const cddpm_vol_view* mask, int H, int W, int D, int iterations, int erode,
                          float* diff_masked_dhw, double* sums, void* stream);
+/* Full-resolution evaluation (cfg.resizedEvaluation == False, utils_eval.py:24-25):
+ * F.interpolate(final_volume, size=new_size, mode="trilinear", align_corners=True) of the logical [H,W,D] view into a
+ * contiguous [Ho,Wo,Do] fp32 buffer (d fastest - the layout of the reference's squeezed tensor). */
+int cddpm_trilinear_resize(const cddpm_vol_view* src, int H, int W, int D, float* dst_hwd, int Ho, int Wo, int Do,
+                           void* stream);
 /* scipy.ndimage.median_filter(vol, (k,k,k)) with mode='reflect' (apply_3d_median_filter :462-464), k in {1,3,5}. */
 int cddpm_median3d(const float* in_dhw, float* out_dhw, int H, int W, int D, int k, void* stream);
 /* np.max of a buffer (val_range top of find_best_val, :86); out_max: one float on the device. */

@@ -111,3 +111,48 @@ def reverse_loop(model: Callable, sched, x_start: torch.Tensor, cond, start_t: i
         n = n.float() if t > 0 else 0.0
         img = mean + (0.5 * logvar).exp() * n
     return (img + 1) * 0.5
+
+
+def ddim_sample(model: Callable, sched, shape, x_start, cond, start_t: int, sampling_timesteps: int, eta: float,
+                noise, noise_fn: Callable[[], torch.Tensor], randn_fn: Callable[[], torch.Tensor],
+                objective: str = "pred_x0", simplex: bool = True, clip_denoised: bool = True,
+                timesteps: int = 1000):
+    """GaussianDiffusion.ddim_sample (cond_DDPM.py:466-515) with its quirks: the first draw is discarded; with
+    start_t != 0 the caller's `noise` argument itself is handed to q_sample (a flag True therefore multiplies
+    sqrt(1 - acp) by 1); alpha comes from alphas_cumprod_prev; the per-step noise type follows cfg.noisetype."""
+    b = shape[0]
+    dev = x_start.device if x_start is not None else torch.device("cpu")
+    total = start_t if start_t > 0 else timesteps
+    times = torch.linspace(0.0, total, steps=sampling_timesteps + 2)[:-1]
+    times = list(reversed(times.int().tolist()))
+    pairs = list(zip(times[:-1], times[1:]))
+    if noise is not None:
+        noise_fn()
+    else:
+        randn_fn()
+    if start_t != 0:
+        nz = randn_fn() if noise is None else noise
+        img = q_sample(sched, x_start, torch.tensor([start_t], device=dev), nz)
+    else:
+        img = randn_fn()
+    for time, time_next in pairs:
+        alpha = sched["alphas_cumprod_prev"][time]
+        alpha_next = sched["alphas_cumprod_prev"][time_next]
+        tt = torch.full((b,), time, device=dev, dtype=torch.long)
+        out = model(img, tt, cond)
+        if objective == "pred_noise":
+            pred_noise = out
+            x0 = _at(sched["sqrt_recip_alphas_cumprod"], tt, 4) * img - _at(sched["sqrt_recipm1_alphas_cumprod"], tt, 4) * out
+        else:
+            pred_noise = (_at(sched["sqrt_recip_alphas_cumprod"], tt, 4) * img - out) / _at(sched["sqrt_recipm1_alphas_cumprod"], tt, 4)
+            x0 = out
+        if clip_denoised:
+            x0 = x0.clamp(-1.0, 1.0)
+        sigma = eta * ((1 - alpha / alpha_next) * (1 - alpha_next) / (1 - alpha)).sqrt()
+        c = ((1 - alpha_next) - sigma ** 2).sqrt()
+        if time_next > 0:
+            n = noise_fn().to(dev) if simplex else randn_fn()
+        else:
+            n = 0.0
+        img = x0 * alpha_next.sqrt() + c * pred_noise + sigma * n
+    return (img + 1) * 0.5

@@ -396,12 +396,58 @@ def _full_ddpm2d(cfg):
     return model.eval()
 
 
+def fit_denoiser_readout(n_samples=32, ridge=1e-3):
+    """Synthetic weights under which the reverse process is WELL-CONDITIONED.  With every tensor random (oracle.weights)
+    the x0-prediction is a random function of x_t with a large Lipschitz constant and the reverse loop amplifies any
+    per-step rounding difference (measured on the fp32 reference itself: a 1e-3 perturbation of each UNet output grows
+    to 2.6e-2 over the last 50 steps) - unlike a trained model, whose x0-prediction is a denoiser.  So the LAST layer
+    (out.2: 128 -> 1 channels, 3x3, 1153 numbers) is fitted by ridge least squares to predict x_0 from x_t over the
+    random features of the layers below it (32 synthetic slices, random t < 500, simplex noise).  Everything below stays
+    the seeded random draw; only these 1153 numbers are stored with the golden.  Returns (weight [1,128,3,3], bias [1])."""
+    import torch.nn.functional as F
+
+    from oracle.simplex_port import gen_noise_port
+
+    spec = unet_port.UNetSpec()
+    sd = make_state_dict(unet_port.param_shapes(spec), seed=1)
+    enc = make_state_dict(resnet_port.param_shapes(128), seed=3)
+    sched = diffusion_port.schedule_buffers()
+    K = 128 * 9 + 1
+    AtA = torch.zeros(K, K, dtype=torch.float64)
+    Aty = torch.zeros(K, dtype=torch.float64)
+    np.random.seed(101)
+    tg = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        for b in range(n_samples // 4):
+            x = synthetic_slices(4, 96, seed=500 + b)
+            cond = resnet_port.resnet_forward(enc, x)
+            t = torch.randint(0, 500, (4,), generator=tg)
+            xt = diffusion_port.q_sample(sched, x * 2 - 1, t, gen_noise_port((4, 1, 96, 96)).float())
+            taps = {}
+            unet_port.unet_forward(sd, spec, xt, t, cond, taps=taps)
+            phi = F.silu(unet_port._gn(taps["output_blocks.11.0"], sd, "out.0", spec.groups))
+            A = F.unfold(phi, 3, padding=1).permute(0, 2, 1).reshape(-1, 128 * 9).double()
+            A = torch.cat([A, torch.ones(A.shape[0], 1, dtype=torch.float64)], 1)
+            AtA += A.T @ A
+            Aty += A.T @ (x * 2 - 1).reshape(-1).double()
+    reg = ridge * torch.diag(AtA).mean() * torch.eye(K, dtype=torch.float64)
+    reg[-1, -1] = 0
+    w = torch.linalg.solve(AtA + reg, Aty)
+    return w[:-1].reshape(1, 128, 3, 3).float().contiguous(), w[-1:].float().contiguous()
+
+
 def golden_reverse_96():
     """BASELINE configs[1] at its OWN geometry (VERDICT r1 'next' #1): the live reference's encoder -> conditioned
     128-channel UNet at 96x96 -> GaussianDiffusion.sample(cond, x_start, start_t=T0, noise=True) (cond_DDPM.py:517-530,
-    :446-464) for T0 in {50, 500}, batch 2, on CPU in fp32.  The simplex fields come from gen_noise under a fixed
+    :446-464) for T0 in {50, 500}, batch 2, on CPU.  The simplex fields come from gen_noise under a fixed
     np.random.seed, so the GPU test regenerates them bit-exactly and nothing but inputs-by-recipe and outputs are stored.
-    The T0=500 run also stores x_t at every 50th step (p_sample return values) so a parity failure can be located."""
+    x_t is stored at every 50th step (p_sample return values) so a deviation can be located.
+
+    Two weight sets: "rand" (every tensor the seeded random draw) and "fit" (same, with the last layer fitted so the
+    model is a denoiser, fit_denoiser_readout).  Two precisions of the SAME unmodified reference code: fp32, and
+    torch.autocast(fp16) - the precision the reference is configured to run at (configs/trainer/default.yaml:7
+    `precision: 16` -> Lightning native AMP).  The autocast run gives the yardstick for an iterated map: how far the
+    reference's own production precision moves from its fp32 path over T0 steps."""
     import time
 
     cfg = base_cfg()
@@ -409,32 +455,50 @@ def golden_reverse_96():
     model.diffusion.use_spatial_transformer = False  # the reference forgets this attribute (cond_DDPM.py:401)
     x = synthetic_slices(2, 96, seed=31)
     out = {}
+    W, b = fit_denoiser_readout()
+    out["fit_out2_weight"], out["fit_out2_bias"] = W, b
+    rand_w = model.diffusion.model.out[2].weight.detach().clone()
+    rand_b = model.diffusion.model.out[2].bias.detach().clone()
     with torch.no_grad():
         cond = model(x)
         out["cond"] = cond
-        for T0, seed in ((50, 17), (500, 19)):
-            snaps = {}
-            orig = model.diffusion.p_sample
+        for wtag in ("rand", "fit"):
+            model.diffusion.model.out[2].weight.copy_(rand_w if wtag == "rand" else W)
+            model.diffusion.model.out[2].bias.copy_(rand_b if wtag == "rand" else b)
+            for T0, seed in ((50, 17), (500, 19)):
+                for prec in ("fp32", "amp16"):
+                    snaps = {}
+                    orig = model.diffusion.p_sample
 
-            def spy(x_, t, *a, _orig=orig, _snaps=snaps, **k):
-                r = _orig(x_, t, *a, **k)
-                if t % 50 == 0:
-                    _snaps[t] = r.detach().clone()
-                return r
+                    def spy(x_, t, *a, _orig=orig, _snaps=snaps, **k):
+                        r = _orig(x_, t, *a, **k)
+                        if t % 50 == 0 and t > 0:
+                            _snaps[t] = r.detach().float().clone()
+                        return r
 
-            model.diffusion.p_sample = spy
-            np.random.seed(seed)
-            t0 = time.time()
-            rec = model.diffusion.sample(cond=cond, x_start=x * 2 - 1, start_t=T0, noise=True)
-            model.diffusion.p_sample = orig
-            print(f"reverse_96 T0={T0}: {time.time() - t0:.1f} s, out range [{rec.min():.3f}, {rec.max():.3f}], "
-                  f"std {rec.std():.4f}")
-            out[f"out_T{T0}"] = rec
-            out[f"seed_T{T0}"] = seed
-            if T0 == 500:
-                ts = sorted(snaps)
-                out["snap_t"] = np.asarray(ts)
-                out["snap_x"] = torch.stack([snaps[t] for t in ts]).half()  # fp16 storage: 2.4e-4 abs at |x|<=1... stated
+                    model.diffusion.p_sample = spy
+                    np.random.seed(seed)
+                    t0 = time.time()
+                    with torch.autocast("cpu", dtype=torch.float16, enabled=(prec == "amp16")):
+                        rec = model.diffusion.sample(cond=cond, x_start=x * 2 - 1, start_t=T0, noise=True).float()
+                    model.diffusion.p_sample = orig
+                    key = f"{wtag}_{prec}_T{T0}"
+                    print(f"reverse_96 {key}: {time.time() - t0:.1f} s, out range [{rec.min():.3f}, {rec.max():.3f}], "
+                          f"std {rec.std():.4f}", flush=True)
+                    out["out_" + key] = rec
+                    ts = sorted(snaps)
+                    if ts and prec == "fp32":  # x_t of sample 0, fp32 (the drift is compared at the 1e-4 level)
+                        out["snap_t_" + key] = np.asarray(ts)
+                        out["snap_x_" + key] = torch.stack([snaps[t][0] for t in ts])
+                    if prec == "amp16":
+                        ref = out[f"out_{wtag}_fp32_T{T0}"]
+                        print(f"   reference amp16 vs its own fp32: max-abs {(rec - ref).abs().max():.4g}", flush=True)
+                        if ts:  # the yardstick trajectory: per-snapshot deviation of amp16 from fp32 (sample 0)
+                            rs = out[f"snap_x_{wtag}_fp32_T{T0}"]
+                            out["amp_drift_" + key] = np.asarray([float((snaps[t][0] - rs[i]).abs().max())
+                                                                  for i, t in enumerate(ts)])
+                            print("   amp16 drift by t:", dict(zip(ts, out["amp_drift_" + key].round(5))), flush=True)
+            out[f"seed_T50"], out[f"seed_T500"] = 17, 19
     save("reverse_96.npz", **out)
 
 
@@ -503,10 +567,122 @@ def golden_uncond_step():
     save("uncond_step_96.npz", reco=reco, loss=loss, seed=29, n_state=len(model.state_dict()))
 
 
+
+def golden_ddim():
+    """GaussianDiffusion.ddim_sample (cond_DDPM.py:466-515; reached through sample() when sampling_timesteps < timesteps)
+    and p_sample with clip_denoised=False, on the small geometry.  Two DDIM cases: start_t = 300 with the simplex flag
+    (fully determined by np.random.seed: the flag True itself is q_sample's noise, the per-step fields are gen_noise
+    draws) and start_t = 0 from a stored Gaussian x_T."""
+    from src.models.modules import cond_DDPM
+    from src.models.modules.cond_DDPM import GaussianDiffusion
+
+    from oracle.simplex_port import gen_noise_port
+
+    spec = unet_port.UNetSpec(model_channels=64, channel_mult=(1, 2), num_res_blocks=1, num_classes=128)
+    m, shapes = ref_unet(spec, image=32)
+    sd = make_state_dict(shapes, seed=2)
+    m.load_state_dict(sd, strict=True)
+    sched = diffusion_port.schedule_buffers()
+    model = lambda x, t, c: unet_port.unet_forward(sd, spec, x, t, c)  # noqa: E731
+    g = torch.Generator().manual_seed(33)
+    img = torch.rand(2, 1, 32, 32, generator=g)
+    cond = torch.randn(2, 128, generator=g)
+    out = {"img": img, "cond": cond}
+    for objective in ("pred_x0", "pred_noise"):
+        d = GaussianDiffusion(m, image_size=(32, 32), timesteps=1000, sampling_timesteps=6, objective=objective,
+                              channels=1, loss_type="l1", p2_loss_weight_gamma=0, ddim_sampling_eta=0.7, cfg=base_cfg())
+        d.use_spatial_transformer = False
+        assert d.is_ddim_sampling
+        with torch.no_grad():
+            np.random.seed(5)
+            rec = d.sample(cond=cond, x_start=img * 2 - 1, start_t=300, noise=True)
+            np.random.seed(5)
+            prec = diffusion_port.ddim_sample(model, sched, (2, 1, 32, 32), img * 2 - 1, cond, 300, 6, 0.7, True,
+                                              lambda: gen_noise_port((2, 1, 32, 32)), None, objective=objective)
+        assert (rec - prec).abs().max().item() < 1e-4, (rec - prec).abs().max().item()
+        out[f"ddim_simplex_{objective}"] = rec
+        # yardstick for an iterated map: the same reference code under its configured precision (fp16 autocast)
+        with torch.no_grad(), torch.autocast("cpu", dtype=torch.float16):
+            np.random.seed(5)
+            amp = d.sample(cond=cond, x_start=img * 2 - 1, start_t=300, noise=True).float()
+        out[f"ddim_simplex_{objective}_amp16_dev"] = float((amp - rec).abs().max())
+        print(f"ddim {objective}: reference amp16 vs its own fp32 max-abs {out[f'ddim_simplex_{objective}_amp16_dev']:.4g}")
+    # start_t = 0: x_T is the SECOND torch.randn draw (the first is discarded); per-step noise is simplex (cfg.noisetype)
+    d = GaussianDiffusion(m, image_size=(32, 32), timesteps=1000, sampling_timesteps=4, objective="pred_x0", channels=1,
+                          loss_type="l1", p2_loss_weight_gamma=0, ddim_sampling_eta=1.0, cfg=base_cfg())
+    d.use_spatial_transformer = False
+    with torch.no_grad():
+        torch.manual_seed(77)
+        torch.randn(2, 1, 32, 32)
+        x_T = torch.randn(2, 1, 32, 32)
+        torch.manual_seed(77)
+        np.random.seed(6)
+        rec = d.sample(cond=cond, x_start=img * 2 - 1, start_t=0, noise=None)
+        draws = [torch.zeros(2, 1, 32, 32), x_T]
+        np.random.seed(6)
+        prec = diffusion_port.ddim_sample(model, sched, (2, 1, 32, 32), img * 2 - 1, cond, 0, 4, 1.0, None,
+                                          lambda: gen_noise_port((2, 1, 32, 32)), lambda: draws.pop(0))
+    assert (rec - prec).abs().max().item() < 1e-4, (rec - prec).abs().max().item()
+    out["ddim_xT"] = x_T
+    out["ddim_gauss_start"] = rec
+    # p_sample without clipping (clip_denoised=False, cond_DDPM.py:422-444), one step with Gaussian noise handed in
+    d = GaussianDiffusion(m, image_size=(32, 32), timesteps=1000, sampling_timesteps=1000, objective="pred_x0",
+                          channels=1, loss_type="l1", p2_loss_weight_gamma=0, cfg=base_cfg())
+    d.use_spatial_transformer = False
+    with torch.no_grad():
+        x = 1.5 * torch.randn(2, 1, 32, 32, generator=g)
+        torch.manual_seed(78)
+        nz = torch.randn(2, 1, 32, 32)
+        torch.manual_seed(78)
+        out["noclip_x"] = x
+        out["noclip_noise"] = nz
+        out["noclip_out"] = d.p_sample(x.clone(), 400, clip_denoised=False, cond=cond, noise=None)
+        torch.manual_seed(78)
+        out["clip_out"] = d.p_sample(x.clone(), 400, clip_denoised=True, cond=cond, noise=None)
+        assert (out["noclip_out"] - out["clip_out"]).abs().max().item() > 1e-3  # the clamp is active on this input
+    save("ddim_small_32.npz", **out)
+
+
+
+def golden_tail_fullres():
+    """utils_eval._test_step with cfg.resizedEvaluation=False (:24-25): the [96,96,50] reconstruction is resized to
+    new_size = [160,190,160] with F.interpolate(trilinear, align_corners=True) and scored against full-resolution
+    originals.  Stored: probes and the float64 sum of the resized volume, the eval_dict scalars."""
+    import torch.nn.functional as F
+
+    from src.utils import utils_eval
+
+    from oracle.weights import synthetic_fullres_case
+
+    class Host:
+        pass
+
+    host = Host()
+    host.cfg = base_cfg(resizedEvaluation=False)
+    host.eval_dict = utils_eval.get_eval_dictionary()
+    host.threshold = {}
+    host.dataset = ["Brats21"]
+    host.new_size = [160, 190, 160]
+    host.diffs_list, host.seg_list = [], []
+    host.stage = "val"
+    c = synthetic_fullres_case(4)
+    utils_eval._test_step(host, c["reco"].clone(), c["vol_orig"].clone(), c["seg_orig"].clone(), c["mask_orig"].clone(),
+                          0, ["v4"], torch.tensor([1]))
+    resized = F.interpolate(c["reco"], size=host.new_size, mode="trilinear", align_corners=True)[0, 0]
+    probes = [(0, 0, 0), (159, 189, 159), (80, 95, 80), (17, 101, 33), (123, 7, 150), (64, 64, 64)]
+    keys = ("DiceScorePerVol", "BestDicePerVol", "BestThresholdPerVol", "AUCPerVol", "AUPRCPerVol", "l1recoErrorAll",
+            "l2recoErrorAll", "l1recoErrorUnhealthy", "l1recoErrorHealthy", "TPPerVol", "FPPerVol", "TNPerVol",
+            "FNPerVol", "HausPerVol", "lesionSizePerVol", "AnomalyScoreRecoPerVol")
+    save("tail_fullres.npz", probes=np.asarray(probes), probe_values=np.asarray([float(resized[p]) for p in probes]),
+         resized_sum=float(resized.double().sum()), resized_slice=resized[:, :, 80],
+         **{k: np.asarray([float(x) for x in host.eval_dict[k]]) for k in keys})
+    print({k: [float(x) for x in host.eval_dict[k]] for k in keys})
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     which = sys.argv[1:] or ["schedule", "simplex", "unet", "encoder", "diffusion", "tail", "test_step", "train_step", "reverse_96",
-                             "test_step_d50", "uncond_step"]
+                             "test_step_d50", "uncond_step", "ddim", "tail_fullres"]
     torch.manual_seed(0)
     for w in which:
         print(f"== {w}")

@@ -75,3 +75,13 @@ def synthetic_volume(seed: int = 0, size: int = 96, depth: int = 50):
     reco = (healthy + 0.02 * torch.randn(H, W, D, generator=g) * mask).clamp(0, 1)
     u = lambda t: t.float()[None, None].contiguous()
     return {"vol": u(vol), "mask_orig": u(mask), "seg_orig": u(seg), "reco": u(reco)}
+
+
+def synthetic_fullres_case(seed: int = 0, new_size=(160, 190, 160)):
+    """A case for full-resolution evaluation (cfg.resizedEvaluation=False, utils_eval.py:24-25): the low-resolution
+    synthetic volume's reconstruction stays [1,1,96,96,50]; vol_orig / mask_orig / seg_orig are its trilinear
+    upsamplings to `new_size` (masks re-binarised), as a datamodule would hand them over."""
+    v = synthetic_volume(seed)
+    up = lambda t: torch.nn.functional.interpolate(t, size=tuple(new_size), mode="trilinear", align_corners=True)
+    return {"reco": v["reco"], "vol_orig": up(v["vol"]).contiguous(), "mask_orig": (up(v["mask_orig"]) > 0.5).float(),
+            "seg_orig": (up(v["seg_orig"]) > 0.5).float()}

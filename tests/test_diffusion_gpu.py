@@ -126,3 +126,91 @@ def test_reverse_loop_vs_reference(monkeypatch):
     err = (rec.cpu() - torch.from_numpy(g["reverse_out"])).abs().max().item()
     print(f"reverse loop T0={T0}: max-abs {err:.4g}")
     assert err <= 1e-2
+
+
+@pytest.mark.parametrize("objective", ["pred_x0", "pred_noise"])
+def test_ddim_sample_vs_reference(objective):
+    """sample() with sampling_timesteps < timesteps -> ddim_sample (cond_DDPM.py:466-515), start_t = 300 with the
+    simplex flag: golden of the live reference (oracle/make_golden.py ddim), noise regenerated from the numpy seed."""
+    from cddpm.diffusion import GaussianDiffusion
+
+    m, _, _ = _small_model()
+    g = np.load(os.path.join(GOLD, "ddim_small_32.npz"))
+    img, cond = torch.from_numpy(g["img"]).cuda(), torch.from_numpy(g["cond"]).cuda()
+    d = GaussianDiffusion(m, image_size=(32, 32), timesteps=1000, sampling_timesteps=6, objective=objective, channels=1,
+                          loss_type="l1", p2_loss_weight_gamma=0, ddim_sampling_eta=0.7,
+                          cfg=Cfg(noisetype="simplex")).cuda()
+    assert d.is_ddim_sampling
+    np.random.seed(5)
+    rec = d.sample(cond=cond, x_start=img * 2 - 1, start_t=300, noise=True)
+    err = (rec.cpu() - torch.from_numpy(g[f"ddim_simplex_{objective}"])).abs().max().item()
+    # An iterated map: six UNet evaluations feed each other, and pred_x0 divides the prediction error by
+    # sqrt(1/acp - 1) (cond_DDPM.py:385-389).  The yardstick stored with the golden is the deviation of the SAME
+    # reference code under its configured precision (fp16 autocast, configs/trainer/default.yaml:7) from its fp32 path.
+    amp = float(g[f"ddim_simplex_{objective}_amp16_dev"])
+    print(f"ddim {objective}: max-abs {err:.4g} (reference fp16-autocast vs its fp32: {amp:.4g})")
+    assert err <= max(1e-2, 1.5 * amp)
+
+
+def test_ddim_sample_from_gaussian_start_vs_reference(monkeypatch):
+    import cddpm.diffusion as dmod
+    from cddpm.diffusion import GaussianDiffusion
+
+    m, _, _ = _small_model()
+    g = np.load(os.path.join(GOLD, "ddim_small_32.npz"))
+    img, cond = torch.from_numpy(g["img"]).cuda(), torch.from_numpy(g["cond"]).cuda()
+    d = GaussianDiffusion(m, image_size=(32, 32), timesteps=1000, sampling_timesteps=4, objective="pred_x0", channels=1,
+                          loss_type="l1", p2_loss_weight_gamma=0, ddim_sampling_eta=1.0,
+                          cfg=Cfg(noisetype="simplex")).cuda()
+    draws = [torch.zeros(2, 1, 32, 32).cuda(), torch.from_numpy(g["ddim_xT"]).cuda()]  # first draw is discarded
+    monkeypatch.setattr(dmod, "_randn", lambda shape, device: draws.pop(0))
+    np.random.seed(6)
+    rec = d.sample(cond=cond, x_start=img * 2 - 1, start_t=0, noise=None)
+    assert not draws
+    err = (rec.cpu() - torch.from_numpy(g["ddim_gauss_start"])).abs().max().item()
+    print(f"ddim from x_T: max-abs {err:.4g}")
+    assert err <= 1e-2
+
+
+def test_p_sample_clip_denoised_flag_vs_reference(monkeypatch):
+    import cddpm.diffusion as dmod
+    from cddpm.diffusion import GaussianDiffusion
+
+    m, _, _ = _small_model()
+    g = np.load(os.path.join(GOLD, "ddim_small_32.npz"))
+    cond = torch.from_numpy(g["cond"]).cuda()
+    x, nz = torch.from_numpy(g["noclip_x"]).cuda(), torch.from_numpy(g["noclip_noise"]).cuda()
+    d = GaussianDiffusion(m, image_size=(32, 32), timesteps=1000, sampling_timesteps=1000, objective="pred_x0",
+                          channels=1, loss_type="l1", p2_loss_weight_gamma=0, cfg=Cfg(noisetype="simplex")).cuda()
+    monkeypatch.setattr(dmod, "_randn", lambda shape, device: nz)
+    for key, clip in (("noclip_out", False), ("clip_out", True)):
+        out = d.p_sample(x.clone(), 400, clip_denoised=clip, cond=cond, noise=None)
+        err = (out.cpu() - torch.from_numpy(g[key])).abs().max().item()
+        print(f"p_sample clip_denoised={clip}: max-abs {err:.4g}")
+        assert err <= 1e-3  # coef1[400] = 3.7e-3 scales the model error
+
+
+def test_out_of_range_timesteps_raise_like_the_reference():
+    """The reference indexes its schedule buffers with t (IndexError outside [0, T)); the kernels read raw pointers, so
+    the host checks."""
+    from cddpm.diffusion import GaussianDiffusion
+
+    m, _, _ = _small_model()
+    d = GaussianDiffusion(m, image_size=(32, 32), timesteps=1000, objective="pred_x0", channels=1,
+                          cfg=Cfg(noisetype="simplex")).cuda()
+    img = torch.rand(2, 1, 32, 32).cuda()
+    cond = torch.randn(2, 128).cuda()
+    with pytest.raises(IndexError):
+        d(img, cond=cond, t=1000)
+    with pytest.raises(IndexError):
+        d(img, cond=cond, t=-1)
+    with pytest.raises(IndexError):  # start_t=0 -> q_sample at index num_timesteps (cond_DDPM.py:452)
+        d.sample(cond=cond, x_start=img * 2 - 1, start_t=0, noise=True)
+    # broadcast-shaped noise is expanded once for q_sample and the finishing kernels (pred_noise reads it again)
+    dn = GaussianDiffusion(m, image_size=(32, 32), timesteps=1000, objective="pred_noise", channels=1,
+                           cfg=Cfg(noisetype="simplex")).cuda()
+    nz = torch.randn(1, 1, 32, 32).cuda()
+    with torch.no_grad():
+        l1, r1 = dn(img, cond=cond, t=100, noise=nz)
+        l2, r2 = dn(img, cond=cond, t=100, noise=nz.expand(2, 1, 32, 32).contiguous())
+    assert torch.equal(r1, r2) and torch.equal(l1, l2)

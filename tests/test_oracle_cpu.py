@@ -266,3 +266,28 @@ def test_ports_reproduce_headline_geometry_goldens():
         rec = diffusion_port.reverse_loop(lambda a, t, c: unet_port.unet_forward(sd, spec, a, t, c), sched, x * 2 - 1,
                                           cond, 50, lambda: gen_noise_port((2, 1, 96, 96)))
         assert (rec - torch.from_numpy(g["out_T50"])).abs().max().item() <= 1e-5
+
+
+def test_ddim_port_matches_reference_golden():
+    """oracle.diffusion_port.ddim_sample against the live reference's ddim_sample (tests/golden/ddim_small_32.npz)."""
+    from oracle import diffusion_port, unet_port
+    from oracle.simplex_port import gen_noise_port
+    from oracle.weights import make_state_dict
+
+    g = np.load(os.path.join(GOLD, "ddim_small_32.npz"))
+    spec = unet_port.UNetSpec(model_channels=64, channel_mult=(1, 2), num_res_blocks=1, num_classes=128)
+    sd = make_state_dict(unet_port.param_shapes(spec), seed=2)
+    model = lambda x, t, c: unet_port.unet_forward(sd, spec, x, t, c)  # noqa: E731
+    sched = diffusion_port.schedule_buffers()
+    img, cond = torch.from_numpy(g["img"]), torch.from_numpy(g["cond"])
+    with torch.no_grad():
+        for objective in ("pred_x0", "pred_noise"):
+            np.random.seed(5)
+            rec = diffusion_port.ddim_sample(model, sched, (2, 1, 32, 32), img * 2 - 1, cond, 300, 6, 0.7, True,
+                                             lambda: gen_noise_port((2, 1, 32, 32)), None, objective=objective)
+            assert (rec - torch.from_numpy(g[f"ddim_simplex_{objective}"])).abs().max().item() < 1e-4
+        draws = [torch.zeros(2, 1, 32, 32), torch.from_numpy(g["ddim_xT"])]
+        np.random.seed(6)
+        rec = diffusion_port.ddim_sample(model, sched, (2, 1, 32, 32), img * 2 - 1, cond, 0, 4, 1.0, None,
+                                         lambda: gen_noise_port((2, 1, 32, 32)), lambda: draws.pop(0))
+        assert (rec - torch.from_numpy(g["ddim_gauss_start"])).abs().max().item() < 1e-4

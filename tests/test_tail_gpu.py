@@ -296,3 +296,43 @@ def test_error_sums_are_run_to_run_identical_and_match_float64():
     assert runs[0][6] == want[6]
     for got, w in zip(runs[0][:6], want[:6]):
         assert abs(got - w) <= 1e-9 * max(1.0, abs(w))
+
+
+def test_full_resolution_evaluation_vs_reference_golden():
+    """cfg.resizedEvaluation=False (utils_eval.py:24-25): the [96,96,50] reconstruction is resized to new_size =
+    [160,190,160] (trilinear, align_corners=True) on the GPU and scored against full-resolution originals.  Golden of the
+    live reference (oracle/make_golden.py tail_fullres).  The resize is compared at 1e-6 (fp32 fused-multiply-add
+    contraction on the host is not specified), thresholds / Dice / counts exactly as far as the resize allows."""
+    from cddpm import eval_tail
+    from oracle.weights import synthetic_fullres_case
+
+    g = np.load(os.path.join(GOLD, "tail_fullres.npz"))
+    c = synthetic_fullres_case(4)
+    # the reconstruction as the UNet hands it over: a permuted [D,1,H,W] view, read in place
+    reco_dchw = c["reco"][0, 0].permute(2, 0, 1).unsqueeze(1).contiguous().cuda()
+    final = reco_dchw.squeeze(1).permute(1, 2, 0).unsqueeze(0).unsqueeze(0)
+    resized = eval_tail.trilinear_resize(final, [160, 190, 160])
+    assert tuple(resized.shape) == (1, 1, 160, 190, 160) and resized.is_contiguous()
+    r = resized[0, 0].cpu()
+    for p, v in zip(g["probes"], g["probe_values"]):
+        assert abs(float(r[tuple(int(i) for i in p)]) - float(v)) <= 1e-6, (p, v)
+    assert (r[:, :, 80] - torch.from_numpy(g["resized_slice"])).abs().max().item() <= 1e-6
+    assert abs(float(r.double().sum()) - float(g["resized_sum"])) <= 1e-6 * abs(float(g["resized_sum"]))
+    # end points are copied exactly (align_corners)
+    assert float(r[0, 0, 0]) == float(c["reco"][0, 0, 0, 0, 0]) and float(r[-1, -1, -1]) == float(c["reco"][0, 0, -1, -1, -1])
+
+    h = _host("val")
+    h.cfg = _cfg(resizedEvaluation=False)
+    h.new_size = [160, 190, 160]
+    eval_tail._test_step(h, final, c["vol_orig"].cuda(), c["seg_orig"].cuda(), c["mask_orig"].cuda(), 0, ["v4"],
+                         torch.tensor([1]))
+    ed = h.eval_dict
+    print({k: float(ed[k][0]) for k in ("DiceScorePerVol", "BestThresholdPerVol", "AUPRCPerVol", "TPPerVol", "HausPerVol")})
+    for k in ("DiceScorePerVol", "BestDicePerVol", "AUCPerVol", "AUPRCPerVol", "l1recoErrorAll", "l2recoErrorAll",
+              "l1recoErrorUnhealthy", "l1recoErrorHealthy", "AnomalyScoreRecoPerVol"):
+        assert abs(float(ed[k][0]) - float(g[k][0])) <= 1e-5, (k, ed[k][0], g[k][0])
+    assert abs(float(ed["BestThresholdPerVol"][0]) - float(g["BestThresholdPerVol"][0])) <= 1e-6
+    assert float(ed["lesionSizePerVol"][0]) == float(g["lesionSizePerVol"][0])
+    assert float(ed["HausPerVol"][0]) == float(g["HausPerVol"][0])
+    for k in ("TPPerVol", "FPPerVol", "TNPerVol", "FNPerVol"):  # 4.86 M voxels; a 1-ulp resize difference may flip a few
+        assert abs(float(ed[k][0]) - float(g[k][0])) <= 5, (k, ed[k][0], g[k][0])
