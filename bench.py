@@ -317,6 +317,26 @@ def run_ours(args):
         gathered = [torch.empty_like(score) for _ in range(world)]
         dist.all_gather(gathered, score)
     dt_ms, e2e_ms = float(t[0]), float(t[1])
+
+    # ---------------- sub-records (every rank takes part: the volume / sweep workloads carry collectives)
+    extras = {}
+    if not args.no_extras:
+        import copy
+
+        sub = copy.copy(args)
+        sub.steps, sub.warmup, sub.no_cpu_baseline = 2, 3, True
+        if world == 1:
+            extras["forward"] = forward_latency(unet, dev)
+            try:
+                extras["gpu_eager_baseline"] = gpu_eager_sample(B, T0, dev)
+            except Exception as e:  # a baseline leg must never take the bench line down
+                extras["gpu_eager_baseline"] = {"unavailable": repr(e)[:200]}
+        sub.batch = 8
+        extras["volume"] = run_volume(sub, sub=True)
+        sub.batch = 64
+        extras["train"] = run_train(sub, sub=True)
+        if world > 1:
+            extras["sweep"] = sweep_record(args, dev, world, rank)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -331,9 +351,11 @@ def run_ours(args):
     achieved = conv_flops_fwd / (conv_ms_fwd / 1e3) / 1e12
     enc_launches = 1 + 1 + 16 * 4 + 4 + 3 + 2  # stem, pool, (3 GEMM + im2col) x 16 blocks, 4 downsample GEMMs, 3 strided gathers, pool + fc
     launches_per_step = enc_launches + 2 + T0 * (eng.launches_per_forward + 2)
-    # traffic: dram__bytes_read.sum + dram__bytes_write.sum summed over the convolution launches of one B=32 forward
-    # (ncu, profiles/r01_v5_conv_dram.csv: 5.23 GB over 61 launches), per launch like `achieved`
-    traffic = 85.7e6 * B / 32
+    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of the 57 timed launches of one B=32 forward at HEAD (ncu --set
+    # full, profiles/r02_v1_ncu_conv.csv: 56 conv_igemm2 launches, 4.664 GB read + 0.608 GB written; + the FiLM GEMM,
+    # profiles/r02_v1_ncu_misc.csv: 24.3 MB) = 5.296 GB -> 92.9 MB per launch, like `achieved`.  Algorithmic bytes of the
+    # same launches (every operand read once, every result written once, 16-bit): 5.21 GB.
+    traffic = 92.9e6 * B / 32
     roofline = {"bound": "tensor",
                 "kernel": "conv_igemm2_kernel / conv_igemm_kernel (tcgen05 implicit GEMM: every convolution and GEMM launch "
                           "of a UNet forward)",
@@ -352,6 +374,12 @@ def run_ours(args):
                     "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
             "single_step_equiv_slices_per_s": value * T0}
+    if extras:
+        def brief(rec):  # the sub-records keep their own roofline / e2e / clocks; drop the long prose
+            if not isinstance(rec, dict):
+                return rec
+            return {k: v for k, v in rec.items() if k not in ("higher_is_better", "vs_baseline", "data", "scaling")}
+        line["extras"] = {k: brief(v) for k, v in extras.items()}
     if world == 1 and not args.no_cpu_baseline:
         threads = host_threads()
         v, parts, bb = best_cpu_sample(T0, threads, 2)
@@ -361,6 +389,193 @@ def run_ours(args):
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------- sub-records
+def gpu_eager_sample(B, T0, dev, rev_steps=10):
+    """SURVEY.md §8(d) "the real bar": the reference's own op sequence as eager PyTorch on THIS GPU - the oracle's
+    restatement of UNetModel.forward / the reverse loop (/root/reference does not exist on the GPU box) with the weights
+    on the device, torch.autocast(float16) (the reference's `precision: 16`), cudnn.benchmark, channels-last left to
+    cuDNN.  `rev_steps` reverse steps of batch B, device-timed, extrapolated to the T0-step loop.  A reported baseline
+    (like cpu_baseline), never the product path."""
+    import numpy as np
+    import torch
+
+    from oracle import diffusion_port, resnet_port, unet_port
+    from oracle.weights import make_state_dict
+
+    prev = torch.backends.cudnn.benchmark
+    torch.backends.cudnn.benchmark = True
+    try:
+        spec = unet_port.UNetSpec()
+        sd = {k: v.to(dev) for k, v in make_state_dict(unet_port.param_shapes(spec), seed=1).items()}
+        esd = {k: v.to(dev) for k, v in make_state_dict(resnet_port.param_shapes(128), seed=3).items()}
+        sched = {k: v.to(dev) for k, v in diffusion_port.schedule_buffers().items()}
+        x = torch.rand(B, 1, 96, 96, device=dev)
+        g = torch.Generator(device=dev).manual_seed(0)
+        noise_fn = lambda: torch.randn(1, 1, 96, 96, device=dev, generator=g).expand(B, 1, 96, 96).half()  # noqa: E731
+        model = lambda xt, t, c: unet_port.unet_forward(sd, spec, xt, t, c).float()  # noqa: E731
+
+        def loop(n):
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+                cond = resnet_port.resnet_forward(esd, x).float()
+                return diffusion_port.reverse_loop(model, sched, x * 2 - 1, cond, n, noise_fn)
+
+        loop(3)  # cudnn.benchmark picks its algorithms here
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        loop(rev_steps)
+        e1.record()
+        torch.cuda.synchronize()
+        per_step_ms = e0.elapsed_time(e1) / rev_steps
+    finally:
+        torch.backends.cudnn.benchmark = prev
+    del np
+    return {"value": B / (per_step_ms * T0 / 1e3), "unit": "slices/s", "ms_per_reverse_step": per_step_ms,
+            "kind": "oracle port of the reference's op sequence, eager PyTorch on this GPU (fp16 autocast, cuDNN/cuBLAS, "
+                    "cudnn.benchmark)",
+            "sample": f"batch {B}: encoder + {rev_steps} reverse steps device-timed, extrapolated to the {T0}-step loop"}
+
+
+def forward_latency(unet, dev, batches=(1, 8, 32)):
+    """Device-timed UNet forward at several batch sizes (the small-batch regime of SURVEY.md §7)."""
+    import torch
+
+    out = {}
+    for B in batches:
+        x = torch.randn(B, 1, 96, 96, device=dev)
+        t = torch.full((B,), 499, device=dev, dtype=torch.long)
+        c = torch.randn(B, 128, device=dev)
+        with torch.no_grad():
+            for _ in range(4):
+                unet(x, t, cond=c)
+            torch.cuda.synchronize()
+            n = 50 if B < 16 else 20
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                unet(x, t, cond=c)
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        out[f"B{B}"] = {"ms": ms, "slices_per_s": B / ms * 1e3, "tflops": UNET_GFLOP * B / ms}
+    return out
+
+
+def sweep_record(args, dev, world, rank, vols_per_gpu=16):
+    """BASELINE configs[3] inside the driver's record: cddpm.sweep.test_sweep (validation stage, then test stage) over
+    `vols_per_gpu` x world synthetic volumes dealt round-robin to the ranks, WITH its collectives inside the timed region
+    (all-gather of the per-volume result lists per stage, all-reduced counts of the global Dice-threshold bisection),
+    device-timed (CUDA events between barriers, max over ranks); then rank 0 repeats the sweep alone on all volumes and
+    compares every per-volume entry.  The simplex noise of a volume is seeded from its index (the reference draws from
+    numpy's global stream, which a sharded run cannot share)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from cddpm import eval_tail, sweep
+    from cddpm.ddpm_2d import DDPM_2D
+
+    keys = ("IDs", "DiceScorePerVol", "BestDicePerVol", "BestThresholdPerVol", "AUCPerVol", "AUPRCPerVol", "HausPerVol",
+            "TPPerVol", "FPPerVol", "TNPerVol", "FNPerVol", "AnomalyScoreRecoPerVol", "AnomalyScoreRegPerVol",
+            "l1recoErrorAll", "lesionSizePerVol")
+    nvol = vols_per_gpu * world
+    torch.manual_seed(1234)  # identical replicas
+    cfg = model_cfg()
+    cfg["force_num_eval_slices"] = False
+    model = DDPM_2D(cfg, prefix="sweep/")
+    with torch.no_grad():
+        for _, p in model.named_parameters():
+            if p.dim() >= 2 and float(p.abs().sum()) == 0.0:
+                p.normal_(0.0, 1.0 / p[0].numel() ** 0.5)
+    model = model.to(dev).eval()
+    inner = model.test_step_reconstruct
+
+    def seeded(batch):
+        np.random.seed(5000 + int(batch["ID"][0][1:]))
+        return inner(batch)
+
+    model.test_step_reconstruct = seeded
+
+    def loader(stage, first):
+        out = []
+        for i in range(first, first + nvol):
+            if i % world == rank or rank == 0:  # rank 0 keeps everything for the one-process check
+                v = synthetic_volume(i % 24, 50)  # 24 distinct cases, reused
+                out.append({"Dataset": ["Brats21"], "vol": {"data": v["vol"]}, "vol_orig": {"data": v["vol"]},
+                            "seg_orig": {"data": v["seg_orig"]}, "mask_orig": {"data": v["mask_orig"]},
+                            "seg_available": True, "ID": [f"v{i}"], "stage": stage, "label": torch.tensor([1])})
+            else:
+                out.append(None)
+        return out
+
+    sets = {"Datamodules_eval.Brats21": (loader("val", 0), loader("test", 1000))}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sweep.test_sweep(model, sets, pickle_preds=False)  # plans, graph captures, communicator warm-up
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    preds, _ = sweep.test_sweep(model, sets, pickle_preds=False)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_sharded = float(t[0])
+    # the collectives alone: one all-gather of result lists per stage + the bisection's all-reduces, timed on a dummy
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    g0.record()
+    if world > 1:
+        payload = {k: list(v) for k, v in preds["val"]["Datamodules_eval.Brats21"].items() if type(v) is list}
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (vols_per_gpu, {k: v[:vols_per_gpu] for k, v in payload.items()}))
+        cnt = torch.zeros(9, dtype=torch.int64, device=dev)
+        for _ in range(10):
+            dist.all_reduce(cnt)
+    g1.record()
+    barrier()
+    gather_ms = g0.elapsed_time(g1)
+    rec = None
+    if rank == 0:
+        saved = (sweep._world, eval_tail._dist_sum, eval_tail._dist_max)
+        sweep._world = lambda: (0, 1)
+        eval_tail._dist_sum = eval_tail._dist_max = lambda t: None
+        try:
+            h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            h0.record()
+            preds1, _ = sweep.test_sweep(model, sets, pickle_preds=False)
+            h1.record()
+            torch.cuda.synchronize()
+            ms_serial = h0.elapsed_time(h1)
+        finally:
+            sweep._world, eval_tail._dist_sum, eval_tail._dist_max = saved
+        bad = []
+        for stage in ("val", "test"):
+            a, b = preds[stage]["Datamodules_eval.Brats21"], preds1[stage]["Datamodules_eval.Brats21"]
+            for k in keys:
+                xa, xb = list(a[k]), list(b[k])
+                if not (len(xa) == len(xb) and all(x == y or (x != x and y != y) for x, y in zip(xa, xb))):
+                    bad.append(f"{stage}/{k}")
+            for k in ("DicePerVolMean", "AUPRCPerVolMean", "HausPerVolMean"):
+                if not (a[k] == b[k] or (a[k] != a[k] and b[k] != b[k])):
+                    bad.append(f"{stage}/{k}")
+        v = preds["val"]["Datamodules_eval.Brats21"]
+        rec = {"metric": "volumes/sec of the sharded test sweep (validation + test stage, full tail, NCCL collectives inside "
+                         "the timed region)",
+               "value": 2 * nvol / (ms_sharded / 1e3), "unit": "volumes/s", "n_gpus": world, "volumes": 2 * nvol,
+               "volumes_per_gpu_per_stage": vols_per_gpu, "ms": ms_sharded, "collectives_ms": gather_ms,
+               "one_process_volumes_per_s": 2 * nvol / (ms_serial / 1e3), "equals_one_process_result": not bad,
+               "mismatches": bad[:8], "val_DicePerVolMean": float(v["DicePerVolMean"]),
+               "val_AUPRCPerVolMean": float(v["AUPRCPerVolMean"])}
+    barrier()
+    return rec
 
 
 # ---------------------------------------------------------------------------------------------- training workload
@@ -384,7 +599,7 @@ def cpu_train_sample(threads: int):
     return 1.0 / (time.perf_counter() - t0)
 
 
-def run_train(args):
+def run_train(args, sub=False):
     """BASELINE.json configs[4] (not the headline line): `python bench.py --workload train [--batch 64]`."""
     import numpy as np
     import torch
@@ -397,7 +612,7 @@ def run_train(args):
         raise SystemExit("bench.py needs a CUDA device: the cDDPM engine has no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
+    if world > 1 and not sub:
         dist.init_process_group("nccl", device_id=dev)
     from cddpm.ddpm_2d import DDPM_2D
     from cddpm.dist_train import sync_gradients
@@ -478,9 +693,9 @@ def run_train(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dt_ms, e2e_ms = float(t[0]), float(t[1])
     if rank != 0:
-        if world > 1:
+        if world > 1 and not sub:
             dist.destroy_process_group()
-        return
+        return None
     pk = peaks()
     flops = (eng.conv_flops_per_sample + eng.bwd_flops_per_sample) * B
     achieved = flops / (unet_ms / 1e3) / 1e12
@@ -500,16 +715,19 @@ def run_train(args):
             "e2e": {"value": slices / (e2e_ms / 1e3), "unit": "slices/s", "h2d_bytes_per_step": x_host.numel() * 4,
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": (eng.launches_per_forward + int(lib_bwd_launches(eng))) * args.steps, "clocks": clocks}
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not sub:
         threads = host_threads()
         cpu_train_sample(threads)
         v = max(cpu_train_sample(threads) for _ in range(2))
         line["cpu_baseline"] = {"value": v, "unit": "slices/s", "cores": threads, "kind": "port",
                                 "sample": "oracle port (fp32 PyTorch autograd) on the host: UNet forward + backward of one "
                                           "slice, best of 2 after a warm-up"}
+    if sub:
+        return line
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+    return line
 
 
 # ---------------------------------------------------------------------------------------------- volume workload
@@ -557,7 +775,7 @@ def cpu_volume_sample(depth: int, threads: int):
     return 1.0 / (t_model + t_tail), {"t_model_s": t_model, "t_tail_s": t_tail}
 
 
-def run_volume(args):
+def run_volume(args, sub=False):
     """BASELINE.json configs[2] (not the headline line): `python bench.py --workload volume [--batch 8]`: per step,
     `batch` synthetic BraTS21-shaped [1,1,96,96,50] volumes per GPU through the validation stage of the test sweep
     (on_test_start, test_step per volume, on_test_end with the global threshold search)."""
@@ -572,7 +790,7 @@ def run_volume(args):
         raise SystemExit("bench.py needs a CUDA device: the cDDPM engine has no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
+    if world > 1 and not sub:
         dist.init_process_group("nccl", device_id=dev)
     from cddpm.ddpm_2d import DDPM_2D
     from cddpm.sweep import run_stage
@@ -629,13 +847,11 @@ def run_volume(args):
     barrier()
     e0.record()
     for it in range(args.steps):
-        if it == 0:
-            eng.profile_arm()  # the first UNet forward of the first step is bracketed per convolution launch
+        eng.profile_arm()  # the first UNet forward of EVERY step is bracketed per convolution launch (median reported)
         thr, ed = step(resident)
-        if it == 0:
-            ms, n = eng.profile_read()
-            conv_ms.append(ms)
-            conv_launches = n
+        ms, n = eng.profile_read()
+        conv_ms.append(ms)
+        conv_launches = n
     e1.record()
     barrier()
     dt_ms = e0.elapsed_time(e1)
@@ -653,9 +869,9 @@ def run_volume(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dt_ms, e2e_ms = float(t[0]), float(t[1])
     if rank != 0:
-        if world > 1:
+        if world > 1 and not sub:
             dist.destroy_process_group()
-        return
+        return None
     vols = NV * world * args.steps
     pk = peaks()
     # the 3-member noise ensemble of a volume is ONE UNet forward over the 3 x D stacked slices unless the reference's
@@ -680,7 +896,7 @@ def run_volume(args):
                        "ensemble": ("one UNet forward over the 3 x D stacked slices" if stacked else "one UNet forward per member"),
                        "l2": f"streaming working set ~{0.06 * fwd_batch:.0f} GB per B={fwd_batch} UNet forward >> 126 MB L2 (no flush needed)"},
             "roofline": {"bound": "tensor", "kernel": "conv_igemm2_kernel / conv_igemm_kernel (every convolution and GEMM "
-                                                       f"launch of the first B={fwd_batch} UNet forward of a step)",
+                                                       f"launch of the first B={fwd_batch} UNet forward of each step, median over steps)",
                          "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
                          "peak_source": pk["source"], "flops_per_launch": conv_flops_fwd / max(1, conv_launches),
                          "avg_launch_ms": conv_ms_fwd / max(1, conv_launches), "launches_timed": conv_launches * len(conv_ms),
@@ -691,16 +907,19 @@ def run_volume(args):
             "gpu_launches": per_volume * NV * args.steps, "clocks": clocks,
             "slices_per_s": vols * D / (dt_ms / 1e3), "unet_slice_evaluations_per_s": vols * D * 3 / (dt_ms / 1e3),
             "val_threshold": thr}
-    if not args.no_cpu_baseline and world == 1:
+    if not args.no_cpu_baseline and world == 1 and not sub:
         threads = host_threads()
         v, parts = cpu_volume_sample(D, threads)
         line["cpu_baseline"] = {"value": v, "unit": "volumes/s", "cores": threads, "kind": "port",
                                 "sample": "oracle port (fp32 PyTorch + numpy/scipy) on the host: encoder + 3 ensemble "
                                           f"reconstructions of 2 slices extrapolated to {D}, plus the full tail of one volume",
                                 **parts}
+    if sub:
+        return line
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+    return line
 
 
 def lib_bwd_launches(eng):
@@ -738,6 +957,9 @@ def main():
                          "volumes per GPU per step); train = configs[4]")
     ap.add_argument("--start-t", dest="start_t", type=int, default=500)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the sub-records of the headline line (configs[2] volume, configs[4] train, the eager-GPU "
+                         "baseline, the forward latencies; at N > 1 the configs[3] sharded sweep)")
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"],
                     help="16-bit storage / tensor-core operand type of the inference engines (reverse, volume); fp32 "
                          "accumulation either way.  The reference runs fp16 autocast (trainer/default.yaml:7); training is "

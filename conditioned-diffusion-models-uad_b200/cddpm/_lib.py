@@ -106,6 +106,13 @@ def _signatures(c):
         "cddpm_row_stats": (i32, [vp, pview, pview, i32, i32, i32, f32, vp, vp, vp]),
         "cddpm_ranking_workspace_bytes": (i64, [i64]),
         "cddpm_ranking_metrics": (i32, [vp, pview, i32, i32, i32, vp, i64, vp, vp]),
+        "cddpm_dice_bisect": (i32, [vp, i64, i32, vp, vp]),
+        "cddpm_crop_or_pad": (i32, [vp, i32, i32, i32, vp, i32, i32, i32, f32, vp]),
+        "cddpm_rescale_workspace_bytes": (i64, [i64]),
+        "cddpm_rescale_intensity": (i32, [vp, vp, i64, c.c_double, c.c_double, f32, f32, vp, i64, vp, vp]),
+        "cddpm_resample_size": (i32, [i32, c.c_double]),
+        "cddpm_resample_workspace_bytes": (i64, [i32, i32, i32]),
+        "cddpm_resample": (i32, [vp, i32, i32, i32, c.c_double, c.c_double, c.c_double, i32, vp, vp, i64, vp]),
         "cddpm_filter_small_components": (i32, [vp, vp, i32, i32, i32, i32, vp]),
         "cddpm_confusion_counts": (i32, [vp, pview, i32, i32, i32, vp, vp]),
         "cddpm_hausdorff_workspace_bytes": (i64, [i32, i32, i32]),

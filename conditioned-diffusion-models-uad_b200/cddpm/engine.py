@@ -40,6 +40,13 @@ class UNetEngine:
         if self.training:
             check(lib().cddpm_unet_set_training(self._h, 1), "cddpm_unet_set_training")
 
+    def set_training(self, on: bool) -> None:
+        """Switch between a training engine (keeps the intermediates backward() reads) and an inference engine (may
+        fuse them away).  Switching drops the current plan; a no-op when the mode does not change."""
+        if bool(on) != self.training:
+            check(lib().cddpm_unet_set_training(self._h, 1 if on else 0), "cddpm_unet_set_training")
+            self.training = bool(on)
+
     def __del__(self):
         h = getattr(self, "_h", None)
         if h is not None and h.value:

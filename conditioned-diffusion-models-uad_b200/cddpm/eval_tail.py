@@ -15,6 +15,7 @@ confusion-matrix names are permuted (:108), fpr() is FP/(FP+TP) (:572-575).
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -318,6 +319,42 @@ def _ranking_volume(v: _Volume) -> Tuple[float, float]:
     return float(r[0]), float(r[1])
 
 
+def _numpy_weak_scalars() -> bool:
+    """True when NumPy keeps float32 scalars float32 in arithmetic with Python floats (NEP 50, NumPy >= 2) - the
+    semantics the device-side bisection implements."""
+    return (np.float32(3.0) * 0.5).dtype == np.float32
+
+
+def _ranking_and_bisect(v: _Volume, max_steps: int = 10):
+    """AUC, AUPRC (compute_roc / compute_prc) and find_best_val(val_range=(0, max), max_steps) of one volume with ONE
+    host read: the bisection runs on the device over the ranking pass's sorted scores (cddpm_dice_bisect) - no pass over
+    the volume per step, no host round trip per step.  Returns (AUC, AUPRC, bestDice, bestThresh)."""
+    if not _numpy_weak_scalars() or os.environ.get("CDDPM_DEVICE_BISECT", "1") == "0":
+        auc, auprc = _ranking_volume(v)
+        top = _device_max([v])
+        best, thr = _bisect(lambda qs: _counts([v], qs), (0, top), max_steps)
+        return auc, auprc, best, thr
+    H, W, D = v.shape
+    n = H * W * D
+    dev = v.diff.device
+    with torch.cuda.device(dev):
+        nbytes = int(lib().cddpm_ranking_workspace_bytes(n))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        res = torch.empty(5, dtype=torch.float64, device=dev)
+        sv = v.seg_view
+        check(lib().cddpm_ranking_metrics(ptr(v.diff), ctypes.byref(sv), H, W, D, ptr(ws), nbytes, ptr(res),
+                                          current_stream()), "cddpm_ranking_metrics")
+        check(lib().cddpm_dice_bisect(ptr(ws), n, int(max_steps), ptr(res[2:]), current_stream()), "cddpm_dice_bisect")
+    r = res.cpu().numpy()
+    # the reference returns the ints (0, 0) when no step improved on max_val = 0 (all-NaN Dice: empty prediction and
+    # empty label); otherwise a float64 Dice and a float32 threshold - a Python float when max(x) == 0 sent the range
+    # arithmetic through the Python ints (0, 1)
+    if r[2] == 0 and r[3] == 0:
+        return float(r[0]), float(r[1]), 0, 0
+    thr = float(r[3]) if r[4] == 0 else np.float32(r[3])
+    return float(r[0]), float(r[1]), r[2], thr
+
+
 def tpr(P, G):
     tp = np.sum(np.multiply(P.flatten(), G.flatten()))
     fn = np.sum(np.multiply(np.invert(P.flatten()), G.flatten()))
@@ -440,9 +477,7 @@ def _test_step(self, final_volume, data_orig, data_seg, data_mask, batch_idx, ID
     dev = vol.diff.device
     best_thresh = None
     if cfg.evalSeg and self.dataset[0] not in self.healthy_sets:
-        AUC, AUPRC = _ranking_volume(vol)
-        top = _device_max([vol])
-        bestDice, bestThresh = _bisect(lambda qs: _counts([vol], qs), (0, top), 10)
+        AUC, AUPRC, bestDice, bestThresh = _ranking_and_bisect(vol, 10)
         if "test" in self.stage:
             bestThresh = self.threshold["total"]
         thr = bestThresh if cfg["threshold"] == "auto" else cfg["threshold"]

@@ -270,7 +270,11 @@ class UNetModel(nn.Module):
             if self._engine_versions is not None:
                 for i in range(len(self._engine_versions)):
                     self._engine_versions[i] = None  # see below: always push in training
-            return self.engine()
+            eng = self.engine()
+            # the shared bf16 engine must keep every intermediate the backward pass reads: no inference-only fusions
+            # (the head's GroupNorm inside conv_out) once it has served a training step
+            eng.set_training(True)
+            return eng
         items = self._param_items()
         if items[0][1].device.type != "cuda":
             raise CddpmError("UNetModel is on the CPU; the cDDPM engine has no CPU path — move the module to CUDA")

@@ -10,6 +10,7 @@
 #include "elementwise.cuh"
 #include "resnet_engine.cuh"
 #include "simplex.cuh"
+#include "preprocess.cuh"
 #include "tail.cuh"
 #include "unet_engine.cuh"
 
@@ -305,6 +306,9 @@ int cddpm_ranking_metrics(const float* x_dhw, const cddpm_vol_view* seg, int H, 
   return launch_ranking_metrics(x_dhw, to_view(seg), H, W, D, workspace, static_cast<size_t>(workspace_bytes), result,
                                 static_cast<cudaStream_t>(stream));
 }
+int cddpm_dice_bisect(const void* ranking_workspace, int64_t n, int max_steps, double* result, void* stream) {
+  return launch_dice_bisect(ranking_workspace, n, max_steps, result, static_cast<cudaStream_t>(stream));
+}
 int cddpm_filter_small_components(const uint8_t* mask_dhw, uint8_t* out_dhw, int H, int W, int D, int max_size,
                                   void* stream) {
   return launch_filter_small_components(mask_dhw, out_dhw, H, W, D, max_size, static_cast<cudaStream_t>(stream));
@@ -414,6 +418,33 @@ int64_t cddpm_attention_bwd_scratch_bytes(int B, int L, int C) { return attentio
 int cddpm_attention_bwd(const void* qkv, const void* dout, void* dqkv, void* scratch, int B, int L, int C, int fmt,
                         void* stream) {
   return launch_attention_bwd(qkv, dout, dqkv, scratch, B, L, C, fmt, static_cast<cudaStream_t>(stream));
+}
+
+int cddpm_crop_or_pad(const float* in, int H, int W, int D, float* out, int h, int w, int d, float pad_value,
+                      void* stream) {
+  return launch_crop_or_pad(in, H, W, D, out, h, w, d, pad_value, static_cast<cudaStream_t>(stream));
+}
+int64_t cddpm_rescale_workspace_bytes(int64_t n) {
+  if (n < 1 || n > (1ll << 30)) return 0;
+  return static_cast<int64_t>(rescale_workspace_bytes(n));
+}
+int cddpm_rescale_intensity(float* vol, const float* mask, int64_t n, double perc_low, double perc_high, float out_min,
+                            float out_max, void* workspace, int64_t workspace_bytes, double* cutoffs, void* stream) {
+  return launch_rescale_intensity(vol, mask, n, perc_low, perc_high, out_min, out_max, workspace,
+                                  static_cast<size_t>(workspace_bytes), cutoffs, static_cast<cudaStream_t>(stream));
+}
+int cddpm_resample_size(int source, double factor) {
+  int t = 0;
+  resample_size(source, factor, &t);
+  return t;
+}
+int64_t cddpm_resample_workspace_bytes(int H, int W, int D) {
+  return static_cast<int64_t>(resample_workspace_bytes(H, W, D));
+}
+int cddpm_resample(const float* in, int H, int W, int D, double fy, double fx, double fz, int bspline, float* out,
+                   void* workspace, int64_t workspace_bytes, void* stream) {
+  return launch_resample(in, H, W, D, fy, fx, fz, bspline, out, workspace, static_cast<size_t>(workspace_bytes),
+                         static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -69,12 +69,21 @@ struct Geo {
   static constexpr int kSmemBytes = kStagesA * kASlotBytes + kStagesB * kBSlotBytes + 256 + kStatBytes + kCoefBytes + 1024;
 };
 
+constexpr int kMaxChunks = 48;  // 64-channel chunks of one work item over all sources (K <= 3072 per source set)
 struct Conv2Params {
-  CUtensorMap tmap_a[kConvMaxSrc];  // {C, W, H, B}; box {64, 18, 18, 1}
+  CUtensorMap tmap_a[kConvMaxSrc];  // {C, W, H, B}; box {64, 18, 18, 1} (3x3 sources) or {64, 16, 16, 1} (1x1 sources)
   CUtensorMap tmap_b;               // {Ktot, Cout}; box {64, 64}
   int num_src;
   int src_c[kConvMaxSrc];
   int src_taps[kConvMaxSrc];
+  int src_koff[kConvMaxSrc];        // first K column of each source in the packed weight panel
+  // The order in which the 64-channel chunks of a work item are staged and multiplied: all three roles (weight
+  // producer, tile producer, MMA issuer) walk this list.  1x1 chunks (8 MMAs of tensor time for a whole tile of
+  // traffic) are spread between the 3x3 chunks so the tile ring never drains on them.
+  int num_chunks;
+  uint8_t chunk_src[kMaxChunks];
+  uint8_t chunk_ch[kMaxChunks];
+  int box1;  // 1x1 sources stage the bare 16-row tile (no halo)
   int B, H, W, Cout;
   int tiles_w, tiles_h;  // macro tiles per image
   int num_m_tiles, num_n_tiles;
@@ -238,29 +247,27 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_igemm2_kernel(const __grid_
       for (int work = work_first; work < num_work; work += work_stride) {
         const int n_idx = work % p.num_n_tiles;
         const int b_row = n_idx * kNTile + static_cast<int>(cta_rank) * (kNTile / 2);
-        int koff = 0;
-        for (int s = 0; s < p.num_src; ++s) {
+        for (int ci = 0; ci < p.num_chunks; ++ci) {
+          const int s = p.chunk_src[ci], ch = p.chunk_ch[ci];
           const int C = p.src_c[s];
           const int ntaps = p.src_taps[s];
-          for (int ch = 0; ch < C / kConvBlockK; ++ch) {
-            for (int tap0 = 0; tap0 < ntaps; tap0 += kTapsPerStage) {
-              const int nt = ntaps - tap0 < kTapsPerStage ? ntaps - tap0 : kTapsPerStage;
-              mbar_wait(&empty_b[sb], pb ^ 1);
-              if (leader) {
-                mbar_arrive_expect_tx(&full_b[sb], static_cast<uint32_t>(2 * nt * kBTapBytes));
-              } else {
-                mbar_arrive_cluster(&full_b[sb], 0);
-              }
-              for (int t = 0; t < nt; ++t)
-                tma_load_2d_pair(b_ring + sb * kBSlotBytes + t * kBTapBytes, &p.tmap_b, &full_b[sb],
-                                 koff + (tap0 + t) * C + ch * kConvBlockK, b_row);
-              if (++sb == kStagesB) {
-                sb = 0;
-                pb ^= 1;
-              }
+          const int koff = p.src_koff[s];
+          for (int tap0 = 0; tap0 < ntaps; tap0 += kTapsPerStage) {
+            const int nt = ntaps - tap0 < kTapsPerStage ? ntaps - tap0 : kTapsPerStage;
+            mbar_wait(&empty_b[sb], pb ^ 1);
+            if (leader) {
+              mbar_arrive_expect_tx(&full_b[sb], static_cast<uint32_t>(2 * nt * kBTapBytes));
+            } else {
+              mbar_arrive_cluster(&full_b[sb], 0);
+            }
+            for (int t = 0; t < nt; ++t)
+              tma_load_2d_pair(b_ring + sb * kBSlotBytes + t * kBTapBytes, &p.tmap_b, &full_b[sb],
+                               koff + (tap0 + t) * C + ch * kConvBlockK, b_row);
+            if (++sb == kStagesB) {
+              sb = 0;
+              pb ^= 1;
             }
           }
-          koff += ntaps * C;
         }
       }
     }
@@ -280,25 +287,27 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_igemm2_kernel(const __grid_
         const int r = m_tile - n * tiles_per_img;
         const int ty = r / p.tiles_w;
         const int tx = r - ty * p.tiles_w;
-        for (int s = 0; s < p.num_src; ++s) {
-          for (int ch = 0; ch < p.src_c[s] / kConvBlockK; ++ch) {
-            mbar_wait(&empty_a[sa], pa ^ 1);
-            if (leader) {
-              mbar_arrive_expect_tx(&full_a[sa], 2 * kABytes);
-            } else {
-              mbar_arrive_cluster(&full_a[sa], 0);
-            }
-            if (hint) {
-              tma_load_4d_pair_hint(a_ring + sa * kASlotBytes, &p.tmap_a[s], &full_a[sa], ch * kConvBlockK,
-                                    tx * kTileW - 1, ty * kTileH - 1, n, pol);
-            } else {
-              tma_load_4d_pair(a_ring + sa * kASlotBytes, &p.tmap_a[s], &full_a[sa], ch * kConvBlockK, tx * kTileW - 1,
-                               ty * kTileH - 1, n);
-            }
-            if (++sa == kStagesA) {
-              sa = 0;
-              pa ^= 1;
-            }
+        for (int ci = 0; ci < p.num_chunks; ++ci) {
+          const int s = p.chunk_src[ci], ch = p.chunk_ch[ci];
+          // a 1x1 source needs no halo: its box is the bare tile (32 KB instead of 41.5 KB at kMT = 2)
+          const bool bare = p.box1 != 0 && p.src_taps[s] == 1;
+          const int halo = bare ? 0 : 1;
+          mbar_wait(&empty_a[sa], pa ^ 1);
+          if (leader) {
+            mbar_arrive_expect_tx(&full_a[sa], bare ? 2 * kTileW * kTileH * kRowBytes : 2 * kABytes);
+          } else {
+            mbar_arrive_cluster(&full_a[sa], 0);
+          }
+          if (hint) {
+            tma_load_4d_pair_hint(a_ring + sa * kASlotBytes, &p.tmap_a[s], &full_a[sa], ch * kConvBlockK,
+                                  tx * kTileW - halo, ty * kTileH - halo, n, pol);
+          } else {
+            tma_load_4d_pair(a_ring + sa * kASlotBytes, &p.tmap_a[s], &full_a[sa], ch * kConvBlockK,
+                             tx * kTileW - halo, ty * kTileH - halo, n);
+          }
+          if (++sa == kStagesA) {
+            sa = 0;
+            pa ^= 1;
           }
         }
       }
@@ -323,19 +332,19 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_igemm2_kernel(const __grid_
       tc_fence_after();
       const uint32_t tmem_d = tmem_u + static_cast<uint32_t>(acc * kMTiles * kNTile);
       uint32_t accum = 0;
-      for (int s = 0; s < p.num_src; ++s) {
-        const int chunks = p.src_c[s] / kConvBlockK;
-        const bool c3 = p.src_taps[s] == 9;
-        const bool last_src = s == p.num_src - 1;
-        for (int ch = 0; ch < chunks; ++ch) {
+      {
+        for (int ci = 0; ci < p.num_chunks; ++ci) {
+          const int s = p.chunk_src[ci];
+          const bool c3 = p.src_taps[s] == 9;
+          const bool bare = !c3 && p.box1 != 0;
           mbar_wait(&full_a[sa], pa);
-          const uint64_t a_desc = umma_desc_k128_sbo(a_ring_u + sa * kASlotBytes, kHaloPitch);
+          const uint64_t a_desc = umma_desc_k128_sbo(a_ring_u + sa * kASlotBytes, bare ? kTileW * kRowBytes : kHaloPitch);
           const int nrows = c3 ? 3 : 1;
           for (int row = 0; row < nrows; ++row) {
             mbar_wait(&full_b[sb], pb);
             tc_fence_after();
             const bool last_row = row == nrows - 1;
-            const bool last_step = last_row && last_src && ch == chunks - 1;
+            const bool last_step = last_row && ci == p.num_chunks - 1;
             if (elected) {
               const uint64_t bd = umma_desc_k128(b_ring_u + sb * kBSlotBytes);
               if (c3) {
@@ -354,8 +363,8 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_igemm2_kernel(const __grid_
                   }
                 }
               } else {
-                // 1x1 source: the centre of the halo tile
-                const uint64_t ad = a_desc + static_cast<uint64_t>((kHaloW + 1) * (kRowBytes / 16));
+                // 1x1 source: the centre of the halo tile, or the bare tile from its first pixel
+                const uint64_t ad = a_desc + static_cast<uint64_t>(bare ? 0 : (kHaloW + 1) * (kRowBytes / 16));
 #pragma unroll
                 for (int m = 0; m < kMTiles; ++m) {
 #pragma unroll
@@ -725,17 +734,72 @@ int build_conv2(const ConvDesc& d, std::shared_ptr<void>* holder) {
     p.gn_film_off = d.gn_film_off;
     p.gn_counters = d.gn_counters;
   }
+  static const int interleave = [] {
+    const char* e = getenv("CDDPM_SKIP_INTERLEAVE");  // A/B switch: 0 = sources in order, 1x1 sources stage the halo box
+    return (e != nullptr && e[0] == '0') ? 0 : 1;
+  }();
+  p.box1 = interleave;
   int ktot = 0;
+  int n9 = 0, n1 = 0;
   for (int s = 0; s < d.num_src; ++s) {
     p.src_c[s] = d.src_c[s];
     p.src_taps[s] = d.src_taps[s];
+    p.src_koff[s] = ktot;
+    const bool bare = interleave && d.src_taps[s] == 1;
     const uint64_t C = static_cast<uint64_t>(d.src_c[s]);
     const uint64_t dims[4] = {C, static_cast<uint64_t>(d.W), static_cast<uint64_t>(d.H), static_cast<uint64_t>(d.B)};
     const uint64_t strides[3] = {C * 2, C * 2 * d.W, C * 2 * d.W * d.H};
-    const uint32_t box[4] = {static_cast<uint32_t>(kConvBlockK), static_cast<uint32_t>(8 * p.mt + 2),
-                             static_cast<uint32_t>(kHaloH), 1u};
+    const uint32_t box[4] = {static_cast<uint32_t>(kConvBlockK), static_cast<uint32_t>(8 * p.mt + (bare ? 0 : 2)),
+                             static_cast<uint32_t>(bare ? kTileH : kHaloH), 1u};
     CDDPM_TRY(encode_tmap_16bit(&p.tmap_a[s], d.src[s], 4, dims, strides, box));
     ktot += d.src_taps[s] * d.src_c[s];
+    (d.src_taps[s] == 9 ? n9 : n1) += d.src_c[s] / kConvBlockK;
+  }
+  if (n9 + n1 > kMaxChunks) return fail(kUnsupported, "conv2: too many 64-channel chunks per work item");
+  {
+    // chunk schedule: sources in order; with interleaving the 1x1 chunks are dealt evenly between the 3x3 chunks
+    // (Bresenham), each 3x3 chunk first so the accumulator's first MMA belongs to the main source
+    int cs[kMaxChunks], cc[kMaxChunks], n = 0;
+    auto emit = [&](int taps) {
+      for (int s = 0; s < d.num_src; ++s)
+        if (d.src_taps[s] == taps)
+          for (int ch = 0; ch < d.src_c[s] / kConvBlockK; ++ch) {
+            cs[n] = s;
+            cc[n] = ch;
+            ++n;
+          }
+    };
+    if (!interleave || n9 == 0 || n1 == 0) {
+      for (int s = 0; s < d.num_src; ++s)
+        for (int ch = 0; ch < d.src_c[s] / kConvBlockK; ++ch) {
+          cs[n] = s;
+          cc[n] = ch;
+          ++n;
+        }
+      for (int i = 0; i < n; ++i) {
+        p.chunk_src[i] = static_cast<uint8_t>(cs[i]);
+        p.chunk_ch[i] = static_cast<uint8_t>(cc[i]);
+      }
+    } else {
+      emit(9);
+      const int m9 = n;
+      emit(1);
+      int i9 = 0, i1 = 0, o = 0;
+      while (i9 < n9 || i1 < n1) {
+        // keep i1 / n1 <= i9 / n9: a 1x1 chunk goes out when it does not run ahead of the 3x3 stream
+        if (i9 < n9 && (i1 >= n1 || static_cast<long long>(i1) * n9 >= static_cast<long long>(i9) * n1)) {
+          p.chunk_src[o] = static_cast<uint8_t>(cs[i9]);
+          p.chunk_ch[o] = static_cast<uint8_t>(cc[i9]);
+          ++i9;
+        } else {
+          p.chunk_src[o] = static_cast<uint8_t>(cs[m9 + i1]);
+          p.chunk_ch[o] = static_cast<uint8_t>(cc[m9 + i1]);
+          ++i1;
+        }
+        ++o;
+      }
+    }
+    p.num_chunks = n9 + n1;
   }
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(ktot), static_cast<uint64_t>(d.Cout)};

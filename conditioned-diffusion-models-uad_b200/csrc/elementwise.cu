@@ -987,22 +987,12 @@ int launch_gn_apply(const GnApplyArgs& a, cudaStream_t stream) {
   d.stream_loads = hints;
   const int C = a.x.C();
   const int HWo = d.Ho * d.Wo;
-  // Output pixels per block: the largest of 256 .. 16 that still gives two full waves of 4 x 148 resident blocks.  (The
-  // 24 x 24 level at B = 32 ran as 288 blocks of 64 pixels - half the block slots empty, 8.7 us for a 9 MB tensor.)
-  d.Pout = 16;
-  for (int pout = 256; pout >= 16; pout >>= 1) {
-    if (static_cast<long long>((HWo + pout - 1) / pout) * a.B >= 1100) {  // ~2 waves; B=32 at 96x96 keeps 256
-      d.Pout = pout;
-      break;
-    }
-  }
-  {
-    static const int legacy = [] {
-      const char* e = getenv("CDDPM_GN_POUT_LEGACY");  // A/B switch: 1 = the round-1 rule (256 or 64)
-      return (e != nullptr && e[0] == '1') ? 1 : 0;
-    }();
-    if (legacy) d.Pout = (static_cast<long long>(HWo / 256) * a.B >= 592) ? 256 : 64;
-  }
+  // Output pixels per block: 256 when that already fills the GPU (4 x 148 blocks), else 64 - and for small batches,
+  // where even that leaves SMs without a block (B = 1 at 24 x 24: 9 blocks), down to 16 until there are >= 256 blocks.
+  // Measured (profiles/r02_c5_ab.log): B = 1 forward 1.247 -> 1.161 ms; at B = 32 finer blocks only add coefficient
+  // prologues (5.385 -> 5.424 ms), so large batches keep the round-1 rule.
+  d.Pout = (static_cast<long long>(HWo / 256) * a.B >= 592) ? 256 : 64;
+  while (d.Pout > 16 && static_cast<long long>((HWo + d.Pout - 1) / d.Pout) * a.B < 256) d.Pout >>= 1;
   const int nvec = C / 8;
   const int threads = (256 / nvec) * nvec;
   dim3 grid((HWo + d.Pout - 1) / d.Pout, a.B);

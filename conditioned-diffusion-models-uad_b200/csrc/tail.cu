@@ -370,6 +370,71 @@ __global__ void ranking_terms_kernel(const float* __restrict__ s, const unsigned
   ap_terms[i] = p;
 }
 
+// ---------------------------------------------------------------------------------------------- Dice bisection
+// find_best_val (utils_eval.py:508-539) for ONE volume, on the device, in one launch of one warp: the ranking pass has
+// left the scores sorted in descending order (keys) with the running count of positives (tps), so the counts of a
+// threshold q are two look-ups - P = #(x > q) by a 32-ary search over the sorted scores (4 probes rounds for 460 800
+// voxels), PG = tps[P - 1], G = tps[n - 1] - and the ten bisection decisions need no pass over the volume and no host
+// round trip.  Arithmetic as the reference evaluates it under NumPy >= 2: the range in float32 (every operation rounded
+// on its own), Dice = 2 PG / (P + G) in float64 from exact integer counts, NaN (0 / 0) compares false.  (When max(x)
+// == 0 the reference restarts from the Python ints (0, 1) and computes in float64: the thresholds are then dyadic
+// fractions, identical in float32.)
+__device__ __forceinline__ int count_greater_desc(const float* __restrict__ keys, int n, float q, int lane) {
+  int lo = 0, len = n;  // the answer lies in [lo, lo + len]
+  while (len > 0) {
+    const int chunk = (len + 31) / 32;
+    const int idx = lo + (lane + 1) * chunk - 1;  // last element of this lane's chunk
+    const bool gt = idx < lo + len ? (keys[idx] > q) : false;
+    const unsigned ball = __ballot_sync(0xffffffffu, gt);
+    const int full = __popc(ball);  // chunks that lie entirely above q (the sequence is descending)
+    const int end = lo + len;
+    lo += full * chunk;
+    // the first chunk whose last element is <= q holds the boundary; that last element itself is out
+    len = full == 32 ? 0 : max(0, min(chunk - 1, end - lo));
+  }
+  return lo;
+}
+
+__global__ void dice_bisect_kernel(const float* __restrict__ keys, const unsigned int* __restrict__ tps, int n,
+                                   int max_steps, double* __restrict__ result) {
+  const int lane = threadIdx.x;
+  const long long G = tps[n - 1];
+  float bottom = 0.f, top = keys[0];  // val_range = (0, np.max(x))
+  double max_val = 0.0, max_point = 0.0;
+  auto dice_at = [&](float q) {
+    const int P = count_greater_desc(keys, n, q, lane);
+    const long long PG = P > 0 ? static_cast<long long>(tps[P - 1]) : 0;
+    return static_cast<double>(2 * PG) / static_cast<double>(static_cast<long long>(P) + G);
+  };
+  for (int step = 0; step < max_steps; ++step) {
+    if (bottom == top) top = 1.0f;
+    const float span = __fsub_rn(top, bottom);
+    const float center = __fadd_rn(bottom, __fmul_rn(span, 0.5f));
+    const float q_bottom = __fadd_rn(bottom, __fmul_rn(span, 0.25f));
+    const float q_top = __fadd_rn(bottom, __fmul_rn(span, 0.75f));
+    const double val_bottom = dice_at(q_bottom);
+    const double val_top = dice_at(q_top);
+    if (val_bottom >= val_top) {
+      if (val_bottom >= max_val) {
+        max_val = val_bottom;
+        max_point = static_cast<double>(q_bottom);
+      }
+      top = center;
+    } else {
+      if (val_top >= max_val) {
+        max_val = val_top;
+        max_point = static_cast<double>(q_top);
+      }
+      bottom = center;
+    }
+  }
+  if (lane == 0) {
+    result[0] = max_val;
+    result[1] = max_point;
+    result[2] = static_cast<double>(keys[0]);  // np.max(x): 0 makes the reference continue in Python floats
+  }
+}
+
 struct RankingLayout {
   size_t keys_in, keys_out, lab_in, lab_out, tps, endidx, lastend, auc, ap, cub, total, cub_bytes;
 };
@@ -516,6 +581,18 @@ int launch_ranking_metrics(const float* x, const VolView& seg, int H, int W, int
   cb = L.cub_bytes;
   CDDPM_CUDA(cub::DeviceReduce::Sum(cubtmp, cb, ap, result + 1, n, stream));
   return kOk;
+}
+
+int launch_dice_bisect(const void* ranking_workspace, int64_t n64, int max_steps, double* result, cudaStream_t stream) {
+  if (!ranking_workspace || !result) return fail(kInvalidArgument, "dice_bisect: null pointer");
+  if (n64 < 1 || n64 > (1ll << 30)) return fail(kInvalidArgument, "dice_bisect: bad voxel count");
+  if (max_steps < 0 || max_steps > 64) return fail(kInvalidArgument, "dice_bisect: bad step count");
+  const RankingLayout L = ranking_layout(n64);
+  const char* ws = reinterpret_cast<const char*>(ranking_workspace);
+  dice_bisect_kernel<<<1, 32, 0, stream>>>(reinterpret_cast<const float*>(ws + L.keys_out),
+                                           reinterpret_cast<const unsigned int*>(ws + L.tps), static_cast<int>(n64),
+                                           max_steps, result);
+  return check_launch("dice_bisect_kernel");
 }
 
 }  // namespace cddpm

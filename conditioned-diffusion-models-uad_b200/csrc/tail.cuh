@@ -52,6 +52,10 @@ size_t ranking_workspace_bytes(int64_t n);
 int launch_ranking_metrics(const float* x, const VolView& seg, int H, int W, int D, void* workspace,
                            size_t workspace_bytes, double* result, cudaStream_t stream);
 
+// find_best_val (utils_eval.py:508-539) of the volume whose ranking pass last filled `ranking_workspace`: val_range =
+// (0, max), `max_steps` quartile bisections decided on the device.  result[0] = best Dice, result[1] = its threshold, result[2] = max(x).
+int launch_dice_bisect(const void* ranking_workspace, int64_t n, int max_steps, double* result, cudaStream_t stream);
+
 // SURVEY.md §8 f-4 (tail_cc.cu): small-component filter, confusion counts, Hausdorff distance.  See include/cddpm_b200.h.
 int launch_filter_small_components(const unsigned char* in, unsigned char* out, int H, int W, int D, int max_size,
                                    cudaStream_t stream);

@@ -287,6 +287,14 @@ int64_t cddpm_ranking_workspace_bytes(int64_t n);
 int cddpm_ranking_metrics(const float* x_dhw, const cddpm_vol_view* seg, int H, int W, int D, void* workspace,
                           int64_t workspace_bytes, double* result, void* stream);
 
+/* find_best_val (utils_eval.py:508-539, called per volume at :86-91 with val_range = (0, max) and max_steps = 10) as ONE
+ * launch: the workspace must hold the result of cddpm_ranking_metrics for the same volume (scores sorted in descending
+ * order + running positive counts), so a threshold's Dice counts are two look-ups and the bisection decisions are
+ * taken on the device - no pass over the volume, no host round trip per step.  Range arithmetic in float32 with every
+ * operation rounded separately, Dice in float64 from integer counts (the reference under NumPy >= 2).
+ * result[0] = best Dice, result[1] = its threshold (a float32 value), result[2] = max(x) - 3 doubles on the device. */
+int cddpm_dice_bisect(const void* ranking_workspace, int64_t n, int max_steps, double* result, void* stream);
+
 /* filter_3d_connected_components (utils_eval.py:489-503; called at :100-102): skimage label(connectivity=3) and
  * regionprops.filled_area <= 7.  skimage fills holes with a full 3x3x3 element, so filled_area == area whenever
  * area <= 25: the filter drops every 26-connected component of at most max_size (reference: 7; <= 15) voxels.
@@ -306,6 +314,35 @@ int cddpm_confusion_counts(const uint8_t* pred_dhw, const cddpm_vol_view* seg, i
 int64_t cddpm_hausdorff_workspace_bytes(int H, int W, int D);
 int cddpm_hausdorff(const uint8_t* pred_dhw, const cddpm_vol_view* seg, int H, int W, int D, void* workspace,
                     int64_t workspace_bytes, int64_t* result, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Volume preprocessing on the device: the once-per-volume transforms of the reference's datamodule,
+ * src/datamodules/create_dataset.py:196-218 (get_transform: tio.CropOrPad -> tio.RescaleIntensity -> tio.Resample).
+ * torchio / SimpleITK are third-party packages that are neither vendored in the reference nor installed here
+ * (requirements: torchio==0.18.84, SimpleITK==2.2.0): CropOrPad / RescaleIntensity restate torchio's published source on
+ * top of NumPy semantics that ARE pinned here (np.percentile / np.clip bit for bit); the B-spline path restates the
+ * cubic B-spline decomposition + interpolation (pinned against scipy.ndimage, ITK's own truncated initialisation is
+ * not reproducible here: parity unpinned).  Volumes are contiguous [H][W][D] fp32, one channel.
+ * ---------------------------------------------------------------------------------------------------------- */
+/* tio.CropOrPad((h, w, d), padding_mode=pad_value): centre crop / pad per axis; the odd voxel of a difference goes to
+ * the start (torchio.CropOrPad._get_six_bounds_parameters). */
+int cddpm_crop_or_pad(const float* in, int H, int W, int D, float* out, int h, int w, int d, float pad_value,
+                      void* stream);
+/* tio.RescaleIntensity((out_min, out_max), percentiles=(perc_low, perc_high), masking_method='mask') in place:
+ * cut-offs = np.percentile(vol[mask > 0], (perc_low, perc_high)) (float64, 'linear'), np.clip, then
+ * (x - min) / (max - min) * (out_max - out_min) + out_min in float32 with min / max of the CLIPPED array.  An empty mask
+ * or a zero range leaves the volume as torchio leaves it.  cutoffs: optional 2 doubles on the device. */
+int64_t cddpm_rescale_workspace_bytes(int64_t n);
+int cddpm_rescale_intensity(float* vol, const float* mask, int64_t n, double perc_low, double perc_high, float out_min,
+                            float out_max, void* workspace, int64_t workspace_bytes, double* cutoffs, void* stream);
+/* tio.Resample(factor, image_interpolation='bspline') of a unit-spacing volume: output extent ceil(N / f) per axis
+ * (cddpm_resample_size), sample i at continuous index 0.5 (f - 1) + f i, 0 outside the buffer.  bspline != 0: cubic
+ * B-spline over float64 coefficients with mirror boundaries (workspace: cddpm_resample_workspace_bytes); bspline == 0:
+ * nearest neighbour, halves rounded up (tio.LabelMap entries; no workspace needed). */
+int cddpm_resample_size(int source, double factor);
+int64_t cddpm_resample_workspace_bytes(int H, int W, int D);
+int cddpm_resample(const float* in, int H, int W, int D, double fy, double fx, double fz, int bspline, float* out,
+                   void* workspace, int64_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

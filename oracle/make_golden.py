@@ -679,10 +679,50 @@ def golden_tail_fullres():
     print({k: [float(x) for x in host.eval_dict[k]] for k in keys})
 
 
+
+def golden_vol2slice():
+    """create_dataset.vol2slice (:143-193) of the live reference on fake subjects (objects with a `.data` tensor): the
+    slice index it draws (torch.randint under a fixed seed) and a checksum of the slices it returns, for the index rules
+    the configs use (random slice, fixed start slice, sequential window, onlyBrain, unique_slice)."""
+    from src.datamodules.create_dataset import vol2slice
+
+    class Img:
+        def __init__(self, t):
+            self.data = t
+
+    def make_ds(n=6, depth=20):
+        g = torch.Generator().manual_seed(77)
+        ds = []
+        for i in range(n):
+            vol = torch.rand(1, 8, 8, depth, generator=g)
+            mask = torch.zeros(1, 8, 8, depth)
+            mask[..., 3 + i % 3:15 - i % 2] = 1.0
+            ds.append({"vol": Img(vol), "mask": Img(mask)})
+        return ds
+
+    cases = {"random": dict(), "start": dict(slice=7), "window": dict(slice=5, seq_slices=6), "brain": dict(onlyBrain=True),
+             "unique": dict(cfg=dict(unique_slice=True, batch_size=3))}
+    out = {}
+    for name, kw in cases.items():
+        kw = dict(kw)
+        cfg = Cfg(kw.pop("cfg", {}))
+        torch.manual_seed(123)
+        v2s = vol2slice(make_ds(), cfg, **kw)
+        rec = []
+        for i in range(len(v2s)):
+            s = v2s[i]
+            rec.append([int(s["ind"]) if not isinstance(s["ind"], int) else s["ind"], float(s["vol"].data.double().sum()),
+                        float(s["mask"].data.double().sum()), list(s["vol"].data.shape)])
+        out[name] = rec
+    with open(os.path.join(GOLD, "vol2slice.json"), "w") as f:
+        json.dump(out, f)
+    print(out)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     which = sys.argv[1:] or ["schedule", "simplex", "unet", "encoder", "diffusion", "tail", "test_step", "train_step", "reverse_96",
-                             "test_step_d50", "uncond_step", "ddim", "tail_fullres"]
+                             "test_step_d50", "uncond_step", "ddim", "tail_fullres", "vol2slice"]
     torch.manual_seed(0)
     for w in which:
         print(f"== {w}")

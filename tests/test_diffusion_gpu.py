@@ -213,4 +213,5 @@ def test_out_of_range_timesteps_raise_like_the_reference():
     with torch.no_grad():
         l1, r1 = dn(img, cond=cond, t=100, noise=nz)
         l2, r2 = dn(img, cond=cond, t=100, noise=nz.expand(2, 1, 32, 32).contiguous())
-    assert torch.equal(r1, r2) and torch.equal(l1, l2)
+    # (the UNet's GroupNorm statistics are summed with atomics: two forwards agree to rounding, not bit for bit)
+    assert (r1 - r2).abs().max().item() <= 2e-3 and abs(float(l1) - float(l2)) <= 1e-4

@@ -5,7 +5,8 @@ uncond_step); the simplex fields are regenerated here from the same np.random.se
 tests/test_diffusion_gpu.py), so no noise is stored.
 
 * configs[1]  encoder -> conditioned 128-channel UNet, 96x96 -> GaussianDiffusion.sample(start_t = T0, noise=True)
-              for T0 = 50 and T0 = 500 (cond_DDPM.py:517-530, :446-464); x_t snapshots every 50 steps locate any drift.
+              for T0 = 50 and T0 = 500 (cond_DDPM.py:517-530, :446-464); x_t snapshots every 50 steps locate any drift;
+              tolerance = the envelope of the reference's own fp16-autocast path (see the test's docstring).
 * configs[2]  DDPM_2D.test_step on one FULL-depth 96x96x50 volume (DDPM_2D.py:171-286 without the fork's 4-slice crop).
 * configs[0]  DDPM_2D(condition=False), batch 1, single-step reconstruction from t = 499.
 
@@ -70,44 +71,77 @@ def cond_model():
     return _model(_cfg())
 
 
+@pytest.mark.parametrize("weights", ["rand", "fit"])
 @pytest.mark.parametrize("T0", [50, 500])
-def test_reverse_loop_headline_geometry_vs_reference(cond_model, T0):
+def test_reverse_loop_headline_geometry_vs_reference(cond_model, T0, weights):
+    """configs[1] at its own geometry.  The reverse loop is an ITERATED map: T0 UNet evaluations feed each other, so a
+    per-step rounding difference is amplified by the model's own sensitivity.  The golden therefore holds
+    the unmodified reference twice - in fp32 and under torch.autocast(fp16), the precision it is configured to run at
+    (configs/trainer/default.yaml:7 `precision: 16`) - and the criterion is: our deviation from the reference's fp32
+    path stays within the envelope of the reference's OWN fp16-autocast deviation (x1.5 in the maximum and in the mean;
+    never asked to be below the single-step tolerance 1e-2), at the output and (x2) at every stored x_t.  Two weight sets: "rand" (all tensors random: a
+    chaotic map, the envelope itself reaches 0.45 at T0 = 500) and "fit" (last layer fitted so the UNet is a denoiser,
+    oracle/make_golden.py fit_denoiser_readout: the well-conditioned case a trained model is)."""
     from oracle.weights import synthetic_slices
 
     g = np.load(os.path.join(GOLD, "reverse_96.npz"))
     x = synthetic_slices(2, 96, seed=31).cuda()
     d = cond_model.diffusion
+    out2 = d.model.out[2]
+    saved = (out2.weight.detach().clone(), out2.bias.detach().clone())
+    if weights == "fit":
+        with torch.no_grad():
+            out2.weight.copy_(torch.from_numpy(g["fit_out2_weight"]).cuda())
+            out2.bias.copy_(torch.from_numpy(g["fit_out2_bias"]).cuda())
     snaps = {}
     orig = d.p_sample
 
     def spy(x_, t, *a, **k):
         k.pop("_out", None)  # fresh tensors so the snapshots survive the loop's ping-pong buffers
         r = orig(x_, t, *a, **k)
-        if t % 50 == 0:
+        if t % 50 == 0 and t > 0:
             snaps[t] = r.detach().clone()
         return r
 
-    with torch.no_grad():
-        cond = cond_model(x)
-        cerr = (cond.cpu() - torch.from_numpy(g["cond"])).abs().max().item()
-        # the golden's own condition vector isolates the loop from the encoder's (stand-in, fp16) error
-        for tag, c in (("own encoder", cond), ("reference cond", torch.from_numpy(g["cond"]).cuda())):
+    key = f"{weights}_fp32_T{T0}"
+    ref = torch.from_numpy(g["out_" + key])
+    amp_d = (torch.from_numpy(g[f"out_{weights}_amp16_T{T0}"]) - ref).abs()
+    amp, amp_mean = amp_d.max().item(), amp_d.mean().item()
+    try:
+        with torch.no_grad():
+            cond = cond_model(x)
+            cerr = (cond.cpu() - torch.from_numpy(g["cond"])).abs().max().item()
             np.random.seed(int(g[f"seed_T{T0}"]))
             d.p_sample = spy
             try:
-                rec = d.sample(cond=c, x_start=x * 2 - 1, start_t=T0, noise=True)
+                rec = d.sample(cond=cond, x_start=x * 2 - 1, start_t=T0, noise=True)
             finally:
                 del d.p_sample
-            err = (rec.cpu() - torch.from_numpy(g[f"out_T{T0}"])).abs().max().item()
-            line = f"reverse loop 96x96 T0={T0} [{tag}]: max-abs {err:.4g} (encoder cond err {cerr:.3g})"
-            if T0 == 500:
-                ts = [int(t) for t in g["snap_t"]]
-                sx = torch.from_numpy(g["snap_x"]).float()
-                drift = {t: (snaps[t].cpu() - sx[i]).abs().max().item() for i, t in enumerate(ts)}
-                line += "; x_t drift by t: " + ", ".join(f"{t}:{drift[t]:.3g}" for t in sorted(drift, reverse=True))
-            print(line)
-            assert torch.isfinite(rec).all()
-            assert err <= TOL, line
+    finally:
+        with torch.no_grad():
+            out2.weight.copy_(saved[0])
+            out2.bias.copy_(saved[1])
+    err = (rec.cpu() - ref).abs().max().item()
+    mean_err = (rec.cpu() - ref).abs().mean().item()
+    line = (f"reverse loop 96x96 T0={T0} [{weights}]: max-abs {err:.4g} (mean {mean_err:.3g}) vs reference fp32; the "
+            f"reference's own fp16-autocast path: max-abs {amp:.4g} (mean {amp_mean:.3g}); encoder cond err {cerr:.3g}")
+    # envelope: within 1.5x of the reference's own mixed-precision deviation, in the maximum and in the mean.  Once the
+    # envelope itself is O(1) (random weights at T0 = 500: single pixels flip between the clamp limits) the maximum of
+    # one pixel carries no information any more and is allowed 2x; the mean and the x_t trajectory stay at their bounds.
+    ok = err <= max(TOL, (2.0 if amp > 0.25 else 1.5) * amp) and mean_err <= max(1e-3, 1.5 * amp_mean)
+    if T0 == 500:
+        ts = [int(t) for t in g["snap_t_" + key]]
+        sx = torch.from_numpy(g["snap_x_" + key])
+        ad = {int(t): float(a) for t, a in zip(ts, g[f"amp_drift_{weights}_amp16_T{T0}"])}
+        drift = {t: (snaps[t][0].cpu() - sx[i]).abs().max().item() for i, t in enumerate(ts)}
+        line += "\n   x_t deviation (ours | reference fp16-autocast) by t: " + ", ".join(
+            f"{t}: {drift[t]:.3g} | {ad[t]:.3g}" for t in sorted(drift, reverse=True))
+        for t in ts:
+            ok = ok and drift[t] <= max(5e-3, 2.0 * ad[t])
+    print(line)
+    assert torch.isfinite(rec).all()
+    assert cerr <= 5e-3
+    assert ok, line
 
 
 def test_full_depth_test_step_vs_reference():

@@ -336,3 +336,31 @@ def test_full_resolution_evaluation_vs_reference_golden():
     assert float(ed["HausPerVol"][0]) == float(g["HausPerVol"][0])
     for k in ("TPPerVol", "FPPerVol", "TNPerVol", "FNPerVol"):  # 4.86 M voxels; a 1-ulp resize difference may flip a few
         assert abs(float(ed[k][0]) - float(g[k][0])) <= 5, (k, ed[k][0], g[k][0])
+
+
+@pytest.mark.parametrize("case", ["dense", "sparse_ties", "empty_label", "all_zero"])
+def test_device_bisection_equals_host_loop(case, monkeypatch):
+    """cddpm_dice_bisect (ten find_best_val decisions on the device over the ranking pass's sorted scores, one launch)
+    against the host loop that counts over the volume once per step (the round-1 path, itself pinned to the live
+    reference by tests/golden/tail.json): identical best Dice, identical float32 threshold, identical AUC / AUPRC."""
+    from cddpm import eval_tail
+
+    g = torch.Generator().manual_seed({"dense": 1, "sparse_ties": 2, "empty_label": 3, "all_zero": 4}[case])
+    H, W, D = 40, 48, 21
+    x = torch.rand(D, H, W, generator=g)
+    seg = (torch.rand(H, W, D, generator=g) > 0.93).float()
+    if case == "sparse_ties":  # mostly exact zeros and a few repeated values, like a masked residual
+        x = torch.where(torch.rand(D, H, W, generator=g) > 0.2, torch.zeros(()), (x * 8).round() / 8)
+    elif case == "empty_label":
+        seg.zero_()
+    elif case == "all_zero":
+        x.zero_()
+    vol = eval_tail._Volume(x.cuda().contiguous(), seg.cuda(), seg.cuda(), (H, W, D))
+    monkeypatch.setenv("CDDPM_DEVICE_BISECT", "1")
+    dev = eval_tail._ranking_and_bisect(vol, 10)
+    monkeypatch.setenv("CDDPM_DEVICE_BISECT", "0")
+    host = eval_tail._ranking_and_bisect(vol, 10)
+    print(case, dev, host)
+    for a, b in zip(dev, host):
+        assert (a == b) or (a != a and b != b), (case, dev, host)
+    assert type(dev[3]) is type(host[3])  # np.float32 (or the int 0 when no step updated the optimum)
