@@ -59,6 +59,9 @@ class ResNet(nn.Module):
         self.image_size = tuple(int(s) for s in image_size)
         self.engine_dtype = engine_dtype
         self.drop_rate = 0.0
+        # timm's stochastic depth (the reference builds resnet50 with drop_path_rate=0.05, spark/models.py:50,92-109):
+        # block i of the 16 bottlenecks drops its residual branch with probability rate * i / 15 in training mode
+        self.drop_path_rate = 0.05
         self.conv1 = nn.Conv2d(in_chans, 64, 7, stride=2, padding=3, bias=False)
         self.bn1 = nn.BatchNorm2d(64)
         cin = 64
@@ -154,12 +157,15 @@ class ResNet(nn.Module):
         hand-written engine covers the eval-mode forward only (DESIGN.md lists the encoder backward under "next").
         The ~500 small launches of the forward and the backward are replayed as CUDA graphs
         (torch.cuda.make_graphed_callables, one pair per input shape; CDDPM_ENCODER_GRAPH=0 disables it).
-        timm's DropPath(0.05) is not applied (timm is not available to pin it; the oracle stand-in has none either)."""
+        timm's DropPath(0.05) on the residual branches is restated from timm's published source (`drop_path_rate`
+        attribute / cfg `encoder_drop_path_rate`; 0 disables it); the draws happen inside the replayed graph (torch's
+        graph-safe Philox offsets), so every step sees fresh masks."""
         import os
 
         if os.environ.get("CDDPM_ENCODER_GRAPH", "1") == "0":
             return _encoder_train_eager(self, x)
-        key = (tuple(x.shape), x.device.index, os.environ.get("CDDPM_ENCODER_TRAIN_DTYPE", getattr(self, "train_dtype", "tf32")))
+        key = (tuple(x.shape), x.device.index, os.environ.get("CDDPM_ENCODER_TRAIN_DTYPE", getattr(self, "train_dtype", "tf32")),
+               float(getattr(self, "drop_path_rate", 0.0) or 0.0))
         graphs = self.__dict__.setdefault("_train_graphs", {})
         if key not in graphs:
             holder = _EncoderTrainModule(self)
@@ -222,12 +228,24 @@ def _encoder_train_eager(self, x):
             x = x.contiguous(memory_format=torch.channels_last)
         h = F.relu(bn(self.bn1, F.conv2d(x, cl(self.conv1.weight), None, 2, 3)))
         h = F.max_pool2d(h, 3, 2, 1)
+        rate = float(getattr(self, "drop_path_rate", 0.0) or 0.0)
+        n_blocks = sum(len(getattr(self, f"layer{li}")) for li in range(1, 5))
+        bi = 0
         for li in range(1, 5):
             for blk in getattr(self, f"layer{li}"):
                 idt = h
                 o = F.relu(bn(blk.bn1, F.conv2d(h, cl(blk.conv1.weight))))
                 o = F.relu(bn(blk.bn2, F.conv2d(o, cl(blk.conv2.weight), None, blk.conv2.stride, 1)))
                 o = bn(blk.bn3, F.conv2d(o, cl(blk.conv3.weight)))
+                # timm DropPath(block_dpr), block_dpr = rate * block_index / (blocks - 1) (timm/models/resnet.py make_blocks,
+                # layers/drop.py drop_path: one Bernoulli(keep) draw per SAMPLE, scaled by 1 / keep), on the residual
+                # branch before the shortcut is added.  timm is not installed here: restated, parity unpinned.
+                dpr = rate * bi / max(1, n_blocks - 1)
+                if dpr > 0.0:
+                    keep = 1.0 - dpr
+                    mask = torch.empty(o.shape[0], 1, 1, 1, dtype=o.dtype, device=o.device).bernoulli_(keep)
+                    o = o * mask.div_(keep)
+                bi += 1
                 if blk.downsample is not None:
                     idt = bn(blk.downsample[1], F.conv2d(h, cl(blk.downsample[0].weight), None, blk.downsample[0].stride))
                 h = F.relu(o + idt)
@@ -246,6 +264,7 @@ class SparK_2D_encoder(nn.Module):
         self.encoder = ResNet(cfg.version, in_chans=1, num_classes=cfg.get("cond_dim", 128), image_size=size,
                               engine_dtype=dtype)
         self.encoder.train_dtype = str(cfg.get("encoder_train_dtype", "tf32"))  # "bf16" | "tf32" | "fp32"
+        self.encoder.drop_path_rate = float(cfg.get("encoder_drop_path_rate", 0.05))  # spark/models.py:50
 
     def forward(self, x):
         return self.encoder(x)

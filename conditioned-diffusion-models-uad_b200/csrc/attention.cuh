@@ -17,4 +17,9 @@ namespace cddpm {
 int64_t attention_bwd_scratch_elems(int B, int L, int C);
 int launch_attention_bwd(const void* qkv, const void* dout, void* dqkv, void* scratch, int B, int L, int C, int fmt,
                          cudaStream_t stream);
+// tcgen05 version (attention_bwd_tc.cu; the default - CDDPM_ATTN_BWD_TC=0 selects the mma.sync kernels): same arguments,
+// same scratch layout.
+bool attention_bwd_tc_enabled();
+int launch_attention_bwd_tc(const void* qkv, const void* dout, void* dqkv, void* scratch, int B, int L, int C, int fmt,
+                            cudaStream_t stream);
 }  // namespace cddpm

@@ -1,6 +1,7 @@
 // Backward of the self-attention core (QKVAttention, OpenAI_Unet.py:457-476), bf16.
 //
-// 0.2 % of the training step's FLOPs (one 24x24 attention block), so this first version trades speed for simplicity:
+// FIRST version, kept as the A/B reference (CDDPM_ATTN_BWD_TC=0); the product path is attention_bwd_tc.cu (tcgen05).
+// 0.2 % of the training step's FLOPs (one 24x24 attention block), so this version trades speed for simplicity:
 // warp-level mma.sync tensor cores through nvcuda::wmma, probabilities P and score gradients dS materialised once in
 // an L2-friendly bf16 scratch ([B*heads][L][L]).  A tcgen05 version is listed under "next" in DESIGN.md.
 //   kernel 1 (per 32 queries, head, image): S = Q K^T, dP = dO V^T, P = softmax(S / 8), D = rowsum(P * dP),
@@ -183,6 +184,7 @@ int launch_attention_bwd(const void* qkv, const void* dout, void* dqkv, void* sc
   if (!qkv || !dout || !dqkv || !scratch) return fail(kInvalidArgument, "attention_bwd: null pointer");
   if (fmt != 1) return fail(kUnsupported, "attention_bwd: the training path is bf16");
   if (C % kD != 0 || L % 64 != 0 || L > 576) return fail(kUnsupported, "attention_bwd: needs L % 64 == 0, L <= 576");
+  if (attention_bwd_tc_enabled()) return launch_attention_bwd_tc(qkv, dout, dqkv, scratch, B, L, C, fmt, stream);
   const int heads = C / kD;
   __nv_bfloat16* Pbuf = reinterpret_cast<__nv_bfloat16*>(scratch);
   __nv_bfloat16* dSbuf = Pbuf + static_cast<size_t>(B) * heads * L * L;

@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(256) gn_stats4_kernel(const uint16_t* __restri
 template <int kMode>
 __global__ void __launch_bounds__(256, kMode == 0 ? 4 : 3) gn_apply_kernel(const GnApplyDev a) {
   constexpr bool kPlain = kMode == 0;
-  extern __shared__ float sh[];  // A[C], Bc[C], mean[32], rstd[32]
+  extern __shared__ float sh[];  // A[C], Bc[C], mean[32], rstd[32], FiLM scale[C], shift[C]
   const int C = a.c0 + a.c1;
   float* sA = sh;
   float* sB = sh + C;
@@ -211,6 +211,21 @@ __global__ void __launch_bounds__(256, kMode == 0 ? 4 : 3) gn_apply_kernel(const
   int op = chunk * a.Pout + pl;
   if (kMode != 2 && worker) issue(op);
 
+  // Coefficient prologue.  The group statistics are finalised in float64 by 32 threads (one per group: float64 division
+  // and square root are slow enough on this part that letting every channel redo them cost 2.5 us per launch), while
+  // ALL threads fetch gamma / beta / FiLM into shared memory: both sets of loads are in flight together and the second
+  // phase runs out of shared memory.
+  float* sSc = sRstd + kGnGroups;  // FiLM scale / shift staging: [C], [C]
+  float* sSh = sSc + C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    sA[c] = a.gamma[c];
+    sB[c] = a.beta[c];
+    if (a.film != nullptr) {
+      const float* f = a.film + static_cast<size_t>(b) * a.film_stride + a.film_off;
+      sSc[c] = f[c];
+      sSh[c] = f[C + c];
+    }
+  }
   if (threadIdx.x < kGnGroups) {
     double s = 0.0, q = 0.0;
     if (a.stats0 != nullptr) {
@@ -237,16 +252,14 @@ __global__ void __launch_bounds__(256, kMode == 0 ? 4 : 3) gn_apply_kernel(const
     sRstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + 1e-5));
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {  // each thread rewrites only the entries it staged itself
     const int g = c / cpg;
-    float A = sRstd[g] * a.gamma[c];
-    float Bc = a.beta[c] - sMean[g] * A;
+    float A = sRstd[g] * sA[c];
+    float Bc = sB[c] - sMean[g] * A;
     if (a.film != nullptr) {
-      const float* f = a.film + static_cast<size_t>(b) * a.film_stride + a.film_off;
-      const float sc = 1.0f + f[c];
-      const float shf = f[C + c];
+      const float sc = 1.0f + sSc[c];
       A *= sc;
-      Bc = Bc * sc + shf;
+      Bc = Bc * sc + sSh[c];
     }
     sA[c] = A;
     sB[c] = Bc;
@@ -996,7 +1009,7 @@ int launch_gn_apply(const GnApplyArgs& a, cudaStream_t stream) {
   const int nvec = C / 8;
   const int threads = (256 / nvec) * nvec;
   dim3 grid((HWo + d.Pout - 1) / d.Pout, a.B);
-  const size_t shmem = (2 * C + 2 * kGnGroups) * sizeof(float);
+  const size_t shmem = (4 * C + 2 * kGnGroups) * sizeof(float);
   cudaError_t e;
   if (a.mode == kResampleNone && a.raw_out == nullptr) {
     e = launch_k(gn_apply_kernel<0>, grid, dim3(threads), shmem, stream, d);

@@ -227,7 +227,7 @@ def test_training_step_matches_live_reference_golden():
     g = np.load(os.path.join(ROOT, "tests", "golden", "train_step_96.npz"))
     cfg = Cfg(imageDim=[192, 192, 100], rescaleFactor=2, unet_dim=128, dim_mults=[1, 2, 2], condition=True,
               backbone="Spark_Encoder_2D", version="resnet50", cond_dim=128, noisetype="simplex", test_timesteps=500,
-              lr=1e-4, pretrained_encoder=False, encoder_train_dtype="fp32")
+              lr=1e-4, pretrained_encoder=False, encoder_train_dtype="fp32", encoder_drop_path_rate=0.0)
     m = DDPM_2D(cfg, prefix="t/")
     full = {"encoder.encoder." + k: v for k, v in make_state_dict(resnet_port.param_shapes(128), seed=3).items()}
     full.update({"diffusion." + k: v for k, v in diffusion_port.schedule_buffers().items()})
@@ -433,3 +433,34 @@ def test_encoder_eval_after_graphed_training_sees_new_bn_statistics():
         y_fresh = fresh(x)
     assert (y_after - y_before).abs().max().item() > 1e-4, "eval output did not react to three training steps"
     assert torch.equal(y_after, y_fresh), (y_after - y_fresh).abs().max().item()
+
+
+def test_encoder_drop_path_is_training_only_and_per_sample():
+    """timm DropPath on the bottleneck residual branches (reference: resnet50(drop_path_rate=0.05), spark/models.py:50,
+    :92-109): active in train() only, one Bernoulli draw per sample and block, fresh draws on every (graph-replayed)
+    step, rate 0 switches it off.  Parity unpinned (timm is not installed); this pins the contract."""
+    from cddpm.encoder import get_encoder
+
+    cfg = Cfg(imageDim=[192, 192, 100], rescaleFactor=2, backbone="Spark_Encoder_2D", version="resnet50", cond_dim=128,
+              encoder_train_dtype="fp32", encoder_drop_path_rate=0.5)
+    torch.manual_seed(5)
+    enc, _ = get_encoder(cfg)
+    assert enc.encoder.drop_path_rate == 0.5
+    with torch.no_grad():
+        for n, p in enc.named_parameters():
+            if n.endswith("bn3.weight"):
+                p.fill_(0.5)
+    enc = enc.cuda().train()
+    x = torch.rand(8, 1, 96, 96, device="cuda")
+    outs = [enc(x).detach().clone() for _ in range(3)]  # capture, then two replays
+    assert (outs[1] - outs[2]).abs().max().item() > 1e-4, "replays reuse the same drop-path masks"
+    enc.encoder.drop_path_rate = 0.0
+    a, b = enc(x).detach().clone(), enc(x).detach().clone()
+    assert (a - b).abs().max().item() <= 1e-5  # deterministic again (running statistics do not enter the batch-stat forward)
+    enc.eval()
+    enc.encoder.drop_path_rate = 0.5
+    with torch.no_grad():
+        e1, e2 = enc(x).clone(), enc(x).clone()
+    assert torch.equal(e1, e2)
+    assert get_encoder(Cfg(cfg, encoder_drop_path_rate=None) if False else Cfg(imageDim=[192, 192, 100], rescaleFactor=2,
+                       backbone="Spark_Encoder_2D", version="resnet50", cond_dim=128))[0].encoder.drop_path_rate == 0.05
