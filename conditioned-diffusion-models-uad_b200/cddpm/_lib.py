@@ -90,6 +90,17 @@ def _signatures(c):
         "cddpm_encoder_param_info": (i32, [vp, i32, c.POINTER(c.c_char_p), c.POINTER(i64)]),
         "cddpm_encoder_set_param": (i32, [vp, c.c_char_p, vp, i64, vp]),
         "cddpm_encoder_forward": (i32, [vp, vp, vp, i32, vp]),
+        "cddpm_encoder_train_create": (i32, [i32, i32, i32, pvp]),
+        "cddpm_encoder_train_destroy": (None, [vp]),
+        "cddpm_encoder_train_entry_count": (i32, [vp]),
+        "cddpm_encoder_train_entry_info": (i32, [vp, i32, c.POINTER(c.c_char_p), c.POINTER(i64), pi32]),
+        "cddpm_encoder_train_grad_total": (i64, [vp]),
+        "cddpm_encoder_train_grad_offset": (i32, [vp, i32, c.POINTER(i64)]),
+        "cddpm_encoder_train_num_blocks": (i32, [vp]),
+        "cddpm_encoder_train_launches": (i32, [vp, i32]),
+        "cddpm_encoder_train_forward": (i32, [vp, pvp, i32, vp, vp, vp, i32, vp]),
+        "cddpm_encoder_train_backward": (i32, [vp, vp, vp, i32, vp]),
+        "cddpm_flat_wgrad": (i32, [vp, vp, i32, i32, i32, vp, vp]),
         "cddpm_simplex_noise": (i32, [c.c_char_p, vp, vp, i32, i32, i32, i32, c.c_double, c.c_double, vp]),
         "cddpm_q_sample": (i32, [vp, vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
         "cddpm_posterior_step": (i32, [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, vp]),

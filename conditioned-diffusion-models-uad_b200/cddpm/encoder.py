@@ -86,6 +86,12 @@ class ResNet(nn.Module):
                 lib().cddpm_encoder_destroy(h)
             except Exception:
                 pass
+        th = self.__dict__.get("_th")
+        if th is not None and th.value:
+            try:
+                lib().cddpm_encoder_train_destroy(th)
+            except Exception:
+                pass
 
     def _apply(self, fn, *args, **kwargs):
         self._items = None
@@ -152,9 +158,66 @@ class ResNet(nn.Module):
 
 
     def _train_forward(self, x):
-        """Training-mode forward WITH an autograd tape (batch-statistics BatchNorm, running-stat updates): ~1 % of the
-        training step's FLOPs, evaluated with torch's library kernels (cuDNN convolutions, TF32 by default) — the
-        hand-written engine covers the eval-mode forward only (DESIGN.md lists the encoder backward under "next").
+        """Training-mode forward (batch-statistics BatchNorm, running-statistics updates, DropPath) with an autograd
+        tape.  Default (`encoder_train_dtype: b200`): the hand-written engine - tcgen05 GEMMs for every convolution's
+        forward, data gradient and weight gradient, BatchNorm forward / backward kernels (csrc/resnet_train.cu) - as ONE
+        autograd node.  `tf32 | bf16 | fp32` select the library path below (torch autograd over cuDNN), kept as the
+        A/B and parity reference."""
+        import os
+
+        mode = os.environ.get("CDDPM_ENCODER_TRAIN_DTYPE", getattr(self, "train_dtype", "b200"))
+        if mode == "b200":
+            return self._train_forward_engine(x)
+        return self._train_forward_library(x)
+
+    # ------------------------------------------------------------------ hand-written training engine
+    def _train_engine(self):
+        h = self.__dict__.get("_th")
+        if h is None:
+            h = ctypes.c_void_p()
+            check(lib().cddpm_encoder_train_create(self.image_size[0], self.image_size[1], self.num_classes,
+                                                   ctypes.byref(h)), "cddpm_encoder_train_create")
+            n = lib().cddpm_encoder_train_entry_count(h)
+            name, numel, isp, off = ctypes.c_char_p(), ctypes.c_int64(), ctypes.c_int(), ctypes.c_int64()
+            meta = []
+            for i in range(n):
+                check(lib().cddpm_encoder_train_entry_info(h, i, ctypes.byref(name), ctypes.byref(numel), ctypes.byref(isp)))
+                check(lib().cddpm_encoder_train_grad_offset(h, i, ctypes.byref(off)))
+                meta.append((name.value.decode(), int(numel.value), bool(isp.value), int(off.value)))
+            if [m[0] for m in meta] != [k for k, _ in self._engine_items()]:
+                raise CddpmError("training-encoder entry list differs from the module's state_dict layout")
+            self.__dict__["_th"] = h
+            self.__dict__["_th_meta"] = meta
+            self.__dict__["_th_blocks"] = int(lib().cddpm_encoder_train_num_blocks(h))
+            self.__dict__["_th_total"] = int(lib().cddpm_encoder_train_grad_total(h))
+        return h
+
+    def _drop_scale(self, B, device):
+        rate = float(getattr(self, "drop_path_rate", 0.0) or 0.0)
+        if rate <= 0.0:
+            return None
+        n = self.__dict__["_th_blocks"]
+        keep = 1.0 - rate * torch.arange(n, dtype=torch.float32, device=device) / max(1, n - 1)  # linear decay rule
+        mask = torch.bernoulli(keep[:, None].expand(n, B).contiguous())
+        return (mask / keep[:, None]).contiguous()
+
+    def _train_forward_engine(self, x):
+        self._train_engine()
+        items = self._engine_items()
+        for _, t in items:
+            if t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda:
+                raise CddpmError("the training encoder needs contiguous fp32 CUDA parameters and buffers")
+        params = [t for (_, t), m in zip(items, self.__dict__["_th_meta"]) if m[2]]
+        out = _EncoderTrainFunction.apply(self, x.detach().float().contiguous(), *params)
+        with torch.no_grad():
+            nbt = [b for n, b in self.named_buffers() if n.endswith("num_batches_tracked")]
+            if nbt:
+                torch._foreach_add_(nbt, 1)
+        return out
+
+    def _train_forward_library(self, x):
+        """The same forward through torch autograd on library kernels (cuDNN convolutions; `encoder_train_dtype: tf32 |
+        bf16 | fp32`) - the round-1 path, kept as the parity / A-B reference of the hand-written engine.
         The ~500 small launches of the forward and the backward are replayed as CUDA graphs
         (torch.cuda.make_graphed_callables, one pair per input shape; CDDPM_ENCODER_GRAPH=0 disables it).
         timm's DropPath(0.05) on the residual branches is restated from timm's published source (`drop_path_rate`
@@ -164,7 +227,7 @@ class ResNet(nn.Module):
 
         if os.environ.get("CDDPM_ENCODER_GRAPH", "1") == "0":
             return _encoder_train_eager(self, x)
-        key = (tuple(x.shape), x.device.index, os.environ.get("CDDPM_ENCODER_TRAIN_DTYPE", getattr(self, "train_dtype", "tf32")),
+        key = (tuple(x.shape), x.device.index, os.environ.get("CDDPM_ENCODER_TRAIN_DTYPE", getattr(self, "train_dtype", "b200")),
                float(getattr(self, "drop_path_rate", 0.0) or 0.0))
         graphs = self.__dict__.setdefault("_train_graphs", {})
         if key not in graphs:
@@ -183,6 +246,47 @@ class ResNet(nn.Module):
         if fn is None:
             return _encoder_train_eager(self, x)
         return fn(x.detach().float())
+
+
+class _EncoderTrainFunction(torch.autograd.Function):
+    """ResNet-50 training forward / backward in libcddpm_b200 as one autograd node (cddpm_encoder_train_forward /
+    _backward).  The parameters are inputs of the node so that autograd routes their gradients: views of one flat fp32
+    buffer in the reference's shapes."""
+
+    @staticmethod
+    def forward(ctx, net, x, *params):
+        h = net._train_engine()
+        items = net._engine_items()
+        B = x.shape[0]
+        if tuple(x.shape[1:]) != (1, *net.image_size):
+            raise CddpmError(f"expected [B,1,{net.image_size[0]},{net.image_size[1]}], got {tuple(x.shape)}")
+        table = (ctypes.c_void_p * len(items))(*[t.data_ptr() for _, t in items])
+        drop = net._drop_scale(B, x.device)
+        out = torch.empty(B, net.num_classes, dtype=torch.float32, device=x.device)
+        check(lib().cddpm_encoder_train_forward(h, table, len(items), ptr(x), ptr(drop), ptr(out), B, current_stream()),
+              "cddpm_encoder_train_forward")
+        ctx.net = net
+        ctx.B = B
+        ctx.drop = drop  # the backward pass reads the same per-sample scales
+        ctx.shapes = [tuple(p.shape) for p in params]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        net = ctx.net
+        h = net._train_engine()
+        flat = torch.empty(net.__dict__["_th_total"], dtype=torch.float32, device=dout.device)
+        g = dout.detach().float().contiguous()
+        check(lib().cddpm_encoder_train_backward(h, ptr(g), ptr(flat), ctx.B, current_stream()),
+              "cddpm_encoder_train_backward")
+        grads = []
+        k = 0
+        for (name, numel, is_param, off) in net.__dict__["_th_meta"]:
+            if not is_param:
+                continue
+            grads.append(flat[off:off + numel].view(ctx.shapes[k]))
+            k += 1
+        return (None, None, *grads)
 
 
 class _EncoderTrainModule(nn.Module):
@@ -216,7 +320,9 @@ def _encoder_train_eager(self, x):
     # step), "bf16" (autocast) or "fp32" (50.6 ms).  Batch-statistics BatchNorm over a handful of samples (layer4 sees
     # 3x3 pixels per slice) amplifies operand rounding: at B=2 bf16 autocast moves the features by O(1) - on the CPU
     # as much as here - so small-batch parity runs use fp32.
-    mode = os.environ.get("CDDPM_ENCODER_TRAIN_DTYPE", getattr(self, "train_dtype", "tf32"))
+    mode = os.environ.get("CDDPM_ENCODER_TRAIN_DTYPE", getattr(self, "train_dtype", "b200"))
+    if mode == "b200":
+        mode = "tf32"  # the library path asked for explicitly (CDDPM_ENCODER_GRAPH=0 etc.) under the default setting
     if mode == "bf16":
         ctx = torch.autocast("cuda", dtype=torch.bfloat16, cache_enabled=False)
     else:
@@ -263,7 +369,8 @@ class SparK_2D_encoder(nn.Module):
         dtype = {"bf16": torch.bfloat16, "bfloat16": torch.bfloat16}.get(str(cfg.get("engine_dtype", "fp16")), torch.float16)
         self.encoder = ResNet(cfg.version, in_chans=1, num_classes=cfg.get("cond_dim", 128), image_size=size,
                               engine_dtype=dtype)
-        self.encoder.train_dtype = str(cfg.get("encoder_train_dtype", "tf32"))  # "bf16" | "tf32" | "fp32"
+        # "b200" (default): the hand-written training engine; "tf32" | "bf16" | "fp32": torch autograd over cuDNN
+        self.encoder.train_dtype = str(cfg.get("encoder_train_dtype", "b200"))
         self.encoder.drop_path_rate = float(cfg.get("encoder_drop_path_rate", 0.05))  # spark/models.py:50
 
     def forward(self, x):

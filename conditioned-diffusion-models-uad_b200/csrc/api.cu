@@ -9,6 +9,7 @@
 #include "diffusion.cuh"
 #include "elementwise.cuh"
 #include "resnet_engine.cuh"
+#include "resnet_train.cuh"
 #include "simplex.cuh"
 #include "preprocess.cuh"
 #include "tail.cuh"
@@ -253,6 +254,50 @@ int cddpm_encoder_set_param(cddpm_encoder_t* h, const char* name, const float* v
 int cddpm_encoder_forward(cddpm_encoder_t* h, const float* x, float* c, int B, void* stream) {
   if (!h) return fail(kInvalidArgument, "encoder_forward: null handle");
   return h->engine.forward(x, c, B, static_cast<cudaStream_t>(stream));
+}
+
+struct cddpm_encoder_train {
+  ResNetTrainEngine engine;
+};
+int cddpm_encoder_train_create(int image_h, int image_w, int cond_dim, cddpm_encoder_train_t** out) {
+  if (!out) return fail(kInvalidArgument, "encoder_train_create: null pointer");
+  cddpm_encoder_train* h = new cddpm_encoder_train();
+  int st = h->engine.init(image_h, image_w, cond_dim);
+  if (st != kOk) {
+    delete h;
+    return st;
+  }
+  *out = h;
+  return kOk;
+}
+void cddpm_encoder_train_destroy(cddpm_encoder_train_t* h) { delete h; }
+int cddpm_encoder_train_entry_count(const cddpm_encoder_train_t* h) { return h ? h->engine.entry_count() : 0; }
+int cddpm_encoder_train_entry_info(const cddpm_encoder_train_t* h, int index, const char** name, int64_t* numel,
+                                   int* is_param) {
+  if (!h || !name || !numel || !is_param) return fail(kInvalidArgument, "encoder_train_entry_info: null pointer");
+  return h->engine.entry_info(index, name, numel, is_param);
+}
+int64_t cddpm_encoder_train_grad_total(const cddpm_encoder_train_t* h) { return h ? h->engine.grad_total() : 0; }
+int cddpm_encoder_train_grad_offset(const cddpm_encoder_train_t* h, int index, int64_t* offset) {
+  if (!h || !offset) return fail(kInvalidArgument, "encoder_train_grad_offset: null pointer");
+  return h->engine.grad_offset(index, offset);
+}
+int cddpm_encoder_train_num_blocks(const cddpm_encoder_train_t* h) { return h ? h->engine.num_blocks() : 0; }
+int cddpm_encoder_train_launches(const cddpm_encoder_train_t* h, int backward) {
+  if (!h) return 0;
+  return backward ? h->engine.launches_backward() : h->engine.launches_forward();
+}
+int cddpm_encoder_train_forward(cddpm_encoder_train_t* h, const float* const* values, int count, const float* x,
+                                const float* drop_scale, float* out, int B, void* stream) {
+  if (!h) return fail(kInvalidArgument, "encoder_train_forward: null handle");
+  return h->engine.forward(values, count, x, drop_scale, out, B, static_cast<cudaStream_t>(stream));
+}
+int cddpm_flat_wgrad(const void* dy, const void* x, int M, int Cout, int K, float* dw, void* stream) {
+  return launch_flat_wgrad_bf16(dy, x, M, Cout, K, dw, static_cast<cudaStream_t>(stream));
+}
+int cddpm_encoder_train_backward(cddpm_encoder_train_t* h, const float* dout, float* grads, int B, void* stream) {
+  if (!h) return fail(kInvalidArgument, "encoder_train_backward: null handle");
+  return h->engine.backward(dout, grads, B, static_cast<cudaStream_t>(stream));
 }
 
 static VolView to_view(const cddpm_vol_view* v) {

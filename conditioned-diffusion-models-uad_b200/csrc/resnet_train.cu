@@ -1,0 +1,1057 @@
+// Training-mode condition encoder (see resnet_train.cuh): kernels + the planned forward / backward launch lists.
+#include "resnet_train.cuh"
+
+#include <cuda_bf16.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "backward.cuh"
+#include "elementwise.cuh"
+#include "ptx.cuh"
+
+namespace cddpm {
+
+namespace {
+
+constexpr float kBnEps = 1e-5f;
+constexpr float kBnMomentum = 0.1f;
+
+__device__ __forceinline__ uint16_t to_bf16(float v) {
+  __nv_bfloat16 h = __float2bfloat16_rn(v);
+  return *reinterpret_cast<uint16_t*>(&h);
+}
+__device__ __forceinline__ float from_bf16(uint16_t u) { return __uint_as_float(static_cast<uint32_t>(u) << 16); }
+
+int grid_for(size_t n, int per_block = 256) {
+  return static_cast<int>(std::min<size_t>((n + per_block - 1) / per_block, 148 * 16));
+}
+
+// ---------------------------------------------------------------------------------------------- parameters
+// w fp32 [cout][cin][taps] -> panel[cout][tap * cin + ci] and panel_t[tap * cin + ci][cout] (bf16)
+__global__ void pack_panels_kernel(const float* __restrict__ w, int cout, int cin, int taps, uint16_t* __restrict__ panel,
+                                   uint16_t* __restrict__ panel_t) {
+  const size_t total = static_cast<size_t>(cout) * cin * taps;
+  const int K = cin * taps;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i % K);
+    const int co = static_cast<int>(i / K);
+    const int tap = k / cin, ci = k - tap * cin;
+    const uint16_t v = to_bf16(w[(static_cast<size_t>(co) * cin + ci) * taps + tap]);
+    panel[i] = v;
+    panel_t[static_cast<size_t>(k) * cout + co] = v;
+  }
+}
+
+// grad[co][ci][tap] = dwp[co][tap * cin + ci]
+__global__ void unpack_grad_kernel(const float* __restrict__ dwp, int cout, int cin, int taps, float* __restrict__ grad) {
+  const size_t total = static_cast<size_t>(cout) * cin * taps;
+  const int K = cin * taps;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int tap = static_cast<int>(i % taps);
+    const int ci = static_cast<int>((i / taps) % cin);
+    const int co = static_cast<int>(i / (static_cast<size_t>(taps) * cin));
+    grad[i] = dwp[static_cast<size_t>(co) * K + tap * cin + ci];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- forward kernels
+// col[(n,oy,ox)][tap][c] = in[n][oy*stride+ky-pad][ox*stride+kx-pad][c] (zero outside); 8 channels per thread.
+__global__ void im2col_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ col, int B, int H, int W, int C,
+                              int k, int stride, int pad, int Ho, int Wo) {
+  const int cv = C >> 3;
+  const size_t total = static_cast<size_t>(B) * Ho * Wo * k * k * cv;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % cv);
+    const int tap = static_cast<int>((i / cv) % (k * k));
+    const size_t pix = i / (static_cast<size_t>(cv) * k * k);
+    const int ox = static_cast<int>(pix % Wo), oy = static_cast<int>((pix / Wo) % Ho);
+    const size_t n = pix / (static_cast<size_t>(Wo) * Ho);
+    const int iy = oy * stride + tap / k - pad, ix = ox * stride + tap % k - pad;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+      val = __ldg(reinterpret_cast<const uint4*>(in + ((n * H + iy) * W + ix) * C + v * 8));
+    *reinterpret_cast<uint4*>(col + (pix * k * k + tap) * C + v * 8) = val;
+  }
+}
+
+// Stem 7x7 stride 2 pad 3 over one input channel, RAW output fp32 [B*Ho*Wo][64] (bf16-rounded weights like every
+// other layer's operands; the input stays fp32).
+__global__ void __launch_bounds__(256) stem_raw_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                       float* __restrict__ y, int B, int H, int W) {
+  __shared__ float sw[49 * 64];
+  for (int i = threadIdx.x; i < 49 * 64; i += blockDim.x) {
+    const int tap = i / 64, co = i % 64;
+    sw[i] = from_bf16(to_bf16(w[co * 49 + tap]));
+  }
+  __syncthreads();
+  const int Ho = H / 2, Wo = W / 2;
+  const int g = threadIdx.x & 7;
+  const size_t total = static_cast<size_t>(B) * Ho * Wo;
+  for (size_t pix = static_cast<size_t>(blockIdx.x) * 32 + (threadIdx.x >> 3); pix < total;
+       pix += static_cast<size_t>(gridDim.x) * 32) {
+    const int ox = static_cast<int>(pix % Wo), oy = static_cast<int>((pix / Wo) % Ho);
+    const size_t n = pix / (static_cast<size_t>(Wo) * Ho);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int ky = 0; ky < 7; ++ky) {
+      const int iy = oy * 2 + ky - 3;
+      if (iy < 0 || iy >= H) continue;
+      for (int kx = 0; kx < 7; ++kx) {
+        const int ix = ox * 2 + kx - 3;
+        if (ix < 0 || ix >= W) continue;
+        const float v = __ldg(x + (n * H + iy) * W + ix);
+        const float* wr = &sw[(ky * 7 + kx) * 64 + g * 8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wr[j], acc[j]);
+      }
+    }
+    float4* o = reinterpret_cast<float4*>(y + pix * 64 + g * 8);
+    o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  }
+}
+
+// stats[c][0] += sum_m y[m][c], stats[c][1] += sum_m y[m][c]^2 (double atomics; the caller zeroes stats)
+__global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ y, int M, int C, int rows_per_block,
+                                                       double* __restrict__ stats) {
+  const int m0 = blockIdx.x * rows_per_block;
+  const int m1 = min(m0 + rows_per_block, M);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double s = 0.0, q = 0.0;
+    for (int m = m0; m < m1; ++m) {
+      const double v = static_cast<double>(y[static_cast<size_t>(m) * C + c]);
+      s += v;
+      q += v * v;
+    }
+    atomicAdd(&stats[2 * c], s);
+    atomicAdd(&stats[2 * c + 1], q);
+  }
+}
+
+// Batch statistics -> (mean, rstd) for the normalisation (biased variance) and the running statistics update of
+// nn.BatchNorm2d in train() mode: running = (1 - momentum) running + momentum * (mean | unbiased variance).
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, int M, int C, float* __restrict__ mean,
+                                   float* __restrict__ rstd, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mu = stats[2 * c] / M;
+  double var = stats[2 * c + 1] / M - mu * mu;
+  if (var < 0.0) var = 0.0;
+  mean[c] = static_cast<float>(mu);
+  rstd[c] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(kBnEps)));
+  const double unbiased = M > 1 ? var * (static_cast<double>(M) / (M - 1)) : var;
+  running_mean[c] = (1.0f - kBnMomentum) * running_mean[c] + kBnMomentum * static_cast<float>(mu);
+  running_var[c] = (1.0f - kBnMomentum) * running_var[c] + kBnMomentum * static_cast<float>(unbiased);
+}
+
+// a = relu?((gamma (y - mean) rstd + beta) * scale[n] + identity), bf16; 4 channels per thread
+__global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ y, const float* __restrict__ mean,
+                                                       const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta,
+                                                       const uint16_t* __restrict__ identity,
+                                                       const float* __restrict__ scale, int rows_per_sample, int relu,
+                                                       size_t M, int C, uint16_t* __restrict__ a) {
+  const int cv = C >> 2;
+  const size_t total = M * cv;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % cv) * 4;
+    const size_t m = i / cv;
+    const float4 v = *reinterpret_cast<const float4*>(y + m * C + c);
+    const float4 mu = *reinterpret_cast<const float4*>(mean + c);
+    const float4 rs = *reinterpret_cast<const float4*>(rstd + c);
+    const float4 ga = *reinterpret_cast<const float4*>(gamma + c);
+    const float4 be = *reinterpret_cast<const float4*>(beta + c);
+    float o[4] = {(v.x - mu.x) * rs.x * ga.x + be.x, (v.y - mu.y) * rs.y * ga.y + be.y,
+                  (v.z - mu.z) * rs.z * ga.z + be.z, (v.w - mu.w) * rs.w * ga.w + be.w};
+    if (scale != nullptr) {
+      const float s = scale[m / rows_per_sample];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] *= s;
+    }
+    if (identity != nullptr) {
+      const uint2 id = *reinterpret_cast<const uint2*>(identity + m * C + c);
+      o[0] += from_bf16(static_cast<uint16_t>(id.x & 0xFFFF));
+      o[1] += from_bf16(static_cast<uint16_t>(id.x >> 16));
+      o[2] += from_bf16(static_cast<uint16_t>(id.y & 0xFFFF));
+      o[3] += from_bf16(static_cast<uint16_t>(id.y >> 16));
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = fmaxf(o[j], 0.f);
+    }
+    uint2 pk;
+    pk.x = static_cast<uint32_t>(to_bf16(o[0])) | (static_cast<uint32_t>(to_bf16(o[1])) << 16);
+    pk.y = static_cast<uint32_t>(to_bf16(o[2])) | (static_cast<uint32_t>(to_bf16(o[3])) << 16);
+    *reinterpret_cast<uint2*>(a + m * C + c) = pk;
+  }
+}
+
+__global__ void maxpool3s2_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int B, int H, int W, int C) {
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const size_t total = static_cast<size_t>(B) * Ho * Wo * C;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const int ox = static_cast<int>((i / C) % Wo), oy = static_cast<int>((i / (static_cast<size_t>(C) * Wo)) % Ho);
+    const size_t n = i / (static_cast<size_t>(C) * Wo * Ho);
+    float m = -INFINITY;
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) {
+        const int iy = oy * 2 + ky - 1, ix = ox * 2 + kx - 1;
+        if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+        m = fmaxf(m, from_bf16(in[((n * H + iy) * W + ix) * C + c]));
+      }
+    out[i] = to_bf16(m);
+  }
+}
+
+__global__ void avgpool_kernel(const uint16_t* __restrict__ in, float* __restrict__ out, int B, int HW, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int c = i % C, n = i / C;
+  float s = 0.f;
+  for (int p = 0; p < HW; ++p) s += from_bf16(in[(static_cast<size_t>(n) * HW + p) * C + c]);
+  out[i] = s / static_cast<float>(HW);
+}
+
+// ---------------------------------------------------------------------------------------------- backward kernels
+// A gradient that reaches a [B,H,W,C] tensor along up to two paths.
+struct Src {
+  const float* p;
+  int mode;  // 0 none, 1 same shape, 2 source is the stride-2 subsampled tensor [B,H/2,W/2,C], 3 [B][C] / (H W)
+};
+__device__ __forceinline__ float src_at(const Src& s, size_t n, int y, int x, int c, int H, int W, int C) {
+  if (s.mode == 1) return s.p[((n * H + y) * W + x) * C + c];
+  if (s.mode == 2) {
+    if ((y | x) & 1) return 0.f;
+    return s.p[((n * (H / 2) + (y >> 1)) * (W / 2) + (x >> 1)) * C + c];
+  }
+  if (s.mode == 3) return s.p[n * C + c] / static_cast<float>(H * W);
+  return 0.f;
+}
+
+// E = (g0 + g1) * [o > 0]
+__global__ void __launch_bounds__(256) mask_relu_kernel(Src g0, Src g1, const uint16_t* __restrict__ o, int B, int H,
+                                                        int W, int C, float* __restrict__ E) {
+  const size_t total = static_cast<size_t>(B) * H * W * C;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const int x = static_cast<int>((i / C) % W);
+    const int y = static_cast<int>((i / (static_cast<size_t>(C) * W)) % H);
+    const size_t n = i / (static_cast<size_t>(C) * W * H);
+    const float g = src_at(g0, n, y, x, c, H, W, C) + src_at(g1, n, y, x, c, H, W, C);
+    E[i] = from_bf16(o[i]) > 0.f ? g : 0.f;
+  }
+}
+
+// dz = up * (relu ? a > 0 : 1) * (scale ? scale[n] : 1);  bsum[c] += (sum dz, sum dz xhat), xhat = (y - mean) rstd
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ up, const uint16_t* __restrict__ a,
+                                                            int relu, const float* __restrict__ scale,
+                                                            int rows_per_sample, const float* __restrict__ y,
+                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                            int M, int C, int rows_per_block,
+                                                            double* __restrict__ bsum) {
+  const int m0 = blockIdx.x * rows_per_block;
+  const int m1 = min(m0 + rows_per_block, M);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float mu = mean[c], rs = rstd[c];
+    double s1 = 0.0, s2 = 0.0;
+    for (int m = m0; m < m1; ++m) {
+      const size_t idx = static_cast<size_t>(m) * C + c;
+      float dz = up[idx];
+      if (relu && !(from_bf16(a[idx]) > 0.f)) dz = 0.f;
+      if (scale != nullptr) dz *= scale[m / rows_per_sample];
+      s1 += static_cast<double>(dz);
+      s2 += static_cast<double>(dz) * static_cast<double>((y[idx] - mu) * rs);
+    }
+    atomicAdd(&bsum[2 * c], s1);
+    atomicAdd(&bsum[2 * c + 1], s2);
+  }
+}
+
+// dy = gamma rstd (dz - S1 / M - xhat S2 / M), bf16; 4 channels per thread
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ up, const uint16_t* __restrict__ a,
+                                                           int relu, const float* __restrict__ scale,
+                                                           int rows_per_sample, const float* __restrict__ y,
+                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                           const float* __restrict__ gamma,
+                                                           const double* __restrict__ bsum, size_t M, int C,
+                                                           uint16_t* __restrict__ dy) {
+  const size_t total = M * C;
+  const float invM = 1.0f / static_cast<float>(M);
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const size_t m = i / C;
+    float dz = up[i];
+    if (relu && !(from_bf16(a[i]) > 0.f)) dz = 0.f;
+    if (scale != nullptr) dz *= scale[m / rows_per_sample];
+    const float rs = rstd[c];
+    const float xhat = (y[i] - mean[c]) * rs;
+    const float s1 = static_cast<float>(bsum[2 * c]), s2 = static_cast<float>(bsum[2 * c + 1]);
+    dy[i] = to_bf16(gamma[c] * rs * (dz - s1 * invM - xhat * s2 * invM));
+  }
+}
+
+__global__ void bn_bwd_params_kernel(const double* __restrict__ bsum, int C, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  dbeta[c] = static_cast<float>(bsum[2 * c]);
+  dgamma[c] = static_cast<float>(bsum[2 * c + 1]);
+}
+
+// dxin[n,iy,ix,c] = sum over the taps (ky,kx) and output pixels (oy,ox) with oy*stride + ky - 1 == iy (same for x) of
+// dcol[(n,oy,ox)][(ky*3+kx) * C + c]   (3x3, pad 1)
+__global__ void __launch_bounds__(256) col2im3_kernel(const float* __restrict__ dcol, int B, int H, int W, int C,
+                                                      int stride, int Ho, int Wo, float* __restrict__ dxin) {
+  const size_t total = static_cast<size_t>(B) * H * W * C;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const int ix = static_cast<int>((i / C) % W);
+    const int iy = static_cast<int>((i / (static_cast<size_t>(C) * W)) % H);
+    const size_t n = i / (static_cast<size_t>(C) * W * H);
+    float acc = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int ty = iy + 1 - ky;
+      if (ty < 0 || ty % stride != 0) continue;
+      const int oy = ty / stride;
+      if (oy >= Ho) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int tx = ix + 1 - kx;
+        if (tx < 0 || tx % stride != 0) continue;
+        const int ox = tx / stride;
+        if (ox >= Wo) continue;
+        acc += dcol[((n * Ho + oy) * Wo + ox) * (static_cast<size_t>(9) * C) + (ky * 3 + kx) * C + c];
+      }
+    }
+    dxin[i] = acc;
+  }
+}
+
+// Backward of max_pool2d(3, 2, 1) as a gather: the gradient of an output window goes to the FIRST maximum of the
+// window in row-major scan order (torch's argmax); an input pixel collects from the (up to four) windows it wins.
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(Src g0, Src g1, const uint16_t* __restrict__ in, int B, int H,
+                                                          int W, int C, float* __restrict__ gin) {
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const size_t total = static_cast<size_t>(B) * H * W * C;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const int ix = static_cast<int>((i / C) % W);
+    const int iy = static_cast<int>((i / (static_cast<size_t>(C) * W)) % H);
+    const size_t n = i / (static_cast<size_t>(C) * W * H);
+    const float mine = from_bf16(in[i]);
+    float acc = 0.f;
+    for (int oy = max(0, (iy - 1 + 1) / 2); oy <= min(Ho - 1, (iy + 1) / 2); ++oy)
+      for (int ox = max(0, (ix - 1 + 1) / 2); ox <= min(Wo - 1, (ix + 1) / 2); ++ox) {
+        // is (iy, ix) the first maximum of window (oy, ox)?
+        bool win = true;
+        for (int ky = 0; ky < 3 && win; ++ky)
+          for (int kx = 0; kx < 3; ++kx) {
+            const int yy = oy * 2 + ky - 1, xx = ox * 2 + kx - 1;
+            if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+            const float v = from_bf16(in[((n * H + yy) * W + xx) * C + c]);
+            const bool before = (yy < iy) || (yy == iy && xx < ix);
+            if (v > mine || (before && v == mine)) {
+              win = false;
+              break;
+            }
+          }
+        if (win) acc += src_at(g0, n, oy, ox, c, Ho, Wo, C) + src_at(g1, n, oy, ox, c, Ho, Wo, C);
+      }
+    gin[i] = acc;
+  }
+}
+
+// Stem weight gradient: dw[co][tap] = sum over output pixels of dy[pix][co] * x[n, 2 oy + ky - 3, 2 ox + kx - 3]
+// (dy bf16 [B*Ho*Wo][64]).  One block per chunk of pixels: thread = (co, tap group), partial sums reduced by atomics.
+__global__ void __launch_bounds__(256) stem_wgrad_kernel(const uint16_t* __restrict__ dy, const float* __restrict__ x,
+                                                         int B, int H, int W, int pix_per_block,
+                                                         float* __restrict__ dw) {
+  const int Ho = H / 2, Wo = W / 2;
+  const int co = threadIdx.x & 63, tg = threadIdx.x >> 6;  // 4 tap groups: taps tg, tg + 4, ...
+  const size_t total = static_cast<size_t>(B) * Ho * Wo;
+  const size_t p0 = static_cast<size_t>(blockIdx.x) * pix_per_block;
+  const size_t p1 = min(p0 + pix_per_block, total);
+  float acc[13];
+#pragma unroll
+  for (int j = 0; j < 13; ++j) acc[j] = 0.f;
+  for (size_t pix = p0; pix < p1; ++pix) {
+    const int ox = static_cast<int>(pix % Wo), oy = static_cast<int>((pix / Wo) % Ho);
+    const size_t n = pix / (static_cast<size_t>(Wo) * Ho);
+    const float g = from_bf16(dy[pix * 64 + co]);
+#pragma unroll
+    for (int j = 0; j < 13; ++j) {
+      const int tap = tg + 4 * j;
+      if (tap < 49) {
+        const int iy = oy * 2 + tap / 7 - 3, ix = ox * 2 + tap % 7 - 3;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) acc[j] = fmaf(g, __ldg(x + (n * H + iy) * W + ix), acc[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 13; ++j) {
+    const int tap = tg + 4 * j;
+    if (tap < 49) atomicAdd(&dw[co * 49 + tap], acc[j]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- weight gradient GEMM
+// dw[co][k] += sum_m dy[m][co] * x[m][k] over this CTA's slice of rows m.  Both operands are row-major [M][.] bf16
+// matrices, i.e. MN-major UMMA operands (the contraction index m is the ROW): TMA stages [128 rows x 64 columns] boxes
+// as 128-byte swizzled rows and one MMA (M = 128 co, N = 128 k, K = 16) consumes sixteen rows - the descriptor form of
+// conv_wgrad.cu / attention_bwd_tc.cu.  Two stages; thread 0 produces and issues, all 128 threads drain the accumulator
+// (one co row each) with red.global.add.f32.
+constexpr int kWgRows = 128;                         // rows of m per stage
+constexpr int kWgBox = kWgRows * 128;                // bytes of one [128 x 64] bf16 box
+constexpr int kWgStage = 4 * kWgBox;                 // dy x 2 column chunks + x x 2 column chunks
+constexpr int kWgSmem = 2 * kWgStage + 1024 + 64;
+
+struct FlatWgradParams {
+  CUtensorMap tmap_dy;  // {Cout, M}, box {64, 128}
+  CUtensorMap tmap_x;   // {K, M}, box {64, 128}
+  float* dw;
+  int M, Cout, K, chunks_per_split, nchunks;
+};
+
+__device__ __forceinline__ uint64_t desc_mn128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(128, 1) flat_wgrad_tc_kernel(const __grid_constant__ FlatWgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kWgStage);
+  uint64_t* full = bars;       // [2]
+  uint64_t* empty = bars + 2;  // [2]
+  uint64_t* done = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  const int warp = threadIdx.x >> 5;
+  const int k0 = blockIdx.x * 128, co0 = blockIdx.y * 128;
+  const int c_begin = blockIdx.z * p.chunks_per_split;
+  const int c_end = min(c_begin + p.chunks_per_split, p.nchunks);
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tmap_dy);
+    tma_prefetch_desc(&p.tmap_x);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (c_begin >= c_end) {  // an empty slice (the split count does not divide the chunk count)
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+      tc_fence_after();
+      tmem_dealloc(tmem_base, 128);
+    }
+    return;
+  }
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = umma_idesc_f16(128, 128, 1u) | (1u << 15) | (1u << 16);  // bf16, A and B MN-major
+    const uint32_t base = smem_u32(smem);
+    auto load = [&](int c, int st) {
+      uint8_t* s = smem + st * kWgStage;
+      mbar_arrive_expect_tx(&full[st], static_cast<uint32_t>(kWgStage));
+      tma_load_2d(s, &p.tmap_dy, &full[st], co0, c * kWgRows);
+      tma_load_2d(s + kWgBox, &p.tmap_dy, &full[st], co0 + 64, c * kWgRows);
+      tma_load_2d(s + 2 * kWgBox, &p.tmap_x, &full[st], k0, c * kWgRows);
+      tma_load_2d(s + 3 * kWgBox, &p.tmap_x, &full[st], k0 + 64, c * kWgRows);
+    };
+    auto mma = [&](int st, bool first) {
+      const uint32_t a_addr = base + st * kWgStage, b_addr = a_addr + 2 * kWgBox;
+#pragma unroll
+      for (int j = 0; j < kWgRows / 16; ++j) {
+        const uint32_t ko = static_cast<uint32_t>(j) * 16u * 128u;
+        umma_f16_ss(tmem_base, desc_mn128(a_addr + ko, kWgBox), desc_mn128(b_addr + ko, kWgBox), idesc,
+                    (first && j == 0) ? 0u : 1u);
+      }
+    };
+    uint32_t full_ph[2] = {0, 0}, empty_ph[2] = {0, 0};
+    int uses[2] = {0, 0};
+    load(c_begin, 0);
+    uses[0] = 1;
+    for (int c = c_begin; c < c_end; ++c) {
+      const int st = (c - c_begin) & 1;
+      if (c + 1 < c_end) {  // prefetch the next chunk into the other stage once its previous MMAs are done
+        const int nst = st ^ 1;
+        if (uses[nst] > 0) {
+          mbar_wait(&empty[nst], empty_ph[nst]);
+          empty_ph[nst] ^= 1;
+        }
+        load(c + 1, nst);
+        ++uses[nst];
+      }
+      mbar_wait(&full[st], full_ph[st]);
+      full_ph[st] ^= 1;
+      tc_fence_after();
+      mma(st, c == c_begin);
+      umma_commit(&empty[st]);
+    }
+    umma_commit(done);
+  }
+  mbar_wait(done, 0);
+  tc_fence_after();
+  const int co = co0 + static_cast<int>(threadIdx.x);
+  const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+#pragma unroll 1
+  for (int c0 = 0; c0 < 128; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld_32x32(tmem_base + lane_off + c0, v);
+    tmem_ld_wait();
+    if (co < p.Cout) {
+      float* row = p.dw + static_cast<size_t>(co) * p.K + k0 + c0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (k0 + c0 + j < p.K) atomicAdd(row + j, __uint_as_float(v[j]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 128);
+  }
+}
+
+int launch_flat_wgrad(const uint16_t* dy, const uint16_t* x, int M, int Cout, int K, float* dw, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CDDPM_CUDA(cudaFuncSetAttribute(flat_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem));
+    attr_set = true;
+  }
+  FlatWgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.dw = dw;
+  p.M = M;
+  p.Cout = Cout;
+  p.K = K;
+  p.nchunks = (M + kWgRows - 1) / kWgRows;
+  const uint32_t box[2] = {64u, static_cast<uint32_t>(kWgRows)};
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(Cout), static_cast<uint64_t>(M)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(Cout) * 2};
+    CDDPM_TRY(encode_tmap_16bit(&p.tmap_dy, dy, 2, dims, strides, box));
+  }
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(K) * 2};
+    CDDPM_TRY(encode_tmap_16bit(&p.tmap_x, x, 2, dims, strides, box));
+  }
+  const int tiles = ((K + 127) / 128) * ((Cout + 127) / 128);
+  int splits = (2 * 148 + tiles - 1) / tiles;
+  splits = std::max(1, std::min(splits, p.nchunks));
+  p.chunks_per_split = (p.nchunks + splits - 1) / splits;
+  splits = (p.nchunks + p.chunks_per_split - 1) / p.chunks_per_split;
+  dim3 grid((K + 127) / 128, (Cout + 127) / 128, splits);
+  flat_wgrad_tc_kernel<<<grid, 128, kWgSmem, stream>>>(p);
+  return check_launch("flat_wgrad_tc_kernel");
+}
+
+}  // namespace
+
+int launch_flat_wgrad_bf16(const void* dy, const void* x, int M, int Cout, int K, float* dw, cudaStream_t stream) {
+  if (!dy || !x || !dw) return fail(kInvalidArgument, "flat_wgrad: null pointer");
+  if (M < 1 || Cout < 8 || K < 8 || Cout % 8 != 0 || K % 8 != 0)
+    return fail(kInvalidArgument, "flat_wgrad: Cout and K must be multiples of 8");
+  return launch_flat_wgrad(reinterpret_cast<const uint16_t*>(dy), reinterpret_cast<const uint16_t*>(x), M, Cout, K, dw,
+                           stream);
+}
+
+// ================================================================================================ engine
+ResNetTrainEngine::~ResNetTrainEngine() {
+  free_acts();
+  for (void* p : owned_) cudaFree(p);
+}
+
+void ResNetTrainEngine::free_acts() {
+  for (void* p : act_owned_) cudaFree(p);
+  act_owned_.clear();
+  fwd_ops_.clear();
+  bwd_ops_.clear();
+  planned_B_ = 0;
+  forward_done_ = false;
+}
+
+template <typename T>
+int ResNetTrainEngine::dalloc(T** p, size_t n, std::vector<void*>* pool) {
+  void* q = nullptr;
+  CDDPM_CUDA(cudaMalloc(&q, n * sizeof(T) + 1024));
+  pool->push_back(q);
+  *p = reinterpret_cast<T*>(q);
+  return kOk;
+}
+
+int ResNetTrainEngine::add_entry(const std::string& name, int64_t numel, int is_param) {
+  Entry e;
+  e.name = name;
+  e.numel = numel;
+  e.is_param = is_param;
+  if (is_param) {
+    e.goff = grad_total_;
+    grad_total_ += (numel + 3) & ~int64_t(3);  // 16-byte aligned slots
+  }
+  entries_.push_back(e);
+  return static_cast<int>(entries_.size()) - 1;
+}
+
+int ResNetTrainEngine::add_unit(const std::string& conv, const std::string& bn, int cin, int cout, int k, int stride,
+                                int pad) {
+  Unit u;
+  u.cin = cin;
+  u.cout = cout;
+  u.k = k;
+  u.stride = stride;
+  u.pad = pad;
+  u.e_w = add_entry(conv + ".weight", static_cast<int64_t>(cout) * cin * k * k, 1);
+  u.e_gamma = add_entry(bn + ".weight", cout, 1);
+  u.e_beta = add_entry(bn + ".bias", cout, 1);
+  u.e_mean = add_entry(bn + ".running_mean", cout, 0);
+  u.e_var = add_entry(bn + ".running_var", cout, 0);
+  if (!(cin == 1)) {
+    const size_t K = static_cast<size_t>(cin) * k * k;
+    CDDPM_TRY(dalloc(&u.panel, static_cast<size_t>(cout) * K, &owned_));
+    CDDPM_TRY(dalloc(&u.panel_t, static_cast<size_t>(cout) * K, &owned_));
+  }
+  units_.push_back(u);
+  return kOk;
+}
+
+int ResNetTrainEngine::init(int image_h, int image_w, int cond_dim) {
+  H_ = image_h;
+  W_ = image_w;
+  cond_dim_ = cond_dim;
+  if (image_h % 32 != 0 || image_w % 32 != 0) return fail(kUnsupported, "encoder: image size must be a multiple of 32");
+  CDDPM_TRY(add_unit("conv1", "bn1", 1, 64, 7, 2, 3));  // unit 0: the stem (direct kernels)
+  const int layers[4] = {3, 4, 6, 3};
+  const int widths[4] = {64, 128, 256, 512};
+  int cin = 64;
+  for (int li = 0; li < 4; ++li) {
+    for (int bi = 0; bi < layers[li]; ++bi) {
+      const std::string p = "layer" + std::to_string(li + 1) + "." + std::to_string(bi);
+      const int w = widths[li];
+      const int stride = (bi == 0 && li > 0) ? 2 : 1;
+      Block b;
+      CDDPM_TRY(add_unit(p + ".conv1", p + ".bn1", cin, w, 1, 1, 0));
+      b.c1 = static_cast<int>(units_.size()) - 1;
+      CDDPM_TRY(add_unit(p + ".conv2", p + ".bn2", w, w, 3, stride, 1));
+      b.c2 = static_cast<int>(units_.size()) - 1;
+      CDDPM_TRY(add_unit(p + ".conv3", p + ".bn3", w, 4 * w, 1, 1, 0));
+      b.c3 = static_cast<int>(units_.size()) - 1;
+      if (bi == 0) {
+        CDDPM_TRY(add_unit(p + ".downsample.0", p + ".downsample.1", cin, 4 * w, 1, stride, 0));
+        b.down = static_cast<int>(units_.size()) - 1;
+      }
+      blocks_.push_back(b);
+      cin = 4 * w;
+    }
+  }
+  e_fc_w_ = add_entry("fc.weight", static_cast<int64_t>(cond_dim) * 2048, 1);
+  e_fc_b_ = add_entry("fc.bias", cond_dim, 1);
+  return kOk;
+}
+
+int ResNetTrainEngine::entry_info(int i, const char** name, int64_t* numel, int* is_param) const {
+  if (i < 0 || i >= entry_count()) return fail(kInvalidArgument, "entry index out of range");
+  *name = entries_[i].name.c_str();
+  *numel = entries_[i].numel;
+  *is_param = entries_[i].is_param;
+  return kOk;
+}
+
+int ResNetTrainEngine::grad_offset(int i, int64_t* off) const {
+  if (i < 0 || i >= entry_count()) return fail(kInvalidArgument, "entry index out of range");
+  *off = entries_[i].goff;
+  return kOk;
+}
+
+int ResNetTrainEngine::push_gemm(std::vector<std::function<int(cudaStream_t)>>* ops, const void* a, int rows, int K,
+                                 const void* panel, int N, void* out_f32) {
+  ConvDesc d;
+  d.num_src = 1;
+  d.src[0] = a;
+  d.src_c[0] = K;
+  d.src_taps[0] = 1;
+  d.flat_rows = rows;
+  d.Cout = N;
+  d.wpacked = panel;
+  d.out = out_f32;
+  d.out_is_f32 = 1;
+  d.ab_format = 1;  // bf16
+  auto p = std::make_shared<ConvIgemmParams>();
+  CDDPM_TRY(build_conv_params(d, p.get()));
+  ops->push_back([p](cudaStream_t s) { return launch_conv_igemm(*p, s); });
+  return kOk;
+}
+
+// conv (im2col + GEMM) -> batch statistics -> finalize (+ running statistics); the apply step is pushed by the caller
+int ResNetTrainEngine::plan_unit_forward(Unit& u, const uint16_t* in, int Hin, int Win, int B) {
+  u.in = in;
+  u.Hin = Hin;
+  u.Win = Win;
+  u.Hout = (Hin + 2 * u.pad - u.k) / u.stride + 1;
+  u.Wout = (Win + 2 * u.pad - u.k) / u.stride + 1;
+  const int M = B * u.Hout * u.Wout;
+  const int K = u.cin * u.k * u.k;
+  const uint16_t* operand = in;
+  if (u.k > 1 || u.stride > 1) {
+    CDDPM_TRY(dalloc(&u.col, static_cast<size_t>(M) * K, &act_owned_));
+    uint16_t* col = u.col;
+    const int cin = u.cin, k = u.k, stride = u.stride, pad = u.pad, ho = u.Hout, wo = u.Wout;
+    fwd_ops_.push_back([=](cudaStream_t s) {
+      const size_t total = static_cast<size_t>(B) * ho * wo * k * k * (cin / 8);
+      im2col_kernel<<<grid_for(total), 256, 0, s>>>(in, col, B, Hin, Win, cin, k, stride, pad, ho, wo);
+      return check_launch("im2col_kernel");
+    });
+    operand = u.col;
+  }
+  CDDPM_TRY(dalloc(&u.y, static_cast<size_t>(M) * u.cout, &act_owned_));
+  CDDPM_TRY(dalloc(&u.stats, static_cast<size_t>(u.cout) * 2, &act_owned_));
+  CDDPM_TRY(dalloc(&u.mean, static_cast<size_t>(u.cout), &act_owned_));
+  CDDPM_TRY(dalloc(&u.rstd, static_cast<size_t>(u.cout), &act_owned_));
+  CDDPM_TRY(dalloc(&u.a, static_cast<size_t>(M) * u.cout, &act_owned_));
+  CDDPM_TRY(push_gemm(&fwd_ops_, operand, M, K, u.panel, u.cout, u.y));
+  {
+    float* y = u.y;
+    double* stats = u.stats;
+    float *mean = u.mean, *rstd = u.rstd;
+    const int C = u.cout, e_mean = u.e_mean, e_var = u.e_var;
+    ResNetTrainEngine* self = this;
+    fwd_ops_.push_back([=](cudaStream_t s) {
+      CDDPM_CUDA(cudaMemsetAsync(stats, 0, static_cast<size_t>(C) * 2 * sizeof(double), s));
+      const int rpb = std::max(8, (M + 591) / 592);
+      bn_stats_kernel<<<(M + rpb - 1) / rpb, 256, 0, s>>>(y, M, C, rpb, stats);
+      CDDPM_TRY(check_launch("bn_stats_kernel"));
+      bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(stats, M, C, mean, rstd,
+                                                        const_cast<float*>(self->values_[e_mean]),
+                                                        const_cast<float*>(self->values_[e_var]));
+      return check_launch("bn_finalize_kernel");
+    });
+  }
+  return kOk;
+}
+
+// BatchNorm backward (the upstream gradient and its options are bound by the caller through `up`), weight gradient,
+// data gradient.  Pushes: reduce, params, apply, wgrad, unpack, [dgrad, col2im].
+int ResNetTrainEngine::plan_unit_backward(Unit& u, int B, bool need_dx) {
+  const int M = B * u.Hout * u.Wout;
+  const int K = u.cin * u.k * u.k;
+  CDDPM_TRY(dalloc(&u.dwp, static_cast<size_t>(u.cout) * K, &act_owned_));
+  {
+    const uint16_t* dy = u.dy;
+    const uint16_t* operand = (u.col != nullptr) ? u.col : u.in;
+    float* dwp = u.dwp;
+    const int cout = u.cout, cin = u.cin, taps = u.k * u.k, e_w = u.e_w;
+    ResNetTrainEngine* self = this;
+    bwd_ops_.push_back([=](cudaStream_t s) {
+      CDDPM_CUDA(cudaMemsetAsync(dwp, 0, static_cast<size_t>(cout) * K * sizeof(float), s));
+      CDDPM_TRY(launch_flat_wgrad(dy, operand, M, cout, K, dwp, s));
+      float* g = self->cur_grads_ + self->entries_[e_w].goff;
+      unpack_grad_kernel<<<grid_for(static_cast<size_t>(cout) * K), 256, 0, s>>>(dwp, cout, cin, taps, g);
+      return check_launch("unpack_grad_kernel");
+    });
+  }
+  if (!need_dx) return kOk;
+  CDDPM_TRY(dalloc(&u.dx, static_cast<size_t>(M) * K, &act_owned_));
+  CDDPM_TRY(push_gemm(&bwd_ops_, u.dy, M, u.cout, u.panel_t, K, u.dx));
+  if (u.k == 3) {
+    const size_t n_in = static_cast<size_t>(B) * u.Hin * u.Win * u.cin;
+    CDDPM_TRY(dalloc(&u.dxin, n_in, &act_owned_));
+    const float* dcol = u.dx;
+    float* dxin = u.dxin;
+    const int H = u.Hin, W = u.Win, C = u.cin, stride = u.stride, ho = u.Hout, wo = u.Wout;
+    bwd_ops_.push_back([=](cudaStream_t s) {
+      col2im3_kernel<<<grid_for(n_in), 256, 0, s>>>(dcol, B, H, W, C, stride, ho, wo, dxin);
+      return check_launch("col2im3_kernel");
+    });
+  } else {
+    u.dxin = u.dx;  // 1x1: the GEMM output is the data gradient (at the output resolution when strided)
+  }
+  return kOk;
+}
+
+int ResNetTrainEngine::plan(int B) {
+  free_acts();
+  ResNetTrainEngine* self = this;
+  // ---- parameter panels (every forward: the optimizer changed the weights)
+  for (size_t ui = 1; ui < units_.size(); ++ui) {
+    const Unit u = units_[ui];
+    fwd_ops_.push_back([=](cudaStream_t s) {
+      const size_t total = static_cast<size_t>(u.cout) * u.cin * u.k * u.k;
+      pack_panels_kernel<<<grid_for(total), 256, 0, s>>>(self->values_[u.e_w], u.cout, u.cin, u.k * u.k, u.panel, u.panel_t);
+      return check_launch("pack_panels_kernel");
+    });
+  }
+  // ---- stem: conv 7x7 s2 (raw) -> BN (batch statistics) + ReLU -> maxpool 3x3 s2
+  Unit& st = units_[0];
+  st.Hin = H_;
+  st.Win = W_;
+  st.Hout = H_ / 2;
+  st.Wout = W_ / 2;
+  const int Ms = B * st.Hout * st.Wout;
+  CDDPM_TRY(dalloc(&st.y, static_cast<size_t>(Ms) * 64, &act_owned_));
+  CDDPM_TRY(dalloc(&st.stats, 128, &act_owned_));
+  CDDPM_TRY(dalloc(&st.mean, 64, &act_owned_));
+  CDDPM_TRY(dalloc(&st.rstd, 64, &act_owned_));
+  CDDPM_TRY(dalloc(&st.a, static_cast<size_t>(Ms) * 64, &act_owned_));
+  {
+    float* y = st.y;
+    double* stats = st.stats;
+    float *mean = st.mean, *rstd = st.rstd;
+    uint16_t* a = st.a;
+    const int Hin = H_, Win = W_;
+    const Unit u0 = st;
+    fwd_ops_.push_back([=](cudaStream_t s) {
+      const size_t total = static_cast<size_t>(Ms);
+      stem_raw_kernel<<<static_cast<int>(std::min<size_t>((total + 31) / 32, 148 * 8)), 256, 0, s>>>(
+          self->cur_x_, self->values_[u0.e_w], y, B, Hin, Win);
+      CDDPM_TRY(check_launch("stem_raw_kernel"));
+      CDDPM_CUDA(cudaMemsetAsync(stats, 0, 128 * sizeof(double), s));
+      const int rpb = std::max(8, (Ms + 591) / 592);
+      bn_stats_kernel<<<(Ms + rpb - 1) / rpb, 256, 0, s>>>(y, Ms, 64, rpb, stats);
+      CDDPM_TRY(check_launch("bn_stats_kernel"));
+      bn_finalize_kernel<<<1, 128, 0, s>>>(stats, Ms, 64, mean, rstd, const_cast<float*>(self->values_[u0.e_mean]),
+                                           const_cast<float*>(self->values_[u0.e_var]));
+      CDDPM_TRY(check_launch("bn_finalize_kernel"));
+      bn_apply_kernel<<<grid_for(static_cast<size_t>(Ms) * 16), 256, 0, s>>>(
+          y, mean, rstd, self->values_[u0.e_gamma], self->values_[u0.e_beta], nullptr, nullptr, 1, 1,
+          static_cast<size_t>(Ms), 64, a);
+      return check_launch("bn_apply_kernel");
+    });
+  }
+  int H = (st.Hout + 2 - 3) / 2 + 1, W = (st.Wout + 2 - 3) / 2 + 1;
+  CDDPM_TRY(dalloc(&pool_a_, static_cast<size_t>(B) * H * W * 64, &act_owned_));
+  {
+    const uint16_t* src = st.a;
+    uint16_t* dst = pool_a_;
+    const int h = st.Hout, w = st.Wout;
+    fwd_ops_.push_back([=](cudaStream_t s) {
+      const size_t total = static_cast<size_t>(B) * H * W * 64;
+      maxpool3s2_kernel<<<grid_for(total), 256, 0, s>>>(src, dst, B, h, w, 64);
+      return check_launch("maxpool3s2_kernel");
+    });
+  }
+  // ---- bottleneck blocks
+  const uint16_t* x = pool_a_;
+  int C = 64;
+  for (size_t bi = 0; bi < blocks_.size(); ++bi) {
+    Block& b = blocks_[bi];
+    Unit& c1 = units_[b.c1];
+    Unit& c2 = units_[b.c2];
+    Unit& c3 = units_[b.c3];
+    auto apply = [&](const Unit& u, const uint16_t* identity, bool scaled, int relu) {
+      const Unit uu = u;
+      const int M = B * u.Hout * u.Wout, rows = u.Hout * u.Wout;
+      const int blk = static_cast<int>(bi);
+      fwd_ops_.push_back([=](cudaStream_t s) {
+        const float* scale = (scaled && self->cur_drop_ != nullptr) ? self->cur_drop_ + static_cast<size_t>(blk) * B : nullptr;
+        bn_apply_kernel<<<grid_for(static_cast<size_t>(M) * (uu.cout / 4)), 256, 0, s>>>(
+            uu.y, uu.mean, uu.rstd, self->values_[uu.e_gamma], self->values_[uu.e_beta], identity, scale, rows, relu,
+            static_cast<size_t>(M), uu.cout, uu.a);
+        return check_launch("bn_apply_kernel");
+      });
+    };
+    CDDPM_TRY(plan_unit_forward(c1, x, H, W, B));
+    apply(c1, nullptr, false, 1);
+    CDDPM_TRY(plan_unit_forward(c2, c1.a, H, W, B));
+    apply(c2, nullptr, false, 1);
+    const uint16_t* identity = x;
+    if (b.down >= 0) {
+      Unit& cd = units_[b.down];
+      CDDPM_TRY(plan_unit_forward(cd, x, H, W, B));
+      apply(cd, nullptr, false, 0);
+      identity = cd.a;
+    }
+    CDDPM_TRY(plan_unit_forward(c3, c2.a, c2.Hout, c2.Wout, B));
+    apply(c3, identity, true, 1);  // out = relu(bn3(.) * drop_scale + identity)
+    x = c3.a;
+    H = c3.Hout;
+    W = c3.Wout;
+    C = c3.cout;
+  }
+  // ---- head: global average pool + fc
+  CDDPM_TRY(dalloc(&pooled_, static_cast<size_t>(B) * C, &act_owned_));
+  CDDPM_TRY(dalloc(&dpooled_, static_cast<size_t>(B) * C, &act_owned_));
+  {
+    const uint16_t* src = x;
+    float* pooled = pooled_;
+    const int hw = H * W, cc = C, cd = cond_dim_;
+    fwd_ops_.push_back([=](cudaStream_t s) {
+      avgpool_kernel<<<(B * cc + 255) / 256, 256, 0, s>>>(src, pooled, B, hw, cc);
+      CDDPM_TRY(check_launch("avgpool_kernel"));
+      return launch_linear(pooled, cc, self->values_[self->e_fc_w_], self->values_[self->e_fc_b_], self->cur_out_, cd, B,
+                           cc, cd, 0, s);
+    });
+  }
+
+  // ================================================================ backward plan (reverse order)
+  {
+    float *pooled = pooled_, *dpooled = dpooled_;
+    const int cc = C, cd = cond_dim_;
+    bwd_ops_.push_back([=](cudaStream_t s) {
+      float* g = self->cur_grads_;
+      CDDPM_TRY(launch_linear_bwd_weight(self->cur_dout_, cd, pooled, cc, 0, g + self->entries_[self->e_fc_w_].goff,
+                                         g + self->entries_[self->e_fc_b_].goff, B, cc, cd, s));
+      return launch_linear_bwd_input(self->cur_dout_, cd, self->values_[self->e_fc_w_], nullptr, 1, dpooled, cc, nullptr,
+                                     0, B, cc, cd, s);
+    });
+  }
+  GradSrc g0{dpooled_, 3}, g1{nullptr, 0};
+  for (int bi = static_cast<int>(blocks_.size()) - 1; bi >= 0; --bi) {
+    Block& b = blocks_[bi];
+    Unit& c1 = units_[b.c1];
+    Unit& c2 = units_[b.c2];
+    Unit& c3 = units_[b.c3];
+    const int Ho = c3.Hout, Wo = c3.Wout, C4 = c3.cout;
+    const int Mo = B * Ho * Wo;
+    CDDPM_TRY(dalloc(&b.E, static_cast<size_t>(Mo) * C4, &act_owned_));
+    {
+      const Src s0{g0.p, g0.mode}, s1{g1.p, g1.mode};
+      const uint16_t* o = c3.a;
+      float* E = b.E;
+      bwd_ops_.push_back([=](cudaStream_t s) {
+        mask_relu_kernel<<<grid_for(static_cast<size_t>(Mo) * C4), 256, 0, s>>>(s0, s1, o, B, Ho, Wo, C4, E);
+        return check_launch("mask_relu_kernel");
+      });
+    }
+    // BatchNorm backward of a unit given its upstream gradient
+    auto bn_bwd = [&](Unit& u, const float* up, int relu, bool scaled) -> int {
+      const int M = B * u.Hout * u.Wout, rows = u.Hout * u.Wout;
+      CDDPM_TRY(dalloc(&u.dy, static_cast<size_t>(M) * u.cout, &act_owned_));
+      CDDPM_TRY(dalloc(&u.bsum, static_cast<size_t>(u.cout) * 2, &act_owned_));
+      const Unit uu = u;
+      const int blk = bi;
+      bwd_ops_.push_back([=](cudaStream_t s) {
+        const float* scale = (scaled && self->cur_drop_ != nullptr) ? self->cur_drop_ + static_cast<size_t>(blk) * B : nullptr;
+        CDDPM_CUDA(cudaMemsetAsync(uu.bsum, 0, static_cast<size_t>(uu.cout) * 2 * sizeof(double), s));
+        const int rpb = std::max(8, (M + 591) / 592);
+        bn_bwd_reduce_kernel<<<(M + rpb - 1) / rpb, 256, 0, s>>>(up, uu.a, relu, scale, rows, uu.y, uu.mean, uu.rstd, M,
+                                                                 uu.cout, rpb, uu.bsum);
+        CDDPM_TRY(check_launch("bn_bwd_reduce_kernel"));
+        float* g = self->cur_grads_;
+        bn_bwd_params_kernel<<<(uu.cout + 127) / 128, 128, 0, s>>>(uu.bsum, uu.cout, g + self->entries_[uu.e_gamma].goff,
+                                                                   g + self->entries_[uu.e_beta].goff);
+        CDDPM_TRY(check_launch("bn_bwd_params_kernel"));
+        bn_bwd_apply_kernel<<<grid_for(static_cast<size_t>(M) * uu.cout), 256, 0, s>>>(
+            up, uu.a, relu, scale, rows, uu.y, uu.mean, uu.rstd, self->values_[uu.e_gamma], uu.bsum,
+            static_cast<size_t>(M), uu.cout, uu.dy);
+        return check_launch("bn_bwd_apply_kernel");
+      });
+      return kOk;
+    };
+    CDDPM_TRY(bn_bwd(c3, b.E, 0, true));
+    CDDPM_TRY(plan_unit_backward(c3, B, true));  // dx: gradient of a2 [Mo][w]
+    CDDPM_TRY(bn_bwd(c2, c3.dxin, 1, false));
+    CDDPM_TRY(plan_unit_backward(c2, B, true));  // dxin: gradient of a1 [M_in][w] after col2im
+    CDDPM_TRY(bn_bwd(c1, c2.dxin, 1, false));
+    CDDPM_TRY(plan_unit_backward(c1, B, true));  // dxin: gradient of the block input [M_in][cin]
+    GradSrc n0{c1.dxin, 1}, n1;
+    if (b.down >= 0) {
+      Unit& cd = units_[b.down];
+      CDDPM_TRY(bn_bwd(cd, b.E, 0, false));
+      CDDPM_TRY(plan_unit_backward(cd, B, true));  // [Mo][cin] at the output resolution
+      n1 = GradSrc{cd.dxin, cd.stride == 2 ? 2 : 1};
+    } else {
+      n1 = GradSrc{b.E, 1};
+    }
+    g0 = n0;
+    g1 = n1;
+  }
+  // ---- maxpool backward -> stem BatchNorm backward -> stem weight gradient
+  {
+    Unit& st0 = units_[0];
+    const int Hs = st0.Hout, Ws = st0.Wout;
+    CDDPM_TRY(dalloc(&stem_g_, static_cast<size_t>(Ms) * 64, &act_owned_));
+    CDDPM_TRY(dalloc(&st0.dy, static_cast<size_t>(Ms) * 64, &act_owned_));
+    CDDPM_TRY(dalloc(&st0.bsum, 128, &act_owned_));
+    const Src s0{g0.p, g0.mode}, s1{g1.p, g1.mode};
+    const Unit u0 = st0;
+    float* sg = stem_g_;
+    const int Hin = H_, Win = W_;
+    bwd_ops_.push_back([=](cudaStream_t s) {
+      maxpool_bwd_kernel<<<grid_for(static_cast<size_t>(Ms) * 64), 256, 0, s>>>(s0, s1, u0.a, B, Hs, Ws, 64, sg);
+      CDDPM_TRY(check_launch("maxpool_bwd_kernel"));
+      CDDPM_CUDA(cudaMemsetAsync(u0.bsum, 0, 128 * sizeof(double), s));
+      const int rpb = std::max(8, (Ms + 591) / 592);
+      bn_bwd_reduce_kernel<<<(Ms + rpb - 1) / rpb, 256, 0, s>>>(sg, u0.a, 1, nullptr, 1, u0.y, u0.mean, u0.rstd, Ms, 64,
+                                                                rpb, u0.bsum);
+      CDDPM_TRY(check_launch("bn_bwd_reduce_kernel"));
+      float* g = self->cur_grads_;
+      bn_bwd_params_kernel<<<1, 128, 0, s>>>(u0.bsum, 64, g + self->entries_[u0.e_gamma].goff,
+                                             g + self->entries_[u0.e_beta].goff);
+      CDDPM_TRY(check_launch("bn_bwd_params_kernel"));
+      bn_bwd_apply_kernel<<<grid_for(static_cast<size_t>(Ms) * 64), 256, 0, s>>>(
+          sg, u0.a, 1, nullptr, 1, u0.y, u0.mean, u0.rstd, self->values_[u0.e_gamma], u0.bsum, static_cast<size_t>(Ms),
+          64, u0.dy);
+      CDDPM_TRY(check_launch("bn_bwd_apply_kernel"));
+      float* gw = g + self->entries_[u0.e_w].goff;
+      CDDPM_CUDA(cudaMemsetAsync(gw, 0, 64 * 49 * sizeof(float), s));
+      const int ppb = std::max(64, (Ms + 591) / 592);
+      stem_wgrad_kernel<<<(Ms + ppb - 1) / ppb, 256, 0, s>>>(u0.dy, self->cur_x_, B, Hin, Win, ppb, gw);
+      return check_launch("stem_wgrad_kernel");
+    });
+  }
+  planned_B_ = B;
+  return kOk;
+}
+
+int ResNetTrainEngine::forward(const float* const* values, int count, const float* x, const float* drop_scale,
+                               float* out, int B, cudaStream_t stream) {
+  if (!values || !x || !out) return fail(kInvalidArgument, "encoder_train_forward: null pointer");
+  if (count != entry_count()) return fail(kInvalidArgument, "encoder_train_forward: wrong number of entries");
+  if (B < 1) return fail(kInvalidArgument, "encoder_train_forward: empty batch");
+  values_.assign(values, values + count);
+  for (const float* v : values_)
+    if (v == nullptr) return fail(kInvalidArgument, "encoder_train_forward: null entry pointer");
+  if (B != planned_B_) {
+    CDDPM_CUDA(cudaDeviceSynchronize());
+    int st = plan(B);
+    if (st != kOk) {
+      free_acts();
+      return st;
+    }
+  }
+  cur_x_ = x;
+  cur_drop_ = drop_scale;
+  cur_out_ = out;
+  for (auto& op : fwd_ops_) CDDPM_TRY(op(stream));
+  forward_done_ = true;
+  return kOk;
+}
+
+int ResNetTrainEngine::backward(const float* dout, float* grads, int B, cudaStream_t stream) {
+  if (!dout || !grads) return fail(kInvalidArgument, "encoder_train_backward: null pointer");
+  if (B != planned_B_ || !forward_done_) return fail(kNotReady, "encoder_train_backward: run the forward of this batch first");
+  cur_dout_ = dout;
+  cur_grads_ = grads;
+  for (auto& op : bwd_ops_) CDDPM_TRY(op(stream));
+  forward_done_ = false;
+  return kOk;
+}
+
+}  // namespace cddpm

@@ -187,6 +187,37 @@ int cddpm_encoder_set_param(cddpm_encoder_t* h, const char* name, const float* v
 int cddpm_encoder_forward(cddpm_encoder_t* h, const float* x, float* c, int B, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Condition encoder in TRAINING mode (DDPM_2D.training_step -> self(input), DDPM_2D.py:101-122, with the module in
+ * train(): batch-statistics BatchNorm, running statistics updated, timm DropPath on the residual branches; and
+ * loss.backward() through it).  Entries are the state_dict keys of the eval engine above (parameters and running
+ * statistics, no num_batches_tracked), passed as a table of the caller's fp32 device tensors on every forward: the
+ * optimizer owns the values, the engine re-packs its bf16 panels per step and updates the running statistics IN PLACE
+ * (momentum 0.1, unbiased variance).  Convolutions: tcgen05 GEMMs (forward, data gradient, weight gradient), bf16
+ * operands, fp32 accumulation; BatchNorm statistics / normalisation / summed gradients fp32 (sums in fp64).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct cddpm_encoder_train cddpm_encoder_train_t;
+int cddpm_encoder_train_create(int image_h, int image_w, int cond_dim, cddpm_encoder_train_t** out);
+void cddpm_encoder_train_destroy(cddpm_encoder_train_t* h);
+int cddpm_encoder_train_entry_count(const cddpm_encoder_train_t* h);
+int cddpm_encoder_train_entry_info(const cddpm_encoder_train_t* h, int index, const char** name, int64_t* numel,
+                                   int* is_param);
+/* Parameter gradients land in ONE flat fp32 buffer of grad_total floats; entry i at grad_offset (-1: a buffer). */
+int64_t cddpm_encoder_train_grad_total(const cddpm_encoder_train_t* h);
+int cddpm_encoder_train_grad_offset(const cddpm_encoder_train_t* h, int index, int64_t* offset);
+int cddpm_encoder_train_num_blocks(const cddpm_encoder_train_t* h);       /* bottleneck blocks (16) */
+int cddpm_encoder_train_launches(const cddpm_encoder_train_t* h, int backward);
+/* x [B,1,H,W] fp32 -> out [B,cond_dim] fp32, B >= 2.  drop_scale: NULL or [num_blocks][B] per-sample scale of each
+ * block's residual branch (timm DropPath: 0 or 1 / keep_prob). */
+int cddpm_encoder_train_forward(cddpm_encoder_train_t* h, const float* const* values, int count, const float* x,
+                                const float* drop_scale, float* out, int B, void* stream);
+/* The weight-gradient GEMM of the training encoder on its own: dw[co][k] += sum_m dy[m][co] * x[m][k] for row-major
+ * bf16 matrices dy [M][Cout], x [M][K] (the im2col'ed input of a convolution); dw fp32 [Cout][K] in the packed panel
+ * order, accumulated with atomics (zero it first).  tcgen05, both operands MN-major. */
+int cddpm_flat_wgrad(const void* dy, const void* x, int M, int Cout, int K, float* dw, void* stream);
+/* Backward of the LAST forward: dout [B,cond_dim] -> grads (overwritten). */
+int cddpm_encoder_train_backward(cddpm_encoder_train_t* h, const float* dout, float* grads, int B, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * gen_noise (src/utils/generate_noise.py:8-52): OpenSimplex-2D fractal field (octaves 6, persistence 0.8,
  * frequency 64 in the reference), bit-identical to the reference's float64 numba code.  perm_host is the 256-entry
  * permutation of generate_noise.py:214-232 in HOST memory.  out_f16 [B,1,H,W] (same field for every b) and/or
