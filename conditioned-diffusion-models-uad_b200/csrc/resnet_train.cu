@@ -116,20 +116,52 @@ __global__ void __launch_bounds__(256) stem_raw_kernel(const float* __restrict__
   }
 }
 
-// stats[c][0] += sum_m y[m][c], stats[c][1] += sum_m y[m][c]^2 (double atomics; the caller zeroes stats)
+// stats[c][0] += sum_m y[m][c], stats[c][1] += sum_m y[m][c]^2 (double atomics; the caller zeroes stats).
+// A block owns `rows_per_block` rows; thread = (4 channels, row lane): fp32 partial sums per thread over at most a few
+// dozen rows, combined across the row lanes in shared memory in float64, one atomic pair per channel and block.
 __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ y, int M, int C, int rows_per_block,
                                                        double* __restrict__ stats) {
+  __shared__ double red[256][8];
+  const int cv = C >> 2;  // float4 columns; 256 / cv row lanes share a column group (one lane when C > 1024)
   const int m0 = blockIdx.x * rows_per_block;
   const int m1 = min(m0 + rows_per_block, M);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    double s = 0.0, q = 0.0;
-    for (int m = m0; m < m1; ++m) {
-      const double v = static_cast<double>(y[static_cast<size_t>(m) * C + c]);
-      s += v;
-      q += v * v;
+  for (int c4 = threadIdx.x % cv; c4 < cv; c4 += (cv > 256 ? 256 : cv)) {
+    const int lane = cv > 256 ? 0 : threadIdx.x / cv;
+    const int nl = cv > 256 ? 1 : max(1, 256 / cv);
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+    if (lane < nl) {
+      for (int m = m0 + lane; m < m1; m += nl) {
+        const float4 v = *reinterpret_cast<const float4*>(y + static_cast<size_t>(m) * C + c4 * 4);
+        s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+        q[0] = fmaf(v.x, v.x, q[0]); q[1] = fmaf(v.y, v.y, q[1]); q[2] = fmaf(v.z, v.z, q[2]); q[3] = fmaf(v.w, v.w, q[3]);
+      }
     }
-    atomicAdd(&stats[2 * c], s);
-    atomicAdd(&stats[2 * c + 1], q);
+    if (nl == 1) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        atomicAdd(&stats[2 * (c4 * 4 + j)], static_cast<double>(s[j]));
+        atomicAdd(&stats[2 * (c4 * 4 + j) + 1], static_cast<double>(q[j]));
+      }
+      continue;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      red[threadIdx.x][j] = static_cast<double>(s[j]);
+      red[threadIdx.x][4 + j] = static_cast<double>(q[j]);
+    }
+    __syncthreads();
+    if (lane == 0) {
+      double t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int l = 0; l < nl; ++l)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] += red[l * cv + c4][j];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        atomicAdd(&stats[2 * (c4 * 4 + j)], t[j]);
+        atomicAdd(&stats[2 * (c4 * 4 + j) + 1], t[4 + j]);
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -193,7 +225,10 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
   }
 }
 
-__global__ void maxpool3s2_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, int B, int H, int W, int C) {
+// max_pool2d(3, 2, 1); arg[i] = window position (ky * 3 + kx) of the FIRST maximum in row-major scan order (torch's
+// argmax), kept for the backward pass.
+__global__ void maxpool3s2_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, uint8_t* __restrict__ arg,
+                                  int B, int H, int W, int C) {
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const size_t total = static_cast<size_t>(B) * Ho * Wo * C;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -202,13 +237,19 @@ __global__ void maxpool3s2_kernel(const uint16_t* __restrict__ in, uint16_t* __r
     const int ox = static_cast<int>((i / C) % Wo), oy = static_cast<int>((i / (static_cast<size_t>(C) * Wo)) % Ho);
     const size_t n = i / (static_cast<size_t>(C) * Wo * Ho);
     float m = -INFINITY;
+    int best = 0;
     for (int ky = 0; ky < 3; ++ky)
       for (int kx = 0; kx < 3; ++kx) {
         const int iy = oy * 2 + ky - 1, ix = ox * 2 + kx - 1;
         if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
-        m = fmaxf(m, from_bf16(in[((n * H + iy) * W + ix) * C + c]));
+        const float v = from_bf16(in[((n * H + iy) * W + ix) * C + c]);
+        if (v > m) {
+          m = v;
+          best = ky * 3 + kx;
+        }
       }
     out[i] = to_bf16(m);
+    arg[i] = static_cast<uint8_t>(best);
   }
 }
 
@@ -237,43 +278,110 @@ __device__ __forceinline__ float src_at(const Src& s, size_t n, int y, int x, in
   return 0.f;
 }
 
-// E = (g0 + g1) * [o > 0]
+__device__ __forceinline__ float4 src4_at(const Src& s, size_t n, int y, int x, int c, int H, int W, int C) {
+  if (s.mode == 1) return *reinterpret_cast<const float4*>(s.p + ((n * H + y) * W + x) * C + c);
+  if (s.mode == 2) {
+    if ((y | x) & 1) return make_float4(0.f, 0.f, 0.f, 0.f);
+    return *reinterpret_cast<const float4*>(s.p + ((n * (H / 2) + (y >> 1)) * (W / 2) + (x >> 1)) * C + c);
+  }
+  if (s.mode == 3) {
+    const float4 v = *reinterpret_cast<const float4*>(s.p + n * C + c);
+    const float r = 1.0f / static_cast<float>(H * W);
+    return make_float4(v.x * r, v.y * r, v.z * r, v.w * r);
+  }
+  return make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// E = (g0 + g1) * [o > 0]; 4 channels per thread
 __global__ void __launch_bounds__(256) mask_relu_kernel(Src g0, Src g1, const uint16_t* __restrict__ o, int B, int H,
                                                         int W, int C, float* __restrict__ E) {
-  const size_t total = static_cast<size_t>(B) * H * W * C;
+  const int cv = C >> 2;
+  const size_t total = static_cast<size_t>(B) * H * W * cv;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % C);
-    const int x = static_cast<int>((i / C) % W);
-    const int y = static_cast<int>((i / (static_cast<size_t>(C) * W)) % H);
-    const size_t n = i / (static_cast<size_t>(C) * W * H);
-    const float g = src_at(g0, n, y, x, c, H, W, C) + src_at(g1, n, y, x, c, H, W, C);
-    E[i] = from_bf16(o[i]) > 0.f ? g : 0.f;
+    const int c = static_cast<int>(i % cv) * 4;
+    const int x = static_cast<int>((i / cv) % W);
+    const int y = static_cast<int>((i / (static_cast<size_t>(cv) * W)) % H);
+    const size_t n = i / (static_cast<size_t>(cv) * W * H);
+    const float4 a = src4_at(g0, n, y, x, c, H, W, C), b = src4_at(g1, n, y, x, c, H, W, C);
+    const size_t idx = ((n * H + y) * W + x) * C + c;
+    const uint2 ov = *reinterpret_cast<const uint2*>(o + idx);
+    float4 e;
+    e.x = from_bf16(static_cast<uint16_t>(ov.x & 0xFFFF)) > 0.f ? a.x + b.x : 0.f;
+    e.y = from_bf16(static_cast<uint16_t>(ov.x >> 16)) > 0.f ? a.y + b.y : 0.f;
+    e.z = from_bf16(static_cast<uint16_t>(ov.y & 0xFFFF)) > 0.f ? a.z + b.z : 0.f;
+    e.w = from_bf16(static_cast<uint16_t>(ov.y >> 16)) > 0.f ? a.w + b.w : 0.f;
+    *reinterpret_cast<float4*>(E + idx) = e;
   }
 }
 
-// dz = up * (relu ? a > 0 : 1) * (scale ? scale[n] : 1);  bsum[c] += (sum dz, sum dz xhat), xhat = (y - mean) rstd
+// dz = up * (relu ? a > 0 : 1) * (scale ? scale[n] : 1);  bsum[c] += (sum dz, sum dz xhat), xhat = (y - mean) rstd.
+// Same tiling as bn_stats_kernel.
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ up, const uint16_t* __restrict__ a,
                                                             int relu, const float* __restrict__ scale,
                                                             int rows_per_sample, const float* __restrict__ y,
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
                                                             int M, int C, int rows_per_block,
                                                             double* __restrict__ bsum) {
+  __shared__ double red[256][8];
+  const int cv = C >> 2;
+  const int nl = cv > 256 ? 1 : max(1, 256 / cv);
   const int m0 = blockIdx.x * rows_per_block;
   const int m1 = min(m0 + rows_per_block, M);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float mu = mean[c], rs = rstd[c];
-    double s1 = 0.0, s2 = 0.0;
-    for (int m = m0; m < m1; ++m) {
-      const size_t idx = static_cast<size_t>(m) * C + c;
-      float dz = up[idx];
-      if (relu && !(from_bf16(a[idx]) > 0.f)) dz = 0.f;
-      if (scale != nullptr) dz *= scale[m / rows_per_sample];
-      s1 += static_cast<double>(dz);
-      s2 += static_cast<double>(dz) * static_cast<double>((y[idx] - mu) * rs);
+  for (int c4 = threadIdx.x % cv; c4 < cv; c4 += (cv > 256 ? 256 : cv)) {
+    const int lane = cv > 256 ? 0 : threadIdx.x / cv;
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    if (lane < nl) {
+      const float4 mu = *reinterpret_cast<const float4*>(mean + c4 * 4);
+      const float4 rs = *reinterpret_cast<const float4*>(rstd + c4 * 4);
+      for (int m = m0 + lane; m < m1; m += nl) {
+        const size_t idx = static_cast<size_t>(m) * C + c4 * 4;
+        float4 g = *reinterpret_cast<const float4*>(up + idx);
+        if (relu) {
+          const uint2 av = *reinterpret_cast<const uint2*>(a + idx);
+          if (!(from_bf16(static_cast<uint16_t>(av.x & 0xFFFF)) > 0.f)) g.x = 0.f;
+          if (!(from_bf16(static_cast<uint16_t>(av.x >> 16)) > 0.f)) g.y = 0.f;
+          if (!(from_bf16(static_cast<uint16_t>(av.y & 0xFFFF)) > 0.f)) g.z = 0.f;
+          if (!(from_bf16(static_cast<uint16_t>(av.y >> 16)) > 0.f)) g.w = 0.f;
+        }
+        if (scale != nullptr) {
+          const float sc = scale[m / rows_per_sample];
+          g.x *= sc; g.y *= sc; g.z *= sc; g.w *= sc;
+        }
+        const float4 v = *reinterpret_cast<const float4*>(y + idx);
+        s1[0] += g.x; s1[1] += g.y; s1[2] += g.z; s1[3] += g.w;
+        s2[0] = fmaf(g.x, (v.x - mu.x) * rs.x, s2[0]);
+        s2[1] = fmaf(g.y, (v.y - mu.y) * rs.y, s2[1]);
+        s2[2] = fmaf(g.z, (v.z - mu.z) * rs.z, s2[2]);
+        s2[3] = fmaf(g.w, (v.w - mu.w) * rs.w, s2[3]);
+      }
     }
-    atomicAdd(&bsum[2 * c], s1);
-    atomicAdd(&bsum[2 * c + 1], s2);
+    if (nl == 1) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        atomicAdd(&bsum[2 * (c4 * 4 + j)], static_cast<double>(s1[j]));
+        atomicAdd(&bsum[2 * (c4 * 4 + j) + 1], static_cast<double>(s2[j]));
+      }
+      continue;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      red[threadIdx.x][j] = static_cast<double>(s1[j]);
+      red[threadIdx.x][4 + j] = static_cast<double>(s2[j]);
+    }
+    __syncthreads();
+    if (lane == 0) {
+      double t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int l = 0; l < nl; ++l)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] += red[l * cv + c4][j];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        atomicAdd(&bsum[2 * (c4 * 4 + j)], t[j]);
+        atomicAdd(&bsum[2 * (c4 * 4 + j) + 1], t[4 + j]);
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -285,19 +393,46 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
                                                            const float* __restrict__ gamma,
                                                            const double* __restrict__ bsum, size_t M, int C,
                                                            uint16_t* __restrict__ dy) {
-  const size_t total = M * C;
+  const int cv = C >> 2;
+  const size_t total = M * cv;
   const float invM = 1.0f / static_cast<float>(M);
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % C);
-    const size_t m = i / C;
-    float dz = up[i];
-    if (relu && !(from_bf16(a[i]) > 0.f)) dz = 0.f;
-    if (scale != nullptr) dz *= scale[m / rows_per_sample];
-    const float rs = rstd[c];
-    const float xhat = (y[i] - mean[c]) * rs;
-    const float s1 = static_cast<float>(bsum[2 * c]), s2 = static_cast<float>(bsum[2 * c + 1]);
-    dy[i] = to_bf16(gamma[c] * rs * (dz - s1 * invM - xhat * s2 * invM));
+    const int c = static_cast<int>(i % cv) * 4;
+    const size_t m = i / cv;
+    const size_t idx = m * C + c;
+    float4 g = *reinterpret_cast<const float4*>(up + idx);
+    if (relu) {
+      const uint2 av = *reinterpret_cast<const uint2*>(a + idx);
+      if (!(from_bf16(static_cast<uint16_t>(av.x & 0xFFFF)) > 0.f)) g.x = 0.f;
+      if (!(from_bf16(static_cast<uint16_t>(av.x >> 16)) > 0.f)) g.y = 0.f;
+      if (!(from_bf16(static_cast<uint16_t>(av.y & 0xFFFF)) > 0.f)) g.z = 0.f;
+      if (!(from_bf16(static_cast<uint16_t>(av.y >> 16)) > 0.f)) g.w = 0.f;
+    }
+    if (scale != nullptr) {
+      const float sc = scale[m / rows_per_sample];
+      g.x *= sc; g.y *= sc; g.z *= sc; g.w *= sc;
+    }
+    const float4 v = *reinterpret_cast<const float4*>(y + idx);
+    const float4 mu = *reinterpret_cast<const float4*>(mean + c);
+    const float4 rs = *reinterpret_cast<const float4*>(rstd + c);
+    const float4 ga = *reinterpret_cast<const float4*>(gamma + c);
+    const float dz[4] = {g.x, g.y, g.z, g.w};
+    const float yy[4] = {v.x, v.y, v.z, v.w};
+    const float mm[4] = {mu.x, mu.y, mu.z, mu.w};
+    const float rr[4] = {rs.x, rs.y, rs.z, rs.w};
+    const float gg[4] = {ga.x, ga.y, ga.z, ga.w};
+    uint16_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float xhat = (yy[j] - mm[j]) * rr[j];
+      const float s1 = static_cast<float>(bsum[2 * (c + j)]), s2 = static_cast<float>(bsum[2 * (c + j) + 1]);
+      o[j] = to_bf16(gg[j] * rr[j] * (dz[j] - s1 * invM - xhat * s2 * invM));
+    }
+    uint2 pk;
+    pk.x = static_cast<uint32_t>(o[0]) | (static_cast<uint32_t>(o[1]) << 16);
+    pk.y = static_cast<uint32_t>(o[2]) | (static_cast<uint32_t>(o[3]) << 16);
+    *reinterpret_cast<uint2*>(dy + idx) = pk;
   }
 }
 
@@ -310,17 +445,18 @@ __global__ void bn_bwd_params_kernel(const double* __restrict__ bsum, int C, flo
 }
 
 // dxin[n,iy,ix,c] = sum over the taps (ky,kx) and output pixels (oy,ox) with oy*stride + ky - 1 == iy (same for x) of
-// dcol[(n,oy,ox)][(ky*3+kx) * C + c]   (3x3, pad 1)
-__global__ void __launch_bounds__(256) col2im3_kernel(const float* __restrict__ dcol, int B, int H, int W, int C,
+// dcol[(n,oy,ox)][(ky*3+kx) * C + c]   (3x3, pad 1; dcol bf16, sum in fp32); 4 channels per thread
+__global__ void __launch_bounds__(256) col2im3_kernel(const uint16_t* __restrict__ dcol, int B, int H, int W, int C,
                                                       int stride, int Ho, int Wo, float* __restrict__ dxin) {
-  const size_t total = static_cast<size_t>(B) * H * W * C;
+  const int cv = C >> 2;
+  const size_t total = static_cast<size_t>(B) * H * W * cv;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % C);
-    const int ix = static_cast<int>((i / C) % W);
-    const int iy = static_cast<int>((i / (static_cast<size_t>(C) * W)) % H);
-    const size_t n = i / (static_cast<size_t>(C) * W * H);
-    float acc = 0.f;
+    const int c = static_cast<int>(i % cv) * 4;
+    const int ix = static_cast<int>((i / cv) % W);
+    const int iy = static_cast<int>((i / (static_cast<size_t>(cv) * W)) % H);
+    const size_t n = i / (static_cast<size_t>(cv) * W * H);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
       const int ty = iy + 1 - ky;
@@ -333,16 +469,21 @@ __global__ void __launch_bounds__(256) col2im3_kernel(const float* __restrict__ 
         if (tx < 0 || tx % stride != 0) continue;
         const int ox = tx / stride;
         if (ox >= Wo) continue;
-        acc += dcol[((n * Ho + oy) * Wo + ox) * (static_cast<size_t>(9) * C) + (ky * 3 + kx) * C + c];
+        const uint2 v = *reinterpret_cast<const uint2*>(dcol + ((n * Ho + oy) * Wo + ox) * (static_cast<size_t>(9) * C) +
+                                                        (ky * 3 + kx) * C + c);
+        acc[0] += from_bf16(static_cast<uint16_t>(v.x & 0xFFFF));
+        acc[1] += from_bf16(static_cast<uint16_t>(v.x >> 16));
+        acc[2] += from_bf16(static_cast<uint16_t>(v.y & 0xFFFF));
+        acc[3] += from_bf16(static_cast<uint16_t>(v.y >> 16));
       }
     }
-    dxin[i] = acc;
+    *reinterpret_cast<float4*>(dxin + (((n * H + iy) * W + ix) * C + c)) = make_float4(acc[0], acc[1], acc[2], acc[3]);
   }
 }
 
-// Backward of max_pool2d(3, 2, 1) as a gather: the gradient of an output window goes to the FIRST maximum of the
-// window in row-major scan order (torch's argmax); an input pixel collects from the (up to four) windows it wins.
-__global__ void __launch_bounds__(256) maxpool_bwd_kernel(Src g0, Src g1, const uint16_t* __restrict__ in, int B, int H,
+// Backward of max_pool2d(3, 2, 1) as a gather over the stored argmax: an input pixel collects the gradient of the (up
+// to four) windows whose first maximum it is.
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(Src g0, Src g1, const uint8_t* __restrict__ arg, int B, int H,
                                                           int W, int C, float* __restrict__ gin) {
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const size_t total = static_cast<size_t>(B) * H * W * C;
@@ -352,34 +493,24 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(Src g0, Src g1, const 
     const int ix = static_cast<int>((i / C) % W);
     const int iy = static_cast<int>((i / (static_cast<size_t>(C) * W)) % H);
     const size_t n = i / (static_cast<size_t>(C) * W * H);
-    const float mine = from_bf16(in[i]);
     float acc = 0.f;
-    for (int oy = max(0, (iy - 1 + 1) / 2); oy <= min(Ho - 1, (iy + 1) / 2); ++oy)
-      for (int ox = max(0, (ix - 1 + 1) / 2); ox <= min(Wo - 1, (ix + 1) / 2); ++ox) {
-        // is (iy, ix) the first maximum of window (oy, ox)?
-        bool win = true;
-        for (int ky = 0; ky < 3 && win; ++ky)
-          for (int kx = 0; kx < 3; ++kx) {
-            const int yy = oy * 2 + ky - 1, xx = ox * 2 + kx - 1;
-            if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-            const float v = from_bf16(in[((n * H + yy) * W + xx) * C + c]);
-            const bool before = (yy < iy) || (yy == iy && xx < ix);
-            if (v > mine || (before && v == mine)) {
-              win = false;
-              break;
-            }
-          }
-        if (win) acc += src_at(g0, n, oy, ox, c, Ho, Wo, C) + src_at(g1, n, oy, ox, c, Ho, Wo, C);
+    for (int oy = max(0, iy / 2); oy <= min(Ho - 1, (iy + 1) / 2); ++oy)
+      for (int ox = max(0, ix / 2); ox <= min(Wo - 1, (ix + 1) / 2); ++ox) {
+        const int ky = iy - (oy * 2 - 1), kx = ix - (ox * 2 - 1);  // this pixel's position inside window (oy, ox)
+        if (arg[((n * Ho + oy) * Wo + ox) * C + c] == ky * 3 + kx)
+          acc += src_at(g0, n, oy, ox, c, Ho, Wo, C) + src_at(g1, n, oy, ox, c, Ho, Wo, C);
       }
     gin[i] = acc;
   }
 }
 
 // Stem weight gradient: dw[co][tap] = sum over output pixels of dy[pix][co] * x[n, 2 oy + ky - 3, 2 ox + kx - 3]
-// (dy bf16 [B*Ho*Wo][64]).  One block per chunk of pixels: thread = (co, tap group), partial sums reduced by atomics.
+// (dy bf16 [B*Ho*Wo][64]).  One block per chunk of pixels, thread = (co, tap group): every thread owns its (co, tap)
+// outputs, so a block writes its 64 x 49 partial sums to a scratch row without atomics (592 blocks adding into 3136
+// addresses cost 0.64 ms in the first version) and a second kernel adds the rows.
 __global__ void __launch_bounds__(256) stem_wgrad_kernel(const uint16_t* __restrict__ dy, const float* __restrict__ x,
                                                          int B, int H, int W, int pix_per_block,
-                                                         float* __restrict__ dw) {
+                                                         float* __restrict__ partial) {
   const int Ho = H / 2, Wo = W / 2;
   const int co = threadIdx.x & 63, tg = threadIdx.x >> 6;  // 4 tap groups: taps tg, tg + 4, ...
   const size_t total = static_cast<size_t>(B) * Ho * Wo;
@@ -401,23 +532,32 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const uint16_t* __restr
       }
     }
   }
+  float* row = partial + static_cast<size_t>(blockIdx.x) * (64 * 49);
 #pragma unroll
   for (int j = 0; j < 13; ++j) {
     const int tap = tg + 4 * j;
-    if (tap < 49) atomicAdd(&dw[co * 49 + tap], acc[j]);
+    if (tap < 49) row[co * 49 + tap] = acc[j];
   }
+}
+__global__ void stem_wgrad_reduce_kernel(const float* __restrict__ partial, int nblocks, float* __restrict__ dw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 64 * 49) return;
+  float s = 0.f;
+  for (int b = 0; b < nblocks; ++b) s += partial[static_cast<size_t>(b) * (64 * 49) + i];
+  dw[i] = s;
 }
 
 // ---------------------------------------------------------------------------------------------- weight gradient GEMM
 // dw[co][k] += sum_m dy[m][co] * x[m][k] over this CTA's slice of rows m.  Both operands are row-major [M][.] bf16
 // matrices, i.e. MN-major UMMA operands (the contraction index m is the ROW): TMA stages [128 rows x 64 columns] boxes
 // as 128-byte swizzled rows and one MMA (M = 128 co, N = 128 k, K = 16) consumes sixteen rows - the descriptor form of
-// conv_wgrad.cu / attention_bwd_tc.cu.  Two stages; thread 0 produces and issues, all 128 threads drain the accumulator
-// (one co row each) with red.global.add.f32.
+// conv_wgrad.cu / attention_bwd_tc.cu.  Three stages; thread 0 produces and issues, all 128 threads drain the accumulator
+// (one co row each) with red.global.add.v4.f32.
 constexpr int kWgRows = 128;                         // rows of m per stage
 constexpr int kWgBox = kWgRows * 128;                // bytes of one [128 x 64] bf16 box
 constexpr int kWgStage = 4 * kWgBox;                 // dy x 2 column chunks + x x 2 column chunks
-constexpr int kWgSmem = 2 * kWgStage + 1024 + 64;
+constexpr int kWgStages = 3;
+constexpr int kWgSmem = kWgStages * kWgStage + 1024 + 128;
 
 struct FlatWgradParams {
   CUtensorMap tmap_dy;  // {Cout, M}, box {64, 128}
@@ -439,11 +579,11 @@ __device__ __forceinline__ uint64_t desc_mn128(uint32_t smem_addr, uint32_t lbo_
 __global__ void __launch_bounds__(128, 1) flat_wgrad_tc_kernel(const __grid_constant__ FlatWgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kWgStage);
-  uint64_t* full = bars;       // [2]
-  uint64_t* empty = bars + 2;  // [2]
-  uint64_t* done = bars + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgStages * kWgStage);
+  uint64_t* full = bars;                // [kWgStages]
+  uint64_t* empty = bars + kWgStages;   // [kWgStages]
+  uint64_t* done = bars + 2 * kWgStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWgStages + 1);
   const int warp = threadIdx.x >> 5;
   const int k0 = blockIdx.x * 128, co0 = blockIdx.y * 128;
   const int c_begin = blockIdx.z * p.chunks_per_split;
@@ -451,7 +591,7 @@ __global__ void __launch_bounds__(128, 1) flat_wgrad_tc_kernel(const __grid_cons
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.tmap_dy);
     tma_prefetch_desc(&p.tmap_x);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kWgStages; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
@@ -492,25 +632,24 @@ __global__ void __launch_bounds__(128, 1) flat_wgrad_tc_kernel(const __grid_cons
                     (first && j == 0) ? 0u : 1u);
       }
     };
-    uint32_t full_ph[2] = {0, 0}, empty_ph[2] = {0, 0};
-    int uses[2] = {0, 0};
-    load(c_begin, 0);
-    uses[0] = 1;
-    for (int c = c_begin; c < c_end; ++c) {
-      const int st = (c - c_begin) & 1;
-      if (c + 1 < c_end) {  // prefetch the next chunk into the other stage once its previous MMAs are done
-        const int nst = st ^ 1;
-        if (uses[nst] > 0) {
-          mbar_wait(&empty[nst], empty_ph[nst]);
-          empty_ph[nst] ^= 1;
-        }
-        load(c + 1, nst);
-        ++uses[nst];
+    // chunk i of this slice lives in stage i % kWgStages; its k-th reuse waits for the MMAs of use k - 1
+    const int n = c_end - c_begin;
+    int loaded = 0;
+    auto try_load = [&](int i) {
+      const int st = i % kWgStages, k = i / kWgStages;
+      if (k > 0) mbar_wait(&empty[st], static_cast<uint32_t>((k - 1) & 1));
+      load(c_begin + i, st);
+    };
+    for (; loaded < n && loaded < kWgStages - 1; ++loaded) try_load(loaded);
+    for (int i = 0; i < n; ++i) {
+      if (loaded < n) {
+        try_load(loaded);
+        ++loaded;
       }
-      mbar_wait(&full[st], full_ph[st]);
-      full_ph[st] ^= 1;
+      const int st = i % kWgStages;
+      mbar_wait(&full[st], static_cast<uint32_t>((i / kWgStages) & 1));
       tc_fence_after();
-      mma(st, c == c_begin);
+      mma(st, i == 0);
       umma_commit(&empty[st]);
     }
     umma_commit(done);
@@ -527,8 +666,11 @@ __global__ void __launch_bounds__(128, 1) flat_wgrad_tc_kernel(const __grid_cons
     if (co < p.Cout) {
       float* row = p.dw + static_cast<size_t>(co) * p.K + k0 + c0;
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (k0 + c0 + j < p.K) atomicAdd(row + j, __uint_as_float(v[j]));
+      for (int j = 0; j < 32; j += 4)  // K is a multiple of 8: a group of four is inside the row or outside it
+        if (k0 + c0 + j < p.K)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(row + j), "f"(__uint_as_float(v[j])),
+                       "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                       : "memory");
     }
   }
   tc_fence_before();
@@ -691,7 +833,7 @@ int ResNetTrainEngine::grad_offset(int i, int64_t* off) const {
 }
 
 int ResNetTrainEngine::push_gemm(std::vector<std::function<int(cudaStream_t)>>* ops, const void* a, int rows, int K,
-                                 const void* panel, int N, void* out_f32) {
+                                 const void* panel, int N, void* out, bool out_f32) {
   ConvDesc d;
   d.num_src = 1;
   d.src[0] = a;
@@ -700,8 +842,8 @@ int ResNetTrainEngine::push_gemm(std::vector<std::function<int(cudaStream_t)>>* 
   d.flat_rows = rows;
   d.Cout = N;
   d.wpacked = panel;
-  d.out = out_f32;
-  d.out_is_f32 = 1;
+  d.out = out;
+  d.out_is_f32 = out_f32 ? 1 : 0;
   d.ab_format = 1;  // bf16
   auto p = std::make_shared<ConvIgemmParams>();
   CDDPM_TRY(build_conv_params(d, p.get()));
@@ -735,7 +877,7 @@ int ResNetTrainEngine::plan_unit_forward(Unit& u, const uint16_t* in, int Hin, i
   CDDPM_TRY(dalloc(&u.mean, static_cast<size_t>(u.cout), &act_owned_));
   CDDPM_TRY(dalloc(&u.rstd, static_cast<size_t>(u.cout), &act_owned_));
   CDDPM_TRY(dalloc(&u.a, static_cast<size_t>(M) * u.cout, &act_owned_));
-  CDDPM_TRY(push_gemm(&fwd_ops_, operand, M, K, u.panel, u.cout, u.y));
+  CDDPM_TRY(push_gemm(&fwd_ops_, operand, M, K, u.panel, u.cout, u.y, true));
   {
     float* y = u.y;
     double* stats = u.stats;
@@ -777,19 +919,24 @@ int ResNetTrainEngine::plan_unit_backward(Unit& u, int B, bool need_dx) {
     });
   }
   if (!need_dx) return kOk;
-  CDDPM_TRY(dalloc(&u.dx, static_cast<size_t>(M) * K, &act_owned_));
-  CDDPM_TRY(push_gemm(&bwd_ops_, u.dy, M, u.cout, u.panel_t, K, u.dx));
   if (u.k == 3) {
+    // the im2col-space gradient [M][9 cin] is the largest tensor of the backward pass: bf16 (it is summed over the nine
+    // taps in fp32 right away)
+    uint16_t* dcol16 = nullptr;
+    CDDPM_TRY(dalloc(&dcol16, static_cast<size_t>(M) * K, &act_owned_));
+    CDDPM_TRY(push_gemm(&bwd_ops_, u.dy, M, u.cout, u.panel_t, K, dcol16, false));
     const size_t n_in = static_cast<size_t>(B) * u.Hin * u.Win * u.cin;
     CDDPM_TRY(dalloc(&u.dxin, n_in, &act_owned_));
-    const float* dcol = u.dx;
+    const uint16_t* dcol = dcol16;
     float* dxin = u.dxin;
     const int H = u.Hin, W = u.Win, C = u.cin, stride = u.stride, ho = u.Hout, wo = u.Wout;
     bwd_ops_.push_back([=](cudaStream_t s) {
-      col2im3_kernel<<<grid_for(n_in), 256, 0, s>>>(dcol, B, H, W, C, stride, ho, wo, dxin);
+      col2im3_kernel<<<grid_for(n_in / 4), 256, 0, s>>>(dcol, B, H, W, C, stride, ho, wo, dxin);
       return check_launch("col2im3_kernel");
     });
   } else {
+    CDDPM_TRY(dalloc(&u.dx, static_cast<size_t>(M) * K, &act_owned_));
+    CDDPM_TRY(push_gemm(&bwd_ops_, u.dy, M, u.cout, u.panel_t, K, u.dx, true));
     u.dxin = u.dx;  // 1x1: the GEMM output is the data gradient (at the output resolution when strided)
   }
   return kOk;
@@ -846,13 +993,15 @@ int ResNetTrainEngine::plan(int B) {
   }
   int H = (st.Hout + 2 - 3) / 2 + 1, W = (st.Wout + 2 - 3) / 2 + 1;
   CDDPM_TRY(dalloc(&pool_a_, static_cast<size_t>(B) * H * W * 64, &act_owned_));
+  CDDPM_TRY(dalloc(&pool_arg_, static_cast<size_t>(B) * H * W * 64, &act_owned_));
   {
     const uint16_t* src = st.a;
     uint16_t* dst = pool_a_;
+    uint8_t* parg = pool_arg_;
     const int h = st.Hout, w = st.Wout;
     fwd_ops_.push_back([=](cudaStream_t s) {
       const size_t total = static_cast<size_t>(B) * H * W * 64;
-      maxpool3s2_kernel<<<grid_for(total), 256, 0, s>>>(src, dst, B, h, w, 64);
+      maxpool3s2_kernel<<<grid_for(total), 256, 0, s>>>(src, dst, parg, B, h, w, 64);
       return check_launch("maxpool3s2_kernel");
     });
   }
@@ -935,7 +1084,7 @@ int ResNetTrainEngine::plan(int B) {
       const uint16_t* o = c3.a;
       float* E = b.E;
       bwd_ops_.push_back([=](cudaStream_t s) {
-        mask_relu_kernel<<<grid_for(static_cast<size_t>(Mo) * C4), 256, 0, s>>>(s0, s1, o, B, Ho, Wo, C4, E);
+        mask_relu_kernel<<<grid_for(static_cast<size_t>(Mo) * (C4 / 4)), 256, 0, s>>>(s0, s1, o, B, Ho, Wo, C4, E);
         return check_launch("mask_relu_kernel");
       });
     }
@@ -957,7 +1106,7 @@ int ResNetTrainEngine::plan(int B) {
         bn_bwd_params_kernel<<<(uu.cout + 127) / 128, 128, 0, s>>>(uu.bsum, uu.cout, g + self->entries_[uu.e_gamma].goff,
                                                                    g + self->entries_[uu.e_beta].goff);
         CDDPM_TRY(check_launch("bn_bwd_params_kernel"));
-        bn_bwd_apply_kernel<<<grid_for(static_cast<size_t>(M) * uu.cout), 256, 0, s>>>(
+        bn_bwd_apply_kernel<<<grid_for(static_cast<size_t>(M) * (uu.cout / 4)), 256, 0, s>>>(
             up, uu.a, relu, scale, rows, uu.y, uu.mean, uu.rstd, self->values_[uu.e_gamma], uu.bsum,
             static_cast<size_t>(M), uu.cout, uu.dy);
         return check_launch("bn_bwd_apply_kernel");
@@ -992,9 +1141,12 @@ int ResNetTrainEngine::plan(int B) {
     const Src s0{g0.p, g0.mode}, s1{g1.p, g1.mode};
     const Unit u0 = st0;
     float* sg = stem_g_;
+    float* spart = nullptr;  // per-block partial sums of the stem weight gradient
+    CDDPM_TRY(dalloc(&spart, static_cast<size_t>(600) * 64 * 49, &act_owned_));
+    const uint8_t* parg = pool_arg_;
     const int Hin = H_, Win = W_;
     bwd_ops_.push_back([=](cudaStream_t s) {
-      maxpool_bwd_kernel<<<grid_for(static_cast<size_t>(Ms) * 64), 256, 0, s>>>(s0, s1, u0.a, B, Hs, Ws, 64, sg);
+      maxpool_bwd_kernel<<<grid_for(static_cast<size_t>(Ms) * 64), 256, 0, s>>>(s0, s1, parg, B, Hs, Ws, 64, sg);
       CDDPM_TRY(check_launch("maxpool_bwd_kernel"));
       CDDPM_CUDA(cudaMemsetAsync(u0.bsum, 0, 128 * sizeof(double), s));
       const int rpb = std::max(8, (Ms + 591) / 592);
@@ -1005,15 +1157,17 @@ int ResNetTrainEngine::plan(int B) {
       bn_bwd_params_kernel<<<1, 128, 0, s>>>(u0.bsum, 64, g + self->entries_[u0.e_gamma].goff,
                                              g + self->entries_[u0.e_beta].goff);
       CDDPM_TRY(check_launch("bn_bwd_params_kernel"));
-      bn_bwd_apply_kernel<<<grid_for(static_cast<size_t>(Ms) * 64), 256, 0, s>>>(
+      bn_bwd_apply_kernel<<<grid_for(static_cast<size_t>(Ms) * 16), 256, 0, s>>>(
           sg, u0.a, 1, nullptr, 1, u0.y, u0.mean, u0.rstd, self->values_[u0.e_gamma], u0.bsum, static_cast<size_t>(Ms),
           64, u0.dy);
       CDDPM_TRY(check_launch("bn_bwd_apply_kernel"));
       float* gw = g + self->entries_[u0.e_w].goff;
-      CDDPM_CUDA(cudaMemsetAsync(gw, 0, 64 * 49 * sizeof(float), s));
       const int ppb = std::max(64, (Ms + 591) / 592);
-      stem_wgrad_kernel<<<(Ms + ppb - 1) / ppb, 256, 0, s>>>(u0.dy, self->cur_x_, B, Hin, Win, ppb, gw);
-      return check_launch("stem_wgrad_kernel");
+      const int nb = (Ms + ppb - 1) / ppb;
+      stem_wgrad_kernel<<<nb, 256, 0, s>>>(u0.dy, self->cur_x_, B, Hin, Win, ppb, spart);
+      CDDPM_TRY(check_launch("stem_wgrad_kernel"));
+      stem_wgrad_reduce_kernel<<<(64 * 49 + 127) / 128, 128, 0, s>>>(spart, nb, gw);
+      return check_launch("stem_wgrad_reduce_kernel");
     });
   }
   planned_B_ = B;

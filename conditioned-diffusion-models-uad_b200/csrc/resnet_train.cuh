@@ -88,7 +88,7 @@ class ResNetTrainEngine {
   int plan_unit_forward(Unit& u, const uint16_t* in, int Hin, int Win, int B);
   int plan_unit_backward(Unit& u, int B, bool need_dx);
   int push_gemm(std::vector<std::function<int(cudaStream_t)>>* ops, const void* a, int rows, int K, const void* panel,
-                int N, void* out_f32);
+                int N, void* out, bool out_f32);
 
   int H_ = 0, W_ = 0, cond_dim_ = 0;
   std::vector<Entry> entries_;
@@ -114,6 +114,7 @@ class ResNetTrainEngine {
   uint16_t *stem_a_ = nullptr, *pool_a_ = nullptr;
   float *pooled_ = nullptr, *dpooled_ = nullptr, *stem_g_ = nullptr;
   uint16_t* stem_dy_ = nullptr;
+  uint8_t* pool_arg_ = nullptr;  // argmax position of every max-pool window (forward -> backward)
 };
 
 }  // namespace cddpm
