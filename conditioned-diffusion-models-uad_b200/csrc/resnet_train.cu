@@ -23,24 +23,71 @@ __device__ __forceinline__ uint16_t to_bf16(float v) {
 }
 __device__ __forceinline__ float from_bf16(uint16_t u) { return __uint_as_float(static_cast<uint32_t>(u) << 16); }
 
+// rows per block of the BatchNorm column reductions: about four blocks per SM, at least eight rows
+int bn_rows_per_block(int M) { return std::max(8, (M + 591) / 592); }
+
 int grid_for(size_t n, int per_block = 256) {
   return static_cast<int>(std::min<size_t>((n + per_block - 1) / per_block, 148 * 16));
 }
 
 // ---------------------------------------------------------------------------------------------- parameters
-// w fp32 [cout][cin][taps] -> panel[cout][tap * cin + ci] and panel_t[tap * cin + ci][cout] (bf16)
-__global__ void pack_panels_kernel(const float* __restrict__ w, int cout, int cin, int taps, uint16_t* __restrict__ panel,
-                                   uint16_t* __restrict__ panel_t) {
-  const size_t total = static_cast<size_t>(cout) * cin * taps;
-  const int K = cin * taps;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int k = static_cast<int>(i % K);
-    const int co = static_cast<int>(i / K);
-    const int tap = k / cin, ci = k - tap * cin;
-    const uint16_t v = to_bf16(w[(static_cast<size_t>(co) * cin + ci) * taps + tap]);
-    panel[i] = v;
-    panel_t[static_cast<size_t>(k) * cout + co] = v;
+// w fp32 [cout][cin][taps] -> panel[cout][Kp] (k = tap * cin + ci, zero for k >= cin * taps) and panel_t[Kp][cout], bf16.
+// Every convolution of the encoder in ONE launch: the job table travels as a kernel parameter, a block finds its job
+// from the block ranges.
+struct PackJob {
+  const float* w;
+  uint16_t *panel, *panel_t;
+  int cout, cin, taps, Kp, block0;
+};
+constexpr int kMaxPackJobs = 56;
+struct PackTable {
+  PackJob job[kMaxPackJobs];
+  int njobs;
+};
+__global__ void __launch_bounds__(256) pack_panels_kernel(const __grid_constant__ PackTable t) {
+  __shared__ uint16_t tile[32][32 * 9 + 2];
+  int j = 0;
+  while (j + 1 < t.njobs && static_cast<int>(blockIdx.x) >= t.job[j + 1].block0) ++j;
+  const PackJob jb = t.job[j];
+  const int local = static_cast<int>(blockIdx.x) - jb.block0;
+  const int K = jb.cin * jb.taps;
+  if (jb.cin % 32 != 0 || jb.taps > 9) {  // the stem (1 x 49 taps): a few thousand elements, element-wise
+    const int nblk = (j + 1 < t.njobs ? t.job[j + 1].block0 : static_cast<int>(gridDim.x)) - jb.block0;
+    const size_t total = static_cast<size_t>(jb.cout) * jb.Kp;
+    for (size_t i = local * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(nblk) * blockDim.x) {
+      const int k = static_cast<int>(i % jb.Kp);
+      const int co = static_cast<int>(i / jb.Kp);
+      uint16_t v = 0;
+      if (k < K) {
+        const int tap = k / jb.cin, ci = k - tap * jb.cin;
+        v = to_bf16(__ldg(jb.w + (static_cast<size_t>(co) * jb.cin + ci) * jb.taps + tap));
+      }
+      jb.panel[i] = v;
+      jb.panel_t[static_cast<size_t>(k) * jb.cout + co] = v;
+    }
+    return;
+  }
+  // a block owns 32 output channels x 32 input channels x every tap: the reads, the panel rows and the transposed panel
+  // rows are all contiguous runs
+  const int ci_tiles = jb.cin / 32;
+  const int co0 = (local / ci_tiles) * 32, ci0 = (local % ci_tiles) * 32;
+  const int run = 32 * jb.taps;
+  for (int idx = threadIdx.x; idx < 32 * run; idx += blockDim.x) {
+    const int co_l = idx / run, r = idx - co_l * run;
+    const int ci_l = r / jb.taps, tap = r - ci_l * jb.taps;
+    tile[co_l][tap * 32 + ci_l] = to_bf16(__ldg(jb.w + (static_cast<size_t>(co0 + co_l) * jb.cin + ci0) * jb.taps + r));
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 32 * run; idx += blockDim.x) {
+    const int co_l = idx / run, r = idx - co_l * run;
+    const int tap = r >> 5, ci_l = r & 31;
+    jb.panel[static_cast<size_t>(co0 + co_l) * K + tap * jb.cin + ci0 + ci_l] = tile[co_l][r];
+  }
+  for (int idx = threadIdx.x; idx < 32 * run; idx += blockDim.x) {
+    const int r = idx >> 5, co_l = idx & 31;
+    const int tap = r >> 5, ci_l = r & 31;
+    jb.panel_t[static_cast<size_t>(tap * jb.cin + ci0 + ci_l) * jb.cout + co0 + co_l] = tile[co_l][r];
   }
 }
 
@@ -78,102 +125,156 @@ __global__ void im2col_kernel(const uint16_t* __restrict__ in, uint16_t* __restr
   }
 }
 
-// Stem 7x7 stride 2 pad 3 over one input channel, RAW output fp32 [B*Ho*Wo][64] (bf16-rounded weights like every
-// other layer's operands; the input stays fp32).
-__global__ void __launch_bounds__(256) stem_raw_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                       float* __restrict__ y, int B, int H, int W) {
-  __shared__ float sw[49 * 64];
-  for (int i = threadIdx.x; i < 49 * 64; i += blockDim.x) {
-    const int tap = i / 64, co = i % 64;
-    sw[i] = from_bf16(to_bf16(w[co * 49 + tap]));
-  }
-  __syncthreads();
+// Stem 7x7 stride 2 pad 3 over one input channel as a GEMM operand: xcol[(n,oy,ox)][tap] = bf16(x[n][2 oy + ky - 3]
+// [2 ox + kx - 3]) for tap < 49, zero for the padding taps 49..63.  One thread per (pixel, group of 8 taps).  The same
+// matrix is the x operand of the stem's weight gradient.
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x, uint16_t* __restrict__ xcol, int B,
+                                                          int H, int W) {
   const int Ho = H / 2, Wo = W / 2;
-  const int g = threadIdx.x & 7;
-  const size_t total = static_cast<size_t>(B) * Ho * Wo;
-  for (size_t pix = static_cast<size_t>(blockIdx.x) * 32 + (threadIdx.x >> 3); pix < total;
-       pix += static_cast<size_t>(gridDim.x) * 32) {
+  const size_t total = static_cast<size_t>(B) * Ho * Wo * 8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i & 7);
+    const size_t pix = i >> 3;
     const int ox = static_cast<int>(pix % Wo), oy = static_cast<int>((pix / Wo) % Ho);
     const size_t n = pix / (static_cast<size_t>(Wo) * Ho);
-    float acc[8];
+    uint32_t pk[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    for (int ky = 0; ky < 7; ++ky) {
-      const int iy = oy * 2 + ky - 3;
-      if (iy < 0 || iy >= H) continue;
-      for (int kx = 0; kx < 7; ++kx) {
-        const int ix = ox * 2 + kx - 3;
-        if (ix < 0 || ix >= W) continue;
-        const float v = __ldg(x + (n * H + iy) * W + ix);
-        const float* wr = &sw[(ky * 7 + kx) * 64 + g * 8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wr[j], acc[j]);
-      }
+    for (int j = 0; j < 8; ++j) {
+      const int tap = g * 8 + j;
+      const int iy = oy * 2 + tap / 7 - 3, ix = ox * 2 + tap % 7 - 3;
+      uint16_t v = 0;
+      if (tap < 49 && iy >= 0 && iy < H && ix >= 0 && ix < W) v = to_bf16(__ldg(x + (n * H + iy) * W + ix));
+      if (j & 1)
+        pk[j >> 1] |= static_cast<uint32_t>(v) << 16;
+      else
+        pk[j >> 1] = v;
     }
-    float4* o = reinterpret_cast<float4*>(y + pix * 64 + g * 8);
-    o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-    o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    *reinterpret_cast<uint4*>(xcol + pix * 64 + g * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   }
 }
+// grad[co][tap] = dwp[co][tap] for the 49 real taps of the 64-wide stem panel
+__global__ void stem_unpack_kernel(const float* __restrict__ dwp, float* __restrict__ grad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 64 * 49) grad[i] = dwp[(i / 49) * 64 + i % 49];
+}
 
-// stats[c][0] += sum_m y[m][c], stats[c][1] += sum_m y[m][c]^2 (double atomics; the caller zeroes stats).
-// A block owns `rows_per_block` rows; thread = (4 channels, row lane): fp32 partial sums per thread over at most a few
-// dozen rows, combined across the row lanes in shared memory in float64, one atomic pair per channel and block.
-__global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ y, int M, int C, int rows_per_block,
-                                                       double* __restrict__ stats) {
-  __shared__ double red[256][8];
+// Column sums of a row-major [M][C] matrix without atomics: block g owns `rows_per_block` rows and writes its partial
+// sums to partial[g][0..C) and partial[g][C..2C) (fp32; combined in float64 by the finalize kernels).  Adding ~590
+// blocks' partials into one [C][2] table with atomics serialised on the few cache lines of that table (30 us for a
+// 64-channel layer); the partial rows cost one coalesced store per block.
+// Thread = (4 channels, row lane); the row lanes of a column group are combined in shared memory.
+template <typename F>
+__device__ __forceinline__ void column_partials(int M, int C, int rows_per_block, float* __restrict__ partial, F&& term) {
+  __shared__ float red[256][8];
   const int cv = C >> 2;  // float4 columns; 256 / cv row lanes share a column group (one lane when C > 1024)
+  const int nl = cv > 256 ? 1 : max(1, 256 / cv);
   const int m0 = blockIdx.x * rows_per_block;
   const int m1 = min(m0 + rows_per_block, M);
+  float* prow = partial + static_cast<size_t>(blockIdx.x) * 2 * C;
   for (int c4 = threadIdx.x % cv; c4 < cv; c4 += (cv > 256 ? 256 : cv)) {
     const int lane = cv > 256 ? 0 : threadIdx.x / cv;
-    const int nl = cv > 256 ? 1 : max(1, 256 / cv);
     float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
-    if (lane < nl) {
-      for (int m = m0 + lane; m < m1; m += nl) {
-        const float4 v = *reinterpret_cast<const float4*>(y + static_cast<size_t>(m) * C + c4 * 4);
-        s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
-        q[0] = fmaf(v.x, v.x, q[0]); q[1] = fmaf(v.y, v.y, q[1]); q[2] = fmaf(v.z, v.z, q[2]); q[3] = fmaf(v.w, v.w, q[3]);
-      }
-    }
+    if (lane < nl)
+      for (int m = m0 + lane; m < m1; m += nl) term(m, c4 * 4, s, q);
     if (nl == 1) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        atomicAdd(&stats[2 * (c4 * 4 + j)], static_cast<double>(s[j]));
-        atomicAdd(&stats[2 * (c4 * 4 + j) + 1], static_cast<double>(q[j]));
-      }
+      *reinterpret_cast<float4*>(prow + c4 * 4) = make_float4(s[0], s[1], s[2], s[3]);
+      *reinterpret_cast<float4*>(prow + C + c4 * 4) = make_float4(q[0], q[1], q[2], q[3]);
       continue;
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      red[threadIdx.x][j] = static_cast<double>(s[j]);
-      red[threadIdx.x][4 + j] = static_cast<double>(q[j]);
+      red[threadIdx.x][j] = s[j];
+      red[threadIdx.x][4 + j] = q[j];
     }
     __syncthreads();
     if (lane == 0) {
-      double t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      float t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       for (int l = 0; l < nl; ++l)
 #pragma unroll
         for (int j = 0; j < 8; ++j) t[j] += red[l * cv + c4][j];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        atomicAdd(&stats[2 * (c4 * 4 + j)], t[j]);
-        atomicAdd(&stats[2 * (c4 * 4 + j) + 1], t[4 + j]);
-      }
+      *reinterpret_cast<float4*>(prow + c4 * 4) = make_float4(t[0], t[1], t[2], t[3]);
+      *reinterpret_cast<float4*>(prow + C + c4 * 4) = make_float4(t[4], t[5], t[6], t[7]);
     }
     __syncthreads();
   }
 }
 
+// float64 sum over the G partial rows of columns c and C + c.  Block = 32 channels x 32 row lanes (1024 threads): a lane
+// adds at most ~19 rows, four loads in flight, so the kernel is a few L2 round trips long instead of G / 8 of them.
+constexpr int kRedLanes = 32;
+__device__ __forceinline__ bool reduce_partials(const float* __restrict__ partial, int G, int C, double* s0, double* s1) {
+  __shared__ double red2[kRedLanes][32][2];
+  const int cl = threadIdx.x & 31, lane = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  double a = 0.0, b = 0.0;
+  if (c < C) {
+    const float* p = partial + c;
+    const size_t row = static_cast<size_t>(2) * C;
+    int g = lane;
+    for (; g + 3 * kRedLanes < G; g += 4 * kRedLanes) {
+      float va[4], vb[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        va[j] = p[(g + j * kRedLanes) * row];
+        vb[j] = p[(g + j * kRedLanes) * row + C];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        a += static_cast<double>(va[j]);
+        b += static_cast<double>(vb[j]);
+      }
+    }
+    for (; g < G; g += kRedLanes) {
+      a += static_cast<double>(p[g * row]);
+      b += static_cast<double>(p[g * row + C]);
+    }
+  }
+  red2[lane][cl][0] = a;
+  red2[lane][cl][1] = b;
+  __syncthreads();
+  if (lane >= 4) return false;
+  // lanes 0..3 each fold eight rows, lane 0 folds the four results
+  for (int l = lane + 4; l < kRedLanes; l += 4) {
+    a += red2[l][cl][0];
+    b += red2[l][cl][1];
+  }
+  red2[lane][cl][0] = a;
+  red2[lane][cl][1] = b;
+  __syncwarp();
+  // the four lanes of a channel are four different warps: a block-level barrier among the 128 remaining threads
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  if (lane != 0 || c >= C) return false;
+  for (int l = 1; l < 4; ++l) {
+    a += red2[l][cl][0];
+    b += red2[l][cl][1];
+  }
+  *s0 = a;
+  *s1 = b;
+  return true;
+}
+
+// partial[g] = (sum_m y[m][c], sum_m y[m][c]^2) over block g's rows
+__global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ y, int M, int C, int rows_per_block,
+                                                       float* __restrict__ partial) {
+  column_partials(M, C, rows_per_block, partial, [&](int m, int c, float* s, float* q) {
+    const float4 v = *reinterpret_cast<const float4*>(y + static_cast<size_t>(m) * C + c);
+    s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+    q[0] = fmaf(v.x, v.x, q[0]); q[1] = fmaf(v.y, v.y, q[1]); q[2] = fmaf(v.z, v.z, q[2]); q[3] = fmaf(v.w, v.w, q[3]);
+  });
+}
+
 // Batch statistics -> (mean, rstd) for the normalisation (biased variance) and the running statistics update of
 // nn.BatchNorm2d in train() mode: running = (1 - momentum) running + momentum * (mean | unbiased variance).
-__global__ void bn_finalize_kernel(const double* __restrict__ stats, int M, int C, float* __restrict__ mean,
-                                   float* __restrict__ rstd, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const double mu = stats[2 * c] / M;
-  double var = stats[2 * c + 1] / M - mu * mu;
+__global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restrict__ partial, int G, int M, int C,
+                                                          float* __restrict__ mean, float* __restrict__ rstd,
+                                                          float* __restrict__ running_mean,
+                                                          float* __restrict__ running_var) {
+  double s0, s1;
+  if (!reduce_partials(partial, G, C, &s0, &s1)) return;
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const double mu = s0 / M;
+  double var = s1 / M - mu * mu;
   if (var < 0.0) var = 0.0;
   mean[c] = static_cast<float>(mu);
   rstd[c] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(kBnEps)));
@@ -268,16 +369,6 @@ struct Src {
   const float* p;
   int mode;  // 0 none, 1 same shape, 2 source is the stride-2 subsampled tensor [B,H/2,W/2,C], 3 [B][C] / (H W)
 };
-__device__ __forceinline__ float src_at(const Src& s, size_t n, int y, int x, int c, int H, int W, int C) {
-  if (s.mode == 1) return s.p[((n * H + y) * W + x) * C + c];
-  if (s.mode == 2) {
-    if ((y | x) & 1) return 0.f;
-    return s.p[((n * (H / 2) + (y >> 1)) * (W / 2) + (x >> 1)) * C + c];
-  }
-  if (s.mode == 3) return s.p[n * C + c] / static_cast<float>(H * W);
-  return 0.f;
-}
-
 __device__ __forceinline__ float4 src4_at(const Src& s, size_t n, int y, int x, int c, int H, int W, int C) {
   if (s.mode == 1) return *reinterpret_cast<const float4*>(s.p + ((n * H + y) * W + x) * C + c);
   if (s.mode == 2) {
@@ -315,74 +406,51 @@ __global__ void __launch_bounds__(256) mask_relu_kernel(Src g0, Src g1, const ui
   }
 }
 
-// dz = up * (relu ? a > 0 : 1) * (scale ? scale[n] : 1);  bsum[c] += (sum dz, sum dz xhat), xhat = (y - mean) rstd.
-// Same tiling as bn_stats_kernel.
+// dz = up * (relu ? a > 0 : 1) * (scale ? scale[n] : 1);  partial[g] = (sum dz, sum dz xhat), xhat = (y - mean) rstd,
+// over block g's rows (the tiling of bn_stats_kernel).
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ up, const uint16_t* __restrict__ a,
                                                             int relu, const float* __restrict__ scale,
                                                             int rows_per_sample, const float* __restrict__ y,
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
                                                             int M, int C, int rows_per_block,
-                                                            double* __restrict__ bsum) {
-  __shared__ double red[256][8];
-  const int cv = C >> 2;
-  const int nl = cv > 256 ? 1 : max(1, 256 / cv);
-  const int m0 = blockIdx.x * rows_per_block;
-  const int m1 = min(m0 + rows_per_block, M);
-  for (int c4 = threadIdx.x % cv; c4 < cv; c4 += (cv > 256 ? 256 : cv)) {
-    const int lane = cv > 256 ? 0 : threadIdx.x / cv;
-    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-    if (lane < nl) {
-      const float4 mu = *reinterpret_cast<const float4*>(mean + c4 * 4);
-      const float4 rs = *reinterpret_cast<const float4*>(rstd + c4 * 4);
-      for (int m = m0 + lane; m < m1; m += nl) {
-        const size_t idx = static_cast<size_t>(m) * C + c4 * 4;
-        float4 g = *reinterpret_cast<const float4*>(up + idx);
-        if (relu) {
-          const uint2 av = *reinterpret_cast<const uint2*>(a + idx);
-          if (!(from_bf16(static_cast<uint16_t>(av.x & 0xFFFF)) > 0.f)) g.x = 0.f;
-          if (!(from_bf16(static_cast<uint16_t>(av.x >> 16)) > 0.f)) g.y = 0.f;
-          if (!(from_bf16(static_cast<uint16_t>(av.y & 0xFFFF)) > 0.f)) g.z = 0.f;
-          if (!(from_bf16(static_cast<uint16_t>(av.y >> 16)) > 0.f)) g.w = 0.f;
-        }
-        if (scale != nullptr) {
-          const float sc = scale[m / rows_per_sample];
-          g.x *= sc; g.y *= sc; g.z *= sc; g.w *= sc;
-        }
-        const float4 v = *reinterpret_cast<const float4*>(y + idx);
-        s1[0] += g.x; s1[1] += g.y; s1[2] += g.z; s1[3] += g.w;
-        s2[0] = fmaf(g.x, (v.x - mu.x) * rs.x, s2[0]);
-        s2[1] = fmaf(g.y, (v.y - mu.y) * rs.y, s2[1]);
-        s2[2] = fmaf(g.z, (v.z - mu.z) * rs.z, s2[2]);
-        s2[3] = fmaf(g.w, (v.w - mu.w) * rs.w, s2[3]);
-      }
+                                                            float* __restrict__ partial) {
+  column_partials(M, C, rows_per_block, partial, [&](int m, int c, float* s1, float* s2) {
+    const size_t idx = static_cast<size_t>(m) * C + c;
+    float4 g = *reinterpret_cast<const float4*>(up + idx);
+    if (relu) {
+      const uint2 av = *reinterpret_cast<const uint2*>(a + idx);
+      if (!(from_bf16(static_cast<uint16_t>(av.x & 0xFFFF)) > 0.f)) g.x = 0.f;
+      if (!(from_bf16(static_cast<uint16_t>(av.x >> 16)) > 0.f)) g.y = 0.f;
+      if (!(from_bf16(static_cast<uint16_t>(av.y & 0xFFFF)) > 0.f)) g.z = 0.f;
+      if (!(from_bf16(static_cast<uint16_t>(av.y >> 16)) > 0.f)) g.w = 0.f;
     }
-    if (nl == 1) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        atomicAdd(&bsum[2 * (c4 * 4 + j)], static_cast<double>(s1[j]));
-        atomicAdd(&bsum[2 * (c4 * 4 + j) + 1], static_cast<double>(s2[j]));
-      }
-      continue;
+    if (scale != nullptr) {
+      const float sc = scale[m / rows_per_sample];
+      g.x *= sc; g.y *= sc; g.z *= sc; g.w *= sc;
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      red[threadIdx.x][j] = static_cast<double>(s1[j]);
-      red[threadIdx.x][4 + j] = static_cast<double>(s2[j]);
-    }
-    __syncthreads();
-    if (lane == 0) {
-      double t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      for (int l = 0; l < nl; ++l)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) t[j] += red[l * cv + c4][j];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        atomicAdd(&bsum[2 * (c4 * 4 + j)], t[j]);
-        atomicAdd(&bsum[2 * (c4 * 4 + j) + 1], t[4 + j]);
-      }
-    }
-    __syncthreads();
-  }
+    const float4 v = *reinterpret_cast<const float4*>(y + idx);
+    const float4 mu = *reinterpret_cast<const float4*>(mean + c);
+    const float4 rs = *reinterpret_cast<const float4*>(rstd + c);
+    s1[0] += g.x; s1[1] += g.y; s1[2] += g.z; s1[3] += g.w;
+    s2[0] = fmaf(g.x, (v.x - mu.x) * rs.x, s2[0]);
+    s2[1] = fmaf(g.y, (v.y - mu.y) * rs.y, s2[1]);
+    s2[2] = fmaf(g.z, (v.z - mu.z) * rs.z, s2[2]);
+    s2[3] = fmaf(g.w, (v.w - mu.w) * rs.w, s2[3]);
+  });
+}
+
+// (S1, S2) = sum of the partial rows: the gradients of beta and gamma, and the fp32 copy bn_bwd_apply_kernel reads
+// (sums[c] = S1, sums[C + c] = S2).
+__global__ void __launch_bounds__(1024) bn_bwd_params_kernel(const float* __restrict__ partial, int G, int C,
+                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                            float* __restrict__ sums) {
+  double s0, s1;
+  if (!reduce_partials(partial, G, C, &s0, &s1)) return;
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  dbeta[c] = static_cast<float>(s0);
+  dgamma[c] = static_cast<float>(s1);
+  sums[c] = static_cast<float>(s0);
+  sums[C + c] = static_cast<float>(s1);
 }
 
 // dy = gamma rstd (dz - S1 / M - xhat S2 / M), bf16; 4 channels per thread
@@ -391,7 +459,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
                                                            int rows_per_sample, const float* __restrict__ y,
                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
                                                            const float* __restrict__ gamma,
-                                                           const double* __restrict__ bsum, size_t M, int C,
+                                                           const float* __restrict__ sums, size_t M, int C,
                                                            uint16_t* __restrict__ dy) {
   const int cv = C >> 2;
   const size_t total = M * cv;
@@ -417,7 +485,11 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
     const float4 mu = *reinterpret_cast<const float4*>(mean + c);
     const float4 rs = *reinterpret_cast<const float4*>(rstd + c);
     const float4 ga = *reinterpret_cast<const float4*>(gamma + c);
+    const float4 t1 = *reinterpret_cast<const float4*>(sums + c);
+    const float4 t2 = *reinterpret_cast<const float4*>(sums + C + c);
     const float dz[4] = {g.x, g.y, g.z, g.w};
+    const float S1[4] = {t1.x, t1.y, t1.z, t1.w};
+    const float S2[4] = {t2.x, t2.y, t2.z, t2.w};
     const float yy[4] = {v.x, v.y, v.z, v.w};
     const float mm[4] = {mu.x, mu.y, mu.z, mu.w};
     const float rr[4] = {rs.x, rs.y, rs.z, rs.w};
@@ -426,22 +498,13 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float xhat = (yy[j] - mm[j]) * rr[j];
-      const float s1 = static_cast<float>(bsum[2 * (c + j)]), s2 = static_cast<float>(bsum[2 * (c + j) + 1]);
-      o[j] = to_bf16(gg[j] * rr[j] * (dz[j] - s1 * invM - xhat * s2 * invM));
+      o[j] = to_bf16(gg[j] * rr[j] * (dz[j] - S1[j] * invM - xhat * S2[j] * invM));
     }
     uint2 pk;
     pk.x = static_cast<uint32_t>(o[0]) | (static_cast<uint32_t>(o[1]) << 16);
     pk.y = static_cast<uint32_t>(o[2]) | (static_cast<uint32_t>(o[3]) << 16);
     *reinterpret_cast<uint2*>(dy + idx) = pk;
   }
-}
-
-__global__ void bn_bwd_params_kernel(const double* __restrict__ bsum, int C, float* __restrict__ dgamma,
-                                     float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  dbeta[c] = static_cast<float>(bsum[2 * c]);
-  dgamma[c] = static_cast<float>(bsum[2 * c + 1]);
 }
 
 // dxin[n,iy,ix,c] = sum over the taps (ky,kx) and output pixels (oy,ox) with oy*stride + ky - 1 == iy (same for x) of
@@ -486,65 +549,29 @@ __global__ void __launch_bounds__(256) col2im3_kernel(const uint16_t* __restrict
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(Src g0, Src g1, const uint8_t* __restrict__ arg, int B, int H,
                                                           int W, int C, float* __restrict__ gin) {
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  const size_t total = static_cast<size_t>(B) * H * W * C;
+  const int cv = C >> 2;  // 4 channels per thread
+  const size_t total = static_cast<size_t>(B) * H * W * cv;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % C);
-    const int ix = static_cast<int>((i / C) % W);
-    const int iy = static_cast<int>((i / (static_cast<size_t>(C) * W)) % H);
-    const size_t n = i / (static_cast<size_t>(C) * W * H);
-    float acc = 0.f;
+    const int c = static_cast<int>(i % cv) * 4;
+    const int ix = static_cast<int>((i / cv) % W);
+    const int iy = static_cast<int>((i / (static_cast<size_t>(cv) * W)) % H);
+    const size_t n = i / (static_cast<size_t>(cv) * W * H);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (int oy = max(0, iy / 2); oy <= min(Ho - 1, (iy + 1) / 2); ++oy)
       for (int ox = max(0, ix / 2); ox <= min(Wo - 1, (ix + 1) / 2); ++ox) {
-        const int ky = iy - (oy * 2 - 1), kx = ix - (ox * 2 - 1);  // this pixel's position inside window (oy, ox)
-        if (arg[((n * Ho + oy) * Wo + ox) * C + c] == ky * 3 + kx)
-          acc += src_at(g0, n, oy, ox, c, Ho, Wo, C) + src_at(g1, n, oy, ox, c, Ho, Wo, C);
+        const uint32_t pos = static_cast<uint32_t>((iy - (oy * 2 - 1)) * 3 + ix - (ox * 2 - 1));  // inside window (oy, ox)
+        const uint32_t a4 = *reinterpret_cast<const uint32_t*>(arg + ((n * Ho + oy) * Wo + ox) * C + c);
+        if (((a4 & 0xFF) != pos) && (((a4 >> 8) & 0xFF) != pos) && (((a4 >> 16) & 0xFF) != pos) && ((a4 >> 24) != pos))
+          continue;
+        const float4 u = src4_at(g0, n, oy, ox, c, Ho, Wo, C), v = src4_at(g1, n, oy, ox, c, Ho, Wo, C);
+        if ((a4 & 0xFF) == pos) acc[0] += u.x + v.x;
+        if (((a4 >> 8) & 0xFF) == pos) acc[1] += u.y + v.y;
+        if (((a4 >> 16) & 0xFF) == pos) acc[2] += u.z + v.z;
+        if ((a4 >> 24) == pos) acc[3] += u.w + v.w;
       }
-    gin[i] = acc;
+    *reinterpret_cast<float4*>(gin + i * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
   }
-}
-
-// Stem weight gradient: dw[co][tap] = sum over output pixels of dy[pix][co] * x[n, 2 oy + ky - 3, 2 ox + kx - 3]
-// (dy bf16 [B*Ho*Wo][64]).  One block per chunk of pixels, thread = (co, tap group): every thread owns its (co, tap)
-// outputs, so a block writes its 64 x 49 partial sums to a scratch row without atomics (592 blocks adding into 3136
-// addresses cost 0.64 ms in the first version) and a second kernel adds the rows.
-__global__ void __launch_bounds__(256) stem_wgrad_kernel(const uint16_t* __restrict__ dy, const float* __restrict__ x,
-                                                         int B, int H, int W, int pix_per_block,
-                                                         float* __restrict__ partial) {
-  const int Ho = H / 2, Wo = W / 2;
-  const int co = threadIdx.x & 63, tg = threadIdx.x >> 6;  // 4 tap groups: taps tg, tg + 4, ...
-  const size_t total = static_cast<size_t>(B) * Ho * Wo;
-  const size_t p0 = static_cast<size_t>(blockIdx.x) * pix_per_block;
-  const size_t p1 = min(p0 + pix_per_block, total);
-  float acc[13];
-#pragma unroll
-  for (int j = 0; j < 13; ++j) acc[j] = 0.f;
-  for (size_t pix = p0; pix < p1; ++pix) {
-    const int ox = static_cast<int>(pix % Wo), oy = static_cast<int>((pix / Wo) % Ho);
-    const size_t n = pix / (static_cast<size_t>(Wo) * Ho);
-    const float g = from_bf16(dy[pix * 64 + co]);
-#pragma unroll
-    for (int j = 0; j < 13; ++j) {
-      const int tap = tg + 4 * j;
-      if (tap < 49) {
-        const int iy = oy * 2 + tap / 7 - 3, ix = ox * 2 + tap % 7 - 3;
-        if (iy >= 0 && iy < H && ix >= 0 && ix < W) acc[j] = fmaf(g, __ldg(x + (n * H + iy) * W + ix), acc[j]);
-      }
-    }
-  }
-  float* row = partial + static_cast<size_t>(blockIdx.x) * (64 * 49);
-#pragma unroll
-  for (int j = 0; j < 13; ++j) {
-    const int tap = tg + 4 * j;
-    if (tap < 49) row[co * 49 + tap] = acc[j];
-  }
-}
-__global__ void stem_wgrad_reduce_kernel(const float* __restrict__ partial, int nblocks, float* __restrict__ dw) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 64 * 49) return;
-  float s = 0.f;
-  for (int b = 0; b < nblocks; ++b) s += partial[static_cast<size_t>(b) * (64 * 49) + i];
-  dw[i] = s;
 }
 
 // ---------------------------------------------------------------------------------------------- weight gradient GEMM
@@ -775,11 +802,9 @@ int ResNetTrainEngine::add_unit(const std::string& conv, const std::string& bn, 
   u.e_beta = add_entry(bn + ".bias", cout, 1);
   u.e_mean = add_entry(bn + ".running_mean", cout, 0);
   u.e_var = add_entry(bn + ".running_var", cout, 0);
-  if (!(cin == 1)) {
-    const size_t K = static_cast<size_t>(cin) * k * k;
-    CDDPM_TRY(dalloc(&u.panel, static_cast<size_t>(cout) * K, &owned_));
-    CDDPM_TRY(dalloc(&u.panel_t, static_cast<size_t>(cout) * K, &owned_));
-  }
+  const size_t K = cin == 1 ? 64 : static_cast<size_t>(cin) * k * k;  // the stem's 49 taps are padded to 64
+  CDDPM_TRY(dalloc(&u.panel, static_cast<size_t>(cout) * K, &owned_));
+  CDDPM_TRY(dalloc(&u.panel_t, static_cast<size_t>(cout) * K, &owned_));
   units_.push_back(u);
   return kOk;
 }
@@ -873,29 +898,29 @@ int ResNetTrainEngine::plan_unit_forward(Unit& u, const uint16_t* in, int Hin, i
     operand = u.col;
   }
   CDDPM_TRY(dalloc(&u.y, static_cast<size_t>(M) * u.cout, &act_owned_));
-  CDDPM_TRY(dalloc(&u.stats, static_cast<size_t>(u.cout) * 2, &act_owned_));
   CDDPM_TRY(dalloc(&u.mean, static_cast<size_t>(u.cout), &act_owned_));
   CDDPM_TRY(dalloc(&u.rstd, static_cast<size_t>(u.cout), &act_owned_));
   CDDPM_TRY(dalloc(&u.a, static_cast<size_t>(M) * u.cout, &act_owned_));
   CDDPM_TRY(push_gemm(&fwd_ops_, operand, M, K, u.panel, u.cout, u.y, true));
-  {
-    float* y = u.y;
-    double* stats = u.stats;
-    float *mean = u.mean, *rstd = u.rstd;
-    const int C = u.cout, e_mean = u.e_mean, e_var = u.e_var;
-    ResNetTrainEngine* self = this;
-    fwd_ops_.push_back([=](cudaStream_t s) {
-      CDDPM_CUDA(cudaMemsetAsync(stats, 0, static_cast<size_t>(C) * 2 * sizeof(double), s));
-      const int rpb = std::max(8, (M + 591) / 592);
-      bn_stats_kernel<<<(M + rpb - 1) / rpb, 256, 0, s>>>(y, M, C, rpb, stats);
-      CDDPM_TRY(check_launch("bn_stats_kernel"));
-      bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(stats, M, C, mean, rstd,
-                                                        const_cast<float*>(self->values_[e_mean]),
-                                                        const_cast<float*>(self->values_[e_var]));
-      return check_launch("bn_finalize_kernel");
-    });
-  }
+  push_stats(u, M);
   return kOk;
+}
+
+// batch statistics of u.y [M][cout] -> mean, rstd, running statistics
+void ResNetTrainEngine::push_stats(const Unit& u, int M) {
+  float* y = u.y;
+  float *mean = u.mean, *rstd = u.rstd;
+  const int C = u.cout, e_mean = u.e_mean, e_var = u.e_var;
+  ResNetTrainEngine* self = this;
+  fwd_ops_.push_back([=](cudaStream_t s) {
+    const int rpb = bn_rows_per_block(M), G = (M + rpb - 1) / rpb;
+    bn_stats_kernel<<<G, 256, 0, s>>>(y, M, C, rpb, self->partial_);
+    CDDPM_TRY(check_launch("bn_stats_kernel"));
+    bn_finalize_kernel<<<(C + 31) / 32, 1024, 0, s>>>(self->partial_, G, M, C, mean, rstd,
+                                                     const_cast<float*>(self->values_[e_mean]),
+                                                     const_cast<float*>(self->values_[e_var]));
+    return check_launch("bn_finalize_kernel");
+  });
 }
 
 // BatchNorm backward (the upstream gradient and its options are bound by the caller through `up`), weight gradient,
@@ -903,17 +928,20 @@ int ResNetTrainEngine::plan_unit_forward(Unit& u, const uint16_t* in, int Hin, i
 int ResNetTrainEngine::plan_unit_backward(Unit& u, int B, bool need_dx) {
   const int M = B * u.Hout * u.Wout;
   const int K = u.cin * u.k * u.k;
-  CDDPM_TRY(dalloc(&u.dwp, static_cast<size_t>(u.cout) * K, &act_owned_));
+  if (u.k > 1) CDDPM_TRY(dalloc(&u.dwp, static_cast<size_t>(u.cout) * K, &act_owned_));
   {
     const uint16_t* dy = u.dy;
     const uint16_t* operand = (u.col != nullptr) ? u.col : u.in;
     float* dwp = u.dwp;
     const int cout = u.cout, cin = u.cin, taps = u.k * u.k, e_w = u.e_w;
     ResNetTrainEngine* self = this;
-    bwd_ops_.push_back([=](cudaStream_t s) {
-      CDDPM_CUDA(cudaMemsetAsync(dwp, 0, static_cast<size_t>(cout) * K * sizeof(float), s));
-      CDDPM_TRY(launch_flat_wgrad(dy, operand, M, cout, K, dwp, s));
+    bwd_ops_.push_back([=](cudaStream_t s) -> int {
       float* g = self->cur_grads_ + self->entries_[e_w].goff;
+      // 1x1: the panel order [cout][cin] IS the parameter layout, the GEMM accumulates into the gradient itself
+      float* acc = taps == 1 ? g : dwp;
+      CDDPM_CUDA(cudaMemsetAsync(acc, 0, static_cast<size_t>(cout) * K * sizeof(float), s));
+      CDDPM_TRY(launch_flat_wgrad(dy, operand, M, cout, K, acc, s));
+      if (taps == 1) return kOk;
       unpack_grad_kernel<<<grid_for(static_cast<size_t>(cout) * K), 256, 0, s>>>(dwp, cout, cin, taps, g);
       return check_launch("unpack_grad_kernel");
     });
@@ -942,18 +970,51 @@ int ResNetTrainEngine::plan_unit_backward(Unit& u, int B, bool need_dx) {
   return kOk;
 }
 
+// BatchNorm backward of unit u given the upstream gradient `up` [M][cout]: partial sums -> (dgamma, dbeta, S1, S2) ->
+// dy (bf16)
+int ResNetTrainEngine::launch_bn_backward(const Unit& u, const float* up, int relu, const float* scale,
+                                          int rows_per_sample, int M, cudaStream_t s) {
+  const int rpb = bn_rows_per_block(M), G = (M + rpb - 1) / rpb;
+  bn_bwd_reduce_kernel<<<G, 256, 0, s>>>(up, u.a, relu, scale, rows_per_sample, u.y, u.mean, u.rstd, M, u.cout, rpb,
+                                         partial_);
+  CDDPM_TRY(check_launch("bn_bwd_reduce_kernel"));
+  float* g = cur_grads_;
+  bn_bwd_params_kernel<<<(u.cout + 31) / 32, 1024, 0, s>>>(partial_, G, u.cout, g + entries_[u.e_gamma].goff,
+                                                          g + entries_[u.e_beta].goff, u.bsum);
+  CDDPM_TRY(check_launch("bn_bwd_params_kernel"));
+  bn_bwd_apply_kernel<<<grid_for(static_cast<size_t>(M) * (u.cout / 4)), 256, 0, s>>>(
+      up, u.a, relu, scale, rows_per_sample, u.y, u.mean, u.rstd, values_[u.e_gamma], u.bsum, static_cast<size_t>(M),
+      u.cout, u.dy);
+  return check_launch("bn_bwd_apply_kernel");
+}
+
 int ResNetTrainEngine::plan(int B) {
   free_acts();
   ResNetTrainEngine* self = this;
-  // ---- parameter panels (every forward: the optimizer changed the weights)
-  for (size_t ui = 1; ui < units_.size(); ++ui) {
-    const Unit u = units_[ui];
-    fwd_ops_.push_back([=](cudaStream_t s) {
-      const size_t total = static_cast<size_t>(u.cout) * u.cin * u.k * u.k;
-      pack_panels_kernel<<<grid_for(total), 256, 0, s>>>(self->values_[u.e_w], u.cout, u.cin, u.k * u.k, u.panel, u.panel_t);
-      return check_launch("pack_panels_kernel");
-    });
-  }
+  // ---- parameter panels (every forward: the optimizer changed the weights), one launch for all convolutions
+  if (units_.size() > static_cast<size_t>(kMaxPackJobs)) return fail(kUnsupported, "encoder: pack table too small");
+  CDDPM_TRY(dalloc(&partial_, static_cast<size_t>(600) * 2 * 2048, &act_owned_));
+  fwd_ops_.push_back([=](cudaStream_t s) {
+    PackTable t;
+    memset(&t, 0, sizeof(t));
+    int block = 0;
+    for (size_t ui = 0; ui < self->units_.size(); ++ui) {
+      const Unit& u = self->units_[ui];
+      PackJob& j = t.job[t.njobs++];
+      j.w = self->values_[u.e_w];
+      j.panel = u.panel;
+      j.panel_t = u.panel_t;
+      j.cout = u.cout;
+      j.cin = u.cin;
+      j.taps = u.k * u.k;
+      j.Kp = u.cin == 1 ? 64 : u.cin * u.k * u.k;
+      j.block0 = block;
+      block += u.cin % 32 == 0 ? (u.cout / 32) * (u.cin / 32)  // 32 x 32 (x taps) tiles
+                               : static_cast<int>((static_cast<size_t>(j.cout) * j.Kp + 1023) / 1024);
+    }
+    pack_panels_kernel<<<block, 256, 0, s>>>(t);
+    return check_launch("pack_panels_kernel");
+  });
   // ---- stem: conv 7x7 s2 (raw) -> BN (batch statistics) + ReLU -> maxpool 3x3 s2
   Unit& st = units_[0];
   st.Hin = H_;
@@ -962,32 +1023,26 @@ int ResNetTrainEngine::plan(int B) {
   st.Wout = W_ / 2;
   const int Ms = B * st.Hout * st.Wout;
   CDDPM_TRY(dalloc(&st.y, static_cast<size_t>(Ms) * 64, &act_owned_));
-  CDDPM_TRY(dalloc(&st.stats, 128, &act_owned_));
   CDDPM_TRY(dalloc(&st.mean, 64, &act_owned_));
   CDDPM_TRY(dalloc(&st.rstd, 64, &act_owned_));
   CDDPM_TRY(dalloc(&st.a, static_cast<size_t>(Ms) * 64, &act_owned_));
+  CDDPM_TRY(dalloc(&stem_col_, static_cast<size_t>(Ms) * 64, &act_owned_));
   {
-    float* y = st.y;
-    double* stats = st.stats;
-    float *mean = st.mean, *rstd = st.rstd;
-    uint16_t* a = st.a;
+    uint16_t* xcol = stem_col_;
     const int Hin = H_, Win = W_;
+    fwd_ops_.push_back([=](cudaStream_t s) {
+      stem_im2col_kernel<<<grid_for(static_cast<size_t>(Ms) * 8), 256, 0, s>>>(self->cur_x_, xcol, B, Hin, Win);
+      return check_launch("stem_im2col_kernel");
+    });
+  }
+  CDDPM_TRY(push_gemm(&fwd_ops_, stem_col_, Ms, 64, st.panel, 64, st.y, true));
+  push_stats(st, Ms);
+  {
     const Unit u0 = st;
     fwd_ops_.push_back([=](cudaStream_t s) {
-      const size_t total = static_cast<size_t>(Ms);
-      stem_raw_kernel<<<static_cast<int>(std::min<size_t>((total + 31) / 32, 148 * 8)), 256, 0, s>>>(
-          self->cur_x_, self->values_[u0.e_w], y, B, Hin, Win);
-      CDDPM_TRY(check_launch("stem_raw_kernel"));
-      CDDPM_CUDA(cudaMemsetAsync(stats, 0, 128 * sizeof(double), s));
-      const int rpb = std::max(8, (Ms + 591) / 592);
-      bn_stats_kernel<<<(Ms + rpb - 1) / rpb, 256, 0, s>>>(y, Ms, 64, rpb, stats);
-      CDDPM_TRY(check_launch("bn_stats_kernel"));
-      bn_finalize_kernel<<<1, 128, 0, s>>>(stats, Ms, 64, mean, rstd, const_cast<float*>(self->values_[u0.e_mean]),
-                                           const_cast<float*>(self->values_[u0.e_var]));
-      CDDPM_TRY(check_launch("bn_finalize_kernel"));
       bn_apply_kernel<<<grid_for(static_cast<size_t>(Ms) * 16), 256, 0, s>>>(
-          y, mean, rstd, self->values_[u0.e_gamma], self->values_[u0.e_beta], nullptr, nullptr, 1, 1,
-          static_cast<size_t>(Ms), 64, a);
+          u0.y, u0.mean, u0.rstd, self->values_[u0.e_gamma], self->values_[u0.e_beta], nullptr, nullptr, 1, 1,
+          static_cast<size_t>(Ms), 64, u0.a);
       return check_launch("bn_apply_kernel");
     });
   }
@@ -1097,19 +1152,7 @@ int ResNetTrainEngine::plan(int B) {
       const int blk = bi;
       bwd_ops_.push_back([=](cudaStream_t s) {
         const float* scale = (scaled && self->cur_drop_ != nullptr) ? self->cur_drop_ + static_cast<size_t>(blk) * B : nullptr;
-        CDDPM_CUDA(cudaMemsetAsync(uu.bsum, 0, static_cast<size_t>(uu.cout) * 2 * sizeof(double), s));
-        const int rpb = std::max(8, (M + 591) / 592);
-        bn_bwd_reduce_kernel<<<(M + rpb - 1) / rpb, 256, 0, s>>>(up, uu.a, relu, scale, rows, uu.y, uu.mean, uu.rstd, M,
-                                                                 uu.cout, rpb, uu.bsum);
-        CDDPM_TRY(check_launch("bn_bwd_reduce_kernel"));
-        float* g = self->cur_grads_;
-        bn_bwd_params_kernel<<<(uu.cout + 127) / 128, 128, 0, s>>>(uu.bsum, uu.cout, g + self->entries_[uu.e_gamma].goff,
-                                                                   g + self->entries_[uu.e_beta].goff);
-        CDDPM_TRY(check_launch("bn_bwd_params_kernel"));
-        bn_bwd_apply_kernel<<<grid_for(static_cast<size_t>(M) * (uu.cout / 4)), 256, 0, s>>>(
-            up, uu.a, relu, scale, rows, uu.y, uu.mean, uu.rstd, self->values_[uu.e_gamma], uu.bsum,
-            static_cast<size_t>(M), uu.cout, uu.dy);
-        return check_launch("bn_bwd_apply_kernel");
+        return self->launch_bn_backward(uu, up, relu, scale, rows, M, s);
       });
       return kOk;
     };
@@ -1138,36 +1181,22 @@ int ResNetTrainEngine::plan(int B) {
     CDDPM_TRY(dalloc(&stem_g_, static_cast<size_t>(Ms) * 64, &act_owned_));
     CDDPM_TRY(dalloc(&st0.dy, static_cast<size_t>(Ms) * 64, &act_owned_));
     CDDPM_TRY(dalloc(&st0.bsum, 128, &act_owned_));
+    CDDPM_TRY(dalloc(&stem_dwp_, 64 * 64, &act_owned_));
     const Src s0{g0.p, g0.mode}, s1{g1.p, g1.mode};
     const Unit u0 = st0;
     float* sg = stem_g_;
-    float* spart = nullptr;  // per-block partial sums of the stem weight gradient
-    CDDPM_TRY(dalloc(&spart, static_cast<size_t>(600) * 64 * 49, &act_owned_));
+    float* sdw = stem_dwp_;
+    const uint16_t* xcol = stem_col_;
     const uint8_t* parg = pool_arg_;
-    const int Hin = H_, Win = W_;
     bwd_ops_.push_back([=](cudaStream_t s) {
-      maxpool_bwd_kernel<<<grid_for(static_cast<size_t>(Ms) * 64), 256, 0, s>>>(s0, s1, parg, B, Hs, Ws, 64, sg);
+      maxpool_bwd_kernel<<<grid_for(static_cast<size_t>(Ms) * 16), 256, 0, s>>>(s0, s1, parg, B, Hs, Ws, 64, sg);
       CDDPM_TRY(check_launch("maxpool_bwd_kernel"));
-      CDDPM_CUDA(cudaMemsetAsync(u0.bsum, 0, 128 * sizeof(double), s));
-      const int rpb = std::max(8, (Ms + 591) / 592);
-      bn_bwd_reduce_kernel<<<(Ms + rpb - 1) / rpb, 256, 0, s>>>(sg, u0.a, 1, nullptr, 1, u0.y, u0.mean, u0.rstd, Ms, 64,
-                                                                rpb, u0.bsum);
-      CDDPM_TRY(check_launch("bn_bwd_reduce_kernel"));
-      float* g = self->cur_grads_;
-      bn_bwd_params_kernel<<<1, 128, 0, s>>>(u0.bsum, 64, g + self->entries_[u0.e_gamma].goff,
-                                             g + self->entries_[u0.e_beta].goff);
-      CDDPM_TRY(check_launch("bn_bwd_params_kernel"));
-      bn_bwd_apply_kernel<<<grid_for(static_cast<size_t>(Ms) * 16), 256, 0, s>>>(
-          sg, u0.a, 1, nullptr, 1, u0.y, u0.mean, u0.rstd, self->values_[u0.e_gamma], u0.bsum, static_cast<size_t>(Ms),
-          64, u0.dy);
-      CDDPM_TRY(check_launch("bn_bwd_apply_kernel"));
-      float* gw = g + self->entries_[u0.e_w].goff;
-      const int ppb = std::max(64, (Ms + 591) / 592);
-      const int nb = (Ms + ppb - 1) / ppb;
-      stem_wgrad_kernel<<<nb, 256, 0, s>>>(u0.dy, self->cur_x_, B, Hin, Win, ppb, spart);
-      CDDPM_TRY(check_launch("stem_wgrad_kernel"));
-      stem_wgrad_reduce_kernel<<<(64 * 49 + 127) / 128, 128, 0, s>>>(spart, nb, gw);
-      return check_launch("stem_wgrad_reduce_kernel");
+      CDDPM_TRY(self->launch_bn_backward(u0, sg, 1, nullptr, 1, Ms, s));
+      // weight gradient: the tensor-core GEMM over the forward's im2col matrix (taps padded to 64)
+      CDDPM_CUDA(cudaMemsetAsync(sdw, 0, 64 * 64 * sizeof(float), s));
+      CDDPM_TRY(launch_flat_wgrad(u0.dy, xcol, Ms, 64, 64, sdw, s));
+      stem_unpack_kernel<<<(64 * 49 + 255) / 256, 256, 0, s>>>(sdw, self->cur_grads_ + self->entries_[u0.e_w].goff);
+      return check_launch("stem_unpack_kernel");
     });
   }
   planned_B_ = B;

@@ -62,11 +62,10 @@ class ResNetTrainEngine {
     const uint16_t* in = nullptr;  // input activation [M_in][cin]
     uint16_t* col = nullptr;       // [M_out][K] when k > 1 or stride > 1 (else `in` itself is the GEMM operand)
     float* y = nullptr;            // raw convolution output [M_out][cout]
-    double* stats = nullptr;       // [cout][2] sum, sumsq
     float *mean = nullptr, *rstd = nullptr;
     uint16_t* a = nullptr;         // output activation [M_out][cout]
     uint16_t* dy = nullptr;        // gradient of y, bf16 GEMM operand
-    double* bsum = nullptr;        // [cout][2] sum dz, sum dz xhat
+    float* bsum = nullptr;         // [2][cout] sum dz, sum dz xhat
     float* dwp = nullptr;          // [cout][K] weight gradient in panel order
     float* dx = nullptr;           // data gradient: [M_out][K] (im2col space) or [M_in][cin] directly
     float* dxin = nullptr;         // [M_in][cin] after col2im (3x3 layers)
@@ -87,6 +86,9 @@ class ResNetTrainEngine {
   void free_acts();
   int plan_unit_forward(Unit& u, const uint16_t* in, int Hin, int Win, int B);
   int plan_unit_backward(Unit& u, int B, bool need_dx);
+  void push_stats(const Unit& u, int M);
+  int launch_bn_backward(const Unit& u, const float* up, int relu, const float* scale, int rows_per_sample, int M,
+                         cudaStream_t s);
   int push_gemm(std::vector<std::function<int(cudaStream_t)>>* ops, const void* a, int rows, int K, const void* panel,
                 int N, void* out, bool out_f32);
 
@@ -115,6 +117,9 @@ class ResNetTrainEngine {
   float *pooled_ = nullptr, *dpooled_ = nullptr, *stem_g_ = nullptr;
   uint16_t* stem_dy_ = nullptr;
   uint8_t* pool_arg_ = nullptr;  // argmax position of every max-pool window (forward -> backward)
+  uint16_t* stem_col_ = nullptr;  // [B*Ho*Wo][64] im2col of the input (49 taps + padding), forward and weight gradient
+  float* stem_dwp_ = nullptr;     // [64][64] stem weight gradient in panel order
+  float* partial_ = nullptr;      // per-block partial column sums of the BatchNorm reductions (one reduction at a time)
 };
 
 }  // namespace cddpm
