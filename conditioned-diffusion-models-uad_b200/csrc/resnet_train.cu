@@ -2,6 +2,7 @@
 #include "resnet_train.cuh"
 
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -40,10 +41,37 @@ struct PackJob {
   int cout, cin, taps, Kp, block0;
 };
 constexpr int kMaxPackJobs = 56;
+// input channels per pack tile: span * taps <= 288 elements per output channel row of the shared tile
+__host__ __device__ inline int pack_ci_span(int cin, int taps) { return taps > 1 ? 32 : (cin < 256 ? cin : 256); }
 struct PackTable {
   PackJob job[kMaxPackJobs];
   int njobs;
 };
+// compile-time taps and span: every index split below is a shift or a multiply-shift
+template <int kTaps, int kSpan>
+__device__ __forceinline__ void pack_tile(const PackJob& jb, int local, uint16_t (*tile)[32 * 9 + 2]) {
+  constexpr int kRun = kSpan * kTaps;
+  const int K = jb.cin * kTaps;
+  const int ci_tiles = jb.cin / kSpan;
+  const int co0 = (local / ci_tiles) * 32, ci0 = (local % ci_tiles) * kSpan;
+  for (int idx = threadIdx.x; idx < 32 * kRun; idx += 256) {
+    const int co_l = idx / kRun, r = idx - co_l * kRun;
+    const int ci_l = r / kTaps, tap = r - ci_l * kTaps;
+    tile[co_l][tap * kSpan + ci_l] = to_bf16(__ldg(jb.w + (static_cast<size_t>(co0 + co_l) * jb.cin + ci0) * kTaps + r));
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 32 * kRun; idx += 256) {
+    const int co_l = idx / kRun, r = idx - co_l * kRun;
+    const int tap = r / kSpan, ci_l = r - tap * kSpan;
+    jb.panel[static_cast<size_t>(co0 + co_l) * K + tap * jb.cin + ci0 + ci_l] = tile[co_l][r];
+  }
+  for (int idx = threadIdx.x; idx < 32 * kRun; idx += 256) {
+    const int r = idx >> 5, co_l = idx & 31;
+    const int tap = r / kSpan, ci_l = r - tap * kSpan;
+    jb.panel_t[static_cast<size_t>(tap * jb.cin + ci0 + ci_l) * jb.cout + co0 + co_l] = tile[co_l][r];
+  }
+}
+
 __global__ void __launch_bounds__(256) pack_panels_kernel(const __grid_constant__ PackTable t) {
   __shared__ uint16_t tile[32][32 * 9 + 2];
   int j = 0;
@@ -51,7 +79,7 @@ __global__ void __launch_bounds__(256) pack_panels_kernel(const __grid_constant_
   const PackJob jb = t.job[j];
   const int local = static_cast<int>(blockIdx.x) - jb.block0;
   const int K = jb.cin * jb.taps;
-  if (jb.cin % 32 != 0 || jb.taps > 9) {  // the stem (1 x 49 taps): a few thousand elements, element-wise
+  if (jb.cin % 64 != 0 || (jb.taps != 1 && jb.taps != 9)) {  // the stem (1 x 49 taps): a few thousand elements, element-wise
     const int nblk = (j + 1 < t.njobs ? t.job[j + 1].block0 : static_cast<int>(gridDim.x)) - jb.block0;
     const size_t total = static_cast<size_t>(jb.cout) * jb.Kp;
     for (size_t i = local * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -68,26 +96,17 @@ __global__ void __launch_bounds__(256) pack_panels_kernel(const __grid_constant_
     }
     return;
   }
-  // a block owns 32 output channels x 32 input channels x every tap: the reads, the panel rows and the transposed panel
-  // rows are all contiguous runs
-  const int ci_tiles = jb.cin / 32;
-  const int co0 = (local / ci_tiles) * 32, ci0 = (local % ci_tiles) * 32;
-  const int run = 32 * jb.taps;
-  for (int idx = threadIdx.x; idx < 32 * run; idx += blockDim.x) {
-    const int co_l = idx / run, r = idx - co_l * run;
-    const int ci_l = r / jb.taps, tap = r - ci_l * jb.taps;
-    tile[co_l][tap * 32 + ci_l] = to_bf16(__ldg(jb.w + (static_cast<size_t>(co0 + co_l) * jb.cin + ci0) * jb.taps + r));
-  }
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < 32 * run; idx += blockDim.x) {
-    const int co_l = idx / run, r = idx - co_l * run;
-    const int tap = r >> 5, ci_l = r & 31;
-    jb.panel[static_cast<size_t>(co0 + co_l) * K + tap * jb.cin + ci0 + ci_l] = tile[co_l][r];
-  }
-  for (int idx = threadIdx.x; idx < 32 * run; idx += blockDim.x) {
-    const int r = idx >> 5, co_l = idx & 31;
-    const int tap = r >> 5, ci_l = r & 31;
-    jb.panel_t[static_cast<size_t>(tap * jb.cin + ci0 + ci_l) * jb.cout + co0 + co_l] = tile[co_l][r];
+  // a block owns 32 output channels x `span` input channels x every tap (span = 32 for 3x3, up to 256 for 1x1): the
+  // reads, the panel rows and the transposed panel rows are all contiguous runs
+  const int span = pack_ci_span(jb.cin, jb.taps);
+  if (jb.taps == 9) {
+    pack_tile<9, 32>(jb, local, tile);
+  } else if (span == 256) {
+    pack_tile<1, 256>(jb, local, tile);
+  } else if (span == 128) {
+    pack_tile<1, 128>(jb, local, tile);
+  } else {
+    pack_tile<1, 64>(jb, local, tile);
   }
 }
 
@@ -756,9 +775,77 @@ int launch_flat_wgrad_bf16(const void* dy, const void* x, int M, int Cout, int K
 ResNetTrainEngine::~ResNetTrainEngine() {
   free_acts();
   for (void* p : owned_) cudaFree(p);
+  if (cap_stream_ != nullptr) cudaStreamDestroy(cap_stream_);
+}
+
+void ResNetTrainEngine::drop_graphs() {
+  for (auto* slots : {&fwd_graphs_, &bwd_graphs_}) {
+    for (GraphSlot& g : *slots)
+      if (g.exec != nullptr) cudaGraphExecDestroy(g.exec);
+    slots->clear();
+  }
+}
+
+static bool enc_graphs_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("CDDPM_ENC_GRAPH");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return on;
+}
+
+// Runs a launch list on `stream`: eagerly for a key seen for the first time, as a captured graph from then on.  At most
+// four graphs per list (least recently used is replaced), so a caller that hands in new buffers on every step costs
+// one capture per step at worst and nothing in correctness.
+int ResNetTrainEngine::run_list(std::vector<std::function<int(cudaStream_t)>>& ops, std::vector<GraphSlot>& slots,
+                                const std::vector<const void*>& key, cudaStream_t stream) {
+  auto eager = [&]() -> int {
+    for (auto& op : ops) CDDPM_TRY(op(stream));
+    return kOk;
+  };
+  if (!enc_graphs_enabled()) return eager();
+  GraphSlot* slot = nullptr;
+  for (GraphSlot& g : slots)
+    if (g.key == key) slot = &g;
+  if (slot == nullptr) {
+    if (slots.size() < 4) {
+      slots.emplace_back();
+      slot = &slots.back();
+    } else {
+      slot = &slots[0];
+      for (GraphSlot& g : slots)
+        if (g.last_use < slot->last_use) slot = &g;
+      if (slot->exec != nullptr) cudaGraphExecDestroy(slot->exec);
+      *slot = GraphSlot();
+    }
+    slot->key = key;
+  }
+  slot->last_use = ++use_clock_;
+  if (slot->exec == nullptr) {
+    if (slot->seen++ == 0) return eager();
+    if (cap_stream_ == nullptr) CDDPM_CUDA(cudaStreamCreateWithFlags(&cap_stream_, cudaStreamNonBlocking));
+    CDDPM_CUDA(cudaStreamBeginCapture(cap_stream_, cudaStreamCaptureModeThreadLocal));
+    int st = kOk;
+    for (auto& op : ops) {
+      st = op(cap_stream_);
+      if (st != kOk) break;
+    }
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(cap_stream_, &graph);
+    if (st != kOk || ce != cudaSuccess) {
+      if (graph != nullptr) cudaGraphDestroy(graph);
+      return st != kOk ? st : check_cuda(ce, "cudaStreamEndCapture (encoder)");
+    }
+    const cudaError_t ie = cudaGraphInstantiate(&slot->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    CDDPM_TRY(check_cuda(ie, "cudaGraphInstantiate (encoder)"));
+  }
+  CDDPM_CUDA(cudaGraphLaunch(slot->exec, stream));
+  return kOk;
 }
 
 void ResNetTrainEngine::free_acts() {
+  drop_graphs();
   for (void* p : act_owned_) cudaFree(p);
   act_owned_.clear();
   fwd_ops_.clear();
@@ -872,6 +959,8 @@ int ResNetTrainEngine::push_gemm(std::vector<std::function<int(cudaStream_t)>>* 
   d.ab_format = 1;  // bf16
   auto p = std::make_shared<ConvIgemmParams>();
   CDDPM_TRY(build_conv_params(d, p.get()));
+  // (splitting K over idle SMs for the deep layers' few-tile GEMMs was measured: 23 -> 12 us for those launches, but the
+  // zero-fill launches it needs cancel the gain and the atomic accumulation makes the forward irreproducible)
   ops->push_back([p](cudaStream_t s) { return launch_conv_igemm(*p, s); });
   return kOk;
 }
@@ -1009,7 +1098,7 @@ int ResNetTrainEngine::plan(int B) {
       j.taps = u.k * u.k;
       j.Kp = u.cin == 1 ? 64 : u.cin * u.k * u.k;
       j.block0 = block;
-      block += u.cin % 32 == 0 ? (u.cout / 32) * (u.cin / 32)  // 32 x 32 (x taps) tiles
+      block += (u.cin % 64 == 0 && (j.taps == 1 || j.taps == 9)) ? (u.cout / 32) * (u.cin / pack_ci_span(u.cin, j.taps))  // 32 x span (x taps) tiles
                                : static_cast<int>((static_cast<size_t>(j.cout) * j.Kp + 1023) / 1024);
     }
     pack_panels_kernel<<<block, 256, 0, s>>>(t);
@@ -1222,7 +1311,9 @@ int ResNetTrainEngine::forward(const float* const* values, int count, const floa
   cur_x_ = x;
   cur_drop_ = drop_scale;
   cur_out_ = out;
-  for (auto& op : fwd_ops_) CDDPM_TRY(op(stream));
+  std::vector<const void*> key = {x, drop_scale, out};
+  key.insert(key.end(), values_.begin(), values_.end());
+  CDDPM_TRY(run_list(fwd_ops_, fwd_graphs_, key, stream));
   forward_done_ = true;
   return kOk;
 }
@@ -1232,7 +1323,10 @@ int ResNetTrainEngine::backward(const float* dout, float* grads, int B, cudaStre
   if (B != planned_B_ || !forward_done_) return fail(kNotReady, "encoder_train_backward: run the forward of this batch first");
   cur_dout_ = dout;
   cur_grads_ = grads;
-  for (auto& op : bwd_ops_) CDDPM_TRY(op(stream));
+  // the backward list also binds the forward's drop scales and the parameters (gamma, fc weight)
+  std::vector<const void*> key = {dout, grads, cur_drop_};
+  key.insert(key.end(), values_.begin(), values_.end());
+  CDDPM_TRY(run_list(bwd_ops_, bwd_graphs_, key, stream));
   forward_done_ = false;
   return kOk;
 }

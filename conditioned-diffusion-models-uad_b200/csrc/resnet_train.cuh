@@ -111,6 +111,20 @@ class ResNetTrainEngine {
   const float** values_store_ = nullptr;  // host copy of the pointer table of the last forward
   std::vector<const float*> values_;
   std::vector<std::function<int(cudaStream_t)>> fwd_ops_, bwd_ops_;
+  // The two launch lists as CUDA graphs, keyed by every pointer the captured launches bind (caller tensors and
+  // parameters): a list runs eagerly the first time a key is seen, is captured the second time, replayed afterwards.
+  struct GraphSlot {
+    std::vector<const void*> key;
+    cudaGraphExec_t exec = nullptr;
+    int seen = 0;
+    uint64_t last_use = 0;
+  };
+  int run_list(std::vector<std::function<int(cudaStream_t)>>& ops, std::vector<GraphSlot>& slots,
+               const std::vector<const void*>& key, cudaStream_t stream);
+  void drop_graphs();
+  std::vector<GraphSlot> fwd_graphs_, bwd_graphs_;
+  cudaStream_t cap_stream_ = nullptr;
+  uint64_t use_clock_ = 0;
   // stem / pool / head buffers
   float* stem_y_ = nullptr;
   uint16_t *stem_a_ = nullptr, *pool_a_ = nullptr;
