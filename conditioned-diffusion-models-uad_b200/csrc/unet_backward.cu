@@ -16,6 +16,8 @@
 #include "conv_bwd.cuh"
 #include "unet_engine.cuh"
 
+#include <stdlib.h>
+
 namespace cddpm {
 
 int UNetEngine::grad_offset(int i, int64_t* off) const {
@@ -578,7 +580,53 @@ int UNetEngine::backward(const float* dout, float* grads, float* dcond, int B, c
   cur_dout_ = dout;
   cur_grads_ = grads;
   cur_dcond_ = dcond;
-  for (auto& op : bwd_ops_) CDDPM_TRY(op(stream));
+  auto eager = [&]() -> int {
+    for (auto& op : bwd_ops_) CDDPM_TRY(op(stream));
+    return kOk;
+  };
+  static const bool graphs = [] {
+    const char* e = getenv("CDDPM_BWD_GRAPH");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  if (!graphs) return eager();
+  const std::vector<const void*> key = {dout, grads, dcond, cur_x_, cur_t_, cur_cond_};
+  BwdGraph* slot = nullptr;
+  for (BwdGraph& g : bwd_graphs_)
+    if (g.key == key) slot = &g;
+  if (slot == nullptr) {
+    if (bwd_graphs_.size() < 4) {
+      bwd_graphs_.emplace_back();
+      slot = &bwd_graphs_.back();
+    } else {
+      slot = &bwd_graphs_[0];
+      for (BwdGraph& g : bwd_graphs_)
+        if (g.last_use < slot->last_use) slot = &g;
+      if (slot->exec != nullptr) cudaGraphExecDestroy(slot->exec);
+      *slot = BwdGraph();
+    }
+    slot->key = key;
+  }
+  slot->last_use = ++bwd_clock_;
+  if (slot->exec == nullptr) {
+    if (slot->seen++ == 0) return eager();
+    if (cap_stream_ == nullptr) CDDPM_CUDA(cudaStreamCreateWithFlags(&cap_stream_, cudaStreamNonBlocking));
+    CDDPM_CUDA(cudaStreamBeginCapture(cap_stream_, cudaStreamCaptureModeThreadLocal));
+    int st = kOk;
+    for (auto& op : bwd_ops_) {
+      st = op(cap_stream_);
+      if (st != kOk) break;
+    }
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(cap_stream_, &graph);
+    if (st != kOk || ce != cudaSuccess) {
+      if (graph != nullptr) cudaGraphDestroy(graph);
+      return st != kOk ? st : check_cuda(ce, "cudaStreamEndCapture (backward)");
+    }
+    const cudaError_t ie = cudaGraphInstantiate(&slot->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    CDDPM_TRY(check_cuda(ie, "cudaGraphInstantiate (backward)"));
+  }
+  CDDPM_CUDA(cudaGraphLaunch(slot->exec, stream));
   return kOk;
 }
 

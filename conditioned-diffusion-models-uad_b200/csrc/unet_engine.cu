@@ -24,6 +24,9 @@ UNetEngine::~UNetEngine() {
 void UNetEngine::drop_graph() {
   if (graph_exec_ != nullptr) cudaGraphExecDestroy(graph_exec_);
   graph_exec_ = nullptr;
+  for (BwdGraph& g : bwd_graphs_)
+    if (g.exec != nullptr) cudaGraphExecDestroy(g.exec);
+  bwd_graphs_.clear();
   forwards_on_plan_ = 0;
 }
 

@@ -110,6 +110,16 @@ class UNetEngine {
   float* grad_of(const std::string& name) const;
   std::vector<std::function<int(cudaStream_t)>> bwd_ops_;
   bool bwd_planned_ = false;
+  // the backward launch list as CUDA graphs keyed by every caller pointer the launches bind (eager the first time a
+  // key is seen, captured the second time, replayed afterwards; at most four, least recently used replaced)
+  struct BwdGraph {
+    std::vector<const void*> key;
+    cudaGraphExec_t exec = nullptr;
+    int seen = 0;
+    uint64_t last_use = 0;
+  };
+  std::vector<BwdGraph> bwd_graphs_;
+  uint64_t bwd_clock_ = 0;
   float* cur_grads_ = nullptr;
   const float* cur_dout_ = nullptr;
   float* cur_dcond_ = nullptr;
