@@ -378,6 +378,58 @@ def golden_train_step():
     print("loss", float(loss), "grad norms", min(norms), max(norms))
 
 
+def golden_train_step_b4():
+    """configs[4] arithmetic at B = 4 (the B = 2 golden leaves 18 samples per channel for layer4's
+    batch statistics).  Two runs of the unmodified reference on the same weights, slices and numpy seed:
+      * fp32 (the golden proper): loss, features, every parameter-gradient norm, a few small gradients in full;
+      * torch.autocast('cpu', bfloat16) - the reference's own arithmetic at the operand width the benchmarked training
+        step uses (BASELINE configs[4]: bf16): loss, features, gradient norms.  Its deviation from the fp32 run is the
+        envelope the bf16 engines are held to.
+    timm's DropPath is stochastic: the encoder stand-in has none, i.e. drop_path_rate = 0 on both sides."""
+    from src.models.DDPM_2D import DDPM_2D
+    from src.utils.generate_noise import gen_noise
+
+    cfg = base_cfg()
+    enc_sd = make_state_dict(resnet_port.param_shapes(128), seed=3)
+    unet_sd = make_state_dict(unet_port.param_shapes(unet_port.UNetSpec()), seed=1)
+    full = {"encoder.encoder." + k: v for k, v in enc_sd.items()}
+    full.update({"diffusion." + k: v for k, v in diffusion_port.schedule_buffers().items()})
+    full.update({"diffusion.model." + k: v for k, v in unet_sd.items()})
+    x = synthetic_slices(4, 96, seed=22)
+    out = {}
+    for tag, amp in (("", False), ("_amp", True)):
+        model = DDPM_2D(cfg, prefix="t/")
+        model.load_state_dict(full, strict=True)
+        model.train()
+        np.random.seed(14)
+        with torch.autocast("cpu", dtype=torch.bfloat16, enabled=amp):
+            features = model(x)
+            noise = gen_noise(cfg, x.shape)
+            loss, _ = model.diffusion(x, t=300, cond=features, noise=noise)
+        loss.backward()
+        names, norms = [], []
+        for n, p in model.named_parameters():
+            names.append(n)
+            norms.append(float(p.grad.float().norm()) if p.grad is not None else -1.0)
+        out["loss" + tag] = loss.detach().float()
+        out["features" + tag] = features.detach().float()
+        out["grad_norms" + tag] = np.asarray(norms)
+        if not amp:
+            out["names"] = np.asarray(names)
+            small = {"diffusion.model.out.2.weight", "diffusion.model.time_embed.0.bias", "diffusion.model.label_emb.2.bias",
+                     "diffusion.model.middle_block.1.qkv.bias", "diffusion.model.input_blocks.0.0.weight",
+                     "diffusion.model.output_blocks.11.0.in_layers.0.weight", "encoder.encoder.fc.bias",
+                     "encoder.encoder.conv1.weight", "encoder.encoder.layer4.2.bn3.weight"}
+            out.update({n.replace(".", "__"): p.grad for n, p in model.named_parameters() if n in small})
+        print(tag or "fp32", "loss", float(loss), "grad norms", min(norms), max(norms), flush=True)
+    a, b = out["grad_norms"], out["grad_norms_amp"]
+    rel = np.abs(a - b) / np.maximum(a, 1e-12)
+    print("reference bf16-autocast vs fp32: loss rel", abs(float(out["loss_amp"]) - float(out["loss"])) / float(out["loss"]),
+          "grad-norm rel max", rel.max(), "median", np.median(rel), "features max-abs",
+          float((out["features"] - out["features_amp"]).abs().max()))
+    save("train_step_96_b4.npz", **out)
+
+
 def _full_ddpm2d(cfg):
     """The unmodified reference DDPM_2D with the deterministic synthetic weights (oracle.weights) loaded strictly."""
     from src.models.DDPM_2D import DDPM_2D
@@ -721,7 +773,7 @@ def golden_vol2slice():
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["schedule", "simplex", "unet", "encoder", "diffusion", "tail", "test_step", "train_step", "reverse_96",
+    which = sys.argv[1:] or ["schedule", "simplex", "unet", "encoder", "diffusion", "tail", "test_step", "train_step", "train_step_b4", "reverse_96",
                              "test_step_d50", "uncond_step", "ddim", "tail_fullres", "vol2slice"]
     torch.manual_seed(0)
     for w in which:
