@@ -2,6 +2,8 @@
 // launch-bound, not bandwidth-bound; the win over the reference is removing ~1 s of host scipy/sklearn per volume.
 #include "tail.cuh"
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <cub/cub.cuh>
 
@@ -490,11 +492,134 @@ int launch_trilinear_resize(const VolView& src, int H, int W, int D, float* dst,
   return check_launch("trilinear_kernel");
 }
 
+// ---- 5x5x5 median, second generation: forgetful selection over a shared-memory tile, two x-neighbours per thread.
+// Forgetful selection (Perrot, Domas, Couturier 2014): the median of n keys is found by keeping a working set of
+// n/2 + 2 keys, discarding its minimum and maximum (neither can be the median) and admitting the next unseen key,
+// until one key is left; min / max of a set of S keys cost ~1.5 S compare-exchanges.
+// Sharing: the windows of voxels (x, y, d) and (x + 1, y, d) have 100 of their 125 keys in common.  A common key of
+// rank r among the 100 has rank r .. r + 25 in either window, so only ranks 37 .. 62 can be either median: the same
+// procedure with a working set of 64 drops the 37 smallest and 37 largest common keys ONCE for both voxels; each
+// voxel then needs the median of its 26 candidates + 25 own keys (rank 62 - 37 = 25 of 51).  ~2 x 1850 compare-
+// exchanges per voxel against ~24 000 ALU instructions of the radix descent, every key in a register with a
+// compile-time index.
+__device__ __forceinline__ void cex(uint32_t& lo, uint32_t& hi) {
+  const uint32_t a = lo, b = hi;
+  lo = min(a, b);
+  hi = max(a, b);
+}
+// minimum of a[0..S) -> a[0], maximum -> a[S-1]: pair the two halves, then two log-depth tournaments (the same S/2 +
+// 2 (S/2 - 1) compare-exchanges as two linear scans, without their serial dependence chains)
+template <int S, int N>
+__device__ __forceinline__ void extract_minmax(uint32_t (&a)[N]) {
+  constexpr int h = S / 2;
+  constexpr int hm = (S + 1) / 2;  // an odd set's middle key takes part in both tournaments
+#pragma unroll
+  for (int i = 0; i < h; ++i) cex(a[i], a[S - 1 - i]);
+#pragma unroll
+  for (int stride = 1; stride < hm; stride *= 2)
+#pragma unroll
+    for (int i = 0; i + stride < hm; i += 2 * stride) {
+      cex(a[i], a[i + stride]);
+      cex(a[S - 1 - i - stride], a[S - 1 - i]);
+    }
+}
+// From a working set a[0..S): drop min and max, admit next(S) into the freed slot 0, until the set has END keys; then
+// drop min and max once more: the survivors are a[1 .. END-1).
+template <int S, int END, int N, typename F>
+__device__ __forceinline__ void forget(uint32_t (&a)[N], F&& next) {
+  extract_minmax<S, N>(a);
+  if constexpr (S > END) {
+    a[0] = next(S);
+    forget<S - 1, END, N>(a, next);
+  }
+}
+
+__global__ void __launch_bounds__(256, 2) median5_pair_kernel(const float* __restrict__ in, float* __restrict__ out, int H,
+                                                           int W, int D) {
+  constexpr int TX = 32, TY = 4, TD = 4;  // 512 output voxels per CTA, thread = two x-neighbours
+  constexpr int SX = TX + 4, SY = TY + 4, SD = TD + 4;
+  constexpr uint32_t zero_key = 0x80000000u;
+  __shared__ uint32_t tile[SD][SY][SX];
+  const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY, d0 = blockIdx.z * TD;
+  int nonzero = 0;
+  for (int i = threadIdx.x; i < SD * SY * SX; i += blockDim.x) {
+    const int tx = i % SX, ty = (i / SX) % SY, td = i / (SX * SY);
+    const int gx = reflect(x0 + tx - 2, W), gy = reflect(y0 + ty - 2, H), gd = reflect(d0 + td - 2, D);
+    const uint32_t kv = sort_key(in[(static_cast<size_t>(gd) * H + gy) * W + gx]);
+    tile[td][ty][tx] = kv;
+    nonzero |= (kv != zero_key);
+  }
+  const int any = __syncthreads_or(nonzero);
+  const int lx = (threadIdx.x % 16) * 2, ly = (threadIdx.x / 16) % TY, ld = threadIdx.x / (16 * TY);
+  const int x = x0 + lx, y = y0 + ly, d = d0 + ld;
+  if (x >= W || y >= H || d >= D) return;
+  const size_t oidx = (static_cast<size_t>(d) * H + y) * W + x;
+  const bool has_b = x + 1 < W;
+  if (!any) {  // the whole tile is +0 (outside the eroded brain mask)
+    out[oidx] = 0.f;
+    if (has_b) out[oidx + 1] = 0.f;
+    return;
+  }
+  // the residual volume is >= 0 and mostly exactly 0: the median is 0 as soon as more than half of a window is 0 and
+  // nothing in it is negative
+  {
+    int zc = 0, za = 0, zb = 0, neg = 0;
+#pragma unroll
+    for (int a = 0; a < 5; ++a)
+#pragma unroll
+      for (int b = 0; b < 5; ++b) {
+#pragma unroll
+        for (int c = 1; c < 5; ++c) {
+          const uint32_t kv = tile[ld + a][ly + b][lx + c];
+          zc += (kv == zero_key);
+          neg += (kv < zero_key);
+        }
+        const uint32_t ka = tile[ld + a][ly + b][lx], kb = tile[ld + a][ly + b][lx + 5];
+        za += (ka == zero_key);
+        zb += (kb == zero_key);
+        neg += (ka < zero_key) + (kb < zero_key);
+      }
+    if (neg == 0 && zc + za > 62 && zc + zb > 62) {
+      out[oidx] = 0.f;
+      if (has_b) out[oidx + 1] = 0.f;
+      return;
+    }
+  }
+  // ---- the 100 common keys (x offsets 1..4): 64 in the working set, 36 admitted one by one -> 26 candidates
+  auto common = [&](int j) { return tile[ld + j / 20][ly + (j / 4) % 5][lx + 1 + j % 4]; };
+  uint32_t w[64];
+#pragma unroll
+  for (int j = 0; j < 64; ++j) w[j] = common(j);
+  forget<64, 28, 64>(w, [&](int S) { return common(128 - S); });
+  // ---- each voxel: median of the 26 candidates w[1..26] + its own 25 keys (x offset 0 resp. 5)
+#pragma unroll
+  for (int v = 0; v < 2; ++v) {
+    const int xo = lx + 5 * v;
+    auto own = [&](int e) { return tile[ld + e / 5][ly + e % 5][xo]; };
+    uint32_t m[27];
+#pragma unroll
+    for (int j = 0; j < 26; ++j) m[j] = w[1 + j];
+    m[26] = own(0);
+    forget<27, 3, 27>(m, [&](int S) { return own(28 - S); });
+    if (v == 0 || has_b) out[oidx + v] = key_value(m[1]);
+  }
+}
+
+static bool median_v2_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("CDDPM_MEDIAN_V2");  // A/B switch for measurements: 0 = the radix-descent kernel
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return on;
+}
+
 int launch_median3d(const float* in, float* out, int H, int W, int D, int k, cudaStream_t stream) {
   if (!in || !out) return fail(kInvalidArgument, "median: null pointer");
   if (in == out) return fail(kInvalidArgument, "median: in-place filtering is not supported");
   dim3 grid((W + 15) / 16, (H + 3) / 4, (D + 3) / 4);
-  if (k == 5) {
+  if (k == 5 && median_v2_enabled()) {
+    median5_pair_kernel<<<dim3((W + 31) / 32, (H + 3) / 4, (D + 3) / 4), 256, 0, stream>>>(in, out, H, W, D);
+  } else if (k == 5) {
     median3d_kernel<5><<<grid, 256, 0, stream>>>(in, out, H, W, D);
   } else if (k == 3) {
     median3d_kernel<3><<<grid, 256, 0, stream>>>(in, out, H, W, D);
