@@ -111,6 +111,7 @@ def _signatures(c):
         "cddpm_residual_erode": (i32, [pview, pview, pview, pview, i32, i32, i32, i32, i32, vp, vp, vp]),
         "cddpm_trilinear_resize": (i32, [pview, i32, i32, i32, vp, i32, i32, i32, vp]),
         "cddpm_median3d": (i32, [vp, vp, i32, i32, i32, i32, vp]),
+        "cddpm_compose_grid": (i32, [vp, vp, i32, i32, vp, vp]),
         "cddpm_max": (i32, [vp, i64, vp, vp]),
         "cddpm_threshold_counts": (i32, [vp, pview, i32, i32, i32, c.POINTER(f32), i32, vp, vp]),
         "cddpm_threshold_mask": (i32, [vp, i64, f32, vp, vp]),

@@ -453,6 +453,101 @@ def _dist_max(t: torch.Tensor):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
 
 
+# ---------------------------------------------------------------------------------------------- output image grids
+class _ImageWriter:
+    """PNG encoding and file writes off the critical path: `_test_step` only launches the grid kernel and an
+    asynchronous device-to-host copy into pinned memory; ONE background thread waits for the copy's event, encodes the
+    PNG (PIL) and writes it.  `flush()` (called by `_test_end`) waits for everything queued."""
+
+    def __init__(self):
+        import queue
+        import threading
+
+        self._q = queue.Queue()
+        self._errors: List[BaseException] = []
+        self._t = threading.Thread(target=self._run, name="cddpm-png-writer", daemon=True)
+        self._t.start()
+
+    def _run(self):
+        from PIL import Image
+
+        while True:
+            event, host, path = self._q.get()
+            try:
+                event.synchronize()
+                Image.fromarray(host.numpy()).save(path)
+            except BaseException as e:  # surfaced by flush(): a lost image must not pass silently
+                self._errors.append(e)
+            finally:
+                self._q.task_done()
+
+    def submit(self, event, host, path):
+        self._q.put((event, host, path))
+
+    def flush(self):
+        self._q.join()
+        if self._errors:
+            e = self._errors[0]
+            self._errors.clear()
+            raise CddpmError(f"writing an output image failed: {e!r}")
+
+
+_image_writer: Optional[_ImageWriter] = None
+
+
+def flush_image_writer():
+    """Block until every image queued by log_images has been written (no-op when none was)."""
+    if _image_writer is not None:
+        _image_writer.flush()
+
+
+def log_images(self, diff_volume, data_orig, data_seg, data_mask, final_volume, ID, diff_volume_KL=None, flow=None):
+    """utils_eval.log_images (:586-628): for every 10th axial slice one image `grid/{ID}_{j}_Grid.png` under the working
+    directory with four panels side by side - original, reconstruction (both 'gray', each normalised to its own range),
+    difference ('inferno', 0 .. max of the whole difference volume + 0.01), segmentation ('gray') - each drawn as
+    rot90(., 3).  The panels are composed on the device (`cddpm_compose_grid`), copied to pinned memory asynchronously and
+    encoded / written by a background thread.  Differences from the reference, by necessity: matplotlib is not
+    available, so the image is the four panels at native resolution (H x 4W pixels) without matplotlib's figure
+    resampling and the inferno table is interpolated from its 8-class palette; the wandb upload (:625) is not done."""
+    global _image_writer
+    try:
+        import PIL  # noqa: F401
+    except ImportError as e:
+        raise CddpmError("saveOutputImages needs Pillow to encode PNG files") from e
+    if not torch.cuda.is_available():
+        raise CddpmError("log_images needs a CUDA device (no CPU fallback)")
+    dev = diff_volume.device if isinstance(diff_volume, torch.Tensor) and diff_volume.is_cuda else \
+        torch.device("cuda", torch.cuda.current_device())
+    d = _as_cuda_f32(diff_volume, dev).squeeze()
+    o = _as_cuda_f32(data_orig, dev).squeeze()
+    f = _as_cuda_f32(final_volume, dev).squeeze()
+    g = _as_cuda_f32(data_seg, dev).squeeze()
+    if d.ndim != 3 or o.shape != d.shape or f.shape != d.shape or g.shape != d.shape:
+        raise ValueError("log_images expects [H,W,D] volumes of one shape")
+    H, W, D = d.shape
+    grid_dir = os.path.join(os.getcwd(), "grid")
+    os.makedirs(grid_dir, exist_ok=True)
+    if _image_writer is None:
+        _image_writer = _ImageWriter()
+    name = ID[0] if isinstance(ID, (list, tuple)) else ID
+    with torch.cuda.device(dev):
+        vmax = d.max() + 0.01
+        for j in range(0, D, 10):
+            panels = torch.stack([o[..., j], f[..., j], d[..., j], g[..., j]]).contiguous()
+            ranges = torch.stack([panels.amin(dim=(1, 2)), panels.amax(dim=(1, 2))], dim=1).contiguous()
+            ranges[2, 0] = 0.0
+            ranges[2, 1] = vmax
+            rgb = torch.empty(W, 4 * H, 3, dtype=torch.uint8, device=dev)
+            check(lib().cddpm_compose_grid(ptr(panels), ptr(ranges), H, W, ptr(rgb), current_stream()),
+                  "cddpm_compose_grid")
+            if self.cfg.get("save_to_disc", True):
+                host = torch.empty(rgb.shape, dtype=torch.uint8, pin_memory=True)
+                host.copy_(rgb, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                _image_writer.submit(ev, host, os.path.join(grid_dir, "{}_{}_Grid.png".format(name, j)))
+
+
 def _test_step(self, final_volume, data_orig, data_seg, data_mask, batch_idx, ID, label_vol):
     self.healthy_sets = ["IXI"]
     cfg = self.cfg
@@ -471,8 +566,8 @@ def _test_step(self, final_volume, data_orig, data_seg, data_mask, batch_idx, ID
         ed["l2recoErrorAll"].append(float(sums[1] / n))
         ed["l2recoErrorUnhealthy"].append(float(np.float64(sums[3]) / n_les))
         ed["l2recoErrorHealthy"].append(float(sums[5] / (n - n_les)))
-    if cfg["saveOutputImages"]:
-        raise NotImplementedError("PNG / wandb image logging is out of scope (I/O); run with saveOutputImages=False")
+    if cfg["saveOutputImages"]:  # utils_eval.py:72-74 (after the median filter, before the metrics)
+        log_images(self, vol.diff.permute(1, 2, 0), data_orig, data_seg, data_mask, final_volume, ID)
 
     dev = vol.diff.device
     best_thresh = None
@@ -582,6 +677,7 @@ _MEAN_STD_PLAIN = ["PrecisionPerVol", "RecallPerVol", "PrecisionPerSlice", "Reca
 
 
 def _test_end(self):
+    flush_image_writer()
     ed = self.eval_dict
     with np.errstate(invalid="ignore", divide="ignore"), _quiet():
         for out, src, nan_aware in _MEAN_STD:

@@ -323,6 +323,9 @@ int cddpm_trilinear_resize(const cddpm_vol_view* src, int H, int W, int D, float
   if (!src) return fail(kInvalidArgument, "trilinear_resize: null view");
   return launch_trilinear_resize(to_view(src), H, W, D, dst_hwd, Ho, Wo, Do, static_cast<cudaStream_t>(stream));
 }
+int cddpm_compose_grid(const float* panels, const float* ranges, int H, int W, uint8_t* rgb, void* stream) {
+  return launch_compose_grid(panels, ranges, H, W, rgb, static_cast<cudaStream_t>(stream));
+}
 int cddpm_median3d(const float* in_dhw, float* out_dhw, int H, int W, int D, int k, void* stream) {
   return launch_median3d(in_dhw, out_dhw, H, W, D, k, static_cast<cudaStream_t>(stream));
 }

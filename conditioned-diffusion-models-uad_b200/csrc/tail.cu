@@ -632,6 +632,47 @@ int launch_median3d(const float* in, float* out, int H, int W, int D, int k, cud
   return check_launch("median3d_kernel");
 }
 
+// ---- output image grid (log_images, utils_eval.py:586-628): one RGB row of four panels for one axial slice
+// Eight anchor colours of matplotlib's 'inferno' at equal spacing (its published 8-class palette), interpolated
+// linearly; matplotlib itself is absent here, so the colour table is an approximation.
+__constant__ float kInferno[8][3] = {{0.f, 0.f, 4.f},      {40.f, 11.f, 84.f},   {101.f, 21.f, 110.f}, {159.f, 42.f, 99.f},
+                                     {212.f, 72.f, 66.f},  {245.f, 125.f, 21.f}, {250.f, 193.f, 39.f}, {252.f, 255.f, 164.f}};
+// panels [4][H][W] fp32 (original, reconstruction, difference, segmentation), ranges [4][2] = (vmin, vmax) of each
+// panel's Normalize; every panel is drawn rotated by torch.rot90(., 3) (out[i][j] = in[H-1-j][i], shape [W][H]) and the
+// four are laid side by side: rgb [W][4 H][3] uint8.  Panel 2 uses the inferno table, the others 'gray'.
+__global__ void compose_grid_kernel(const float* __restrict__ panels, const float* __restrict__ ranges, int H, int W,
+                                    uint8_t* __restrict__ rgb) {
+  const int total = W * 4 * H;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int col = i % (4 * H), row = i / (4 * H);
+    const int pnl = col / H, j = col - pnl * H;
+    const float v = panels[(static_cast<size_t>(pnl) * H + (H - 1 - j)) * W + row];
+    const float lo = ranges[2 * pnl], hi = ranges[2 * pnl + 1];
+    float t = hi > lo ? (v - lo) / (hi - lo) : 0.f;  // matplotlib maps a constant image to the bottom of the table
+    t = fminf(fmaxf(t, 0.f), 1.f);
+    float c[3];
+    if (pnl == 2) {
+      const float u = t * 7.f;
+      const int k = min(static_cast<int>(u), 6);
+      const float f = u - static_cast<float>(k);
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) c[ch] = kInferno[k][ch] + f * (kInferno[k + 1][ch] - kInferno[k][ch]);
+    } else {
+      c[0] = c[1] = c[2] = t * 255.f;
+    }
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) rgb[static_cast<size_t>(i) * 3 + ch] = static_cast<uint8_t>(__float2int_rn(c[ch]));
+  }
+}
+
+int launch_compose_grid(const float* panels, const float* ranges, int H, int W, uint8_t* rgb, cudaStream_t stream) {
+  if (!panels || !ranges || !rgb) return fail(kInvalidArgument, "compose_grid: null pointer");
+  if (H < 1 || W < 1) return fail(kInvalidArgument, "compose_grid: empty image");
+  const int total = W * 4 * H;
+  compose_grid_kernel<<<std::min((total + 255) / 256, 148 * 8), 256, 0, stream>>>(panels, ranges, H, W, rgb);
+  return check_launch("compose_grid_kernel");
+}
+
 int launch_max(const float* x, int64_t n, float* out_max, cudaStream_t stream) {
   if (!x || !out_max) return fail(kInvalidArgument, "max: null pointer");
   CDDPM_CUDA(cudaMemsetAsync(out_max, 0, 4, stream));

@@ -21,6 +21,8 @@ int launch_residual_erode(const VolView& orig, const VolView& reco, const VolVie
                           cudaStream_t stream);
 
 // dst[Ho][Wo][Do] = trilinear resize of the [H,W,D] view with align_corners=True (F.interpolate, utils_eval.py:24-25).
+// One slice of the output image grid of log_images (utils_eval.py:586-628): see compose_grid_kernel.
+int launch_compose_grid(const float* panels, const float* ranges, int H, int W, uint8_t* rgb, cudaStream_t stream);
 int launch_trilinear_resize(const VolView& src, int H, int W, int D, float* dst, int Ho, int Wo, int Do,
                             cudaStream_t stream);
 

@@ -297,6 +297,12 @@ int cddpm_residual_erode(const cddpm_vol_view* orig, const cddpm_vol_view* reco,
  * contiguous [Ho,Wo,Do] fp32 buffer (d fastest - the layout of the reference's squeezed tensor). */
 int cddpm_trilinear_resize(const cddpm_vol_view* src, int H, int W, int D, float* dst_hwd, int Ho, int Wo, int Do,
                            void* stream);
+/* One row of log_images' output grid (utils_eval.py:586-628, saveOutputImages): panels [4][H][W] fp32 on the device =
+ * original, reconstruction, difference, segmentation of ONE axial slice; ranges [4][2] = (vmin, vmax) of each panel's
+ * colour normalisation.  Each panel is drawn as torch.rot90(., 3) ('gray'; the difference with 'inferno') and the four
+ * are laid side by side into rgb [W][4 H][3] uint8 (device).  Encoding / writing the PNG is host work done off the
+ * critical path by the caller. */
+int cddpm_compose_grid(const float* panels, const float* ranges, int H, int W, uint8_t* rgb, void* stream);
 /* scipy.ndimage.median_filter(vol, (k,k,k)) with mode='reflect' (apply_3d_median_filter :462-464), k in {1,3,5}. */
 int cddpm_median3d(const float* in_dhw, float* out_dhw, int H, int W, int D, int k, void* stream);
 /* np.max of a buffer (val_range top of find_best_val, :86); out_max: one float on the device. */

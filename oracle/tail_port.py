@@ -271,3 +271,35 @@ def volume_tail(reco: np.ndarray, orig: np.ndarray, seg: np.ndarray, mask: np.nd
     out["AnomalyScoreRecoPerSlice"] = rows_scores
     out["labelPerSlice"] = rows_labels
     return out
+
+
+# ---------------------------------------------------------------------------------------------- output image grid
+_INFERNO8 = np.array([[0, 0, 4], [40, 11, 84], [101, 21, 110], [159, 42, 99], [212, 72, 66], [245, 125, 21],
+                      [250, 193, 39], [252, 255, 164]], dtype=np.float32)
+
+
+def compose_grid_port(panels: np.ndarray, ranges: np.ndarray) -> np.ndarray:
+    """One row of log_images' figure (utils_eval.py:595-608) as an RGB array: panels [4,H,W] = original,
+    reconstruction, difference, segmentation of one axial slice, ranges [4,2] = (vmin, vmax) of each panel's
+    Normalize; every panel drawn as rot90(., 3), 'gray' except the difference ('inferno').  PARITY UNPINNED:
+    matplotlib is absent from this image, so this restates imshow's documented pipeline - Normalize -> clip to [0, 1]
+    -> colour table - at native resolution, with the inferno table interpolated linearly from matplotlib's 8-class
+    palette instead of its 256 entries; it is not a pixel copy of the reference's resampled 1600 x 400 figure."""
+    panels = np.asarray(panels, dtype=np.float32)
+    ranges = np.asarray(ranges, dtype=np.float32)
+    _, H, W = panels.shape
+    out = np.zeros((W, 4 * H, 3), dtype=np.uint8)
+    for k in range(4):
+        img = np.rot90(panels[k], 3)  # [W, H]
+        lo, hi = ranges[k]
+        t = (img - lo) / (hi - lo) if hi > lo else np.zeros_like(img)
+        t = np.clip(t, np.float32(0), np.float32(1)).astype(np.float32)
+        if k == 2:
+            u = t * np.float32(7)
+            i = np.minimum(u.astype(np.int32), 6)
+            fr = (u - i.astype(np.float32))[..., None]
+            c = _INFERNO8[i] + fr * (_INFERNO8[i + 1] - _INFERNO8[i])
+        else:
+            c = np.repeat((t * np.float32(255))[..., None], 3, axis=2)
+        out[:, k * H:(k + 1) * H, :] = np.rint(c).astype(np.uint8)
+    return out

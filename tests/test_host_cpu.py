@@ -337,3 +337,25 @@ def test_bench_reference_arm_prints_exactly_one_json_line():
     assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["config"]["workload"].startswith("configs[1]")
+
+
+def test_compose_grid_port_layout_and_colour_tables():
+    """oracle.tail_port.compose_grid_port (the checker of cddpm_compose_grid / log_images): panel order, rot90(., 3),
+    gray normalisation to the panel's own range, inferno end points and the constant-image case."""
+    import numpy as np
+
+    from oracle.tail_port import compose_grid_port
+
+    H, W = 4, 6
+    panels = np.zeros((4, H, W), dtype=np.float32)
+    panels[0, 0, 0] = 2.0          # top-left of the original -> after rot90(., 3): row 0, column H-1
+    panels[2] = np.linspace(0, 1, H * W, dtype=np.float32).reshape(H, W)
+    panels[3] = 0.5                # constant panel: bottom of the gray table
+    ranges = np.array([[0, 2], [0, 0], [0, 1], [0.5, 0.5]], dtype=np.float32)
+    img = compose_grid_port(panels, ranges)
+    assert img.shape == (W, 4 * H, 3) and img.dtype == np.uint8
+    assert tuple(img[0, H - 1]) == (255, 255, 255) and img[:, :H].sum() == 3 * 255
+    assert img[:, H:2 * H].max() == 0 and img[:, 3 * H:].max() == 0
+    rot = np.rot90(panels[2], 3)
+    lo, hi = np.unravel_index(rot.argmin(), rot.shape), np.unravel_index(rot.argmax(), rot.shape)
+    assert tuple(img[lo[0], 2 * H + lo[1]]) == (0, 0, 4) and tuple(img[hi[0], 2 * H + hi[1]]) == (252, 255, 164)

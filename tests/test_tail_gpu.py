@@ -364,3 +364,40 @@ def test_device_bisection_equals_host_loop(case, monkeypatch):
     for a, b in zip(dev, host):
         assert (a == b) or (a != a and b != b), (case, dev, host)
     assert type(dev[3]) is type(host[3])  # np.float32 (or the int 0 when no step updated the optimum)
+
+
+def test_log_images_writes_the_reference_grid_files(tmp_path, monkeypatch):
+    """saveOutputImages=True (utils_eval.py:72-74, log_images :586-628): `grid/{ID}_{j}_Grid.png` for every 10th axial
+    slice, written off the critical path; each file decodes to the four-panel row of oracle.tail_port.compose_grid_port
+    (rot90(., 3) panels, per-panel gray normalisation, inferno difference normalised to [0, max + 0.01]) within one
+    grey level, and the metrics of the step are unchanged by the logging."""
+    from PIL import Image
+
+    from cddpm import eval_tail
+    from oracle import tail_port
+    from oracle.weights import synthetic_volume
+
+    monkeypatch.chdir(tmp_path)
+    v = synthetic_volume(0, depth=24)
+    args = (v["reco"].cuda(), v["vol"].cuda(), v["seg_orig"].cuda(), v["mask_orig"].cuda(), 0, ["caseA"], torch.tensor([1]))
+    plain = _host("val")
+    eval_tail._test_step(plain, *args)
+    host = _host("val")
+    host.cfg["saveOutputImages"] = True
+    out = eval_tail._test_step(host, *args)
+    eval_tail._test_end(host)  # flushes the writer
+    for k in ("DiceScorePerVol", "AUCPerVol", "BestThresholdPerVol", "HausPerVol"):
+        assert host.eval_dict[k] == plain.eval_dict[k]
+    files = sorted(os.listdir(tmp_path / "grid"))
+    assert files == sorted(f"caseA_{j}_Grid.png" for j in range(0, 24, 10))
+    diff = out.diff_hwd().cpu().numpy()
+    orig, reco, seg = (v[k][0, 0].numpy() for k in ("vol", "reco", "seg_orig"))
+    for j in range(0, 24, 10):
+        panels = np.stack([orig[..., j], reco[..., j], diff[..., j], seg[..., j]]).astype(np.float32)
+        ranges = np.stack([panels.min(axis=(1, 2)), panels.max(axis=(1, 2))], axis=1)
+        ranges[2] = (0.0, np.float32(diff.max()) + np.float32(0.01))
+        want = tail_port.compose_grid_port(panels, ranges)
+        got = np.asarray(Image.open(tmp_path / "grid" / f"caseA_{j}_Grid.png"))
+        assert got.shape == want.shape == (96, 4 * 96, 3)
+        assert np.abs(got.astype(np.int16) - want.astype(np.int16)).max() <= 1
+        assert got[:, 2 * 96:3 * 96].std() > 0  # the difference panel is not blank
