@@ -112,30 +112,33 @@ __global__ void __launch_bounds__(256) pack_panels_kernel(const __grid_constant_
 
 // grad[co][ci][tap] = dwp[co][tap * cin + ci]
 __global__ void unpack_grad_kernel(const float* __restrict__ dwp, int cout, int cin, int taps, float* __restrict__ grad) {
-  const size_t total = static_cast<size_t>(cout) * cin * taps;
+  const uint32_t total = static_cast<uint32_t>(cout) * cin * taps;
   const int K = cin * taps;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+  for (uint32_t i = blockIdx.x * static_cast<uint32_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<uint32_t>(gridDim.x) * blockDim.x) {
     const int tap = static_cast<int>(i % taps);
     const int ci = static_cast<int>((i / taps) % cin);
-    const int co = static_cast<int>(i / (static_cast<size_t>(taps) * cin));
-    grad[i] = dwp[static_cast<size_t>(co) * K + tap * cin + ci];
+    const int co = static_cast<int>(i / (static_cast<uint32_t>(taps) * cin));
+    grad[i] = dwp[static_cast<uint32_t>(co) * K + tap * cin + ci];
   }
 }
 
 // ---------------------------------------------------------------------------------------------- forward kernels
+// Element indices are 32-bit throughout (plan() refuses batches whose largest tensor would not fit): these passes move
+// 8-16 bytes per thread, and the 64-bit divisions of a size_t index split made them instruction-bound (im2col: 72 %
+// issue-slot utilisation at 1.4 TB/s).
 // col[(n,oy,ox)][tap][c] = in[n][oy*stride+ky-pad][ox*stride+kx-pad][c] (zero outside); 8 channels per thread.
 __global__ void im2col_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ col, int B, int H, int W, int C,
                               int k, int stride, int pad, int Ho, int Wo) {
   const int cv = C >> 3;
-  const size_t total = static_cast<size_t>(B) * Ho * Wo * k * k * cv;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+  const uint32_t total = static_cast<uint32_t>(B) * Ho * Wo * k * k * cv;
+  for (uint32_t i = blockIdx.x * static_cast<uint32_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<uint32_t>(gridDim.x) * blockDim.x) {
     const int v = static_cast<int>(i % cv);
     const int tap = static_cast<int>((i / cv) % (k * k));
-    const size_t pix = i / (static_cast<size_t>(cv) * k * k);
+    const uint32_t pix = i / (static_cast<uint32_t>(cv) * k * k);
     const int ox = static_cast<int>(pix % Wo), oy = static_cast<int>((pix / Wo) % Ho);
-    const size_t n = pix / (static_cast<size_t>(Wo) * Ho);
+    const uint32_t n = pix / (static_cast<uint32_t>(Wo) * Ho);
     const int iy = oy * stride + tap / k - pad, ix = ox * stride + tap % k - pad;
     uint4 val = make_uint4(0, 0, 0, 0);
     if (iy >= 0 && iy < H && ix >= 0 && ix < W)
@@ -150,13 +153,13 @@ __global__ void im2col_kernel(const uint16_t* __restrict__ in, uint16_t* __restr
 __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x, uint16_t* __restrict__ xcol, int B,
                                                           int H, int W) {
   const int Ho = H / 2, Wo = W / 2;
-  const size_t total = static_cast<size_t>(B) * Ho * Wo * 8;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+  const uint32_t total = static_cast<uint32_t>(B) * Ho * Wo * 8;
+  for (uint32_t i = blockIdx.x * static_cast<uint32_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<uint32_t>(gridDim.x) * blockDim.x) {
     const int g = static_cast<int>(i & 7);
-    const size_t pix = i >> 3;
+    const uint32_t pix = i >> 3;
     const int ox = static_cast<int>(pix % Wo), oy = static_cast<int>((pix / Wo) % Ho);
-    const size_t n = pix / (static_cast<size_t>(Wo) * Ho);
+    const uint32_t n = pix / (static_cast<uint32_t>(Wo) * Ho);
     uint32_t pk[4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -190,7 +193,7 @@ __device__ __forceinline__ void column_partials(int M, int C, int rows_per_block
   const int nl = cv > 256 ? 1 : max(1, 256 / cv);
   const int m0 = blockIdx.x * rows_per_block;
   const int m1 = min(m0 + rows_per_block, M);
-  float* prow = partial + static_cast<size_t>(blockIdx.x) * 2 * C;
+  float* prow = partial + static_cast<uint32_t>(blockIdx.x) * 2 * C;
   for (int c4 = threadIdx.x % cv; c4 < cv; c4 += (cv > 256 ? 256 : cv)) {
     const int lane = cv > 256 ? 0 : threadIdx.x / cv;
     float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
@@ -229,7 +232,7 @@ __device__ __forceinline__ bool reduce_partials(const float* __restrict__ partia
   double a = 0.0, b = 0.0;
   if (c < C) {
     const float* p = partial + c;
-    const size_t row = static_cast<size_t>(2) * C;
+    const uint32_t row = static_cast<uint32_t>(2) * C;
     int g = lane;
     for (; g + 3 * kRedLanes < G; g += 4 * kRedLanes) {
       float va[4], vb[4];
@@ -277,7 +280,7 @@ __device__ __forceinline__ bool reduce_partials(const float* __restrict__ partia
 __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ y, int M, int C, int rows_per_block,
                                                        float* __restrict__ partial) {
   column_partials(M, C, rows_per_block, partial, [&](int m, int c, float* s, float* q) {
-    const float4 v = *reinterpret_cast<const float4*>(y + static_cast<size_t>(m) * C + c);
+    const float4 v = *reinterpret_cast<const float4*>(y + static_cast<uint32_t>(m) * C + c);
     s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
     q[0] = fmaf(v.x, v.x, q[0]); q[1] = fmaf(v.y, v.y, q[1]); q[2] = fmaf(v.z, v.z, q[2]); q[3] = fmaf(v.w, v.w, q[3]);
   });
@@ -308,13 +311,13 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
                                                        const float* __restrict__ beta,
                                                        const uint16_t* __restrict__ identity,
                                                        const float* __restrict__ scale, int rows_per_sample, int relu,
-                                                       size_t M, int C, uint16_t* __restrict__ a) {
+                                                       uint32_t M, int C, uint16_t* __restrict__ a) {
   const int cv = C >> 2;
-  const size_t total = M * cv;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+  const uint32_t total = M * cv;
+  for (uint32_t i = blockIdx.x * static_cast<uint32_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<uint32_t>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(i % cv) * 4;
-    const size_t m = i / cv;
+    const uint32_t m = i / cv;
     const float4 v = *reinterpret_cast<const float4*>(y + m * C + c);
     const float4 mu = *reinterpret_cast<const float4*>(mean + c);
     const float4 rs = *reinterpret_cast<const float4*>(rstd + c);
@@ -350,12 +353,12 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
 __global__ void maxpool3s2_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, uint8_t* __restrict__ arg,
                                   int B, int H, int W, int C) {
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  const size_t total = static_cast<size_t>(B) * Ho * Wo * C;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+  const uint32_t total = static_cast<uint32_t>(B) * Ho * Wo * C;
+  for (uint32_t i = blockIdx.x * static_cast<uint32_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<uint32_t>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(i % C);
-    const int ox = static_cast<int>((i / C) % Wo), oy = static_cast<int>((i / (static_cast<size_t>(C) * Wo)) % Ho);
-    const size_t n = i / (static_cast<size_t>(C) * Wo * Ho);
+    const int ox = static_cast<int>((i / C) % Wo), oy = static_cast<int>((i / (static_cast<uint32_t>(C) * Wo)) % Ho);
+    const uint32_t n = i / (static_cast<uint32_t>(C) * Wo * Ho);
     float m = -INFINITY;
     int best = 0;
     for (int ky = 0; ky < 3; ++ky)
@@ -378,7 +381,7 @@ __global__ void avgpool_kernel(const uint16_t* __restrict__ in, float* __restric
   if (i >= B * C) return;
   const int c = i % C, n = i / C;
   float s = 0.f;
-  for (int p = 0; p < HW; ++p) s += from_bf16(in[(static_cast<size_t>(n) * HW + p) * C + c]);
+  for (int p = 0; p < HW; ++p) s += from_bf16(in[(static_cast<uint32_t>(n) * HW + p) * C + c]);
   out[i] = s / static_cast<float>(HW);
 }
 
@@ -388,7 +391,7 @@ struct Src {
   const float* p;
   int mode;  // 0 none, 1 same shape, 2 source is the stride-2 subsampled tensor [B,H/2,W/2,C], 3 [B][C] / (H W)
 };
-__device__ __forceinline__ float4 src4_at(const Src& s, size_t n, int y, int x, int c, int H, int W, int C) {
+__device__ __forceinline__ float4 src4_at(const Src& s, uint32_t n, int y, int x, int c, int H, int W, int C) {
   if (s.mode == 1) return *reinterpret_cast<const float4*>(s.p + ((n * H + y) * W + x) * C + c);
   if (s.mode == 2) {
     if ((y | x) & 1) return make_float4(0.f, 0.f, 0.f, 0.f);
@@ -406,15 +409,15 @@ __device__ __forceinline__ float4 src4_at(const Src& s, size_t n, int y, int x, 
 __global__ void __launch_bounds__(256) mask_relu_kernel(Src g0, Src g1, const uint16_t* __restrict__ o, int B, int H,
                                                         int W, int C, float* __restrict__ E) {
   const int cv = C >> 2;
-  const size_t total = static_cast<size_t>(B) * H * W * cv;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+  const uint32_t total = static_cast<uint32_t>(B) * H * W * cv;
+  for (uint32_t i = blockIdx.x * static_cast<uint32_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<uint32_t>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(i % cv) * 4;
     const int x = static_cast<int>((i / cv) % W);
-    const int y = static_cast<int>((i / (static_cast<size_t>(cv) * W)) % H);
-    const size_t n = i / (static_cast<size_t>(cv) * W * H);
+    const int y = static_cast<int>((i / (static_cast<uint32_t>(cv) * W)) % H);
+    const uint32_t n = i / (static_cast<uint32_t>(cv) * W * H);
     const float4 a = src4_at(g0, n, y, x, c, H, W, C), b = src4_at(g1, n, y, x, c, H, W, C);
-    const size_t idx = ((n * H + y) * W + x) * C + c;
+    const uint32_t idx = ((n * H + y) * W + x) * C + c;
     const uint2 ov = *reinterpret_cast<const uint2*>(o + idx);
     float4 e;
     e.x = from_bf16(static_cast<uint16_t>(ov.x & 0xFFFF)) > 0.f ? a.x + b.x : 0.f;
@@ -434,7 +437,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
                                                             int M, int C, int rows_per_block,
                                                             float* __restrict__ partial) {
   column_partials(M, C, rows_per_block, partial, [&](int m, int c, float* s1, float* s2) {
-    const size_t idx = static_cast<size_t>(m) * C + c;
+    const uint32_t idx = static_cast<uint32_t>(m) * C + c;
     float4 g = *reinterpret_cast<const float4*>(up + idx);
     if (relu) {
       const uint2 av = *reinterpret_cast<const uint2*>(a + idx);
@@ -478,16 +481,16 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
                                                            int rows_per_sample, const float* __restrict__ y,
                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
                                                            const float* __restrict__ gamma,
-                                                           const float* __restrict__ sums, size_t M, int C,
+                                                           const float* __restrict__ sums, uint32_t M, int C,
                                                            uint16_t* __restrict__ dy) {
   const int cv = C >> 2;
-  const size_t total = M * cv;
+  const uint32_t total = M * cv;
   const float invM = 1.0f / static_cast<float>(M);
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+  for (uint32_t i = blockIdx.x * static_cast<uint32_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<uint32_t>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(i % cv) * 4;
-    const size_t m = i / cv;
-    const size_t idx = m * C + c;
+    const uint32_t m = i / cv;
+    const uint32_t idx = m * C + c;
     float4 g = *reinterpret_cast<const float4*>(up + idx);
     if (relu) {
       const uint2 av = *reinterpret_cast<const uint2*>(a + idx);
@@ -531,13 +534,13 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
 __global__ void __launch_bounds__(256) col2im3_kernel(const uint16_t* __restrict__ dcol, int B, int H, int W, int C,
                                                       int stride, int Ho, int Wo, float* __restrict__ dxin) {
   const int cv = C >> 2;
-  const size_t total = static_cast<size_t>(B) * H * W * cv;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+  const uint32_t total = static_cast<uint32_t>(B) * H * W * cv;
+  for (uint32_t i = blockIdx.x * static_cast<uint32_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<uint32_t>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(i % cv) * 4;
     const int ix = static_cast<int>((i / cv) % W);
-    const int iy = static_cast<int>((i / (static_cast<size_t>(cv) * W)) % H);
-    const size_t n = i / (static_cast<size_t>(cv) * W * H);
+    const int iy = static_cast<int>((i / (static_cast<uint32_t>(cv) * W)) % H);
+    const uint32_t n = i / (static_cast<uint32_t>(cv) * W * H);
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
@@ -551,7 +554,7 @@ __global__ void __launch_bounds__(256) col2im3_kernel(const uint16_t* __restrict
         if (tx < 0 || tx % stride != 0) continue;
         const int ox = tx / stride;
         if (ox >= Wo) continue;
-        const uint2 v = *reinterpret_cast<const uint2*>(dcol + ((n * Ho + oy) * Wo + ox) * (static_cast<size_t>(9) * C) +
+        const uint2 v = *reinterpret_cast<const uint2*>(dcol + ((n * Ho + oy) * Wo + ox) * (static_cast<uint32_t>(9) * C) +
                                                         (ky * 3 + kx) * C + c);
         acc[0] += from_bf16(static_cast<uint16_t>(v.x & 0xFFFF));
         acc[1] += from_bf16(static_cast<uint16_t>(v.x >> 16));
@@ -569,13 +572,13 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(Src g0, Src g1, const 
                                                           int W, int C, float* __restrict__ gin) {
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const int cv = C >> 2;  // 4 channels per thread
-  const size_t total = static_cast<size_t>(B) * H * W * cv;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+  const uint32_t total = static_cast<uint32_t>(B) * H * W * cv;
+  for (uint32_t i = blockIdx.x * static_cast<uint32_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<uint32_t>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(i % cv) * 4;
     const int ix = static_cast<int>((i / cv) % W);
-    const int iy = static_cast<int>((i / (static_cast<size_t>(cv) * W)) % H);
-    const size_t n = i / (static_cast<size_t>(cv) * W * H);
+    const int iy = static_cast<int>((i / (static_cast<uint32_t>(cv) * W)) % H);
+    const uint32_t n = i / (static_cast<uint32_t>(cv) * W * H);
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (int oy = max(0, iy / 2); oy <= min(Ho - 1, (iy + 1) / 2); ++oy)
       for (int ox = max(0, ix / 2); ox <= min(Wo - 1, (ix + 1) / 2); ++ox) {
@@ -1079,6 +1082,9 @@ int ResNetTrainEngine::launch_bn_backward(const Unit& u, const float* up, int re
 
 int ResNetTrainEngine::plan(int B) {
   free_acts();
+  // 32-bit element indices in the elementwise kernels: the largest tensor is layer1's im2col matrix [B H/4 W/4][576]
+  if (static_cast<double>(B) * (H_ / 4) * (W_ / 4) * 576.0 >= 4.0e9 || static_cast<double>(B) * H_ * W_ * 16.0 >= 4.0e9)
+    return fail(kUnsupported, "encoder_train: batch too large for one call (32-bit tensor indices)");
   ResNetTrainEngine* self = this;
   // ---- parameter panels (every forward: the optimizer changed the weights), one launch for all convolutions
   if (units_.size() > static_cast<size_t>(kMaxPackJobs)) return fail(kUnsupported, "encoder: pack table too small");
