@@ -668,29 +668,33 @@ __global__ void __launch_bounds__(256) wgrad_1ch_kernel(const uint16_t* __restri
   for (int t = 0; t < 9; ++t)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
-  const int64_t total = static_cast<int64_t>(B) * H * W;
-  const int64_t p_end = min(static_cast<int64_t>(blockIdx.x + 1) * P, total);
+  // 32-bit pixel indices (the launcher checks B H W < 2^31): the 64-bit index splits were most of this kernel's
+  // instructions
+  const int total = B * H * W;
+  const int p_end = min((static_cast<int>(blockIdx.x) + 1) * P, total);
   constexpr int kU = 4;  // pixels in flight per thread
-  for (int64_t p0 = static_cast<int64_t>(blockIdx.x) * P + pl; p0 < p_end; p0 += kU * lanes) {
+  for (int p0 = static_cast<int>(blockIdx.x) * P + pl; p0 < p_end; p0 += kU * lanes) {
     uint4 u[kU];
 #pragma unroll
     for (int k = 0; k < kU; ++k) {
-      const int64_t p = p0 + k * lanes;
-      if (p < p_end) u[k] = __ldg(reinterpret_cast<const uint4*>(act + p * C + v * 8));
+      const int p = p0 + k * lanes;
+      if (p < p_end) u[k] = __ldg(reinterpret_cast<const uint4*>(act + static_cast<size_t>(p) * C + v * 8));
     }
 #pragma unroll
     for (int k = 0; k < kU; ++k) {
-      const int64_t p = p0 + k * lanes;
+      const int p = p0 + k * lanes;
       if (p >= p_end) continue;
-      const int x = static_cast<int>(p % W);
-      const int y = static_cast<int>((p / W) % H);
-      const int64_t nb = p / (static_cast<int64_t>(W) * H) * H * W;
+      const int row = p / W;
+      const int x = p - row * W;
+      const int img_n = row / H;
+      const int y = row - img_n * H;
+      const int nb = img_n * H * W;
       float f[8];
       unpack8(u[k], fmt, f);
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
         const int yy = y + sgn * (t / 3 - 1), xx = x + sgn * (t % 3 - 1);
-        const float im = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(img + nb + static_cast<int64_t>(yy) * W + xx) : 0.f;
+        const float im = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(img + nb + yy * W + xx) : 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(f[j], im, acc[t][j]);
       }
@@ -725,24 +729,26 @@ __global__ void __launch_bounds__(256) head_bwd_data_kernel(const float* __restr
   for (int j = 0; j < 8; ++j)
 #pragma unroll
     for (int t = 0; t < 9; ++t) wr[j][t] = __ldg(w + (v * 8 + j) * 9 + t);
-  const int64_t npix = static_cast<int64_t>(B) * H * W;
+  const int npix = B * H * W;  // < 2^31 (checked by the launcher): 32-bit index splits
   const int lanes = blockDim.x / nvec;
-  for (int64_t p = static_cast<int64_t>(blockIdx.x) * lanes + threadIdx.x / nvec; p < npix;
-       p += static_cast<int64_t>(gridDim.x) * lanes) {
-    const int x = static_cast<int>(p % W);
-    const int y = static_cast<int>((p / W) % H);
-    const int64_t nb = p / (static_cast<int64_t>(W) * H) * H * W;
+  for (int p = static_cast<int>(blockIdx.x) * lanes + threadIdx.x / nvec; p < npix;
+       p += static_cast<int>(gridDim.x) * lanes) {
+    const int row = p / W;
+    const int x = p - row * W;
+    const int img_n = row / H;
+    const int y = row - img_n * H;
+    const int nb = img_n * H * W;
     float o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = 0.f;
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       const int yy = y - (t / 3 - 1), xx = x - (t % 3 - 1);
-      const float d = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(dout + nb + static_cast<int64_t>(yy) * W + xx) : 0.f;
+      const float d = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(dout + nb + yy * W + xx) : 0.f;
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = fmaf(d, wr[j][t], o[j]);
     }
-    *reinterpret_cast<uint4*>(dact + p * C + v * 8) = pack8(o, fmt);
+    *reinterpret_cast<uint4*>(dact + static_cast<size_t>(p) * C + v * 8) = pack8(o, fmt);
   }
 }
 
@@ -1066,6 +1072,7 @@ int launch_wgrad_1ch(const void* act, const float* img, float* out, int B, int H
                      cudaStream_t stream) {
   if (C != 128) return fail(kUnsupported, "wgrad_1ch: the stem / head gradient kernel expects 128 channels");
   const int64_t total = static_cast<int64_t>(B) * H * W;
+  if (total >= (1ll << 31) - (1 << 20)) return fail(kUnsupported, "wgrad_1ch: more than 2^31 pixels in one call");
   int blocks = 2 * device_sm_count();
   if (blocks > (total + 15) / 16) blocks = static_cast<int>((total + 15) / 16);
   const int P = static_cast<int>((total + blocks - 1) / blocks);
@@ -1076,6 +1083,8 @@ int launch_wgrad_1ch(const void* act, const float* img, float* out, int B, int H
 int launch_head_bwd_data(const float* dout, const float* w, void* dact, int B, int H, int W, int C, int fmt,
                          cudaStream_t stream) {
   if (C % 8 != 0 || 256 % (C / 8) != 0) return fail(kUnsupported, "head_bwd_data: unsupported channel count");
+  if (static_cast<int64_t>(B) * H * W >= (1ll << 31) - (1 << 24))
+    return fail(kUnsupported, "head_bwd_data: more than 2^31 pixels in one call");
   const int64_t total = static_cast<int64_t>(B) * H * W * (C / 8);
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > 8 * device_sm_count()) blocks = 8 * device_sm_count();
