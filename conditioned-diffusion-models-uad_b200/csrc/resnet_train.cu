@@ -806,7 +806,9 @@ int ResNetTrainEngine::run_list(std::vector<std::function<int(cudaStream_t)>>& o
     for (auto& op : ops) CDDPM_TRY(op(stream));
     return kOk;
   };
-  if (!enc_graphs_enabled()) return eager();
+  // a caller whose buffers never repeat would pay a capture on every second call: once captures clearly outnumber
+  // replays, stay eager
+  if (!enc_graphs_enabled() || (graph_captures_ >= 8 && graph_replays_ < 2 * graph_captures_)) return eager();
   GraphSlot* slot = nullptr;
   for (GraphSlot& g : slots)
     if (g.key == key) slot = &g;
@@ -842,6 +844,9 @@ int ResNetTrainEngine::run_list(std::vector<std::function<int(cudaStream_t)>>& o
     const cudaError_t ie = cudaGraphInstantiate(&slot->exec, graph, 0);
     cudaGraphDestroy(graph);
     CDDPM_TRY(check_cuda(ie, "cudaGraphInstantiate (encoder)"));
+    ++graph_captures_;
+  } else {
+    ++graph_replays_;
   }
   CDDPM_CUDA(cudaGraphLaunch(slot->exec, stream));
   return kOk;

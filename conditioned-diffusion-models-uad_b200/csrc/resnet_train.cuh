@@ -125,6 +125,7 @@ class ResNetTrainEngine {
   std::vector<GraphSlot> fwd_graphs_, bwd_graphs_;
   cudaStream_t cap_stream_ = nullptr;
   uint64_t use_clock_ = 0;
+  int graph_captures_ = 0, graph_replays_ = 0;
   // stem / pool / head buffers
   float* stem_y_ = nullptr;
   uint16_t *stem_a_ = nullptr, *pool_a_ = nullptr;

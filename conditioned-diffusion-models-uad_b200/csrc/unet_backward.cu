@@ -588,7 +588,9 @@ int UNetEngine::backward(const float* dout, float* grads, float* dcond, int B, c
     const char* e = getenv("CDDPM_BWD_GRAPH");
     return !(e != nullptr && e[0] == '0');
   }();
-  if (!graphs) return eager();
+  // (a caller whose buffers never repeat would pay a capture on every second call: stay eager once captures clearly
+  // outnumber replays)
+  if (!graphs || (bwd_captures_ >= 8 && bwd_replays_ < 2 * bwd_captures_)) return eager();
   const std::vector<const void*> key = {dout, grads, dcond, cur_x_, cur_t_, cur_cond_};
   BwdGraph* slot = nullptr;
   for (BwdGraph& g : bwd_graphs_)
@@ -625,6 +627,9 @@ int UNetEngine::backward(const float* dout, float* grads, float* dcond, int B, c
     const cudaError_t ie = cudaGraphInstantiate(&slot->exec, graph, 0);
     cudaGraphDestroy(graph);
     CDDPM_TRY(check_cuda(ie, "cudaGraphInstantiate (backward)"));
+    ++bwd_captures_;
+  } else {
+    ++bwd_replays_;
   }
   CDDPM_CUDA(cudaGraphLaunch(slot->exec, stream));
   return kOk;

@@ -120,6 +120,7 @@ class UNetEngine {
   };
   std::vector<BwdGraph> bwd_graphs_;
   uint64_t bwd_clock_ = 0;
+  int bwd_captures_ = 0, bwd_replays_ = 0;
   float* cur_grads_ = nullptr;
   const float* cur_dout_ = nullptr;
   float* cur_dcond_ = nullptr;

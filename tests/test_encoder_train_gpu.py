@@ -136,3 +136,31 @@ def test_training_encoder_drop_path_and_eval_after_training():
     fresh = fresh.cuda().eval()
     with torch.no_grad():
         assert torch.equal(y, fresh(x))
+
+
+def test_training_encoder_graph_replay_follows_the_callers_buffers():
+    """The launch lists are replayed as CUDA graphs keyed by every pointer they bind (csrc/resnet_train.cu:run_list): a
+    key is run eagerly when first seen, captured the second time, replayed from the third.  Two inputs held alive at
+    once (two addresses) are alternated: for each, the eager, the capturing and the replayed call must return the same
+    features and the same gradients (the forward and the BatchNorm reductions are order-fixed; the weight-gradient GEMM
+    accumulates with atomics, hence a tolerance there)."""
+    enc = _encoder("b200", drop=0.0)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    xs = [torch.rand(8, 1, 96, 96, device="cuda", generator=g) for _ in range(2)]
+    w = torch.randn(8, 128, device="cuda", generator=g)
+    first = {}
+    for rnd in range(4):
+        for i, x in enumerate(xs):
+            for p in enc.parameters():
+                p.grad = None
+            out = enc(x)
+            (out * w).sum().backward()
+            torch.cuda.synchronize()
+            grads = torch.cat([p.grad.flatten() for p in enc.parameters()])
+            if rnd == 0:
+                first[i] = (out.detach().clone(), grads.clone())
+                continue
+            assert torch.equal(out.detach(), first[i][0]), f"input {i}, call {rnd}: features differ from the eager call"
+            rel = ((grads - first[i][1]).norm() / first[i][1].norm()).item()
+            assert rel <= 1e-4, f"input {i}, call {rnd}: gradients differ from the eager call (rel {rel:.3g})"
+    assert not torch.equal(first[0][0], first[1][0])
