@@ -3,11 +3,12 @@
 // timm ResNet.forward in train() mode (src/models/DDPM_2D.py:101-122, spark/resnet.py:13-46, spark/models.py:89-109) and
 // torch autograd over it.
 //
-// Every convolution after the 7x7 stem is a GEMM on the tcgen05 kernels: forward and data gradient on the flat mode of
-// conv_igemm (over an im2col'ed operand for the 3x3 / strided layers), weight gradient on flat_wgrad_tc_kernel
-// (resnet_train.cu: the contraction runs over pixels, both operands MN-major straight from the row-major activations).
-// Operands are bf16 (BASELINE configs[4]), accumulation fp32; the raw convolution outputs, the BatchNorm statistics
-// (fp64 sums), the normalisation and every gradient that is summed over several paths stay fp32.
+// Every convolution is a GEMM on the tcgen05 kernels: forward and data gradient on the flat mode of conv_igemm (over an
+// im2col'ed operand for the 3x3 / strided layers and for the 7x7 stem, whose 49 taps are padded to 64), weight gradient
+// on flat_wgrad_tc_kernel (resnet_train.cu: the contraction runs over pixels, both operands MN-major straight from the
+// row-major activations).  Operands are bf16 (BASELINE configs[4]), accumulation fp32; the raw convolution outputs, the
+// BatchNorm statistics (fp32 per-block partial rows folded in float64), the normalisation and every gradient that is
+// summed over several paths stay fp32.  Both launch lists are replayed as CUDA graphs keyed by the pointers they bind.
 #pragma once
 #include <functional>
 #include <map>
@@ -127,10 +128,8 @@ class ResNetTrainEngine {
   uint64_t use_clock_ = 0;
   int graph_captures_ = 0, graph_replays_ = 0;
   // stem / pool / head buffers
-  float* stem_y_ = nullptr;
-  uint16_t *stem_a_ = nullptr, *pool_a_ = nullptr;
+  uint16_t* pool_a_ = nullptr;
   float *pooled_ = nullptr, *dpooled_ = nullptr, *stem_g_ = nullptr;
-  uint16_t* stem_dy_ = nullptr;
   uint8_t* pool_arg_ = nullptr;  // argmax position of every max-pool window (forward -> backward)
   uint16_t* stem_col_ = nullptr;  // [B*Ho*Wo][64] im2col of the input (49 taps + padding), forward and weight gradient
   float* stem_dwp_ = nullptr;     // [64][64] stem weight gradient in panel order
