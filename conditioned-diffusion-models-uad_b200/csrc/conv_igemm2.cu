@@ -23,9 +23,14 @@
 // ~25 B/cycle/SM from L2.  Weight slabs travel in stages of three taps (one kernel row), so the issuing thread waits
 // on one barrier and commits once per 24 MMAs.
 //
-// With both changes the kernel sits on the shared-memory roofline: operand reads (96 B/cycle) plus TMA writes
-// (~25 B/cycle) use ~95 % of the 128 B/cycle.  (Folding the preceding GroupNorm+SiLU into the staged tiles was built
-// and measured: any extra pass over the tile in shared memory costs more than the HBM pass it saves.)
+// Where the remaining time goes (ncu --set full at HEAD, 128->128 @96x96, 65 us, tensor pipe 81 % active): the
+// tensor core's operand reads are l1tex__data_pipe_tc_wavefronts_mem_shared = 53 % of that pipe's peak (the LSU adds
+// 9 %, the TMA writes show as l1tex__data_bank_writes = 10 %) - shared memory is the second-busiest unit, not a
+// saturated one (an earlier version of this comment claimed ~95 % from a byte budget; the counter does not support
+// it).  What separates this launch from the 95 %-active 256->256 ones (222 us) is fixed cost: launch, TMEM allocation,
+// pipeline fill and the last tiles' epilogues are ~8 us of a 65 us kernel, and at K = 1152 the epilogue paces the
+// MMA stream.  (Folding the preceding GroupNorm+SiLU into the staged tiles was built and measured: an extra LSU pass
+// over every tile in shared memory cost more conv time than the HBM pass it saves.)
 // Warp roles: warp 0 weight producer, warp 3 halo-tile producer (its own thread, so tile loads run ahead by the
 // depth of the tile ring), warp 1 MMA issuer (leader CTA only, warp-uniform operands), warp 2 TMEM allocator,
 // warps 4-11 epilogue (one warpgroup per M tile: bias, residual, activation, GroupNorm partial sums, 16-bit NHWC
