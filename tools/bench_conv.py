@@ -20,6 +20,10 @@ SHAPES = [  # (B, H, W, cins, k, cout, residual)
 
 
 def main():
+    global SHAPES
+    if "--sweep" in sys.argv:  # batch sweep of one class: the intercept of time vs batch is the per-launch fixed cost
+        SHAPES = [(b, 96, 96, [128], 3, 128, False) for b in (2, 4, 8, 16, 32, 64)] + \
+                 [(b, 48, 48, [256], 3, 256, False) for b in (8, 16, 32, 64, 128)]
     dt = torch.float16
     tag = " ".join(f"{k}={os.environ[k]}" for k in ("CDDPM_CONV_PAIR", "CDDPM_CONV_V2", "CDDPM_CONV_DEBUG") if k in os.environ)
     print("variant:", tag or "default", flush=True)
