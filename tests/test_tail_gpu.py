@@ -401,3 +401,43 @@ def test_log_images_writes_the_reference_grid_files(tmp_path, monkeypatch):
         assert got.shape == want.shape == (96, 4 * 96, 3)
         assert np.abs(got.astype(np.int16) - want.astype(np.int16)).max() <= 1
         assert got[:, 2 * 96:3 * 96].std() > 0  # the difference panel is not blank
+
+
+@pytest.mark.parametrize("shape", [(13, 17, 9), (33, 7, 5), (40, 41, 12)])
+def test_median5_pair_kernel_vs_scipy_on_odd_shapes(shape):
+    """The 5x5x5 median (csrc/tail.cu:median5_pair_kernel: two x-neighbours per thread, forgetful selection) against
+    scipy.ndimage.median_filter itself - the reference's implementation (utils_eval.py:462-464) - on volumes whose sides
+    are odd, smaller than a tile, or not multiples of the pair width; values mix exact zeros, ties and negatives."""
+    from scipy import ndimage
+
+    from cddpm.eval_tail import apply_3d_median_filter
+
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.rand(*shape, generator=g)
+    x = torch.where(torch.rand(*shape, generator=g) < 0.4, torch.zeros(()), x)       # many exact zeros (masked residual)
+    x = torch.where(torch.rand(*shape, generator=g) < 0.1, torch.full((), 0.25), x)  # ties
+    x = torch.where(torch.rand(*shape, generator=g) < 0.05, -x, x)                   # a few negatives
+    ref = ndimage.median_filter(x.numpy(), (5, 5, 5))
+    got = apply_3d_median_filter(x.cuda(), kernelsize=5).cpu().numpy()
+    assert np.array_equal(got, ref)
+
+
+def test_compose_grid_kernel_matches_port_on_a_non_square_slice():
+    import ctypes  # noqa: F401
+
+    from cddpm._lib import check, current_stream, lib, ptr
+    from oracle.tail_port import compose_grid_port
+
+    H, W = 40, 56
+    g = torch.Generator().manual_seed(5)
+    panels = torch.rand(4, H, W, generator=g)
+    panels[3] = (panels[3] > 0.7).float()
+    ranges = torch.tensor([[0.1, 0.9], [0.0, 1.0], [0.0, 0.8], [0.0, 1.0]])
+    rgb = torch.empty(W, 4 * H, 3, dtype=torch.uint8, device="cuda")
+    panels_dev, ranges_dev = panels.cuda(), ranges.cuda()  # named: the launch is asynchronous
+    check(lib().cddpm_compose_grid(ptr(panels_dev), ptr(ranges_dev), H, W, ptr(rgb), current_stream()),
+          "cddpm_compose_grid")
+    torch.cuda.synchronize()
+    want = compose_grid_port(panels.numpy(), ranges.numpy())
+    diff = np.abs(rgb.cpu().numpy().astype(np.int16) - want.astype(np.int16))
+    assert diff.max() <= 1 and (diff > 0).mean() < 0.2  # one grey level where the fused multiply-add rounds the other way
