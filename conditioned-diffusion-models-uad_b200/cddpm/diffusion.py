@@ -301,7 +301,8 @@ class GaussianDiffusion(nn.Module):
         if nz is not None:
             nz, f16 = _noise_arg(nz)
         out = _out if _out is not None else torch.empty_like(x)
-        check(lib().cddpm_posterior_step(ptr(model_out), ptr(x.contiguous()), ptr(nz), f16, ptr(out),
+        xc = x.contiguous()  # named: a temporary must outlive the (asynchronous) launch that reads it
+        check(lib().cddpm_posterior_step(ptr(model_out), ptr(xc), ptr(nz), f16, ptr(out),
                                          ptr(self.posterior_mean_coef1), ptr(self.posterior_mean_coef2),
                                          ptr(self.posterior_log_variance_clipped),
                                          ptr(self.sqrt_recip_alphas_cumprod), ptr(self.sqrt_recipm1_alphas_cumprod),
@@ -374,7 +375,8 @@ class GaussianDiffusion(nn.Module):
             if time_next > 0:
                 nz, f16 = _noise_arg(gen_noise(self.cfg, shape, device=device) if simplex else _randn(shape, device))
             out = bufs[i & 1]
-            check(lib().cddpm_ddim_step(ptr(model_out), ptr(img.contiguous()), ptr(nz), f16, ptr(out), float(sr[time]),
+            imgc = img.contiguous()
+            check(lib().cddpm_ddim_step(ptr(model_out), ptr(imgc), ptr(nz), f16, ptr(out), float(sr[time]),
                                         float(srm1[time]), float(alpha_next.sqrt()), float(c), float(sigma), batch, hw,
                                         1 if self.objective == "pred_noise" else 0, 1 if clip_denoised else 0,
                                         1 if i == len(pairs) - 1 else 0, current_stream()), "cddpm_ddim_step")

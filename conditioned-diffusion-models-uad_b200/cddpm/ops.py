@@ -75,7 +75,8 @@ def pack_conv_weight_t(weight: torch.Tensor, dtype=torch.bfloat16) -> torch.Tens
     """OIHW fp32 weight -> panel [Cin, k*k*Cout] of the data-gradient convolution (flipped taps, channels exchanged)."""
     cout, cin, kh, kw = weight.shape
     out = torch.empty(cin, kh * kw * cout, device=weight.device, dtype=dtype)
-    check(lib().cddpm_pack_conv_weight_t(ptr(weight.contiguous()), cout, cin, kh, 0, cin, ptr(out), kh * kw * cout, 0,
+    wc = weight.contiguous()
+    check(lib().cddpm_pack_conv_weight_t(ptr(wc), cout, cin, kh, 0, cin, ptr(out), kh * kw * cout, 0,
                                          fmt_of(dtype), current_stream()), "cddpm_pack_conv_weight_t")
     return out
 
