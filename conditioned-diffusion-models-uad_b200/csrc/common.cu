@@ -77,6 +77,19 @@ bool pdl_enabled() {
 }
 static thread_local bool g_pdl_next = false;
 void pdl_set_next(bool on) { g_pdl_next = on && pdl_enabled(); }
+// Which kernels accept the programmatic launch that capture offers them.  Measured on one box (profiles/r02_summary.md,
+// call 52-54): only the convolutions (default, 3) - their barrier init, TMEM allocation, descriptor prefetch and weight
+// ring then run under the tail of the GroupNorm pass in front of them: B=32 forward 4.956 -> 4.784 ms, B=8 1.733 ->
+// 1.661, B=1 1.187 -> 1.156; letting the GroupNorm / attention / stem / head kernels start early as well (1) gives the
+// gain back at every batch size above 4 (their early blocks sit on SM slots the convolution's last tiles still use).
+int pdl_mode() {
+  static const int mode = [] {
+    const char* e = getenv("CDDPM_PDL_MODE");  // 1 = every kernel with a griddepcontrol.wait, 2 = all but the convolutions
+    return e != nullptr ? atoi(e) : 3;
+  }();
+  return mode;
+}
+bool pdl_elementwise_ok() { return pdl_mode() != 3; }
 bool pdl_take_next() {
   const bool v = g_pdl_next;
   g_pdl_next = false;

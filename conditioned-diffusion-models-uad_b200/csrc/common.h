@@ -54,6 +54,8 @@ int device_sm_count();
 bool pdl_enabled();
 void pdl_set_next(bool on);
 bool pdl_take_next();
+int pdl_mode();             // CDDPM_PDL_MODE: 3 (default) only the convolutions take the offer, 1 every kernel, 2 all but them
+bool pdl_elementwise_ok();
 
 template <typename... P, typename... A>
 inline cudaError_t launch_k(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A&&... args) {
@@ -64,7 +66,7 @@ inline cudaError_t launch_k(void (*kernel)(P...), dim3 grid, dim3 block, size_t 
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   int n = 0;
-  if (pdl_take_next()) {
+  if (pdl_take_next() && pdl_elementwise_ok()) {
     attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[n].val.programmaticStreamSerializationAllowed = 1;
     ++n;

@@ -854,7 +854,7 @@ int launch_conv2(const std::shared_ptr<void>& holder, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (pdl_take_next()) {
+  if (pdl_take_next() && pdl_mode() != 2) {
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.numAttrs = 2;

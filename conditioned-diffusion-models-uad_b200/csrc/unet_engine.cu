@@ -1010,8 +1010,8 @@ int UNetEngine::plan(int B) {
 // hide a prologue under), so the attribute is only offered to small batches (CDDPM_PDL_MAX_B overrides, default 4).
 static bool pdl_batch_ok(int B) {
   static const int max_b = [] {
-    const char* e = getenv("CDDPM_PDL_MAX_B");
-    return e != nullptr ? atoi(e) : 4;
+    const char* e = getenv("CDDPM_PDL_MAX_B");  // A/B switch: offer programmatic launches only up to this batch size
+    return e != nullptr ? atoi(e) : (1 << 30);
   }();
   return B <= max_b;
 }
