@@ -167,8 +167,10 @@ __global__ void __launch_bounds__(256, kMode == 0 ? 4 : 3) gn_apply_kernel(const
   const int b = a.reverse ? static_cast<int>(gridDim.y - 1 - blockIdx.y) : static_cast<int>(blockIdx.y);
   const int chunk = a.reverse ? static_cast<int>(gridDim.x - 1 - blockIdx.x) : static_cast<int>(blockIdx.x);
   const int cpg = C / kGnGroups;
-  pdl_trigger();
+  // wait first: a pass that was itself launched programmatically must not release its own dependent (the next
+  // convolution, whose CTAs take whole SMs) before it has begun to run
   pdl_wait();  // the statistics and x come from the preceding convolution
+  pdl_trigger();
 
   // ---- pixel / channel assignment, and the FIRST batch of loads before the coefficient prologue: the prologue is two
   // dependent L2 round trips + a block barrier each (~1 us), as long as the whole data phase of a 64-pixel block
