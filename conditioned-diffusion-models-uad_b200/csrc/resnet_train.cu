@@ -779,6 +779,9 @@ ResNetTrainEngine::~ResNetTrainEngine() {
   free_acts();
   for (void* p : owned_) cudaFree(p);
   if (cap_stream_ != nullptr) cudaStreamDestroy(cap_stream_);
+  if (side_stream_ != nullptr) cudaStreamDestroy(side_stream_);
+  if (ev_fork_ != nullptr) cudaEventDestroy(ev_fork_);
+  if (ev_join_ != nullptr) cudaEventDestroy(ev_join_);
 }
 
 void ResNetTrainEngine::drop_graphs() {
@@ -800,12 +803,52 @@ static bool enc_graphs_enabled() {
 // Runs a launch list on `stream`: eagerly for a key seen for the first time, as a captured graph from then on.  At most
 // four graphs per list (least recently used is replaced), so a caller that hands in new buffers on every step costs
 // one capture per step at worst and nothing in correctness.
-int ResNetTrainEngine::run_list(std::vector<std::function<int(cudaStream_t)>>& ops, std::vector<GraphSlot>& slots,
-                                const std::vector<const void*>& key, cudaStream_t stream) {
-  auto eager = [&]() -> int {
+// The ops of a list in order on `stream`; ops flagged in `side` go to a second stream that forks off `stream` in front
+// of each of them and is joined at the end.  The weight-gradient GEMMs of the backward list hang off the data-gradient
+// chain (they read dy and the forward activations, write their own slice of the gradients): on the side branch their
+// 12-15 us launch floors run beside the chain instead of inside it.  CDDPM_ENC_SIDE=0 keeps one stream.
+int ResNetTrainEngine::run_ops(std::vector<std::function<int(cudaStream_t)>>& ops, const std::vector<uint8_t>* side,
+                               cudaStream_t stream) {
+  static const bool side_on = [] {
+    const char* e = getenv("CDDPM_ENC_SIDE");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  if (side == nullptr || !side_on || side->size() != ops.size()) {
     for (auto& op : ops) CDDPM_TRY(op(stream));
     return kOk;
-  };
+  }
+  if (side_stream_ == nullptr) {
+    CDDPM_CUDA(cudaStreamCreateWithFlags(&side_stream_, cudaStreamNonBlocking));
+    CDDPM_CUDA(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
+    CDDPM_CUDA(cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming));
+  }
+  bool forked = false;
+  int st = kOk;
+  for (size_t i = 0; i < ops.size() && st == kOk; ++i) {
+    if ((*side)[i]) {
+      CDDPM_CUDA(cudaEventRecord(ev_fork_, stream));
+      CDDPM_CUDA(cudaStreamWaitEvent(side_stream_, ev_fork_, 0));
+      st = ops[i](side_stream_);
+      forked = true;
+    } else {
+      st = ops[i](stream);
+    }
+  }
+  if (forked) {  // always join, also on an error: a capture must not end with a dangling branch
+    const cudaError_t e1 = cudaEventRecord(ev_join_, side_stream_);
+    const cudaError_t e2 = cudaStreamWaitEvent(stream, ev_join_, 0);
+    if (st == kOk) {
+      CDDPM_CUDA(e1);
+      CDDPM_CUDA(e2);
+    }
+  }
+  return st;
+}
+
+int ResNetTrainEngine::run_list(std::vector<std::function<int(cudaStream_t)>>& ops, std::vector<GraphSlot>& slots,
+                                const std::vector<const void*>& key, cudaStream_t stream,
+                                const std::vector<uint8_t>* side) {
+  auto eager = [&]() -> int { return run_ops(ops, side, stream); };
   // a caller whose buffers never repeat would pay a capture on every second call: once captures clearly outnumber
   // replays, stay eager
   if (!enc_graphs_enabled() || (graph_captures_ >= 8 && graph_replays_ < 2 * graph_captures_)) return eager();
@@ -830,11 +873,7 @@ int ResNetTrainEngine::run_list(std::vector<std::function<int(cudaStream_t)>>& o
     if (slot->seen++ == 0) return eager();
     if (cap_stream_ == nullptr) CDDPM_CUDA(cudaStreamCreateWithFlags(&cap_stream_, cudaStreamNonBlocking));
     CDDPM_CUDA(cudaStreamBeginCapture(cap_stream_, cudaStreamCaptureModeThreadLocal));
-    int st = kOk;
-    for (auto& op : ops) {
-      st = op(cap_stream_);
-      if (st != kOk) break;
-    }
+    const int st = run_ops(ops, side, cap_stream_);
     cudaGraph_t graph = nullptr;
     const cudaError_t ce = cudaStreamEndCapture(cap_stream_, &graph);
     if (st != kOk || ce != cudaSuccess) {
@@ -858,6 +897,7 @@ void ResNetTrainEngine::free_acts() {
   act_owned_.clear();
   fwd_ops_.clear();
   bwd_ops_.clear();
+  bwd_side_.clear();
   planned_B_ = 0;
   forward_done_ = false;
 }
@@ -1042,6 +1082,8 @@ int ResNetTrainEngine::plan_unit_backward(Unit& u, int B, bool need_dx) {
       unpack_grad_kernel<<<grid_for(static_cast<size_t>(cout) * K), 256, 0, s>>>(dwp, cout, cin, taps, g);
       return check_launch("unpack_grad_kernel");
     });
+    bwd_side_.resize(bwd_ops_.size(), 0);
+    bwd_side_.back() = 1;  // off the data-gradient chain: runs on the side branch (run_ops)
   }
   if (!need_dx) return kOk;
   if (u.k == 3) {
@@ -1337,7 +1379,8 @@ int ResNetTrainEngine::backward(const float* dout, float* grads, int B, cudaStre
   // the backward list also binds the forward's drop scales and the parameters (gamma, fc weight)
   std::vector<const void*> key = {dout, grads, cur_drop_};
   key.insert(key.end(), values_.begin(), values_.end());
-  CDDPM_TRY(run_list(bwd_ops_, bwd_graphs_, key, stream));
+  bwd_side_.resize(bwd_ops_.size(), 0);
+  CDDPM_TRY(run_list(bwd_ops_, bwd_graphs_, key, stream, &bwd_side_));
   forward_done_ = false;
   return kOk;
 }

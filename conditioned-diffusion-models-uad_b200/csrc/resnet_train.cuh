@@ -120,8 +120,14 @@ class ResNetTrainEngine {
     int seen = 0;
     uint64_t last_use = 0;
   };
+  // side: optional flags, one per op - flagged ops (the weight-gradient GEMMs: off the data-gradient chain) run on a
+  // forked side stream / graph branch that is joined at the end of the list
   int run_list(std::vector<std::function<int(cudaStream_t)>>& ops, std::vector<GraphSlot>& slots,
-               const std::vector<const void*>& key, cudaStream_t stream);
+               const std::vector<const void*>& key, cudaStream_t stream, const std::vector<uint8_t>* side = nullptr);
+  int run_ops(std::vector<std::function<int(cudaStream_t)>>& ops, const std::vector<uint8_t>* side, cudaStream_t stream);
+  std::vector<uint8_t> bwd_side_;
+  cudaStream_t side_stream_ = nullptr;
+  cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr;
   void drop_graphs();
   std::vector<GraphSlot> fwd_graphs_, bwd_graphs_;
   cudaStream_t cap_stream_ = nullptr;
