@@ -11,7 +11,6 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "conditioned-diffusion-models-uad_b200"
 
 def main():
     from cddpm._lib import check, current_stream, lib, ptr
-    from oracle.weights import synthetic_fullres_case  # noqa: F401  (same generator family as the tail goldens)
 
     D, H, W = (int(v) for v in sys.argv[1:4]) if len(sys.argv) >= 4 else (50, 96, 96)
     g = torch.Generator(device="cuda").manual_seed(0)
