@@ -528,7 +528,10 @@ def log_images(self, diff_volume, data_orig, data_seg, data_mask, final_volume, 
     grid_dir = os.path.join(os.getcwd(), "grid")
     os.makedirs(grid_dir, exist_ok=True)
     if _image_writer is None:
+        import atexit
+
         _image_writer = _ImageWriter()
+        atexit.register(flush_image_writer)  # a run that never reaches _test_end still gets its files
     name = ID[0] if isinstance(ID, (list, tuple)) else ID
     with torch.cuda.device(dev):
         vmax = d.max() + 0.01
