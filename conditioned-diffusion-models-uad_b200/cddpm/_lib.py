@@ -53,6 +53,7 @@ def _signatures(c):
         "cddpm_memcpy_d2d": (i32, [vp, vp, i64, vp]),
         "cddpm_pack_conv_weight": (i32, [vp, i32, i32, i32, i32, i32, vp, i32, i32, i32, vp]),
         "cddpm_conv_igemm": (i32, [i32, pvp, pi32, pi32, i32, i32, i32, i32, vp, vp, vp, vp, i32, i32, vp]),
+        "cddpm_conv_igemm_stats": (i32, [i32, pvp, pi32, pi32, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp]),
         "cddpm_pack_conv_weight_t": (i32, [vp, i32, i32, i32, i32, i32, vp, i32, i32, i32, vp]),
         "cddpm_conv_wgrad": (i32, [i32, pvp, pi32, pi32, pi32, vp, i32, i32, i32, i32, vp, i32, vp]),
         "cddpm_unpack_conv_grad": (i32, [vp, i32, i32, i32, i32, i32, vp, i32, i32, vp]),

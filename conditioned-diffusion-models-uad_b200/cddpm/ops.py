@@ -61,6 +61,36 @@ def conv_igemm(
     return out
 
 
+def conv_igemm_stats(
+    srcs: Sequence[torch.Tensor],
+    taps: Sequence[int],
+    wpacked: torch.Tensor,
+    bias: Optional[torch.Tensor] = None,
+    residual: Optional[torch.Tensor] = None,
+):
+    """conv_igemm with a 16-bit output plus the GroupNorm partial sums of the fp32 result: returns (out, stats) with
+    stats [B, cout/4, 2] float64 = (sum, sum of squares) per image and 4-channel bucket (util.py:214-216 GroupNorm32
+    over the output of a ResBlock convolution, OpenAI_Unet.py:284-338)."""
+    B, H, W, _ = srcs[0].shape
+    cout = wpacked.shape[0]
+    dtype = srcs[0].dtype
+    out = torch.empty(B, H, W, cout, device=srcs[0].device, dtype=dtype)
+    stats = torch.zeros(B, cout // 4, 2, device=srcs[0].device, dtype=torch.float64)
+    check(
+        lib().cddpm_conv_igemm_stats(
+            len(srcs),
+            ptr_array([ptr(s) for s in srcs]),
+            int_array([s.shape[3] for s in srcs]),
+            int_array(list(taps)),
+            B, H, W, cout,
+            ptr(wpacked), ptr(bias), ptr(residual), ptr(out),
+            fmt_of(dtype), ptr(stats), current_stream(),
+        ),
+        "cddpm_conv_igemm_stats",
+    )
+    return out, stats
+
+
 def attention(qkv: torch.Tensor, channels: int) -> torch.Tensor:
     """QKVAttention over qkv [B, L, 3*C] (q | k | v, heads of 64 channels) -> [B, L, C] (OpenAI_Unet.py:457-476)."""
     B, L, c3 = qkv.shape

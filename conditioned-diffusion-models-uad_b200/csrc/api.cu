@@ -41,9 +41,9 @@ int cddpm_pack_conv_weight(const float* w_oihw, int cout, int cin_total, int ksi
                                  static_cast<cudaStream_t>(stream));
 }
 
-int cddpm_conv_igemm(int num_src, const void* const* src, const int* src_c, const int* src_taps, int B, int H,
-                     int W, int cout, const void* wpacked, const float* bias, const void* residual, void* out,
-                     int out_f32, int fmt, void* stream) {
+static int conv_igemm_impl(int num_src, const void* const* src, const int* src_c, const int* src_taps, int B, int H,
+                           int W, int cout, const void* wpacked, const float* bias, const void* residual, void* out,
+                           int out_f32, int fmt, double* gn_stats, void* stream) {
   if (!src || !src_c || !src_taps || !wpacked || !out) return fail(kInvalidArgument, "conv_igemm: null pointer");
   if (num_src < 1 || num_src > kConvMaxSrc) return fail(kInvalidArgument, "conv_igemm: num_src must be 1..3");
   ConvDesc d;
@@ -63,7 +63,8 @@ int cddpm_conv_igemm(int num_src, const void* const* src, const int* src_c, cons
   d.out = out;
   d.out_is_f32 = out_f32;
   d.ab_format = fmt;
-  {
+  d.gn_stats = gn_stats;
+  if (gn_stats == nullptr) {
     // measurement aid (tools/bench_conv.py): CDDPM_CONV_BENCH_STATS=1 makes the epilogue also emit its GroupNorm
     // (sum, sumsq) partials, into a scratch table, the way every convolution planned by the UNet engine does
     static const bool bench_stats = [] {
@@ -82,9 +83,27 @@ int cddpm_conv_igemm(int num_src, const void* const* src, const int* src_c, cons
     CDDPM_TRY(build_conv2(d, &holder));
     return launch_conv2(holder, static_cast<cudaStream_t>(stream));
   }
+  if (gn_stats != nullptr)
+    return fail(kUnsupported, "conv_igemm_stats: this geometry runs on the first-generation kernel, whose statistics "
+                              "are per-box partial rows (planned by the engine), not the [B][cout/4][2] table");
   ConvIgemmParams p;
   CDDPM_TRY(build_conv_params(d, &p));
   return launch_conv_igemm(p, static_cast<cudaStream_t>(stream));
+}
+
+int cddpm_conv_igemm(int num_src, const void* const* src, const int* src_c, const int* src_taps, int B, int H,
+                     int W, int cout, const void* wpacked, const float* bias, const void* residual, void* out,
+                     int out_f32, int fmt, void* stream) {
+  return conv_igemm_impl(num_src, src, src_c, src_taps, B, H, W, cout, wpacked, bias, residual, out, out_f32, fmt,
+                         nullptr, stream);
+}
+
+int cddpm_conv_igemm_stats(int num_src, const void* const* src, const int* src_c, const int* src_taps, int B, int H,
+                           int W, int cout, const void* wpacked, const float* bias, const void* residual, void* out,
+                           int fmt, double* gn_stats, void* stream) {
+  if (!gn_stats) return fail(kInvalidArgument, "conv_igemm_stats: gn_stats is required");
+  return conv_igemm_impl(num_src, src, src_c, src_taps, B, H, W, cout, wpacked, bias, residual, out, 0, fmt, gn_stats,
+                         stream);
 }
 
 int cddpm_pack_conv_weight_t(const float* w_oihw, int cout, int cin_total, int ksize, int cin_off, int c_s,

@@ -61,22 +61,34 @@ constexpr int kTmemCols = 512;            // 2 stages x (up to) 2 M tiles x 128 
 
 // Geometry for kMT M tiles (each 8 pixels wide x 16 high) side by side per CTA: 2 where the image width is a multiple
 // of 16, 1 for the 24 x 24 level (rows past the image bottom are computed on zero padding and masked on the way out).
-template <int kMT>
+//
+// kIL (image-interleaved tiles, kMT = 1 only; the 24 x 24 level): an M tile is 8 image rows of TWO consecutive images,
+// 8 pixels wide - its 16 row groups alternate between the images (group 2 j = row j of image 2 n, group 2 j + 1 = row j
+// of image 2 n + 1).  One TMA box over the tensor seen as {C, W, B, H} (image index before the row index) lands in
+// shared memory in exactly that order, so the group stride stays the halo row pitch and tap (dy, dx) still is a start
+// address: (2 dy x halo width + dx) rows.  A 24-row image then is three full tiles instead of one full and one
+// half-empty 16-row tile: 4.5 instead of 6 M tiles per image (144 instead of 192 work items at B = 32: two rounds on
+// 74 CTA pairs instead of three).
+template <int kMT, bool kIL = false>
 struct Geo {
   static constexpr int kTileW = 8 * kMT;                           // macro tile (output pixels) of one CTA
   static constexpr int kHaloW = kTileW + 2;
   static constexpr int kHaloPitch = kHaloW * kRowBytes;            // bytes between the 8-pixel row groups of an M tile
-  static constexpr int kABytes = kHaloW * kHaloH * kRowBytes;      // one staged halo tile (41472 B for kMT = 2)
+  static constexpr int kImgs = kIL ? 2 : 1;                        // images whose rows alternate inside a tile
+  static constexpr int kTileRows = kTileH / kImgs;                 // image rows of a tile
+  static constexpr int kABytes = kHaloW * (kTileRows + 2) * kImgs * kRowBytes;  // one staged halo tile (41472 B for kMT = 2)
   static constexpr int kASlotBytes = (kABytes + 1023) & ~1023;     // slots stay 1 KB aligned (swizzle atom)
   static constexpr int kEpiWarps = 4 * kMT;
-  static constexpr int kStatBytes = 2 * kEpiWarps * kStatW2 * 4;
+  static constexpr int kStatW = kStatW2 * kImgs;                   // per warp: (images x) 4 chunks x 16 values
+  static constexpr int kStatBytes = 2 * kEpiWarps * kStatW * 4;
   static constexpr int kCoefBytes = 2 * kNTile * 4;               // fused GroupNorm finish: A[128], B[128]
   static constexpr int kSmemBytes = kStagesA * kASlotBytes + kStagesB * kBSlotBytes + 256 + kStatBytes + kCoefBytes + 1024;
 };
 
 constexpr int kMaxChunks = 48;  // 64-channel chunks of one work item over all sources (K <= 3072 per source set)
 struct Conv2Params {
-  CUtensorMap tmap_a[kConvMaxSrc];  // {C, W, H, B}; box {64, 18, 18, 1} (3x3 sources) or {64, 16, 16, 1} (1x1 sources)
+  CUtensorMap tmap_a[kConvMaxSrc];  // {C, W, H, B}; box {64, 18, 18, 1} (3x3 sources) or {64, 16, 16, 1} (1x1 sources);
+                                    // image-interleaved tiles: {C, W, B, H}; box {64, 10, 2, 10} or {64, 8, 2, 8}
   CUtensorMap tmap_b;               // {Ktot, Cout}; box {64, 64}
   int num_src;
   int src_c[kConvMaxSrc];
@@ -90,7 +102,8 @@ struct Conv2Params {
   uint8_t chunk_ch[kMaxChunks];
   int box1;  // 1x1 sources stage the bare 16-row tile (no halo)
   int B, H, W, Cout;
-  int tiles_w, tiles_h;  // macro tiles per image
+  int tiles_w, tiles_h;  // macro tiles per image (per image PAIR with interleaved tiles)
+  int il;                // image-interleaved tiles (kernel template argument kIL)
   int num_m_tiles, num_n_tiles;
   int mt;  // M tiles per CTA (kernel template argument)
   int ab_format, relu;
@@ -149,6 +162,11 @@ __device__ __forceinline__ void quad_exchange(uint4& a, uint4& b, bool hi, int m
 
 // Per 4-channel bucket: sum and sum of squares of this pixel's 32 channels, then a butterfly over the warp's 32 pixels
 // (16 shuffles leave value (lane >> 1) & 15 in every lane); lanes write the warp's 16 totals of chunk c.
+//
+// kIL: lanes 8-15 and 24-31 of a warp hold pixels of the SECOND image of the tile's pair, so the butterfly runs over
+// lane bits 4, 2, 1, 0 only (16 lanes per image, 16 values -> one finished value per lane, index (lane >> 4) * 8 +
+// (lane & 7)) and lane bit 3 selects the image's 64-value block of stat_dst.
+template <bool kIL = false>
 __device__ __forceinline__ void emit_stats(const float (&f)[32], bool in_img, int lane, float* stat_dst) {
   float v16[16];
 #pragma unroll
@@ -164,7 +182,7 @@ __device__ __forceinline__ void emit_stats(const float (&f)[32], bool in_img, in
   }
 #pragma unroll
   for (int w = 8; w >= 1; w >>= 1) {
-    const int msk = w * 2;
+    const int msk = kIL ? (w == 8 ? 16 : w) : w * 2;
     const bool hi = (lane & msk) != 0;
 #pragma unroll
     for (int k = 0; k < w; ++k) {
@@ -173,15 +191,23 @@ __device__ __forceinline__ void emit_stats(const float (&f)[32], bool in_img, in
       v16[k] = keep + __shfl_xor_sync(0xffffffffu, send, msk);
     }
   }
-  const float tot = v16[0] + __shfl_xor_sync(0xffffffffu, v16[0], 1);
-  if ((lane & 1) == 0) stat_dst[lane >> 1] = tot;
+  if constexpr (kIL) {
+    stat_dst[((lane >> 3) & 1) * kStatW2 + ((lane >> 4) << 3) + (lane & 7)] = v16[0];
+  } else {
+    const float tot = v16[0] + __shfl_xor_sync(0xffffffffu, v16[0], 1);
+    if ((lane & 1) == 0) stat_dst[lane >> 1] = tot;
+  }
 }
 
 // kFuse: the experimental GroupNorm finish inside the epilogue (ConvDesc::gn_gamma) is its own instantiation, so the
 // default kernel does not carry its registers.
-template <int kMT, bool kFuse = false>
+template <int kMT, bool kFuse = false, bool kIL = false>
 __global__ void __launch_bounds__(kThreads2, 1) conv_igemm2_kernel(const __grid_constant__ Conv2Params p) {
-  using G = Geo<kMT>;
+  static_assert(!kIL || (kMT == 1 && !kFuse), "image-interleaved tiles: one M tile per CTA, no fused GroupNorm finish");
+  using G = Geo<kMT, kIL>;
+  constexpr int kTileRows = G::kTileRows;
+  constexpr int kRowStep = G::kImgs * G::kHaloW * (kRowBytes / 16);  // descriptor units between image rows of the halo tile
+  constexpr int kStatW = G::kStatW;
   constexpr int kMTiles = kMT;
   constexpr int kTileW = G::kTileW;
   constexpr int kHaloW = G::kHaloW;
@@ -303,12 +329,17 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_igemm2_kernel(const __grid_
           } else {
             mbar_arrive_cluster(&full_a[sa], 0);
           }
+          // coordinates in the order of the tensor map's dimensions: {C, W, H, B}, interleaved tiles {C, W, B, H}
+          // (there `n` counts image PAIRS; an image index past the batch is zero-filled like any halo)
+          const int cy = ty * kTileRows - halo;
+          const int c2 = kIL ? 2 * n : cy;
+          const int c3 = kIL ? cy : n;
           if (hint) {
             tma_load_4d_pair_hint(a_ring + sa * kASlotBytes, &p.tmap_a[s], &full_a[sa], ch * kConvBlockK,
-                                  tx * kTileW - halo, ty * kTileH - halo, n, pol);
+                                  tx * kTileW - halo, c2, c3, pol);
           } else {
             tma_load_4d_pair(a_ring + sa * kASlotBytes, &p.tmap_a[s], &full_a[sa], ch * kConvBlockK,
-                             tx * kTileW - halo, ty * kTileH - halo, n);
+                             tx * kTileW - halo, c2, c3);
           }
           if (++sa == kStagesA) {
             sa = 0;
@@ -354,7 +385,7 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_igemm2_kernel(const __grid_
               const uint64_t bd = umma_desc_k128(b_ring_u + sb * kBSlotBytes);
               if (c3) {
                 // kernel row `row`: taps (row, 0..2) read the halo tile from pixel (row, dx + 8 m)
-                const uint64_t ad = a_desc + static_cast<uint64_t>(row * kHaloW * (kRowBytes / 16));
+                const uint64_t ad = a_desc + static_cast<uint64_t>(row * kRowStep);
 #pragma unroll
                 for (int dx = 0; dx < 3; ++dx) {
 #pragma unroll
@@ -369,7 +400,7 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_igemm2_kernel(const __grid_
                 }
               } else {
                 // 1x1 source: the centre of the halo tile, or the bare tile from its first pixel
-                const uint64_t ad = a_desc + static_cast<uint64_t>(bare ? 0 : (kHaloW + 1) * (kRowBytes / 16));
+                const uint64_t ad = a_desc + static_cast<uint64_t>(bare ? 0 : kRowStep + kRowBytes / 16);
 #pragma unroll
                 for (int m = 0; m < kMTiles; ++m) {
 #pragma unroll
@@ -418,9 +449,12 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_igemm2_kernel(const __grid_
       const int ty = r / p.tiles_w;
       const int tx = r - ty * p.tiles_w;
       const int x = tx * kTileW + m * 8 + (row & 7);
-      const int y = ty * kTileH + (row >> 3);
-      const size_t off0 = ((static_cast<size_t>(n) * p.H + y) * p.W + x) * p.Cout + n_idx * kNTile;
-      const bool in_img = valid && y < p.H;  // the bottom tile of a 24-row image hangs over its edge
+      // row group g = row >> 3: image row g of the tile, or (interleaved tiles) row g >> 1 of image 2 n + (g & 1)
+      const int y = kIL ? ty * kTileRows + (row >> 4) : ty * kTileH + (row >> 3);
+      const int img = kIL ? 2 * n + ((row >> 3) & 1) : n;
+      const size_t off0 = ((static_cast<size_t>(img) * p.H + y) * p.W + x) * p.Cout + n_idx * kNTile;
+      // the bottom tile of a 24-row image hangs over its edge; the last pair of an odd batch has no second image
+      const bool in_img = valid && (kIL ? img < p.B : y < p.H);
       const bool has_res = p.residual != nullptr && in_img;
 
       if constexpr (kFuse) {
@@ -647,19 +681,22 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_igemm2_kernel(const __grid_
           }
         }
         if (p.gn_stats != nullptr)
-          emit_stats(f, in_img, lane, stat_sh + (acc * kEpiWarps + ew) * kStatW2 + c * 16);
+          emit_stats<kIL>(f, in_img, lane, stat_sh + (acc * kEpiWarps + ew) * kStatW + c * 16);
       }
       if (p.gn_stats != nullptr) {
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-        if (epi_tid < kStatW2 && valid) {
-          const int within = epi_tid & 15;
+        // one thread per (image of the tile, 32-channel chunk, value): 64 threads, 128 with interleaved tiles
+        const int stat_img = kIL ? 2 * n + (epi_tid >> 6) : n;
+        if (epi_tid < kStatW && valid && stat_img < p.B) {
+          const int e = epi_tid & (kStatW2 - 1);
+          const int within = e & 15;
           const int is_q = within >> 3;
-          const int bucket = (epi_tid >> 4) * 8 + (within & 7);
-          const float* sp = stat_sh + acc * kEpiWarps * kStatW2 + epi_tid;
+          const int bucket = (e >> 4) * 8 + (within & 7);
+          const float* sp = stat_sh + acc * kEpiWarps * kStatW + epi_tid;
           float t = 0.f;
 #pragma unroll
-          for (int w = 0; w < kEpiWarps; ++w) t += sp[w * kStatW2];
-          atomicAdd(&p.gn_stats[(static_cast<size_t>(n) * nb4 + n_idx * (kNTile >> 2) + bucket) * 2 + is_q],
+          for (int w = 0; w < kEpiWarps; ++w) t += sp[w * kStatW];
+          atomicAdd(&p.gn_stats[(static_cast<size_t>(stat_img) * nb4 + n_idx * (kNTile >> 2) + bucket) * 2 + is_q],
                     static_cast<double>(t));
         }
       }
@@ -709,9 +746,23 @@ int build_conv2(const ConvDesc& d, std::shared_ptr<void>* holder) {
   p.W = d.W;
   p.Cout = d.Cout;
   p.mt = (d.W % 16 == 0 && d.H % 16 == 0) ? 2 : 1;
+  {
+    // Image-interleaved tiles for the geometries whose height is not a multiple of 16 (the 24 x 24 level).  A/B switch
+    // for measurements: CDDPM_CONV_IL=0 keeps the 16-row tiles with a masked bottom half.
+    static const int il = [] {
+      const char* e = getenv("CDDPM_CONV_IL");
+      return (e != nullptr && e[0] == '0') ? 0 : 1;
+    }();
+    p.il = (il != 0 && p.mt == 1 && d.H % 16 != 0 && d.B >= 2 && d.gn_gamma == nullptr) ? 1 : 0;
+  }
   p.tiles_w = d.W / (8 * p.mt);
-  p.tiles_h = (d.H + kTileH - 1) / kTileH;
-  p.num_m_tiles = d.B * p.tiles_w * p.tiles_h;
+  if (p.il != 0) {
+    p.tiles_h = d.H / (kTileH / 2);
+    p.num_m_tiles = ((d.B + 1) / 2) * p.tiles_w * p.tiles_h;
+  } else {
+    p.tiles_h = (d.H + kTileH - 1) / kTileH;
+    p.num_m_tiles = d.B * p.tiles_w * p.tiles_h;
+  }
   p.num_n_tiles = d.Cout / kNTile;
   p.ab_format = d.ab_format;
   p.relu = d.relu;
@@ -752,11 +803,21 @@ int build_conv2(const ConvDesc& d, std::shared_ptr<void>* holder) {
     p.src_koff[s] = ktot;
     const bool bare = interleave && d.src_taps[s] == 1;
     const uint64_t C = static_cast<uint64_t>(d.src_c[s]);
-    const uint64_t dims[4] = {C, static_cast<uint64_t>(d.W), static_cast<uint64_t>(d.H), static_cast<uint64_t>(d.B)};
-    const uint64_t strides[3] = {C * 2, C * 2 * d.W, C * 2 * d.W * d.H};
-    const uint32_t box[4] = {static_cast<uint32_t>(kConvBlockK), static_cast<uint32_t>(8 * p.mt + (bare ? 0 : 2)),
-                             static_cast<uint32_t>(bare ? kTileH : kHaloH), 1u};
-    CDDPM_TRY(encode_tmap_16bit(&p.tmap_a[s], d.src[s], 4, dims, strides, box));
+    if (p.il != 0) {
+      // the tensor as {C, W, B, H}: a box of two images x (8 + halo) rows is written image-fastest, i.e. with the rows
+      // of the two images alternating - the order the interleaved M tile reads them in
+      const uint64_t dims[4] = {C, static_cast<uint64_t>(d.W), static_cast<uint64_t>(d.B), static_cast<uint64_t>(d.H)};
+      const uint64_t strides[3] = {C * 2, C * 2 * d.W * d.H, C * 2 * d.W};
+      const uint32_t box[4] = {static_cast<uint32_t>(kConvBlockK), static_cast<uint32_t>(8 + (bare ? 0 : 2)), 2u,
+                               static_cast<uint32_t>(kTileH / 2 + (bare ? 0 : 2))};
+      CDDPM_TRY(encode_tmap_16bit(&p.tmap_a[s], d.src[s], 4, dims, strides, box));
+    } else {
+      const uint64_t dims[4] = {C, static_cast<uint64_t>(d.W), static_cast<uint64_t>(d.H), static_cast<uint64_t>(d.B)};
+      const uint64_t strides[3] = {C * 2, C * 2 * d.W, C * 2 * d.W * d.H};
+      const uint32_t box[4] = {static_cast<uint32_t>(kConvBlockK), static_cast<uint32_t>(8 * p.mt + (bare ? 0 : 2)),
+                               static_cast<uint32_t>(bare ? kTileH : kHaloH), 1u};
+      CDDPM_TRY(encode_tmap_16bit(&p.tmap_a[s], d.src[s], 4, dims, strides, box));
+    }
     ktot += d.src_taps[s] * d.src_c[s];
     (d.src_taps[s] == 9 ? n9 : n1) += d.src_c[s] / kConvBlockK;
   }
@@ -827,6 +888,8 @@ int launch_conv2(const std::shared_ptr<void>& holder, cudaStream_t stream) {
                                     Geo<1>::kSmemBytes));
     CDDPM_CUDA(cudaFuncSetAttribute(conv_igemm2_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     Geo<2>::kSmemBytes));
+    CDDPM_CUDA(cudaFuncSetAttribute(conv_igemm2_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    Geo<1, true>::kSmemBytes));
     attr_set = true;
   }
   const Conv2Launch* L = reinterpret_cast<const Conv2Launch*>(holder.get());
@@ -845,7 +908,7 @@ int launch_conv2(const std::shared_ptr<void>& holder, cudaStream_t stream) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * pairs);
   cfg.blockDim = dim3(kThreads2);
-  cfg.dynamicSmemBytes = L->p.mt == 2 ? Geo<2>::kSmemBytes : Geo<1>::kSmemBytes;
+  cfg.dynamicSmemBytes = L->p.mt == 2 ? Geo<2>::kSmemBytes : (L->p.il != 0 ? Geo<1, true>::kSmemBytes : Geo<1>::kSmemBytes);
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -866,6 +929,8 @@ int launch_conv2(const std::shared_ptr<void>& holder, cudaStream_t stream) {
     } else {
       CDDPM_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm2_kernel<2>, L->p));
     }
+  } else if (L->p.il != 0) {
+    CDDPM_CUDA(cudaLaunchKernelEx(&cfg, (conv_igemm2_kernel<1, false, true>), L->p));
   } else {
     if (fuse) {
       CDDPM_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm2_kernel<1, true>, L->p));

@@ -53,6 +53,14 @@ int cddpm_pack_conv_weight(const float* w_oihw, int cout, int cin_total, int ksi
 int cddpm_conv_igemm(int num_src, const void* const* src, const int* src_c, const int* src_taps, int B, int H,
                      int W, int cout, const void* wpacked, const float* bias, const void* residual, void* out,
                      int out_f32, int fmt, void* stream);
+/* The same convolution (16-bit output) whose epilogue also ADDS the GroupNorm partial sums of its fp32 result into
+ * gn_stats[B][cout/4][2] (float64: sum and sum of squares per image and 4-channel bucket; zeroed by the caller) - the
+ * statistics util.py:214-216 (GroupNorm32) needs for the normalisation that follows every ResBlock convolution
+ * (OpenAI_Unet.py:284-338), produced without a pass over the tensor.  Geometries of the macro-tile kernel only
+ * (H, W multiples of 8, src_c multiples of 64, cout multiple of 128); others return an error. */
+int cddpm_conv_igemm_stats(int num_src, const void* const* src, const int* src_c, const int* src_taps, int B, int H,
+                           int W, int cout, const void* wpacked, const float* bias, const void* residual, void* out,
+                           int fmt, double* gn_stats, void* stream);
 
 /* Backward of the convolutions (training step: DDPM_2D.py:114-138 -> loss.backward(), torch autograd of nn.Conv2d).
  * Data gradient = the forward kernel over the transposed / flipped panel built here:

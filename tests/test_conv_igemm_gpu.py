@@ -116,3 +116,54 @@ def test_conv_fp16_and_no_bias():
 def test_conv_many_tiles_persistent():
     # more tiles than SMs: every CTA loops, accumulator stages and smem ring wrap several times
     _run_case(8, 96, 96, [128], 3, 128, out_f32=True, seed=3)
+
+
+# Image-interleaved M tiles (conv_igemm2.cu, kIL): geometries whose height is not a multiple of 16 - the 24 x 24 level
+# of the UNet (OpenAI_Unet.py: input_blocks 8-11, middle_block, output_blocks 0-3) - pair the rows of two consecutive
+# images in one tile.  Odd batches (last pair has one image), every source mix the level sees, 8 x 8 and 40 x 40 images.
+IL_CASES = [
+    dict(B=2, H=24, W=24, cins=[256], ksize=3, cout=256),
+    dict(B=3, H=24, W=24, cins=[256], ksize=3, cout=256),
+    dict(B=5, H=24, W=24, cins=[256, 256], ksize=3, cout=256),
+    dict(B=4, H=24, W=24, cins=[256], ksize=3, cout=256, residual=True),
+    dict(B=3, H=24, W=24, cins=[256], ksize=3, cout=256, skip_c=[256, 256]),
+    dict(B=3, H=24, W=24, cins=[256], ksize=1, cout=768),
+    dict(B=33, H=24, W=24, cins=[256], ksize=3, cout=256),  # more work items than CTA pairs: rings and stages wrap
+    dict(B=4, H=8, W=8, cins=[64], ksize=3, cout=128),
+    dict(B=3, H=40, W=40, cins=[64], ksize=3, cout=128),
+    dict(B=2, H=24, W=48, cins=[128], ksize=3, cout=128),
+]
+
+
+@pytest.mark.parametrize("case", IL_CASES, ids=lambda c: "_".join(f"{k}{v}" for k, v in c.items()).replace(" ", ""))
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+def test_conv_interleaved_tiles(case, dtype):
+    _run_case(dtype=dtype, **case)
+
+
+@pytest.mark.parametrize("B,H,W,cin,cout", [(2, 24, 24, 256, 256), (3, 24, 24, 256, 256), (2, 48, 48, 128, 256),
+                                            (1, 96, 96, 128, 128), (5, 8, 8, 64, 128)])
+def test_conv_epilogue_groupnorm_statistics(B, H, W, cin, cout):
+    """(sum, sum of squares) per image and 4-channel bucket of the fp32 convolution result, emitted by the epilogue
+    (GroupNorm32 input statistics, util.py:214-216) - plain and image-interleaved tiles."""
+    from cddpm import ops
+
+    _setup()
+    dtype = torch.float16
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn(B, cin, H, W, device="cuda", generator=g)
+    w = torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / (cin * 9) ** 0.5
+    b = torch.randn(cout, device="cuda", generator=g)
+    # per-image offsets make a pixel attributed to the wrong image of a pair visible in the sums
+    x = x + torch.arange(B, device="cuda", dtype=torch.float32).view(B, 1, 1, 1) * 0.25
+    xq, wq = x.to(dtype).float(), w.to(dtype).float()
+    ref = F.conv2d(xq, wq, b, padding=1).double()
+    out, stats = ops.conv_igemm_stats([_nhwc16(x, dtype)], [9], ops.pack_conv_weight(wq, [cin], dtype), b)
+    torch.cuda.synchronize()
+    rb = ref.view(B, cout // 4, 4, H * W)
+    want = torch.stack([rb.sum(dim=(2, 3)), (rb * rb).sum(dim=(2, 3))], dim=-1)
+    scale = want.abs().amax(dim=(1,), keepdim=True).clamp_min(1.0)
+    err = ((stats - want).abs() / scale).max().item()
+    assert err < 2e-4, f"statistics off by {err:.3g} (relative to the largest bucket of each image)"
+    got = out.float().permute(0, 3, 1, 2)
+    assert (got - ref.float()).abs().max().item() <= 2.0 ** -11 * max(ref.abs().max().item(), 1.0) + 1e-4

@@ -24,8 +24,10 @@ def main():
     if "--sweep" in sys.argv:  # batch sweep of one class: the intercept of time vs batch is the per-launch fixed cost
         SHAPES = [(b, 96, 96, [128], 3, 128, False) for b in (2, 4, 8, 16, 32, 64)] + \
                  [(b, 48, 48, [256], 3, 256, False) for b in (8, 16, 32, 64, 128)]
+    if "--level24" in sys.argv:  # the 24 x 24 classes of a forward (CDDPM_CONV_IL=0/1: plain / image-interleaved tiles)
+        SHAPES = [(b, 24, 24, cins, 3, 256, False) for b in (32, 64, 150) for cins in ([256], [256, 256])]
     dt = torch.float16
-    tag = " ".join(f"{k}={os.environ[k]}" for k in ("CDDPM_CONV_PAIR", "CDDPM_CONV_V2", "CDDPM_CONV_DEBUG") if k in os.environ)
+    tag = " ".join(f"{k}={os.environ[k]}" for k in ("CDDPM_CONV_PAIR", "CDDPM_CONV_V2", "CDDPM_CONV_DEBUG", "CDDPM_CONV_IL") if k in os.environ)
     print("variant:", tag or "default", flush=True)
     once = "--once" in sys.argv  # one launch per shape (for ncu captures)
     for B, H, W, cins, k, cout, res in SHAPES:
