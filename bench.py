@@ -358,11 +358,11 @@ def run_ours(args):
     achieved = conv_flops_fwd / (conv_ms_fwd / 1e3) / 1e12
     enc_launches = 1 + 1 + 16 * 4 + 4 + 3 + 2  # stem, pool, (3 GEMM + im2col) x 16 blocks, 4 downsample GEMMs, 3 strided gathers, pool + fc
     launches_per_step = enc_launches + 2 + T0 * (eng.launches_per_forward + 2)
-    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of the 57 timed launches of one B=32 forward at HEAD (ncu --set
-    # full, profiles/r02_v1_ncu_conv.csv: 56 conv_igemm2 launches, 4.664 GB read + 0.608 GB written; + the FiLM GEMM,
-    # profiles/r02_v1_ncu_misc.csv: 24.3 MB) = 5.296 GB -> 92.9 MB per launch, like `achieved`.  Algorithmic bytes of the
-    # same launches (every operand read once, every result written once, 16-bit): 5.21 GB.
-    traffic = 92.9e6 * B / 32
+    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of the timed launches of one B=32 forward at HEAD (ncu --set
+    # full, profiles/r02_v4_ncu_conv.csv: 55 of the 56 conv_igemm2 launches, 4.462 GB read + 0.575 GB written =
+    # 91.6 MB per launch, like `achieved`; the FiLM GEMM, profiles/r02_v3_ncu_misc.csv, reads 24.3 MB).  Algorithmic
+    # bytes of the 57 launches (every operand read once, every result written once, 16-bit): 5.21 GB = 91.4 MB each.
+    traffic = 91.6e6 * B / 32
     roofline = {"bound": "tensor",
                 "kernel": "conv_igemm2_kernel / conv_igemm_kernel (tcgen05 implicit GEMM: every convolution and GEMM launch "
                           "of a UNet forward)",

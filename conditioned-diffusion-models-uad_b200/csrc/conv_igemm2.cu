@@ -54,7 +54,6 @@ constexpr int kRowBytes = 128;            // 64 channels x 16 bit
 constexpr int kBTapBytes = (kNTile / 2) * kRowBytes;    // 8192: this CTA's 64 weight rows of one tap
 constexpr int kTapsPerStage = 3;
 constexpr int kBSlotBytes = kTapsPerStage * kBTapBytes; // 24576
-constexpr int kStagesA = 3;
 constexpr int kStagesB = 4;
 constexpr int kStatW2 = 64;               // (128 / 32) chunks x 16 values per warp
 constexpr int kTmemCols = 512;            // 2 stages x (up to) 2 M tiles x 128 columns
@@ -68,16 +67,24 @@ constexpr int kTmemCols = 512;            // 2 stages x (up to) 2 M tiles x 128 
 // shared memory in exactly that order, so the group stride stays the halo row pitch and tap (dy, dx) still is a start
 // address: (2 dy x halo width + dx) rows.  A 24-row image then is three full tiles instead of one full and one
 // half-empty 16-row tile: 4.5 instead of 6 M tiles per image (144 instead of 192 work items at B = 32: two rounds on
-// 74 CTA pairs instead of three).
+// 74 CTA pairs instead of three).  With kMT = 2 a CTA owns two such tiles (consecutive in the tile list, each its own
+// box) and every weight stage serves both (CDDPM_CONV_IL=2; measured no faster than one tile per CTA, see build_conv2).
 template <int kMT, bool kIL = false>
 struct Geo {
-  static constexpr int kTileW = 8 * kMT;                           // macro tile (output pixels) of one CTA
+  static constexpr int kTileW = kIL ? 8 : 8 * kMT;                 // macro tile (output pixels) of one TMA box
   static constexpr int kHaloW = kTileW + 2;
   static constexpr int kHaloPitch = kHaloW * kRowBytes;            // bytes between the 8-pixel row groups of an M tile
   static constexpr int kImgs = kIL ? 2 : 1;                        // images whose rows alternate inside a tile
   static constexpr int kTileRows = kTileH / kImgs;                 // image rows of a tile
-  static constexpr int kABytes = kHaloW * (kTileRows + 2) * kImgs * kRowBytes;  // one staged halo tile (41472 B for kMT = 2)
-  static constexpr int kASlotBytes = (kABytes + 1023) & ~1023;     // slots stay 1 KB aligned (swizzle atom)
+  static constexpr int kBoxes = kIL ? kMT : 1;                     // TMA boxes per chunk (interleaved: one per M tile)
+  static constexpr int kBoxBytes = kHaloW * (kTileRows + 2) * kImgs * kRowBytes;  // one staged halo tile (41472 B for kMT = 2)
+  static constexpr int kBareBytes = kTileW * kTileH * kRowBytes;   // the same without halo (1x1 sources)
+  static constexpr int kBoxPitch = (kBoxBytes + 1023) & ~1023;     // boxes stay 1 KB aligned (swizzle atom)
+  static constexpr int kABytes = kBoxes * kBoxBytes;
+  static constexpr int kASlotBytes = kBoxes * kBoxPitch;
+  // descriptor units (16 B) between the M tiles of a CTA: 8 pixels of the shared halo tile, or the next box
+  static constexpr int kMStep = kIL ? kBoxPitch / 16 : 8 * (kRowBytes / 16);
+  static constexpr int kStagesA = (kIL && kMT == 2) ? 2 : 3;       // 2 x 51 KB + the weight ring fill the 227 KB
   static constexpr int kEpiWarps = 4 * kMT;
   static constexpr int kStatW = kStatW2 * kImgs;                   // per warp: (images x) 4 chunks x 16 values
   static constexpr int kStatBytes = 2 * kEpiWarps * kStatW * 4;
@@ -104,6 +111,7 @@ struct Conv2Params {
   int B, H, W, Cout;
   int tiles_w, tiles_h;  // macro tiles per image (per image PAIR with interleaved tiles)
   int il;                // image-interleaved tiles (kernel template argument kIL)
+  int num_il_tiles;      // interleaved M tiles of the launch (num_m_tiles counts CTA tiles of `mt` of them)
   int num_m_tiles, num_n_tiles;
   int mt;  // M tiles per CTA (kernel template argument)
   int ab_format, relu;
@@ -203,18 +211,17 @@ __device__ __forceinline__ void emit_stats(const float (&f)[32], bool in_img, in
 // default kernel does not carry its registers.
 template <int kMT, bool kFuse = false, bool kIL = false>
 __global__ void __launch_bounds__(kThreads2, 1) conv_igemm2_kernel(const __grid_constant__ Conv2Params p) {
-  static_assert(!kIL || (kMT == 1 && !kFuse), "image-interleaved tiles: one M tile per CTA, no fused GroupNorm finish");
+  static_assert(!kIL || !kFuse, "image-interleaved tiles: no fused GroupNorm finish");
   using G = Geo<kMT, kIL>;
   constexpr int kTileRows = G::kTileRows;
   constexpr int kRowStep = G::kImgs * G::kHaloW * (kRowBytes / 16);  // descriptor units between image rows of the halo tile
   constexpr int kStatW = G::kStatW;
   constexpr int kMTiles = kMT;
   constexpr int kTileW = G::kTileW;
-  constexpr int kHaloW = G::kHaloW;
   constexpr int kHaloPitch = G::kHaloPitch;
-  constexpr int kABytes = G::kABytes;
   constexpr int kASlotBytes = G::kASlotBytes;
   constexpr int kEpiWarps = G::kEpiWarps;
+  constexpr int kStagesA = G::kStagesA;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_ring = smem;
@@ -314,10 +321,16 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_igemm2_kernel(const __grid_
       for (int work = work_first; work < num_work; work += work_stride) {
         const int m_tile = 2 * (work / p.num_n_tiles) + static_cast<int>(cta_rank);
         // an odd trailing tile has no partner: its coordinates fall outside the batch and TMA fills zeros
-        const int n = m_tile / tiles_per_img;
-        const int r = m_tile - n * tiles_per_img;
-        const int ty = r / p.tiles_w;
-        const int tx = r - ty * p.tiles_w;
+        // (interleaved tiles: box b is tile kMT * m_tile + b of the list; `n` counts image PAIRS there)
+        int bn[G::kBoxes], by[G::kBoxes], bx[G::kBoxes];
+#pragma unroll
+        for (int b = 0; b < G::kBoxes; ++b) {
+          const int t = kIL ? m_tile * kMT + b : m_tile;
+          bn[b] = t / tiles_per_img;
+          const int r = t - bn[b] * tiles_per_img;
+          by[b] = r / p.tiles_w;
+          bx[b] = r - by[b] * p.tiles_w;
+        }
         for (int ci = 0; ci < p.num_chunks; ++ci) {
           const int s = p.chunk_src[ci], ch = p.chunk_ch[ci];
           // a 1x1 source needs no halo: its box is the bare tile (32 KB instead of 41.5 KB at kMT = 2)
@@ -325,21 +338,23 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_igemm2_kernel(const __grid_
           const int halo = bare ? 0 : 1;
           mbar_wait(&empty_a[sa], pa ^ 1);
           if (leader) {
-            mbar_arrive_expect_tx(&full_a[sa], bare ? 2 * kTileW * kTileH * kRowBytes : 2 * kABytes);
+            mbar_arrive_expect_tx(&full_a[sa], 2 * G::kBoxes * (bare ? G::kBareBytes : G::kBoxBytes));
           } else {
             mbar_arrive_cluster(&full_a[sa], 0);
           }
-          // coordinates in the order of the tensor map's dimensions: {C, W, H, B}, interleaved tiles {C, W, B, H}
-          // (there `n` counts image PAIRS; an image index past the batch is zero-filled like any halo)
-          const int cy = ty * kTileRows - halo;
-          const int c2 = kIL ? 2 * n : cy;
-          const int c3 = kIL ? cy : n;
-          if (hint) {
-            tma_load_4d_pair_hint(a_ring + sa * kASlotBytes, &p.tmap_a[s], &full_a[sa], ch * kConvBlockK,
-                                  tx * kTileW - halo, c2, c3, pol);
-          } else {
-            tma_load_4d_pair(a_ring + sa * kASlotBytes, &p.tmap_a[s], &full_a[sa], ch * kConvBlockK,
-                             tx * kTileW - halo, c2, c3);
+#pragma unroll
+          for (int b = 0; b < G::kBoxes; ++b) {
+            // coordinates in the order of the tensor map's dimensions: {C, W, H, B}, interleaved tiles {C, W, B, H}
+            // (an image index past the batch is zero-filled like any halo)
+            const int cy = by[b] * kTileRows - halo;
+            const int c2 = kIL ? 2 * bn[b] : cy;
+            const int c3 = kIL ? cy : bn[b];
+            uint8_t* dst = a_ring + sa * kASlotBytes + b * G::kBoxPitch;
+            if (hint) {
+              tma_load_4d_pair_hint(dst, &p.tmap_a[s], &full_a[sa], ch * kConvBlockK, bx[b] * kTileW - halo, c2, c3, pol);
+            } else {
+              tma_load_4d_pair(dst, &p.tmap_a[s], &full_a[sa], ch * kConvBlockK, bx[b] * kTileW - halo, c2, c3);
+            }
           }
           if (++sa == kStagesA) {
             sa = 0;
@@ -392,7 +407,7 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_igemm2_kernel(const __grid_
                   for (int m = 0; m < kMTiles; ++m) {
 #pragma unroll
                     for (int kk = 0; kk < kConvBlockK / 16; ++kk) {
-                      umma_f16_ss_pair(tmem_d + m * kNTile, ad + ((dx + m * 8) * (kRowBytes / 16) + kk * 2),
+                      umma_f16_ss_pair(tmem_d + m * kNTile, ad + (dx * (kRowBytes / 16) + m * G::kMStep + kk * 2),
                                        bd + (dx * (kBTapBytes / 16) + kk * 2), idesc,
                                        (dx == 0 && kk == 0) ? accum : 1u);
                     }
@@ -405,7 +420,7 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_igemm2_kernel(const __grid_
                 for (int m = 0; m < kMTiles; ++m) {
 #pragma unroll
                   for (int kk = 0; kk < kConvBlockK / 16; ++kk) {
-                    umma_f16_ss_pair(tmem_d + m * kNTile, ad + (m * 8 * (kRowBytes / 16) + kk * 2), bd + kk * 2, idesc,
+                    umma_f16_ss_pair(tmem_d + m * kNTile, ad + (m * G::kMStep + kk * 2), bd + kk * 2, idesc,
                                      kk == 0 ? accum : 1u);
                   }
                 }
@@ -441,14 +456,15 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_igemm2_kernel(const __grid_
     for (int work = work_first; work < num_work; work += work_stride, ++iter) {
       const int acc = iter & 1;
       const uint32_t acc_phase = (iter >> 1) & 1;
-      const int m_tile = 2 * (work / p.num_n_tiles) + static_cast<int>(cta_rank);
+      // the tile of this warpgroup: the CTA's macro tile, or (interleaved) its own entry of the tile list
+      const int m_tile = (2 * (work / p.num_n_tiles) + static_cast<int>(cta_rank)) * (kIL ? kMT : 1) + (kIL ? m : 0);
       const int n_idx = work % p.num_n_tiles;
-      const bool valid = m_tile < p.num_m_tiles;
+      const bool valid = m_tile < (kIL ? p.num_il_tiles : p.num_m_tiles);
       const int n = m_tile / tiles_per_img;
       const int r = m_tile - n * tiles_per_img;
       const int ty = r / p.tiles_w;
       const int tx = r - ty * p.tiles_w;
-      const int x = tx * kTileW + m * 8 + (row & 7);
+      const int x = tx * kTileW + (kIL ? 0 : m * 8) + (row & 7);
       // row group g = row >> 3: image row g of the tile, or (interleaved tiles) row g >> 1 of image 2 n + (g & 1)
       const int y = kIL ? ty * kTileRows + (row >> 4) : ty * kTileH + (row >> 3);
       const int img = kIL ? 2 * n + ((row >> 3) & 1) : n;
@@ -685,17 +701,19 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_igemm2_kernel(const __grid_
       }
       if (p.gn_stats != nullptr) {
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-        // one thread per (image of the tile, 32-channel chunk, value): 64 threads, 128 with interleaved tiles
-        const int stat_img = kIL ? 2 * n + (epi_tid >> 6) : n;
-        if (epi_tid < kStatW && valid && stat_img < p.B) {
-          const int e = epi_tid & (kStatW2 - 1);
+        // one thread per (32-channel chunk, value): 64 threads summing over all warps of the CTA (one image); with
+        // interleaved tiles every warpgroup sums its own four warps, one thread per (image of its tile, chunk, value)
+        const int st = kIL ? (epi_tid & 127) : epi_tid;
+        const int stat_img = kIL ? 2 * n + (st >> 6) : n;
+        if (st < kStatW && (kIL || epi_tid < kStatW2) && valid && stat_img < p.B) {
+          const int e = st & (kStatW2 - 1);
           const int within = e & 15;
           const int is_q = within >> 3;
           const int bucket = (e >> 4) * 8 + (within & 7);
-          const float* sp = stat_sh + acc * kEpiWarps * kStatW + epi_tid;
+          const float* sp = stat_sh + (acc * kEpiWarps + (kIL ? 4 * m : 0)) * kStatW + st;
           float t = 0.f;
 #pragma unroll
-          for (int w = 0; w < kEpiWarps; ++w) t += sp[w * kStatW];
+          for (int w = 0; w < (kIL ? 4 : kEpiWarps); ++w) t += sp[w * kStatW];
           atomicAdd(&p.gn_stats[(static_cast<size_t>(stat_img) * nb4 + n_idx * (kNTile >> 2) + bucket) * 2 + is_q],
                     static_cast<double>(t));
         }
@@ -749,17 +767,26 @@ int build_conv2(const ConvDesc& d, std::shared_ptr<void>* holder) {
   {
     // Image-interleaved tiles for the geometries whose height is not a multiple of 16 (the 24 x 24 level).  A/B switch
     // for measurements: CDDPM_CONV_IL=0 keeps the 16-row tiles with a masked bottom half.
+    // 1 (default) = one interleaved tile per CTA; 2 = two per CTA (each its own TMA box, every weight stage serving both)
+    // once the one-tile form needs a second round.  Measured (profiles/r02_c17_il2_conv.log): 2 is slower at B = 32 / 64
+    // (22.1 -> 22.8 us, 31.8 -> 34.3 us for 256->256) and 0.5-1.8 % faster at B = 150 - the one-tile rounds are not
+    // limited by the weight stream (6.1-6.6 us per round either way against 4.85 us of MMA time); kept as a switch.
     static const int il = [] {
       const char* e = getenv("CDDPM_CONV_IL");
-      return (e != nullptr && e[0] == '0') ? 0 : 1;
+      return (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
     }();
-    p.il = (il != 0 && p.mt == 1 && d.H % 16 != 0 && d.B >= 2 && d.gn_gamma == nullptr) ? 1 : 0;
+    p.il = (il != 0 && p.mt == 1 && d.H % 16 != 0 && d.gn_gamma == nullptr) ? 1 : 0;
+    if (p.il != 0) {
+      p.tiles_w = d.W / 8;
+      p.tiles_h = d.H / (kTileH / 2);
+      p.num_il_tiles = ((d.B + 1) / 2) * p.tiles_w * p.tiles_h;
+      const int items1 = ((p.num_il_tiles + 1) / 2) * (d.Cout / kNTile);
+      p.mt = (il == 2 && items1 > device_sm_count() / 2) ? 2 : 1;
+      p.num_m_tiles = (p.num_il_tiles + p.mt - 1) / p.mt;
+    }
   }
-  p.tiles_w = d.W / (8 * p.mt);
-  if (p.il != 0) {
-    p.tiles_h = d.H / (kTileH / 2);
-    p.num_m_tiles = ((d.B + 1) / 2) * p.tiles_w * p.tiles_h;
-  } else {
+  if (p.il == 0) {
+    p.tiles_w = d.W / (8 * p.mt);
     p.tiles_h = (d.H + kTileH - 1) / kTileH;
     p.num_m_tiles = d.B * p.tiles_w * p.tiles_h;
   }
@@ -890,6 +917,8 @@ int launch_conv2(const std::shared_ptr<void>& holder, cudaStream_t stream) {
                                     Geo<2>::kSmemBytes));
     CDDPM_CUDA(cudaFuncSetAttribute(conv_igemm2_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     Geo<1, true>::kSmemBytes));
+    CDDPM_CUDA(cudaFuncSetAttribute(conv_igemm2_kernel<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    Geo<2, true>::kSmemBytes));
     attr_set = true;
   }
   const Conv2Launch* L = reinterpret_cast<const Conv2Launch*>(holder.get());
@@ -908,7 +937,11 @@ int launch_conv2(const std::shared_ptr<void>& holder, cudaStream_t stream) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * pairs);
   cfg.blockDim = dim3(kThreads2);
-  cfg.dynamicSmemBytes = L->p.mt == 2 ? Geo<2>::kSmemBytes : (L->p.il != 0 ? Geo<1, true>::kSmemBytes : Geo<1>::kSmemBytes);
+  if (L->p.il != 0) {
+    cfg.dynamicSmemBytes = L->p.mt == 2 ? Geo<2, true>::kSmemBytes : Geo<1, true>::kSmemBytes;
+  } else {
+    cfg.dynamicSmemBytes = L->p.mt == 2 ? Geo<2>::kSmemBytes : Geo<1>::kSmemBytes;
+  }
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -923,14 +956,18 @@ int launch_conv2(const std::shared_ptr<void>& holder, cudaStream_t stream) {
     cfg.numAttrs = 2;
   }
   const bool fuse = L->p.gn_gamma != nullptr;
-  if (L->p.mt == 2) {
+  if (L->p.il != 0) {
+    if (L->p.mt == 2) {
+      CDDPM_CUDA(cudaLaunchKernelEx(&cfg, (conv_igemm2_kernel<2, false, true>), L->p));
+    } else {
+      CDDPM_CUDA(cudaLaunchKernelEx(&cfg, (conv_igemm2_kernel<1, false, true>), L->p));
+    }
+  } else if (L->p.mt == 2) {
     if (fuse) {
       CDDPM_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm2_kernel<2, true>, L->p));
     } else {
       CDDPM_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm2_kernel<2>, L->p));
     }
-  } else if (L->p.il != 0) {
-    CDDPM_CUDA(cudaLaunchKernelEx(&cfg, (conv_igemm2_kernel<1, false, true>), L->p));
   } else {
     if (fuse) {
       CDDPM_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm2_kernel<1, true>, L->p));

@@ -1007,7 +1007,11 @@ int launch_gn_apply(const GnApplyArgs& a, cudaStream_t stream) {
   // Measured (profiles/r02_c5_ab.log): B = 1 forward 1.247 -> 1.161 ms; at B = 32 finer blocks only add coefficient
   // prologues (5.385 -> 5.424 ms), so large batches keep the round-1 rule.
   d.Pout = (static_cast<long long>(HWo / 256) * a.B >= 592) ? 256 : 64;
-  while (d.Pout > 16 && static_cast<long long>((HWo + d.Pout - 1) / d.Pout) * a.B < 256) d.Pout >>= 1;
+  static const int min_blocks = [] {
+    const char* e = getenv("CDDPM_GN_MIN_BLOCKS");  // A/B switch for measurements
+    return (e != nullptr && atoi(e) > 0) ? atoi(e) : 256;
+  }();
+  while (d.Pout > 16 && static_cast<long long>((HWo + d.Pout - 1) / d.Pout) * a.B < min_blocks) d.Pout >>= 1;
   const int nvec = C / 8;
   const int threads = (256 / nvec) * nvec;
   dim3 grid((HWo + d.Pout - 1) / d.Pout, a.B);

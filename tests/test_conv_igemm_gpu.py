@@ -128,7 +128,11 @@ IL_CASES = [
     dict(B=4, H=24, W=24, cins=[256], ksize=3, cout=256, residual=True),
     dict(B=3, H=24, W=24, cins=[256], ksize=3, cout=256, skip_c=[256, 256]),
     dict(B=3, H=24, W=24, cins=[256], ksize=1, cout=768),
-    dict(B=33, H=24, W=24, cins=[256], ksize=3, cout=256),  # more work items than CTA pairs: rings and stages wrap
+    # more work items than CTA pairs: two interleaved tiles per CTA (each its own TMA box), odd tile count (153)
+    dict(B=33, H=24, W=24, cins=[256], ksize=3, cout=256),
+    dict(B=33, H=24, W=24, cins=[128], ksize=3, cout=128, skip_c=[256, 128]),
+    dict(B=34, H=24, W=24, cins=[128, 128], ksize=3, cout=256, residual=True),
+    dict(B=70, H=24, W=24, cins=[64], ksize=3, cout=128),  # ... and several rounds of them
     dict(B=4, H=8, W=8, cins=[64], ksize=3, cout=128),
     dict(B=3, H=40, W=40, cins=[64], ksize=3, cout=128),
     dict(B=2, H=24, W=48, cins=[128], ksize=3, cout=128),
@@ -141,7 +145,8 @@ def test_conv_interleaved_tiles(case, dtype):
     _run_case(dtype=dtype, **case)
 
 
-@pytest.mark.parametrize("B,H,W,cin,cout", [(2, 24, 24, 256, 256), (3, 24, 24, 256, 256), (2, 48, 48, 128, 256),
+@pytest.mark.parametrize("B,H,W,cin,cout", [(2, 24, 24, 256, 256), (3, 24, 24, 256, 256), (33, 24, 24, 128, 256),
+                                            (2, 48, 48, 128, 256),
                                             (1, 96, 96, 128, 128), (5, 8, 8, 64, 128)])
 def test_conv_epilogue_groupnorm_statistics(B, H, W, cin, cout):
     """(sum, sum of squares) per image and 4-channel bucket of the fp32 convolution result, emitted by the epilogue
