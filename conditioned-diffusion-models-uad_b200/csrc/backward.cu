@@ -807,7 +807,7 @@ constexpr int kLwO = 32;
 constexpr int kLwBMax = 64;
 __global__ void __launch_bounds__(128) linear_bwd_weight_kernel(const float* __restrict__ dy, int dy_stride,
                                                                 const float* __restrict__ x, int x_stride, int act_x,
-                                                                float* __restrict__ dw, float* __restrict__ db, int B,
+                                                                float* dw, float* db, int B,
                                                                 int I, int O, const int64_t* __restrict__ tile_w_off,
                                                                 const int64_t* __restrict__ tile_b_off) {
   __shared__ __align__(16) float sdy[kLwBMax][kLwO];

@@ -581,8 +581,7 @@ int launch_conv_igemm(const ConvIgemmParams& p, cudaStream_t stream, int max_cta
   // CTA pairs: a cluster of two CTAs per work item (two adjacent M tiles x one N tile), persistent over SM pairs
   const int num_work = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
   const int pairs = num_work < sms / 2 ? num_work : sms / 2;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * pairs);
   cfg.blockDim = dim3(kConvThreads);
   cfg.dynamicSmemBytes = smem;

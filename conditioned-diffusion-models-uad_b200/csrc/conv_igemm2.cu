@@ -80,7 +80,6 @@ struct Geo {
   static constexpr int kBoxBytes = kHaloW * (kTileRows + 2) * kImgs * kRowBytes;  // one staged halo tile (41472 B for kMT = 2)
   static constexpr int kBareBytes = kTileW * kTileH * kRowBytes;   // the same without halo (1x1 sources)
   static constexpr int kBoxPitch = (kBoxBytes + 1023) & ~1023;     // boxes stay 1 KB aligned (swizzle atom)
-  static constexpr int kABytes = kBoxes * kBoxBytes;
   static constexpr int kASlotBytes = kBoxes * kBoxPitch;
   // descriptor units (16 B) between the M tiles of a CTA: 8 pixels of the shared halo tile, or the next box
   static constexpr int kMStep = kIL ? kBoxPitch / 16 : 8 * (kRowBytes / 16);
