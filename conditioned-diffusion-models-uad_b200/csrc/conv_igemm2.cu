@@ -700,19 +700,20 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_igemm2_kernel(const __grid_
       }
       if (p.gn_stats != nullptr) {
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-        // one thread per (32-channel chunk, value): 64 threads summing over all warps of the CTA (one image); with
-        // interleaved tiles every warpgroup sums its own four warps, one thread per (image of its tile, chunk, value)
-        const int st = kIL ? (epi_tid & 127) : epi_tid;
+        // every warpgroup sums the four warps of ITS M tile, one thread per (image of the tile, 32-channel chunk,
+        // value): a tile's partial sums then do not depend on how many tiles the CTA holds, so a small batch planned
+        // with one tile per CTA reproduces the statistics of a large one planned with two
+        const int st = epi_tid & 127;
         const int stat_img = kIL ? 2 * n + (st >> 6) : n;
-        if (st < kStatW && (kIL || epi_tid < kStatW2) && valid && stat_img < p.B) {
+        if (st < kStatW && valid && stat_img < p.B) {
           const int e = st & (kStatW2 - 1);
           const int within = e & 15;
           const int is_q = within >> 3;
           const int bucket = (e >> 4) * 8 + (within & 7);
-          const float* sp = stat_sh + (acc * kEpiWarps + (kIL ? 4 * m : 0)) * kStatW + st;
+          const float* sp = stat_sh + (acc * kEpiWarps + 4 * m) * kStatW + st;
           float t = 0.f;
 #pragma unroll
-          for (int w = 0; w < (kIL ? 4 : kEpiWarps); ++w) t += sp[w * kStatW];
+          for (int w = 0; w < 4; ++w) t += sp[w * kStatW];
           atomicAdd(&p.gn_stats[(static_cast<size_t>(stat_img) * nb4 + n_idx * (kNTile >> 2) + bucket) * 2 + is_q],
                     static_cast<double>(t));
         }
@@ -763,6 +764,19 @@ int build_conv2(const ConvDesc& d, std::shared_ptr<void>* holder) {
   p.W = d.W;
   p.Cout = d.Cout;
   p.mt = (d.W % 16 == 0 && d.H % 16 == 0) ? 2 : 1;
+  {
+    // Small batches: when the 16 x 16 macro tiles leave more than half of the CTA pairs without a work item (B = 1:
+    // 18 items at 96 x 96, 10 at 48 x 48), plan 8 x 16 tiles instead - twice the CTAs, half the MMA chain each.
+    // CDDPM_CONV_SPLIT_SMALL=0 keeps the macro tiles.
+    static const int split_small = [] {
+      const char* e = getenv("CDDPM_CONV_SPLIT_SMALL");
+      return (e != nullptr && e[0] == '0') ? 0 : 1;
+    }();
+    const int tiles2 = d.B * (d.W / 16) * ((d.H + kTileH - 1) / kTileH);
+    if (split_small != 0 && p.mt == 2 && d.gn_gamma == nullptr &&
+        ((tiles2 + 1) / 2) * (d.Cout / kNTile) <= device_sm_count() / 4)
+      p.mt = 1;
+  }
   {
     // Image-interleaved tiles for the geometries whose height is not a multiple of 16 (the 24 x 24 level).  A/B switch
     // for measurements: CDDPM_CONV_IL=0 keeps the 16-row tiles with a masked bottom half.

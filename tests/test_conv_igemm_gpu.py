@@ -116,6 +116,9 @@ def test_conv_fp16_and_no_bias():
 def test_conv_many_tiles_persistent():
     # more tiles than SMs: every CTA loops, accumulator stages and smem ring wrap several times
     _run_case(8, 96, 96, [128], 3, 128, out_f32=True, seed=3)
+    # ... and the macro-tile kernel with 16-bit output (small batches are planned with 8 x 16 tiles instead)
+    _run_case(8, 96, 96, [128], 3, 128, seed=3)
+    _run_case(8, 48, 48, [256], 3, 256, skip_c=[256, 128], dtype=torch.float16, seed=4)
 
 
 # Image-interleaved M tiles (conv_igemm2.cu, kIL): geometries whose height is not a multiple of 16 - the 24 x 24 level
@@ -146,7 +149,7 @@ def test_conv_interleaved_tiles(case, dtype):
 
 
 @pytest.mark.parametrize("B,H,W,cin,cout", [(2, 24, 24, 256, 256), (3, 24, 24, 256, 256), (33, 24, 24, 128, 256),
-                                            (2, 48, 48, 128, 256),
+                                            (2, 48, 48, 128, 256), (8, 96, 96, 128, 128),
                                             (1, 96, 96, 128, 128), (5, 8, 8, 64, 128)])
 def test_conv_epilogue_groupnorm_statistics(B, H, W, cin, cout):
     """(sum, sum of squares) per image and 4-channel bucket of the fp32 convolution result, emitted by the epilogue
