@@ -18,6 +18,7 @@
 // (cta_group::2, shared X tile) is the next step.
 //
 // Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue.
+#include <stdlib.h>
 #include <string.h>
 
 #include <memory>
@@ -35,7 +36,14 @@ constexpr int kWgTileW = 16;
 constexpr int kWgTileH = 8;
 constexpr int kWgABytes = kWgTileW * kWgTileH * 128;          // 16384: one 64-channel chunk of the dY tile
 constexpr int kWgBBytes3 = (kWgTileW + 2) * kWgTileH * 128;   // 18432: one 64-channel chunk of a halo row band
-constexpr int kWgStageBytes = 2 * kWgABytes + 2 * kWgBBytes3; // 69632
+// Image-interleaved tiles (widths that are not a multiple of 16, i.e. the 24 x 24 level): 8 pixels x 8 rows of TWO
+// consecutive images through one TMA box over the tensor seen as {C, W, B, H} - a row of the staged tile is 8 pixels
+// of image 2 n followed by 8 pixels of image 2 n + 1, the 16 contraction rows of one MMA.  The dY tile has the bytes
+// and the layout of the plain 16-pixel tile; the halo band is 2 x (8 + 2) pixels wide, so the two 8-row groups of an
+// MMA's B operand are 10 rows apart (SBO 1280).  A 24-pixel row then is three full tiles of pixels per image pair
+// instead of two tiles per image, the second half empty: 9 instead of 12 tiles per pair of 24 x 24 images.
+constexpr int kWgBBytes3IL = 2 * (8 + 2) * kWgTileH * 128;    // 20480
+constexpr int kWgStageBytes = 2 * kWgABytes + 2 * kWgBBytes3IL; // 73728
 constexpr int kWgSmem = kWgStages * kWgStageBytes + 256 + 1024;
 constexpr int kWgMaxUnits = 48;
 constexpr int kWgTmemCols = 512;
@@ -45,6 +53,7 @@ struct WgradParams {
   CUtensorMap tmap_x[kConvMaxSrc];  // {C_s, W, H, B}; box {64, 18, 8, 1} (3x3) or {64, 16, 8, 1} (1x1)
   int B, H, W, Cout, ktot;
   int tiles_w, tiles_h, num_tiles;
+  int il;  // image-interleaved tiles: maps are {C, W, B, H}, tiles count per image PAIR
   int units_per_co, splits;
   int ab_format;
   float* dw;
@@ -54,11 +63,11 @@ struct WgradParams {
 
 // MN-major operand: rows of 128 bytes (64 channels) per K index, 8-row groups of 1024 bytes (SBO), 64-channel chunks
 // `lbo` bytes apart.
-__device__ __forceinline__ uint64_t umma_desc_mn128(uint32_t smem_addr, uint32_t lbo_bytes) {
+__device__ __forceinline__ uint64_t umma_desc_mn128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes = 1024) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
   d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(2) << 61;
   return d;
@@ -120,7 +129,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
       if (lane == 0) {
         int st = 0;
         uint32_t ph = 0;
-        const uint32_t b_bytes = c3 ? kWgBBytes3 : kWgABytes;
+        const uint32_t b_bytes = c3 ? (p.il != 0 ? kWgBBytes3IL : kWgBBytes3) : kWgABytes;
+        const int tw = p.il != 0 ? 8 : kWgTileW;
         for (int t = t0; t < t1; ++t) {
           const int n = t / tiles_per_img;
           const int r = t - n * tiles_per_img;
@@ -130,12 +140,15 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
           mbar_arrive_expect_tx(&full[st], 2 * kWgABytes + 2 * b_bytes);
           uint8_t* a = ring + st * kWgStageBytes;
           uint8_t* b = a + 2 * kWgABytes;
-          tma_load_4d(a, &p.tmap_dy, &full[st], co_chunk * 128, tx * kWgTileW, ty * kWgTileH, n);
-          tma_load_4d(a + kWgABytes, &p.tmap_dy, &full[st], co_chunk * 128 + 64, tx * kWgTileW, ty * kWgTileH, n);
-          const int bx = c3 ? tx * kWgTileW - 1 : tx * kWgTileW;
+          const int bx = c3 ? tx * tw - 1 : tx * tw;
           const int by = c3 ? ty * kWgTileH + kdy - 1 : ty * kWgTileH;
-          tma_load_4d(b, &p.tmap_x[s], &full[st], ci_chunk * 128, bx, by, n);
-          tma_load_4d(b + b_bytes, &p.tmap_x[s], &full[st], ci_chunk * 128 + 64, bx, by, n);
+          // coordinates in the order of the maps' dimensions: {C, W, H, B}, interleaved {C, W, B, H} (n = image pair)
+          const int a2 = p.il != 0 ? 2 * n : ty * kWgTileH, a3 = p.il != 0 ? ty * kWgTileH : n;
+          const int b2 = p.il != 0 ? 2 * n : by, b3 = p.il != 0 ? by : n;
+          tma_load_4d(a, &p.tmap_dy, &full[st], co_chunk * 128, tx * tw, a2, a3);
+          tma_load_4d(a + kWgABytes, &p.tmap_dy, &full[st], co_chunk * 128 + 64, tx * tw, a2, a3);
+          tma_load_4d(b, &p.tmap_x[s], &full[st], ci_chunk * 128, bx, b2, b3);
+          tma_load_4d(b + b_bytes, &p.tmap_x[s], &full[st], ci_chunk * 128 + 64, bx, b2, b3);
           if (++st == kWgStages) {
             st = 0;
             ph ^= 1;
@@ -148,8 +161,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t ring_u = __shfl_sync(0xffffffffu, smem_u32(ring), 0);
       const bool elected = elect_one_sync();
-      const uint32_t b_lbo = c3 ? kWgBBytes3 : kWgABytes;
-      const uint32_t b_pitch = c3 ? (kWgTileW + 2) * 128 : kWgTileW * 128;
+      const uint32_t b_lbo = c3 ? (p.il != 0 ? kWgBBytes3IL : kWgBBytes3) : kWgABytes;
+      const uint32_t b_pitch = c3 ? (p.il != 0 ? 2 * (8 + 2) * 128 : (kWgTileW + 2) * 128) : kWgTileW * 128;
+      const uint32_t b_sbo = (c3 && p.il != 0) ? (8 + 2) * 128 : 1024;  // the second image's pixels follow the first's halo
       int st = 0;
       uint32_t ph = 0;
       for (int t = t0; t < t1; ++t) {
@@ -159,7 +173,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_kernel(const __grid_
           const uint32_t a_addr = ring_u + st * kWgStageBytes;
           const uint32_t b_addr = a_addr + 2 * kWgABytes;
           const uint64_t ad0 = umma_desc_mn128(a_addr, kWgABytes);
-          const uint64_t bd0 = umma_desc_mn128(b_addr, b_lbo);
+          const uint64_t bd0 = umma_desc_mn128(b_addr, b_lbo, b_sbo);
 #pragma unroll
           for (int y = 0; y < kWgTileH; ++y) {
             const uint64_t ad = ad0 + static_cast<uint64_t>(y * (kWgTileW * 128 / 16));
@@ -287,16 +301,38 @@ int build_wgrad(const WgradDesc& d, std::shared_ptr<void>* holder) {
   p.Cout = d.Cout;
   p.ab_format = d.ab_format;
   p.dw = d.dw;
-  p.tiles_w = (d.W + kWgTileW - 1) / kWgTileW;
-  p.tiles_h = d.H / kWgTileH;
-  p.num_tiles = d.B * p.tiles_w * p.tiles_h;
   {
-    const uint64_t C = static_cast<uint64_t>(d.Cout);
+    static const int il = [] {
+      const char* e = getenv("CDDPM_WGRAD_IL");  // A/B switch: 0 = 16-pixel tiles with a zero-filled overhang
+      return (e != nullptr && e[0] == '0') ? 0 : 1;
+    }();
+    p.il = (il != 0 && d.W % kWgTileW != 0) ? 1 : 0;
+  }
+  p.tiles_h = d.H / kWgTileH;
+  if (p.il != 0) {
+    p.tiles_w = d.W / 8;
+    p.num_tiles = ((d.B + 1) / 2) * p.tiles_w * p.tiles_h;
+  } else {
+    p.tiles_w = (d.W + kWgTileW - 1) / kWgTileW;
+    p.num_tiles = d.B * p.tiles_w * p.tiles_h;
+  }
+  // a tensor [B][H][W][C] as a tiled map: {C, W, H, B} with a box of `bw` pixels x 8 rows, or (interleaved tiles)
+  // {C, W, B, H} with a box of `bw` pixels x 2 images x 8 rows
+  const int il_flag = p.il;
+  auto encode = [il_flag, &d](CUtensorMap* map, const void* base, uint64_t C, uint32_t bw) {
+    if (il_flag != 0) {
+      const uint64_t dims[4] = {C, static_cast<uint64_t>(d.W), static_cast<uint64_t>(d.B), static_cast<uint64_t>(d.H)};
+      const uint64_t strides[3] = {C * 2, C * 2 * d.W * d.H, C * 2 * d.W};
+      const uint32_t box[4] = {64u, bw, 2u, static_cast<uint32_t>(kWgTileH)};
+      return encode_tmap_16bit(map, base, 4, dims, strides, box);
+    }
     const uint64_t dims[4] = {C, static_cast<uint64_t>(d.W), static_cast<uint64_t>(d.H), static_cast<uint64_t>(d.B)};
     const uint64_t strides[3] = {C * 2, C * 2 * d.W, C * 2 * d.W * d.H};
-    const uint32_t box[4] = {64u, static_cast<uint32_t>(kWgTileW), static_cast<uint32_t>(kWgTileH), 1u};
-    CDDPM_TRY(encode_tmap_16bit(&p.tmap_dy, d.dy, 4, dims, strides, box));
-  }
+    const uint32_t box[4] = {64u, bw, static_cast<uint32_t>(kWgTileH), 1u};
+    return encode_tmap_16bit(map, base, 4, dims, strides, box);
+  };
+  const uint32_t tile_w = p.il != 0 ? 8u : static_cast<uint32_t>(kWgTileW);
+  CDDPM_TRY(encode(&p.tmap_dy, d.dy, static_cast<uint64_t>(d.Cout), tile_w));
   int koff = 0, units = 0;
   for (int s = 0; s < d.num_src; ++s) {
     p.src_c[s] = d.src_c[s];
@@ -305,12 +341,8 @@ int build_wgrad(const WgradDesc& d, std::shared_ptr<void>* holder) {
     koff += d.src_taps[s] * d.src_c[s];
     if (d.src_skip[s]) continue;
     if (!d.src[s]) return fail(kInvalidArgument, "conv wgrad: null source");
-    const uint64_t C = static_cast<uint64_t>(d.src_c[s]);
-    const uint64_t dims[4] = {C, static_cast<uint64_t>(d.W), static_cast<uint64_t>(d.H), static_cast<uint64_t>(d.B)};
-    const uint64_t strides[3] = {C * 2, C * 2 * d.W, C * 2 * d.W * d.H};
-    const uint32_t box[4] = {64u, static_cast<uint32_t>(d.src_taps[s] == 9 ? kWgTileW + 2 : kWgTileW),
-                             static_cast<uint32_t>(kWgTileH), 1u};
-    CDDPM_TRY(encode_tmap_16bit(&p.tmap_x[s], d.src[s], 4, dims, strides, box));
+    CDDPM_TRY(encode(&p.tmap_x[s], d.src[s], static_cast<uint64_t>(d.src_c[s]),
+                     d.src_taps[s] == 9 ? tile_w + 2 : tile_w));
     for (int ci = 0; ci < d.src_c[s] / 128; ++ci)
       for (int dy = 0; dy < (d.src_taps[s] == 9 ? 3 : 1); ++dy) {
         if (units >= kWgMaxUnits) return fail(kUnsupported, "conv wgrad: too many work units");

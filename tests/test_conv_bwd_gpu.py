@@ -25,6 +25,10 @@ def _nhwc16(x, dtype):
     (2, 24, 24, [256], 1, 256),
     (1, 32, 32, [128, 128], 1, 256),
     (4, 96, 96, [128], 3, 128),
+    # widths that are not a multiple of 16 run on image-interleaved tiles (8 pixels of two consecutive images per row)
+    (5, 24, 24, [128, 128], 3, 128),
+    (2, 40, 40, [128], 3, 128),
+    (9, 24, 24, [128], 1, 128),
 ])
 def test_wgrad_matches_autograd(B, H, W, cins, ksize, cout):
     from cddpm import ops
