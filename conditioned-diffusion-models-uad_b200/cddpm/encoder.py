@@ -145,7 +145,10 @@ class ResNet(nn.Module):
             raise NotImplementedError("pyramid features are only used by SparK pre-training (out of scope)")
         if not x.is_cuda:
             raise CddpmError("encoder forward needs CUDA tensors (there is no CPU path)")
-        if self.training and torch.is_grad_enabled():
+        if self.training:
+            # train() mode means batch statistics, running-statistics updates and DropPath whether or not a tape is
+            # being recorded (nn.BatchNorm2d / timm DropPath in the reference, spark/resnet.py:13-46): under
+            # torch.no_grad() the same engine forward runs and its autograd node simply never sees a backward
             return self._train_forward(x)
         self._sync()
         x = x.float().contiguous()
